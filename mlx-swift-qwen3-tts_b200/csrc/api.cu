@@ -1,0 +1,804 @@
+// extern "C" entry points of libqwen3tts_b200.so (declared in include/qwen3tts_b200.h).
+#include <algorithm>
+#include <deque>
+#include <map>
+
+#include "codec.h"
+#include "engine.h"
+
+using namespace q3;
+
+namespace q3 {
+void init_talker_kernels();
+Handle::~Handle() {
+  talker.reset();
+  codec.reset();
+  if (ev_start) cudaEventDestroy(ev_start);
+  if (ev_stop) cudaEventDestroy(ev_stop);
+  if (h_pcm) cudaFreeHost(h_pcm);
+  if (h_codes) cudaFreeHost(h_codes);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+}  // namespace q3
+
+struct q3tts_handle : q3::Handle {};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <typename F>
+q3tts_status guarded(q3tts_handle* h, F&& f) {
+  if (!h) return Q3TTS_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> lk(h->mu);
+  try {
+    Q3_CUDA(cudaSetDevice(h->opt.device));
+    f();
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    h->last_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  } catch (const std::exception& e) {
+    h->last_error = e.what();
+    return Q3TTS_ERR_CUDA;
+  }
+}
+
+void require_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    fail(Q3TTS_ERR_NO_DEVICE, "no CUDA device visible (%s); libqwen3tts_b200 has no CPU path", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+  }
+  Q3_CHECK(device >= 0 && device < n, Q3TTS_ERR_NO_DEVICE, "CUDA device %d not present (%d visible)", device, n);
+  cudaDeviceProp p;
+  Q3_CUDA(cudaGetDeviceProperties(&p, device));
+  Q3_CHECK(p.major == 10, Q3TTS_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, p.major, p.minor);
+  Q3_CUDA(cudaSetDevice(device));
+}
+
+struct CallTimer {
+  q3tts_handle* h;
+  int64_t launches0;
+  int64_t replays0 = 0;
+  explicit CallTimer(q3tts_handle* hh) : h(hh) {
+    h->timing = q3tts_timing{};
+    launches0 = h->counter.n;
+    if (h->talker) { replays0 = h->talker->graph_replays; h->talker->last_prefill_ms = 0; }
+    cudaEventRecord(h->ev_start, h->stream);
+  }
+  void finish() {
+    cudaEventRecord(h->ev_stop, h->stream);
+    cudaEventSynchronize(h->ev_stop);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop);
+    h->timing.device_ms = ms;
+    h->timing.kernel_launches = h->counter.n - launches0;
+    if (h->talker) {
+      h->timing.graph_replays = h->talker->graph_replays - replays0;
+      h->timing.prefill_ms = h->talker->last_prefill_ms;
+      h->timing.weight_bytes_per_frame = (int64_t)h->talker->weight_bytes_per_frame();
+    }
+  }
+};
+
+bool frame_valid(const int32_t* f) { return f[0] >= 0 && f[0] < 2048; }  // Model/Qwen3Talker.swift:571-576
+
+// ---- talker drivers ------------------------------------------------------------------------------------------
+// Runs one admitted utterance in slot 0 to completion; returns raw frames.
+void run_single(q3tts_handle* h, const q3tts_request& req, std::vector<int32_t>& raw, int& n_raw) {
+  TalkerEngine& t = *h->talker;
+  n_raw = 0;
+  Admission a = t.admit(0, req);
+  if (a.too_short) return;
+  std::vector<SlotState> st;
+  const int limit = (req.forced_codes && req.n_forced_frames > 0) ? req.n_forced_frames : std::min(std::max(req.max_tokens, 0), t.max_frames());
+  int done_steps = 0;
+  while (true) {
+    const int chunk = std::min(8, std::max(1, limit - done_steps));
+    t.run_frames(1, chunk);
+    t.fetch_states(1, st);
+    done_steps = st[0].step;
+    if (st[0].finished || st[0].step >= limit) break;
+  }
+  n_raw = st[0].n_frames;
+  h->timing.frames += n_raw;
+  raw.resize((size_t)std::max(n_raw, 1) * 16);
+  t.fetch_frames(0, 0, n_raw, raw.data());
+  if (req.code0_logits_out || req.cp_logits_out) t.fetch_logits(std::min(st[0].step + (st[0].finished ? 1 : 0), req.logits_capacity_frames), req.code0_logits_out, req.cp_logits_out);
+  t.release(0);
+}
+
+int filter_frames(const q3tts_request& req, const std::vector<int32_t>& raw, int n_raw, int32_t* out, int capacity) {
+  int n = 0;
+  for (int i = 0; i < n_raw && n < capacity; ++i) {
+    const int32_t* f = raw.data() + (size_t)i * 16;
+    if (req.keep_invalid_frames || frame_valid(f)) {
+      if (out) memcpy(out + (size_t)n * 16, f, 64);
+      ++n;
+    }
+  }
+  return n;
+}
+
+// Continuous batching of independent utterances over the handle's slots; raw[i] receives utterance i's raw frames.
+void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<std::vector<int32_t>>& raw, std::vector<int>& n_raw) {
+  TalkerEngine& t = *h->talker;
+  const int B = t.max_batch();
+  raw.assign(n, {});
+  n_raw.assign(n, 0);
+  std::vector<int> slot_req(B, -1);
+  int next = 0, active = 0;
+  std::vector<SlotState> st;
+  while (next < n || active > 0) {
+    for (int s = 0; s < B && next < n; ++s) {
+      if (slot_req[s] >= 0) continue;
+      while (next < n) {
+        Q3_CHECK(!(reqs[next].code0_logits_out || reqs[next].cp_logits_out), Q3TTS_ERR_INVALID_ARG, "logit dumps are only available through q3tts_generate_codes");
+        Admission a = t.admit(s, reqs[next]);
+        if (!a.too_short) { slot_req[s] = next++; ++active; break; }
+        ++next;  // too short: zero frames, like the reference's [] (Model/Qwen3Talker.swift:348-352)
+      }
+    }
+    if (active == 0) break;
+    int hi = 0;
+    for (int s = 0; s < B; ++s)
+      if (slot_req[s] >= 0) hi = s + 1;
+    t.run_frames(hi, 8);
+    t.fetch_states(hi, st);
+    for (int s = 0; s < hi; ++s) {
+      if (slot_req[s] < 0 || !st[s].finished) continue;
+      const int r = slot_req[s];
+      n_raw[r] = st[s].n_frames;
+      h->timing.frames += n_raw[r];
+      raw[r].resize((size_t)std::max(n_raw[r], 1) * 16);
+      t.fetch_frames(s, 0, n_raw[r], raw[r].data());
+      t.release(s);
+      slot_req[s] = -1;
+      --active;
+    }
+  }
+}
+
+// ---- codec drivers ---------------------------------------------------------------------------------------------
+struct DecodeJob {
+  const int32_t* frames;  // host [T][16]
+  int T;
+  float* out;         // host destination
+  int64_t drop;       // leading samples to skip (left context)
+  int64_t max_out;    // samples to deliver at most
+};
+
+void ensure_pinned(q3tts_handle* h, size_t pcm_floats, size_t code_ints) {
+  if (pcm_floats > h->h_pcm_floats) {
+    if (h->h_pcm) cudaFreeHost(h->h_pcm);
+    h->h_pcm = nullptr;
+    Q3_CUDA(cudaMallocHost(&h->h_pcm, pcm_floats * sizeof(float)));
+    h->h_pcm_floats = pcm_floats;
+  }
+  if (code_ints > h->h_codes_ints) {
+    if (h->h_codes) cudaFreeHost(h->h_codes);
+    h->h_codes = nullptr;
+    Q3_CUDA(cudaMallocHost(&h->h_codes, code_ints * sizeof(int32_t)));
+    h->h_codes_ints = code_ints;
+  }
+}
+
+// Decodes jobs grouped by equal T, each group in passes of up to pass_frames frames (jobs stacked on the batch axis).
+void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
+  CodecDecoder& c = *h->codec;
+  const int up = c.total_upsample();
+  std::map<int, std::vector<size_t>> by_t;
+  for (size_t i = 0; i < jobs.size(); ++i)
+    if (jobs[i].T > 0) by_t[jobs[i].T].push_back(i);
+  cudaEvent_t e0, e1;
+  Q3_CUDA(cudaEventCreate(&e0));
+  Q3_CUDA(cudaEventCreate(&e1));
+  for (auto& kv : by_t) {
+    const int T = kv.first;
+    Q3_CHECK(T <= c.pass_frames(), Q3TTS_ERR_CAPACITY, "decode window of %d frames exceeds codec pass capacity %d (q3tts_options.codec_max_frames)", T, c.pass_frames());
+    const int per_pass = std::max(1, c.pass_frames() / T);
+    const auto& idx = kv.second;
+    for (size_t p0 = 0; p0 < idx.size(); p0 += per_pass) {
+      const int nb = (int)std::min<size_t>(per_pass, idx.size() - p0);
+      const size_t code_ints = (size_t)nb * T * 16, pcm_floats = (size_t)nb * T * up;
+      ensure_pinned(h, pcm_floats, code_ints);
+      for (int b = 0; b < nb; ++b) memcpy(h->h_codes + (size_t)b * T * 16, jobs[idx[p0 + b]].frames, (size_t)T * 64);
+      int32_t* d_codes = nullptr;
+      float* d_pcm = nullptr;
+      Q3_CUDA(cudaMallocAsync(&d_codes, code_ints * 4, h->stream));
+      Q3_CUDA(cudaMallocAsync(&d_pcm, pcm_floats * 4, h->stream));
+      Q3_CUDA(cudaMemcpyAsync(d_codes, h->h_codes, code_ints * 4, cudaMemcpyHostToDevice, h->stream));
+      h->timing.h2d_bytes += (int64_t)code_ints * 4;
+      Q3_CUDA(cudaEventRecord(e0, h->stream));
+      c.decode_pass(d_codes, nb, T, d_pcm);
+      Q3_CUDA(cudaEventRecord(e1, h->stream));
+      Q3_CUDA(cudaMemcpyAsync(h->h_pcm, d_pcm, pcm_floats * 4, cudaMemcpyDeviceToHost, h->stream));
+      h->timing.d2h_bytes += (int64_t)pcm_floats * 4;
+      Q3_CUDA(cudaFreeAsync(d_codes, h->stream));
+      Q3_CUDA(cudaFreeAsync(d_pcm, h->stream));
+      Q3_CUDA(cudaStreamSynchronize(h->stream));
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      h->timing.decode_ms += ms;
+      for (int b = 0; b < nb; ++b) {
+        DecodeJob& j = jobs[idx[p0 + b]];
+        const int64_t total = (int64_t)T * up;
+        const int64_t n = std::max<int64_t>(0, std::min<int64_t>(total - j.drop, j.max_out));
+        if (n > 0) memcpy(j.out, h->h_pcm + (size_t)b * total + j.drop, (size_t)n * sizeof(float));
+      }
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+// NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732)
+void clean_samples(float* p, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) {
+    const float v = p[i];
+    p[i] = (v != v || v > 3.0e38f || v < -3.0e38f) ? 0.0f : std::max(-1.0f, std::min(1.0f, v));
+  }
+}
+
+// Schedules the decode windows of one utterance's valid frames as `mode` prescribes; appends jobs writing into out.
+int64_t plan_decode(int mode, const int32_t* frames, int n, float* out, int64_t capacity, int up, std::vector<DecodeJob>& jobs) {
+  if (n <= 0) return 0;
+  const int64_t total = std::min<int64_t>((int64_t)n * up, capacity);
+  if (mode == Q3TTS_DECODE_WHOLE) {
+    jobs.push_back({frames, n, out, 0, total});
+    return total;
+  }
+  const int chunk = mode == Q3TTS_DECODE_FILE ? 16 : (mode == Q3TTS_DECODE_BATCHAPI ? 24 : 18), left = 8;
+  for (int pos = 0; pos < n; pos += chunk) {
+    const int end = std::min(pos + chunk, n);
+    const int ctx = pos == 0 ? 0 : std::min(left, pos);  // codes[max(0,end-8)..<end] of the previous window (:734, 561)
+    const int64_t o0 = (int64_t)pos * up;
+    if (o0 >= total) break;
+    jobs.push_back({frames + (size_t)(pos - ctx) * 16, end - pos + ctx, out + o0, (int64_t)ctx * up, std::min<int64_t>((int64_t)(end - pos) * up, total - o0)});
+  }
+  return total;
+}
+
+}  // namespace
+
+// =================================================================================================== lifecycle
+extern "C" {
+
+int32_t q3tts_abi_version(void) { return Q3TTS_ABI_VERSION; }
+
+void q3tts_default_options(q3tts_options* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->struct_size = (int32_t)sizeof *o;
+  o->device = 0;
+  o->max_batch = 1;
+  o->kv_capacity = 512;
+  o->max_frames = 2400;
+  o->use_cuda_graph = 1;
+  o->load_codec = 1;
+  o->load_talker = 1;
+  o->codec_max_frames = 2400;
+  o->codec_max_batch = 8;
+}
+
+void q3tts_default_request(q3tts_request* r) {
+  if (!r) return;
+  memset(r, 0, sizeof *r);
+  r->struct_size = (int32_t)sizeof *r;
+  r->speaker_id = -1;
+  r->temperature = 0.9f;          // Model/Qwen3Talker.swift:335
+  r->top_k = 0;                   // :277
+  r->top_p = 1.0f;
+  r->repetition_penalty = 1.05f;  // :279
+  r->max_tokens = 1200;           // :336
+}
+
+q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tts_handle** out) {
+  if (!out) return Q3TTS_ERR_INVALID_ARG;
+  *out = nullptr;
+  q3tts_handle* h = nullptr;
+  try {
+    Q3_CHECK(model_dir != nullptr, Q3TTS_ERR_INVALID_ARG, "model_dir is NULL");
+    q3tts_options o;
+    q3tts_default_options(&o);
+    if (opts) {
+      const size_t n = std::min<size_t>(sizeof o, opts->struct_size > 0 ? (size_t)opts->struct_size : sizeof o);
+      memcpy(&o, opts, n);
+    }
+    require_device(o.device);
+    h = new q3tts_handle();
+    h->opt.device = o.device;
+    h->opt.max_batch = o.max_batch > 0 ? o.max_batch : 1;
+    h->opt.kv_capacity = o.kv_capacity > 0 ? std::max(o.kv_capacity, 208) : 512;
+    h->opt.max_frames = o.max_frames > 0 ? o.max_frames : 2400;
+    h->opt.use_cuda_graph = o.use_cuda_graph;
+    h->opt.load_codec = o.load_codec;
+    h->opt.load_talker = o.load_talker;
+    h->opt.codec_max_frames = o.codec_max_frames > 0 ? o.codec_max_frames : 2400;
+    h->opt.codec_max_batch = o.codec_max_batch > 0 ? o.codec_max_batch : 8;
+    if (o.cuda_stream) {
+      h->stream = (cudaStream_t)o.cuda_stream;
+    } else {
+      Q3_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+      h->own_stream = true;
+    }
+    h->opt.stream = h->stream;
+    Q3_CUDA(cudaEventCreate(&h->ev_start));
+    Q3_CUDA(cudaEventCreate(&h->ev_stop));
+    const std::string dir(model_dir);
+    if (h->opt.load_talker) {
+      // config.json, then model.safetensors (Qwen3TTSPipeline.swift:127-141)
+      Json root = parse_json_file(dir + "/config.json");
+      h->cfg = parse_talker_config(root);
+      h->talker.reset(new TalkerEngine(dir, h->cfg, h->opt, h->stream, &h->counter));
+      h->has_talker = true;
+    }
+    if (h->opt.load_codec) {
+      // speech_tokenizer/{config...} + model.safetensors (Qwen3TTSPipeline.swift:191-208)
+      // one pass holds up to codec_max_frames frames (batch x window); the workspace itself is allocated on first use
+      h->codec.reset(new CodecDecoder(dir + "/speech_tokenizer", h->stream, &h->counter, h->opt.codec_max_frames));
+    }
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    delete h;
+    return e.status;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete h;
+    return Q3TTS_ERR_CUDA;
+  }
+}
+
+void q3tts_destroy(q3tts_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->opt.device);
+  cudaStreamSynchronize(h->stream);
+  delete h;
+}
+
+const char* q3tts_last_error(const q3tts_handle* h) { return h ? h->last_error.c_str() : g_create_error.c_str(); }
+
+q3tts_status q3tts_get_info(const q3tts_handle* hc, q3tts_info* out) {
+  if (!hc || !out) return Q3TTS_ERR_INVALID_ARG;
+  memset(out, 0, sizeof *out);
+  const TalkerConfig& c = hc->cfg;
+  if (hc->talker) {
+    out->hidden_size = c.hidden_size; out->num_layers = c.num_hidden_layers; out->num_heads = c.num_attention_heads;
+    out->num_kv_heads = c.num_key_value_heads; out->head_dim = c.head_dim; out->intermediate_size = c.intermediate_size;
+    out->vocab_size = c.vocab_size; out->text_vocab_size = c.text_vocab_size; out->text_hidden_size = c.text_hidden_size;
+    out->cp_hidden_size = c.cp.hidden_size; out->cp_num_layers = c.cp.num_hidden_layers; out->cp_vocab_size = c.cp.vocab_size;
+    out->num_code_groups = c.cp.num_code_groups;
+    out->quant_bits = hc->talker->quant_bits(); out->quant_group_size = hc->talker->quant_group();
+    out->weight_dtype = hc->talker->weight_dtype();
+    out->num_speakers = (int32_t)c.spk_id.size();
+    out->model_type = c.tts_model_type == "voice_design" ? 1 : (c.tts_model_type == "custom_voice" ? 2 : 0);
+    out->codec_eos_id = c.codec_eos_token_id; out->codec_pad_id = c.codec_pad_id;
+    out->max_batch = hc->talker->max_batch(); out->kv_capacity = hc->talker->kv_capacity(); out->max_frames = hc->talker->max_frames();
+    out->device_bytes += (int64_t)hc->talker->device_bytes();
+  }
+  if (hc->codec) {
+    out->has_codec = 1;
+    out->codec_num_quantizers = hc->codec->config().num_quantizers;
+    out->codec_total_upsample = hc->codec->total_upsample();
+    out->device_bytes += (int64_t)hc->codec->device_bytes();
+  }
+  return Q3TTS_OK;
+}
+
+q3tts_status q3tts_speaker_name(const q3tts_handle* h, int32_t index, char* name_out, int32_t capacity, int32_t* id_out) {
+  if (!h || index < 0 || index >= (int32_t)h->cfg.spk_id.size()) return Q3TTS_ERR_INVALID_ARG;
+  std::vector<std::pair<std::string, int>> s = h->cfg.spk_id;
+  std::sort(s.begin(), s.end());  // availableSpeakers = keys.sorted() (Qwen3TTSPipeline.swift:77-79)
+  if (name_out && capacity > 0) {
+    strncpy(name_out, s[index].first.c_str(), capacity - 1);
+    name_out[capacity - 1] = 0;
+  }
+  if (id_out) *id_out = s[index].second;
+  return Q3TTS_OK;
+}
+
+int32_t q3tts_speaker_id(const q3tts_handle* h, const char* name) {
+  if (!h || !name) return -1;
+  for (auto& kv : h->cfg.spk_id)
+    if (kv.first == name) return kv.second;
+  return -1;
+}
+
+q3tts_status q3tts_clear_cache(q3tts_handle* h) {
+  return guarded(h, [&] {
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->talker) h->talker->drop_graphs();
+  });
+}
+
+q3tts_status q3tts_get_timing(const q3tts_handle* h, q3tts_timing* out) {
+  if (!h || !out) return Q3TTS_ERR_INVALID_ARG;
+  *out = h->timing;
+  return Q3TTS_OK;
+}
+
+// =================================================================================================== talker
+q3tts_status q3tts_generate_codes(q3tts_handle* h, const q3tts_request* req, int32_t* codes_out, int32_t capacity_frames,
+                                  int32_t* frames_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(req && frames_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    *frames_out = 0;
+    CallTimer tm(h);
+    std::vector<int32_t> raw;
+    int n_raw = 0;
+    run_single(h, *req, raw, n_raw);
+    *frames_out = filter_frames(*req, raw, n_raw, codes_out, capacity_frames);
+    h->timing.d2h_bytes += (int64_t)n_raw * 64;
+    h->timing.h2d_bytes += (int64_t)req->n_text_ids * 4;
+    tm.finish();
+  });
+}
+
+q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t* const* codes_out,
+                                        int32_t capacity_frames, int32_t* frames_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(reqs && frames_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    CallTimer tm(h);
+    std::vector<std::vector<int32_t>> raw;
+    std::vector<int> n_raw;
+    run_batch(h, reqs, n, raw, n_raw);
+    for (int i = 0; i < n; ++i) {
+      frames_out[i] = filter_frames(reqs[i], raw[i], n_raw[i], codes_out ? codes_out[i] : nullptr, capacity_frames);
+      h->timing.d2h_bytes += (int64_t)n_raw[i] * 64;
+      h->timing.h2d_bytes += (int64_t)reqs[i].n_text_ids * 4;
+    }
+    tm.finish();
+  });
+}
+
+}  // extern "C"
+
+// ---- streaming ---------------------------------------------------------------------------------------------------
+struct q3tts_stream {
+  q3tts_handle* h = nullptr;
+  int chunk_size = 12;
+  int limit = 0;
+  int emitted = 0;     // raw frames already delivered
+  bool talker_done = false, cancelled = false, too_short = false;
+  // consumer state of _generateStreamImpl (Qwen3TTSPipeline.swift:520-563)
+  std::deque<std::vector<int32_t>> code_buffer;  // valid frames
+  std::vector<int32_t> left_context;             // up to 8 frames
+  bool first_decode = true, final_sent = false;
+  int total_processed = 0;
+  bool released = false;
+};
+
+namespace {
+// Produce the next chunk of raw frames (up to chunk_size); sets talker_done when the loop ended.
+int stream_pull(q3tts_stream* s, int32_t* out) {
+  TalkerEngine& t = *s->h->talker;
+  if (s->talker_done || s->too_short) { s->talker_done = true; return 0; }
+  std::vector<SlotState> st;
+  t.fetch_states(1, st);
+  while (!s->cancelled && !st[0].finished && st[0].n_frames - s->emitted < s->chunk_size) {
+    const int want = s->chunk_size - (st[0].n_frames - s->emitted);
+    t.run_frames(1, std::max(1, std::min(want, s->limit - st[0].step)));
+    t.fetch_states(1, st);
+  }
+  const int avail = st[0].n_frames - s->emitted;
+  const int n = std::min(avail, s->chunk_size);
+  if (n > 0) t.fetch_frames(0, s->emitted, n, out);
+  s->emitted += n;
+  s->h->timing.frames += n;
+  if ((st[0].finished || s->cancelled) && s->emitted >= st[0].n_frames) {
+    s->talker_done = true;
+    if (!s->released) { t.release(0); s->released = true; }
+  }
+  return n;
+}
+}  // namespace
+
+extern "C" {
+
+q3tts_status q3tts_stream_begin(q3tts_handle* h, const q3tts_request* req, int32_t chunk_size, q3tts_stream** out) {
+  if (out) *out = nullptr;
+  return guarded(h, [&] {
+    Q3_CHECK(req && out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    h->timing = q3tts_timing{};
+    std::unique_ptr<q3tts_stream> s(new q3tts_stream());
+    s->h = h;
+    s->chunk_size = chunk_size > 0 ? chunk_size : 12;  // defaultStreamingChunkSize (Qwen3TTSPipeline.swift:43)
+    q3tts_request r = *req;
+    r.stream_variant = 1;
+    Admission a = h->talker->admit(0, r);
+    s->too_short = a.too_short;
+    s->limit = std::min(std::max(r.max_tokens, 0), h->talker->max_frames());
+    *out = s.release();
+  });
+}
+
+q3tts_status q3tts_stream_next(q3tts_stream* s, int32_t* codes_out, int32_t* frames_out, int32_t* done_out) {
+  if (!s || !codes_out || !frames_out || !done_out) return Q3TTS_ERR_INVALID_ARG;
+  return guarded(s->h, [&] {
+    *frames_out = stream_pull(s, codes_out);
+    *done_out = s->talker_done ? 1 : 0;
+  });
+}
+
+q3tts_status q3tts_stream_next_audio(q3tts_stream* s, float* pcm_out, int32_t capacity_samples, int32_t* samples_out,
+                                     int32_t* token_start_out, int32_t* token_end_out, int32_t* is_final_out, int32_t* done_out) {
+  if (!s || !pcm_out || !samples_out || !done_out) return Q3TTS_ERR_INVALID_ARG;
+  return guarded(s->h, [&] {
+    q3tts_handle* h = s->h;
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    const int DECODE_CHUNK = 18, LEFT = 8, up = h->codec->total_upsample();
+    *samples_out = 0;
+    *done_out = 0;
+    int tok0 = s->total_processed, tok1 = s->total_processed, is_final = 0;
+    auto decode_batch = [&](int count) {
+      std::vector<int32_t> win;
+      const int ctx = s->first_decode ? 0 : (int)s->left_context.size() / 16;
+      if (!s->first_decode) win = s->left_context;
+      s->first_decode = false;
+      std::vector<int32_t> batch;
+      for (int i = 0; i < count; ++i) {
+        batch.insert(batch.end(), s->code_buffer.front().begin(), s->code_buffer.front().end());
+        s->code_buffer.pop_front();
+      }
+      win.insert(win.end(), batch.begin(), batch.end());
+      const int T = (int)win.size() / 16;
+      Q3_CHECK((int64_t)count * up <= capacity_samples, Q3TTS_ERR_CAPACITY, "pcm_out too small for a %d-frame chunk", count);
+      std::vector<DecodeJob> jobs{{win.data(), T, pcm_out, (int64_t)ctx * up, (int64_t)count * up}};
+      run_decode_jobs(h, jobs);
+      clean_samples(pcm_out, (int64_t)count * up);
+      const int keep = std::min(LEFT, count);  // leftContext = codes.suffix(8) (:561)
+      s->left_context.assign(batch.end() - (size_t)keep * 16, batch.end());
+      *samples_out = count * up;
+      tok0 = s->total_processed;
+      s->total_processed += count;
+      tok1 = s->total_processed;
+    };
+    std::vector<int32_t> chunk((size_t)s->chunk_size * 16);
+    while (true) {
+      if ((int)s->code_buffer.size() >= DECODE_CHUNK) { decode_batch(DECODE_CHUNK); break; }
+      if (!s->talker_done) {
+        const int n = stream_pull(s, chunk.data());
+        for (int i = 0; i < n; ++i)
+          if (frame_valid(chunk.data() + (size_t)i * 16))  // :576-579
+            s->code_buffer.emplace_back(chunk.begin() + (size_t)i * 16, chunk.begin() + (size_t)(i + 1) * 16);
+        continue;
+      }
+      if (!s->code_buffer.empty()) { decode_batch((int)s->code_buffer.size()); is_final = 1; break; }  // flush (:598-605)
+      // trailing empty isFinal chunk, always (:607)
+      s->final_sent = true;
+      is_final = 1;
+      *done_out = 1;
+      break;
+    }
+    if (token_start_out) *token_start_out = tok0;
+    if (token_end_out) *token_end_out = tok1;
+    if (is_final_out) *is_final_out = is_final;
+  });
+}
+
+q3tts_status q3tts_stream_cancel(q3tts_stream* s) {
+  if (!s) return Q3TTS_ERR_INVALID_ARG;
+  s->cancelled = true;
+  return Q3TTS_OK;
+}
+
+void q3tts_stream_free(q3tts_stream* s) {
+  if (!s) return;
+  if (s->h && s->h->talker && !s->released) {
+    guarded(s->h, [&] { s->h->talker->release(0); });
+  }
+  delete s;
+}
+
+// =================================================================================================== codec
+q3tts_status q3tts_decode(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, float* pcm_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    Q3_CHECK(codes && pcm_out && batch >= 0 && frames >= 0, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    CallTimer tm(h);
+    const int up = h->codec->total_upsample(), Q = h->codec->config().num_quantizers;
+    Q3_CHECK(Q == 16, Q3TTS_ERR_BAD_CONFIG, "codec with %d quantizers: the ABI carries 16 codes per frame", Q);
+    std::vector<DecodeJob> jobs;
+    for (int b = 0; b < batch; ++b)
+      jobs.push_back({codes + (size_t)b * frames * 16, frames, pcm_out + (size_t)b * frames * up, 0, (int64_t)frames * up});
+    run_decode_jobs(h, jobs);
+    tm.finish();
+  });
+}
+
+q3tts_status q3tts_decode_chunked(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, int32_t chunk_size,
+                                  int32_t left_context, float* pcm_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    Q3_CHECK(codes && pcm_out && batch >= 0 && frames >= 0 && chunk_size > 0 && left_context >= 0, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    CallTimer tm(h);
+    const int up = h->codec->total_upsample();
+    // chunkedDecode (Vocoder/SpeechTokenizer.swift:954-987): left-pad with code 0 x left_context, right-pad to a multiple of
+    // chunk_size, windows of chunk_size + left_context stacked on the batch axis, drop the context samples, trim to T*up.
+    const int n_chunks = (frames + chunk_size - 1) / chunk_size;
+    const int Lw = chunk_size + left_context;
+    std::vector<int32_t> win((size_t)batch * n_chunks * Lw * 16, 0);
+    std::vector<DecodeJob> jobs;
+    for (int b = 0; b < batch; ++b)
+      for (int ci = 0; ci < n_chunks; ++ci) {
+        int32_t* w = win.data() + ((size_t)b * n_chunks + ci) * Lw * 16;
+        for (int p = 0; p < Lw; ++p) {
+          const int src = ci * chunk_size + p - left_context;
+          if (src >= 0 && src < frames) memcpy(w + (size_t)p * 16, codes + ((size_t)b * frames + src) * 16, 64);
+        }
+        const int64_t o0 = (int64_t)ci * chunk_size * up;
+        jobs.push_back({w, Lw, pcm_out + (size_t)b * frames * up + o0, (int64_t)left_context * up,
+                        std::min<int64_t>((int64_t)chunk_size * up, (int64_t)frames * up - o0)});
+      }
+    run_decode_jobs(h, jobs);
+    tm.finish();
+  });
+}
+
+// =================================================================================================== fused text -> PCM
+q3tts_status q3tts_generate_pcm(q3tts_handle* h, const q3tts_request* req, int32_t mode, float* pcm_out, int64_t capacity_samples,
+                                int64_t* samples_out, int32_t* frames_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(req && pcm_out && samples_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    *samples_out = 0;
+    if (frames_out) *frames_out = 0;
+    CallTimer tm(h);
+    std::vector<int32_t> raw;
+    int n_raw = 0;
+    run_single(h, *req, raw, n_raw);
+    std::vector<int32_t> valid((size_t)std::max(n_raw, 1) * 16);
+    q3tts_request r = *req;
+    r.keep_invalid_frames = 0;
+    const int n = filter_frames(r, raw, n_raw, valid.data(), n_raw);
+    std::vector<DecodeJob> jobs;
+    const int64_t total = plan_decode(mode, valid.data(), n, pcm_out, capacity_samples, h->codec->total_upsample(), jobs);
+    run_decode_jobs(h, jobs);
+    clean_samples(pcm_out, total);
+    *samples_out = total;
+    if (frames_out) *frames_out = n;
+    h->timing.h2d_bytes += (int64_t)req->n_text_ids * 4;
+    tm.finish();
+  });
+}
+
+q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t mode, float* const* pcm_out,
+                                      int64_t capacity_samples, int64_t* samples_out, int32_t* frames_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(reqs && pcm_out && samples_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    CallTimer tm(h);
+    std::vector<std::vector<int32_t>> raw;
+    std::vector<int> n_raw;
+    run_batch(h, reqs, n, raw, n_raw);
+    std::vector<std::vector<int32_t>> valid(n);
+    std::vector<DecodeJob> jobs;
+    std::vector<int64_t> totals(n, 0);
+    for (int i = 0; i < n; ++i) {
+      valid[i].resize((size_t)std::max(n_raw[i], 1) * 16);
+      q3tts_request r = reqs[i];
+      r.keep_invalid_frames = 0;
+      const int nv = filter_frames(r, raw[i], n_raw[i], valid[i].data(), n_raw[i]);
+      if (frames_out) frames_out[i] = nv;
+      totals[i] = plan_decode(mode, valid[i].data(), nv, pcm_out[i], capacity_samples, h->codec->total_upsample(), jobs);
+      h->timing.h2d_bytes += (int64_t)reqs[i].n_text_ids * 4;
+    }
+    run_decode_jobs(h, jobs);
+    for (int i = 0; i < n; ++i) {
+      clean_samples(pcm_out[i], totals[i]);
+      samples_out[i] = totals[i];
+    }
+    tm.finish();
+  });
+}
+
+// =================================================================================================== parity probes
+q3tts_status q3tts_dequantize(int32_t device, const uint32_t* packed, const void* scales, const void* biases, int32_t scale_dtype,
+                              int32_t out_f, int32_t in_f, int32_t group, int32_t bits, int32_t out_dtype, void* out) {
+  try {
+    Q3_CHECK(packed && scales && biases && out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK((bits == 4 || bits == 8) && group > 0 && in_f % group == 0 && group % (32 / bits) == 0, Q3TTS_ERR_INVALID_ARG,
+             "unsupported bits/group (%d/%d)", bits, group);
+    require_device(device);
+    const size_t wbytes = (size_t)out_f * in_f * bits / 8, sbytes = (size_t)out_f * (in_f / group) * dtype_size(scale_dtype);
+    const size_t obytes = (size_t)out_f * in_f * dtype_size(out_dtype);
+    void *dw = nullptr, *ds = nullptr, *db = nullptr, *dout = nullptr;
+    Q3_CUDA(cudaMalloc(&dw, wbytes)); Q3_CUDA(cudaMalloc(&ds, sbytes)); Q3_CUDA(cudaMalloc(&db, sbytes)); Q3_CUDA(cudaMalloc(&dout, obytes));
+    Q3_CUDA(cudaMemcpy(dw, packed, wbytes, cudaMemcpyHostToDevice));
+    Q3_CUDA(cudaMemcpy(ds, scales, sbytes, cudaMemcpyHostToDevice));
+    Q3_CUDA(cudaMemcpy(db, biases, sbytes, cudaMemcpyHostToDevice));
+    LaunchCtx c{nullptr, nullptr};
+    launch_dequantize(c, (const uint32_t*)dw, ds, db, scale_dtype, out_f, in_f, group, bits, out_dtype, dout);
+    Q3_CUDA(cudaDeviceSynchronize());
+    Q3_CUDA(cudaMemcpy(out, dout, obytes, cudaMemcpyDeviceToHost));
+    cudaFree(dw); cudaFree(ds); cudaFree(db); cudaFree(dout);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
+q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, const uint32_t* packed, const void* scales,
+                                    const void* biases, int32_t scale_dtype, int32_t out_f, int32_t in_f, int32_t group,
+                                    int32_t bits, float* y) {
+  try {
+    Q3_CHECK(x && packed && y && m > 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    require_device(device);
+    q3::init_talker_kernels();
+    Linear L;
+    L.out = out_f; L.in = in_f; L.bits = bits; L.group = group; L.sdt = scale_dtype;
+    const size_t wbytes = bits ? (size_t)out_f * in_f * bits / 8 : (size_t)out_f * in_f * dtype_size(scale_dtype);
+    const size_t sbytes = bits ? (size_t)out_f * (in_f / group) * dtype_size(scale_dtype) : 0;
+    void *dw = nullptr, *ds = nullptr, *db = nullptr;
+    float *dx = nullptr, *dy = nullptr;
+    Q3_CUDA(cudaMalloc(&dw, wbytes));
+    Q3_CUDA(cudaMemcpy(dw, packed, wbytes, cudaMemcpyHostToDevice));
+    if (bits) {
+      Q3_CHECK(scales && biases, Q3TTS_ERR_INVALID_ARG, "NULL scales/biases");
+      Q3_CUDA(cudaMalloc(&ds, sbytes)); Q3_CUDA(cudaMalloc(&db, sbytes));
+      Q3_CUDA(cudaMemcpy(ds, scales, sbytes, cudaMemcpyHostToDevice));
+      Q3_CUDA(cudaMemcpy(db, biases, sbytes, cudaMemcpyHostToDevice));
+      L.qw = (const uint32_t*)dw; L.scales = ds; L.biases = db;
+    } else {
+      L.w = dw;
+    }
+    Q3_CUDA(cudaMalloc(&dx, (size_t)m * in_f * 4)); Q3_CUDA(cudaMalloc(&dy, (size_t)m * out_f * 4));
+    Q3_CUDA(cudaMemcpy(dx, x, (size_t)m * in_f * 4, cudaMemcpyHostToDevice));
+    LaunchCtx c{nullptr, nullptr};
+    launch_linear(c, L, dx, in_f, m, dy, out_f, nullptr, 0.f, EPI_STORE);
+    Q3_CUDA(cudaDeviceSynchronize());
+    Q3_CUDA(cudaMemcpy(y, dy, (size_t)m * out_f * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dw); cudaFree(ds); cudaFree(db); cudaFree(dx); cudaFree(dy);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
+q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vocab, float temperature, int32_t top_k, float top_p,
+                                float repetition_penalty, const int32_t* token_set, int32_t n_token_set, uint64_t seed,
+                                uint64_t counter, int32_t* id_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(logits && id_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    *id_out = h->talker->sample_probe(logits, vocab, temperature, top_k, top_p, repetition_penalty, token_set, n_token_set, seed, counter);
+  });
+}
+
+q3tts_status q3tts_rvq_embed(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, float* first_out, float* rest_out,
+                             int32_t* dim_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
+    Q3_CHECK(codes && first_out && rest_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    const int M = batch * frames, D = h->codec->vq_dim();
+    if (dim_out) *dim_out = D;
+    if (M <= 0) return;
+    int32_t* dc = nullptr;
+    float *d1 = nullptr, *d2 = nullptr;
+    Q3_CUDA(cudaMalloc(&dc, (size_t)M * 64)); Q3_CUDA(cudaMalloc(&d1, (size_t)M * D * 4)); Q3_CUDA(cudaMalloc(&d2, (size_t)M * D * 4));
+    Q3_CUDA(cudaMemcpyAsync(dc, codes, (size_t)M * 64, cudaMemcpyHostToDevice, h->stream));
+    h->codec->rvq_embed(dc, batch, frames, d1, d2);
+    Q3_CUDA(cudaMemcpyAsync(first_out, d1, (size_t)M * D * 4, cudaMemcpyDeviceToHost, h->stream));
+    Q3_CUDA(cudaMemcpyAsync(rest_out, d2, (size_t)M * D * 4, cudaMemcpyDeviceToHost, h->stream));
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(dc); cudaFree(d1); cudaFree(d2);
+  });
+}
+
+}  // extern "C"

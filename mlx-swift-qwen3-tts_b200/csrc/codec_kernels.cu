@@ -1,0 +1,337 @@
+// Codec-decoder kernels, first correct (fp32 SIMT) generation.  Channels-last [B, T, C] activations.
+// The dense contractions (causal convs, polyphase transposed convs, linears) all go through one implicit-GEMM
+// formulation:  Y[m, n] = bias[n] + sum_tap X[m - shift(tap), :] . W[tap][n][:]   with m = b*T + t and rows whose source
+// time is negative reading zeros (causal left padding, Vocoder/SpeechTokenizer.swift:160-169, 796-801).
+#include "codec_kernels.h"
+
+namespace q3 {
+
+__device__ __forceinline__ float warp_sum_c(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_c(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------- implicit-GEMM conv (SIMT fp32)
+constexpr int CB_M = 64, CB_N = 64, CB_K = 16;
+
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ x, ConvW w, float* y, const float* res,
+                                                        const float* __restrict__ scale, int M, int T, int epi) {
+  __shared__ float As[CB_K][CB_M + 4];
+  __shared__ float Bs[CB_K][CB_N + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * CB_M, n0 = blockIdx.y * CB_N;  // M tiles on x: up to 2^31-1 blocks
+  const int lrow = tid >> 2, kq = (tid & 3) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int am = m0 + lrow;
+  const int at = am % T;
+  const bool vec = (w.cin & 3) == 0;
+  for (int tap = 0; tap < w.ntap; ++tap) {
+    const int shift = (w.ntap - 1 - tap) * w.dil;
+    const bool a_ok = am < M && (at - shift) >= 0;
+    const float* xa = x + (size_t)(am - shift) * w.cin;
+    const int bn = n0 + lrow;
+    const bool b_ok = bn < w.n;
+    const float* wb = w.w + ((size_t)tap * w.n + bn) * w.cin;
+    for (int c0 = 0; c0 < w.cin; c0 += CB_K) {
+      float av[4] = {0.f, 0.f, 0.f, 0.f}, bv[4] = {0.f, 0.f, 0.f, 0.f};
+      const int c = c0 + kq;
+      if (vec && c + 3 < w.cin) {
+        if (a_ok) { const float4 t4 = *reinterpret_cast<const float4*>(xa + c); av[0] = t4.x; av[1] = t4.y; av[2] = t4.z; av[3] = t4.w; }
+        if (b_ok) { const float4 t4 = *reinterpret_cast<const float4*>(wb + c); bv[0] = t4.x; bv[1] = t4.y; bv[2] = t4.z; bv[3] = t4.w; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (c + i < w.cin) {
+            if (a_ok) av[i] = xa[c + i];
+            if (b_ok) bv[i] = wb[c + i];
+          }
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { As[kq + i][lrow] = av[i]; Bs[kq + i][lrow] = bv[i]; }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < CB_K; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= w.n) continue;
+      float v = acc[i][j] + (w.bias ? w.bias[n] : 0.f);
+      const size_t o = (size_t)m * w.n + n;
+      if (epi == CE_GELU) v = 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f));  // exact erf GELU (:230)
+      else if (epi == CE_RES_SCALE) v = res[o] + (scale ? scale[n] : 1.0f) * v;
+      y[o] = v;
+    }
+  }
+}
+
+void launch_conv_gemm(const LaunchCtx& c, const float* x, const ConvW& w, float* y, const float* res, const float* scale, int M,
+                      int T, int epi) {
+  if (M <= 0) return;
+  dim3 grid((M + CB_M - 1) / CB_M, (w.n + CB_N - 1) / CB_N);
+  conv_gemm_kernel<<<grid, 256, 0, c.stream>>>(x, w, y, res, scale, M, T, epi);
+  c.tick();
+}
+
+// ---------------------------------------------------------------------------------------------- elementwise / small ops
+__global__ void snake_kernel(const float* __restrict__ x, const float* __restrict__ ea, const float* __restrict__ inv_eb, int C,
+                             size_t total, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    const float v = x[i];
+    const float s = sinf(v * ea[ch]);
+    y[i] = v + inv_eb[ch] * (s * s);  // x + sin^2(x e^alpha) / (e^beta + 1e-9)  (SpeechTokenizer.swift:105-109)
+  }
+}
+void launch_snake(const LaunchCtx& c, const float* x, const SnakeW& s, size_t rows, float* y) {
+  const size_t total = rows * s.ch;
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  snake_kernel<<<blocks, 256, 0, c.stream>>>(x, s.alpha, s.beta, s.ch, total, y);
+  c.tick();
+}
+
+__global__ void dwconv7_kernel(const float* __restrict__ x, const float* __restrict__ w /*[7][C]*/, const float* __restrict__ b,
+                               int C, int T, size_t total, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ch = (int)(i % C);
+    const size_t m = i / C;
+    const int t = (int)(m % T);
+    float acc = b[ch];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+      const int sh = 6 - k;
+      if (t - sh >= 0) acc = fmaf(x[i - (size_t)sh * C], w[k * C + ch], acc);
+    }
+    y[i] = acc;
+  }
+}
+void launch_dwconv7(const LaunchCtx& c, const float* x, const float* w, const float* b, int C, int T, size_t rows, float* y) {
+  const size_t total = rows * C;
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  dwconv7_kernel<<<blocks, 256, 0, c.stream>>>(x, w, b, C, T, total, y);
+  c.tick();
+}
+
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int C, const float* __restrict__ w,
+                                                        const float* __restrict__ b, float eps, float* __restrict__ y) {
+  __shared__ float red[8], red2[8];
+  const float* xr = x + (size_t)blockIdx.x * C;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) s += xr[i];
+  s = warp_sum_c(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float mean = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) mean += red[i];
+  mean /= (float)C;
+  float v = 0.f;
+  for (int i = threadIdx.x; i < C; i += 256) { const float d = xr[i] - mean; v += d * d; }
+  v = warp_sum_c(v);
+  if ((threadIdx.x & 31) == 0) red2[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) var += red2[i];
+  const float inv = rsqrtf(var / (float)C + eps);
+  float* yr = y + (size_t)blockIdx.x * C;
+  for (int i = threadIdx.x; i < C; i += 256) yr[i] = (xr[i] - mean) * inv * w[i] + b[i];
+}
+void launch_layernorm(const LaunchCtx& c, const float* x, int rows, int C, const float* w, const float* b, float eps, float* y) {
+  if (rows <= 0) return;
+  layernorm_kernel<<<rows, 256, 0, c.stream>>>(x, C, w, b, eps, y);
+  c.tick();
+}
+
+__global__ void silu_mul_kernel(const float* __restrict__ gu, int I, size_t total, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / I;
+    const int j = (int)(i % I);
+    const float g = gu[m * 2 * I + j], u = gu[m * 2 * I + I + j];
+    y[i] = (g / (1.0f + expf(-g))) * u;
+  }
+}
+void launch_silu_mul(const LaunchCtx& c, const float* gu, size_t rows, int I, float* y) {
+  const size_t total = rows * I;
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  silu_mul_kernel<<<blocks, 256, 0, c.stream>>>(gu, I, total, y);
+  c.tick();
+}
+
+// RoPE of the codec transformer: head_dim 64, positions restart at 0 in every window (SpeechTokenizer.swift:469-472, 304-317)
+__global__ void codec_rope_kernel(float* __restrict__ qkv, int ld, int M, int T, int n_rot_heads, const float* __restrict__ inv_freq) {
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= M * n_rot_heads) return;
+  const int m = gw / n_rot_heads, h = gw - m * n_rot_heads, lane = threadIdx.x & 31;
+  float* p = qkv + (size_t)m * ld + (size_t)h * 64;
+  const float ang = (float)(m % T) * inv_freq[lane];
+  float s, co;
+  sincosf(ang, &s, &co);
+  const float a = p[lane], b = p[lane + 32];
+  p[lane] = a * co - b * s;
+  p[lane + 32] = b * co + a * s;
+}
+void launch_codec_rope(const LaunchCtx& c, float* qkv, int ld, int M, int T, int n_rot_heads, const float* inv_freq) {
+  const int warps = M * n_rot_heads;
+  if (warps <= 0) return;
+  codec_rope_kernel<<<(warps + 3) / 4, 128, 0, c.stream>>>(qkv, ld, M, T, n_rot_heads, inv_freq);
+  c.tick();
+}
+
+// Full-causal MHA, head_dim 64, online softmax; grid (q tiles of 16, heads, batch), 4 warps x 4 query rows.
+__global__ void __launch_bounds__(128) codec_attention_kernel(const float* __restrict__ qkv, int ld, int T, int nh, int nkv, float scale,
+                                                              float* __restrict__ out, int ldo) {
+  __shared__ float Ks[32][65];
+  __shared__ float Vs[32][64];
+  __shared__ float Qs[16][64];
+  const int r0 = blockIdx.x * 16, h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (nh / nkv);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* base = qkv + (size_t)b * T * ld;
+  for (int i = tid; i < 16 * 64; i += 128) {
+    const int r = i >> 6, d = i & 63;
+    Qs[r][d] = (r0 + r < T) ? base[(size_t)(r0 + r) * ld + h * 64 + d] : 0.f;
+  }
+  float mi[4], li[4], acc[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { mi[i] = -INFINITY; li[i] = 0.f; acc[i][0] = acc[i][1] = 0.f; }
+  const int koff = nh * 64 + kvh * 64, voff = nh * 64 + nkv * 64 + kvh * 64;
+  const int last = min(T, r0 + 16);
+  for (int kt = 0; kt < last; kt += 32) {
+    __syncthreads();
+    for (int i = tid; i < 32 * 64; i += 128) {
+      const int r = i >> 6, d = i & 63;
+      const bool ok = kt + r < T;
+      Ks[r][d] = ok ? base[(size_t)(kt + r) * ld + koff + d] : 0.f;
+      Vs[r][d] = ok ? base[(size_t)(kt + r) * ld + voff + d] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int rl = warp * 4 + i, row = r0 + rl;
+      if (row >= T) continue;
+      float s = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < 64; ++d) s = fmaf(Qs[rl][d], Ks[lane][d], s);
+      const int j = kt + lane;
+      s = (j <= row && j < T) ? s * scale : -INFINITY;
+      const float mt = warp_max_c(s);
+      const float mnew = fmaxf(mi[i], mt);
+      if (mnew == -INFINITY) continue;  // whole tile masked for this row
+      const float p = (s == -INFINITY) ? 0.f : expf(s - mnew);
+      const float corr = (mi[i] == -INFINITY) ? 0.f : expf(mi[i] - mnew);
+      li[i] = li[i] * corr + warp_sum_c(p);
+      float a0 = acc[i][0] * corr, a1 = acc[i][1] * corr;
+#pragma unroll 8
+      for (int jj = 0; jj < 32; ++jj) {
+        const float pj = __shfl_sync(0xffffffffu, p, jj);
+        a0 = fmaf(pj, Vs[jj][lane], a0);
+        a1 = fmaf(pj, Vs[jj][lane + 32], a1);
+      }
+      acc[i][0] = a0; acc[i][1] = a1;
+      mi[i] = mnew;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = r0 + warp * 4 + i;
+    if (row >= T) continue;
+    float* o = out + ((size_t)b * T + row) * ldo + h * 64;
+    o[lane] = acc[i][0] / li[i];
+    o[lane + 32] = acc[i][1] / li[i];
+  }
+}
+void launch_codec_attention(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo) {
+  if (B <= 0 || T <= 0) return;
+  dim3 grid((T + 15) / 16, nh, B);
+  codec_attention_kernel<<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
+  c.tick();
+}
+
+// code -> embedding gather-sum in codebook order, fp32 adds (bit-exact contract).  emb [M][2*D] = [first | rest].
+__global__ void rvq_embed_kernel(const int* __restrict__ codes, const float* const* __restrict__ codebooks, int Q, int n_sem, int D,
+                                 int size, int M, float* __restrict__ emb) {
+  const int m = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float first = 0.f, rest = 0.f;
+    for (int q = 0; q < Q; ++q) {
+      int code = codes[(size_t)m * Q + q];
+      code = min(max(code, 0), size - 1);
+      const float v = codebooks[q][(size_t)code * D + d];
+      if (q < n_sem) first = __fadd_rn(first, v);
+      else rest = __fadd_rn(rest, v);
+    }
+    emb[(size_t)m * 2 * D + d] = first;
+    emb[(size_t)m * 2 * D + D + d] = rest;
+  }
+}
+void launch_rvq_embed(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
+                      float* emb) {
+  if (M <= 0) return;
+  rvq_embed_kernel<<<M, 128, 0, c.stream>>>(codes, codebooks, Q, n_sem, D, size, M, emb);
+  c.tick();
+}
+
+// DecoderOutputConv (k = 7, C -> 1) + clip(-1, 1) (SpeechTokenizer.swift:823-840, 951); x is already snake-activated.
+__global__ void __launch_bounds__(128) out_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[7][C]*/,
+                                                       const float* __restrict__ bias, int C, int T, float* __restrict__ y) {
+  extern __shared__ float xs[];  // [(128 + 6)][C + 1]  (+1: consecutive threads read consecutive rows)
+  const int b = blockIdx.y, t0 = blockIdx.x * 128;
+  const float* xb = x + (size_t)b * T * C;
+  const int rows = 134, ldc = C + 1;
+  for (int i = threadIdx.x; i < rows * C; i += 128) {
+    const int r = i / C, ch = i - r * C;
+    const int t = t0 - 6 + r;
+    xs[r * ldc + ch] = (t >= 0 && t < T) ? xb[(size_t)t * C + ch] : 0.f;
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= T) return;
+  float acc = bias[0];
+  for (int k = 0; k < 7; ++k) {
+    const float* xr = xs + (size_t)(threadIdx.x + k) * ldc;
+    const float* wr = w + (size_t)k * C;
+    for (int ch = 0; ch < C; ++ch) acc = fmaf(xr[ch], wr[ch], acc);
+  }
+  y[(size_t)b * T + t] = fminf(1.0f, fmaxf(-1.0f, acc));
+}
+void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y) {
+  if (B <= 0 || T <= 0) return;
+  dim3 grid((T + 127) / 128, B);
+  out_conv_kernel<<<grid, 128, (size_t)134 * (C + 1) * sizeof(float), c.stream>>>(x, w, bias, C, T, y);
+  c.tick();
+}
+
+void init_codec_kernels() {
+  Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+}
+
+}  // namespace q3

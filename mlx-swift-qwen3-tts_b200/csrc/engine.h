@@ -1,0 +1,135 @@
+// The handle behind the C ABI: talker engine (slots, KV rings, frame-step graphs) + codec decoder.
+#pragma once
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+namespace q3 {
+
+class CodecDecoder;  // codec.h
+
+struct EngineOptions {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int max_batch = 1, kv_capacity = 512, max_frames = 2400, use_cuda_graph = 1;
+  int load_codec = 1, load_talker = 1, codec_max_frames = 2400, codec_max_batch = 8;
+  int max_trailing = 1024;
+};
+
+// Result of admitting one request into a slot.
+struct Admission {
+  bool too_short = false;  // < 9 text ids: the reference returns [] (Model/Qwen3Talker.swift:348-352)
+  int prefill_len = 0;
+};
+
+class TalkerEngine {
+ public:
+  TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
+               LaunchCounter* counter);
+  ~TalkerEngine();
+
+  // Prompt assembly + prefill of `req` into `slot` (Model/Qwen3Talker.swift:344-462).
+  Admission admit(int slot, const q3tts_request& req);
+  // Run `n` frame steps for slots [0, n_slots) — CUDA-graph replay when enabled.
+  void run_frames(int n_slots, int n);
+  // Read back slot states (synchronises the stream).
+  void fetch_states(int n_slots, std::vector<SlotState>& out);
+  // Copy raw frames [first, first+count) of `slot` into host memory (synchronises).
+  void fetch_frames(int slot, int first, int count, int32_t* dst);
+  void fetch_logits(int frames, float* code0_out, float* cp_out);
+  void release(int slot);
+  void drop_graphs();
+
+  const TalkerConfig& config() const { return cfg_; }
+  const TalkerWeights& weights() const { return w_; }
+  int max_batch() const { return opt_.max_batch; }
+  int kv_capacity() const { return opt_.kv_capacity; }
+  int max_frames() const { return opt_.max_frames; }
+  int weight_dtype() const { return weight_dtype_; }
+  int quant_bits() const { return eff_bits_; }
+  int quant_group() const { return eff_group_; }
+  size_t device_bytes() const { return arena_.total(); }
+  size_t weight_bytes_per_frame() const { return w_.talker_step_bytes + 15 * w_.cp_pass_bytes; }
+  int64_t graph_replays = 0, graph_nodes_replayed = 0;
+  double last_prefill_ms = 0;
+
+  // probe used by q3tts_sample_token
+  int sample_probe(const float* logits, int vocab, float temperature, int top_k, float top_p, float rep_penalty,
+                   const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter);
+
+ private:
+  void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
+                     const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity);
+  void issue_frame(int n_slots);
+  LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
+
+  TalkerConfig cfg_;
+  EngineOptions opt_;
+  cudaStream_t stream_;
+  LaunchCounter* counter_;
+  DeviceArena arena_;
+  TalkerWeights w_;
+  int weight_dtype_ = Q3TTS_BF16, eff_bits_ = 0, eff_group_ = 64;
+
+  int max_rows_ = 0, max_tp_rows_ = 0, set_words_ = 0;
+  // device buffers
+  float *kcache_ = nullptr, *vcache_ = nullptr, *cp_k_ = nullptr, *cp_v_ = nullptr;
+  size_t kv_slot_stride_ = 0, kv_layer_stride_ = 0, cpkv_slot_stride_ = 0, cpkv_layer_stride_ = 0;
+  static constexpr int kCpCapacity = 32;
+  SlotState* d_state_ = nullptr;
+  int *d_step_slot_ = nullptr, *d_step_pos_ = nullptr, *d_win_ = nullptr;
+  int *d_cp_slot2_ = nullptr, *d_cp_pos2_ = nullptr, *d_iota_ = nullptr, *d_cp_pos_ = nullptr;  // cp_pos [16][B]
+  int *d_pf_slot_ = nullptr, *d_pf_pos_ = nullptr, *d_pf_win_ = nullptr;
+  float *d_x_ = nullptr, *d_qkv_ = nullptr, *d_attn_ = nullptr, *d_act_ = nullptr;
+  float *d_hlast_ = nullptr, *d_logits0_ = nullptr, *d_cplogits_ = nullptr, *d_cpin_ = nullptr, *d_cpx_ = nullptr, *d_xstep_ = nullptr;
+  int *d_cur_codes_ = nullptr, *d_frames_ = nullptr, *d_forced_ = nullptr;
+  unsigned* d_sets_ = nullptr;
+  float *d_trailing_ = nullptr, *d_tts_ = nullptr;  // tts rows: bos, eos, pad
+  float *d_tpe_ = nullptr, *d_tph_ = nullptr, *d_tp_ = nullptr, *d_spk_ = nullptr;
+  int *d_ids_ = nullptr, *d_desc_ = nullptr;
+  Embedding* d_cp_emb_ = nullptr;
+  float *d_inv_freq_ = nullptr, *d_cp_inv_freq_ = nullptr;
+  float *d_dump0_ = nullptr, *d_dumpcp_ = nullptr;  // logits dumps of slot 0 (allocated on first use)
+  int dump_cap_ = 0;
+  bool dump_enabled_ = false;
+  float* d_probe_logits_ = nullptr;
+  unsigned* d_probe_set_ = nullptr;
+  int* d_probe_out_ = nullptr;
+  // pinned staging
+  int* h_stage_ = nullptr;
+  size_t h_stage_ints_ = 0;
+  SlotState* h_state_ = nullptr;
+  cudaEvent_t ev_a_ = nullptr, ev_b_ = nullptr;
+
+  struct Graph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t nodes = 0;
+  };
+  std::map<int, Graph> graphs_;  // key: n_slots * 2 + dump_enabled
+};
+
+struct Handle {
+  std::mutex mu;
+  std::string last_error;
+  EngineOptions opt;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  LaunchCounter counter;
+  TalkerConfig cfg;
+  bool has_talker = false;
+  std::unique_ptr<TalkerEngine> talker;
+  std::unique_ptr<CodecDecoder> codec;
+  q3tts_timing timing{};
+  cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+  float* h_pcm = nullptr;  // pinned staging for PCM read-back
+  size_t h_pcm_floats = 0;
+  int32_t* h_codes = nullptr;
+  size_t h_codes_ints = 0;
+  ~Handle();
+};
+
+}  // namespace q3

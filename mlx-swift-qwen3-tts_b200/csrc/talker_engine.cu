@@ -1,0 +1,418 @@
+// Talker engine: slot state in HBM, KV rings, prompt assembly + prefill, and the device-resident frame step
+// (code0 sample -> 15 code-predictor passes -> frame finalize -> talker step) replayed as one CUDA graph so the 16
+// host syncs per frame of the reference loop (Model/Qwen3Talker.swift:482, 520) disappear.
+#include <algorithm>
+#include <cmath>
+
+#include "engine.h"
+
+namespace q3 {
+
+void init_talker_kernels();  // talker_kernels.cu: opt-in shared-memory attributes, once per device
+
+TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
+                           LaunchCounter* counter)
+    : cfg_(cfg), opt_(opt), stream_(stream), counter_(counter) {
+  init_talker_kernels();
+  load_talker_weights(model_dir, cfg_, arena_, stream_, w_, weight_dtype_, eff_bits_, eff_group_);
+  const int B = opt_.max_batch, C = opt_.kv_capacity, F = opt_.max_frames;
+  const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size;
+  Q3_CHECK(B >= 1 && C >= 208 && F >= 1, Q3TTS_ERR_INVALID_ARG, "bad options: max_batch %d kv_capacity %d max_frames %d", B, C, F);
+  const StackWeights &T = w_.talker, &P = w_.cp;
+  max_rows_ = std::max(2 * B, C);
+  max_tp_rows_ = C + opt_.max_trailing + 8;
+  set_words_ = (std::max(cfg_.vocab_size, cfg_.cp.vocab_size) + 31) / 32;
+
+  kv_layer_stride_ = (size_t)T.kv_heads * C * 128;
+  kv_slot_stride_ = kv_layer_stride_ * T.layers;
+  kcache_ = arena_.alloc_n<float>(kv_slot_stride_ * B);
+  vcache_ = arena_.alloc_n<float>(kv_slot_stride_ * B);
+  cpkv_layer_stride_ = (size_t)P.kv_heads * kCpCapacity * 128;
+  cpkv_slot_stride_ = cpkv_layer_stride_ * P.layers;
+  cp_k_ = arena_.alloc_n<float>(cpkv_slot_stride_ * B);
+  cp_v_ = arena_.alloc_n<float>(cpkv_slot_stride_ * B);
+
+  d_state_ = arena_.alloc_n<SlotState>(B);
+  Q3_CUDA(cudaMemsetAsync(d_state_, 0, sizeof(SlotState) * B, stream_));
+  d_step_slot_ = arena_.alloc_n<int>(B); d_step_pos_ = arena_.alloc_n<int>(B); d_win_ = arena_.alloc_n<int>(B);
+  d_cp_slot2_ = arena_.alloc_n<int>(2 * B); d_cp_pos2_ = arena_.alloc_n<int>(2 * B);
+  d_iota_ = arena_.alloc_n<int>(B); d_cp_pos_ = arena_.alloc_n<int>(16 * B);
+  d_pf_slot_ = arena_.alloc_n<int>(C); d_pf_pos_ = arena_.alloc_n<int>(C); d_pf_win_ = arena_.alloc_n<int>(B);
+  Q3_CUDA(cudaMemsetAsync(d_pf_win_, 0, sizeof(int) * B, stream_));
+  Q3_CUDA(cudaMemsetAsync(d_win_, 0, sizeof(int) * B, stream_));
+
+  const int wide_h = std::max(H, Hcp);
+  const int qkv_w = std::max((T.heads + 2 * T.kv_heads) * 128, (P.heads + 2 * P.kv_heads) * 128);
+  const int attn_w = std::max(T.heads, P.heads) * 128;
+  const int act_w = std::max(T.inter, P.inter);
+  d_x_ = arena_.alloc_n<float>((size_t)max_rows_ * wide_h);
+  d_qkv_ = arena_.alloc_n<float>((size_t)max_rows_ * qkv_w);
+  d_attn_ = arena_.alloc_n<float>((size_t)max_rows_ * attn_w);
+  d_act_ = arena_.alloc_n<float>((size_t)max_rows_ * act_w);
+  d_hlast_ = arena_.alloc_n<float>((size_t)B * H);
+  d_logits0_ = arena_.alloc_n<float>((size_t)B * cfg_.vocab_size);
+  d_cplogits_ = arena_.alloc_n<float>((size_t)B * cfg_.cp.vocab_size);
+  d_cpin_ = arena_.alloc_n<float>((size_t)2 * B * H);
+  d_cpx_ = arena_.alloc_n<float>((size_t)2 * B * Hcp);
+  d_xstep_ = arena_.alloc_n<float>((size_t)B * H);
+  d_cur_codes_ = arena_.alloc_n<int>((size_t)B * 16);
+  Q3_CUDA(cudaMemsetAsync(d_cur_codes_, 0, sizeof(int) * B * 16, stream_));
+  d_frames_ = arena_.alloc_n<int>((size_t)B * F * 16);
+  d_forced_ = arena_.alloc_n<int>((size_t)B * F * 16);
+  d_sets_ = arena_.alloc_n<unsigned>((size_t)B * 16 * set_words_);
+  d_trailing_ = arena_.alloc_n<float>((size_t)B * opt_.max_trailing * H);
+  d_tts_ = arena_.alloc_n<float>((size_t)3 * H);
+  d_tpe_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * cfg_.text_hidden_size);
+  d_tph_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * cfg_.text_hidden_size);
+  d_tp_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * H);
+  d_spk_ = arena_.alloc_n<float>(H);
+  d_ids_ = arena_.alloc_n<int>(max_tp_rows_);
+  d_desc_ = arena_.alloc_n<int>((size_t)3 * C);
+  d_probe_logits_ = arena_.alloc_n<float>(4096);
+  d_probe_set_ = arena_.alloc_n<unsigned>(128);
+  d_probe_out_ = arena_.alloc_n<int>(1);
+
+  // static row metadata for the code-predictor passes
+  std::vector<int> slot2(2 * B), pos2(2 * B), iota(B), cpos(16 * B);
+  for (int s = 0; s < B; ++s) {
+    slot2[2 * s] = slot2[2 * s + 1] = s;
+    pos2[2 * s] = 0; pos2[2 * s + 1] = 1;
+    iota[s] = s;
+    for (int g = 0; g < 16; ++g) cpos[g * B + s] = g + 1;
+  }
+  Q3_CUDA(cudaMemcpy(d_cp_slot2_, slot2.data(), slot2.size() * 4, cudaMemcpyHostToDevice));
+  Q3_CUDA(cudaMemcpy(d_cp_pos2_, pos2.data(), pos2.size() * 4, cudaMemcpyHostToDevice));
+  Q3_CUDA(cudaMemcpy(d_iota_, iota.data(), iota.size() * 4, cudaMemcpyHostToDevice));
+  Q3_CUDA(cudaMemcpy(d_cp_pos_, cpos.data(), cpos.size() * 4, cudaMemcpyHostToDevice));
+
+  // inv_freq = 1 / pow(base, Float(2i) / Float(dim))  in fp32 (Model/Qwen3Layers.swift:45; Qwen3CodePredictor.swift:16)
+  std::vector<float> f(64), fc(64);
+  for (int i = 0; i < 64; ++i) {
+    f[i] = 1.0f / powf(cfg_.rope_theta, (float)(2 * i) / 128.0f);
+    fc[i] = 1.0f / powf(cfg_.cp.rope_theta, (float)(2 * i) / 128.0f);
+  }
+  d_inv_freq_ = arena_.alloc_n<float>(64); d_cp_inv_freq_ = arena_.alloc_n<float>(64);
+  Q3_CUDA(cudaMemcpy(d_inv_freq_, f.data(), 256, cudaMemcpyHostToDevice));
+  Q3_CUDA(cudaMemcpy(d_cp_inv_freq_, fc.data(), 256, cudaMemcpyHostToDevice));
+
+  d_cp_emb_ = arena_.alloc_n<Embedding>(15);
+  Q3_CUDA(cudaMemcpy(d_cp_emb_, w_.cp_codec_embedding.data(), sizeof(Embedding) * 15, cudaMemcpyHostToDevice));
+
+  h_stage_ints_ = (size_t)max_tp_rows_ + 3 * (size_t)C + 64;
+  Q3_CUDA(cudaMallocHost(&h_stage_, h_stage_ints_ * sizeof(int)));
+  Q3_CUDA(cudaMallocHost(&h_state_, sizeof(SlotState) * B));
+  Q3_CUDA(cudaEventCreate(&ev_a_));
+  Q3_CUDA(cudaEventCreate(&ev_b_));
+
+  // tts_{bos,eos,pad} rows through text_projection(text_embedding(.)) (Model/Qwen3Talker.swift:354-358)
+  h_stage_[0] = cfg_.tts_bos_token_id; h_stage_[1] = cfg_.tts_eos_token_id; h_stage_[2] = cfg_.tts_pad_token_id;
+  for (int i = 0; i < 3; ++i)
+    Q3_CHECK(h_stage_[i] >= 0 && h_stage_[i] < cfg_.text_vocab_size, Q3TTS_ERR_BAD_CONFIG, "tts special token id %d outside text vocab", h_stage_[i]);
+  Q3_CUDA(cudaMemcpyAsync(d_ids_, h_stage_, 12, cudaMemcpyHostToDevice, stream_));
+  LaunchCtx c{stream_, nullptr};
+  launch_gather_rows(c, w_.text_embedding, d_ids_, 3, d_tpe_, cfg_.text_hidden_size, false);
+  launch_linear(c, w_.fc1, d_tpe_, cfg_.text_hidden_size, 3, d_tph_, cfg_.text_hidden_size, nullptr, 0.f, EPI_SILU);
+  launch_linear(c, w_.fc2, d_tph_, cfg_.text_hidden_size, 3, d_tts_, H, nullptr, 0.f, EPI_STORE);
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+}
+
+TalkerEngine::~TalkerEngine() {
+  drop_graphs();
+  if (h_stage_) cudaFreeHost(h_stage_);
+  if (h_state_) cudaFreeHost(h_state_);
+  if (ev_a_) cudaEventDestroy(ev_a_);
+  if (ev_b_) cudaEventDestroy(ev_b_);
+  if (d_dump0_) cudaFree(d_dump0_);
+  if (d_dumpcp_) cudaFree(d_dumpcp_);
+}
+
+void TalkerEngine::drop_graphs() {
+  for (auto& g : graphs_)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  graphs_.clear();
+}
+
+// Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
+void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
+                                 const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
+                                 size_t layer_stride, int capacity) {
+  const LaunchCtx c = ctx();
+  const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
+  for (int l = 0; l < S.layers; ++l) {
+    const LayerWeights& L = S.layer[l];
+    KVLayout kv;
+    kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
+    launch_linear(c, L.qkv, x, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
+    launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
+                               row_pos, kv);
+    launch_attention(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, d_attn_, attn_ld);
+    launch_linear(c, L.o, d_attn_, attn_ld, m, x, S.hidden, nullptr, 0.f, EPI_ADD);
+    launch_linear(c, L.gate_up, x, S.hidden, m, d_act_, S.inter, L.post_norm, S.eps, EPI_SWIGLU);
+    launch_linear(c, L.down, d_act_, S.inter, m, x, S.hidden, nullptr, 0.f, EPI_ADD);
+  }
+}
+
+Admission TalkerEngine::admit(int slot, const q3tts_request& r) {
+  Admission adm;
+  const int H = cfg_.hidden_size, C = opt_.kv_capacity, F = opt_.max_frames, TH = cfg_.text_hidden_size;
+  Q3_CHECK(slot >= 0 && slot < opt_.max_batch, Q3TTS_ERR_INVALID_ARG, "slot %d out of range", slot);
+  Q3_CHECK(r.text_ids != nullptr || r.n_text_ids == 0, Q3TTS_ERR_INVALID_ARG, "text_ids is NULL");
+  if (r.n_text_ids < 9) {  // minTokens (Model/Qwen3Talker.swift:348-352)
+    adm.too_short = true;
+    return adm;
+  }
+  auto check_text = [&](const int32_t* ids, int n, const char* what) {
+    for (int i = 0; i < n; ++i)
+      Q3_CHECK(ids[i] >= 0 && ids[i] < cfg_.text_vocab_size, Q3TTS_ERR_INVALID_ARG, "%s id %d outside the text vocabulary", what, ids[i]);
+  };
+  check_text(r.text_ids, r.n_text_ids, "text");
+  const bool has_instruct = r.instruct_ids != nullptr && r.n_instruct_ids > 0;
+  const bool use_icl = !has_instruct && r.ref_codes != nullptr && r.ref_text_ids != nullptr && r.n_ref_text_ids > 0;  // :338, 395
+  if (has_instruct) check_text(r.instruct_ids, r.n_instruct_ids, "instruct");
+  if (use_icl) check_text(r.ref_text_ids, r.n_ref_text_ids, "reference transcript");
+  const bool spk_by_id = r.speaker_id >= 0;
+  const bool spk_by_vec = !spk_by_id && r.speaker_embedding != nullptr;
+  if (spk_by_id) Q3_CHECK(r.speaker_id < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "speaker_id %d outside codec vocabulary", r.speaker_id);
+  if (spk_by_vec) Q3_CHECK(r.speaker_embedding_dim == H, Q3TTS_ERR_INVALID_ARG, "speaker embedding has %d dims, model hidden size is %d", r.speaker_embedding_dim, H);
+
+  // --- text rows to project: [tts_bos, tts_eos, tts_pad, instruct|ref-text..., role(3), first text, trailing...]
+  int* ids = h_stage_;
+  int n_tp = 0;
+  ids[n_tp++] = cfg_.tts_bos_token_id; ids[n_tp++] = cfg_.tts_eos_token_id; ids[n_tp++] = cfg_.tts_pad_token_id;
+  const int TP_BOS = 0, TP_EOS = 1, TP_PAD = 2;
+  const int n_front_text = has_instruct ? r.n_instruct_ids : (use_icl ? r.n_ref_text_ids : 0);
+  const int n_ref_audio = (use_icl && r.ref_frames > 0) ? r.ref_frames : 0;
+  const int trailing_len = r.n_text_ids - 4 - 5;  // :426
+  const int n_trailing = trailing_len > 0 ? trailing_len : 0;
+  Q3_CHECK(3 + n_front_text + 4 + n_trailing <= max_tp_rows_, Q3TTS_ERR_CAPACITY, "prompt too long for this handle (text rows %d > %d)",
+           3 + n_front_text + 4 + n_trailing, max_tp_rows_);
+  Q3_CHECK(n_trailing + 1 <= opt_.max_trailing, Q3TTS_ERR_CAPACITY, "text too long: %d trailing tokens > %d", n_trailing + 1, opt_.max_trailing);
+  const int tp_front = n_tp;
+  for (int i = 0; i < n_front_text; ++i) ids[n_tp++] = has_instruct ? r.instruct_ids[i] : r.ref_text_ids[i];
+  const int tp_role = n_tp;
+  for (int i = 0; i < 3; ++i) ids[n_tp++] = r.text_ids[i];
+  const int tp_first = n_tp;
+  ids[n_tp++] = r.text_ids[3];
+  const int tp_trailing = n_tp;
+  for (int i = 0; i < n_trailing; ++i) ids[n_tp++] = r.text_ids[4 + i];
+
+  // --- prefill row descriptors (tp index, codec row, speaker flag)
+  int* desc = h_stage_ + max_tp_rows_;
+  int P = 0;
+  auto row = [&](int tp, int codec, int spk) { desc[3 * P] = tp; desc[3 * P + 1] = codec; desc[3 * P + 2] = spk; ++P; };
+  const int n_codec = 5 + ((spk_by_id || spk_by_vec) ? 1 : 0);
+  const int P_total = n_front_text + n_ref_audio + 3 + (n_codec - 1) + 1;
+  Q3_CHECK(P_total <= C - 16, Q3TTS_ERR_CAPACITY, "prefill of %d positions exceeds kv_capacity %d - 16; raise q3tts_options.kv_capacity", P_total, C);
+  for (int i = 0; i < n_front_text; ++i) row(tp_front + i, -1, 0);
+  for (int i = 0; i < n_ref_audio; ++i) {  // codec_embedding(refCodes[0]) — first codebook only (:402-403)
+    const int code = r.ref_codes[i];
+    Q3_CHECK(code >= 0 && code < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "reference code %d outside codec vocabulary", code);
+    row(-1, code, 0);
+  }
+  for (int i = 0; i < 3; ++i) row(tp_role + i, -1, 0);
+  // codecEmbed = [nothink, think_bos, think_eos, (speaker), pad, bos] (:360-379);
+  // combined = [tts_pad x (n-2), tts_bos] + codecEmbed[0 ..< n-1] (:383-386)
+  int codec_ids[6];
+  int codec_spk[6] = {0, 0, 0, 0, 0, 0};
+  int k = 0;
+  codec_ids[k++] = cfg_.codec_nothink_id; codec_ids[k++] = cfg_.codec_think_bos_id; codec_ids[k++] = cfg_.codec_think_eos_id;
+  if (spk_by_id) codec_ids[k++] = r.speaker_id;
+  else if (spk_by_vec) { codec_ids[k] = -1; codec_spk[k] = 1; ++k; }
+  codec_ids[k++] = cfg_.codec_pad_id; codec_ids[k++] = cfg_.codec_bos_id;
+  for (int i = 0; i < n_codec - 1; ++i) row(i < n_codec - 2 ? TP_PAD : TP_BOS, codec_ids[i], codec_spk[i]);
+  row(tp_first, codec_ids[n_codec - 1], 0);  // firstTextEmbed (:423)
+  adm.prefill_len = P;
+
+  const LaunchCtx c = ctx();
+  Q3_CUDA(cudaEventRecord(ev_a_, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_ids_, ids, sizeof(int) * n_tp, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_desc_, desc, sizeof(int) * 3 * P, cudaMemcpyHostToDevice, stream_));
+  if (spk_by_vec) Q3_CUDA(cudaMemcpyAsync(d_spk_, r.speaker_embedding, sizeof(float) * H, cudaMemcpyHostToDevice, stream_));
+  // text_projection(text_embedding(ids)) (Model/Qwen3Talker.swift:103-106; Qwen3Layers.swift:276-279)
+  launch_gather_rows(c, w_.text_embedding, d_ids_, n_tp, d_tpe_, TH, false);
+  launch_linear(c, w_.fc1, d_tpe_, TH, n_tp, d_tph_, TH, nullptr, 0.f, EPI_SILU);
+  launch_linear(c, w_.fc2, d_tph_, TH, n_tp, d_tp_, H, nullptr, 0.f, EPI_STORE);
+  launch_assemble_rows(c, d_tp_, H, w_.codec_embedding, d_spk_, d_desc_, P, d_x_);
+  // trailingTextHidden = textproj(ids[4 ..< len-5]) ++ tts_eos (:426-433)
+  float* tr = d_trailing_ + (size_t)slot * opt_.max_trailing * H;
+  if (n_trailing > 0)
+    Q3_CUDA(cudaMemcpyAsync(tr, d_tp_ + (size_t)tp_trailing * H, sizeof(float) * n_trailing * H, cudaMemcpyDeviceToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(tr + (size_t)n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
+
+  // prefill: rows 0..P-1 of this slot at positions 0..P-1 (Model/Qwen3Talker.swift:437)
+  std::vector<int> meta(2 * P);
+  for (int i = 0; i < P; ++i) { meta[i] = slot; meta[P + i] = i; }
+  // the pinned stage is still being read by the async copies above: use a synchronous pageable copy for the metadata
+  Q3_CUDA(cudaMemcpyAsync(d_pf_slot_, meta.data(), sizeof(int) * P, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_pf_pos_, meta.data() + P, sizeof(int) * P, cudaMemcpyHostToDevice, stream_));
+  forward_stack(w_.talker, d_x_, P, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C);
+  // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
+  launch_rmsnorm(c, d_x_ + (size_t)(P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)slot * H, H);
+  launch_linear(c, w_.codec_head, d_hlast_ + (size_t)slot * H, H, 1, d_logits0_ + (size_t)slot * cfg_.vocab_size, cfg_.vocab_size, nullptr, 0.f, EPI_STORE);
+
+  // teacher forcing / dumps
+  const bool forced = r.forced_codes != nullptr && r.n_forced_frames > 0;
+  if (forced) {
+    Q3_CHECK(r.n_forced_frames <= F, Q3TTS_ERR_CAPACITY, "n_forced_frames %d > max_frames %d", r.n_forced_frames, F);
+    Q3_CUDA(cudaMemcpyAsync(d_forced_ + (size_t)slot * F * 16, r.forced_codes, sizeof(int) * 16 * r.n_forced_frames, cudaMemcpyHostToDevice, stream_));
+  }
+  int logits_cap = 0;
+  if (slot == 0 && (r.code0_logits_out != nullptr || r.cp_logits_out != nullptr) && r.logits_capacity_frames > 0) {
+    logits_cap = std::min(r.logits_capacity_frames, F);
+    if (logits_cap > dump_cap_) {
+      Q3_CUDA(cudaStreamSynchronize(stream_));
+      if (d_dump0_) cudaFree(d_dump0_);
+      if (d_dumpcp_) cudaFree(d_dumpcp_);
+      Q3_CUDA(cudaMalloc(&d_dump0_, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size));
+      Q3_CUDA(cudaMalloc(&d_dumpcp_, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size));
+      dump_cap_ = logits_cap;
+      drop_graphs();  // dump pointers are baked into captured graphs
+    }
+    Q3_CUDA(cudaMemsetAsync(d_dump0_, 0, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size, stream_));
+    Q3_CUDA(cudaMemsetAsync(d_dumpcp_, 0, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size, stream_));
+  }
+  if (slot == 0) dump_enabled_ = logits_cap > 0;
+
+  SlotState s{};
+  s.active = 1;
+  s.pos = P;  // positionOffset = inputEmbeds.shape[1] (:438)
+  s.total_text = n_trailing + 1;
+  s.max_tokens = forced ? r.n_forced_frames : std::min(std::max(r.max_tokens, 0), F);
+  s.n_forced = forced ? r.n_forced_frames : 0;
+  s.stream_variant = r.stream_variant ? 1 : 0;
+  s.top_k = r.top_k;
+  s.logits_cap = logits_cap;
+  s.temperature = r.temperature;
+  s.top_p = (r.top_p > 0.f) ? r.top_p : 1.0f;
+  s.rep_penalty = (r.repetition_penalty > 0.f) ? r.repetition_penalty : 1.0f;
+  s.seed = r.seed;
+  if (s.max_tokens <= 0) s.finished = 1;
+  Q3_CUDA(cudaStreamSynchronize(stream_));  // staging buffers are reused by the next admit
+  h_state_[slot] = s;
+  Q3_CUDA(cudaMemcpyAsync(d_state_ + slot, h_state_ + slot, sizeof(SlotState), cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemsetAsync(d_sets_ + (size_t)slot * 16 * set_words_, 0, sizeof(unsigned) * 16 * set_words_, stream_));
+  Q3_CUDA(cudaEventRecord(ev_b_, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_a_, ev_b_);
+  last_prefill_ms += ms;
+  return adm;
+}
+
+void TalkerEngine::release(int slot) {
+  Q3_CUDA(cudaMemsetAsync(d_state_ + slot, 0, sizeof(SlotState), stream_));
+}
+
+// One 12.5 Hz frame for slots [0, n_slots): the loop body of Model/Qwen3Talker.swift:464-562 with every decision on device.
+void TalkerEngine::issue_frame(int n_slots) {
+  const LaunchCtx c = ctx();
+  const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size, V = cfg_.vocab_size, Vc = cfg_.cp.vocab_size;
+  const int B = opt_.max_batch, F = opt_.max_frames;
+  SamplerParams p{};
+  p.vocab = V; p.group = 0; p.codec_vocab = V; p.eos_id = cfg_.codec_eos_token_id; p.pad_id = cfg_.codec_pad_id;
+  p.groups = 16; p.set_words = set_words_;
+  float* dump0 = dump_enabled_ ? d_dump0_ : nullptr;
+  float* dumpcp = dump_enabled_ ? d_dumpcp_ : nullptr;
+  launch_sample(c, d_logits0_, V, n_slots, d_state_, p, d_sets_, d_cur_codes_, d_forced_, F, dump0, V, 0, 0);
+  for (int g = 0; g < 15; ++g) {  // code predictor, strictly sequential (:501-523)
+    launch_cp_input(c, g, n_slots, d_hlast_, H, w_.codec_embedding, d_cp_emb_, d_cur_codes_, d_cpin_);
+    const int m = g == 0 ? 2 * n_slots : n_slots;
+    float* x = d_cpin_;
+    if (w_.has_mtp) {  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
+      launch_linear(c, w_.small_to_mtp, d_cpin_, H, m, d_cpx_, Hcp, nullptr, 0.f, EPI_STORE);
+      x = d_cpx_;
+    }
+    forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
+                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity);
+    // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
+    if (g == 0) launch_linear(c, w_.lm_head[0], x + Hcp, 2 * Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
+    else launch_linear(c, w_.lm_head[g], x, Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
+    SamplerParams pg = p;
+    pg.vocab = Vc; pg.group = g + 1;
+    launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, 0);
+  }
+  launch_frame_finalize(c, n_slots, d_state_, d_cur_codes_, d_frames_, F, d_sets_, set_words_, d_trailing_, opt_.max_trailing,
+                        d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_);
+  launch_step_rows(c, n_slots, d_state_, d_step_slot_, d_step_pos_, d_win_);
+  forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
+                kv_layer_stride_, opt_.kv_capacity);
+  launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
+  launch_linear(c, w_.codec_head, d_hlast_, H, n_slots, d_logits0_, V, nullptr, 0.f, EPI_STORE);
+  launch_step_advance(c, n_slots, d_state_, 192);  // maxKVCacheWindow (Model/Qwen3Layers.swift:108)
+}
+
+void TalkerEngine::run_frames(int n_slots, int n) {
+  if (n <= 0 || n_slots <= 0) return;
+  if (!opt_.use_cuda_graph) {
+    for (int i = 0; i < n; ++i) issue_frame(n_slots);
+    return;
+  }
+  const int key = n_slots * 2 + (dump_enabled_ ? 1 : 0);
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    cudaGraph_t g = nullptr;
+    if (counter_) { counter_->capturing = true; counter_->captured = 0; }
+    Q3_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      issue_frame(n_slots);
+    } catch (...) {
+      cudaStreamEndCapture(stream_, &g);
+      if (g) cudaGraphDestroy(g);
+      if (counter_) counter_->capturing = false;
+      throw;
+    }
+    cudaError_t e = cudaStreamEndCapture(stream_, &g);
+    if (counter_) counter_->capturing = false;
+    if (e != cudaSuccess) fail(Q3TTS_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    Graph gr;
+    gr.nodes = counter_ ? counter_->captured : 0;
+    e = cudaGraphInstantiate(&gr.exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) fail(Q3TTS_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    it = graphs_.emplace(key, gr).first;
+  }
+  for (int i = 0; i < n; ++i) {
+    Q3_CUDA(cudaGraphLaunch(it->second.exec, stream_));
+    if (counter_) counter_->n += it->second.nodes;
+    ++graph_replays;
+  }
+}
+
+void TalkerEngine::fetch_states(int n_slots, std::vector<SlotState>& out) {
+  Q3_CUDA(cudaMemcpyAsync(h_state_, d_state_, sizeof(SlotState) * n_slots, cudaMemcpyDeviceToHost, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+  out.assign(h_state_, h_state_ + n_slots);
+}
+
+void TalkerEngine::fetch_frames(int slot, int first, int count, int32_t* dst) {
+  if (count <= 0) return;
+  Q3_CUDA(cudaMemcpyAsync(dst, d_frames_ + ((size_t)slot * opt_.max_frames + first) * 16, sizeof(int) * 16 * count,
+                          cudaMemcpyDeviceToHost, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+}
+
+void TalkerEngine::fetch_logits(int frames, float* code0_out, float* cp_out) {
+  frames = std::min(frames, dump_cap_);
+  if (frames <= 0) return;
+  if (code0_out) Q3_CUDA(cudaMemcpyAsync(code0_out, d_dump0_, sizeof(float) * (size_t)frames * cfg_.vocab_size, cudaMemcpyDeviceToHost, stream_));
+  if (cp_out) Q3_CUDA(cudaMemcpyAsync(cp_out, d_dumpcp_, sizeof(float) * (size_t)frames * 15 * cfg_.cp.vocab_size, cudaMemcpyDeviceToHost, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+}
+
+int TalkerEngine::sample_probe(const float* logits, int vocab, float temperature, int top_k, float top_p, float rep_penalty,
+                               const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter) {
+  Q3_CHECK(vocab > 0 && vocab <= 4096, Q3TTS_ERR_INVALID_ARG, "vocab %d out of range", vocab);
+  std::vector<unsigned> bm(128, 0u);
+  for (int i = 0; i < n_set; ++i)
+    if (token_set[i] >= 0 && token_set[i] < vocab) bm[token_set[i] >> 5] |= 1u << (token_set[i] & 31);
+  Q3_CUDA(cudaMemcpyAsync(d_probe_logits_, logits, sizeof(float) * vocab, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_probe_set_, bm.data(), sizeof(unsigned) * 128, cudaMemcpyHostToDevice, stream_));
+  launch_sample_probe(ctx(), d_probe_logits_, vocab, cfg_.vocab_size, temperature, top_k, top_p > 0.f ? top_p : 1.f,
+                      rep_penalty > 0.f ? rep_penalty : 1.f, n_set > 0 ? d_probe_set_ : nullptr, seed, counter, d_probe_out_);
+  int id = -1;
+  Q3_CUDA(cudaMemcpyAsync(&id, d_probe_out_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+  return id;
+}
+
+}  // namespace q3

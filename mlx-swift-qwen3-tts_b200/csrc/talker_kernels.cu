@@ -1,0 +1,885 @@
+// Hand-written sm_100a kernels for the Qwen3-TTS talker / code-predictor decode path.
+//
+// Everything here is HBM/L2-bandwidth or latency bound (batch-1..8 GEMV, norms, RoPE, window attention, sampling),
+// so the design rules are: 128-bit coalesced loads of the packed weights, activations staged once per CTA in shared
+// memory in a lane-major layout (bank-conflict free float4 reads), warp-shuffle reductions, no integer->float
+// conversion instructions on the dequant path (magic-number bit tricks), and fusion of the RMSNorm prologue and the
+// bias / residual / SiLU / SwiGLU epilogues into the GEMV so a decoder layer is 6 launches.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+
+namespace q3 {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float load_as_f32(const void* p, size_t i, int dt) {
+  if (dt == Q3TTS_F32) return reinterpret_cast<const float*>(p)[i];
+  if (dt == Q3TTS_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {  // weights are read once: keep them out of L1
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ dequantize
+// deq32 = fp32(scale) * q (rounded) + fp32(bias) (rounded) — __fmul_rn/__fadd_rn forbid FMA contraction so the
+// result is bit-identical to the two-rounding contract of the oracle.
+__global__ void dequantize_kernel(const uint32_t* __restrict__ qw, const void* __restrict__ scales,
+                                  const void* __restrict__ biases, int sdt, int out, int in, int group, int bits,
+                                  int out_dt, void* __restrict__ dst) {
+  const int per = 32 / bits;
+  const size_t words = (size_t)out * (in / per);
+  const uint32_t mask = (1u << bits) - 1u;
+  for (size_t wi = (size_t)blockIdx.x * blockDim.x + threadIdx.x; wi < words; wi += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = wi / (in / per);
+    const int col0 = (int)(wi % (in / per)) * per;
+    const uint32_t w = qw[wi];
+    const size_t gi = row * (in / group) + col0 / group;  // `per` divides group: one scale per word
+    const float s = load_as_f32(scales, gi, sdt), b = load_as_f32(biases, gi, sdt);
+    for (int j = 0; j < per; ++j) {
+      const float q = (float)((w >> (j * bits)) & mask);
+      const float v = __fadd_rn(__fmul_rn(s, q), b);
+      const size_t o = row * in + col0 + j;
+      if (out_dt == Q3TTS_F32) reinterpret_cast<float*>(dst)[o] = v;
+      else if (out_dt == Q3TTS_F16) reinterpret_cast<__half*>(dst)[o] = __float2half_rn(v);
+      else reinterpret_cast<__nv_bfloat16*>(dst)[o] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+void launch_dequantize(const LaunchCtx& c, const uint32_t* qw, const void* scales, const void* biases, int sdt, int out,
+                       int in, int group, int bits, int out_dt, void* dst) {
+  const size_t words = (size_t)out * in * bits / 32;
+  int blocks = (int)std::min<size_t>((words + 255) / 256, 148 * 16);
+  if (blocks < 1) blocks = 1;
+  dequantize_kernel<<<blocks, 256, 0, c.stream>>>(qw, scales, biases, sdt, out, in, group, bits, out_dt, dst);
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ GEMV / small-M linear
+enum WFmt { W_Q4 = 0, W_Q8 = 1, W_BF16 = 2, W_F16 = 3, W_F32 = 4 };
+template <int FMT> struct FmtTraits;
+template <> struct FmtTraits<W_Q4> { static constexpr int VPL = 32; };   // values per lane per 16-byte load
+template <> struct FmtTraits<W_Q8> { static constexpr int VPL = 16; };
+template <> struct FmtTraits<W_BF16> { static constexpr int VPL = 8; };
+template <> struct FmtTraits<W_F16> { static constexpr int VPL = 8; };
+template <> struct FmtTraits<W_F32> { static constexpr int VPL = 4; };
+
+// Integer code -> float without I2F (quarter-rate pipe): OR the code into the mantissa of 2^23, subtract 2^23.
+__device__ __forceinline__ float code_to_f32(uint32_t code) { return __uint_as_float(0x4B000000u | code) - 8388608.0f; }
+
+// dot of this lane's VPL weights (one 16-byte load) with its VPL activations (VPL/4 float4 from lane-major smem)
+template <int FMT>
+__device__ __forceinline__ float lane_dot(const uint4& w, const float4* __restrict__ xs /* stride 32 float4 */) {
+  float acc = 0.f;
+  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+  if constexpr (FMT == W_Q4) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 x = xs[j * 32];
+      const uint32_t h = ww[j >> 1] >> ((j & 1) * 16);
+      acc = fmaf(code_to_f32(h & 0xF), x.x, acc);
+      acc = fmaf(code_to_f32((h >> 4) & 0xF), x.y, acc);
+      acc = fmaf(code_to_f32((h >> 8) & 0xF), x.z, acc);
+      acc = fmaf(code_to_f32((h >> 12) & 0xF), x.w, acc);
+    }
+  } else if constexpr (FMT == W_Q8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 x = xs[j * 32];
+      const uint32_t h = ww[j];
+      // __byte_perm places byte k of h into byte 0 of 0x4B0000xx in one PRMT
+      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7440)) - 8388608.0f, x.x, acc);
+      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7441)) - 8388608.0f, x.y, acc);
+      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7442)) - 8388608.0f, x.z, acc);
+      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7443)) - 8388608.0f, x.w, acc);
+    }
+  } else if constexpr (FMT == W_BF16) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float4 x = xs[j * 32];
+      acc = fmaf(__uint_as_float(ww[2 * j] << 16), x.x, acc);
+      acc = fmaf(__uint_as_float(ww[2 * j] & 0xFFFF0000u), x.y, acc);
+      acc = fmaf(__uint_as_float(ww[2 * j + 1] << 16), x.z, acc);
+      acc = fmaf(__uint_as_float(ww[2 * j + 1] & 0xFFFF0000u), x.w, acc);
+    }
+  } else if constexpr (FMT == W_F16) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const float4 x = xs[j * 32];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ww[2 * j]));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ww[2 * j + 1]));
+      acc = fmaf(a.x, x.x, acc);
+      acc = fmaf(a.y, x.y, acc);
+      acc = fmaf(b.x, x.z, acc);
+      acc = fmaf(b.y, x.w, acc);
+    }
+  } else {
+    const float4 x = xs[0];
+    acc = fmaf(__uint_as_float(ww[0]), x.x, acc);
+    acc = fmaf(__uint_as_float(ww[1]), x.y, acc);
+    acc = fmaf(__uint_as_float(ww[2]), x.z, acc);
+    acc = fmaf(__uint_as_float(ww[3]), x.w, acc);
+  }
+  return acc;
+}
+
+struct LinearKArgs {
+  const void* w;        // packed or dense weights, row-major
+  const void* scales;   // quantised only
+  const void* biases;
+  const float* bias;    // [out] or null
+  const float* x;
+  float* y;
+  const float* norm_w;  // fused RMSNorm weight or null
+  float eps;
+  int out, in, group, sdt, m, ldx, ldy, epi;
+};
+
+// Shared-memory layout per CTA:  xs[MT][in/4] float4 in lane-major order,  xsum[MT][in/VPL] (quantised formats).
+// Lane-major: element e of a K-chunk (KC = 32*VPL values) lives at float4 index ((e%VPL)/4)*32 + e/VPL, so the 32
+// lanes of a warp read 32 consecutive float4 — conflict free — while each lane's weights stay one contiguous
+// 16-byte global load.
+template <int FMT, int MT>
+__global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
+  constexpr int VPL = FmtTraits<FMT>::VPL;
+  constexpr int KC = 32 * VPL;
+  constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nchunk = (a.in + KC - 1) / KC;   // the last chunk may be partial (in must be a multiple of VPL)
+  const int xstride = nchunk * (KC / 4);     // float4 per activation row in shared memory (chunk-padded)
+  float4* xs = reinterpret_cast<float4*>(smem_raw);
+  float* xsum = reinterpret_cast<float*>(smem_raw + (size_t)MT * xstride * sizeof(float4));
+  __shared__ float red[MT][8];
+  __shared__ float inv_rms[MT];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.y * MT;
+  const int in4 = a.in >> 2;
+
+  // ---- stage activations (optionally RMS-normalised) ----
+  if (a.norm_w != nullptr) {
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) {
+      float ss = 0.f;
+      if (m0 + mi < a.m) {
+        const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(m0 + mi) * a.ldx);
+        for (int f = tid; f < in4; f += 256) {
+          const float4 v = xr[f];
+          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red[mi][warp] = ss;
+    }
+    __syncthreads();
+    if (tid < MT) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[tid][w];
+      inv_rms[tid] = rsqrtf(s / (float)a.in + a.eps);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < MT; ++mi) {
+    const bool valid = (m0 + mi) < a.m;
+    const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(valid ? m0 + mi : 0) * a.ldx);
+    const float sc = a.norm_w ? inv_rms[mi] : 1.0f;
+    for (int f = tid; f < in4; f += 256) {
+      float4 v = valid ? xr[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.norm_w) {
+        const float4 nw = reinterpret_cast<const float4*>(a.norm_w)[f];
+        v.x = v.x * sc * nw.x; v.y = v.y * sc * nw.y; v.z = v.z * sc * nw.z; v.w = v.w * sc * nw.w;
+      }
+      const int e = f << 2;             // element index
+      const int ch = e / KC, ec = e - ch * KC;
+      const int l = ec / VPL, j = (ec - l * VPL) >> 2;
+      xs[(size_t)mi * xstride + ch * (KC / 4) + j * 32 + l] = v;
+    }
+  }
+  __syncthreads();
+  if constexpr (QUANT) {  // per-lane activation sums (for the group bias term): xsum[mi][chunk][lane]
+    const int nl = nchunk * 32;
+    for (int i = tid; i < MT * nl; i += 256) {
+      const int mi = i / nl, r = i - mi * nl, ch = r >> 5, l = r & 31;
+      float s = 0.f;
+      if (ch * KC + l * VPL < a.in) {
+        const float4* p = xs + (size_t)mi * xstride + ch * (KC / 4) + l;
+#pragma unroll
+        for (int j = 0; j < VPL / 4; ++j) { const float4 v = p[j * 32]; s += (v.x + v.y) + (v.z + v.w); }
+      }
+      xsum[i] = s;
+    }
+    __syncthreads();
+  }
+
+  // ---- stream weight rows: one warp per output row (pair of rows for SwiGLU) ----
+  const int out_eff = (a.epi == EPI_SWIGLU) ? (a.out >> 1) : a.out;
+  const int nsub = (a.epi == EPI_SWIGLU) ? 2 : 1;
+  const size_t row_bytes = QUANT ? (size_t)a.in * (FMT == W_Q4 ? 4 : 8) / 8
+                                 : (size_t)a.in * (FMT == W_F32 ? 4 : 2);
+  const int ngroups = QUANT ? a.in / a.group : 0;
+  for (int r = blockIdx.x * 8 + warp; r < out_eff; r += gridDim.x * 8) {
+    float res[2][MT];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) res[s][mi] = 0.f;
+    }
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      if (s >= nsub) break;
+      const int row = r + s * out_eff;
+      const uint4* wr = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.w) + (size_t)row * row_bytes);
+      float acc[MT];
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) acc[mi] = 0.f;
+      for (int c0 = 0; c0 < nchunk; c0 += 4) {
+        uint4 wv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if ((c0 + u) * KC + lane * VPL < a.in) wv[u] = ldg_stream(wr + (size_t)(c0 + u) * 32 + lane);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if ((c0 + u) * KC + lane * VPL < a.in) {
+            const int ch = c0 + u;
+            float sc = 1.f, bi = 0.f;
+            if constexpr (QUANT) {
+              const size_t gi = (size_t)row * ngroups + (ch * KC + lane * VPL) / a.group;
+              sc = load_as_f32(a.scales, gi, a.sdt);
+              bi = load_as_f32(a.biases, gi, a.sdt);
+            }
+#pragma unroll
+            for (int mi = 0; mi < MT; ++mi) {
+              const float d = lane_dot<FMT>(wv[u], xs + (size_t)mi * xstride + ch * (KC / 4) + lane);
+              if constexpr (QUANT) acc[mi] += sc * d + bi * xsum[mi * (nchunk * 32) + ch * 32 + lane];
+              else acc[mi] += d;
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) res[s][mi] = warp_sum(acc[mi]);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int mi = 0; mi < MT; ++mi) {
+        if (m0 + mi >= a.m) break;
+        float v = res[0][mi];
+        float* yp = a.y + (size_t)(m0 + mi) * a.ldy + r;
+        if (a.epi == EPI_SWIGLU) {
+          float g = v, u = res[1][mi];
+          if (a.bias) { g += a.bias[r]; u += a.bias[r + out_eff]; }
+          *yp = silu_f(g) * u;
+        } else {
+          if (a.bias) v += a.bias[r];
+          if (a.epi == EPI_SILU) v = silu_f(v);
+          if (a.epi == EPI_ADD) v += *yp;
+          *yp = v;
+        }
+      }
+    }
+  }
+}
+
+template <int FMT, int MT>
+static void launch_linear_t(const LaunchCtx& c, const LinearKArgs& a, int num_sms) {
+  constexpr int VPL = FmtTraits<FMT>::VPL;
+  constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
+  constexpr int KC = 32 * VPL;
+  const int nchunk = (a.in + KC - 1) / KC;
+  size_t smem = (size_t)MT * nchunk * KC * sizeof(float) + (QUANT ? (size_t)MT * nchunk * 32 * sizeof(float) : 0);
+  const int out_eff = (a.epi == EPI_SWIGLU) ? a.out / 2 : a.out;
+  int bx = (out_eff + 7) / 8;
+  const int cap = num_sms * 8;
+  if (bx > cap) bx = cap;
+  dim3 grid(bx, (a.m + MT - 1) / MT);
+  linear_kernel<FMT, MT><<<grid, 256, smem, c.stream>>>(a);
+  c.tick();
+}
+
+template <int FMT>
+static void launch_linear_f(const LaunchCtx& c, LinearKArgs a) {
+  // M-tile: largest of {8,4,2,1} not above m whose activation stage fits ~96 KB of shared memory
+  int mt = 8;
+  while (mt > 1 && (mt > a.m * 2 - 1 || (size_t)mt * a.in * 5 > 96 * 1024)) mt >>= 1;
+  if (a.m == 1) mt = 1;
+  switch (mt) {
+    case 8: launch_linear_t<FMT, 8>(c, a, 148); break;
+    case 4: launch_linear_t<FMT, 4>(c, a, 148); break;
+    case 2: launch_linear_t<FMT, 2>(c, a, 148); break;
+    default: launch_linear_t<FMT, 1>(c, a, 148); break;
+  }
+}
+
+void launch_linear(const LaunchCtx& c, const Linear& L, const float* x, int ldx, int m, float* y, int ldy,
+                   const float* norm_w, float eps, int epilogue) {
+  if (m <= 0) return;
+  LinearKArgs a;
+  a.w = L.bits ? (const void*)L.qw : L.w;
+  a.scales = L.scales; a.biases = L.biases; a.bias = L.bias;
+  a.x = x; a.y = y; a.norm_w = norm_w; a.eps = eps;
+  a.out = L.out; a.in = L.in; a.group = L.group; a.sdt = L.sdt; a.m = m; a.ldx = ldx; a.ldy = ldy; a.epi = epilogue;
+  Q3_CHECK((ldx % 4) == 0, Q3TTS_ERR_INVALID_ARG, "linear: activation stride %d not 16-byte aligned", ldx);
+  if (L.bits == 4) {
+    Q3_CHECK(L.in % 32 == 0 && L.group % 32 == 0, Q3TTS_ERR_BAD_CONFIG, "4-bit linear needs in %% 32 == 0 and group %% 32 == 0 (in=%d, group=%d)", L.in, L.group);
+    launch_linear_f<W_Q4>(c, a);
+  } else if (L.bits == 8) {
+    Q3_CHECK(L.in % 16 == 0 && L.group % 16 == 0, Q3TTS_ERR_BAD_CONFIG, "8-bit linear needs in %% 16 == 0 (in=%d)", L.in);
+    launch_linear_f<W_Q8>(c, a);
+  } else if (L.bits == 0) {
+    if (L.sdt == Q3TTS_BF16) { Q3_CHECK(L.in % 8 == 0, Q3TTS_ERR_BAD_CONFIG, "bf16 linear needs in %% 8 == 0 (in=%d)", L.in); launch_linear_f<W_BF16>(c, a); }
+    else if (L.sdt == Q3TTS_F16) { Q3_CHECK(L.in % 8 == 0, Q3TTS_ERR_BAD_CONFIG, "f16 linear needs in %% 8 == 0 (in=%d)", L.in); launch_linear_f<W_F16>(c, a); }
+    else { Q3_CHECK(L.in % 4 == 0, Q3TTS_ERR_BAD_CONFIG, "f32 linear needs in %% 4 == 0 (in=%d)", L.in); launch_linear_f<W_F32>(c, a); }
+  } else {
+    fail(Q3TTS_ERR_BAD_CONFIG, "unsupported quantisation bits %d (4 and 8 are in scope; 6-bit runtime quantisation is not)", L.bits);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ RMSNorm
+__global__ void __launch_bounds__(256) rmsnorm_kernel(const float* __restrict__ x, int ldx, int dim, const float* __restrict__ w,
+                                                      float eps, float* __restrict__ y, int ldy) {
+  __shared__ float red[8];
+  const float* xr = x + (size_t)blockIdx.x * ldx;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < dim; i += 256) { const float v = xr[i]; ss += v * v; }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)dim + eps);
+  float* yr = y + (size_t)blockIdx.x * ldy;
+  for (int i = threadIdx.x; i < dim; i += 256) yr[i] = xr[i] * inv * w[i];
+}
+void launch_rmsnorm(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, float* y, int ldy) {
+  if (m <= 0) return;
+  rmsnorm_kernel<<<m, 256, 0, c.stream>>>(x, ldx, dim, w, eps, y, ldy);
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ q/k norm + RoPE + KV append
+// One warp per (row, head).  head < heads: q;  < heads+kv: k;  else v.  head_dim == 128: lane l owns dims l, l+32 and
+// their rotate-half partners l+64, l+96.
+__global__ void __launch_bounds__(128) qk_norm_rope_append_kernel(float* __restrict__ qkv, int ld, int m, int heads, int kv_heads,
+                                                                  const float* __restrict__ q_norm, const float* __restrict__ k_norm,
+                                                                  float eps, const float* __restrict__ inv_freq,
+                                                                  const int* __restrict__ row_slot, const int* __restrict__ row_pos,
+                                                                  KVLayout kv) {
+  const int total_heads = heads + 2 * kv_heads;
+  const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (gw >= m * total_heads) return;
+  const int row = gw / total_heads, head = gw - row * total_heads;
+  const int lane = threadIdx.x & 31;
+  float* p = qkv + (size_t)row * ld + (size_t)head * 128;
+  const int slot = row_slot[row], pos = row_pos[row];
+  const int ring = pos % kv.capacity;
+  if (head >= heads + kv_heads) {  // v: plain append
+    float* dst = kv.v + (size_t)slot * kv.slot_stride + ((size_t)(head - heads - kv_heads) * kv.capacity + ring) * 128;
+    reinterpret_cast<float4*>(dst)[lane] = reinterpret_cast<const float4*>(p)[lane];
+    return;
+  }
+  const float a0 = p[lane], a1 = p[lane + 32], b0 = p[lane + 64], b1 = p[lane + 96];
+  const float ss = warp_sum(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+  const float inv = rsqrtf(ss * (1.0f / 128.0f) + eps);
+  const float* nw = head < heads ? q_norm : k_norm;
+  const float x0 = a0 * inv * nw[lane], x1 = a1 * inv * nw[lane + 32];
+  const float y0 = b0 * inv * nw[lane + 64], y1 = b1 * inv * nw[lane + 96];
+  const float fp = (float)pos;
+  float s0, c0, s1, c1;
+  sincosf(fp * inv_freq[lane], &s0, &c0);
+  sincosf(fp * inv_freq[lane + 32], &s1, &c1);
+  // q*cos + rotate_half(q)*sin with rotate_half = [-x2, x1]  (Model/Qwen3Layers.swift:187-195)
+  const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1;
+  const float o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
+  float* dst = p;
+  if (head >= heads)
+    dst = kv.k + (size_t)slot * kv.slot_stride + ((size_t)(head - heads) * kv.capacity + ring) * 128;
+  dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+}
+void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                                const float* q_norm, const float* k_norm, float eps, const float* inv_freq,
+                                const int* row_slot, const int* row_pos, const KVLayout& kv) {
+  Q3_CHECK(head_dim == 128, Q3TTS_ERR_BAD_CONFIG, "talker kernels are specialised for head_dim 128 (got %d)", head_dim);
+  const int warps = m * (heads + 2 * kv_heads);
+  if (warps <= 0) return;
+  qk_norm_rope_append_kernel<<<(warps + 3) / 4, 128, 0, c.stream>>>(qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq,
+                                                                    row_slot, row_pos, kv);
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ window attention (decode + prefill)
+// grid (row, kv_head), 128 threads.  Keys = absolute positions [win_start[slot], row_pos] of the row's slot, read
+// through the ring.  G = heads / kv_heads query heads share the K/V reads (GQA, head h uses kv head h / G).
+template <int G>
+__global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
+                                                        const int* __restrict__ row_slot, const int* __restrict__ row_pos,
+                                                        const int* __restrict__ win_start, KVLayout kv, float* __restrict__ out,
+                                                        int ldo, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* q = sm;                 // [G][128]
+  float* sc = sm + G * 128;      // [G][S]
+  __shared__ float red_max[G], red_sum[G];
+  const int row = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = row_slot[row], pos = row_pos[row];
+  const int w0 = win_start ? win_start[slot] : 0;
+  const int S = pos - w0 + 1;
+  const int cap = kv.capacity;
+  const float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  const float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+#pragma unroll
+  for (int g = 0; g < G; ++g) q[g * 128 + tid] = qkv[(size_t)row * ld + (size_t)(kvh * G + g) * 128 + tid];
+  __syncthreads();
+  for (int j = tid; j < S; j += 128) {
+    const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)((w0 + j) % cap) * 128);
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) {
+      const float4 kk = kr[d];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 qq = reinterpret_cast<const float4*>(q + g * 128)[d];
+        acc[g] += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) sc[g * S + j] = acc[g] * scale;
+  }
+  __syncthreads();
+  for (int g = warp; g < G; g += 4) {  // softmax per query head, one warp each
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, sc[g * S + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = expf(sc[g * S + j] - mx); sc[g * S + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    if (lane == 0) { red_max[g] = mx; red_sum[g] = sum; }
+  }
+  __syncthreads();
+  float o[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) o[g] = 0.f;
+  for (int j = 0; j < S; ++j) {
+    const float vv = vb[(size_t)((w0 + j) % cap) * 128 + tid];
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) out[(size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid] = o[g] / red_sum[g];
+}
+void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                      const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out, int ldo) {
+  Q3_CHECK(head_dim == 128, Q3TTS_ERR_BAD_CONFIG, "talker kernels are specialised for head_dim 128 (got %d)", head_dim);
+  if (m <= 0) return;
+  const int G = heads / kv_heads;
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  const size_t smem = (size_t)G * (128 + kv.capacity) * sizeof(float);
+  dim3 grid(m, kv_heads);
+#define Q3_ATT(GV)                                                                                                     \
+  {                                                                                                                    \
+    attention_kernel<GV><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
+  }
+  Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
+  if (G == 1) Q3_ATT(1) else if (G == 2) Q3_ATT(2) else if (G == 4) Q3_ATT(4)
+  else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
+#undef Q3_ATT
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ embeddings / prompt assembly
+__global__ void gather_rows_kernel(Embedding e, const int* __restrict__ ids, int n, float* __restrict__ y, int ldy, int accumulate) {
+  const int row = blockIdx.x;
+  const int id = ids[row];
+  if (id < 0 || id >= e.rows) return;
+  for (int d = threadIdx.x; d < e.dim; d += blockDim.x) {
+    const float v = load_as_f32(e.w, (size_t)id * e.dim + d, e.dt);
+    float* p = y + (size_t)row * ldy + d;
+    *p = accumulate ? (*p + v) : v;
+  }
+}
+void launch_gather_rows(const LaunchCtx& c, const Embedding& e, const int* ids, int n, float* y, int ldy, bool accumulate) {
+  if (n <= 0) return;
+  gather_rows_kernel<<<n, 256, 0, c.stream>>>(e, ids, n, y, ldy, accumulate ? 1 : 0);
+  c.tick();
+}
+
+__global__ void assemble_rows_kernel(const float* __restrict__ tp_rows, int H, Embedding codec, const float* __restrict__ spk,
+                                     const int* __restrict__ desc, float* __restrict__ y) {
+  const int row = blockIdx.x;
+  const int tp = desc[row * 3 + 0], cd = desc[row * 3 + 1], sp = desc[row * 3 + 2];
+  for (int d = threadIdx.x; d < H; d += blockDim.x) {
+    float v = 0.f;
+    if (tp >= 0) v += tp_rows[(size_t)tp * H + d];
+    if (cd >= 0) v += load_as_f32(codec.w, (size_t)cd * H + d, codec.dt);
+    if (sp) v += spk[d];
+    y[(size_t)row * H + d] = v;
+  }
+}
+void launch_assemble_rows(const LaunchCtx& c, const float* tp_rows, int H, const Embedding& codec, const float* spk,
+                          const int* desc, int n, float* y) {
+  if (n <= 0) return;
+  assemble_rows_kernel<<<n, 256, 0, c.stream>>>(tp_rows, H, codec, spk, desc, y);
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ sampler
+// Counter-based uniform in (0,1): splitmix64 finaliser over (seed, counter, index), 23-bit mantissa (+0.5 so neither
+// 0 nor 1 occurs).  Same integer arithmetic as oracle/talker.py:counter_uniform.
+__device__ __forceinline__ float counter_uniform(unsigned long long seed, unsigned long long counter, unsigned idx) {
+  unsigned long long x = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull +
+                         (unsigned long long)idx * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull;
+  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+  x ^= x >> 27; x *= 0x94D049BB133111EBull;
+  x ^= x >> 31;
+  return (__uint2float_rn((unsigned)(x >> 41)) + 0.5f) * (1.0f / 8388608.0f);
+}
+__device__ __forceinline__ unsigned ordered_key(float f) {  // monotone float -> uint map
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+constexpr int kSampleThreads = 512;
+constexpr int kMaxVocab = 4096;
+
+struct BlockRed {
+  float fv[16];
+  int iv[16];
+  float bcast_f;
+  int bcast_i;
+};
+
+// argmax with first-index tie break over sl[0..V)
+__device__ int block_argmax(const float* sl, int V, BlockRed& br) {
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
+    const float v = sl[i];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { br.fv[threadIdx.x >> 5] = bv; br.iv[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = br.fv[0]; int idx = br.iv[0];
+    for (int w = 1; w < kSampleThreads / 32; ++w)
+      if (br.fv[w] > v || (br.fv[w] == v && br.iv[w] < idx)) { v = br.fv[w]; idx = br.iv[w]; }
+    if (idx == 0x7fffffff) idx = 0;
+    br.bcast_i = idx;
+  }
+  __syncthreads();
+  return br.bcast_i;
+}
+__device__ float block_sum(float v, BlockRed& br) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) br.fv[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < kSampleThreads / 32; ++w) s += br.fv[w];
+    br.bcast_f = s;
+  }
+  __syncthreads();
+  return br.bcast_f;
+}
+__device__ float block_max(float v, BlockRed& br) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) br.fv[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = -INFINITY;
+    for (int w = 0; w < kSampleThreads / 32; ++w) s = fmaxf(s, br.fv[w]);
+    br.bcast_f = s;
+  }
+  __syncthreads();
+  return br.bcast_f;
+}
+
+// Qwen3Talker.sampleToken (Model/Qwen3Talker.swift:274-322) over sl[0..V) held in shared memory (already carrying
+// the EOS/pad suppression of :470-475 where it applies).  Returns the id to every thread.
+__device__ int sample_block(float* sl, int V, int codec_vocab, float temperature, int top_k, float top_p, float rep_penalty,
+                            const unsigned* set_bitmap, unsigned long long seed, unsigned long long counter, BlockRed& br) {
+  if (set_bitmap != nullptr && rep_penalty != 1.0f) {  // set-based, division regardless of sign (:288-299)
+    for (int i = threadIdx.x; i < V; i += kSampleThreads)
+      if (set_bitmap[i >> 5] & (1u << (i & 31))) sl[i] = sl[i] / rep_penalty;
+  }
+  __syncthreads();
+  if (!(temperature > 0.f)) return block_argmax(sl, V, br);  // greedy: before the valid-token mask (:301-305)
+  for (int i = threadIdx.x; i < V; i += kSampleThreads) sl[i] = sl[i] / temperature;
+  __syncthreads();
+  if (top_k > 0 && top_k < V) {  // threshold = k-th largest; ties at the threshold survive (:307-314)
+    unsigned t = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned cand = t | (1u << bit);
+      float cnt = 0.f;
+      for (int i = threadIdx.x; i < V; i += kSampleThreads) cnt += (ordered_key(sl[i]) >= cand) ? 1.f : 0.f;
+      if (block_sum(cnt, br) >= (float)top_k) t = cand;
+    }
+    for (int i = threadIdx.x; i < V; i += kSampleThreads)
+      if (ordered_key(sl[i]) < t) sl[i] = -INFINITY;
+    __syncthreads();
+  }
+  if (V == codec_vocab) {  // valid ids: < 2048, 2148 (pad), 2150 (eos)  (:19-33, 316-319)
+    for (int i = threadIdx.x; i < V; i += kSampleThreads)
+      if (!(i < 2048 || i == 2148 || i == 2150)) sl[i] = -INFINITY;
+    __syncthreads();
+  }
+  if (top_p < 1.0f) {  // extension (no top-p in the reference): keep i iff mass of strictly more probable ids < top_p
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < V; i += kSampleThreads) mx = fmaxf(mx, sl[i]);
+    mx = block_max(mx, br);
+    float z = 0.f;
+    for (int i = threadIdx.x; i < V; i += kSampleThreads) z += expf(sl[i] - mx);
+    z = block_sum(z, br);
+    unsigned t = 0;  // largest key with mass(key_j > t) >= top_p
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned cand = t | (1u << bit);
+      float mass = 0.f;
+      for (int i = threadIdx.x; i < V; i += kSampleThreads)
+        if (ordered_key(sl[i]) > cand) mass += expf(sl[i] - mx);
+      if (block_sum(mass, br) / z >= top_p) t = cand;
+    }
+    for (int i = threadIdx.x; i < V; i += kSampleThreads)
+      if (ordered_key(sl[i]) <= t) sl[i] = -INFINITY;
+    __syncthreads();
+  }
+  // MLXRandom.categorical == Gumbel-max (:321)
+  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
+    const float l = sl[i];
+    if (l > -INFINITY) {
+      const float u = counter_uniform(seed, counter, (unsigned)i);
+      sl[i] = l + (-logf(-logf(u)));
+    }
+  }
+  __syncthreads();
+  return block_argmax(sl, V, br);
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_kernel(const float* __restrict__ logits, int ld, SlotState* __restrict__ st,
+                                                               SamplerParams p, unsigned* __restrict__ token_sets,
+                                                               int* __restrict__ cur_codes, const int* __restrict__ forced,
+                                                               int max_frames, float* __restrict__ dump, int dump_stride_frame,
+                                                               int dump_offset, int dump_slot) {
+  __shared__ float sl[kMaxVocab];
+  __shared__ BlockRed br;
+  const int slot = blockIdx.x;
+  SlotState& s = st[slot];
+  const int V = p.vocab;
+  if (p.group == 0) {
+    const bool alive = s.active && !s.finished && s.step < s.max_tokens;
+    if (!alive) {
+      if (threadIdx.x == 0) { s.frame_alive = 0; if (s.active && s.step >= s.max_tokens) s.finished = 1; }
+      return;
+    }
+  } else if (!s.frame_alive) {
+    return;
+  }
+  const float* lg = logits + (size_t)slot * ld;
+  const int step = s.step;
+  if (dump != nullptr && slot == dump_slot && step < s.logits_cap) {
+    float* d = dump + (size_t)step * dump_stride_frame + dump_offset;
+    for (int i = threadIdx.x; i < V; i += kSampleThreads) d[i] = lg[i];
+  }
+  const bool suppress = (p.group == 0) && (s.trailing_idx < s.total_text);  // EOS/pad masked while text remains (:470-475)
+  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
+    float v = lg[i];
+    if (suppress && (i == p.eos_id || i == p.pad_id)) v = -INFINITY;
+    sl[i] = v;
+  }
+  __syncthreads();
+  unsigned* set = token_sets + ((size_t)slot * p.groups + p.group) * p.set_words;
+  const bool use_set = (p.group == 0) || !s.stream_variant;  // generateStream: no penalty on CP groups (:821)
+  int tok = sample_block(sl, V, p.codec_vocab, s.temperature, s.top_k, s.top_p, s.rep_penalty, use_set ? set : nullptr, s.seed,
+                         (unsigned long long)step * p.groups + p.group, br);
+  if (threadIdx.x != 0) return;
+  const bool is_forced = s.n_forced > 0 && forced != nullptr;
+  if (is_forced) tok = forced[((size_t)slot * max_frames + step) * p.groups + p.group];
+  if (p.group == 0) {
+    if (!is_forced) {  // stop rules (:485-494)
+      if (tok == p.eos_id) { s.finished = 1; s.frame_alive = 0; return; }
+      if (tok == p.pad_id) {
+        s.consecutive_pad += 1;
+        if (s.consecutive_pad > 6) { s.finished = 1; s.frame_alive = 0; return; }
+      } else {
+        s.consecutive_pad = 0;
+      }
+    }
+    s.frame_alive = 1;
+  } else if (tok >= 0 && tok < V) {
+    set[tok >> 5] |= 1u << (tok & 31);  // generatedCodePredictorSets[g-1].insert (:522)
+  }
+  cur_codes[slot * p.groups + p.group] = tok;
+}
+void launch_sample(const LaunchCtx& c, const float* logits, int ld, int n_slots, SlotState* st, const SamplerParams& p,
+                   unsigned* token_sets, int* cur_codes, const int* forced, int max_frames, float* logits_dump,
+                   int dump_stride_frame, int dump_offset, int dump_slot) {
+  Q3_CHECK(p.vocab <= kMaxVocab, Q3TTS_ERR_BAD_CONFIG, "sampler supports vocab <= %d (got %d)", kMaxVocab, p.vocab);
+  sample_kernel<<<n_slots, kSampleThreads, 0, c.stream>>>(logits, ld, st, p, token_sets, cur_codes, forced, max_frames, logits_dump,
+                                                          dump_stride_frame, dump_offset, dump_slot);
+  c.tick();
+}
+
+__global__ void __launch_bounds__(kSampleThreads) sample_probe_kernel(const float* __restrict__ logits, int V, int codec_vocab,
+                                                                     float temperature, int top_k, float top_p, float rep_penalty,
+                                                                     const unsigned* __restrict__ set_bitmap, unsigned long long seed,
+                                                                     unsigned long long counter, int* __restrict__ id_out) {
+  __shared__ float sl[kMaxVocab];
+  __shared__ BlockRed br;
+  for (int i = threadIdx.x; i < V; i += kSampleThreads) sl[i] = logits[i];
+  __syncthreads();
+  const int tok = sample_block(sl, V, codec_vocab, temperature, top_k, top_p, rep_penalty, set_bitmap, seed, counter, br);
+  if (threadIdx.x == 0) *id_out = tok;
+}
+void launch_sample_probe(const LaunchCtx& c, const float* logits, int vocab, int codec_vocab, float temperature, int top_k,
+                         float top_p, float rep_penalty, const unsigned* set_bitmap, unsigned long long seed,
+                         unsigned long long counter, int* id_out) {
+  Q3_CHECK(vocab <= kMaxVocab, Q3TTS_ERR_INVALID_ARG, "sampler supports vocab <= %d (got %d)", kMaxVocab, vocab);
+  sample_probe_kernel<<<1, kSampleThreads, 0, c.stream>>>(logits, vocab, codec_vocab, temperature, top_k, top_p, rep_penalty,
+                                                          set_bitmap, seed, counter, id_out);
+  c.tick();
+}
+
+// ------------------------------------------------------------------------------------------------ frame plumbing
+__global__ void cp_input_kernel(int pass, const float* __restrict__ h_last, int H, Embedding codec, const Embedding* __restrict__ cp_emb,
+                                const int* __restrict__ cur_codes, float* __restrict__ y, int groups) {
+  const int slot = blockIdx.x;
+  if (pass == 0) {
+    const int code0 = cur_codes[slot * groups];
+    const bool ok = code0 >= 0 && code0 < codec.rows;
+    for (int d = threadIdx.x; d < H; d += blockDim.x) {
+      y[(size_t)(2 * slot) * H + d] = h_last[(size_t)slot * H + d];
+      y[(size_t)(2 * slot + 1) * H + d] = ok ? load_as_f32(codec.w, (size_t)code0 * H + d, codec.dt) : 0.f;
+    }
+  } else {
+    const Embedding e = cp_emb[pass - 1];
+    const int code = cur_codes[slot * groups + pass];
+    const bool ok = code >= 0 && code < e.rows;
+    for (int d = threadIdx.x; d < H; d += blockDim.x)
+      y[(size_t)slot * H + d] = ok ? load_as_f32(e.w, (size_t)code * H + d, e.dt) : 0.f;
+  }
+}
+void launch_cp_input(const LaunchCtx& c, int pass, int n_slots, const float* h_last, int H, const Embedding& codec,
+                     const Embedding* cp_emb_dev, const int* cur_codes, float* y) {
+  cp_input_kernel<<<n_slots, 256, 0, c.stream>>>(pass, h_last, H, codec, cp_emb_dev, cur_codes, y, 16);
+  c.tick();
+}
+
+__global__ void frame_finalize_kernel(SlotState* __restrict__ st, const int* __restrict__ cur_codes, int* __restrict__ frames_out,
+                                      int max_frames, unsigned* __restrict__ token_sets, int set_words,
+                                      const float* __restrict__ trailing, int max_trailing, const float* __restrict__ tts_pad,
+                                      Embedding codec, const Embedding* __restrict__ cp_emb, int H, float* __restrict__ x_next) {
+  const int slot = blockIdx.x;
+  SlotState& s = st[slot];
+  if (!s.frame_alive) return;
+  constexpr int G = 16;
+  __shared__ int codes[G];
+  if (threadIdx.x < G) codes[threadIdx.x] = cur_codes[slot * G + threadIdx.x];
+  __syncthreads();
+  const int ti = s.trailing_idx;
+  const float* text = (ti < s.total_text) ? trailing + ((size_t)slot * max_trailing + ti) * H : tts_pad;
+  for (int d = threadIdx.x; d < H; d += blockDim.x) {
+    // codecEmbedSum = codec_embedding(code0) + sum_i cp.codec_embedding[i](code_{i+1}); input = text + sum (:531-548)
+    float sum = (codes[0] >= 0 && codes[0] < codec.rows) ? load_as_f32(codec.w, (size_t)codes[0] * H + d, codec.dt) : 0.f;
+#pragma unroll
+    for (int g = 1; g < G; ++g) {
+      const Embedding e = cp_emb[g - 1];
+      if (codes[g] >= 0 && codes[g] < e.rows) sum += load_as_f32(e.w, (size_t)codes[g] * H + d, e.dt);
+    }
+    x_next[(size_t)slot * H + d] = text[d] + sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s.n_frames < max_frames) {
+      for (int g = 0; g < G; ++g) frames_out[((size_t)slot * max_frames + s.n_frames) * G + g] = codes[g];
+      s.n_frames += 1;
+    }
+    if (codes[0] >= 0 && codes[0] < set_words * 32) {
+      unsigned* set0 = token_sets + (size_t)slot * G * set_words;
+      set0[codes[0] >> 5] |= 1u << (codes[0] & 31);  // generatedCode0TokensSet.insert (:528)
+    }
+    if (ti < s.total_text) s.trailing_idx = ti + 1;
+  }
+}
+void launch_frame_finalize(const LaunchCtx& c, int n_slots, SlotState* st, const int* cur_codes, int* frames_out,
+                           int max_frames, unsigned* token_sets, int set_words, const float* trailing, int max_trailing,
+                           const float* tts_pad, const Embedding& codec, const Embedding* cp_emb_dev, int H, float* x_next) {
+  frame_finalize_kernel<<<n_slots, 256, 0, c.stream>>>(st, cur_codes, frames_out, max_frames, token_sets, set_words, trailing,
+                                                       max_trailing, tts_pad, codec, cp_emb_dev, H, x_next);
+  c.tick();
+}
+
+__global__ void step_advance_kernel(int n_slots, SlotState* __restrict__ st, int window) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  SlotState& s = st[slot];
+  if (!s.frame_alive) return;
+  s.pos += 1;
+  s.step += 1;
+  // trimKVCache every 15th step when longer than the window (Model/Qwen3Talker.swift:556-558; Qwen3Layers.swift:111-124)
+  if (s.step % 15 == 0 && s.pos - s.win_start > window) s.win_start = s.pos - window;
+  if (s.step >= s.max_tokens) s.finished = 1;
+  s.frame_alive = 0;
+}
+void launch_step_advance(const LaunchCtx& c, int n_slots, SlotState* st, int window) {
+  step_advance_kernel<<<(n_slots + 63) / 64, 64, 0, c.stream>>>(n_slots, st, window);
+  c.tick();
+}
+
+__global__ void step_rows_kernel(int n_slots, const SlotState* __restrict__ st, int* __restrict__ row_slot, int* __restrict__ row_pos,
+                                 int* __restrict__ win_start) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= n_slots) return;
+  row_slot[slot] = slot;
+  row_pos[slot] = st[slot].pos;
+  win_start[slot] = st[slot].win_start;
+}
+void launch_step_rows(const LaunchCtx& c, int n_slots, const SlotState* st, int* row_slot, int* row_pos, int* win_start) {
+  step_rows_kernel<<<(n_slots + 63) / 64, 64, 0, c.stream>>>(n_slots, st, row_slot, row_pos, win_start);
+  c.tick();
+}
+
+// Opt-in dynamic shared memory above 48 KB, set once per device at handle creation (never during graph capture).
+template <int FMT>
+static void init_linear_fmt() {
+  Q3_CUDA(cudaFuncSetAttribute(linear_kernel<FMT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(linear_kernel<FMT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(linear_kernel<FMT, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(linear_kernel<FMT, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+void init_talker_kernels() {
+  init_linear_fmt<W_Q4>();
+  init_linear_fmt<W_Q8>();
+  init_linear_fmt<W_BF16>();
+  init_linear_fmt<W_F16>();
+  init_linear_fmt<W_F32>();
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+}
+
+}  // namespace q3

@@ -1,0 +1,24 @@
+"""CPU oracle for the Qwen3-TTS hot path (TEST INFRASTRUCTURE — never shipped, never measured as product).
+
+What this is
+------------
+A torch-CPU fp32 / numpy restatement of the hot path of hamptus/mlx-swift-qwen3-tts
+(`/root/reference`, Swift on MLX): talker decode + code predictor + sampler + the
+speech-tokenizer decoder, written from the Swift sources cited in each docstring
+(paths relative to `/root/reference/Sources/Qwen3TTS/`).
+
+PARITY UNPINNED
+---------------
+The reference cannot be compiled or imported here (no Swift toolchain, no MLX; its
+arithmetic lives in the un-vendored `ml-explore/mlx-swift` 0.30.3, rev
+4dccaeda1d83cf8697f235d2786c2d72ad4bb925, `Package.resolved:3-11`) and its own tests
+(`Tests/Qwen3TTSTests/*`) hold no numeric golden vector, known-answer test or fixture for
+this path.  The oracle is therefore pinned only by (a) self-checks against independent
+formulations (`torch.nn.functional` convs / SDPA, direct indexing, quantise→dequantise
+round trips — see `tests/test_oracle_*.py`) and (b) MLX's published semantics restated in
+`oracle/mlx_quant.py`.  Parity claims against it are "partial" by construction.
+
+Who may import this package: `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs — as the checker or the CPU baseline only.
+The product (`mlx-swift-qwen3-tts_b200/`) never imports it and has no CPU fallback.
+"""
