@@ -1,0 +1,93 @@
+"""CPU: the MLX affine quantisation restatement (oracle/mlx_quant.py) against independent formulations."""
+import numpy as np
+import pytest
+
+from oracle import mlx_quant
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_pack_layout_lsb_first(bits):
+    per = 32 // bits
+    q = np.arange(per, dtype=np.uint32)[None, :] % (1 << bits)
+    w = mlx_quant.pack(q, bits)
+    assert w.shape == (1, 1)
+    # element j sits at bit offset j*bits
+    want = 0
+    for j in range(per):
+        want |= int(q[0, j]) << (j * bits)
+    assert int(w[0, 0]) == want
+    assert np.array_equal(mlx_quant.unpack(w, bits), q)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("group", [32, 64, 128])
+def test_pack_unpack_roundtrip(bits, group):
+    rng = np.random.default_rng(bits + group)
+    q = rng.integers(0, 1 << bits, size=(17, 256)).astype(np.uint32)
+    assert np.array_equal(mlx_quant.unpack(mlx_quant.pack(q, bits), bits), q)
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+@pytest.mark.parametrize("sdt", ["f32", "bf16", "f16"])
+def test_quantize_error_bound(bits, sdt):
+    """Round-trip error.  Interior points land within |scale|/2; MLX re-fits the scale so the dominant edge is exact
+    (s = edge / round(edge / s)), which can leave the opposite end of the group up to ~one step outside the code range
+    (measured max 0.9995 |scale|), so the bound that holds for every element is one step."""
+    rng = np.random.default_rng(0)
+    w = (rng.standard_normal((64, 512)) * 0.02).astype(np.float32)
+    packed, s, b = mlx_quant.quantize(w, 64, bits, sdt)
+    deq = mlx_quant.dequantize(packed, s, b, 64, bits, "f32")
+    step = np.repeat(np.abs(s), 64, axis=1)
+    slack = {"f32": 1e-7, "bf16": 2 ** -8, "f16": 2 ** -11}[sdt] * np.abs(w).max() * 4
+    assert np.all(np.abs(deq - w) <= step * 1.0 + slack + 1e-7)
+    assert np.median(np.abs(deq - w) / step) <= 0.30
+
+
+def test_quantize_edges_are_exact():
+    """MLX picks the edge (w_min or w_max by magnitude) so that it is represented exactly: q0 = round(edge/s), s = edge/q0."""
+    rng = np.random.default_rng(1)
+    w = (rng.standard_normal((8, 128)) * 0.05).astype(np.float32)
+    packed, s, b = mlx_quant.quantize(w, 64, 4, "f32")
+    deq = mlx_quant.dequantize(packed, s, b, 64, 4, "f32").reshape(8, 2, 64)
+    g = w.reshape(8, 2, 64)
+    edge = np.where(np.abs(g.min(-1)) > np.abs(g.max(-1)), g.min(-1), g.max(-1))
+    # the bias IS the edge value (when q0 != 0), and code 0 decodes to it
+    assert np.allclose(b, edge, rtol=0, atol=0)
+    idx = np.abs(g - edge[..., None]).argmin(-1)
+    assert np.allclose(np.take_along_axis(deq, idx[..., None], -1)[..., 0], edge, rtol=1e-6, atol=1e-8)
+
+
+def test_zero_group():
+    w = np.zeros((2, 64), np.float32)
+    packed, s, b = mlx_quant.quantize(w, 64, 4, "bf16")
+    assert np.all(mlx_quant.dequantize(packed, s, b, 64, 4, "f32") == 0)
+
+
+def test_dequant_two_roundings_contract():
+    """deq32 = round(scale*q) then round(+bias), NOT a fused multiply-add: pick a case where they differ."""
+    s = np.array([[np.float32(1.0000001)]], np.float32)
+    b = np.array([[np.float32(-3.0)]], np.float32)
+    packed = mlx_quant.pack(np.full((1, 64), 3, np.uint32), 8)
+    got = mlx_quant.dequantize(packed, s, b, 64, 8, "f32")[0, 0]
+    prod = np.float32(np.float32(1.0000001) * np.float32(3.0))
+    assert got == np.float32(prod + np.float32(-3.0))
+    assert got != np.float32(np.float64(np.float32(1.0000001)) * 3.0 - 3.0)  # what an FMA would return
+
+
+def test_round_to_bf16_matches_torch():
+    import torch
+
+    rng = np.random.default_rng(2)
+    a = rng.standard_normal(10000).astype(np.float32) * 3
+    want = torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+    assert np.array_equal(mlx_quant.round_to_dtype(a, "bf16"), want)
+
+
+def test_quantized_matmul_equals_dense():
+    rng = np.random.default_rng(3)
+    w = (rng.standard_normal((32, 128)) * 0.02).astype(np.float32)
+    x = rng.standard_normal((3, 128)).astype(np.float32)
+    packed, s, b = mlx_quant.quantize(w, 64, 8, "bf16")
+    y = mlx_quant.quantized_matmul(x, packed, s, b, 64, 8)
+    assert np.allclose(y, x @ mlx_quant.dequantize(packed, s, b, 64, 8).T)
+    assert np.abs(y - x @ w.T).max() < 5e-3
