@@ -132,7 +132,9 @@ typedef struct q3tts_timing {
   int64_t frames;          /* talker frames produced (before the validity filter) */
   int64_t h2d_bytes, d2h_bytes;
   int64_t weight_bytes_per_frame; /* algorithmic bytes streamed per 12.5 Hz frame */
-  int64_t reserved[6];
+  double talker_ms;               /* CUDA-event time of prompt assembly + prefill + all frame steps of the last call */
+  int64_t codec_flops;            /* algorithmic flops of the codec passes of the last call */
+  int64_t reserved[4];
 } q3tts_timing;
 
 /* ------------------------------------------------------------------------------------------------------
@@ -227,6 +229,15 @@ q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vo
  * (rvq_first and rvq_rest sums before their 1x1 output projections). */
 q3tts_status q3tts_rvq_embed(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, float* first_out,
                              float* rest_out, int32_t* dim_out);
+
+/* ------------------------------------------------------------------------------------------------------
+ * measurement hook (bench.py roofline): runs the dequant-fused linear launches of ONE talker decode step
+ * (which = 0: 28 x {qkv, o, gate|up, down} + codec_head) or ONE code-predictor pass (which = 1) for `m` activation
+ * rows, `iters` times back to back on the handle's stream, bracketed by CUDA events.  Same kernels, weights and
+ * shapes as the frame step; no reference counterpart (the reference has no benchmark).
+ * ---------------------------------------------------------------------------------------------------- */
+q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out,
+                                  int64_t* launches_out, int64_t* bytes_per_iter_out);
 
 #ifdef __cplusplus
 }

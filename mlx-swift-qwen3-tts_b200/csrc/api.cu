@@ -88,8 +88,28 @@ bool frame_valid(const int32_t* f) { return f[0] >= 0 && f[0] < 2048; }  // Mode
 
 // ---- talker drivers ------------------------------------------------------------------------------------------
 // Runs one admitted utterance in slot 0 to completion; returns raw frames.
+struct TalkerSpan {  // accumulates q3tts_timing.talker_ms over the talker part of a call
+  q3tts_handle* h;
+  cudaEvent_t a = nullptr, b = nullptr;
+  explicit TalkerSpan(q3tts_handle* hh) : h(hh) {
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, h->stream);
+  }
+  ~TalkerSpan() {
+    cudaEventRecord(b, h->stream);
+    cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    h->timing.talker_ms += ms;
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+  }
+};
+
 void run_single(q3tts_handle* h, const q3tts_request& req, std::vector<int32_t>& raw, int& n_raw) {
   TalkerEngine& t = *h->talker;
+  TalkerSpan span(h);
   n_raw = 0;
   Admission a = t.admit(0, req);
   if (a.too_short) return;
@@ -126,6 +146,7 @@ int filter_frames(const q3tts_request& req, const std::vector<int32_t>& raw, int
 // Continuous batching of independent utterances over the handle's slots; raw[i] receives utterance i's raw frames.
 void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<std::vector<int32_t>>& raw, std::vector<int>& n_raw) {
   TalkerEngine& t = *h->talker;
+  TalkerSpan span(h);
   const int B = t.max_batch();
   raw.assign(n, {});
   n_raw.assign(n, 0);
@@ -223,6 +244,7 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
       h->timing.decode_ms += ms;
+      h->timing.codec_flops += (int64_t)nb * T * c.flops_per_frame();
       for (int b = 0; b < nb; ++b) {
         DecodeJob& j = jobs[idx[p0 + b]];
         const int64_t total = (int64_t)T * up;
@@ -769,6 +791,18 @@ q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, c
     cudaGetLastError();
     return e.status;
   }
+}
+
+q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out, int64_t* launches_out,
+                                  int64_t* bytes_per_iter_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(ms_out && launches_out && bytes_per_iter_out && iters > 0, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    int64_t l = 0, b = 0;
+    *ms_out = h->talker->profile_linears(which, m, iters, l, b);
+    *launches_out = l;
+    *bytes_per_iter_out = b;
+  });
 }
 
 q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vocab, float temperature, int32_t top_k, float top_p,

@@ -57,6 +57,8 @@ class TalkerEngine {
   int64_t graph_replays = 0, graph_nodes_replayed = 0;
   double last_prefill_ms = 0;
 
+  // measurement hook (q3tts_profile_linear)
+  double profile_linears(int which, int m, int iters, int64_t& launches, int64_t& bytes_per_iter);
   // probe used by q3tts_sample_token
   int sample_probe(const float* logits, int vocab, float temperature, int top_k, float top_p, float rep_penalty,
                    const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter);

@@ -399,6 +399,39 @@ void TalkerEngine::fetch_logits(int frames, float* code0_out, float* cp_out) {
   Q3_CUDA(cudaStreamSynchronize(stream_));
 }
 
+double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launches, int64_t& bytes_per_iter) {
+  const StackWeights& S = which == 0 ? w_.talker : w_.cp;
+  Q3_CHECK(m >= 1 && m <= max_rows_, Q3TTS_ERR_INVALID_ARG, "m %d out of range (1..%d)", m, max_rows_);
+  const LaunchCtx c{stream_, nullptr};
+  const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
+  Q3_CUDA(cudaMemsetAsync(d_x_, 0, sizeof(float) * (size_t)m * S.hidden, stream_));
+  Q3_CUDA(cudaMemsetAsync(d_attn_, 0, sizeof(float) * (size_t)m * attn_ld, stream_));
+  launches = 0;
+  bytes_per_iter = 0;
+  auto pass = [&](bool count) {
+    for (int l = 0; l < S.layers; ++l) {
+      const LayerWeights& L = S.layer[l];
+      launch_linear(c, L.qkv, d_x_, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
+      launch_linear(c, L.o, d_attn_, attn_ld, m, d_x_, S.hidden, nullptr, 0.f, EPI_ADD);
+      launch_linear(c, L.gate_up, d_x_, S.hidden, m, d_act_, S.inter, L.post_norm, S.eps, EPI_SWIGLU);
+      launch_linear(c, L.down, d_act_, S.inter, m, d_x_, S.hidden, nullptr, 0.f, EPI_ADD);
+      if (count) { launches += 4; bytes_per_iter += (int64_t)(L.qkv.weight_bytes() + L.o.weight_bytes() + L.gate_up.weight_bytes() + L.down.weight_bytes()); }
+    }
+    const Linear& head = which == 0 ? w_.codec_head : w_.lm_head[0];
+    launch_linear(c, head, d_x_, S.hidden, m, which == 0 ? d_logits0_ : d_cplogits_, head.out, S.final_norm, S.eps, EPI_STORE);
+    if (count) { launches += 1; bytes_per_iter += (int64_t)head.weight_bytes(); }
+  };
+  pass(true);  // warm-up (and the per-iteration accounting)
+  Q3_CUDA(cudaEventRecord(ev_a_, stream_));
+  for (int i = 0; i < iters; ++i) pass(false);
+  Q3_CUDA(cudaEventRecord(ev_b_, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, ev_a_, ev_b_);
+  launches *= iters;
+  return ms;
+}
+
 int TalkerEngine::sample_probe(const float* logits, int vocab, float temperature, int top_k, float top_p, float rep_penalty,
                                const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter) {
   Q3_CHECK(vocab > 0 && vocab <= 4096, Q3TTS_ERR_INVALID_ARG, "vocab %d out of range", vocab);

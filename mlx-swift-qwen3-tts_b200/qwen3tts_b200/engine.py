@@ -261,6 +261,12 @@ class Engine:
         A.check(A.lib().q3tts_generate_pcm_batch(self._h, arr, n, mode, ptrs, cap, ns, fr), self._h)
         return [outs[i][: ns[i]] for i in range(n)], [fr[i] for i in range(n)]
 
+    def profile_linear(self, which: int = 0, m: int = 1, iters: int = 20):
+        """-> (ms_total, launches, bytes_per_iter) of the talker-step (which=0) / code-predictor-pass (which=1) linear launches."""
+        ms, n, b = C.c_double(0), A.i64(0), A.i64(0)
+        A.check(A.lib().q3tts_profile_linear(self._h, which, m, iters, C.byref(ms), C.byref(n), C.byref(b)), self._h)
+        return ms.value, n.value, b.value
+
     def sample_token(self, logits, temperature=0.9, top_k=0, top_p=1.0, repetition_penalty=1.05, token_set=None, seed=0, counter=0) -> int:
         lg = np.ascontiguousarray(np.asarray(logits, dtype=np.float32))
         ts = np.ascontiguousarray(np.asarray(sorted(token_set) if token_set else [], dtype=np.int32))
