@@ -230,6 +230,17 @@ q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vo
 q3tts_status q3tts_rvq_embed(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, float* first_out,
                              float* rest_out, int32_t* dim_out);
 
+/* MLX `Conv1d` / `ConvTransposed1d` (polyphase) / `Linear` as the codec calls them (Vocoder/SpeechTokenizer.swift:142, 179,
+ * 230, 726, 791), through the engine's implicit-GEMM kernels:  y[b,t,n] = epi(bias[n] + sum_tap x[b, t-(ntap-1-tap)*dil, :] . w[tap][n][:])
+ * x [B][T][cin] fp32, w [ntap][N][cin] fp32.  use_tensor_cores = 1: tcgen05/TMEM path (operands rounded to fp16, fp32
+ * accumulate); 0: fp32 SIMT path.  act: 0 none, 1 exact-erf GELU, 2 SiLU.  swiglu = 1: columns (2i, 2i+1) = (gate, up) ->
+ * N/2 outputs.  res/scale: y = res + scale[n]*y (either may be NULL).  snake_ea/snake_ieb [snake_ch]: SnakeBeta applied to
+ * the fp16 copy only.  y32 / y16 (fp16 values widened to fp32) are [B][T][N or N/2]; either may be NULL. */
+q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t T, int32_t cin, const float* w, const float* bias,
+                              int32_t N, int32_t ntap, int32_t dil, int32_t act, int32_t swiglu, const float* res,
+                              const float* scale, const float* snake_ea, const float* snake_ieb, int32_t snake_ch,
+                              int32_t use_tensor_cores, float* y32, float* y16);
+
 /* ------------------------------------------------------------------------------------------------------
  * measurement hook (bench.py roofline): runs the dequant-fused linear launches of ONE talker decode step
  * (which = 0: 28 x {qkv, o, gate|up, down} + codec_head) or ONE code-predictor pass (which = 1) for `m` activation

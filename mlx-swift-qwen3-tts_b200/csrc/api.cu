@@ -4,7 +4,9 @@
 #include <map>
 
 #include "codec.h"
+#include "codec_kernels.h"
 #include "engine.h"
+#include "gemm_tc.h"
 
 using namespace q3;
 
@@ -785,6 +787,69 @@ q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, c
     Q3_CUDA(cudaDeviceSynchronize());
     Q3_CUDA(cudaMemcpy(y, dy, (size_t)m * out_f * 4, cudaMemcpyDeviceToHost));
     cudaFree(dw); cudaFree(ds); cudaFree(db); cudaFree(dx); cudaFree(dy);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
+q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t T, int32_t cin, const float* w, const float* bias, int32_t N,
+                              int32_t ntap, int32_t dil, int32_t act, int32_t swiglu, const float* res, const float* scale,
+                              const float* snake_ea, const float* snake_ieb, int32_t snake_ch, int32_t use_tc, float* y32, float* y16) {
+  try {
+    Q3_CHECK(x && w && B > 0 && T > 0 && cin > 0 && N > 0 && ntap > 0 && dil > 0, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    require_device(device);
+    const size_t M = (size_t)B * T, nx = M * cin, nw = (size_t)ntap * N * cin, n_out = swiglu ? N / 2 : N, ny = M * n_out;
+    std::vector<void*> allocs;
+    auto dev = [&](const void* src, size_t bytes) -> void* {
+      void* d = nullptr;
+      Q3_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+      allocs.push_back(d);
+      if (src) Q3_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+      return d;
+    };
+    float* dx = (float*)dev(x, nx * 4);
+    float* dw = (float*)dev(w, nw * 4);
+    float* dbias = bias ? (float*)dev(bias, (size_t)N * 4) : nullptr;
+    float* dres = res ? (float*)dev(res, ny * 4) : nullptr;
+    float* dscale = scale ? (float*)dev(scale, n_out * 4) : nullptr;
+    float* dea = snake_ea ? (float*)dev(snake_ea, (size_t)snake_ch * 4) : nullptr;
+    float* dieb = snake_ieb ? (float*)dev(snake_ieb, (size_t)snake_ch * 4) : nullptr;
+    float* dy32 = (float*)dev(nullptr, ny * 4);
+    __half* dy16 = (__half*)dev(nullptr, ny * 2);
+    Q3_CUDA(cudaMemset(dy32, 0, ny * 4));
+    Q3_CUDA(cudaMemset(dy16, 0, ny * 2));
+    LaunchCtx c{nullptr, nullptr};
+    if (use_tc) {
+      init_tc_gemm();
+      __half* dx16 = (__half*)dev(nullptr, nx * 2);
+      __half* dw16 = (__half*)dev(nullptr, nw * 2);
+      Q3_CHECK(nx % 4 == 0 && nw % 4 == 0, Q3TTS_ERR_INVALID_ARG, "probe needs element counts divisible by 4");
+      launch_f32_to_f16(c, dx, nx, dx16);
+      launch_f32_to_f16(c, dw, nw, dw16);
+      TcGemm g;
+      g.a = dx16; g.w = dw16; g.Bt = B; g.T = T; g.cin = cin; g.N = N; g.ntap = ntap; g.dil = dil;
+      g.bias = dbias; g.res = dres; g.ld_res = (int)n_out; g.scale = dscale; g.act = act; g.swiglu = swiglu;
+      g.out32 = dy32; g.ld32 = (int)n_out; g.out16 = dy16; g.ld16 = (int)n_out;
+      g.snake_ea = dea; g.snake_ieb = dieb; g.snake_ch = snake_ch;
+      Q3_CHECK(tc_gemm_supported(g), Q3TTS_ERR_INVALID_ARG, "shape not supported by the tcgen05 path (cin %% 8, N %% 32)");
+      launch_tc_gemm(c, g);
+    } else {
+      Q3_CHECK(!swiglu && !snake_ea, Q3TTS_ERR_INVALID_ARG, "SIMT probe supports bias/act(gelu)/res/scale only");
+      ConvW cw;
+      cw.w = dw; cw.bias = dbias; cw.ntap = ntap; cw.dil = dil; cw.cin = cin; cw.n = N;
+      launch_conv_gemm(c, dx, cw, dy32, dres, dscale, (int)M, T, res ? CE_RES_SCALE : (act == 1 ? CE_GELU : CE_STORE));
+    }
+    Q3_CUDA(cudaDeviceSynchronize());
+    if (y32) Q3_CUDA(cudaMemcpy(y32, dy32, ny * 4, cudaMemcpyDeviceToHost));
+    if (y16) {
+      std::vector<uint16_t> h(ny);
+      Q3_CUDA(cudaMemcpy(h.data(), dy16, ny * 2, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < ny; ++i) y16[i] = f16_to_f32(h[i]);
+    }
+    for (void* d : allocs) cudaFree(d);
     return Q3TTS_OK;
   } catch (const Error& e) {
     g_create_error = e.what();

@@ -5,6 +5,8 @@
 #include <string>
 #include <vector>
 
+#include <cuda_fp16.h>
+
 #include "common.h"
 #include "json.h"
 #include "kernels.h"
@@ -31,6 +33,7 @@ CodecConfig parse_codec_config(const Json& root);
 // A causal (dilated) conv / transposed conv / linear, all as  Y[b,t,n] = bias[n] + sum_tap X[b, t-(ntap-1-tap)*dil, :] . W[tap][n][:]
 struct ConvW {
   const float* w = nullptr;   // [ntap][n][cin] fp32
+  const __half* w16 = nullptr;  // same, fp16: B operand of the tcgen05 path
   const float* bias = nullptr;  // [n] or null
   int ntap = 1, dil = 1, cin = 0, n = 0;
   int64_t flops_per_row() const { return 2ll * ntap * cin * n; }
@@ -53,12 +56,17 @@ class CodecDecoder {
   // decodeImpl (Vocoder/SpeechTokenizer.swift:917-952): d_codes [B][T][Q] int32 -> d_pcm [B][T*up] fp32 (clipped to [-1,1]).
   // B*T must be <= pass_frames().
   void decode_pass(const int32_t* d_codes, int B, int T, float* d_pcm);
+  bool uses_tensor_cores() const { return use_tc_; }
   // code -> embedding gather-sums (bit-exact probe): d_first/d_rest [B*T][vq_dim]
   void rvq_embed(const int32_t* d_codes, int B, int T, float* d_first, float* d_rest);
   int64_t flops_per_frame() const { return flops_per_frame_; }
 
  private:
   void ensure_workspace(int frames);
+  void decode_pass_simt(const int32_t* d_codes, int B, int T, float* d_pcm);
+  void decode_pass_tc(const int32_t* d_codes, int B, int T, float* d_pcm);
+  void finish_weight(ConvW& w);           // uploads the fp16 copy, updates use_tc_
+  const __half* upload_f16(const std::vector<float>& h);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
   ConvW load_conv(const std::map<std::string, STensor>& t, const std::string& key, int cout, int cin_per_group, int k, int dil, bool bias);
   ConvW load_convT(const std::map<std::string, STensor>& t, const std::string& key, int cin, int cout, int k, int stride);
@@ -81,6 +89,7 @@ class CodecDecoder {
   ConvW tr_in_, tr_out_;
   struct TLayer {
     ConvW qkv, o, gate_up, down;
+    ConvW gate_up_il;  // rows interleaved (gate_i, up_i) for the fused SwiGLU epilogue of the tcgen05 path
     const float *in_norm, *post_norm, *attn_scale, *mlp_scale;
   };
   std::vector<TLayer> tl_;
@@ -102,7 +111,9 @@ class CodecDecoder {
   const float *out_w_ = nullptr, *out_b_ = nullptr;  // [7][C], [1]
   int out_ch_ = 0;
 
-  // workspace (grow-only)
+  bool use_tc_ = true;  // every dense contraction fits the tcgen05 path (cin % 8 == 0, N % 32 == 0); else the fp32 SIMT pipeline runs
+  // workspace (grow-only); the tcgen05 pipeline uses ws_[0..2] as fp32 and hs_[0..2] as fp16 operand buffers
+  __half* hs_[3] = {nullptr, nullptr, nullptr};
   float* ws_[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t ws_floats_ = 0, ws_bytes_ = 0;
   int ws_frames_ = 0;

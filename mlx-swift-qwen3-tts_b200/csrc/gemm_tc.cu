@@ -1,0 +1,387 @@
+// tcgen05 + TMEM + TMA implicit GEMM (sm_100a).  One CTA = one 128 x BN output tile:
+//   warp 0   : TMA producer   (cp.async.bulk.tensor into a ring of 128B-swizzled smem stages, mbarrier complete_tx)
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BN x 16, fp16 in, fp32 accumulate in TMEM)
+//   warps 2-5: epilogue       (tcgen05.ld 32x32b -> registers -> bias / activation / SwiGLU / residual+scale / fused
+//                              SnakeBeta of the next layer -> fp32 and/or fp16 stores)
+// Causal convolutions are K-loops over (tap, channel block): the A box of a tap is the same [128 time steps x 64 channels]
+// tile shifted back in time; negative time coordinates are zero-filled by the TMA unit, which IS the causal left padding.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+
+#include "gemm_tc.h"
+
+namespace q3 {
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                       // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB per stage
+constexpr int kThreads = 192;
+
+struct TcParams {
+  int Bt, T, cin, N, ntap, dil;
+  int bn, stages, tiles_per_batch, kb_per_tap, tmem_cols;
+  const float* bias;
+  const float* res;
+  int ld_res;
+  const float* scale;
+  int act, swiglu;
+  float* out32;
+  int ld32;
+  __half* out16;
+  int ld16;
+  const float* snake_ea;
+  const float* snake_ieb;
+  int snake_ch;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a trapped kernel (an error code on the host), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
+//   [0,14) start>>4   [16,30) LBO>>4 = 1 (unused for swizzled K-major)   [32,46) SBO>>4 = 64   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+  const uint32_t hi = 64u | (1u << 14) | (2u << 29);
+  return ((uint64_t)hi << 32) | lo;
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024-B aligned
+  const int b_bytes = p.bn * kBlockK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)p.stages * kABytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bidx = blockIdx.x / p.tiles_per_batch;
+  const int t0 = (blockIdx.x - bidx * p.tiles_per_batch) * kTileM;
+  const int n0 = blockIdx.y * p.bn;
+  const int num_kb = p.ntap * p.kb_per_tap;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {  // one warp allocates TMEM columns for the fp32 accumulator tile and later frees them
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+        const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * kBlockK;
+        const int shift = (p.ntap - 1 - tap) * p.dil;
+        tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
+        tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (bit 4), a = b = F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % p.stages, ph = (kb / p.stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kABytes));
+        const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * b_bytes));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+      }
+      umma_commit(tmem_full);    // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int t = t0 + row;
+    const bool row_ok = t < p.T;
+    const size_t m = (size_t)bidx * p.T + t;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.bn; c += 32) {
+      uint32_t raw[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      const int nb = n0 + c;
+      if (!row_ok || nb >= p.N) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nb + j);
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      }
+      if (p.act == TC_ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+      } else if (p.act == TC_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+      }
+      int width = 32, ob = nb;
+      if (p.swiglu) {  // (gate, up) interleaved along n
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = silu(v[2 * j]) * v[2 * j + 1];
+        width = 16;
+        ob = nb >> 1;
+      }
+      if (p.res) {
+        const float* rp = p.res + m * p.ld_res + ob;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < width) {
+            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+            float s0 = 1.f, s1 = 1.f, s2 = 1.f, s3 = 1.f;
+            if (p.scale) { const float4 s4 = *reinterpret_cast<const float4*>(p.scale + ob + j); s0 = s4.x; s1 = s4.y; s2 = s4.z; s3 = s4.w; }
+            v[j] = r4.x + s0 * v[j]; v[j + 1] = r4.y + s1 * v[j + 1]; v[j + 2] = r4.z + s2 * v[j + 2]; v[j + 3] = r4.w + s3 * v[j + 3];
+          }
+        }
+      }
+      if (p.out32) {
+        float* op = p.out32 + m * p.ld32 + ob;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < width) *reinterpret_cast<float4*>(op + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      if (p.out16) {
+        if (p.snake_ea) {  // SnakeBeta of the consumer layer, applied to the fp16 operand copy only
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (j < width) {
+              const int ch = (ob + j) % p.snake_ch;
+              const float sn = sinf(v[j] * p.snake_ea[ch]);
+              v[j] = v[j] + p.snake_ieb[ch] * (sn * sn);
+            }
+          }
+        }
+        __half* hp = p.out16 + m * p.ld16 + ob;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j < width) {
+            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(hp + j) = pk;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+
+void resolve_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  Q3_CHECK(g_encode != nullptr, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+}
+
+CUtensorMap make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  const uint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank,
+           (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return m;
+}
+
+int pick_bn(int N) {
+  if (N <= 256) return N;
+  for (int bn : {256, 192, 128})
+    if (N % bn == 0) return bn;
+  return 256;
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const TcGemm& g) {
+  const int n_out = g.swiglu ? g.N / 2 : g.N;
+  return g.cin % 8 == 0 && g.N % 32 == 0 && g.N >= 32 && g.T >= 1 && g.Bt >= 1 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0 &&
+         (reinterpret_cast<uintptr_t>(g.w) & 15) == 0 && (!g.out32 || (g.ld32 % 4 == 0)) && (!g.out16 || (g.ld16 % 8 == 0)) &&
+         (!g.res || g.ld_res % 4 == 0) && n_out % 16 == 0;
+}
+
+void init_tc_gemm() {
+  resolve_encode();
+  Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+}
+
+void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
+  Q3_CHECK(tc_gemm_supported(g), Q3TTS_ERR_INVALID_ARG, "tc_gemm: unsupported shape (cin %d, N %d)", g.cin, g.N);
+  resolve_encode();
+  TcParams p{};
+  p.Bt = g.Bt; p.T = g.T; p.cin = g.cin; p.N = g.N; p.ntap = g.ntap; p.dil = g.dil;
+  p.bn = pick_bn(g.N);
+  p.kb_per_tap = (g.cin + kBlockK - 1) / kBlockK;
+  p.tiles_per_batch = (g.T + kTileM - 1) / kTileM;
+  const int stage_bytes = kABytes + p.bn * kBlockK * 2;
+  p.stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
+  p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));
+  int cols = 32;
+  while (cols < p.bn) cols <<= 1;
+  p.tmem_cols = cols;
+  p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
+  p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
+  p.snake_ea = g.snake_ea; p.snake_ieb = g.snake_ieb; p.snake_ch = g.snake_ch > 0 ? g.snake_ch : 1;
+
+  const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
+  const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};
+  const uint32_t abox[3] = {(uint32_t)kBlockK, (uint32_t)kTileM, 1};
+  const CUtensorMap ma = make_map(g.a, 3, adims, astr, abox);
+  const uint64_t bdims[2] = {(uint64_t)g.cin, (uint64_t)g.ntap * g.N};
+  const uint64_t bstr[1] = {(uint64_t)g.cin * 2};
+  const uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)p.bn};
+  const CUtensorMap mb = make_map(g.w, 2, bdims, bstr, bbox);
+
+  const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 64 * 8;
+  dim3 grid((unsigned)(g.Bt * p.tiles_per_batch), (unsigned)((g.N + p.bn - 1) / p.bn));
+  tc_gemm_kernel<<<grid, kThreads, smem, c.stream>>>(ma, mb, p);
+  c.tick();
+}
+
+// ---------------------------------------------------------------------------------------------- small fp16 producers
+__global__ void f32_to_f16_kernel(const float* __restrict__ x, size_t n4, __half* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(y)[i] = pk;
+  }
+}
+void launch_f32_to_f16(const LaunchCtx& c, const float* x, size_t n, __half* y) {
+  if (n == 0) return;
+  Q3_CHECK(n % 4 == 0, Q3TTS_ERR_INVALID_ARG, "f32_to_f16: length must be a multiple of 4");
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 32);
+  f32_to_f16_kernel<<<blocks, 256, 0, c.stream>>>(x, n4, y);
+  c.tick();
+}
+
+__global__ void __launch_bounds__(256) rmsnorm_f16_kernel(const float* __restrict__ x, int ldx, int dim, const float* __restrict__ w, float eps,
+                                                          __half* __restrict__ y, int ldy) {
+  __shared__ float red[8];
+  const float* xr = x + (size_t)blockIdx.x * ldx;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < dim; i += 256) { const float v = xr[i]; ss += v * v; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(tot / (float)dim + eps);
+  __half* yr = y + (size_t)blockIdx.x * ldy;
+  for (int i = threadIdx.x; i < dim; i += 256) yr[i] = __float2half_rn(xr[i] * inv * w[i]);
+}
+void launch_rmsnorm_f16(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, __half* y, int ldy) {
+  if (m <= 0) return;
+  rmsnorm_f16_kernel<<<m, 256, 0, c.stream>>>(x, ldx, dim, w, eps, y, ldy);
+  c.tick();
+}
+
+}  // namespace q3

@@ -1,0 +1,48 @@
+// tcgen05 / TMEM / TMA implicit-GEMM for sm_100a: the dense contractions of the codec decoder (causal convs, polyphase
+// transposed convs, linears) and of batched talker decode / prefill.
+//
+//   Y[m, n] = epilogue( sum_tap sum_c A[b, t - shift(tap), c] * W[tap][n][c] ),   m = b*T + t,  shift(tap) = (ntap-1-tap)*dil
+//
+// A: fp16 activations, channels-last [Bt, T, Cin]; rows with negative source time are zero-filled by TMA (causal padding).
+// W: fp16 weights [ntap][N][Cin] (K-major).  Accumulation fp32 in TMEM; epilogue in registers.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "kernels.h"
+
+namespace q3 {
+
+enum TcAct { TC_ACT_NONE = 0, TC_ACT_GELU = 1, TC_ACT_SILU = 2 };
+
+struct TcGemm {
+  // problem
+  const __half* a = nullptr;  // [Bt][T][cin]
+  const __half* w = nullptr;  // [ntap][N][cin]
+  int Bt = 1, T = 0, cin = 0, N = 0, ntap = 1, dil = 1;
+  // epilogue
+  const float* bias = nullptr;   // [N]
+  const float* res = nullptr;    // [M][ld_res]: y = res + scale[n] * (acc + bias)   (may alias out32)
+  int ld_res = 0;
+  const float* scale = nullptr;  // [N] or null (= 1)
+  int act = TC_ACT_NONE;
+  int swiglu = 0;                // columns (2i, 2i+1) = (gate_i, up_i): out column i = silu(gate) * up, N_out = N / 2
+  float* out32 = nullptr;        // [M][ld32] or null
+  int ld32 = 0;
+  __half* out16 = nullptr;       // [M][ld16] or null: fp16 copy (operand of the next contraction)
+  int ld16 = 0;
+  const float* snake_ea = nullptr;   // SnakeBeta of the NEXT layer fused into the fp16 copy: v + ieb[ch] * sin^2(v * ea[ch]),
+  const float* snake_ieb = nullptr;  // ch = n % snake_ch (Vocoder/SpeechTokenizer.swift:105-109)
+  int snake_ch = 0;
+};
+
+// true when the tcgen05 path can run this shape (else the caller uses the SIMT kernel)
+bool tc_gemm_supported(const TcGemm& g);
+void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g);
+void init_tc_gemm();  // resolves cuTensorMapEncodeTiled, sets kernel attributes; once per process/device
+
+// fp32 -> fp16 helpers used around the tensor-core contractions
+void launch_f32_to_f16(const LaunchCtx& c, const float* x, size_t n, __half* y);
+// RMSNorm (fp32 in) -> fp16 out
+void launch_rmsnorm_f16(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, __half* y, int ldy);
+
+}  // namespace q3

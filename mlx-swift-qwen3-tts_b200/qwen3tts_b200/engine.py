@@ -327,3 +327,26 @@ def quantized_matmul(x, packed, scales, biases, group_size=64, bits=4, scale_dty
     A.check(A.lib().q3tts_quantized_matmul(device, x.ctypes.data_as(A.p_f32), m, w.ctypes.data, sp, bp, _DT[scale_dtype], out_f, in_f,
                                            group_size, bits, y.ctypes.data_as(A.p_f32)), None)
     return y
+
+
+def conv_probe(x, w, bias=None, ntap=1, dil=1, act=0, swiglu=False, res=None, scale=None, snake=None, use_tensor_cores=True, device=0):
+    """`q3tts_conv_probe`: x [B,T,cin], w [ntap,N,cin] -> (y32, y16) each [B,T,N or N/2] (fp32 numpy)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    B, T, cin = x.shape
+    nt, N, _ = w.shape
+    assert nt == ntap
+    n_out = N // 2 if swiglu else N
+    f = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32).ctypes.data_as(A.p_f32)
+    keep = [np.ascontiguousarray(a, dtype=np.float32) if a is not None else None for a in (bias, res, scale)]
+    ea = ieb = None
+    sch = 0
+    if snake is not None:
+        ea, ieb = [np.ascontiguousarray(a, dtype=np.float32) for a in snake]
+        sch = int(ea.size)
+    y32 = np.zeros((B, T, n_out), dtype=np.float32)
+    y16 = np.zeros((B, T, n_out), dtype=np.float32)
+    p = lambda a: None if a is None else a.ctypes.data_as(A.p_f32)
+    A.check(A.lib().q3tts_conv_probe(device, p(x), B, T, cin, p(w), p(keep[0]), N, ntap, dil, act, 1 if swiglu else 0, p(keep[1]), p(keep[2]),
+                                     p(ea), p(ieb), sch, 1 if use_tensor_cores else 0, p(y32), p(y16)), None)
+    return y32, y16

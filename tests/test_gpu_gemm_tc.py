@@ -1,0 +1,116 @@
+"""GPU: the tcgen05/TMEM/TMA implicit-GEMM kernel against a float64 numpy restatement of the same causal conv
+(operands rounded to fp16 exactly as the kernel sees them, so the only difference is fp32 accumulation order)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_conv(x, w, bias, ntap, dil, act=0, swiglu=False, res=None, scale=None):
+    x = x.astype(np.float16).astype(np.float64)
+    w = w.astype(np.float16).astype(np.float64)
+    B, T, cin = x.shape
+    N = w.shape[1]
+    y = np.zeros((B, T, N))
+    for tap in range(ntap):
+        sh = (ntap - 1 - tap) * dil
+        if sh >= T:
+            continue
+        xs = np.zeros_like(x)
+        xs[:, sh:] = x[:, : T - sh]
+        y += xs @ w[tap].T
+    if bias is not None:
+        y += bias
+    if act == 1:
+        from math import erf
+        y = 0.5 * y * (1 + np.vectorize(erf)(y / np.sqrt(2)))
+    elif act == 2:
+        y = y / (1 + np.exp(-y))
+    if swiglu:
+        g, u = y[..., 0::2], y[..., 1::2]
+        y = g / (1 + np.exp(-g)) * u
+    if res is not None:
+        y = res + (scale if scale is not None else 1.0) * y
+    return y
+
+
+CASES = [
+    # B, T, cin, N, ntap, dil
+    (1, 128, 64, 64, 1, 1),      # exactly one tile, one k-block
+    (1, 5, 64, 32, 1, 1),        # rows beyond T are zero-filled and masked
+    (2, 200, 128, 96, 1, 1),     # N = 96 (3 x 32 columns), two M tiles per batch item, K = 2 blocks
+    (1, 300, 96, 96, 7, 1),      # cin = 96: second k-block half zero-filled; 7 causal taps
+    (2, 257, 192, 192, 7, 3),    # dilation 3, batch boundary must not leak across items
+    (1, 140, 96, 96, 7, 9),      # dilation 9
+    (1, 64, 512, 1024, 3, 1),    # pre_conv shape, N > 256 -> 4 N tiles of 256
+    (3, 50, 1536, 768, 2, 1),    # polyphase transposed conv (2 taps), long K
+    (1, 40, 1024, 4096, 1, 1),   # pwconv1
+    (1, 130, 1024, 384, 1, 1),   # N = 384 -> 2 tiles of 192
+    (64, 1, 1024, 3072, 1, 1),   # batched decode: 64 utterances x 1 row each (T = 1 per batch item)
+    (1, 64, 1024, 2048, 1, 1),   # the same as one 64-row matrix
+]
+
+
+@pytest.mark.parametrize("B,T,cin,N,ntap,dil", CASES)
+def test_tc_conv_matches_numpy(B, T, cin, N, ntap, dil):
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(B * 7 + T + cin + N + ntap)
+    x = rng.standard_normal((B, T, cin)).astype(np.float32)
+    w = (rng.standard_normal((ntap, N, cin)) / np.sqrt(cin * ntap)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    y32, y16 = q.conv_probe(x, w, bias, ntap=ntap, dil=dil)
+    want = ref_conv(x, w, bias, ntap, dil)
+    err = np.abs(y32 - want).max()
+    print(f"B{B} T{T} cin{cin} N{N} taps{ntap} dil{dil}: max err {err:.2e}")
+    assert err < 2e-4 * max(1.0, np.abs(want).max())
+    assert np.abs(y16 - want).max() < 2e-3 * max(1.0, np.abs(want).max())
+
+
+def test_tc_epilogues():
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(0)
+    B, T, cin, N = 2, 70, 128, 256
+    x = rng.standard_normal((B, T, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, N, cin)) / np.sqrt(cin)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    # GELU
+    y32, _ = q.conv_probe(x, w, bias, act=1)
+    assert np.abs(y32 - ref_conv(x, w, bias, 1, 1, act=1)).max() < 2e-4
+    # residual + per-channel scale
+    res = rng.standard_normal((B, T, N)).astype(np.float32)
+    scale = rng.uniform(0.3, 0.7, N).astype(np.float32)
+    y32, _ = q.conv_probe(x, w, bias, res=res, scale=scale)
+    assert np.abs(y32 - ref_conv(x, w, bias, 1, 1, res=res, scale=scale)).max() < 2e-4
+    # SwiGLU with interleaved (gate, up) columns
+    y32, y16 = q.conv_probe(x, w, None, swiglu=True)
+    want = ref_conv(x, w, None, 1, 1, swiglu=True)
+    assert y32.shape == (B, T, N // 2) and np.abs(y32 - want).max() < 2e-4
+    # SnakeBeta fused into the fp16 copy only
+    ea = np.exp(rng.standard_normal(64) * 0.3).astype(np.float32)
+    ieb = (1 / (np.exp(rng.standard_normal(64) * 0.3) + 1e-9)).astype(np.float32)
+    y32, y16 = q.conv_probe(x, w, bias, snake=(ea, ieb))
+    base = ref_conv(x, w, bias, 1, 1)
+    ch = np.arange(N) % 64
+    assert np.abs(y32 - base).max() < 2e-4
+    assert np.abs(y16 - (base + ieb[ch] * np.sin(base * ea[ch]) ** 2)).max() < 4e-3
+
+
+def test_simt_conv_matches_numpy():
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 37, 12)).astype(np.float32)
+    w = (rng.standard_normal((7, 24, 12)) / 9).astype(np.float32)
+    bias = rng.standard_normal(24).astype(np.float32)
+    y32, _ = q.conv_probe(x, w, bias, ntap=7, dil=3, use_tensor_cores=False)
+    xs, ws = x.astype(np.float64), w.astype(np.float64)
+    want = np.zeros((2, 37, 24))
+    for tap in range(7):
+        sh = (6 - tap) * 3
+        if sh < 37:
+            z = np.zeros_like(xs)
+            z[:, sh:] = xs[:, : 37 - sh]
+            want += z @ ws[tap].T
+    assert np.abs(y32 - (want + bias)).max() < 1e-4
