@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "codec_kernels.h"
+#include "gemm_tc.h"
 
 namespace q3 {
 
@@ -47,6 +48,19 @@ const STensor& need(const std::map<std::string, STensor>& t, const std::string& 
 }
 }  // namespace
 
+const __half* CodecDecoder::upload_f16(const std::vector<float>& h) {
+  std::vector<__half> r(h.size());
+  for (size_t i = 0; i < h.size(); ++i) r[i] = __float2half_rn(h[i]);
+  __half* d = (__half*)arena_.alloc(r.size() * sizeof(__half));
+  Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  return d;
+}
+
+// A contraction can take the tcgen05 path when its K rows are 16-byte multiples (TMA) and N is a multiple of 32 (epilogue chunks).
+void CodecDecoder::finish_weight(ConvW& w) {
+  if (w.cin % 8 != 0 || w.n % 32 != 0) use_tc_ = false;
+}
+
 const float* CodecDecoder::load_vec(const std::map<std::string, STensor>& t, const std::string& key, int n) {
   std::vector<float> h = to_f32_host(need(t, key));
   Q3_CHECK((int)h.size() == n, Q3TTS_ERR_DECODER_LOAD_FAILED, "tensor '%s' has %zu elements, expected %d", key.c_str(), h.size(), n);
@@ -67,8 +81,9 @@ ConvW CodecDecoder::load_conv(const std::map<std::string, STensor>& t, const std
   float* d = arena_.alloc_n<float>(r.size());
   Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
   ConvW w;
-  w.w = d; w.ntap = k; w.dil = dil; w.cin = cin; w.n = cout;
+  w.w = d; w.w16 = upload_f16(r); w.ntap = k; w.dil = dil; w.cin = cin; w.n = cout;
   if (bias) w.bias = load_vec(t, key + ".bias", cout);
+  finish_weight(w);
   return w;
 }
 
@@ -98,7 +113,8 @@ ConvW CodecDecoder::load_convT(const std::map<std::string, STensor>& t, const st
   float* db = arena_.alloc_n<float>(rb.size());
   Q3_CUDA(cudaMemcpy(db, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
   ConvW w;
-  w.w = d; w.bias = db; w.ntap = ntap; w.dil = 1; w.cin = cin; w.n = n;
+  w.w = d; w.w16 = upload_f16(r); w.bias = db; w.ntap = ntap; w.dil = 1; w.cin = cin; w.n = n;
+  finish_weight(w);
   return w;
 }
 
@@ -109,8 +125,9 @@ ConvW CodecDecoder::load_linear(const std::map<std::string, STensor>& t, const s
   float* d = arena_.alloc_n<float>(h.size());
   Q3_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
   ConvW w;
-  w.w = d; w.ntap = 1; w.dil = 1; w.cin = cin; w.n = cout;
+  w.w = d; w.w16 = upload_f16(h); w.ntap = 1; w.dil = 1; w.cin = cin; w.n = cout;
   if (bias) w.bias = load_vec(t, key + ".bias", cout);
+  finish_weight(w);
   return w;
 }
 
@@ -133,6 +150,7 @@ SnakeW CodecDecoder::load_snake(const std::map<std::string, STensor>& t, const s
 CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCounter* counter, int pass_frames)
     : stream_(stream), counter_(counter), pass_frames_(pass_frames) {
   init_codec_kernels();
+  init_tc_gemm();
   // config candidates (Qwen3TTSPipeline.swift:191-199)
   std::string cfg_path;
   for (const char* name : {"config.json", "configuration.json", "speech_tokenizer_config.json"}) {
@@ -183,7 +201,8 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
       }
     float* d = arena_.alloc_n<float>(r.size());
     Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
-    rvq_proj_.w = d; rvq_proj_.ntap = 1; rvq_proj_.dil = 1; rvq_proj_.cin = 2 * D; rvq_proj_.n = c.codebook_dim;
+    rvq_proj_.w = d; rvq_proj_.w16 = upload_f16(r); rvq_proj_.ntap = 1; rvq_proj_.dil = 1; rvq_proj_.cin = 2 * D; rvq_proj_.n = c.codebook_dim;
+    finish_weight(rvq_proj_);
   }
   pre_conv_ = load_conv(t, "decoder.pre_conv.conv", L, c.codebook_dim, 3, 1, true);
   const std::string pt = "decoder.pre_transformer";
@@ -204,12 +223,26 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     float* d = arena_.alloc_n<float>(w.size());
     Q3_CUDA(cudaMemcpy(d, w.data(), w.size() * 4, cudaMemcpyHostToDevice));
     ConvW cw;
-    cw.w = d; cw.ntap = 1; cw.dil = 1; cw.cin = cin; cw.n = n;
+    cw.w = d; cw.w16 = upload_f16(w); cw.ntap = 1; cw.dil = 1; cw.cin = cin; cw.n = n;
     if (bias) {
       float* db = arena_.alloc_n<float>(b.size());
       Q3_CUDA(cudaMemcpy(db, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
       cw.bias = db;
     }
+    finish_weight(cw);
+    return cw;
+  };
+  // (gate_i, up_i) row-interleaved copy: the tcgen05 epilogue pairs adjacent columns for SwiGLU
+  auto interleaved_gate_up = [&](const std::string& gate_key, const std::string& up_key, int inter, int cin) {
+    std::vector<float> g = to_f32_host(need(t, gate_key + ".weight")), u = to_f32_host(need(t, up_key + ".weight")), r((size_t)2 * inter * cin);
+    for (int i = 0; i < inter; ++i)
+      for (int k = 0; k < cin; ++k) {
+        r[((size_t)2 * i) * cin + k] = g[(size_t)i * cin + k];
+        r[((size_t)2 * i + 1) * cin + k] = u[(size_t)i * cin + k];
+      }
+    ConvW cw;
+    cw.w16 = upload_f16(r); cw.ntap = 1; cw.dil = 1; cw.cin = cin; cw.n = 2 * inter;
+    finish_weight(cw);
     return cw;
   };
   for (int i = 0; i < c.num_hidden_layers; ++i) {
@@ -218,6 +251,7 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     l.qkv = concat_linear({lp + ".self_attn.q_proj", lp + ".self_attn.k_proj", lp + ".self_attn.v_proj"}, {qd, kvd, kvd}, hs, c.attention_bias);
     l.o = load_linear(t, lp + ".self_attn.o_proj", hs, qd, c.attention_bias);
     l.gate_up = concat_linear({lp + ".mlp.gate_proj", lp + ".mlp.up_proj"}, {c.intermediate_size, c.intermediate_size}, hs, false);
+    l.gate_up_il = interleaved_gate_up(lp + ".mlp.gate_proj", lp + ".mlp.up_proj", c.intermediate_size, hs);
     l.down = load_linear(t, lp + ".mlp.down_proj", hs, c.intermediate_size, false);
     l.in_norm = load_vec(t, lp + ".input_layernorm.weight", hs);
     l.post_norm = load_vec(t, lp + ".post_attention_layernorm.weight", hs);
@@ -306,10 +340,15 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
   }
   fl += rate * 2ll * 7 * out_ch_;
   flops_per_frame_ = fl;
+  if ((c.num_attention_heads * hd) % 8 != 0 || c.intermediate_size % 16 != 0 || hs % 8 != 0 || L % 8 != 0 || out_ch_ % 8 != 0) use_tc_ = false;
+  if (const char* e = getenv("Q3TTS_CODEC_SIMT"))
+    if (e[0] == '1') use_tc_ = false;  // A/B switch: run the fp32 SIMT pipeline
 }
 
 CodecDecoder::~CodecDecoder() {
   for (float*& p : ws_)
+    if (p) { cudaFree(p); p = nullptr; }
+  for (__half*& p : hs_)
     if (p) { cudaFree(p); p = nullptr; }
 }
 
@@ -327,9 +366,14 @@ void CodecDecoder::ensure_workspace(int frames) {
   Q3_CUDA(cudaStreamSynchronize(stream_));
   for (float*& p : ws_)
     if (p) { cudaFree(p); p = nullptr; }
+  for (__half*& p : hs_)
+    if (p) { cudaFree(p); p = nullptr; }
   ws_floats_ = (size_t)per * frames;
   ws_bytes_ = 0;
-  for (float*& p : ws_) { Q3_CUDA(cudaMalloc(&p, ws_floats_ * sizeof(float))); ws_bytes_ += ws_floats_ * sizeof(float); }
+  const int n32 = use_tc_ ? 3 : 4;
+  for (int i = 0; i < n32; ++i) { Q3_CUDA(cudaMalloc(&ws_[i], ws_floats_ * sizeof(float))); ws_bytes_ += ws_floats_ * sizeof(float); }
+  if (use_tc_)
+    for (__half*& p : hs_) { Q3_CUDA(cudaMalloc(&p, ws_floats_ * sizeof(__half))); ws_bytes_ += ws_floats_ * sizeof(__half); }
   ws_frames_ = frames;
 }
 
@@ -342,6 +386,89 @@ void CodecDecoder::rvq_embed(const int32_t* d_codes, int B, int T, float* d_firs
 }
 
 void CodecDecoder::decode_pass(const int32_t* d_codes, int B, int T, float* d_pcm) {
+  if (use_tc_) decode_pass_tc(d_codes, B, T, d_pcm);
+  else decode_pass_simt(d_codes, B, T, d_pcm);
+}
+
+// tcgen05 pipeline: every dense contraction is one launch of the implicit-GEMM kernel with its elementwise neighbours fused
+// into the epilogue (bias, GELU, SwiGLU, LayerScale/gamma + residual, and the SnakeBeta of the NEXT layer applied to the fp16
+// operand copy), fp32 residual streams, fp16 operands.
+void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d_pcm) {
+  const CodecConfig& c = cfg_;
+  const LaunchCtx lc = ctx();
+  const int N = B * T;
+  if (N <= 0) return;
+  Q3_CHECK(N <= pass_frames_, Q3TTS_ERR_CAPACITY, "codec pass of %d frames exceeds pass capacity %d", N, pass_frames_);
+  ensure_workspace(N);
+  float *F0 = ws_[0], *F1 = ws_[1];
+  __half *H0 = hs_[0], *H1 = hs_[1], *H2 = hs_[2];
+  const int hs = c.hidden_size, nh = c.num_attention_heads, nkv = c.num_key_value_heads, hd = c.head_dim, I = c.intermediate_size, L = c.latent_dim;
+  const int qkvw = (nh + 2 * nkv) * hd;
+  auto gemm = [&](const ConvW& w, const __half* a, int Bt, int Tt) {
+    TcGemm g;
+    g.a = a; g.w = w.w16; g.Bt = Bt; g.T = Tt; g.cin = w.cin; g.N = w.n; g.ntap = w.ntap; g.dil = w.dil; g.bias = w.bias;
+    return g;
+  };
+  auto with_snake = [](TcGemm& g, const SnakeW& s) { g.snake_ea = s.alpha; g.snake_ieb = s.beta; g.snake_ch = s.ch; };
+  // quantizer.decode -> preConv (SpeechTokenizer.swift:922-923)
+  launch_rvq_embed_f16(lc, d_codes, d_codebooks_, c.num_quantizers, c.num_semantic_quantizers, vq_dim(), c.codebook_size, N, H0);
+  { TcGemm g = gemm(rvq_proj_, H0, B, T); g.out16 = H1; g.ld16 = c.codebook_dim; launch_tc_gemm(lc, g); }
+  { TcGemm g = gemm(pre_conv_, H1, B, T); g.out16 = H0; g.ld16 = L; launch_tc_gemm(lc, g); }
+  // preTransformer (:464-487): fp32 residual stream in F0
+  { TcGemm g = gemm(tr_in_, H0, B, T); g.out32 = F0; g.ld32 = hs; launch_tc_gemm(lc, g); }
+  for (auto& l : tl_) {
+    launch_rmsnorm_f16(lc, F0, hs, N, hs, l.in_norm, c.rms_norm_eps, H0, hs);
+    { TcGemm g = gemm(l.qkv, H0, B, T); g.out32 = F1; g.ld32 = qkvw; launch_tc_gemm(lc, g); }
+    launch_codec_rope(lc, F1, qkvw, N, T, nh + nkv, d_inv_freq_);
+    launch_codec_attention_f16(lc, F1, qkvw, B, T, nh, nkv, H1, nh * hd);
+    { TcGemm g = gemm(l.o, H1, B, T); g.res = F0; g.ld_res = hs; g.scale = l.attn_scale; g.out32 = F0; g.ld32 = hs; launch_tc_gemm(lc, g); }
+    launch_rmsnorm_f16(lc, F0, hs, N, hs, l.post_norm, c.rms_norm_eps, H0, hs);
+    { TcGemm g = gemm(l.gate_up_il, H0, B, T); g.swiglu = 1; g.out16 = H1; g.ld16 = I; launch_tc_gemm(lc, g); }
+    { TcGemm g = gemm(l.down, H1, B, T); g.res = F0; g.ld_res = hs; g.scale = l.mlp_scale; g.out32 = F0; g.ld32 = hs; launch_tc_gemm(lc, g); }
+  }
+  launch_rmsnorm_f16(lc, F0, hs, N, hs, tr_norm_, c.rms_norm_eps, H0, hs);
+  { TcGemm g = gemm(tr_out_, H0, B, T); g.out16 = H1; g.ld16 = L; launch_tc_gemm(lc, g); }
+  // upsample stages (:928-936): cur16 = H1
+  int Tc = T;
+  __half *cur = H1, *oa = H0, *ob = H2;
+  for (auto& u : ups_) {
+    { TcGemm g = gemm(u.convT, cur, B, Tc); g.out32 = F0; g.ld32 = u.convT.n; launch_tc_gemm(lc, g); }  // [B, Tc, f*L] == [B, Tc*f, L]
+    Tc *= u.factor;
+    const int M = B * Tc;
+    launch_dwconv7(lc, F0, u.dw_w, u.dw_b, L, Tc, M, F1);
+    launch_layernorm_f16(lc, F1, M, L, u.ln_w, u.ln_b, 1e-6f, oa);
+    { TcGemm g = gemm(u.pw1, oa, B, Tc); g.act = TC_ACT_GELU; g.out16 = ob; g.ld16 = 4 * L; launch_tc_gemm(lc, g); }
+    { TcGemm g = gemm(u.pw2, ob, B, Tc); g.res = F0; g.ld_res = L; g.scale = u.gamma; g.out16 = cur; g.ld16 = L; launch_tc_gemm(lc, g); }
+  }
+  // decoder[0] initial conv (:786-803) with block 0's SnakeBeta fused into its fp16 output
+  {
+    TcGemm g = gemm(init_conv_, cur, B, Tc);
+    g.out16 = oa; g.ld16 = c.decoder_dim;
+    if (!blocks_.empty()) with_snake(g, blocks_[0].snake); else with_snake(g, out_snake_);
+    launch_tc_gemm(lc, g);
+  }
+  std::swap(cur, oa);  // cur = snake(init conv output)
+  for (size_t bi = 0; bi < blocks_.size(); ++bi) {  // DecoderBlock (:753-784)
+    Block& b = blocks_[bi];
+    // polyphase transposed conv: y (fp32 residual stream, F0) and snake_act1(y) (fp16 operand)
+    { TcGemm g = gemm(b.convT, cur, B, Tc); g.out32 = F0; g.ld32 = b.convT.n; g.out16 = oa; g.ld16 = b.convT.n; with_snake(g, b.unit[0].act1); launch_tc_gemm(lc, g); }
+    Tc *= b.rate;
+    for (int j = 0; j < 3; ++j) {  // DecoderResidualUnit (:696-718)
+      { TcGemm g = gemm(b.unit[j].conv1, oa, B, Tc); g.out16 = ob; g.ld16 = b.cout; with_snake(g, b.unit[j].act2); launch_tc_gemm(lc, g); }
+      TcGemm g = gemm(b.unit[j].conv2, ob, B, Tc);
+      g.res = F0; g.ld_res = b.cout;
+      const bool last_unit = j == 2;
+      if (!last_unit) { g.out32 = F0; g.ld32 = b.cout; }
+      g.out16 = last_unit ? cur : oa; g.ld16 = b.cout;
+      const SnakeW& next = !last_unit ? b.unit[j + 1].act1 : (bi + 1 < blocks_.size() ? blocks_[bi + 1].snake : out_snake_);
+      with_snake(g, next);
+      launch_tc_gemm(lc, g);
+    }
+  }
+  launch_out_conv_f16(lc, cur, out_w_, out_b_, out_ch_, B, Tc, d_pcm);
+}
+
+void CodecDecoder::decode_pass_simt(const int32_t* d_codes, int B, int T, float* d_pcm) {
   const CodecConfig& c = cfg_;
   const LaunchCtx lc = ctx();
   const int N = B * T;

@@ -139,8 +139,14 @@ void launch_dwconv7(const LaunchCtx& c, const float* x, const float* w, const fl
   c.tick();
 }
 
+__device__ __forceinline__ void store_out(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_out(__half* p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ float load_in(const float* p) { return *p; }
+__device__ __forceinline__ float load_in(const __half* p) { return __half2float(*p); }
+
+template <typename OutT>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, int C, const float* __restrict__ w,
-                                                        const float* __restrict__ b, float eps, float* __restrict__ y) {
+                                                        const float* __restrict__ b, float eps, OutT* __restrict__ y) {
   __shared__ float red[8], red2[8];
   const float* xr = x + (size_t)blockIdx.x * C;
   float s = 0.f;
@@ -161,12 +167,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int i = 0; i < 8; ++i) var += red2[i];
   const float inv = rsqrtf(var / (float)C + eps);
-  float* yr = y + (size_t)blockIdx.x * C;
-  for (int i = threadIdx.x; i < C; i += 256) yr[i] = (xr[i] - mean) * inv * w[i] + b[i];
+  OutT* yr = y + (size_t)blockIdx.x * C;
+  for (int i = threadIdx.x; i < C; i += 256) store_out(yr + i, (xr[i] - mean) * inv * w[i] + b[i]);
 }
 void launch_layernorm(const LaunchCtx& c, const float* x, int rows, int C, const float* w, const float* b, float eps, float* y) {
   if (rows <= 0) return;
-  layernorm_kernel<<<rows, 256, 0, c.stream>>>(x, C, w, b, eps, y);
+  layernorm_kernel<float><<<rows, 256, 0, c.stream>>>(x, C, w, b, eps, y);
+  c.tick();
+}
+void launch_layernorm_f16(const LaunchCtx& c, const float* x, int rows, int C, const float* w, const float* b, float eps, __half* y) {
+  if (rows <= 0) return;
+  layernorm_kernel<__half><<<rows, 256, 0, c.stream>>>(x, C, w, b, eps, y);
   c.tick();
 }
 
@@ -207,8 +218,9 @@ void launch_codec_rope(const LaunchCtx& c, float* qkv, int ld, int M, int T, int
 }
 
 // Full-causal MHA, head_dim 64, online softmax; grid (q tiles of 16, heads, batch), 4 warps x 4 query rows.
+template <typename OutT>
 __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __restrict__ qkv, int ld, int T, int nh, int nkv, float scale,
-                                                              float* __restrict__ out, int ldo) {
+                                                              OutT* __restrict__ out, int ldo) {
   __shared__ float Ks[32][65];
   __shared__ float Vs[32][64];
   __shared__ float Qs[16][64];
@@ -264,15 +276,21 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
   for (int i = 0; i < 4; ++i) {
     const int row = r0 + warp * 4 + i;
     if (row >= T) continue;
-    float* o = out + ((size_t)b * T + row) * ldo + h * 64;
-    o[lane] = acc[i][0] / li[i];
-    o[lane + 32] = acc[i][1] / li[i];
+    OutT* o = out + ((size_t)b * T + row) * ldo + h * 64;
+    store_out(o + lane, acc[i][0] / li[i]);
+    store_out(o + lane + 32, acc[i][1] / li[i]);
   }
 }
 void launch_codec_attention(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo) {
   if (B <= 0 || T <= 0) return;
   dim3 grid((T + 15) / 16, nh, B);
-  codec_attention_kernel<<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
+  codec_attention_kernel<float><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
+  c.tick();
+}
+void launch_codec_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, __half* out, int ldo) {
+  if (B <= 0 || T <= 0) return;
+  dim3 grid((T + 15) / 16, nh, B);
+  codec_attention_kernel<__half><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
   c.tick();
 }
 
@@ -300,17 +318,41 @@ void launch_rvq_embed(const LaunchCtx& c, const int* codes, const float* const* 
   c.tick();
 }
 
+__global__ void rvq_embed_f16_kernel(const int* __restrict__ codes, const float* const* __restrict__ codebooks, int Q, int n_sem, int D,
+                                     int size, int M, __half* __restrict__ emb) {
+  const int m = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float first = 0.f, rest = 0.f;
+    for (int q = 0; q < Q; ++q) {
+      int code = codes[(size_t)m * Q + q];
+      code = min(max(code, 0), size - 1);
+      const float v = codebooks[q][(size_t)code * D + d];
+      if (q < n_sem) first = __fadd_rn(first, v);
+      else rest = __fadd_rn(rest, v);
+    }
+    emb[(size_t)m * 2 * D + d] = __float2half_rn(first);
+    emb[(size_t)m * 2 * D + D + d] = __float2half_rn(rest);
+  }
+}
+void launch_rvq_embed_f16(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
+                          __half* emb16) {
+  if (M <= 0) return;
+  rvq_embed_f16_kernel<<<M, 128, 0, c.stream>>>(codes, codebooks, Q, n_sem, D, size, M, emb16);
+  c.tick();
+}
+
 // DecoderOutputConv (k = 7, C -> 1) + clip(-1, 1) (SpeechTokenizer.swift:823-840, 951); x is already snake-activated.
-__global__ void __launch_bounds__(128) out_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[7][C]*/,
+template <typename InT>
+__global__ void __launch_bounds__(128) out_conv_kernel(const InT* __restrict__ x, const float* __restrict__ w /*[7][C]*/,
                                                        const float* __restrict__ bias, int C, int T, float* __restrict__ y) {
   extern __shared__ float xs[];  // [(128 + 6)][C + 1]  (+1: consecutive threads read consecutive rows)
   const int b = blockIdx.y, t0 = blockIdx.x * 128;
-  const float* xb = x + (size_t)b * T * C;
+  const InT* xb = x + (size_t)b * T * C;
   const int rows = 134, ldc = C + 1;
   for (int i = threadIdx.x; i < rows * C; i += 128) {
     const int r = i / C, ch = i - r * C;
     const int t = t0 - 6 + r;
-    xs[r * ldc + ch] = (t >= 0 && t < T) ? xb[(size_t)t * C + ch] : 0.f;
+    xs[r * ldc + ch] = (t >= 0 && t < T) ? load_in(xb + (size_t)t * C + ch) : 0.f;
   }
   __syncthreads();
   const int t = t0 + threadIdx.x;
@@ -326,12 +368,19 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const float* __restrict__
 void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y) {
   if (B <= 0 || T <= 0) return;
   dim3 grid((T + 127) / 128, B);
-  out_conv_kernel<<<grid, 128, (size_t)134 * (C + 1) * sizeof(float), c.stream>>>(x, w, bias, C, T, y);
+  out_conv_kernel<float><<<grid, 128, (size_t)134 * (C + 1) * sizeof(float), c.stream>>>(x, w, bias, C, T, y);
+  c.tick();
+}
+void launch_out_conv_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y) {
+  if (B <= 0 || T <= 0) return;
+  dim3 grid((T + 127) / 128, B);
+  out_conv_kernel<__half><<<grid, 128, (size_t)134 * (C + 1) * sizeof(float), c.stream>>>(x, w, bias, C, T, y);
   c.tick();
 }
 
 void init_codec_kernels() {
-  Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 }
 
 }  // namespace q3

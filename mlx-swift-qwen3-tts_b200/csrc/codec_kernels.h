@@ -13,11 +13,17 @@ void launch_conv_gemm(const LaunchCtx& c, const float* x, const ConvW& w, float*
 void launch_snake(const LaunchCtx& c, const float* x, const SnakeW& s, size_t rows, float* y);
 void launch_dwconv7(const LaunchCtx& c, const float* x, const float* w, const float* b, int C, int T, size_t rows, float* y);
 void launch_layernorm(const LaunchCtx& c, const float* x, int rows, int C, const float* w, const float* b, float eps, float* y);
+void launch_layernorm_f16(const LaunchCtx& c, const float* x, int rows, int C, const float* w, const float* b, float eps, __half* y);
 void launch_silu_mul(const LaunchCtx& c, const float* gu, size_t rows, int I, float* y);
 void launch_codec_rope(const LaunchCtx& c, float* qkv, int ld, int M, int T, int n_rot_heads, const float* inv_freq);
 void launch_codec_attention(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo);
+void launch_codec_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, __half* out, int ldo);
 void launch_rvq_embed(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
                       float* emb);
 void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y);
+void launch_out_conv_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y);
+// emb fp32 [M][2D] (bit-exact gather-sums) and/or its fp16 copy
+void launch_rvq_embed_f16(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
+                          __half* emb16);
 
 }  // namespace q3

@@ -1,5 +1,7 @@
 // Launchers of the hand-written sm_100a kernels (talker side).  Every launcher counts itself into LaunchCtx.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "model.h"
 
 namespace q3 {
@@ -41,6 +43,13 @@ void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, i
 void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                       const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out,
                       int ldo);
+
+// same attention, fp16 output (A operand of the tcgen05 o_proj)
+void launch_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                          const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, __half* out, int ldo);
+// dense weight (bf16 / f16 / f32) -> fp16 copy; optional row interleave of two halves ([gate ; up] -> gate_0, up_0, gate_1, ...)
+void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst);
+void launch_gather_rows_f16(const LaunchCtx& c, const Embedding& e, const int* ids, int n, __half* y, int ldy);
 
 // rows of an embedding table -> fp32: y[i][:] (= or +=) table[ids[i]][:]
 void launch_gather_rows(const LaunchCtx& c, const Embedding& e, const int* ids, int n, float* y, int ldy, bool accumulate);

@@ -427,10 +427,13 @@ void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, i
 // ------------------------------------------------------------------------------------------------ window attention (decode + prefill)
 // grid (row, kv_head), 128 threads.  Keys = absolute positions [win_start[slot], row_pos] of the row's slot, read
 // through the ring.  G = heads / kv_heads query heads share the K/V reads (GQA, head h uses kv head h / G).
-template <int G>
+__device__ __forceinline__ void store_act(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_act(__half* p, float v) { *p = __float2half_rn(v); }
+
+template <int G, typename OutT>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                         const int* __restrict__ row_slot, const int* __restrict__ row_pos,
-                                                        const int* __restrict__ win_start, KVLayout kv, float* __restrict__ out,
+                                                        const int* __restrict__ win_start, KVLayout kv, OutT* __restrict__ out,
                                                         int ldo, float scale) {
   extern __shared__ __align__(16) float sm[];
   float* q = sm;                 // [G][128]
@@ -483,10 +486,11 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
     for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
   }
 #pragma unroll
-  for (int g = 0; g < G; ++g) out[(size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid] = o[g] / red_sum[g];
+  for (int g = 0; g < G; ++g) store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, o[g] / red_sum[g]);
 }
-void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
-                      const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out, int ldo) {
+template <typename OutT>
+static void launch_attention_t(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                               const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, OutT* out, int ldo) {
   Q3_CHECK(head_dim == 128, Q3TTS_ERR_BAD_CONFIG, "talker kernels are specialised for head_dim 128 (got %d)", head_dim);
   if (m <= 0) return;
   const int G = heads / kv_heads;
@@ -495,12 +499,49 @@ void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int h
   dim3 grid(m, kv_heads);
 #define Q3_ATT(GV)                                                                                                     \
   {                                                                                                                    \
-    attention_kernel<GV><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
+    attention_kernel<GV, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
   }
   Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
   if (G == 1) Q3_ATT(1) else if (G == 2) Q3_ATT(2) else if (G == 4) Q3_ATT(4)
   else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
 #undef Q3_ATT
+  c.tick();
+}
+void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                      const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out, int ldo) {
+  launch_attention_t<float>(c, qkv, ld, m, heads, kv_heads, head_dim, row_slot, row_pos, win_start, kv, out, ldo);
+}
+void launch_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
+                          const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, __half* out, int ldo) {
+  launch_attention_t<__half>(c, qkv, ld, m, heads, kv_heads, head_dim, row_slot, row_pos, win_start, kv, out, ldo);
+}
+
+__global__ void weight_to_f16_kernel(const void* __restrict__ w, int dt, int rows, int cols, int interleave, __half* __restrict__ dst) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), cidx = (int)(i - (size_t)r * cols);
+    int dr = r;
+    if (interleave) dr = r < rows / 2 ? 2 * r : 2 * (r - rows / 2) + 1;
+    dst[(size_t)dr * cols + cidx] = __float2half_rn(load_as_f32(w, i, dt));
+  }
+}
+void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst) {
+  const size_t total = (size_t)rows * cols;
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  weight_to_f16_kernel<<<blocks, 256, 0, c.stream>>>(w, dt, rows, cols, interleave_halves ? 1 : 0, dst);
+  c.tick();
+}
+
+__global__ void gather_rows_f16_kernel(Embedding e, const int* __restrict__ ids, __half* __restrict__ y, int ldy) {
+  const int row = blockIdx.x;
+  const int id = ids[row];
+  for (int d = threadIdx.x; d < e.dim; d += blockDim.x)
+    y[(size_t)row * ldy + d] = (id >= 0 && id < e.rows) ? __float2half_rn(load_as_f32(e.w, (size_t)id * e.dim + d, e.dt)) : __float2half_rn(0.f);
+}
+void launch_gather_rows_f16(const LaunchCtx& c, const Embedding& e, const int* ids, int n, __half* y, int ldy) {
+  if (n <= 0) return;
+  gather_rows_f16_kernel<<<n, 256, 0, c.stream>>>(e, ids, y, ldy);
   c.tick();
 }
 
@@ -877,9 +918,12 @@ void init_talker_kernels() {
   init_linear_fmt<W_BF16>();
   init_linear_fmt<W_F16>();
   init_linear_fmt<W_F32>();
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
 }
 
 }  // namespace q3

@@ -113,6 +113,14 @@ def preset(name: str) -> tuple[TalkerDims, CodecDims]:
         c = CodecDims(latent_dim=128, codebook_dim=64, decoder_dim=192, hidden_size=128, intermediate_size=256,
                       num_attention_heads=2, num_key_value_heads=2, num_hidden_layers=2)
         return t, c
+    if name == "tcsmall":  # tiny talker + a codec whose every contraction fits the tcgen05 path (cin % 8 == 0, N % 32 == 0)
+        t, _ = preset("tiny")
+        c = CodecDims(latent_dim=128, codebook_dim=64, decoder_dim=512, hidden_size=128, intermediate_size=256,
+                      num_attention_heads=2, num_key_value_heads=2, num_hidden_layers=2)
+        return t, c
+    if name == "codecfull":  # tiny talker + the full-size codec decoder (SpeechTokenizer.swift:42-74 defaults)
+        t, _ = preset("tiny")
+        return t, CodecDims()
     if name == "tiny-mrope":
         t, c = preset("tiny")
         t.mrope_section = [24, 20, 20]

@@ -149,3 +149,40 @@ def test_pipeline_api(tiny8, tmp_path):
         q.Qwen3TTSPipeline(str(tmp_path / "missing"))
     p.clear_cache()
     p.close()
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 pipeline
+@pytest.mark.parametrize("preset,cases", [("tcsmall", [(1, 1), (1, 7), (2, 18), (1, 26), (3, 33), (1, 140)]), ("codecfull", [(1, 3), (2, 5)])])
+def test_decode_tensor_core_path(preset, cases, engines, oracles):
+    """Same parity bar on checkpoints whose codec runs the tcgen05/TMEM pipeline (fp16 operands, fp32 accumulate/residuals)."""
+    d = ckpt(preset, 8)
+    eng, codec = engines(d), oracles(d, "codec")
+    for B, T in cases:
+        codes = rand_codes(B, T, B * 31 + T)
+        got = eng.decode(codes)
+        want = oracle_decode(codec, codes)
+        s = snr_db(got, want)
+        print(f"[{preset}] decode B={B} T={T}: SNR {s:.1f} dB, max|err| {np.abs(got - want).max():.2e}")
+        assert s >= SNR_DB
+
+
+def test_tensor_core_vs_simt_pipeline(engines, monkeypatch):
+    """A/B: the two codec pipelines of the engine agree with each other far inside the parity bar."""
+    import qwen3tts_b200 as q
+
+    d = ckpt("tcsmall", 8)
+    codes = rand_codes(2, 21, 9)
+    a = engines(d).decode(codes)
+    monkeypatch.setenv("Q3TTS_CODEC_SIMT", "1")
+    e2 = q.Engine(d, max_frames=64, load_talker=False)
+    b = e2.decode(codes)
+    e2.close()
+    assert snr_db(a, b) >= 45.0
+
+
+def test_chunked_decode_tensor_core(engines, oracles):
+    d = ckpt("tcsmall", 8)
+    codes = rand_codes(2, 45, 3)
+    got = engines(d).decode_chunked(codes, 20, 4)
+    want = oracles(d, "codec").chunked_decode(torch.as_tensor(codes).transpose(1, 2).contiguous(), 20, 4).reshape(2, -1).numpy()
+    assert snr_db(got, want) >= SNR_DB
