@@ -67,6 +67,11 @@ class TalkerEngine {
   void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
                      const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity);
   void issue_frame(int n_slots);
+  void build_tc_weights();
+  TcLinear make_tc(const Linear& L, bool interleave_halves);
+  bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }
+  // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
+  void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
 
   TalkerConfig cfg_;
@@ -78,6 +83,8 @@ class TalkerEngine {
   int weight_dtype_ = Q3TTS_BF16, eff_bits_ = 0, eff_group_ = 64;
 
   int max_rows_ = 0, max_tp_rows_ = 0, set_words_ = 0;
+  int tc_min_rows_ = 16;  // rows from which linears run on tensor cores (env Q3TTS_TC_MIN_ROWS; 0 disables)
+  void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;
   // device buffers
   float *kcache_ = nullptr, *vcache_ = nullptr, *cp_k_ = nullptr, *cp_v_ = nullptr;
   size_t kv_slot_stride_ = 0, kv_layer_stride_ = 0, cpkv_slot_stride_ = 0, cpkv_layer_stride_ = 0;

@@ -288,11 +288,18 @@ CUtensorMap make_map(const void* base, int rank, const uint64_t* dims, const uin
   return m;
 }
 
-int pick_bn(int N) {
-  if (N <= 256) return N;
-  for (int bn : {256, 192, 128})
-    if (N % bn == 0) return bn;
-  return 256;
+// Tile width: the largest multiple of 32 (<= 256) dividing N that still yields >= one CTA per SM; small-M problems (batched
+// decode) fall through to narrow tiles so the weight stream is spread over many SMs.
+int pick_bn(int N, int tiles_m) {
+  int best = 0, smallest = 0;
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (N % bn != 0) continue;
+    smallest = bn;
+    if (best == 0 && (long long)tiles_m * (N / bn) >= 148) best = bn;
+  }
+  if (best) return best;
+  if (smallest) return smallest;
+  return N <= 256 ? N : 256;
 }
 
 }  // namespace
@@ -314,9 +321,9 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   resolve_encode();
   TcParams p{};
   p.Bt = g.Bt; p.T = g.T; p.cin = g.cin; p.N = g.N; p.ntap = g.ntap; p.dil = g.dil;
-  p.bn = pick_bn(g.N);
   p.kb_per_tap = (g.cin + kBlockK - 1) / kBlockK;
   p.tiles_per_batch = (g.T + kTileM - 1) / kTileM;
+  p.bn = pick_bn(g.N, g.Bt * p.tiles_per_batch);
   const int stage_bytes = kABytes + p.bn * kBlockK * 2;
   p.stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
   p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));

@@ -53,6 +53,13 @@ struct Linear {
   }
 };
 
+// fp16 dense copy of a Linear for the tcgen05 path (rows >= 16: batched decode, prefill)
+struct TcLinear {
+  const void* w = nullptr;  // __half [out][in]
+  int out = 0, in = 0;
+  const float* bias = nullptr;
+};
+
 struct Embedding {
   const void* w = nullptr;
   int rows = 0, dim = 0, dt = Q3TTS_BF16;
@@ -66,10 +73,13 @@ struct LayerWeights {
   const float *in_norm = nullptr, *post_norm = nullptr, *q_norm = nullptr, *k_norm = nullptr;  // fp32
 };
 
+struct LayerTc { TcLinear qkv, o, gate_up_il /* rows interleaved (gate_i, up_i) */, down; };
+
 struct StackWeights {  // a Qwen3 decoder stack (talker or code predictor)
   int hidden = 0, layers = 0, heads = 0, kv_heads = 0, head_dim = 128, inter = 0;
   float eps = 1e-6f, theta = 1e6f;
   std::vector<LayerWeights> layer;
+  std::vector<LayerTc> tc;  // empty when the tcgen05 copies were not built
   const float* final_norm = nullptr;
 };
 
@@ -82,6 +92,9 @@ struct TalkerWeights {
   std::vector<Linear> lm_head;                // 15
   Linear small_to_mtp;                        // out == 0 when absent
   bool has_mtp = false;
+  TcLinear fc1_tc, fc2_tc, codec_head_tc, small_to_mtp_tc;
+  std::vector<TcLinear> lm_head_tc;
+  bool has_tc = false;
   size_t talker_step_bytes = 0, cp_pass_bytes = 0;  // algorithmic weight bytes per invocation
 };
 

@@ -5,6 +5,7 @@
 #include <cmath>
 
 #include "engine.h"
+#include "gemm_tc.h"
 
 namespace q3 {
 
@@ -68,6 +69,17 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   d_spk_ = arena_.alloc_n<float>(H);
   d_ids_ = arena_.alloc_n<int>(max_tp_rows_);
   d_desc_ = arena_.alloc_n<int>((size_t)3 * C);
+  // tensor-core copies: built when the handle can see >= tc_min_rows_ rows at once (batched decode, or any prefill)
+  if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) tc_min_rows_ = atoi(e);
+  if (tc_min_rows_ > 0) {
+    init_tc_gemm();
+    build_tc_weights();
+    d_h16_ = arena_.alloc((size_t)max_rows_ * std::max(wide_h, cfg_.text_hidden_size) * 2);
+    d_attn16_ = arena_.alloc((size_t)max_rows_ * attn_w * 2);
+    d_act16_ = arena_.alloc((size_t)max_rows_ * act_w * 2);
+    d_tpe16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
+    d_tph16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
+  }
   d_probe_logits_ = arena_.alloc_n<float>(4096);
   d_probe_set_ = arena_.alloc_n<unsigned>(128);
   d_probe_out_ = arena_.alloc_n<int>(1);
@@ -132,12 +144,90 @@ void TalkerEngine::drop_graphs() {
   graphs_.clear();
 }
 
+// fp16 dense copy of one Linear for the tcgen05 path.  Packed leaves go through the bit-exact dequant kernel (deq16 =
+// round(fp32(scale) * q + fp32(bias))), float leaves are rounded to fp16.
+TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves) {
+  const LaunchCtx c{stream_, nullptr};
+  TcLinear t;
+  t.out = L.out; t.in = L.in; t.bias = L.bias;
+  __half* dst = (__half*)arena_.alloc((size_t)L.out * L.in * 2);
+  if (L.bits) {
+    if (!interleave_halves) {
+      launch_dequantize(c, L.qw, L.scales, L.biases, L.sdt, L.out, L.in, L.group, L.bits, Q3TTS_F16, dst);
+    } else {
+      __half* tmp = nullptr;
+      Q3_CUDA(cudaMalloc(&tmp, (size_t)L.out * L.in * 2));
+      launch_dequantize(c, L.qw, L.scales, L.biases, L.sdt, L.out, L.in, L.group, L.bits, Q3TTS_F16, tmp);
+      launch_weight_to_f16(c, tmp, Q3TTS_F16, L.out, L.in, true, dst);
+      Q3_CUDA(cudaStreamSynchronize(stream_));
+      cudaFree(tmp);
+    }
+  } else {
+    launch_weight_to_f16(c, L.w, L.sdt, L.out, L.in, interleave_halves, dst);
+  }
+  t.w = dst;
+  return t;
+}
+
+void TalkerEngine::build_tc_weights() {
+  auto ok = [](const Linear& L) { return L.in % 8 == 0 && L.out % 32 == 0; };
+  bool all = ok(w_.fc1) && ok(w_.fc2) && ok(w_.codec_head) && (!w_.has_mtp || ok(w_.small_to_mtp));
+  for (StackWeights* S : {&w_.talker, &w_.cp})
+    for (auto& l : S->layer) all = all && ok(l.qkv) && ok(l.o) && ok(l.gate_up) && ok(l.down) && (l.gate_up.out / 2) % 16 == 0;
+  for (auto& h : w_.lm_head) all = all && ok(h);
+  if (!all) return;  // shapes outside the tcgen05 path: every row count stays on the SIMT kernels
+  for (StackWeights* S : {&w_.talker, &w_.cp}) {
+    S->tc.resize(S->layers);
+    for (int l = 0; l < S->layers; ++l) {
+      S->tc[l].qkv = make_tc(S->layer[l].qkv, false);
+      S->tc[l].o = make_tc(S->layer[l].o, false);
+      S->tc[l].gate_up_il = make_tc(S->layer[l].gate_up, true);
+      S->tc[l].down = make_tc(S->layer[l].down, false);
+    }
+  }
+  w_.fc1_tc = make_tc(w_.fc1, false);
+  w_.fc2_tc = make_tc(w_.fc2, false);
+  w_.codec_head_tc = make_tc(w_.codec_head, false);
+  for (auto& h : w_.lm_head) w_.lm_head_tc.push_back(make_tc(h, false));
+  if (w_.has_mtp) w_.small_to_mtp_tc = make_tc(w_.small_to_mtp, false);
+  Q3_CUDA(cudaStreamSynchronize(stream_));
+  w_.has_tc = true;
+}
+
+void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res,
+                             int act, int swiglu) {
+  TcGemm g;
+  g.a = (const __half*)x16; g.w = (const __half*)L.w; g.Bt = 1; g.T = m; g.cin = L.in; g.N = L.out; g.ntap = 1; g.dil = 1;
+  g.bias = L.bias; g.res = res; g.ld_res = ld32; g.act = act; g.swiglu = swiglu;
+  g.out32 = out32; g.ld32 = ld32; g.out16 = (__half*)out16; g.ld16 = ld16;
+  launch_tc_gemm(ctx(), g);
+}
+
 // Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
 void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
                                  const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
                                  size_t layer_stride, int capacity) {
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
+  if (use_tc(m) && !S.tc.empty()) {
+    // tcgen05 path (rows >= tc_min_rows_): fp16 operands, fp32 accumulate, fp32 residual stream; 8 launches per layer
+    for (int l = 0; l < S.layers; ++l) {
+      const LayerWeights& L = S.layer[l];
+      const LayerTc& Tc = S.tc[l];
+      KVLayout kv;
+      kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
+      launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.in_norm, S.eps, (__half*)d_h16_, S.hidden);
+      linear_tc(Tc.qkv, d_h16_, m, d_qkv_, qkv_ld, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+      launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
+                                 row_pos, kv);
+      launch_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, (__half*)d_attn16_, attn_ld);
+      linear_tc(Tc.o, d_attn16_, m, x, S.hidden, nullptr, 0, x, TC_ACT_NONE, 0);
+      launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.post_norm, S.eps, (__half*)d_h16_, S.hidden);
+      linear_tc(Tc.gate_up_il, d_h16_, m, nullptr, 0, d_act16_, S.inter, nullptr, TC_ACT_NONE, 1);
+      linear_tc(Tc.down, d_act16_, m, x, S.hidden, nullptr, 0, x, TC_ACT_NONE, 0);
+    }
+    return;
+  }
   for (int l = 0; l < S.layers; ++l) {
     const LayerWeights& L = S.layer[l];
     KVLayout kv;
@@ -229,9 +319,15 @@ Admission TalkerEngine::admit(int slot, const q3tts_request& r) {
   Q3_CUDA(cudaMemcpyAsync(d_desc_, desc, sizeof(int) * 3 * P, cudaMemcpyHostToDevice, stream_));
   if (spk_by_vec) Q3_CUDA(cudaMemcpyAsync(d_spk_, r.speaker_embedding, sizeof(float) * H, cudaMemcpyHostToDevice, stream_));
   // text_projection(text_embedding(ids)) (Model/Qwen3Talker.swift:103-106; Qwen3Layers.swift:276-279)
-  launch_gather_rows(c, w_.text_embedding, d_ids_, n_tp, d_tpe_, TH, false);
-  launch_linear(c, w_.fc1, d_tpe_, TH, n_tp, d_tph_, TH, nullptr, 0.f, EPI_SILU);
-  launch_linear(c, w_.fc2, d_tph_, TH, n_tp, d_tp_, H, nullptr, 0.f, EPI_STORE);
+  if (use_tc(n_tp)) {
+    launch_gather_rows_f16(c, w_.text_embedding, d_ids_, n_tp, (__half*)d_tpe16_, TH);
+    linear_tc(w_.fc1_tc, d_tpe16_, n_tp, nullptr, 0, d_tph16_, TH, nullptr, TC_ACT_SILU, 0);
+    linear_tc(w_.fc2_tc, d_tph16_, n_tp, d_tp_, H, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+  } else {
+    launch_gather_rows(c, w_.text_embedding, d_ids_, n_tp, d_tpe_, TH, false);
+    launch_linear(c, w_.fc1, d_tpe_, TH, n_tp, d_tph_, TH, nullptr, 0.f, EPI_SILU);
+    launch_linear(c, w_.fc2, d_tph_, TH, n_tp, d_tp_, H, nullptr, 0.f, EPI_STORE);
+  }
   launch_assemble_rows(c, d_tp_, H, w_.codec_embedding, d_spk_, d_desc_, P, d_x_);
   // trailingTextHidden = textproj(ids[4 ..< len-5]) ++ tts_eos (:426-433)
   float* tr = d_trailing_ + (size_t)slot * opt_.max_trailing * H;
@@ -319,14 +415,25 @@ void TalkerEngine::issue_frame(int n_slots) {
     const int m = g == 0 ? 2 * n_slots : n_slots;
     float* x = d_cpin_;
     if (w_.has_mtp) {  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
-      launch_linear(c, w_.small_to_mtp, d_cpin_, H, m, d_cpx_, Hcp, nullptr, 0.f, EPI_STORE);
+      if (use_tc(m)) {
+        launch_f32_to_f16(c, d_cpin_, (size_t)m * H, (__half*)d_h16_);
+        linear_tc(w_.small_to_mtp_tc, d_h16_, m, d_cpx_, Hcp, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+      } else {
+        launch_linear(c, w_.small_to_mtp, d_cpin_, H, m, d_cpx_, Hcp, nullptr, 0.f, EPI_STORE);
+      }
       x = d_cpx_;
     }
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
                   d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
-    if (g == 0) launch_linear(c, w_.lm_head[0], x + Hcp, 2 * Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
-    else launch_linear(c, w_.lm_head[g], x, Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
+    if (use_tc(n_slots)) {
+      launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, w_.cp.final_norm, w_.cp.eps, (__half*)d_h16_, Hcp);
+      linear_tc(w_.lm_head_tc[g], d_h16_, n_slots, d_cplogits_, Vc, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+    } else if (g == 0) {
+      launch_linear(c, w_.lm_head[0], x + Hcp, 2 * Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
+    } else {
+      launch_linear(c, w_.lm_head[g], x, Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
+    }
     SamplerParams pg = p;
     pg.vocab = Vc; pg.group = g + 1;
     launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, 0);
@@ -337,7 +444,12 @@ void TalkerEngine::issue_frame(int n_slots) {
   forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
                 kv_layer_stride_, opt_.kv_capacity);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
-  launch_linear(c, w_.codec_head, d_hlast_, H, n_slots, d_logits0_, V, nullptr, 0.f, EPI_STORE);
+  if (use_tc(n_slots)) {
+    launch_f32_to_f16(c, d_hlast_, (size_t)n_slots * H, (__half*)d_h16_);
+    linear_tc(w_.codec_head_tc, d_h16_, n_slots, d_logits0_, V, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+  } else {
+    launch_linear(c, w_.codec_head, d_hlast_, H, n_slots, d_logits0_, V, nullptr, 0.f, EPI_STORE);
+  }
   launch_step_advance(c, n_slots, d_state_, 192);  // maxKVCacheWindow (Model/Qwen3Layers.swift:108)
 }
 
@@ -406,16 +518,37 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
   Q3_CUDA(cudaMemsetAsync(d_x_, 0, sizeof(float) * (size_t)m * S.hidden, stream_));
   Q3_CUDA(cudaMemsetAsync(d_attn_, 0, sizeof(float) * (size_t)m * attn_ld, stream_));
+  if (d_h16_) {
+    Q3_CUDA(cudaMemsetAsync(d_h16_, 0, (size_t)m * S.hidden * 2, stream_));
+    Q3_CUDA(cudaMemsetAsync(d_attn16_, 0, (size_t)m * attn_ld * 2, stream_));
+    Q3_CUDA(cudaMemsetAsync(d_act16_, 0, (size_t)m * S.inter * 2, stream_));
+  }
   launches = 0;
   bytes_per_iter = 0;
+  const bool tc = use_tc(m) && !S.tc.empty();
   auto pass = [&](bool count) {
     for (int l = 0; l < S.layers; ++l) {
       const LayerWeights& L = S.layer[l];
+      if (tc) {  // the launches batched decode actually issues (fp16 dense copies through tcgen05)
+        const LayerTc& T = S.tc[l];
+        linear_tc(T.qkv, d_h16_, m, d_qkv_, qkv_ld, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+        linear_tc(T.o, d_attn16_, m, d_x_, S.hidden, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+        linear_tc(T.gate_up_il, d_h16_, m, nullptr, 0, d_act16_, S.inter, nullptr, TC_ACT_NONE, 1);
+        linear_tc(T.down, d_act16_, m, d_x_, S.hidden, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+        if (count) { launches += 4; bytes_per_iter += (int64_t)2 * ((int64_t)T.qkv.out * T.qkv.in + (int64_t)T.o.out * T.o.in + (int64_t)T.gate_up_il.out * T.gate_up_il.in + (int64_t)T.down.out * T.down.in); }
+        continue;
+      }
       launch_linear(c, L.qkv, d_x_, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
       launch_linear(c, L.o, d_attn_, attn_ld, m, d_x_, S.hidden, nullptr, 0.f, EPI_ADD);
       launch_linear(c, L.gate_up, d_x_, S.hidden, m, d_act_, S.inter, L.post_norm, S.eps, EPI_SWIGLU);
       launch_linear(c, L.down, d_act_, S.inter, m, d_x_, S.hidden, nullptr, 0.f, EPI_ADD);
       if (count) { launches += 4; bytes_per_iter += (int64_t)(L.qkv.weight_bytes() + L.o.weight_bytes() + L.gate_up.weight_bytes() + L.down.weight_bytes()); }
+    }
+    if (tc) {
+      const TcLinear& head = which == 0 ? w_.codec_head_tc : w_.lm_head_tc[0];
+      linear_tc(head, d_h16_, m, which == 0 ? d_logits0_ : d_cplogits_, head.out, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+      if (count) { launches += 1; bytes_per_iter += (int64_t)2 * head.out * head.in; }
+      return;
     }
     const Linear& head = which == 0 ? w_.codec_head : w_.lm_head[0];
     launch_linear(c, head, d_x_, S.hidden, m, which == 0 ? d_logits0_ : d_cplogits_, head.out, S.final_norm, S.eps, EPI_STORE);

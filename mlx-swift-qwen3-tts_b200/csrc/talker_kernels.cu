@@ -150,91 +150,111 @@ struct LinearKArgs {
   int out, in, group, sdt, m, ldx, ldy, epi;
 };
 
-// Shared-memory layout per CTA:  xs[MT][in/4] float4 in lane-major order,  xsum[MT][in/VPL] (quantised formats).
+// Shared-memory layout per CTA:  xs[MT][nchunk*KC/4] float4 in lane-major order,  xsum[MT][nchunk*32] (quantised formats).
 // Lane-major: element e of a K-chunk (KC = 32*VPL values) lives at float4 index ((e%VPL)/4)*32 + e/VPL, so the 32
 // lanes of a warp read 32 consecutive float4 — conflict free — while each lane's weights stay one contiguous
 // 16-byte global load.
+//
+// Latency structure (batch-1 decode is latency bound, ~2 MB of weights per launch): the weight / scale loads of the warp's
+// first row do not depend on the activations, so they are issued FIRST and fly while the CTA stages x; staging is a single
+// pass (RMSNorm statistics, per-lane activation sums for the group-bias term and the smem fill together) behind ONE
+// __syncthreads; the RMS scale is applied to the finished dot product (it is a per-row scalar).
 template <int FMT, int MT>
 __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
   constexpr int VPL = FmtTraits<FMT>::VPL;
   constexpr int KC = 32 * VPL;
   constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
+  constexpr int LPG = VPL / 4;  // staging threads (one float4 each) per weight lane
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nchunk = (a.in + KC - 1) / KC;   // the last chunk may be partial (in must be a multiple of VPL)
   const int xstride = nchunk * (KC / 4);     // float4 per activation row in shared memory (chunk-padded)
   float4* xs = reinterpret_cast<float4*>(smem_raw);
   float* xsum = reinterpret_cast<float*>(smem_raw + (size_t)MT * xstride * sizeof(float4));
   __shared__ float red[MT][8];
-  __shared__ float inv_rms[MT];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.y * MT;
   const int in4 = a.in >> 2;
+  const int out_eff = (a.epi == EPI_SWIGLU) ? (a.out >> 1) : a.out;
+  const int nsub = (a.epi == EPI_SWIGLU) ? 2 : 1;
+  const size_t row_bytes = QUANT ? (size_t)a.in * (FMT == W_Q4 ? 4 : 8) / 8 : (size_t)a.in * (FMT == W_F32 ? 4 : 2);
+  const int ngroups = QUANT ? a.in / a.group : 0;
+  const int r_first = blockIdx.x * 8 + warp;
 
-  // ---- stage activations (optionally RMS-normalised) ----
-  if (a.norm_w != nullptr) {
+  // ---- (0) prefetch the first row's first chunk group: independent of x ----
+  uint4 pre_w[2][4];
+  float pre_s[2][4], pre_b[2][4];
+  if (r_first < out_eff) {
 #pragma unroll
-    for (int mi = 0; mi < MT; ++mi) {
-      float ss = 0.f;
-      if (m0 + mi < a.m) {
-        const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(m0 + mi) * a.ldx);
-        for (int f = tid; f < in4; f += 256) {
-          const float4 v = xr[f];
-          ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int s = 0; s < 2; ++s) {
+      if (s < nsub) {
+        const int row = r_first + s * out_eff;
+        const uint4* wr = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.w) + (size_t)row * row_bytes);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (u * KC + lane * VPL < a.in) {
+            pre_w[s][u] = ldg_stream(wr + (size_t)u * 32 + lane);
+            if constexpr (QUANT) {
+              const size_t gi = (size_t)row * ngroups + (u * KC + lane * VPL) / a.group;
+              pre_s[s][u] = load_as_f32(a.scales, gi, a.sdt);
+              pre_b[s][u] = load_as_f32(a.biases, gi, a.sdt);
+            }
+          }
         }
       }
-      ss = warp_sum(ss);
-      if (lane == 0) red[mi][warp] = ss;
     }
-    __syncthreads();
-    if (tid < MT) {
-      float s = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[tid][w];
-      inv_rms[tid] = rsqrtf(s / (float)a.in + a.eps);
-    }
-    __syncthreads();
   }
+
+  // ---- (1) stage activations: one pass, one barrier ----
+  const int iters = (in4 + 255) / 256;
 #pragma unroll
   for (int mi = 0; mi < MT; ++mi) {
     const bool valid = (m0 + mi) < a.m;
     const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(valid ? m0 + mi : 0) * a.ldx);
-    const float sc = a.norm_w ? inv_rms[mi] : 1.0f;
-    for (int f = tid; f < in4; f += 256) {
-      float4 v = valid ? xr[f] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (a.norm_w) {
+    float ss = 0.f;
+    for (int it = 0; it < iters; ++it) {
+      const int f = tid + it * 256;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid && f < in4) v = xr[f];
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      if (a.norm_w != nullptr && f < in4) {
         const float4 nw = reinterpret_cast<const float4*>(a.norm_w)[f];
-        v.x = v.x * sc * nw.x; v.y = v.y * sc * nw.y; v.z = v.z * sc * nw.z; v.w = v.w * sc * nw.w;
+        v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
       }
-      const int e = f << 2;             // element index
+      const int e = f << 2;
       const int ch = e / KC, ec = e - ch * KC;
       const int l = ec / VPL, j = (ec - l * VPL) >> 2;
-      xs[(size_t)mi * xstride + ch * (KC / 4) + j * 32 + l] = v;
+      if (f < in4) xs[(size_t)mi * xstride + ch * (KC / 4) + j * 32 + l] = v;
+      if constexpr (QUANT) {  // sum over the LPG consecutive float4 that belong to one weight lane (all lanes participate)
+        float s4 = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+        for (int o = 1; o < LPG; o <<= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        if ((tid & (LPG - 1)) == 0 && f < in4) xsum[mi * (nchunk * 32) + ch * 32 + l] = s4;
+      }
+    }
+    if (a.norm_w != nullptr) {
+      ss = warp_sum(ss);
+      if (lane == 0) red[mi][warp] = ss;
     }
   }
   __syncthreads();
-  if constexpr (QUANT) {  // per-lane activation sums (for the group bias term): xsum[mi][chunk][lane]
-    const int nl = nchunk * 32;
-    for (int i = tid; i < MT * nl; i += 256) {
-      const int mi = i / nl, r = i - mi * nl, ch = r >> 5, l = r & 31;
-      float s = 0.f;
-      if (ch * KC + l * VPL < a.in) {
-        const float4* p = xs + (size_t)mi * xstride + ch * (KC / 4) + l;
+  float inv_rms[MT];
 #pragma unroll
-        for (int j = 0; j < VPL / 4; ++j) { const float4 v = p[j * 32]; s += (v.x + v.y) + (v.z + v.w); }
-      }
-      xsum[i] = s;
+  for (int mi = 0; mi < MT; ++mi) {
+    inv_rms[mi] = 1.0f;
+    if (a.norm_w != nullptr) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[mi][w];
+      inv_rms[mi] = rsqrtf(s / (float)a.in + a.eps);
     }
-    __syncthreads();
   }
 
-  // ---- stream weight rows: one warp per output row (pair of rows for SwiGLU) ----
-  const int out_eff = (a.epi == EPI_SWIGLU) ? (a.out >> 1) : a.out;
-  const int nsub = (a.epi == EPI_SWIGLU) ? 2 : 1;
-  const size_t row_bytes = QUANT ? (size_t)a.in * (FMT == W_Q4 ? 4 : 8) / 8
-                                 : (size_t)a.in * (FMT == W_F32 ? 4 : 2);
-  const int ngroups = QUANT ? a.in / a.group : 0;
-  for (int r = blockIdx.x * 8 + warp; r < out_eff; r += gridDim.x * 8) {
+  // ---- (2) stream weight rows: one warp per output row (pair of rows for SwiGLU) ----
+  for (int r = r_first; r < out_eff; r += gridDim.x * 8) {
+    float yold[MT];
+#pragma unroll
+    for (int mi = 0; mi < MT; ++mi) yold[mi] = (a.epi == EPI_ADD && lane == 0 && m0 + mi < a.m) ? a.y[(size_t)(m0 + mi) * a.ldy + r] : 0.f;
     float res[2][MT];
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
@@ -251,30 +271,39 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
       for (int mi = 0; mi < MT; ++mi) acc[mi] = 0.f;
       for (int c0 = 0; c0 < nchunk; c0 += 4) {
         uint4 wv[4];
+        float scv[4], biv[4];
+        const bool use_pre = (r == r_first) && (c0 == 0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if ((c0 + u) * KC + lane * VPL < a.in) wv[u] = ldg_stream(wr + (size_t)(c0 + u) * 32 + lane);
+        for (int u = 0; u < 4; ++u) {
+          if ((c0 + u) * KC + lane * VPL < a.in) {
+            if (use_pre) {
+              wv[u] = pre_w[s][u];
+              if constexpr (QUANT) { scv[u] = pre_s[s][u]; biv[u] = pre_b[s][u]; }
+            } else {
+              wv[u] = ldg_stream(wr + (size_t)(c0 + u) * 32 + lane);
+              if constexpr (QUANT) {
+                const size_t gi = (size_t)row * ngroups + ((c0 + u) * KC + lane * VPL) / a.group;
+                scv[u] = load_as_f32(a.scales, gi, a.sdt);
+                biv[u] = load_as_f32(a.biases, gi, a.sdt);
+              }
+            }
+          }
+        }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if ((c0 + u) * KC + lane * VPL < a.in) {
             const int ch = c0 + u;
-            float sc = 1.f, bi = 0.f;
-            if constexpr (QUANT) {
-              const size_t gi = (size_t)row * ngroups + (ch * KC + lane * VPL) / a.group;
-              sc = load_as_f32(a.scales, gi, a.sdt);
-              bi = load_as_f32(a.biases, gi, a.sdt);
-            }
 #pragma unroll
             for (int mi = 0; mi < MT; ++mi) {
               const float d = lane_dot<FMT>(wv[u], xs + (size_t)mi * xstride + ch * (KC / 4) + lane);
-              if constexpr (QUANT) acc[mi] += sc * d + bi * xsum[mi * (nchunk * 32) + ch * 32 + lane];
+              if constexpr (QUANT) acc[mi] += scv[u] * d + biv[u] * xsum[mi * (nchunk * 32) + ch * 32 + lane];
               else acc[mi] += d;
             }
           }
         }
       }
 #pragma unroll
-      for (int mi = 0; mi < MT; ++mi) res[s][mi] = warp_sum(acc[mi]);
+      for (int mi = 0; mi < MT; ++mi) res[s][mi] = warp_sum(acc[mi]) * inv_rms[mi];
     }
     if (lane == 0) {
 #pragma unroll
@@ -289,7 +318,7 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
         } else {
           if (a.bias) v += a.bias[r];
           if (a.epi == EPI_SILU) v = silu_f(v);
-          if (a.epi == EPI_ADD) v += *yp;
+          if (a.epi == EPI_ADD) v += yold[mi];
           *yp = v;
         }
       }

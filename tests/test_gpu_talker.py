@@ -246,3 +246,72 @@ def test_sampled_generation_is_reproducible_and_valid(tiny8, engines):
     assert a == b and a != c
     assert all(f[0] < 2048 or f[0] in (2148, 2150) for f in a)
     assert all(0 <= v < 2048 for f in a for v in f[1:])
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 linears
+def _tc_engine(d, monkeypatch, **kw):
+    """An engine whose every linear (any row count) runs the tcgen05 path: fp16 operands, fp32 accumulate."""
+    import qwen3tts_b200 as q
+
+    monkeypatch.setenv("Q3TTS_TC_MIN_ROWS", "1")
+    kw.setdefault("max_frames", 256)
+    return q.Engine(d, **kw)
+
+
+@pytest.mark.parametrize("ck", ["tiny8", "tiny4", "tiny_bf16"])
+def test_teacher_forced_logits_tensor_core_path(ck, request, oracles, monkeypatch):
+    """Same 1e-2 logit bar for the tensor-core linears (the path batched decode and prefill take)."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    d = request.getfixturevalue(ck)
+    F = 20
+    forced = np.random.default_rng(5).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    rec = {}
+    oracles(d).generate_codes(_oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec, filter_invalid=False)
+    eng = _tc_engine(d, monkeypatch, load_codec=False)
+    frames, lg = eng.generate_codes(q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced,
+                                                 keep_invalid_frames=True, want_logits=F))
+    eng.close()
+    e0 = np.abs(lg["code0_logits"] - rec["code0_logits"]).max()
+    ec = np.abs(lg["cp_logits"] - rec["cp_logits"]).max()
+    print(f"[{ck}] tensor-core path teacher-forced max-abs logit error: code0 {e0:.3e}, code predictor {ec:.3e} (logit rms {rec['code0_logits'].std():.2f})")
+    assert e0 <= LOGIT_TOL and ec <= LOGIT_TOL
+
+
+def test_batched_tensor_core_decode_equals_singles(tiny8, monkeypatch):
+    """Rows of a GEMM are independent: a 24-slot batch must reproduce the single-utterance results bit for bit."""
+    import qwen3tts_b200 as q
+
+    e1 = _tc_engine(tiny8, monkeypatch, load_codec=False)
+    eb = _tc_engine(tiny8, monkeypatch, load_codec=False, max_batch=24)
+    reqs = [q.GenRequest(text_ids=[11, 21, 22] + list(range(60 + i, 60 + i + 8 + (i % 5))), speaker_id=[2861, 3066, -1, 2873][i % 4],
+                         temperature=0.0 if i % 2 else 0.8, top_k=0 if i % 3 else 40, seed=i, max_tokens=8 + (i % 7), keep_invalid_frames=True)
+            for i in range(40)]
+    singles = [e1.generate_codes(r).tolist() for r in reqs]
+    batch = [b.tolist() for b in eb.generate_codes_batch(reqs)]
+    e1.close()
+    eb.close()
+    assert batch == singles
+
+
+def test_default_batch_engine_uses_tensor_cores_and_stays_in_tolerance(tiny8, engines, oracles):
+    """max_batch = 32 (default threshold: >= 16 rows -> tcgen05): frames agree with the oracle wherever its margin allows."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    eng = engines(tiny8, max_batch=32, load_codec=False)
+    reqs = [q.GenRequest(text_ids=TEXT_IDS[:3] + [40 + i] + TEXT_IDS[4:], speaker_id=2861, temperature=0.0, max_tokens=10, keep_invalid_frames=True) for i in range(32)]
+    outs = eng.generate_codes_batch(reqs)
+    bad = 0
+    for i, o in enumerate(outs):
+        rec = {}
+        want = oracles(tiny8).generate_codes(_oreq(otalker, text_ids=reqs[i].text_ids, speaker_id=2861, temperature=0.0, max_tokens=10), record=rec, filter_invalid=False)
+        got = o.tolist()
+        for f in range(min(len(got), len(want))):
+            if got[f] != want[f]:
+                g = next(k for k in range(16) if got[f][k] != want[f][k])
+                assert rec["margins"][f][g] < MARGIN_TOL, f"utterance {i} frame {f} group {g}: divergence at margin {rec['margins'][f][g]:.4f}"
+                bad += 1
+                break
+    print(f"{bad}/32 utterances diverged at a near-tie (margin < {MARGIN_TOL})")
