@@ -156,14 +156,30 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
   int next = 0, active = 0;
   std::vector<SlotState> st;
   while (next < n || active > 0) {
+    // admit as many pending utterances as there are free slots, in ONE concatenated prefill pass
+    std::vector<TalkerEngine::AdmitItem> items;
+    std::vector<int> item_req;
+    int rows = 0;
     for (int s = 0; s < B && next < n; ++s) {
       if (slot_req[s] >= 0) continue;
       while (next < n) {
-        Q3_CHECK(!(reqs[next].code0_logits_out || reqs[next].cp_logits_out), Q3TTS_ERR_INVALID_ARG, "logit dumps are only available through q3tts_generate_codes");
-        Admission a = t.admit(s, reqs[next]);
-        if (!a.too_short) { slot_req[s] = next++; ++active; break; }
-        ++next;  // too short: zero frames, like the reference's [] (Model/Qwen3Talker.swift:348-352)
+        const q3tts_request& rq = reqs[next];
+        Q3_CHECK(!(rq.code0_logits_out || rq.cp_logits_out), Q3TTS_ERR_INVALID_ARG, "logit dumps are only available through q3tts_generate_codes");
+        if (rq.n_text_ids < 9) { ++next; continue; }  // too short: zero frames, like the reference's [] (Model/Qwen3Talker.swift:348-352)
+        const int est = rq.n_instruct_ids + rq.n_ref_text_ids + std::max(rq.ref_frames, 0) + 10;
+        if (!items.empty() && rows + est > t.max_prefill_rows()) break;
+        rows += est;
+        items.push_back({s, &rq});
+        item_req.push_back(next);
+        slot_req[s] = next++;
+        ++active;
+        break;
       }
+      if (!items.empty() && rows >= t.max_prefill_rows()) break;
+    }
+    if (!items.empty()) {
+      std::vector<Admission> adm;
+      t.admit_batch(items, adm);
     }
     if (active == 0) break;
     int hi = 0;

@@ -34,6 +34,10 @@ class TalkerEngine {
 
   // Prompt assembly + prefill of `req` into `slot` (Model/Qwen3Talker.swift:344-462).
   Admission admit(int slot, const q3tts_request& req);
+  struct AdmitItem { int slot; const q3tts_request* req; };
+  // Several utterances at once: one concatenated prefill pass (rows carry their own slot / position).
+  void admit_batch(const std::vector<AdmitItem>& items, std::vector<Admission>& out);
+  int max_prefill_rows() const { return max_rows_; }
   // Run `n` frame steps for slots [0, n_slots) — CUDA-graph replay when enabled.
   void run_frames(int n_slots, int n);
   // Read back slot states (synchronises the stream).

@@ -55,7 +55,7 @@ void launch_gather_rows_f16(const LaunchCtx& c, const Embedding& e, const int* i
 void launch_gather_rows(const LaunchCtx& c, const Embedding& e, const int* ids, int n, float* y, int ldy, bool accumulate);
 
 // prompt assembly (Model/Qwen3Talker.swift:354-433): row r = (tp >= 0 ? tp_rows[tp] : 0) + (codec >= 0 ?
-// codec_embedding[codec] : 0) + (spk ? speaker_embedding : 0)
+// codec_embedding[codec] : 0) + (spk > 0 ? speaker_embedding[spk - 1] : 0)
 void launch_assemble_rows(const LaunchCtx& c, const float* tp_rows, int H, const Embedding& codec, const float* spk,
                           const int* desc /*[n][3] = tp, codec, spk*/, int n, float* y);
 

@@ -20,8 +20,9 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size;
   Q3_CHECK(B >= 1 && C >= 208 && F >= 1, Q3TTS_ERR_INVALID_ARG, "bad options: max_batch %d kv_capacity %d max_frames %d", B, C, F);
   const StackWeights &T = w_.talker, &P = w_.cp;
-  max_rows_ = std::max(2 * B, C);
-  max_tp_rows_ = C + opt_.max_trailing + 8;
+  // rows of one batched pass: a decode step (<= 2B), one prompt (<= C), or the prefill of a whole admission batch
+  max_rows_ = std::max(std::max(2 * B, C), std::min(B * 96, 8192));
+  max_tp_rows_ = std::max(C + opt_.max_trailing + 8, std::min(B * 128, 16384));
   set_words_ = (std::max(cfg_.vocab_size, cfg_.cp.vocab_size) + 31) / 32;
 
   kv_layer_stride_ = (size_t)T.kv_heads * C * 128;
@@ -38,7 +39,7 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   d_step_slot_ = arena_.alloc_n<int>(B); d_step_pos_ = arena_.alloc_n<int>(B); d_win_ = arena_.alloc_n<int>(B);
   d_cp_slot2_ = arena_.alloc_n<int>(2 * B); d_cp_pos2_ = arena_.alloc_n<int>(2 * B);
   d_iota_ = arena_.alloc_n<int>(B); d_cp_pos_ = arena_.alloc_n<int>(16 * B);
-  d_pf_slot_ = arena_.alloc_n<int>(C); d_pf_pos_ = arena_.alloc_n<int>(C); d_pf_win_ = arena_.alloc_n<int>(B);
+  d_pf_slot_ = arena_.alloc_n<int>(max_rows_); d_pf_pos_ = arena_.alloc_n<int>(max_rows_); d_pf_win_ = arena_.alloc_n<int>(B);
   Q3_CUDA(cudaMemsetAsync(d_pf_win_, 0, sizeof(int) * B, stream_));
   Q3_CUDA(cudaMemsetAsync(d_win_, 0, sizeof(int) * B, stream_));
 
@@ -66,9 +67,9 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   d_tpe_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * cfg_.text_hidden_size);
   d_tph_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * cfg_.text_hidden_size);
   d_tp_ = arena_.alloc_n<float>((size_t)max_tp_rows_ * H);
-  d_spk_ = arena_.alloc_n<float>(H);
+  d_spk_ = arena_.alloc_n<float>((size_t)B * H);
   d_ids_ = arena_.alloc_n<int>(max_tp_rows_);
-  d_desc_ = arena_.alloc_n<int>((size_t)3 * C);
+  d_desc_ = arena_.alloc_n<int>((size_t)3 * max_rows_);
   // tensor-core copies: built when the handle can see >= tc_min_rows_ rows at once (batched decode, or any prefill)
   if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) tc_min_rows_ = atoi(e);
   if (tc_min_rows_ > 0) {
@@ -243,81 +244,107 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
 }
 
 Admission TalkerEngine::admit(int slot, const q3tts_request& r) {
-  Admission adm;
+  std::vector<AdmitItem> items{{slot, &r}};
+  std::vector<Admission> out;
+  admit_batch(items, out);
+  return out[0];
+}
+
+// Prompt assembly + prefill of several utterances at once (Model/Qwen3Talker.swift:344-462 for each): their prefill rows
+// are concatenated into one [R, H] activation matrix so the 28-layer prefill is ONE pass of (tensor-core) GEMMs; rows carry
+// (slot, position) so RoPE / KV append / causal attention stay per utterance.
+void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<Admission>& out) {
   const int H = cfg_.hidden_size, C = opt_.kv_capacity, F = opt_.max_frames, TH = cfg_.text_hidden_size;
-  Q3_CHECK(slot >= 0 && slot < opt_.max_batch, Q3TTS_ERR_INVALID_ARG, "slot %d out of range", slot);
-  Q3_CHECK(r.text_ids != nullptr || r.n_text_ids == 0, Q3TTS_ERR_INVALID_ARG, "text_ids is NULL");
-  if (r.n_text_ids < 9) {  // minTokens (Model/Qwen3Talker.swift:348-352)
-    adm.too_short = true;
-    return adm;
-  }
-  auto check_text = [&](const int32_t* ids, int n, const char* what) {
-    for (int i = 0; i < n; ++i)
-      Q3_CHECK(ids[i] >= 0 && ids[i] < cfg_.text_vocab_size, Q3TTS_ERR_INVALID_ARG, "%s id %d outside the text vocabulary", what, ids[i]);
-  };
-  check_text(r.text_ids, r.n_text_ids, "text");
-  const bool has_instruct = r.instruct_ids != nullptr && r.n_instruct_ids > 0;
-  const bool use_icl = !has_instruct && r.ref_codes != nullptr && r.ref_text_ids != nullptr && r.n_ref_text_ids > 0;  // :338, 395
-  if (has_instruct) check_text(r.instruct_ids, r.n_instruct_ids, "instruct");
-  if (use_icl) check_text(r.ref_text_ids, r.n_ref_text_ids, "reference transcript");
-  const bool spk_by_id = r.speaker_id >= 0;
-  const bool spk_by_vec = !spk_by_id && r.speaker_embedding != nullptr;
-  if (spk_by_id) Q3_CHECK(r.speaker_id < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "speaker_id %d outside codec vocabulary", r.speaker_id);
-  if (spk_by_vec) Q3_CHECK(r.speaker_embedding_dim == H, Q3TTS_ERR_INVALID_ARG, "speaker embedding has %d dims, model hidden size is %d", r.speaker_embedding_dim, H);
-
-  // --- text rows to project: [tts_bos, tts_eos, tts_pad, instruct|ref-text..., role(3), first text, trailing...]
-  int* ids = h_stage_;
-  int n_tp = 0;
-  ids[n_tp++] = cfg_.tts_bos_token_id; ids[n_tp++] = cfg_.tts_eos_token_id; ids[n_tp++] = cfg_.tts_pad_token_id;
+  out.assign(items.size(), Admission{});
+  std::vector<int> ids{cfg_.tts_bos_token_id, cfg_.tts_eos_token_id, cfg_.tts_pad_token_id};
   const int TP_BOS = 0, TP_EOS = 1, TP_PAD = 2;
-  const int n_front_text = has_instruct ? r.n_instruct_ids : (use_icl ? r.n_ref_text_ids : 0);
-  const int n_ref_audio = (use_icl && r.ref_frames > 0) ? r.ref_frames : 0;
-  const int trailing_len = r.n_text_ids - 4 - 5;  // :426
-  const int n_trailing = trailing_len > 0 ? trailing_len : 0;
-  Q3_CHECK(3 + n_front_text + 4 + n_trailing <= max_tp_rows_, Q3TTS_ERR_CAPACITY, "prompt too long for this handle (text rows %d > %d)",
-           3 + n_front_text + 4 + n_trailing, max_tp_rows_);
-  Q3_CHECK(n_trailing + 1 <= opt_.max_trailing, Q3TTS_ERR_CAPACITY, "text too long: %d trailing tokens > %d", n_trailing + 1, opt_.max_trailing);
-  const int tp_front = n_tp;
-  for (int i = 0; i < n_front_text; ++i) ids[n_tp++] = has_instruct ? r.instruct_ids[i] : r.ref_text_ids[i];
-  const int tp_role = n_tp;
-  for (int i = 0; i < 3; ++i) ids[n_tp++] = r.text_ids[i];
-  const int tp_first = n_tp;
-  ids[n_tp++] = r.text_ids[3];
-  const int tp_trailing = n_tp;
-  for (int i = 0; i < n_trailing; ++i) ids[n_tp++] = r.text_ids[4 + i];
-
-  // --- prefill row descriptors (tp index, codec row, speaker flag)
-  int* desc = h_stage_ + max_tp_rows_;
-  int P = 0;
-  auto row = [&](int tp, int codec, int spk) { desc[3 * P] = tp; desc[3 * P + 1] = codec; desc[3 * P + 2] = spk; ++P; };
-  const int n_codec = 5 + ((spk_by_id || spk_by_vec) ? 1 : 0);
-  const int P_total = n_front_text + n_ref_audio + 3 + (n_codec - 1) + 1;
-  Q3_CHECK(P_total <= C - 16, Q3TTS_ERR_CAPACITY, "prefill of %d positions exceeds kv_capacity %d - 16; raise q3tts_options.kv_capacity", P_total, C);
-  for (int i = 0; i < n_front_text; ++i) row(tp_front + i, -1, 0);
-  for (int i = 0; i < n_ref_audio; ++i) {  // codec_embedding(refCodes[0]) — first codebook only (:402-403)
-    const int code = r.ref_codes[i];
-    Q3_CHECK(code >= 0 && code < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "reference code %d outside codec vocabulary", code);
-    row(-1, code, 0);
+  std::vector<int> desc, meta_slot, meta_pos;
+  std::vector<float> spk_host;
+  struct Plan { int slot, row0, P, tp_trailing, n_trailing; const q3tts_request* r; };
+  std::vector<Plan> plans;
+  auto check_text = [&](const int32_t* p, int n, const char* what) {
+    for (int i = 0; i < n; ++i)
+      Q3_CHECK(p[i] >= 0 && p[i] < cfg_.text_vocab_size, Q3TTS_ERR_INVALID_ARG, "%s id %d outside the text vocabulary", what, p[i]);
+  };
+  for (size_t it = 0; it < items.size(); ++it) {
+    const int slot = items[it].slot;
+    const q3tts_request& r = *items[it].req;
+    Q3_CHECK(slot >= 0 && slot < opt_.max_batch, Q3TTS_ERR_INVALID_ARG, "slot %d out of range", slot);
+    Q3_CHECK(r.text_ids != nullptr || r.n_text_ids == 0, Q3TTS_ERR_INVALID_ARG, "text_ids is NULL");
+    if (r.n_text_ids < 9) {  // minTokens (Model/Qwen3Talker.swift:348-352)
+      out[it].too_short = true;
+      continue;
+    }
+    check_text(r.text_ids, r.n_text_ids, "text");
+    const bool has_instruct = r.instruct_ids != nullptr && r.n_instruct_ids > 0;
+    const bool use_icl = !has_instruct && r.ref_codes != nullptr && r.ref_text_ids != nullptr && r.n_ref_text_ids > 0;  // :338, 395
+    if (has_instruct) check_text(r.instruct_ids, r.n_instruct_ids, "instruct");
+    if (use_icl) check_text(r.ref_text_ids, r.n_ref_text_ids, "reference transcript");
+    const bool spk_by_id = r.speaker_id >= 0;
+    const bool spk_by_vec = !spk_by_id && r.speaker_embedding != nullptr;
+    if (spk_by_id) Q3_CHECK(r.speaker_id < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "speaker_id %d outside codec vocabulary", r.speaker_id);
+    if (spk_by_vec) Q3_CHECK(r.speaker_embedding_dim == H, Q3TTS_ERR_INVALID_ARG, "speaker embedding has %d dims, model hidden size is %d", r.speaker_embedding_dim, H);
+    const int n_front_text = has_instruct ? r.n_instruct_ids : (use_icl ? r.n_ref_text_ids : 0);
+    const int n_ref_audio = (use_icl && r.ref_frames > 0) ? r.ref_frames : 0;
+    const int trailing_len = r.n_text_ids - 4 - 5;  // :426
+    const int n_trailing = trailing_len > 0 ? trailing_len : 0;
+    Q3_CHECK(n_trailing + 1 <= opt_.max_trailing, Q3TTS_ERR_CAPACITY, "text too long: %d trailing tokens > %d", n_trailing + 1, opt_.max_trailing);
+    const int n_codec = 5 + ((spk_by_id || spk_by_vec) ? 1 : 0);
+    const int P = n_front_text + n_ref_audio + 3 + (n_codec - 1) + 1;
+    Q3_CHECK(P <= C - 16, Q3TTS_ERR_CAPACITY, "prefill of %d positions exceeds kv_capacity %d - 16; raise q3tts_options.kv_capacity", P, C);
+    Q3_CHECK((int)ids.size() + n_front_text + 4 + n_trailing <= max_tp_rows_ && (int)meta_slot.size() + P <= max_rows_, Q3TTS_ERR_CAPACITY,
+             "prompt batch too large for this handle");
+    // text rows to project: [instruct | ref-text ..., role(3), first text, trailing ...]
+    const int tp_front = (int)ids.size();
+    for (int i = 0; i < n_front_text; ++i) ids.push_back(has_instruct ? r.instruct_ids[i] : r.ref_text_ids[i]);
+    const int tp_role = (int)ids.size();
+    for (int i = 0; i < 3; ++i) ids.push_back(r.text_ids[i]);
+    const int tp_first = (int)ids.size();
+    ids.push_back(r.text_ids[3]);
+    const int tp_trailing = (int)ids.size();
+    for (int i = 0; i < n_trailing; ++i) ids.push_back(r.text_ids[4 + i]);
+    // prefill row descriptors (tp index, codec row, speaker-vector index + 1)
+    int spk_ref = 0;
+    if (spk_by_vec) {
+      spk_host.insert(spk_host.end(), r.speaker_embedding, r.speaker_embedding + H);
+      spk_ref = (int)(spk_host.size() / H);
+    }
+    const int row0 = (int)meta_slot.size();
+    auto row = [&](int tp, int codec, int spk) {
+      desc.push_back(tp); desc.push_back(codec); desc.push_back(spk);
+      meta_slot.push_back(slot); meta_pos.push_back((int)meta_slot.size() - 1 - row0);
+    };
+    for (int i = 0; i < n_front_text; ++i) row(tp_front + i, -1, 0);
+    for (int i = 0; i < n_ref_audio; ++i) {  // codec_embedding(refCodes[0]) — first codebook only (:402-403)
+      const int code = r.ref_codes[i];
+      Q3_CHECK(code >= 0 && code < cfg_.vocab_size, Q3TTS_ERR_INVALID_ARG, "reference code %d outside codec vocabulary", code);
+      row(-1, code, 0);
+    }
+    for (int i = 0; i < 3; ++i) row(tp_role + i, -1, 0);
+    // codecEmbed = [nothink, think_bos, think_eos, (speaker), pad, bos] (:360-379);
+    // combined = [tts_pad x (n-2), tts_bos] + codecEmbed[0 ..< n-1] (:383-386)
+    int codec_ids[6], codec_spk[6] = {0, 0, 0, 0, 0, 0};
+    int k = 0;
+    codec_ids[k++] = cfg_.codec_nothink_id; codec_ids[k++] = cfg_.codec_think_bos_id; codec_ids[k++] = cfg_.codec_think_eos_id;
+    if (spk_by_id) codec_ids[k++] = r.speaker_id;
+    else if (spk_by_vec) { codec_ids[k] = -1; codec_spk[k] = spk_ref; ++k; }
+    codec_ids[k++] = cfg_.codec_pad_id; codec_ids[k++] = cfg_.codec_bos_id;
+    for (int i = 0; i < n_codec - 1; ++i) row(i < n_codec - 2 ? TP_PAD : TP_BOS, codec_ids[i], codec_spk[i]);
+    row(tp_first, codec_ids[n_codec - 1], 0);  // firstTextEmbed (:423)
+    out[it].prefill_len = P;
+    plans.push_back({slot, row0, P, tp_trailing, n_trailing, &r});
   }
-  for (int i = 0; i < 3; ++i) row(tp_role + i, -1, 0);
-  // codecEmbed = [nothink, think_bos, think_eos, (speaker), pad, bos] (:360-379);
-  // combined = [tts_pad x (n-2), tts_bos] + codecEmbed[0 ..< n-1] (:383-386)
-  int codec_ids[6];
-  int codec_spk[6] = {0, 0, 0, 0, 0, 0};
-  int k = 0;
-  codec_ids[k++] = cfg_.codec_nothink_id; codec_ids[k++] = cfg_.codec_think_bos_id; codec_ids[k++] = cfg_.codec_think_eos_id;
-  if (spk_by_id) codec_ids[k++] = r.speaker_id;
-  else if (spk_by_vec) { codec_ids[k] = -1; codec_spk[k] = 1; ++k; }
-  codec_ids[k++] = cfg_.codec_pad_id; codec_ids[k++] = cfg_.codec_bos_id;
-  for (int i = 0; i < n_codec - 1; ++i) row(i < n_codec - 2 ? TP_PAD : TP_BOS, codec_ids[i], codec_spk[i]);
-  row(tp_first, codec_ids[n_codec - 1], 0);  // firstTextEmbed (:423)
-  adm.prefill_len = P;
+  if (plans.empty()) return;
+  const int n_tp = (int)ids.size(), R = (int)meta_slot.size();
+  Q3_CHECK((int)(spk_host.size() / H) <= opt_.max_batch, Q3TTS_ERR_CAPACITY, "too many speaker embeddings in one admission batch");
 
   const LaunchCtx c = ctx();
   Q3_CUDA(cudaEventRecord(ev_a_, stream_));
-  Q3_CUDA(cudaMemcpyAsync(d_ids_, ids, sizeof(int) * n_tp, cudaMemcpyHostToDevice, stream_));
-  Q3_CUDA(cudaMemcpyAsync(d_desc_, desc, sizeof(int) * 3 * P, cudaMemcpyHostToDevice, stream_));
-  if (spk_by_vec) Q3_CUDA(cudaMemcpyAsync(d_spk_, r.speaker_embedding, sizeof(float) * H, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_ids_, ids.data(), sizeof(int) * n_tp, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_desc_, desc.data(), sizeof(int) * 3 * R, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_pf_slot_, meta_slot.data(), sizeof(int) * R, cudaMemcpyHostToDevice, stream_));
+  Q3_CUDA(cudaMemcpyAsync(d_pf_pos_, meta_pos.data(), sizeof(int) * R, cudaMemcpyHostToDevice, stream_));
+  if (!spk_host.empty()) Q3_CUDA(cudaMemcpyAsync(d_spk_, spk_host.data(), sizeof(float) * spk_host.size(), cudaMemcpyHostToDevice, stream_));
   // text_projection(text_embedding(ids)) (Model/Qwen3Talker.swift:103-106; Qwen3Layers.swift:276-279)
   if (use_tc(n_tp)) {
     launch_gather_rows_f16(c, w_.text_embedding, d_ids_, n_tp, (__half*)d_tpe16_, TH);
@@ -328,71 +355,69 @@ Admission TalkerEngine::admit(int slot, const q3tts_request& r) {
     launch_linear(c, w_.fc1, d_tpe_, TH, n_tp, d_tph_, TH, nullptr, 0.f, EPI_SILU);
     launch_linear(c, w_.fc2, d_tph_, TH, n_tp, d_tp_, H, nullptr, 0.f, EPI_STORE);
   }
-  launch_assemble_rows(c, d_tp_, H, w_.codec_embedding, d_spk_, d_desc_, P, d_x_);
-  // trailingTextHidden = textproj(ids[4 ..< len-5]) ++ tts_eos (:426-433)
-  float* tr = d_trailing_ + (size_t)slot * opt_.max_trailing * H;
-  if (n_trailing > 0)
-    Q3_CUDA(cudaMemcpyAsync(tr, d_tp_ + (size_t)tp_trailing * H, sizeof(float) * n_trailing * H, cudaMemcpyDeviceToDevice, stream_));
-  Q3_CUDA(cudaMemcpyAsync(tr + (size_t)n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
-
-  // prefill: rows 0..P-1 of this slot at positions 0..P-1 (Model/Qwen3Talker.swift:437)
-  std::vector<int> meta(2 * P);
-  for (int i = 0; i < P; ++i) { meta[i] = slot; meta[P + i] = i; }
-  // the pinned stage is still being read by the async copies above: use a synchronous pageable copy for the metadata
-  Q3_CUDA(cudaMemcpyAsync(d_pf_slot_, meta.data(), sizeof(int) * P, cudaMemcpyHostToDevice, stream_));
-  Q3_CUDA(cudaMemcpyAsync(d_pf_pos_, meta.data() + P, sizeof(int) * P, cudaMemcpyHostToDevice, stream_));
-  forward_stack(w_.talker, d_x_, P, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C);
+  launch_assemble_rows(c, d_tp_, H, w_.codec_embedding, d_spk_, d_desc_, R, d_x_);
+  for (const Plan& p : plans) {  // trailingTextHidden = textproj(ids[4 ..< len-5]) ++ tts_eos (:426-433)
+    float* tr = d_trailing_ + (size_t)p.slot * opt_.max_trailing * H;
+    if (p.n_trailing > 0)
+      Q3_CUDA(cudaMemcpyAsync(tr, d_tp_ + (size_t)p.tp_trailing * H, sizeof(float) * p.n_trailing * H, cudaMemcpyDeviceToDevice, stream_));
+    Q3_CUDA(cudaMemcpyAsync(tr + (size_t)p.n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
+  }
+  // prefill: every row at its own (slot, position) (Model/Qwen3Talker.swift:437)
+  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C);
   // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
-  launch_rmsnorm(c, d_x_ + (size_t)(P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)slot * H, H);
-  launch_linear(c, w_.codec_head, d_hlast_ + (size_t)slot * H, H, 1, d_logits0_ + (size_t)slot * cfg_.vocab_size, cfg_.vocab_size, nullptr, 0.f, EPI_STORE);
-
-  // teacher forcing / dumps
-  const bool forced = r.forced_codes != nullptr && r.n_forced_frames > 0;
-  if (forced) {
-    Q3_CHECK(r.n_forced_frames <= F, Q3TTS_ERR_CAPACITY, "n_forced_frames %d > max_frames %d", r.n_forced_frames, F);
-    Q3_CUDA(cudaMemcpyAsync(d_forced_ + (size_t)slot * F * 16, r.forced_codes, sizeof(int) * 16 * r.n_forced_frames, cudaMemcpyHostToDevice, stream_));
+  for (const Plan& p : plans) {
+    launch_rmsnorm(c, d_x_ + (size_t)(p.row0 + p.P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)p.slot * H, H);
+    launch_linear(c, w_.codec_head, d_hlast_ + (size_t)p.slot * H, H, 1, d_logits0_ + (size_t)p.slot * cfg_.vocab_size, cfg_.vocab_size, nullptr, 0.f, EPI_STORE);
   }
-  int logits_cap = 0;
-  if (slot == 0 && (r.code0_logits_out != nullptr || r.cp_logits_out != nullptr) && r.logits_capacity_frames > 0) {
-    logits_cap = std::min(r.logits_capacity_frames, F);
-    if (logits_cap > dump_cap_) {
-      Q3_CUDA(cudaStreamSynchronize(stream_));
-      if (d_dump0_) cudaFree(d_dump0_);
-      if (d_dumpcp_) cudaFree(d_dumpcp_);
-      Q3_CUDA(cudaMalloc(&d_dump0_, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size));
-      Q3_CUDA(cudaMalloc(&d_dumpcp_, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size));
-      dump_cap_ = logits_cap;
-      drop_graphs();  // dump pointers are baked into captured graphs
+  for (const Plan& p : plans) {
+    const q3tts_request& r = *p.r;
+    const int slot = p.slot;
+    const bool forced = r.forced_codes != nullptr && r.n_forced_frames > 0;
+    if (forced) {
+      Q3_CHECK(r.n_forced_frames <= F, Q3TTS_ERR_CAPACITY, "n_forced_frames %d > max_frames %d", r.n_forced_frames, F);
+      Q3_CUDA(cudaMemcpyAsync(d_forced_ + (size_t)slot * F * 16, r.forced_codes, sizeof(int) * 16 * r.n_forced_frames, cudaMemcpyHostToDevice, stream_));
     }
-    Q3_CUDA(cudaMemsetAsync(d_dump0_, 0, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size, stream_));
-    Q3_CUDA(cudaMemsetAsync(d_dumpcp_, 0, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size, stream_));
+    int logits_cap = 0;
+    if (slot == 0 && (r.code0_logits_out != nullptr || r.cp_logits_out != nullptr) && r.logits_capacity_frames > 0) {
+      logits_cap = std::min(r.logits_capacity_frames, F);
+      if (logits_cap > dump_cap_) {
+        Q3_CUDA(cudaStreamSynchronize(stream_));
+        if (d_dump0_) cudaFree(d_dump0_);
+        if (d_dumpcp_) cudaFree(d_dumpcp_);
+        Q3_CUDA(cudaMalloc(&d_dump0_, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size));
+        Q3_CUDA(cudaMalloc(&d_dumpcp_, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size));
+        dump_cap_ = logits_cap;
+        drop_graphs();  // dump pointers are baked into captured graphs
+      }
+      Q3_CUDA(cudaMemsetAsync(d_dump0_, 0, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size, stream_));
+      Q3_CUDA(cudaMemsetAsync(d_dumpcp_, 0, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size, stream_));
+    }
+    if (slot == 0) dump_enabled_ = logits_cap > 0;
+    SlotState s{};
+    s.active = 1;
+    s.pos = p.P;  // positionOffset = inputEmbeds.shape[1] (:438)
+    s.total_text = p.n_trailing + 1;
+    s.max_tokens = forced ? r.n_forced_frames : std::min(std::max(r.max_tokens, 0), F);
+    s.n_forced = forced ? r.n_forced_frames : 0;
+    s.stream_variant = r.stream_variant ? 1 : 0;
+    s.top_k = r.top_k;
+    s.logits_cap = logits_cap;
+    s.temperature = r.temperature;
+    s.top_p = (r.top_p > 0.f) ? r.top_p : 1.0f;
+    s.rep_penalty = (r.repetition_penalty > 0.f) ? r.repetition_penalty : 1.0f;
+    s.seed = r.seed;
+    if (s.max_tokens <= 0) s.finished = 1;
+    h_state_[slot] = s;
+    Q3_CUDA(cudaMemsetAsync(d_sets_ + (size_t)slot * 16 * set_words_, 0, sizeof(unsigned) * 16 * set_words_, stream_));
   }
-  if (slot == 0) dump_enabled_ = logits_cap > 0;
-
-  SlotState s{};
-  s.active = 1;
-  s.pos = P;  // positionOffset = inputEmbeds.shape[1] (:438)
-  s.total_text = n_trailing + 1;
-  s.max_tokens = forced ? r.n_forced_frames : std::min(std::max(r.max_tokens, 0), F);
-  s.n_forced = forced ? r.n_forced_frames : 0;
-  s.stream_variant = r.stream_variant ? 1 : 0;
-  s.top_k = r.top_k;
-  s.logits_cap = logits_cap;
-  s.temperature = r.temperature;
-  s.top_p = (r.top_p > 0.f) ? r.top_p : 1.0f;
-  s.rep_penalty = (r.repetition_penalty > 0.f) ? r.repetition_penalty : 1.0f;
-  s.seed = r.seed;
-  if (s.max_tokens <= 0) s.finished = 1;
-  Q3_CUDA(cudaStreamSynchronize(stream_));  // staging buffers are reused by the next admit
-  h_state_[slot] = s;
-  Q3_CUDA(cudaMemcpyAsync(d_state_ + slot, h_state_ + slot, sizeof(SlotState), cudaMemcpyHostToDevice, stream_));
-  Q3_CUDA(cudaMemsetAsync(d_sets_ + (size_t)slot * 16 * set_words_, 0, sizeof(unsigned) * 16 * set_words_, stream_));
+  Q3_CUDA(cudaStreamSynchronize(stream_));  // pinned h_state_ entries were written after earlier async reads completed
+  for (const Plan& p : plans)
+    Q3_CUDA(cudaMemcpyAsync(d_state_ + p.slot, h_state_ + p.slot, sizeof(SlotState), cudaMemcpyHostToDevice, stream_));
   Q3_CUDA(cudaEventRecord(ev_b_, stream_));
   Q3_CUDA(cudaStreamSynchronize(stream_));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev_a_, ev_b_);
   last_prefill_ms += ms;
-  return adm;
 }
 
 void TalkerEngine::release(int slot) {

@@ -599,7 +599,7 @@ __global__ void assemble_rows_kernel(const float* __restrict__ tp_rows, int H, E
     float v = 0.f;
     if (tp >= 0) v += tp_rows[(size_t)tp * H + d];
     if (cd >= 0) v += load_as_f32(codec.w, (size_t)cd * H + d, codec.dt);
-    if (sp) v += spk[d];
+    if (sp > 0) v += spk[(size_t)(sp - 1) * H + d];  // sp = 1 + index of the utterance's raw speaker embedding
     y[(size_t)row * H + d] = v;
   }
 }
