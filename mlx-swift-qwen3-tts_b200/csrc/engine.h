@@ -68,8 +68,10 @@ class TalkerEngine {
                    const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter);
 
  private:
+  // one_row_per_slot: decode steps may fuse norm+RoPE+append into the attention launch (prefill / CP pass 0 may not)
   void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
-                     const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity);
+                     const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity,
+                     bool one_row_per_slot);
   void issue_frame(int n_slots);
   void build_tc_weights();
   TcLinear make_tc(const Linear& L, bool interleave_halves);

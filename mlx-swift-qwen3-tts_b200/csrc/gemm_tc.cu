@@ -313,7 +313,7 @@ bool tc_gemm_supported(const TcGemm& g) {
 
 void init_tc_gemm() {
   resolve_encode();
-  Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
 }
 
 void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
@@ -325,7 +325,11 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.tiles_per_batch = (g.T + kTileM - 1) / kTileM;
   p.bn = pick_bn(g.N, g.Bt * p.tiles_per_batch);
   const int stage_bytes = kABytes + p.bn * kBlockK * 2;
-  p.stages = std::max(2, std::min(6, (100 * 1024) / stage_bytes));
+  const long long ctas = (long long)g.Bt * p.tiles_per_batch * ((g.N + p.bn - 1) / p.bn);
+  // Bytes in flight per SM bound a latency-limited K loop: big grids run 2 CTAs/SM with ~100 KB rings each, small grids
+  // (batched decode: one CTA per SM at most) take the whole shared memory for one deep ring.
+  const int ring_budget = ctas > 148 ? 100 * 1024 : 200 * 1024;
+  p.stages = std::max(2, std::min(12, ring_budget / stage_bytes));
   p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
@@ -344,6 +348,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const CUtensorMap mb = make_map(g.w, 2, bdims, bstr, bbox);
 
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 64 * 8;
+  Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
   dim3 grid((unsigned)(g.Bt * p.tiles_per_batch), (unsigned)((g.N + p.bn - 1) / p.bn));
   tc_gemm_kernel<<<grid, kThreads, smem, c.stream>>>(ma, mb, p);
   c.tick();

@@ -44,6 +44,13 @@ void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int h
                       const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out,
                       int ldo);
 
+// decode-step fusion of the two launches above (valid when every slot has ONE row in the launch)
+void launch_rope_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
+                           const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
+                           const int* win_start, const KVLayout& kv, float* out, int ldo);
+void launch_rope_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
+                               const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
+                               const int* win_start, const KVLayout& kv, __half* out, int ldo);
 // same attention, fp16 output (A operand of the tcgen05 o_proj)
 void launch_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                           const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, __half* out, int ldo);

@@ -207,7 +207,7 @@ void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* o
 // Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
 void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
                                  const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
-                                 size_t layer_stride, int capacity) {
+                                 size_t layer_stride, int capacity, bool one_row_per_slot) {
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
   if (use_tc(m) && !S.tc.empty()) {
@@ -219,9 +219,14 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
       launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.in_norm, S.eps, (__half*)d_h16_, S.hidden);
       linear_tc(Tc.qkv, d_h16_, m, d_qkv_, qkv_ld, nullptr, 0, nullptr, TC_ACT_NONE, 0);
-      launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
-                                 row_pos, kv);
-      launch_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, (__half*)d_attn16_, attn_ld);
+      if (one_row_per_slot) {
+        launch_rope_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
+                                  (__half*)d_attn16_, attn_ld);
+      } else {
+        launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
+                                   row_pos, kv);
+        launch_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, (__half*)d_attn16_, attn_ld);
+      }
       linear_tc(Tc.o, d_attn16_, m, x, S.hidden, nullptr, 0, x, TC_ACT_NONE, 0);
       launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.post_norm, S.eps, (__half*)d_h16_, S.hidden);
       linear_tc(Tc.gate_up_il, d_h16_, m, nullptr, 0, d_act16_, S.inter, nullptr, TC_ACT_NONE, 1);
@@ -234,9 +239,14 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
     KVLayout kv;
     kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
     launch_linear(c, L.qkv, x, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
-    launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
-                               row_pos, kv);
-    launch_attention(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, d_attn_, attn_ld);
+    if (one_row_per_slot) {
+      launch_rope_attention(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
+                            d_attn_, attn_ld);
+    } else {
+      launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
+                                 row_pos, kv);
+      launch_attention(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, d_attn_, attn_ld);
+    }
     launch_linear(c, L.o, d_attn_, attn_ld, m, x, S.hidden, nullptr, 0.f, EPI_ADD);
     launch_linear(c, L.gate_up, x, S.hidden, m, d_act_, S.inter, L.post_norm, S.eps, EPI_SWIGLU);
     launch_linear(c, L.down, d_act_, S.inter, m, x, S.hidden, nullptr, 0.f, EPI_ADD);
@@ -363,7 +373,7 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
     Q3_CUDA(cudaMemcpyAsync(tr + (size_t)p.n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
   }
   // prefill: every row at its own (slot, position) (Model/Qwen3Talker.swift:437)
-  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C);
+  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false);
   // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
   for (const Plan& p : plans) {
     launch_rmsnorm(c, d_x_ + (size_t)(p.row0 + p.P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)p.slot * H, H);
@@ -449,7 +459,7 @@ void TalkerEngine::issue_frame(int n_slots) {
       x = d_cpx_;
     }
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
-                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity);
+                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
     if (use_tc(n_slots)) {
       launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, w_.cp.final_norm, w_.cp.eps, (__half*)d_h16_, Hcp);
@@ -467,7 +477,7 @@ void TalkerEngine::issue_frame(int n_slots) {
                         d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_);
   launch_step_rows(c, n_slots, d_state_, d_step_slot_, d_step_pos_, d_win_);
   forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
-                kv_layer_stride_, opt_.kv_capacity);
+                kv_layer_stride_, opt_.kv_capacity, true);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
   if (use_tc(n_slots)) {
     launch_f32_to_f16(c, d_hlast_, (size_t)n_slots * H, (__half*)d_h16_);

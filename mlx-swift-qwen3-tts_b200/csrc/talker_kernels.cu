@@ -33,6 +33,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {  // weights are re
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ dequantize
@@ -82,58 +83,55 @@ template <> struct FmtTraits<W_F32> { static constexpr int VPL = 4; };
 // Integer code -> float without I2F (quarter-rate pipe): OR the code into the mantissa of 2^23, subtract 2^23.
 __device__ __forceinline__ float code_to_f32(uint32_t code) { return __uint_as_float(0x4B000000u | code) - 8388608.0f; }
 
-// dot of this lane's VPL weights (one 16-byte load) with its VPL activations (VPL/4 float4 from lane-major smem)
+// Expand this lane's 16-byte weight load into VPL floats (integer codes for the packed formats; the group scale / bias are
+// applied to the finished dot product).  Done ONCE per weight load and reused for every activation row of the M tile.
 template <int FMT>
-__device__ __forceinline__ float lane_dot(const uint4& w, const float4* __restrict__ xs /* stride 32 float4 */) {
-  float acc = 0.f;
+__device__ __forceinline__ void lane_expand(const uint4& w, float (&o)[FmtTraits<FMT>::VPL]) {
   const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
   if constexpr (FMT == W_Q4) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 x = xs[j * 32];
-      const uint32_t h = ww[j >> 1] >> ((j & 1) * 16);
-      acc = fmaf(code_to_f32(h & 0xF), x.x, acc);
-      acc = fmaf(code_to_f32((h >> 4) & 0xF), x.y, acc);
-      acc = fmaf(code_to_f32((h >> 8) & 0xF), x.z, acc);
-      acc = fmaf(code_to_f32((h >> 12) & 0xF), x.w, acc);
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int n = 0; n < 8; ++n) o[i * 8 + n] = code_to_f32((ww[i] >> (4 * n)) & 0xF);
     }
   } else if constexpr (FMT == W_Q8) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 x = xs[j * 32];
-      const uint32_t h = ww[j];
-      // __byte_perm places byte k of h into byte 0 of 0x4B0000xx in one PRMT
-      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7440)) - 8388608.0f, x.x, acc);
-      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7441)) - 8388608.0f, x.y, acc);
-      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7442)) - 8388608.0f, x.z, acc);
-      acc = fmaf(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7443)) - 8388608.0f, x.w, acc);
+    for (int i = 0; i < 4; ++i) {
+      // __byte_perm places byte k of the word into byte 0 of 0x4B0000xx in one PRMT
+      o[i * 4 + 0] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7440)) - 8388608.0f;
+      o[i * 4 + 1] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7441)) - 8388608.0f;
+      o[i * 4 + 2] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7442)) - 8388608.0f;
+      o[i * 4 + 3] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7443)) - 8388608.0f;
     }
   } else if constexpr (FMT == W_BF16) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float4 x = xs[j * 32];
-      acc = fmaf(__uint_as_float(ww[2 * j] << 16), x.x, acc);
-      acc = fmaf(__uint_as_float(ww[2 * j] & 0xFFFF0000u), x.y, acc);
-      acc = fmaf(__uint_as_float(ww[2 * j + 1] << 16), x.z, acc);
-      acc = fmaf(__uint_as_float(ww[2 * j + 1] & 0xFFFF0000u), x.w, acc);
+    for (int i = 0; i < 4; ++i) {
+      o[2 * i] = __uint_as_float(ww[i] << 16);
+      o[2 * i + 1] = __uint_as_float(ww[i] & 0xFFFF0000u);
     }
   } else if constexpr (FMT == W_F16) {
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const float4 x = xs[j * 32];
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ww[2 * j]));
-      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&ww[2 * j + 1]));
-      acc = fmaf(a.x, x.x, acc);
-      acc = fmaf(a.y, x.y, acc);
-      acc = fmaf(b.x, x.z, acc);
-      acc = fmaf(b.y, x.w, acc);
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
+      o[2 * i] = a.x;
+      o[2 * i + 1] = a.y;
     }
   } else {
-    const float4 x = xs[0];
-    acc = fmaf(__uint_as_float(ww[0]), x.x, acc);
-    acc = fmaf(__uint_as_float(ww[1]), x.y, acc);
-    acc = fmaf(__uint_as_float(ww[2]), x.z, acc);
-    acc = fmaf(__uint_as_float(ww[3]), x.w, acc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __uint_as_float(ww[i]);
+  }
+}
+// dot of the expanded weights with this lane's VPL activations (VPL/4 float4 from lane-major smem, stride 32 float4)
+template <int FMT>
+__device__ __forceinline__ float lane_dot(const float (&w)[FmtTraits<FMT>::VPL], const float4* __restrict__ xs) {
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < FmtTraits<FMT>::VPL / 4; ++j) {
+    const float4 x = xs[j * 32];
+    acc = fmaf(w[4 * j], x.x, acc);
+    acc = fmaf(w[4 * j + 1], x.y, acc);
+    acc = fmaf(w[4 * j + 2], x.z, acc);
+    acc = fmaf(w[4 * j + 3], x.w, acc);
   }
   return acc;
 }
@@ -160,7 +158,7 @@ struct LinearKArgs {
 // pass (RMSNorm statistics, per-lane activation sums for the group-bias term and the smem fill together) behind ONE
 // __syncthreads; the RMS scale is applied to the finished dot product (it is a per-row scalar).
 template <int FMT, int MT>
-__global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
+__global__ void __launch_bounds__(256, (MT <= 2 ? 3 : 1)) linear_kernel(const LinearKArgs a) {
   constexpr int VPL = FmtTraits<FMT>::VPL;
   constexpr int KC = 32 * VPL;
   constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
@@ -181,26 +179,15 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
   const int ngroups = QUANT ? a.in / a.group : 0;
   const int r_first = blockIdx.x * 8 + warp;
 
-  // ---- (0) prefetch the first row's first chunk group: independent of x ----
-  uint4 pre_w[2][4];
-  float pre_s[2][4], pre_b[2][4];
+  // ---- (0) L2 prefetch of the warp's first row(s): weights do not depend on x, so their HBM->L2 trip overlaps the staging ----
   if (r_first < out_eff) {
-#pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      if (s < nsub) {
-        const int row = r_first + s * out_eff;
-        const uint4* wr = reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(a.w) + (size_t)row * row_bytes);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (u * KC + lane * VPL < a.in) {
-            pre_w[s][u] = ldg_stream(wr + (size_t)u * 32 + lane);
-            if constexpr (QUANT) {
-              const size_t gi = (size_t)row * ngroups + (u * KC + lane * VPL) / a.group;
-              pre_s[s][u] = load_as_f32(a.scales, gi, a.sdt);
-              pre_b[s][u] = load_as_f32(a.biases, gi, a.sdt);
-            }
-          }
-        }
+    for (int s = 0; s < nsub; ++s) {
+      const int row = r_first + s * out_eff;
+      const unsigned char* wr = reinterpret_cast<const unsigned char*>(a.w) + (size_t)row * row_bytes;
+      for (size_t off = (size_t)lane * 128; off < row_bytes; off += 32 * 128) prefetch_l2(wr + off);
+      if constexpr (QUANT) {
+        if (lane == 0) prefetch_l2(reinterpret_cast<const unsigned char*>(a.scales) + (size_t)row * ngroups * (a.sdt == Q3TTS_F32 ? 4 : 2));
+        if (lane == 1) prefetch_l2(reinterpret_cast<const unsigned char*>(a.biases) + (size_t)row * ngroups * (a.sdt == Q3TTS_F32 ? 4 : 2));
       }
     }
   }
@@ -272,20 +259,14 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
       for (int c0 = 0; c0 < nchunk; c0 += 4) {
         uint4 wv[4];
         float scv[4], biv[4];
-        const bool use_pre = (r == r_first) && (c0 == 0);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if ((c0 + u) * KC + lane * VPL < a.in) {
-            if (use_pre) {
-              wv[u] = pre_w[s][u];
-              if constexpr (QUANT) { scv[u] = pre_s[s][u]; biv[u] = pre_b[s][u]; }
-            } else {
-              wv[u] = ldg_stream(wr + (size_t)(c0 + u) * 32 + lane);
-              if constexpr (QUANT) {
-                const size_t gi = (size_t)row * ngroups + ((c0 + u) * KC + lane * VPL) / a.group;
-                scv[u] = load_as_f32(a.scales, gi, a.sdt);
-                biv[u] = load_as_f32(a.biases, gi, a.sdt);
-              }
+            wv[u] = ldg_stream(wr + (size_t)(c0 + u) * 32 + lane);
+            if constexpr (QUANT) {
+              const size_t gi = (size_t)row * ngroups + ((c0 + u) * KC + lane * VPL) / a.group;
+              scv[u] = load_as_f32(a.scales, gi, a.sdt);
+              biv[u] = load_as_f32(a.biases, gi, a.sdt);
             }
           }
         }
@@ -293,9 +274,11 @@ __global__ void __launch_bounds__(256) linear_kernel(const LinearKArgs a) {
         for (int u = 0; u < 4; ++u) {
           if ((c0 + u) * KC + lane * VPL < a.in) {
             const int ch = c0 + u;
+            float wf[VPL];
+            lane_expand<FMT>(wv[u], wf);
 #pragma unroll
             for (int mi = 0; mi < MT; ++mi) {
-              const float d = lane_dot<FMT>(wv[u], xs + (size_t)mi * xstride + ch * (KC / 4) + lane);
+              const float d = lane_dot<FMT>(wf, xs + (size_t)mi * xstride + ch * (KC / 4) + lane);
               if constexpr (QUANT) acc[mi] += scv[u] * d + biv[u] * xsum[mi * (nchunk * 32) + ch * 32 + lane];
               else acc[mi] += d;
             }
@@ -517,6 +500,132 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
   for (int g = 0; g < G; ++g) store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, o[g] / red_sum[g]);
 }
+// Decode-step fusion of q/k norm + RoPE + KV append + window attention (one launch instead of two, no q/k round trip through
+// HBM).  Valid only when every slot contributes ONE row to the launch (talker step, code-predictor passes >= 1): the keys of
+// positions < pos were written by earlier launches, the current position's k/v are produced here and used from shared memory.
+template <int G, typename OutT>
+__global__ void __launch_bounds__(128) rope_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
+                                                             const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
+                                                             const float* __restrict__ inv_freq, const int* __restrict__ row_slot,
+                                                             const int* __restrict__ row_pos, const int* __restrict__ win_start, KVLayout kv,
+                                                             OutT* __restrict__ out, int ldo, float scale) {
+  extern __shared__ __align__(16) float sm[];
+  float* q = sm;                  // [G][128]
+  float* kcur = sm + G * 128;     // [128]
+  float* vcur = kcur + 128;       // [128]
+  float* sc = vcur + 128;         // [G][S]
+  __shared__ float red_sum[G];
+  const int row = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slot = row_slot[row], pos = row_pos[row];
+  const int w0 = win_start ? win_start[slot] : 0;
+  const int S = pos - w0 + 1;
+  const int cap = kv.capacity;
+  const int ring = pos % cap;
+  float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  const float* rowp = qkv + (size_t)row * ld;
+  // phase 0: per-head RMSNorm + rotate-half RoPE (Model/Qwen3Layers.swift:174-195); warp hh < G -> q head, hh == G -> k head
+  for (int hh = warp; hh <= G; hh += 4) {
+    const float* src = rowp + (size_t)(hh < G ? (kvh * G + hh) : (heads + kvh)) * 128;
+    const float a0 = src[lane], a1 = src[lane + 32], b0 = src[lane + 64], b1 = src[lane + 96];
+    const float ss = warp_sum(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+    const float inv = rsqrtf(ss * (1.0f / 128.0f) + eps);
+    const float* nw = hh < G ? q_norm : k_norm;
+    const float x0 = a0 * inv * nw[lane], x1 = a1 * inv * nw[lane + 32], y0 = b0 * inv * nw[lane + 64], y1 = b1 * inv * nw[lane + 96];
+    float s0, c0, s1, c1;
+    sincosf((float)pos * inv_freq[lane], &s0, &c0);
+    sincosf((float)pos * inv_freq[lane + 32], &s1, &c1);
+    const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
+    float* dst = hh < G ? q + hh * 128 : kcur;
+    dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+    if (hh == G) {  // append k to the ring (:197-201)
+      float* kd = kb + (size_t)ring * 128;
+      kd[lane] = o0; kd[lane + 32] = o1; kd[lane + 64] = o2; kd[lane + 96] = o3;
+    }
+  }
+  {
+    const float v = rowp[(size_t)(heads + kv_heads + kvh) * 128 + tid];
+    vcur[tid] = v;
+    vb[(size_t)ring * 128 + tid] = v;
+  }
+  __syncthreads();
+  // phase 1: scores; the newest key comes from shared memory
+  for (int j = tid; j < S; j += 128) {
+    const float4* kr = (j == S - 1) ? reinterpret_cast<const float4*>(kcur) : reinterpret_cast<const float4*>(kb + (size_t)((w0 + j) % cap) * 128);
+    float acc[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < 32; ++d) {
+      const float4 kk = kr[d];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float4 qq = reinterpret_cast<const float4*>(q + g * 128)[d];
+        acc[g] += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) sc[g * S + j] = acc[g] * scale;
+  }
+  __syncthreads();
+  for (int g = warp; g < G; g += 4) {
+    float mx = -INFINITY;
+    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, sc[g * S + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < S; j += 32) { const float e = expf(sc[g * S + j] - mx); sc[g * S + j] = e; sum += e; }
+    sum = warp_sum(sum);
+    if (lane == 0) red_sum[g] = sum;
+  }
+  __syncthreads();
+  float o[G];
+#pragma unroll
+  for (int g = 0; g < G; ++g) o[g] = 0.f;
+  int j = 0;
+  for (; j + 4 <= S - 1; j += 4) {  // 4 independent V loads in flight
+    const float v0 = vb[(size_t)((w0 + j) % cap) * 128 + tid], v1 = vb[(size_t)((w0 + j + 1) % cap) * 128 + tid];
+    const float v2 = vb[(size_t)((w0 + j + 2) % cap) * 128 + tid], v3 = vb[(size_t)((w0 + j + 3) % cap) * 128 + tid];
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j + 3], v3, fmaf(sc[g * S + j + 2], v2, fmaf(sc[g * S + j + 1], v1, fmaf(sc[g * S + j], v0, o[g]))));
+  }
+  for (; j < S - 1; ++j) {
+    const float vv = vb[(size_t)((w0 + j) % cap) * 128 + tid];
+#pragma unroll
+    for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    o[g] = fmaf(sc[g * S + S - 1], vcur[tid], o[g]);
+    store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, o[g] / red_sum[g]);
+  }
+}
+template <typename OutT>
+static void launch_rope_attention_t(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
+                                    const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
+                                    const int* win_start, const KVLayout& kv, OutT* out, int ldo) {
+  if (m <= 0) return;
+  const int G = heads / kv_heads;
+  const float scale = 1.0f / sqrtf(128.0f);
+  const size_t smem = (size_t)(G * 128 + 256 + G * kv.capacity) * sizeof(float);
+  Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
+  dim3 grid(m, kv_heads);
+  if (G == 1) rope_attention_kernel<1, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  else if (G == 2) rope_attention_kernel<2, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  else if (G == 4) rope_attention_kernel<4, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
+  c.tick();
+}
+void launch_rope_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
+                           const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
+                           const int* win_start, const KVLayout& kv, float* out, int ldo) {
+  launch_rope_attention_t<float>(c, qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo);
+}
+void launch_rope_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
+                               const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
+                               const int* win_start, const KVLayout& kv, __half* out, int ldo) {
+  launch_rope_attention_t<__half>(c, qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo);
+}
+
 template <typename OutT>
 static void launch_attention_t(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                                const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, OutT* out, int ldo) {
@@ -947,6 +1056,12 @@ void init_talker_kernels() {
   init_linear_fmt<W_BF16>();
   init_linear_fmt<W_F16>();
   init_linear_fmt<W_F32>();
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<1, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<2, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
