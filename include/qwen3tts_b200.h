@@ -134,7 +134,8 @@ typedef struct q3tts_timing {
   int64_t weight_bytes_per_frame; /* algorithmic bytes streamed per 12.5 Hz frame */
   double talker_ms;               /* CUDA-event time of prompt assembly + prefill + all frame steps of the last call */
   int64_t codec_flops;            /* algorithmic flops of the codec passes of the last call */
-  int64_t reserved[4];
+  int64_t persistent_launches;    /* launches of the persistent frame kernel in the last call (0 = CUDA-graph / eager path) */
+  int64_t reserved[3];
 } q3tts_timing;
 
 /* ------------------------------------------------------------------------------------------------------

@@ -64,11 +64,11 @@ void require_device(int device) {
 struct CallTimer {
   q3tts_handle* h;
   int64_t launches0;
-  int64_t replays0 = 0;
+  int64_t replays0 = 0, mega0 = 0;
   explicit CallTimer(q3tts_handle* hh) : h(hh) {
     h->timing = q3tts_timing{};
     launches0 = h->counter.n;
-    if (h->talker) { replays0 = h->talker->graph_replays; h->talker->last_prefill_ms = 0; }
+    if (h->talker) { replays0 = h->talker->graph_replays; mega0 = h->talker->mega_launches; h->talker->last_prefill_ms = 0; }
     cudaEventRecord(h->ev_start, h->stream);
   }
   void finish() {
@@ -80,6 +80,7 @@ struct CallTimer {
     h->timing.kernel_launches = h->counter.n - launches0;
     if (h->talker) {
       h->timing.graph_replays = h->talker->graph_replays - replays0;
+      h->timing.persistent_launches = h->talker->mega_launches - mega0;
       h->timing.prefill_ms = h->talker->last_prefill_ms;
       h->timing.weight_bytes_per_frame = (int64_t)h->talker->weight_bytes_per_frame();
     }

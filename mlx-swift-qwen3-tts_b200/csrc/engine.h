@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 
+#include "frame_kernel.h"
 #include "kernels.h"
 
 namespace q3 {
@@ -58,7 +59,8 @@ class TalkerEngine {
   int quant_group() const { return eff_group_; }
   size_t device_bytes() const { return arena_.total(); }
   size_t weight_bytes_per_frame() const { return w_.talker_step_bytes + 15 * w_.cp_pass_bytes; }
-  int64_t graph_replays = 0, graph_nodes_replayed = 0;
+  int64_t graph_replays = 0, graph_nodes_replayed = 0, mega_launches = 0;
+  bool megakernel_enabled() const { return mega_.ok; }
   double last_prefill_ms = 0;
 
   // measurement hook (q3tts_profile_linear)
@@ -74,6 +76,7 @@ class TalkerEngine {
                      bool one_row_per_slot);
   void issue_frame(int n_slots);
   void build_tc_weights();
+  void build_mega_plan();
   TcLinear make_tc(const Linear& L, bool interleave_halves);
   bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }
   // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
@@ -125,6 +128,7 @@ class TalkerEngine {
     int64_t nodes = 0;
   };
   std::map<int, Graph> graphs_;  // key: n_slots * 2 + dump_enabled
+  MegaPlan mega_;                // persistent frame kernel (batch-1 decode); !ok -> graph path
 };
 
 struct Handle {

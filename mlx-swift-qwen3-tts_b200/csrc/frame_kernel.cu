@@ -1,0 +1,777 @@
+// Persistent frame kernel (sm_100a).  Grid = one CTA per SM (cooperative launch), 16 warps per CTA:
+//   warps 0-14 : consumers.  Every Qwen3DecoderLayer is five phases — [RMSNorm + qkv GEMV] | [q/k norm + RoPE + KV append +
+//                split-key window attention] | [split combine + o GEMV + residual] | [RMSNorm + gate/up GEMV + SwiGLU] |
+//                [down GEMV + residual] — separated by a grid barrier (one L2 atomic + one L2 poll) instead of a kernel launch.
+//                Each CTA owns a contiguous slice of every linear's output rows; a warp owns a row: 128-bit reads of the
+//                packed row from shared memory, dequant in registers, activations lane-major in shared memory, shuffle reduce.
+//   warp 15    : weight producer.  Walks the frame's linears in execution order and copies this CTA's row slices (weights,
+//                scales, biases) global -> shared with 1-D TMA bulk copies (UBLKCP) into a ring of slots, mbarrier
+//                complete_tx to the consumers.  Weight addresses never depend on activations, so the stream runs several
+//                phases ahead and the dependency chain waits only on L2-resident activations.
+// Sampling (Qwen3Talker.sampleToken), the next-input embedding sum and all loop bookkeeping run inside the same kernel.
+//
+// Batch-1 decode is bound by the LATENCY of ~660 dependent phases per frame, not by bandwidth: each warp runs nearly alone on
+// its scheduler, so what counts is the number of dependent instructions per phase.  Hence: one copy of every phase body
+// (instruction cache), no integer division on the per-phase path, descriptors prefetched a phase ahead into shared memory,
+// 16 warps so that ptxas may use 128 registers, and shared-memory pointers the compiler can prove are shared (LDS, not LD).
+#include "device_utils.cuh"
+#include "frame_kernel.h"
+#include "sampler.cuh"
+
+namespace q3 {
+
+namespace {
+
+constexpr int kCWarps = 15;            // consumer warps
+constexpr int kCons = kCWarps * 32;    // 480 consumer threads (named barrier 1)
+constexpr int kMegaThreads = 512;
+constexpr int kKeyTile = 128;          // keys per attention item (host sizes nsplit so that a split never exceeds it)
+constexpr int kKeyGroups = 3;          // P.V key groups: 3 x 128 threads
+
+__device__ __forceinline__ void cbar() { asm volatile("bar.sync 1, %0;" ::"n"(kCons) : "memory"); }
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded waits: a protocol bug must surface as a trapped kernel (an error on the host), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+               "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {  // (a & b) | c in ONE LOP3
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// Shared-memory plan.  Everything is addressed from the one extern array so the compiler keeps the shared address space.
+extern __shared__ __align__(128) uint8_t smem[];
+
+struct Sm {   // byte offsets into smem (from MegaParams) resolved once
+  uint8_t* ring;
+  uint64_t *full, *empty;
+  float4* xs;       // lane-major staged activations; also the scratch of the attention / sampling phases
+  float* xsum;
+  float* xraw;      // raw residual rows of the current layer input
+  float* red;       // [rows][16] partial sums of squares
+  MegaLinear* dsc;  // [2] descriptor of the current / next linear
+};
+
+struct Slice { int r0, rows, rch, nch; };
+// no integer division on the per-phase path: the unit split over the grid and the chunk size come precomputed from the host
+__device__ __forceinline__ Slice slice_of(const MegaLinear& L) {
+  const int c = blockIdx.x;
+  Slice s;
+  s.rows = (L.ubase + (c < L.urem ? 1 : 0)) * L.unit;
+  s.r0 = (c * L.ubase + min(c, L.urem)) * L.unit;
+  s.rch = L.rch;
+  s.nch = s.rows == 0 ? 0 : (s.rows <= s.rch ? 1 : (s.rows + s.rch - 1) / s.rch);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------ producer warp
+__device__ void producer_loop(const MegaParams& p, uint8_t* ring, uint64_t* full, uint64_t* empty) {
+  int slot = 0;
+  uint32_t ph = 0;
+  for (int f = 0; f < p.n_frames; ++f) {
+    for (int li = 0; li < p.n_lin; ++li) {
+      const MegaLinear L = p.lin[li];
+      const Slice s = slice_of(L);
+      for (int c = 0; c < s.nch; ++c) {
+        mbar_wait(&empty[slot], ph ^ 1u);
+        const int row0 = s.r0 + c * s.rch;
+        const int rows = min(s.rch, s.rows - c * s.rch);
+        const uint32_t wb = (uint32_t)rows * L.row_bytes, sb = (uint32_t)rows * L.srow_bytes;
+        mbar_expect_tx(&full[slot], (uint32_t)L.nsub * (wb + 2u * sb));
+        uint8_t* dst = ring + (size_t)slot * p.slot_bytes;
+        for (int sub = 0; sub < L.nsub; ++sub) {
+          const size_t grow = (size_t)sub * L.out_eff + row0;
+          bulk_g2s(dst, reinterpret_cast<const uint8_t*>(L.w) + grow * L.row_bytes, wb, &full[slot]);
+          dst += wb;
+          if (sb) {
+            bulk_g2s(dst, reinterpret_cast<const uint8_t*>(L.scales) + grow * L.srow_bytes, sb, &full[slot]);
+            dst += sb;
+            bulk_g2s(dst, reinterpret_cast<const uint8_t*>(L.biases) + grow * L.srow_bytes, sb, &full[slot]);
+            dst += sb;
+          }
+        }
+        if (++slot == p.n_ring) { slot = 0; ph ^= 1u; }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-thread state
+struct Ctx {
+  int slot;          // ring position of the next chunk (consumer side)
+  uint32_t ph;
+  unsigned bar_target;
+  int tid, lane, warp;
+  long long* trace;  // per-phase cycle stamps of this CTA's thread 0 (diagnostics; null = off)
+  long long wait_full;
+};
+
+// ------------------------------------------------------------------------------------------------ grid barrier
+__device__ __forceinline__ void grid_sync(const MegaParams& p, Ctx& cx) {
+  cx.bar_target += gridDim.x;
+  cbar();
+  if (cx.tid == 0) {
+    if (cx.trace) cx.trace[3] = clock64();
+    __threadfence();
+    atomicAdd(p.barrier, 1u);
+    if (cx.trace) cx.trace[4] = clock64();
+    uint32_t spins = 0;
+    while (ld_acquire_u32(p.barrier) < cx.bar_target) {
+      if (++spins > (1u << 24)) __trap();
+    }
+    __threadfence();
+    if (cx.trace) { cx.trace[5] = clock64(); cx.trace += 8; }
+  }
+  cbar();
+}
+
+// ------------------------------------------------------------------------------------------------ activation staging
+__device__ __forceinline__ float4 ld_emb4(const Embedding& e, int id, int f) {  // 4 consecutive elements of row `id`
+  if (id < 0 || id >= e.rows) return make_float4(0.f, 0.f, 0.f, 0.f);
+  const size_t i = (size_t)id * e.dim + (size_t)f * 4;
+  if (e.dt == Q3TTS_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.w) + i);
+  const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(e.w) + i);
+  if (e.dt == Q3TTS_F16) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  return make_float4(__uint_as_float(r.x << 16), __uint_as_float(r.x & 0xFFFF0000u), __uint_as_float(r.y << 16), __uint_as_float(r.y & 0xFFFF0000u));
+}
+__device__ __forceinline__ void add4(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+enum InKind {
+  IN_GX = 0,        // residual rows from the exchange buffer
+  IN_GX_LAST,       // last row of each slot (code-predictor head)
+  IN_CP0,           // pass 0: rows (2s, 2s+1) = [h_last[s], codec_embedding(code0)]          (Model/Qwen3Talker.swift:503-505)
+  IN_CPG,           // pass g: row s = code_predictor.codec_embedding[g-1](code_g)            (:509-510)
+  IN_TALKER,        // next talker input = (trailing text | tts_pad) + sum of 16 code embeddings  (:531-549)
+  IN_ATTN,          // attention output: combine of the split-key partials
+  IN_ACT            // SwiGLU activations
+};
+
+struct InArgs {
+  int kind;
+  int pass;      // code-predictor pass (IN_CPG) ; rows per slot (IN_GX_LAST)
+  int ld;        // row stride of the source buffer (IN_GX*, IN_ACT)
+  int nsplit, heads;
+};
+
+__device__ __forceinline__ float4 load_in(const MegaParams& p, const InArgs& a, int mi, int f) {
+  switch (a.kind) {
+    case IN_GX: return ldcg4(p.gx + (size_t)mi * a.ld + (size_t)f * 4);
+    case IN_GX_LAST: return ldcg4(p.gx + (size_t)(mi * a.pass + a.pass - 1) * a.ld + (size_t)f * 4);
+    case IN_ACT: return ldcg4(p.gact + (size_t)mi * a.ld + (size_t)f * 4);
+    case IN_CP0: {
+      const int slot = mi >> 1;
+      if ((mi & 1) == 0) return ldcg4(p.hlast + (size_t)slot * p.H + (size_t)f * 4);
+      return ld_emb4(p.codec, __ldcg(p.cur_codes + slot * 16), f);
+    }
+    case IN_CPG: return ld_emb4(p.cp_emb[a.pass - 1], __ldcg(p.cur_codes + mi * 16 + a.pass), f);
+    case IN_TALKER: {
+      const SlotState& s = p.st[mi];
+      const int ti = __ldcg(&s.trailing_idx), tt = __ldcg(&s.total_text);
+      const float* text = (ti < tt) ? p.trailing + ((size_t)mi * p.max_trailing + ti) * p.H : p.tts_pad;
+      float4 sum = ld_emb4(p.codec, __ldcg(p.cur_codes + mi * 16), f);
+#pragma unroll
+      for (int g = 1; g < 16; ++g) add4(sum, ld_emb4(p.cp_emb[g - 1], __ldcg(p.cur_codes + mi * 16 + g), f));
+      float4 t = *reinterpret_cast<const float4*>(text + (size_t)f * 4);
+      add4(t, sum);
+      return t;
+    }
+    default: {  // IN_ATTN: softmax-weighted merge of the key splits (flash-decoding combine)
+      const int h = f >> 5;
+      float M = -INFINITY;
+      for (int sp = 0; sp < a.nsplit; ++sp)
+        M = fmaxf(M, __ldcg(p.gpart + (size_t)(mi * a.nsplit + sp) * p.part_stride + a.heads * 128 + 2 * h));
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      float den = 0.f;
+      for (int sp = 0; sp < a.nsplit; ++sp) {
+        const float* base = p.gpart + (size_t)(mi * a.nsplit + sp) * p.part_stride;
+        const float l = __ldcg(base + a.heads * 128 + 2 * h + 1);
+        if (l > 0.f) {
+          const float w = expf(__ldcg(base + a.heads * 128 + 2 * h) - M);
+          const float4 o = ldcg4(base + (size_t)f * 4);
+          acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
+          den += w * l;
+        }
+      }
+      const float inv = 1.0f / den;
+      return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    }
+  }
+}
+
+// Stage `m` rows of K values: raw copy (residual) when keep_raw, RMSNorm weight folded in, lane-major layout, per-lane sums
+// for the group-bias term.  Leaves sum(x^2) per row in sm.red (the RMS scale is applied to the finished dot products).
+template <int FMT>
+__device__ __forceinline__ void stage_rows(const MegaParams& p, const Sm& sm, const Ctx& cx, const InArgs& in, int m, int K, const float* norm_w,
+                                           bool keep_raw) {
+  constexpr int VPL = FmtTraits<FMT>::VPL;
+  constexpr int KC = 32 * VPL;
+  constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
+  constexpr int LPG = VPL / 4;
+  const int nchunk = (K + KC - 1) / KC;
+  const int xstride = nchunk * (KC / 4);
+  const int in4 = K >> 2;
+  for (int mi = 0; mi < m; ++mi) {
+    float ss = 0.f;
+    for (int f0 = 0; f0 < in4; f0 += kCons) {
+      const int f = f0 + cx.tid;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f < in4) {
+        v = load_in(p, in, mi, f);
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (keep_raw) reinterpret_cast<float4*>(sm.xraw + mi * p.raw_ld)[f] = v;
+        if (norm_w != nullptr) {
+          const float4 nw = __ldg(reinterpret_cast<const float4*>(norm_w) + f);
+          v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
+        }
+        const int e = f << 2;
+        const int ch = e / KC, ec = e - ch * KC;
+        const int l = ec / VPL, j = (ec - l * VPL) >> 2;
+        sm.xs[mi * xstride + ch * (KC / 4) + j * 32 + l] = v;
+      }
+      if constexpr (QUANT) {
+        float s4 = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+        for (int o = 1; o < LPG; o <<= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        if ((cx.tid & (LPG - 1)) == 0 && f < in4) {
+          const int e = f << 2;
+          const int ch = e / KC;
+          sm.xsum[mi * (nchunk * 32) + ch * 32 + (e - ch * KC) / VPL] = s4;
+        }
+      }
+    }
+    if (norm_w != nullptr) {
+      ss = warp_sum(ss);
+      if (cx.lane == 0) sm.red[mi * 16 + cx.warp] = ss;
+    }
+  }
+  cbar();
+}
+
+// ------------------------------------------------------------------------------------------------ GEMV over the ring
+enum EpiKind { E_STORE = 0, E_ADD_RAW = 1, E_SWIGLU = 2 };
+
+__device__ __forceinline__ float scale_to_f32(uint32_t raw16, int sdt) {  // bf16 / f16 payload of a 16-bit shared-memory load
+  const float as_bf16 = __uint_as_float(raw16 << 16);
+  const float as_f16 = __half2float(__ushort_as_half((unsigned short)raw16));
+  return sdt == Q3TTS_F16 ? as_f16 : as_bf16;
+}
+
+template <int FMT, int M>
+__device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx& cx, const MegaLinear& L, int m, bool has_norm, float eps, int epi,
+                                          float* out, int ld_out) {
+  constexpr int VPL = FmtTraits<FMT>::VPL;
+  constexpr int KC = 32 * VPL;
+  constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
+  const int K = L.in;
+  const int nchunk = (K + KC - 1) / KC;
+  const int xstride = nchunk * (KC / 4);
+  const int row_bytes = L.row_bytes, srow_bytes = L.srow_bytes, nsub = L.nsub, sdt = L.sdt, gshift = L.group_shift;
+  float inv_rms[M];
+#pragma unroll
+  for (int mi = 0; mi < M; ++mi) {
+    inv_rms[mi] = 1.0f;
+    if (has_norm && mi < m) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kCWarps; ++w) s += sm.red[mi * 16 + w];
+      inv_rms[mi] = rsqrtf(s / (float)K + eps);
+    }
+  }
+  const Slice s = slice_of(L);
+  for (int c = 0; c < s.nch; ++c) {
+    const int slot = cx.slot;
+    const long long tw0 = cx.trace ? clock64() : 0;
+    mbar_wait(&sm.full[slot], cx.ph);
+    if (cx.trace) cx.wait_full += clock64() - tw0;
+    const int row0 = s.r0 + c * s.rch;
+    const int rows = min(s.rch, s.rows - c * s.rch);
+    const int wb = rows * row_bytes, sb = rows * srow_bytes;
+    const uint8_t* base = sm.ring + slot * p.slot_bytes;
+    for (int r = cx.warp; r < rows; r += kCWarps) {
+      float res[2][M];
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+        for (int mi = 0; mi < M; ++mi) res[sub][mi] = 0.f;
+      }
+#pragma unroll
+      for (int sub = 0; sub < 2; ++sub) {
+        if (sub < nsub) {
+          const uint8_t* sbase = base + sub * (wb + 2 * sb);
+          const uint4* wr = reinterpret_cast<const uint4*>(sbase + r * row_bytes);
+          const uint8_t* scp = sbase + wb + r * srow_bytes;
+          float acc[M];
+#pragma unroll
+          for (int mi = 0; mi < M; ++mi) acc[mi] = 0.f;
+          for (int ch = 0; ch < nchunk; ++ch) {
+            const int e0 = ch * KC + cx.lane * VPL;
+            if (e0 < K) {
+              const uint4 wv = wr[ch * 32 + cx.lane];
+              float scv = 1.f, biv = 0.f;
+              if constexpr (QUANT) {
+                const int gi = e0 >> gshift;
+                if (sdt == Q3TTS_F32) {
+                  scv = reinterpret_cast<const float*>(scp)[gi];
+                  biv = reinterpret_cast<const float*>(scp + sb)[gi];
+                } else {
+                  scv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp)[gi], sdt);
+                  biv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp + sb)[gi], sdt);
+                }
+              }
+              float wf[VPL];
+              if constexpr (FMT == W_Q4) {  // m = 1 + q/16: shift + one LOP3 per value, no FADD
+                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                  for (int n = 0; n < 8; ++n) {
+                    const uint32_t sh = (19 - 4 * n) >= 0 ? (ww[i] << ((19 - 4 * n) & 31)) : (ww[i] >> ((4 * n - 19) & 31));
+                    wf[i * 8 + n] = __uint_as_float(lop3_and_or(sh, 0x00780000u, 0x3F800000u));
+                  }
+                }
+                scv *= 16.0f;  // s*q.x + b*sum(x) = 16s*(m.x) + (b - 16s)*sum(x)
+                biv -= scv;
+              } else {
+                lane_expand<FMT>(wv, wf);
+              }
+#pragma unroll
+              for (int mi = 0; mi < M; ++mi) {
+                const float d = lane_dot<FMT>(wf, sm.xs + mi * xstride + ch * (KC / 4) + cx.lane);
+                if constexpr (QUANT) acc[mi] += scv * d + biv * sm.xsum[mi * (nchunk * 32) + ch * 32 + cx.lane];
+                else acc[mi] += d;
+              }
+            }
+          }
+#pragma unroll
+          for (int mi = 0; mi < M; ++mi) res[sub][mi] = warp_sum(acc[mi]) * inv_rms[mi];
+        }
+      }
+      const int grow = row0 + r;
+#pragma unroll
+      for (int mi = 0; mi < M; ++mi) {
+        if (cx.lane == mi && mi < m) {
+          float v = res[0][mi];
+          if (epi == E_SWIGLU) {
+            float g = v, u = res[1][mi];
+            if (L.bias) { g += L.bias[grow]; u += L.bias[grow + L.out_eff]; }
+            v = silu_f(g) * u;
+          } else {
+            if (L.bias) v += L.bias[grow];
+            if (epi == E_ADD_RAW) v += sm.xraw[mi * p.raw_ld + grow];
+          }
+          out[(size_t)mi * ld_out + grow] = v;
+        }
+      }
+    }
+    __syncwarp();
+    if (cx.lane == 0) mbar_arrive(&sm.empty[slot]);
+    if (++cx.slot == p.n_ring) { cx.slot = 0; cx.ph ^= 1u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ attention phase
+// item = (slot, kv head, key split).  rps rows per slot (2 only in code-predictor pass 0).  Writes unnormalised partial
+// outputs + (max, sum) per head; the o-projection staging merges the splits.
+template <int G>
+__device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, const MegaStack& S, const float* q_norm, const float* k_norm, int rps,
+                           bool talker, int cp_pos0, int l) {
+  float* sc0 = reinterpret_cast<float*>(sm.xs);
+  float* q = sc0;                        // [2][G][128]
+  float* kcur = q + 2 * G * 128;         // [2][128]
+  float* vcur = kcur + 256;              // [2][128]
+  float* sc = vcur + 256;                // [G][kKeyTile]
+  float* ored = sc + G * kKeyTile;       // [kKeyGroups][G][128]
+  float* stat = ored + kKeyGroups * G * 128;  // [G][2]
+  const int heads = S.heads, kv_heads = S.kv_heads, nsplit = S.nsplit, cap = S.capacity;
+  const int qkv_ld = (heads + 2 * kv_heads) * 128;
+  const int n_items = p.n_slots * kv_heads * nsplit;
+  const float scale = 0.08838834764831845f;  // 1 / sqrt(128)
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int slot = item / (kv_heads * nsplit);
+    const int rem = item - slot * (kv_heads * nsplit);
+    const int kvh = rem / nsplit, sp = rem - kvh * nsplit;
+    int pos0 = cp_pos0, w0 = 0;
+    if (talker) { pos0 = __ldcg(&p.st[slot].pos); w0 = __ldcg(&p.st[slot].win_start); }
+    const int w0r = w0 % cap;  // ring index of the window start; later keys wrap with one conditional subtract
+    float* kb = S.k + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
+    float* vb = S.v + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
+    // (a) per-head RMSNorm + rotate-half RoPE of q (G warps) and k (1 warp), v copy (1 warp) for each of the rps rows
+    if (cx.warp < rps * (G + 2)) {
+      const int rr = cx.warp / (G + 2), role = cx.warp - rr * (G + 2);
+      const int row = slot * rps + rr, pos = pos0 + rr;
+      const int ring = pos % cap;
+      const float* rowp = p.gqkv + (size_t)row * qkv_ld;
+      const int lane = cx.lane;
+      if (role <= G) {
+        const float* src = rowp + (size_t)(role < G ? (kvh * G + role) : (heads + kvh)) * 128;
+        const float a0 = __ldcg(src + lane), a1 = __ldcg(src + lane + 32), b0 = __ldcg(src + lane + 64), b1 = __ldcg(src + lane + 96);
+        const float ss = warp_sum(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+        const float inv = rsqrtf(ss * (1.0f / 128.0f) + S.eps);
+        const float* nw = role < G ? q_norm : k_norm;
+        const float x0 = a0 * inv * nw[lane], x1 = a1 * inv * nw[lane + 32], y0 = b0 * inv * nw[lane + 64], y1 = b1 * inv * nw[lane + 96];
+        float s0, c0, s1, c1;
+        sincosf((float)pos * S.inv_freq[lane], &s0, &c0);
+        sincosf((float)pos * S.inv_freq[lane + 32], &s1, &c1);
+        const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
+        float* dst = role < G ? q + (rr * G + role) * 128 : kcur + rr * 128;
+        dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+        if (role == G && sp == 0) {  // append k to the ring (Model/Qwen3Layers.swift:197-201)
+          float* kd = kb + (size_t)ring * 128;
+          kd[lane] = o0; kd[lane + 32] = o1; kd[lane + 64] = o2; kd[lane + 96] = o3;
+        }
+      } else {
+        const float4 v = ldcg4(rowp + (size_t)(heads + kv_heads + kvh) * 128 + lane * 4);
+        reinterpret_cast<float4*>(vcur + rr * 128)[lane] = v;
+        if (sp == 0) reinterpret_cast<float4*>(vb + (size_t)ring * 128)[lane] = v;
+      }
+    }
+    cbar();
+    for (int rr = 0; rr < rps; ++rr) {
+      const int row = slot * rps + rr, pos = pos0 + rr;
+      const int Sk = pos - w0 + 1;
+      const int per = (Sk + nsplit - 1) / nsplit;
+      const int j0 = sp * per, j1 = min(Sk, j0 + per);
+      const int n = max(0, j1 - j0);
+      if (n > kKeyTile) __trap();
+      // (b) scores: one warp per key, the row of 128 floats is one coalesced 512-byte read
+      for (int jb = cx.warp; jb < n; jb += 4 * kCWarps) {
+        float4 kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = jb + u * kCWarps;
+          kk[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (jj < n) {
+            const int j = j0 + jj, back = (Sk - 1) - j;  // keys of this launch's own rows come from shared memory
+            const int rj = w0r + j >= cap ? w0r + j - cap : w0r + j;
+            kk[u] = (back <= rr) ? reinterpret_cast<const float4*>(kcur + (rr - back) * 128)[cx.lane] : ldcg4(kb + (size_t)rj * 128 + cx.lane * 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int jj = jb + u * kCWarps;
+          if (jj < n) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const float4 qq = reinterpret_cast<const float4*>(q + (rr * G + g) * 128)[cx.lane];
+              const float d = warp_sum(kk[u].x * qq.x + kk[u].y * qq.y + kk[u].z * qq.z + kk[u].w * qq.w);
+              if (cx.lane == 0) sc[g * kKeyTile + jj] = d * scale;
+            }
+          }
+        }
+      }
+      cbar();
+      if (cx.warp < G) {  // softmax statistics of this split
+        const int g = cx.warp;
+        float mx = -INFINITY;
+        for (int jj = cx.lane; jj < n; jj += 32) mx = fmaxf(mx, sc[g * kKeyTile + jj]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int jj = cx.lane; jj < n; jj += 32) { const float e = expf(sc[g * kKeyTile + jj] - mx); sc[g * kKeyTile + jj] = e; sum += e; }
+        sum = warp_sum(sum);
+        if (cx.lane == 0) { stat[2 * g] = mx; stat[2 * g + 1] = sum; }
+      }
+      cbar();
+      if (cx.tid < kKeyGroups * 128) {  // (c) P.V: key groups x 128 dims
+        const int d = cx.tid & 127, kg = cx.tid >> 7;
+        float o[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) o[g] = 0.f;
+        for (int jb = kg; jb < n; jb += 4 * kKeyGroups) {
+          float vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int jj = jb + kKeyGroups * u;
+            vv[u] = 0.f;
+            if (jj < n) {
+              const int j = j0 + jj, back = (Sk - 1) - j;
+              const int rj = w0r + j >= cap ? w0r + j - cap : w0r + j;
+              vv[u] = (back <= rr) ? vcur[(rr - back) * 128 + d] : __ldcg(vb + (size_t)rj * 128 + d);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int jj = jb + kKeyGroups * u;
+            if (jj < n) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * kKeyTile + jj], vv[u], o[g]);
+            }
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) ored[(kg * G + g) * 128 + d] = o[g];
+      }
+      cbar();
+      float* part = p.gpart + (size_t)(row * nsplit + sp) * p.part_stride;
+      if (cx.tid < G * 128) {
+        const int g = cx.tid >> 7, d = cx.tid & 127;
+        float o = 0.f;
+#pragma unroll
+        for (int kg = 0; kg < kKeyGroups; ++kg) o += ored[(kg * G + g) * 128 + d];
+        part[(kvh * G + g) * 128 + d] = o;
+      }
+      if (cx.tid < 2 * G) part[heads * 128 + 2 * kvh * G + cx.tid] = stat[cx.tid];
+      cbar();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ bookkeeping (CTA 0)
+__device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, int group) {
+  if (blockIdx.x == 0) {
+    float* sl = reinterpret_cast<float*>(sm.xs);
+    BlockRed& br = *reinterpret_cast<BlockRed*>(sl + kMaxVocab);
+    SamplerParams sp;
+    sp.vocab = group == 0 ? p.V : p.Vc; sp.group = group; sp.codec_vocab = p.V; sp.eos_id = p.eos_id; sp.pad_id = p.pad_id;
+    sp.groups = 16; sp.set_words = p.set_words;
+    const float* logits = group == 0 ? p.logits0 : p.cplogits;
+    float* dump = group == 0 ? p.dump0 : p.dumpcp;
+    const int dump_stride = group == 0 ? p.V : 15 * p.Vc, dump_off = group == 0 ? 0 : (group - 1) * p.Vc;
+    for (int s = 0; s < p.n_slots; ++s) {
+      sample_slot<1, kCons>(s, logits, sp.vocab, p.st, sp, p.sets, p.cur_codes, p.forced, p.max_frames, dump, dump_stride, dump_off, 0, sl, br);
+      cbar();
+    }
+  }
+}
+
+// record the frame, add code0 to its set, advance the trailing-text cursor (Model/Qwen3Talker.swift:526-549)
+__device__ void finalize_bookkeeping(const MegaParams& p) {
+  for (int slot = 0; slot < p.n_slots; ++slot) {
+    SlotState& s = p.st[slot];
+    if (!s.frame_alive) continue;
+    const int* codes = p.cur_codes + slot * 16;
+    if (s.n_frames < p.max_frames) {
+      for (int g = 0; g < 16; ++g) p.frames[((size_t)slot * p.max_frames + s.n_frames) * 16 + g] = codes[g];
+      s.n_frames += 1;
+    }
+    const int c0 = codes[0];
+    if (c0 >= 0 && c0 < p.set_words * 32) {
+      unsigned* set0 = p.sets + (size_t)slot * 16 * p.set_words;
+      set0[c0 >> 5] |= 1u << (c0 & 31);
+    }
+    if (s.trailing_idx < s.total_text) s.trailing_idx += 1;
+  }
+}
+
+// pos++, step++, window trim every 15th step, max_tokens stop (Model/Qwen3Talker.swift:554-558; Qwen3Layers.swift:111-124)
+__device__ void step_advance(const MegaParams& p) {
+  for (int slot = 0; slot < p.n_slots; ++slot) {
+    SlotState& s = p.st[slot];
+    if (!s.frame_alive) continue;
+    s.pos += 1;
+    s.step += 1;
+    if (s.step % 15 == 0 && s.pos - s.win_start > p.window) s.win_start = s.pos - p.window;
+    if (s.step >= s.max_tokens) s.finished = 1;
+    s.frame_alive = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the frame loop
+// ONE copy of every phase body: the 16 units of a frame (15 code-predictor passes + the talker step) run through the same
+// loop over linear phases [mtp?] + layers x {qkv, o, gate|up, down} + head.
+enum LinKind { K_MTP = 0, K_QKV = 1, K_O = 2, K_GU = 3, K_DOWN = 4, K_HEAD = 5 };
+
+template <int FMT, int NS>
+__global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid_constant__ MegaParams p) {
+  constexpr int M = 2 * NS;
+  Sm sm;
+  sm.ring = smem;
+  sm.xs = reinterpret_cast<float4*>(smem + p.off_xs);
+  sm.xsum = reinterpret_cast<float*>(smem + p.off_xsum);
+  sm.xraw = reinterpret_cast<float*>(smem + p.off_xraw);
+  sm.red = reinterpret_cast<float*>(smem + p.off_red);
+  sm.full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  sm.empty = sm.full + p.n_ring;
+  sm.dsc = reinterpret_cast<MegaLinear*>(smem + p.off_dsc);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int kDscVec = (int)(sizeof(MegaLinear) / 16);
+  if (tid == 0) {
+    for (int s = 0; s < p.n_ring; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], kCWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[0])[tid] = __ldg(reinterpret_cast<const uint4*>(&p.lin[0]) + tid);
+  __syncthreads();
+  if (warp == kCWarps) {
+    if (lane == 0) producer_loop(p, sm.ring, sm.full, sm.empty);
+    return;
+  }
+  Ctx cx;
+  cx.slot = 0; cx.ph = 0; cx.bar_target = 0; cx.tid = tid; cx.lane = lane; cx.warp = warp;
+  cx.trace = nullptr; cx.wait_full = 0;
+  if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
+    cx.trace = p.trace + (size_t)(blockIdx.x == 0 ? 0 : 1) * p.trace_stride;
+  const int ns = p.n_slots;
+  int cur = 0;  // which of the two descriptor slots holds the current linear
+
+  for (int f = 0; f < p.n_frames; ++f) {
+    int li = 0;
+    for (int u = 0; u < 16; ++u) {   // units 0..14: code-predictor pass u (Model/Qwen3Talker.swift:501-523); 15: talker step
+      const bool talker = (u == 15);
+      const MegaStack& S = talker ? p.tk : p.cp;
+      if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
+      sample_phase(p, sm, u);        // code_u from the logits of the previous unit (code0: previous frame / prefill)
+      if (cx.trace) cx.trace[2] = clock64();
+      grid_sync(p, cx);
+      const int rps = (u == 0) ? 2 : 1;
+      const int m = ns * rps;
+      const int mtp = (!talker && p.has_mtp) ? 1 : 0;  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
+      const int layers = S.layers, hidden = S.hidden, inter = S.inter, heads = S.heads;
+      const int nj = mtp + 4 * layers + 1;
+      const int first_kind = talker ? IN_TALKER : (u == 0 ? IN_CP0 : IN_CPG);
+      const int qkv_ld = (heads + 2 * S.kv_heads) * 128;
+      const float eps = S.eps;
+      for (int j = 0; j < nj; ++j) {
+        const MegaLinear& L = sm.dsc[cur];
+        ++li;
+        // next phase's descriptor: loaded now, parked in the other slot before the barrier (never on the critical path)
+        uint4 nd = make_uint4(0u, 0u, 0u, 0u);
+        const int lnext = li < p.n_lin ? li : 0;
+        if (tid < kDscVec) nd = __ldg(reinterpret_cast<const uint4*>(&p.lin[lnext]) + tid);
+        int kind, l = 0;
+        if (j < mtp) kind = K_MTP;
+        else if (j == nj - 1) kind = K_HEAD;
+        else { l = (j - mtp) >> 2; kind = K_QKV + ((j - mtp) & 3); }
+        InArgs in{};
+        in.pass = u; in.ld = hidden; in.nsplit = S.nsplit; in.heads = heads;
+        int rows = m, K = hidden, epi = E_STORE, ld_out = hidden;
+        float* out = p.gx;
+        bool keep_raw = false;
+        switch (kind) {
+          case K_MTP: in.kind = first_kind; K = p.H; ld_out = p.Hcp; break;
+          case K_QKV: in.kind = (l == 0 && !mtp) ? first_kind : IN_GX; keep_raw = true; out = p.gqkv; ld_out = qkv_ld; break;
+          case K_O: in.kind = IN_ATTN; K = heads * 128; epi = E_ADD_RAW; break;
+          case K_GU: in.kind = IN_GX; keep_raw = true; epi = E_SWIGLU; out = p.gact; ld_out = inter; break;
+          case K_DOWN: in.kind = IN_ACT; in.ld = inter; K = inter; epi = E_ADD_RAW; break;
+          default:  // K_HEAD: final norm + lm_head[u] on the last position of each slot / codec_head (Qwen3CodePredictor.swift:207-212)
+            in.kind = talker ? IN_GX : IN_GX_LAST; in.pass = rps; rows = ns; keep_raw = talker;
+            out = talker ? p.logits0 : p.cplogits; ld_out = talker ? p.V : p.Vc;
+            break;
+        }
+        const float* norm_w = L.norm_w;
+        if (cx.trace) { cx.trace[0] = clock64(); cx.wait_full = 0; }
+        stage_rows<FMT>(p, sm, cx, in, rows, K, norm_w, keep_raw);
+        if (cx.trace) cx.trace[1] = clock64();
+        if (kind == K_HEAD && talker && blockIdx.x == 0) {  // h_last = final norm of the talker step (next frame's pass-0 input)
+          for (int s = 0; s < ns; ++s) {
+            float ss = 0.f;
+            for (int w = 0; w < kCWarps; ++w) ss += sm.red[s * 16 + w];
+            const float inv = rsqrtf(ss / (float)p.H + eps);
+            for (int i = tid; i < p.H; i += kCons) p.hlast[(size_t)s * p.H + i] = sm.xraw[s * p.raw_ld + i] * inv * norm_w[i];
+          }
+        }
+        if (rps == 2 && kind != K_HEAD) gemv_rows<FMT, M>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out);
+        else gemv_rows<FMT, NS>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out);
+        if (cx.trace) { cx.trace[2] = clock64(); cx.trace[6] = cx.wait_full; cx.trace[7] = kind; }
+        if (kind == K_HEAD && talker && blockIdx.x == 0 && tid == 0) step_advance(p);
+        const float* q_norm = L.q_norm;
+        const float* k_norm = L.k_norm;
+        if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[cur ^ 1])[tid] = nd;
+        cur ^= 1;
+        grid_sync(p, cx);
+        if (kind == K_QKV) {
+          if (talker && l == 0 && blockIdx.x == 0 && tid == 0) finalize_bookkeeping(p);
+          if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
+          const int G = heads / S.kv_heads;
+          const int cp_pos0 = u == 0 ? 0 : u + 1;
+          if (G == 2) attn_phase<2>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+          else if (G == 1) attn_phase<1>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+          else attn_phase<4>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+          if (cx.trace) cx.trace[2] = clock64();
+          grid_sync(p, cx);
+        }
+      }
+    }
+  }
+}
+
+template <int FMT>
+void launch_fmt(const LaunchCtx& c, const MegaPlan& plan, const MegaParams& p) {
+  void* args[] = {const_cast<MegaParams*>(&p)};
+  Q3_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&frame_megakernel<FMT, kMegaMaxSlots>), dim3(plan.grid), dim3(kMegaThreads), args,
+                                      plan.smem, c.stream));
+}
+
+template <int FMT>
+void init_fmt() {
+  Q3_CUDA(cudaFuncSetAttribute(frame_megakernel<FMT, kMegaMaxSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+}
+
+}  // namespace
+
+void init_mega_kernels() {
+  init_fmt<W_Q4>();
+  init_fmt<W_Q8>();
+  init_fmt<W_BF16>();
+  init_fmt<W_F16>();
+  init_fmt<W_F32>();
+}
+
+int mega_max_blocks_per_sm(int fmt, size_t smem_bytes) {
+  int n = 0;
+  cudaError_t e = cudaErrorInvalidValue;
+  switch (fmt) {
+    case W_Q4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q4, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    case W_Q8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q8, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    case W_BF16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_BF16, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    case W_F16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F16, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    case W_F32: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F32, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    default: break;
+  }
+  return e == cudaSuccess ? n : 0;
+}
+
+void launch_frame_megakernel(const LaunchCtx& c, const MegaPlan& plan, int n_slots, int n_frames, float* dump0, float* dumpcp) {
+  Q3_CHECK(plan.ok && n_slots >= 1 && n_slots <= kMegaMaxSlots && n_frames >= 1, Q3TTS_ERR_INVALID_ARG, "frame megakernel: bad launch");
+  MegaParams p = plan.p;
+  p.n_slots = n_slots; p.n_frames = n_frames; p.dump0 = dump0; p.dumpcp = dumpcp;
+  Q3_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), c.stream));
+  switch (plan.fmt) {
+    case W_Q4: launch_fmt<W_Q4>(c, plan, p); break;
+    case W_Q8: launch_fmt<W_Q8>(c, plan, p); break;
+    case W_BF16: launch_fmt<W_BF16>(c, plan, p); break;
+    case W_F16: launch_fmt<W_F16>(c, plan, p); break;
+    case W_F32: launch_fmt<W_F32>(c, plan, p); break;
+    default: fail(Q3TTS_ERR_BAD_CONFIG, "frame megakernel: unknown weight format %d", plan.fmt);
+  }
+  c.tick();
+}
+
+}  // namespace q3

@@ -1,0 +1,92 @@
+// Persistent frame kernel ("megakernel") for the batch-1..NS decode loop: ONE cooperative launch runs n frames of
+// Model/Qwen3Talker.swift:464-562 — code0 sample, 15 code-predictor passes, frame finalize, talker step — with every
+// Qwen3DecoderLayer phase separated by a grid barrier instead of a kernel boundary.  Weights are streamed by a producer
+// warp (1-D TMA bulk copies into a shared-memory ring, several phases ahead of the math), so the dependency chain only
+// ever waits on L2-resident activations.
+#pragma once
+#include "kernels.h"
+
+namespace q3 {
+
+struct MegaLinear {       // one QuantizedLayerFactory.linear leaf in execution order
+  const void* w;          // packed (MLX affine) or dense rows
+  const void* scales;     // quantised only: [out][in/group]
+  const void* biases;
+  const float* bias;      // optional Linear bias, fp32 [out]
+  int out_eff;            // rows of one sub-matrix (SwiGLU: out / 2)
+  int nsub;               // 1, or 2 for [gate ; up]
+  int in;                 // K
+  int row_bytes;          // bytes of one weight row
+  int srow_bytes;         // bytes of one row of scales (== biases); 0 for dense formats
+  int unit;               // row granularity of a CTA's slice (keeps every bulk copy 16-byte aligned)
+  int sdt;                // dtype of scales / biases
+  int group;
+  int ubase, urem;        // slice of CTA c: ubase + (c < urem) units starting at unit c*ubase + min(c, urem)
+  int rch;                // rows per ring chunk
+  int group_shift;        // log2(group)
+  const float* norm_w;    // RMSNorm weight fused into this linear's prologue (qkv, gate|up, heads), or null
+  const float* q_norm;    // qkv entries: per-head norms of the attention phase that follows
+  const float* k_norm;
+  int pad_[2];            // sizeof == 112: the kernel moves descriptors as 16-byte vectors
+};
+static_assert(sizeof(MegaLinear) % 16 == 0, "MegaLinear must be a whole number of 16-byte vectors");
+
+struct MegaStack {
+  int hidden, layers, heads, kv_heads, inter;
+  float eps;
+  const float* final_norm;
+  const float* inv_freq;
+  float* k;
+  float* v;
+  size_t slot_stride, layer_stride;
+  int capacity;
+  int nsplit;               // key splits per (slot, kv head) attention item
+};
+
+struct MegaParams {
+  const MegaLinear* lin;    // device array, one frame's linears in execution order
+  int n_lin;
+  MegaStack cp, tk;
+  int has_mtp, H, Hcp, V, Vc;
+  Embedding codec;
+  const Embedding* cp_emb;  // device array [15]
+  SlotState* st;
+  int n_slots;
+  int* cur_codes;
+  int* frames;
+  const int* forced;
+  int max_frames;
+  unsigned* sets;
+  int set_words;
+  const float* trailing;
+  int max_trailing;
+  const float* tts_pad;
+  float *hlast, *logits0, *cplogits, *dump0, *dumpcp;
+  float *gx, *gqkv, *gpart, *gact;
+  int part_stride;          // floats per (row, split) partial: heads*128 + 2*heads, padded to 4
+  unsigned* barrier;
+  int n_frames, window, eos_id, pad_id;
+  // shared-memory plan (bytes from the 1024-aligned base)
+  int slot_bytes, n_ring;
+  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc;
+  int raw_ld;               // floats per row of the raw residual copy
+  long long* trace;         // diagnostics: [2 CTAs][trace_stride] cycle stamps, 8 per phase (null = off)
+  int trace_stride;
+};
+
+constexpr int kMegaMaxSlots = 1;   // NS instantiated: rows per phase <= 2 * NS
+
+// false when this checkpoint / option set is outside the kernel's envelope (the CUDA-graph path is used instead)
+struct MegaPlan {
+  bool ok = false;
+  MegaParams p{};
+  int fmt = 0;       // WFmt
+  int G_cp = 0, G_tk = 0;
+  size_t smem = 0;
+  int grid = 0;
+};
+
+void init_mega_kernels();
+void launch_frame_megakernel(const LaunchCtx& c, const MegaPlan& plan, int n_slots, int n_frames, float* dump0, float* dumpcp);
+
+}  // namespace q3

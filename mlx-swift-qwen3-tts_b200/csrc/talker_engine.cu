@@ -5,11 +5,13 @@
 #include <cmath>
 
 #include "engine.h"
+#include "frame_kernel.h"
 #include "gemm_tc.h"
 
 namespace q3 {
 
 void init_talker_kernels();  // talker_kernels.cu: opt-in shared-memory attributes, once per device
+int mega_max_blocks_per_sm(int fmt, size_t smem);  // frame_kernel.cu
 
 TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
                            LaunchCounter* counter)
@@ -127,6 +129,144 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   launch_linear(c, w_.fc1, d_tpe_, cfg_.text_hidden_size, 3, d_tph_, cfg_.text_hidden_size, nullptr, 0.f, EPI_SILU);
   launch_linear(c, w_.fc2, d_tph_, cfg_.text_hidden_size, 3, d_tts_, H, nullptr, 0.f, EPI_STORE);
   Q3_CUDA(cudaStreamSynchronize(stream_));
+  build_mega_plan();
+}
+
+// Plan of the persistent frame kernel (frame_kernel.cu): the frame's linears in execution order, the shared-memory
+// layout, and the envelope checks.  Anything outside the envelope keeps the CUDA-graph path (mega_.ok stays false).
+void TalkerEngine::build_mega_plan() {
+  mega_ = MegaPlan{};
+  if (const char* e = getenv("Q3TTS_MEGAKERNEL"))
+    if (atoi(e) == 0) return;
+  if (!opt_.use_cuda_graph) return;
+  const StackWeights &T = w_.talker, &P = w_.cp;
+  std::vector<const Linear*> order;
+  std::vector<int> swiglu;
+  struct Norms { const float *norm_w, *q_norm, *k_norm; };
+  std::vector<Norms> norms;
+  auto push = [&](const Linear& L, bool sw, const float* nw = nullptr, const float* qn = nullptr, const float* kn = nullptr) {
+    order.push_back(&L); swiglu.push_back(sw ? 1 : 0); norms.push_back({nw, qn, kn});
+  };
+  auto push_layer = [&](const LayerWeights& l) {
+    push(l.qkv, false, l.in_norm, l.q_norm, l.k_norm); push(l.o, false); push(l.gate_up, true, l.post_norm); push(l.down, false);
+  };
+  for (int g = 0; g < 15; ++g) {
+    if (w_.has_mtp) push(w_.small_to_mtp, false);
+    for (int l = 0; l < P.layers; ++l) push_layer(P.layer[l]);
+    push(w_.lm_head[g], false, P.final_norm);
+  }
+  for (int l = 0; l < T.layers; ++l) push_layer(T.layer[l]);
+  push(w_.codec_head, false, T.final_norm);
+  // one weight format for the whole frame
+  const Linear& L0 = *order[0];
+  int fmt = -1;
+  if (L0.bits == 4) fmt = 0; else if (L0.bits == 8) fmt = 1;
+  else if (L0.bits == 0) fmt = L0.sdt == Q3TTS_BF16 ? 2 : (L0.sdt == Q3TTS_F16 ? 3 : 4);
+  if (fmt < 0) return;
+  const int vpl = fmt == 0 ? 32 : (fmt == 1 ? 16 : (fmt == 4 ? 4 : 8));
+  const int kc = 32 * vpl;
+  std::vector<MegaLinear> lin;
+  int kmax = 0, need_slot = 0;
+  for (size_t i = 0; i < order.size(); ++i) {
+    const Linear& L = *order[i];
+    if (L.bits != L0.bits || (L.bits == 0 && L.sdt != L0.sdt)) return;
+    if (L.bits && (L.group % vpl != 0 || L.in % L.group != 0)) return;
+    if (L.in % vpl != 0 || L.in % 4 != 0) return;
+    MegaLinear m{};
+    m.w = L.bits ? (const void*)L.qw : L.w; m.scales = L.scales; m.biases = L.biases; m.bias = L.bias;
+    m.nsub = swiglu[i] ? 2 : 1;
+    m.out_eff = L.out / m.nsub;
+    m.in = L.in;
+    m.row_bytes = L.bits ? L.in * L.bits / 8 : L.in * (int)dtype_size(L.sdt);
+    m.srow_bytes = L.bits ? (L.in / L.group) * (int)dtype_size(L.sdt) : 0;
+    m.sdt = L.sdt; m.group = L.bits ? L.group : 1;
+    if (m.group & (m.group - 1)) return;  // power-of-two groups only
+    m.group_shift = 0;
+    while ((1 << m.group_shift) < m.group) ++m.group_shift;
+    int u = 1;
+    while (u <= 16 && ((u * m.row_bytes) % 16 != 0 || (u * m.srow_bytes) % 16 != 0)) u <<= 1;
+    if (u > 16 || m.out_eff % u != 0) return;
+    m.unit = u;
+    m.norm_w = norms[i].norm_w; m.q_norm = norms[i].q_norm; m.k_norm = norms[i].k_norm;
+    need_slot = std::max(need_slot, u * m.nsub * (m.row_bytes + 2 * m.srow_bytes));
+    kmax = std::max(kmax, L.in);
+    lin.push_back(m);
+  }
+  const int G_tk = T.heads / T.kv_heads, G_cp = P.heads / P.kv_heads;
+  auto g_ok = [](int g) { return g == 1 || g == 2 || g == 4; };
+  if (!g_ok(G_tk) || !g_ok(G_cp) || T.head_dim != 128 || P.head_dim != 128) return;
+  if (T.heads % T.kv_heads || P.heads % P.kv_heads) return;
+  if (cfg_.vocab_size > 4096 || cfg_.cp.vocab_size > 4096) return;
+  if (T.hidden % 4 || P.hidden % 4 || T.inter % 4 || P.inter % 4) return;
+  constexpr int NS = kMegaMaxSlots, MT = 2 * NS;
+  int slot_bytes = 32 * 1024;
+  while (slot_bytes < need_slot) slot_bytes += 8 * 1024;
+  const int nchunk = (kmax + kc - 1) / kc;
+  const int hmax = std::max(T.hidden, P.hidden);
+  auto up = [](int v, int a) { return (v + a - 1) / a * a; };
+  const int xs_bytes = up(std::max(MT * nchunk * kc * 4, 24 * 1024), 128);
+  const int xsum_bytes = up(MT * nchunk * 32 * 4, 128);
+  const int xraw_bytes = up(MT * hmax * 4, 128);
+  const int red_bytes = up(MT * 16 * 4, 128);
+  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 256 + 128;
+  const int budget = 226 * 1024;
+  int n_ring = std::min(8, (budget - fixed) / slot_bytes);
+  if (n_ring < 2) return;
+  MegaParams& p = mega_.p;
+  p.slot_bytes = slot_bytes; p.n_ring = n_ring;
+  p.off_xs = n_ring * slot_bytes;
+  p.off_xsum = p.off_xs + xs_bytes;
+  p.off_xraw = p.off_xsum + xsum_bytes;
+  p.off_red = p.off_xraw + xraw_bytes;
+  p.off_bar = p.off_red + red_bytes;
+  p.off_dsc = p.off_bar + 256;
+  p.raw_ld = hmax;
+  mega_.smem = (size_t)p.off_dsc + 256 + 128;
+  mega_.fmt = fmt; mega_.G_cp = G_cp; mega_.G_tk = G_tk;
+  int dev = 0, sms = 0, coop = 0;
+  Q3_CUDA(cudaGetDevice(&dev));
+  Q3_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  Q3_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+  if (!coop || sms < 1) return;
+  init_mega_kernels();
+  if (mega_max_blocks_per_sm(fmt, mega_.smem) < 1) return;
+  mega_.grid = sms;
+  for (MegaLinear& m : lin) {
+    const int U = m.out_eff / m.unit;
+    m.ubase = U / mega_.grid; m.urem = U % mega_.grid;
+    m.rch = (slot_bytes / (m.nsub * (m.row_bytes + 2 * m.srow_bytes))) / m.unit * m.unit;
+  }
+  // device tables
+  MegaLinear* d_lin = arena_.alloc_n<MegaLinear>(lin.size());
+  Q3_CUDA(cudaMemcpy(d_lin, lin.data(), sizeof(MegaLinear) * lin.size(), cudaMemcpyHostToDevice));
+  auto stack_of = [&](const StackWeights& S, const float* inv_freq, float* k, float* v, size_t slot_stride, size_t layer_stride, int cap, int nsplit) {
+    MegaStack s{};
+    s.hidden = S.hidden; s.layers = S.layers; s.heads = S.heads; s.kv_heads = S.kv_heads; s.inter = S.inter; s.eps = S.eps;
+    s.final_norm = S.final_norm; s.inv_freq = inv_freq; s.k = k; s.v = v;
+    s.slot_stride = slot_stride; s.layer_stride = layer_stride; s.capacity = cap; s.nsplit = nsplit;
+    return s;
+  };
+  const int nsplit_tk = std::max(4, (opt_.kv_capacity + 127) / 128);
+  p.lin = d_lin; p.n_lin = (int)lin.size();
+  p.cp = stack_of(P, d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, 1);
+  p.tk = stack_of(T, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, opt_.kv_capacity, nsplit_tk);
+  p.has_mtp = w_.has_mtp ? 1 : 0; p.H = cfg_.hidden_size; p.Hcp = cfg_.cp.hidden_size; p.V = cfg_.vocab_size; p.Vc = cfg_.cp.vocab_size;
+  p.codec = w_.codec_embedding; p.cp_emb = d_cp_emb_;
+  p.st = d_state_; p.cur_codes = d_cur_codes_; p.frames = d_frames_; p.forced = d_forced_; p.max_frames = opt_.max_frames;
+  p.sets = d_sets_; p.set_words = set_words_;
+  p.trailing = d_trailing_; p.max_trailing = opt_.max_trailing; p.tts_pad = d_tts_ + (size_t)2 * cfg_.hidden_size;
+  p.hlast = d_hlast_; p.logits0 = d_logits0_; p.cplogits = d_cplogits_;
+  p.gx = d_x_; p.gqkv = d_qkv_; p.gact = d_act_;
+  p.part_stride = up(std::max(T.heads, P.heads) * 130, 4);
+  p.gpart = arena_.alloc_n<float>((size_t)MT * nsplit_tk * p.part_stride);
+  p.barrier = arena_.alloc_n<unsigned>(64);
+  p.window = 192;  // maxKVCacheWindow (Model/Qwen3Layers.swift:108)
+  p.eos_id = cfg_.codec_eos_token_id; p.pad_id = cfg_.codec_pad_id;
+  if (getenv("Q3TTS_MEGA_TRACE")) {  // diagnostics: per-phase cycle stamps of one launch (frame_kernel.cu), dumped by run_frames
+    p.trace_stride = 8 * 1024 * 8;
+    p.trace = arena_.alloc_n<long long>((size_t)2 * p.trace_stride);
+  }
+  mega_.ok = true;
 }
 
 TalkerEngine::~TalkerEngine() {
@@ -492,6 +632,18 @@ void TalkerEngine::run_frames(int n_slots, int n) {
   if (n <= 0 || n_slots <= 0) return;
   if (!opt_.use_cuda_graph) {
     for (int i = 0; i < n; ++i) issue_frame(n_slots);
+    return;
+  }
+  if (mega_.ok && n_slots <= kMegaMaxSlots && !use_tc(n_slots)) {  // batch-1 decode: one persistent cooperative launch for all n frames
+    if (mega_.p.trace) Q3_CUDA(cudaMemsetAsync(mega_.p.trace, 0, sizeof(long long) * 2 * mega_.p.trace_stride, stream_));
+    launch_frame_megakernel(ctx(), mega_, n_slots, n, dump_enabled_ ? d_dump0_ : nullptr, dump_enabled_ ? d_dumpcp_ : nullptr);
+    ++mega_launches;
+    if (mega_.p.trace) {
+      std::vector<long long> t((size_t)2 * mega_.p.trace_stride);
+      Q3_CUDA(cudaMemcpyAsync(t.data(), mega_.p.trace, sizeof(long long) * t.size(), cudaMemcpyDeviceToHost, stream_));
+      Q3_CUDA(cudaStreamSynchronize(stream_));
+      if (FILE* f = fopen(getenv("Q3TTS_MEGA_TRACE"), "wb")) { fwrite(t.data(), sizeof(long long), t.size(), f); fclose(f); }
+    }
     return;
   }
   const int key = n_slots * 2 + (dump_enabled_ ? 1 : 0);

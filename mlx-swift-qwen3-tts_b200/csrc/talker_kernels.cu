@@ -9,32 +9,10 @@
 #include <cuda_fp16.h>
 
 #include "kernels.h"
+#include "device_utils.cuh"
+#include "sampler.cuh"
 
 namespace q3 {
-
-// ------------------------------------------------------------------------------------------------ helpers
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ float load_as_f32(const void* p, size_t i, int dt) {
-  if (dt == Q3TTS_F32) return reinterpret_cast<const float*>(p)[i];
-  if (dt == Q3TTS_F16) return __half2float(reinterpret_cast<const __half*>(p)[i]);
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);
-}
-__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {  // weights are read once: keep them out of L1
-  uint4 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-  return r;
-}
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ dequantize
 // deq32 = fp32(scale) * q (rounded) + fp32(bias) (rounded) — __fmul_rn/__fadd_rn forbid FMA contraction so the
@@ -72,70 +50,6 @@ void launch_dequantize(const LaunchCtx& c, const uint32_t* qw, const void* scale
 }
 
 // ------------------------------------------------------------------------------------------------ GEMV / small-M linear
-enum WFmt { W_Q4 = 0, W_Q8 = 1, W_BF16 = 2, W_F16 = 3, W_F32 = 4 };
-template <int FMT> struct FmtTraits;
-template <> struct FmtTraits<W_Q4> { static constexpr int VPL = 32; };   // values per lane per 16-byte load
-template <> struct FmtTraits<W_Q8> { static constexpr int VPL = 16; };
-template <> struct FmtTraits<W_BF16> { static constexpr int VPL = 8; };
-template <> struct FmtTraits<W_F16> { static constexpr int VPL = 8; };
-template <> struct FmtTraits<W_F32> { static constexpr int VPL = 4; };
-
-// Integer code -> float without I2F (quarter-rate pipe): OR the code into the mantissa of 2^23, subtract 2^23.
-__device__ __forceinline__ float code_to_f32(uint32_t code) { return __uint_as_float(0x4B000000u | code) - 8388608.0f; }
-
-// Expand this lane's 16-byte weight load into VPL floats (integer codes for the packed formats; the group scale / bias are
-// applied to the finished dot product).  Done ONCE per weight load and reused for every activation row of the M tile.
-template <int FMT>
-__device__ __forceinline__ void lane_expand(const uint4& w, float (&o)[FmtTraits<FMT>::VPL]) {
-  const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-  if constexpr (FMT == W_Q4) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-      for (int n = 0; n < 8; ++n) o[i * 8 + n] = code_to_f32((ww[i] >> (4 * n)) & 0xF);
-    }
-  } else if constexpr (FMT == W_Q8) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      // __byte_perm places byte k of the word into byte 0 of 0x4B0000xx in one PRMT
-      o[i * 4 + 0] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7440)) - 8388608.0f;
-      o[i * 4 + 1] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7441)) - 8388608.0f;
-      o[i * 4 + 2] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7442)) - 8388608.0f;
-      o[i * 4 + 3] = __uint_as_float(__byte_perm(ww[i], 0x4B000000u, 0x7443)) - 8388608.0f;
-    }
-  } else if constexpr (FMT == W_BF16) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      o[2 * i] = __uint_as_float(ww[i] << 16);
-      o[2 * i + 1] = __uint_as_float(ww[i] & 0xFFFF0000u);
-    }
-  } else if constexpr (FMT == W_F16) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&ww[i]));
-      o[2 * i] = a.x;
-      o[2 * i + 1] = a.y;
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = __uint_as_float(ww[i]);
-  }
-}
-// dot of the expanded weights with this lane's VPL activations (VPL/4 float4 from lane-major smem, stride 32 float4)
-template <int FMT>
-__device__ __forceinline__ float lane_dot(const float (&w)[FmtTraits<FMT>::VPL], const float4* __restrict__ xs) {
-  float acc = 0.f;
-#pragma unroll
-  for (int j = 0; j < FmtTraits<FMT>::VPL / 4; ++j) {
-    const float4 x = xs[j * 32];
-    acc = fmaf(w[4 * j], x.x, acc);
-    acc = fmaf(w[4 * j + 1], x.y, acc);
-    acc = fmaf(w[4 * j + 2], x.z, acc);
-    acc = fmaf(w[4 * j + 3], x.w, acc);
-  }
-  return acc;
-}
-
 struct LinearKArgs {
   const void* w;        // packed or dense weights, row-major
   const void* scales;   // quantised only
@@ -720,145 +634,7 @@ void launch_assemble_rows(const LaunchCtx& c, const float* tp_rows, int H, const
 }
 
 // ------------------------------------------------------------------------------------------------ sampler
-// Counter-based uniform in (0,1): splitmix64 finaliser over (seed, counter, index), 23-bit mantissa (+0.5 so neither
-// 0 nor 1 occurs).  Same integer arithmetic as oracle/talker.py:counter_uniform.
-__device__ __forceinline__ float counter_uniform(unsigned long long seed, unsigned long long counter, unsigned idx) {
-  unsigned long long x = seed * 0x9E3779B97F4A7C15ull + counter * 0xD1B54A32D192ED03ull +
-                         (unsigned long long)idx * 0x8CB92BA72F3D8DD7ull + 0x2545F4914F6CDD1Dull;
-  x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
-  x ^= x >> 27; x *= 0x94D049BB133111EBull;
-  x ^= x >> 31;
-  return (__uint2float_rn((unsigned)(x >> 41)) + 0.5f) * (1.0f / 8388608.0f);
-}
-__device__ __forceinline__ unsigned ordered_key(float f) {  // monotone float -> uint map
-  const unsigned u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-
-constexpr int kSampleThreads = 512;
-constexpr int kMaxVocab = 4096;
-
-struct BlockRed {
-  float fv[16];
-  int iv[16];
-  float bcast_f;
-  int bcast_i;
-};
-
-// argmax with first-index tie break over sl[0..V)
-__device__ int block_argmax(const float* sl, int V, BlockRed& br) {
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
-    const float v = sl[i];
-    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) { br.fv[threadIdx.x >> 5] = bv; br.iv[threadIdx.x >> 5] = bi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float v = br.fv[0]; int idx = br.iv[0];
-    for (int w = 1; w < kSampleThreads / 32; ++w)
-      if (br.fv[w] > v || (br.fv[w] == v && br.iv[w] < idx)) { v = br.fv[w]; idx = br.iv[w]; }
-    if (idx == 0x7fffffff) idx = 0;
-    br.bcast_i = idx;
-  }
-  __syncthreads();
-  return br.bcast_i;
-}
-__device__ float block_sum(float v, BlockRed& br) {
-  v = warp_sum(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) br.fv[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int w = 0; w < kSampleThreads / 32; ++w) s += br.fv[w];
-    br.bcast_f = s;
-  }
-  __syncthreads();
-  return br.bcast_f;
-}
-__device__ float block_max(float v, BlockRed& br) {
-  v = warp_max(v);
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) br.fv[threadIdx.x >> 5] = v;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = -INFINITY;
-    for (int w = 0; w < kSampleThreads / 32; ++w) s = fmaxf(s, br.fv[w]);
-    br.bcast_f = s;
-  }
-  __syncthreads();
-  return br.bcast_f;
-}
-
-// Qwen3Talker.sampleToken (Model/Qwen3Talker.swift:274-322) over sl[0..V) held in shared memory (already carrying
-// the EOS/pad suppression of :470-475 where it applies).  Returns the id to every thread.
-__device__ int sample_block(float* sl, int V, int codec_vocab, float temperature, int top_k, float top_p, float rep_penalty,
-                            const unsigned* set_bitmap, unsigned long long seed, unsigned long long counter, BlockRed& br) {
-  if (set_bitmap != nullptr && rep_penalty != 1.0f) {  // set-based, division regardless of sign (:288-299)
-    for (int i = threadIdx.x; i < V; i += kSampleThreads)
-      if (set_bitmap[i >> 5] & (1u << (i & 31))) sl[i] = sl[i] / rep_penalty;
-  }
-  __syncthreads();
-  if (!(temperature > 0.f)) return block_argmax(sl, V, br);  // greedy: before the valid-token mask (:301-305)
-  for (int i = threadIdx.x; i < V; i += kSampleThreads) sl[i] = sl[i] / temperature;
-  __syncthreads();
-  if (top_k > 0 && top_k < V) {  // threshold = k-th largest; ties at the threshold survive (:307-314)
-    unsigned t = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const unsigned cand = t | (1u << bit);
-      float cnt = 0.f;
-      for (int i = threadIdx.x; i < V; i += kSampleThreads) cnt += (ordered_key(sl[i]) >= cand) ? 1.f : 0.f;
-      if (block_sum(cnt, br) >= (float)top_k) t = cand;
-    }
-    for (int i = threadIdx.x; i < V; i += kSampleThreads)
-      if (ordered_key(sl[i]) < t) sl[i] = -INFINITY;
-    __syncthreads();
-  }
-  if (V == codec_vocab) {  // valid ids: < 2048, 2148 (pad), 2150 (eos)  (:19-33, 316-319)
-    for (int i = threadIdx.x; i < V; i += kSampleThreads)
-      if (!(i < 2048 || i == 2148 || i == 2150)) sl[i] = -INFINITY;
-    __syncthreads();
-  }
-  if (top_p < 1.0f) {  // extension (no top-p in the reference): keep i iff mass of strictly more probable ids < top_p
-    float mx = -INFINITY;
-    for (int i = threadIdx.x; i < V; i += kSampleThreads) mx = fmaxf(mx, sl[i]);
-    mx = block_max(mx, br);
-    float z = 0.f;
-    for (int i = threadIdx.x; i < V; i += kSampleThreads) z += expf(sl[i] - mx);
-    z = block_sum(z, br);
-    unsigned t = 0;  // largest key with mass(key_j > t) >= top_p
-    for (int bit = 31; bit >= 0; --bit) {
-      const unsigned cand = t | (1u << bit);
-      float mass = 0.f;
-      for (int i = threadIdx.x; i < V; i += kSampleThreads)
-        if (ordered_key(sl[i]) > cand) mass += expf(sl[i] - mx);
-      if (block_sum(mass, br) / z >= top_p) t = cand;
-    }
-    for (int i = threadIdx.x; i < V; i += kSampleThreads)
-      if (ordered_key(sl[i]) <= t) sl[i] = -INFINITY;
-    __syncthreads();
-  }
-  // MLXRandom.categorical == Gumbel-max (:321)
-  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
-    const float l = sl[i];
-    if (l > -INFINITY) {
-      const float u = counter_uniform(seed, counter, (unsigned)i);
-      sl[i] = l + (-logf(-logf(u)));
-    }
-  }
-  __syncthreads();
-  return block_argmax(sl, V, br);
-}
-
+// (device code in sampler.cuh, shared with the frame megakernel)
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const float* __restrict__ logits, int ld, SlotState* __restrict__ st,
                                                                SamplerParams p, unsigned* __restrict__ token_sets,
                                                                int* __restrict__ cur_codes, const int* __restrict__ forced,
@@ -866,53 +642,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const float* __r
                                                                int dump_offset, int dump_slot) {
   __shared__ float sl[kMaxVocab];
   __shared__ BlockRed br;
-  const int slot = blockIdx.x;
-  SlotState& s = st[slot];
-  const int V = p.vocab;
-  if (p.group == 0) {
-    const bool alive = s.active && !s.finished && s.step < s.max_tokens;
-    if (!alive) {
-      if (threadIdx.x == 0) { s.frame_alive = 0; if (s.active && s.step >= s.max_tokens) s.finished = 1; }
-      return;
-    }
-  } else if (!s.frame_alive) {
-    return;
-  }
-  const float* lg = logits + (size_t)slot * ld;
-  const int step = s.step;
-  if (dump != nullptr && slot == dump_slot && step < s.logits_cap) {
-    float* d = dump + (size_t)step * dump_stride_frame + dump_offset;
-    for (int i = threadIdx.x; i < V; i += kSampleThreads) d[i] = lg[i];
-  }
-  const bool suppress = (p.group == 0) && (s.trailing_idx < s.total_text);  // EOS/pad masked while text remains (:470-475)
-  for (int i = threadIdx.x; i < V; i += kSampleThreads) {
-    float v = lg[i];
-    if (suppress && (i == p.eos_id || i == p.pad_id)) v = -INFINITY;
-    sl[i] = v;
-  }
-  __syncthreads();
-  unsigned* set = token_sets + ((size_t)slot * p.groups + p.group) * p.set_words;
-  const bool use_set = (p.group == 0) || !s.stream_variant;  // generateStream: no penalty on CP groups (:821)
-  int tok = sample_block(sl, V, p.codec_vocab, s.temperature, s.top_k, s.top_p, s.rep_penalty, use_set ? set : nullptr, s.seed,
-                         (unsigned long long)step * p.groups + p.group, br);
-  if (threadIdx.x != 0) return;
-  const bool is_forced = s.n_forced > 0 && forced != nullptr;
-  if (is_forced) tok = forced[((size_t)slot * max_frames + step) * p.groups + p.group];
-  if (p.group == 0) {
-    if (!is_forced) {  // stop rules (:485-494)
-      if (tok == p.eos_id) { s.finished = 1; s.frame_alive = 0; return; }
-      if (tok == p.pad_id) {
-        s.consecutive_pad += 1;
-        if (s.consecutive_pad > 6) { s.finished = 1; s.frame_alive = 0; return; }
-      } else {
-        s.consecutive_pad = 0;
-      }
-    }
-    s.frame_alive = 1;
-  } else if (tok >= 0 && tok < V) {
-    set[tok >> 5] |= 1u << (tok & 31);  // generatedCodePredictorSets[g-1].insert (:522)
-  }
-  cur_codes[slot * p.groups + p.group] = tok;
+  sample_slot<0, kSampleThreads>(blockIdx.x, logits, ld, st, p, token_sets, cur_codes, forced, max_frames, dump, dump_stride_frame, dump_offset, dump_slot, sl, br);
 }
 void launch_sample(const LaunchCtx& c, const float* logits, int ld, int n_slots, SlotState* st, const SamplerParams& p,
                    unsigned* token_sets, int* cur_codes, const int* forced, int max_frames, float* logits_dump,
@@ -931,7 +661,7 @@ __global__ void __launch_bounds__(kSampleThreads) sample_probe_kernel(const floa
   __shared__ BlockRed br;
   for (int i = threadIdx.x; i < V; i += kSampleThreads) sl[i] = logits[i];
   __syncthreads();
-  const int tok = sample_block(sl, V, codec_vocab, temperature, top_k, top_p, rep_penalty, set_bitmap, seed, counter, br);
+  const int tok = sample_block<0, kSampleThreads>(sl, V, codec_vocab, temperature, top_k, top_p, rep_penalty, set_bitmap, seed, counter, br);
   if (threadIdx.x == 0) *id_out = tok;
 }
 void launch_sample_probe(const LaunchCtx& c, const float* logits, int vocab, int codec_vocab, float temperature, int top_k,

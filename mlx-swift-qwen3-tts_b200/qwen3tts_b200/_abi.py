@@ -50,7 +50,7 @@ class Request(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("prefill_ms", C.c_double), ("decode_ms", C.c_double), ("kernel_launches", i64),
                 ("graph_replays", i64), ("frames", i64), ("h2d_bytes", i64), ("d2h_bytes", i64), ("weight_bytes_per_frame", i64),
-                ("talker_ms", C.c_double), ("codec_flops", i64), ("reserved", i64 * 4)]
+                ("talker_ms", C.c_double), ("codec_flops", i64), ("persistent_launches", i64), ("reserved", i64 * 3)]
 
 
 # every symbol include/qwen3tts_b200.h declares: name -> (restype, argtypes)
