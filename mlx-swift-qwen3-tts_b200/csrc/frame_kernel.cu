@@ -1,7 +1,9 @@
 // Persistent frame kernel (sm_100a).  Grid = one CTA per SM (cooperative launch), 16 warps per CTA:
 //   warps 0-14 : consumers.  Every Qwen3DecoderLayer is five phases — [RMSNorm + qkv GEMV] | [q/k norm + RoPE + KV append +
 //                split-key window attention] | [split combine + o GEMV + residual] | [RMSNorm + gate/up GEMV + SwiGLU] |
-//                [down GEMV + residual] — separated by a grid barrier (one L2 atomic + one L2 poll) instead of a kernel launch.
+//                [down GEMV + residual].  There is NO grid barrier: every value a phase hands to the next one travels as an
+//                8-byte (value, phase tag) pair ("LL" exchange) that the consumer polls directly in L2, so a phase boundary
+//                costs one store->load round trip instead of fence + atomic + poll + reload.
 //                Each CTA owns a contiguous slice of every linear's output rows; a warp owns a row: 128-bit reads of the
 //                packed row from shared memory, dequant in registers, activations lane-major in shared memory, shuffle reduce.
 //   warp 15    : weight producer.  Walks the frame's linears in execution order and copies this CTA's row slices (weights,
@@ -62,10 +64,37 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// ---- LL exchange: element = (tag << 32) | value bits, written / read with single 64-bit (or paired 2 x 64-bit) accesses.
+// A reader spins until the tag equals the producing phase's id; buffers are zeroed per launch and tags start at 1.
+typedef unsigned long long u64;
+__device__ __forceinline__ void ll_store(u64* p, uint32_t bits, uint32_t tag) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(((u64)tag << 32) | bits) : "memory");
+}
+__device__ __forceinline__ void ll_ld2(const u64* p, u64& a, u64& b) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ bool ll_ok(u64 v, uint32_t tag) { return (uint32_t)(v >> 32) == tag; }
+__device__ __forceinline__ float ll_f(u64 v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ uint32_t ll_load1(const u64* p, uint32_t tag) {
+  u64 v;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    if (ll_ok(v, tag)) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+  return (uint32_t)v;
+}
+__device__ __forceinline__ float4 ll_load4(const u64* p, uint32_t tag) {  // 4 consecutive elements, 32-byte aligned
+  u64 a, b, c, d;
+  uint32_t spins = 0;
+  while (true) {
+    ll_ld2(p, a, b);
+    ll_ld2(p + 2, c, d);
+    if (ll_ok(a, tag) && ll_ok(b, tag) && ll_ok(c, tag) && ll_ok(d, tag)) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+  return make_float4(ll_f(a), ll_f(b), ll_f(c), ll_f(d));
 }
 __device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ uint32_t lop3_and_or(uint32_t a, uint32_t b, uint32_t c) {  // (a & b) | c in ONE LOP3
@@ -85,6 +114,7 @@ struct Sm {   // byte offsets into smem (from MegaParams) resolved once
   float* xraw;      // raw residual rows of the current layer input
   float* red;       // [rows][16] partial sums of squares
   MegaLinear* dsc;  // [2] descriptor of the current / next linear
+  float* hl;        // [slots][raw_ld] h_last of the previous talker step (every CTA keeps its own copy)
 };
 
 struct Slice { int r0, rows, rch, nch; };
@@ -134,30 +164,21 @@ __device__ void producer_loop(const MegaParams& p, uint8_t* ring, uint64_t* full
 // ------------------------------------------------------------------------------------------------ per-thread state
 struct Ctx {
   int slot;          // ring position of the next chunk (consumer side)
-  uint32_t ph;
-  unsigned bar_target;
+  uint32_t ring_ph;
+  uint32_t ph;       // id of the phase being executed (identical in every CTA); values written carry it as their tag
+  uint32_t fseq;     // 1 + frame index within the launch: tag of the per-frame messages
   int tid, lane, warp;
   long long* trace;  // per-phase cycle stamps of this CTA's thread 0 (diagnostics; null = off)
   long long wait_full;
 };
 
-// ------------------------------------------------------------------------------------------------ grid barrier
-__device__ __forceinline__ void grid_sync(const MegaParams& p, Ctx& cx) {
-  cx.bar_target += gridDim.x;
-  cbar();
-  if (cx.tid == 0) {
-    if (cx.trace) cx.trace[3] = clock64();
-    __threadfence();
-    atomicAdd(p.barrier, 1u);
-    if (cx.trace) cx.trace[4] = clock64();
-    uint32_t spins = 0;
-    while (ld_acquire_u32(p.barrier) < cx.bar_target) {
-      if (++spins > (1u << 24)) __trap();
-    }
-    __threadfence();
-    if (cx.trace) { cx.trace[5] = clock64(); cx.trace += 8; }
-  }
-  cbar();
+__device__ __forceinline__ void trace_close(Ctx& cx) {
+  if (cx.trace) { cx.trace[3] = cx.trace[4] = cx.trace[5] = clock64(); cx.trace += 8; }
+}
+
+// per-frame message of unit u for `slot`: 4 LL elements {code_u, pos, win_start, text row (-1: tts_pad)} (the last three: unit 0)
+__device__ __forceinline__ u64* msg_at(const MegaParams& p, uint32_t fseq, int u, int slot) {
+  return p.ex_msg + ((size_t)((fseq & 1u) * 16 + u) * kMegaMaxSlots + slot) * 4;
 }
 
 // ------------------------------------------------------------------------------------------------ activation staging
@@ -187,52 +208,84 @@ enum InKind {
 struct InArgs {
   int kind;
   int pass;      // code-predictor pass (IN_CPG) ; rows per slot (IN_GX_LAST)
-  int ld;        // row stride of the source buffer (IN_GX*, IN_ACT)
   int nsplit, heads;
 };
 
-__device__ __forceinline__ float4 load_in(const MegaParams& p, const InArgs& a, int mi, int f) {
+// softmax-weighted merge of NSPLIT key splits (flash-decoding combine); every load of a round is in flight together
+template <int NSPLIT>
+__device__ __forceinline__ float4 combine_splits(const MegaParams& p, int mi, int f, int heads, uint32_t tag) {
+  const int h = f >> 5;
+  u64 o[NSPLIT][4], ml[NSPLIT][2];
+  uint32_t spins = 0;
+  while (true) {
+    bool ok = true;
+#pragma unroll
+    for (int sp = 0; sp < NSPLIT; ++sp) {
+      const u64* base = p.ex_part + (size_t)(mi * NSPLIT + sp) * p.part_stride;
+      ll_ld2(base + heads * 128 + 2 * h, ml[sp][0], ml[sp][1]);
+      ll_ld2(base + (size_t)f * 4, o[sp][0], o[sp][1]);
+      ll_ld2(base + (size_t)f * 4 + 2, o[sp][2], o[sp][3]);
+    }
+#pragma unroll
+    for (int sp = 0; sp < NSPLIT; ++sp)
+      ok = ok && ll_ok(ml[sp][0], tag) && ll_ok(ml[sp][1], tag) && ll_ok(o[sp][0], tag) && ll_ok(o[sp][1], tag) && ll_ok(o[sp][2], tag) && ll_ok(o[sp][3], tag);
+    if (ok) break;
+    if (++spins > (1u << 22)) __trap();
+  }
+  float M = -INFINITY;
+#pragma unroll
+  for (int sp = 0; sp < NSPLIT; ++sp) M = fmaxf(M, ll_f(ml[sp][0]));
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float den = 0.f;
+#pragma unroll
+  for (int sp = 0; sp < NSPLIT; ++sp) {
+    const float l = ll_f(ml[sp][1]);
+    if (l > 0.f) {
+      const float w = expf(ll_f(ml[sp][0]) - M);
+      acc.x += w * ll_f(o[sp][0]); acc.y += w * ll_f(o[sp][1]); acc.z += w * ll_f(o[sp][2]); acc.w += w * ll_f(o[sp][3]);
+      den += w * l;
+    }
+  }
+  const float inv = 1.0f / den;
+  return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+}
+
+__device__ __forceinline__ float4 load_in(const MegaParams& p, const Ctx& cx, const float* hl, const InArgs& a, int mi, int f) {
+  const uint32_t tag = cx.ph - 1u;  // every exchanged value was produced by the immediately preceding phase
   switch (a.kind) {
-    case IN_GX: return ldcg4(p.gx + (size_t)mi * a.ld + (size_t)f * 4);
-    case IN_GX_LAST: return ldcg4(p.gx + (size_t)(mi * a.pass + a.pass - 1) * a.ld + (size_t)f * 4);
-    case IN_ACT: return ldcg4(p.gact + (size_t)mi * a.ld + (size_t)f * 4);
+    case IN_GX: return ll_load4(p.ex_x + (size_t)mi * p.ld_x + (size_t)f * 4, tag);
+    case IN_GX_LAST: return ll_load4(p.ex_x + (size_t)(mi * a.pass + a.pass - 1) * p.ld_x + (size_t)f * 4, tag);
+    case IN_ACT: return ll_load4(p.ex_act + (size_t)mi * p.ld_act + (size_t)f * 4, tag);
     case IN_CP0: {
       const int slot = mi >> 1;
-      if ((mi & 1) == 0) return ldcg4(p.hlast + (size_t)slot * p.H + (size_t)f * 4);
-      return ld_emb4(p.codec, __ldcg(p.cur_codes + slot * 16), f);
+      if ((mi & 1) == 0) return reinterpret_cast<const float4*>(hl + slot * p.raw_ld)[f];
+      return ld_emb4(p.codec, (int)ll_load1(msg_at(p, cx.fseq, 0, slot), cx.fseq), f);
     }
-    case IN_CPG: return ld_emb4(p.cp_emb[a.pass - 1], __ldcg(p.cur_codes + mi * 16 + a.pass), f);
+    case IN_CPG: return ld_emb4(p.cp_emb[a.pass - 1], (int)ll_load1(msg_at(p, cx.fseq, a.pass, mi), cx.fseq), f);
     case IN_TALKER: {
-      const SlotState& s = p.st[mi];
-      const int ti = __ldcg(&s.trailing_idx), tt = __ldcg(&s.total_text);
-      const float* text = (ti < tt) ? p.trailing + ((size_t)mi * p.max_trailing + ti) * p.H : p.tts_pad;
-      float4 sum = ld_emb4(p.codec, __ldcg(p.cur_codes + mi * 16), f);
+      u64 c[16], hdr;
+      uint32_t spins = 0;
+      while (true) {  // the 16 codes of this frame + the text cursor: all loads in flight together
+        bool ok = true;
 #pragma unroll
-      for (int g = 1; g < 16; ++g) add4(sum, ld_emb4(p.cp_emb[g - 1], __ldcg(p.cur_codes + mi * 16 + g), f));
+        for (int g = 0; g < 16; ++g) asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(c[g]) : "l"(msg_at(p, cx.fseq, g, mi)) : "memory");
+        asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(hdr) : "l"(msg_at(p, cx.fseq, 0, mi) + 3) : "memory");
+#pragma unroll
+        for (int g = 0; g < 16; ++g) ok = ok && ll_ok(c[g], cx.fseq);
+        if (ok && ll_ok(hdr, cx.fseq)) break;
+        if (++spins > (1u << 22)) __trap();
+      }
+      const int ti = (int)(uint32_t)hdr;
+      const float* text = ti >= 0 ? p.trailing + ((size_t)mi * p.max_trailing + ti) * p.H : p.tts_pad;
+      float4 sum = ld_emb4(p.codec, (int)(uint32_t)c[0], f);
+#pragma unroll
+      for (int g = 1; g < 16; ++g) add4(sum, ld_emb4(p.cp_emb[g - 1], (int)(uint32_t)c[g], f));
       float4 t = *reinterpret_cast<const float4*>(text + (size_t)f * 4);
       add4(t, sum);
       return t;
     }
-    default: {  // IN_ATTN: softmax-weighted merge of the key splits (flash-decoding combine)
-      const int h = f >> 5;
-      float M = -INFINITY;
-      for (int sp = 0; sp < a.nsplit; ++sp)
-        M = fmaxf(M, __ldcg(p.gpart + (size_t)(mi * a.nsplit + sp) * p.part_stride + a.heads * 128 + 2 * h));
-      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      float den = 0.f;
-      for (int sp = 0; sp < a.nsplit; ++sp) {
-        const float* base = p.gpart + (size_t)(mi * a.nsplit + sp) * p.part_stride;
-        const float l = __ldcg(base + a.heads * 128 + 2 * h + 1);
-        if (l > 0.f) {
-          const float w = expf(__ldcg(base + a.heads * 128 + 2 * h) - M);
-          const float4 o = ldcg4(base + (size_t)f * 4);
-          acc.x += w * o.x; acc.y += w * o.y; acc.z += w * o.z; acc.w += w * o.w;
-          den += w * l;
-        }
-      }
-      const float inv = 1.0f / den;
-      return make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    }
+    default:  // IN_ATTN
+      return a.nsplit == 1 ? combine_splits<1>(p, mi, f, a.heads, tag) : combine_splits<4>(p, mi, f, a.heads, tag);
   }
 }
 
@@ -254,13 +307,12 @@ __device__ __forceinline__ void stage_rows(const MegaParams& p, const Sm& sm, co
       const int f = f0 + cx.tid;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (f < in4) {
-        v = load_in(p, in, mi, f);
+        float4 nw = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (norm_w != nullptr) nw = __ldg(reinterpret_cast<const float4*>(norm_w) + f);  // in flight with the poll below
+        v = load_in(p, cx, sm.hl, in, mi, f);
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         if (keep_raw) reinterpret_cast<float4*>(sm.xraw + mi * p.raw_ld)[f] = v;
-        if (norm_w != nullptr) {
-          const float4 nw = __ldg(reinterpret_cast<const float4*>(norm_w) + f);
-          v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
-        }
+        v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
         const int e = f << 2;
         const int ch = e / KC, ec = e - ch * KC;
         const int l = ec / VPL, j = (ec - l * VPL) >> 2;
@@ -294,9 +346,10 @@ __device__ __forceinline__ float scale_to_f32(uint32_t raw16, int sdt) {  // bf1
   return sdt == Q3TTS_F16 ? as_f16 : as_bf16;
 }
 
-template <int FMT, int M>
+// R rows of the warp are in flight together (independent FMA chains, the staged activations are read once for all of them).
+template <int FMT, int M, int R>
 __device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx& cx, const MegaLinear& L, int m, bool has_norm, float eps, int epi,
-                                          float* out, int ld_out) {
+                                          u64* out, int ld_out, float* plain_out, int plain_ld) {
   constexpr int VPL = FmtTraits<FMT>::VPL;
   constexpr int KC = 32 * VPL;
   constexpr bool QUANT = (FMT == W_Q4 || FMT == W_Q8);
@@ -319,97 +372,133 @@ __device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx
   for (int c = 0; c < s.nch; ++c) {
     const int slot = cx.slot;
     const long long tw0 = cx.trace ? clock64() : 0;
-    mbar_wait(&sm.full[slot], cx.ph);
+    mbar_wait(&sm.full[slot], cx.ring_ph);
     if (cx.trace) cx.wait_full += clock64() - tw0;
     const int row0 = s.r0 + c * s.rch;
     const int rows = min(s.rch, s.rows - c * s.rch);
     const int wb = rows * row_bytes, sb = rows * srow_bytes;
     const uint8_t* base = sm.ring + slot * p.slot_bytes;
-    for (int r = cx.warp; r < rows; r += kCWarps) {
-      float res[2][M];
+    for (int r = cx.warp; r < rows; r += R * kCWarps) {
+      float res[R][2][M];
 #pragma unroll
-      for (int sub = 0; sub < 2; ++sub) {
+      for (int q = 0; q < R; ++q) {
 #pragma unroll
-        for (int mi = 0; mi < M; ++mi) res[sub][mi] = 0.f;
+        for (int sub = 0; sub < 2; ++sub) {
+#pragma unroll
+          for (int mi = 0; mi < M; ++mi) res[q][sub][mi] = 0.f;
+        }
       }
 #pragma unroll
       for (int sub = 0; sub < 2; ++sub) {
         if (sub < nsub) {
           const uint8_t* sbase = base + sub * (wb + 2 * sb);
-          const uint4* wr = reinterpret_cast<const uint4*>(sbase + r * row_bytes);
-          const uint8_t* scp = sbase + wb + r * srow_bytes;
-          float acc[M];
+          float acc[R][M][2];
 #pragma unroll
-          for (int mi = 0; mi < M; ++mi) acc[mi] = 0.f;
+          for (int q = 0; q < R; ++q) {
+#pragma unroll
+            for (int mi = 0; mi < M; ++mi) acc[q][mi][0] = acc[q][mi][1] = 0.f;
+          }
           for (int ch = 0; ch < nchunk; ++ch) {
             const int e0 = ch * KC + cx.lane * VPL;
             if (e0 < K) {
-              const uint4 wv = wr[ch * 32 + cx.lane];
-              float scv = 1.f, biv = 0.f;
-              if constexpr (QUANT) {
-                const int gi = e0 >> gshift;
-                if (sdt == Q3TTS_F32) {
-                  scv = reinterpret_cast<const float*>(scp)[gi];
-                  biv = reinterpret_cast<const float*>(scp + sb)[gi];
-                } else {
-                  scv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp)[gi], sdt);
-                  biv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp + sb)[gi], sdt);
-                }
-              }
-              float wf[VPL];
-              if constexpr (FMT == W_Q4) {  // m = 1 + q/16: shift + one LOP3 per value, no FADD
-                const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+              for (int q = 0; q < R; ++q) {
+                const int rq = r + q * kCWarps;
+                if (q == 0 || rq < rows) {
+                  const uint4 wv = reinterpret_cast<const uint4*>(sbase + rq * row_bytes)[ch * 32 + cx.lane];
+                  const uint8_t* scp = sbase + wb + rq * srow_bytes;
+                  float scv = 1.f, biv = 0.f;
+                  if constexpr (QUANT) {
+                    const int gi = e0 >> gshift;
+                    if (sdt == Q3TTS_F32) {
+                      scv = reinterpret_cast<const float*>(scp)[gi];
+                      biv = reinterpret_cast<const float*>(scp + sb)[gi];
+                    } else {
+                      scv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp)[gi], sdt);
+                      biv = scale_to_f32(reinterpret_cast<const unsigned short*>(scp + sb)[gi], sdt);
+                    }
+                  }
+                  float wf[VPL];
+                  if constexpr (FMT == W_Q4) {  // m = 1 + q/16: shift + one LOP3 per value, no FADD
+                    const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
 #pragma unroll
-                  for (int n = 0; n < 8; ++n) {
-                    const uint32_t sh = (19 - 4 * n) >= 0 ? (ww[i] << ((19 - 4 * n) & 31)) : (ww[i] >> ((4 * n - 19) & 31));
-                    wf[i * 8 + n] = __uint_as_float(lop3_and_or(sh, 0x00780000u, 0x3F800000u));
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                      for (int n = 0; n < 8; ++n) {
+                        const uint32_t sh = (19 - 4 * n) >= 0 ? (ww[i] << ((19 - 4 * n) & 31)) : (ww[i] >> ((4 * n - 19) & 31));
+                        wf[i * 8 + n] = __uint_as_float(lop3_and_or(sh, 0x00780000u, 0x3F800000u));
+                      }
+                    }
+                    scv *= 16.0f;  // s*q.x + b*sum(x) = 16s*(m.x) + (b - 16s)*sum(x)
+                    biv -= scv;
+                  } else {
+                    lane_expand<FMT>(wv, wf);
+                  }
+#pragma unroll
+                  for (int mi = 0; mi < M; ++mi) {
+                    const float4* xp = sm.xs + mi * xstride + ch * (KC / 4) + cx.lane;
+                    float d0 = 0.f, d1 = 0.f;  // two independent FMA chains per (row, activation row)
+#pragma unroll
+                    for (int j = 0; j < VPL / 4; ++j) {
+                      const float4 x = xp[j * 32];
+                      d0 = fmaf(wf[4 * j], x.x, d0);
+                      d1 = fmaf(wf[4 * j + 1], x.y, d1);
+                      d0 = fmaf(wf[4 * j + 2], x.z, d0);
+                      d1 = fmaf(wf[4 * j + 3], x.w, d1);
+                    }
+                    if constexpr (QUANT) {
+                      acc[q][mi][0] = fmaf(scv, d0 + d1, acc[q][mi][0]);
+                      acc[q][mi][1] = fmaf(biv, sm.xsum[mi * (nchunk * 32) + ch * 32 + cx.lane], acc[q][mi][1]);
+                    } else {
+                      acc[q][mi][0] += d0;
+                      acc[q][mi][1] += d1;
+                    }
                   }
                 }
-                scv *= 16.0f;  // s*q.x + b*sum(x) = 16s*(m.x) + (b - 16s)*sum(x)
-                biv -= scv;
-              } else {
-                lane_expand<FMT>(wv, wf);
-              }
-#pragma unroll
-              for (int mi = 0; mi < M; ++mi) {
-                const float d = lane_dot<FMT>(wf, sm.xs + mi * xstride + ch * (KC / 4) + cx.lane);
-                if constexpr (QUANT) acc[mi] += scv * d + biv * sm.xsum[mi * (nchunk * 32) + ch * 32 + cx.lane];
-                else acc[mi] += d;
               }
             }
           }
 #pragma unroll
-          for (int mi = 0; mi < M; ++mi) res[sub][mi] = warp_sum(acc[mi]) * inv_rms[mi];
+          for (int q = 0; q < R; ++q) {
+#pragma unroll
+            for (int mi = 0; mi < M; ++mi) res[q][sub][mi] = warp_sum(acc[q][mi][0] + acc[q][mi][1]) * inv_rms[mi];
+          }
         }
       }
-      const int grow = row0 + r;
 #pragma unroll
-      for (int mi = 0; mi < M; ++mi) {
-        if (cx.lane == mi && mi < m) {
-          float v = res[0][mi];
-          if (epi == E_SWIGLU) {
-            float g = v, u = res[1][mi];
-            if (L.bias) { g += L.bias[grow]; u += L.bias[grow + L.out_eff]; }
-            v = silu_f(g) * u;
-          } else {
-            if (L.bias) v += L.bias[grow];
-            if (epi == E_ADD_RAW) v += sm.xraw[mi * p.raw_ld + grow];
+      for (int q = 0; q < R; ++q) {
+        const int rq = r + q * kCWarps;
+        if (q == 0 || rq < rows) {
+          const int grow = row0 + rq;
+#pragma unroll
+          for (int mi = 0; mi < M; ++mi) {
+            if (cx.lane == mi && mi < m) {
+              float v = res[q][0][mi];
+              if (epi == E_SWIGLU) {
+                float g = v, u = res[q][1][mi];
+                if (L.bias) { g += L.bias[grow]; u += L.bias[grow + L.out_eff]; }
+                v = silu_f(g) * u;
+              } else {
+                if (L.bias) v += L.bias[grow];
+                if (epi == E_ADD_RAW) v += sm.xraw[mi * p.raw_ld + grow];
+              }
+              ll_store(out + (size_t)mi * ld_out + grow, __float_as_uint(v), cx.ph);
+              if (plain_out) plain_out[(size_t)mi * plain_ld + grow] = v;
+            }
           }
-          out[(size_t)mi * ld_out + grow] = v;
         }
       }
     }
     __syncwarp();
     if (cx.lane == 0) mbar_arrive(&sm.empty[slot]);
-    if (++cx.slot == p.n_ring) { cx.slot = 0; cx.ph ^= 1u; }
+    if (++cx.slot == p.n_ring) { cx.slot = 0; cx.ring_ph ^= 1u; }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ attention phase
 // item = (slot, kv head, key split).  rps rows per slot (2 only in code-predictor pass 0).  Writes unnormalised partial
-// outputs + (max, sum) per head; the o-projection staging merges the splits.
+// outputs + (max, sum) per head; the o-projection staging merges the splits.  A lane owns 4 consecutive head dims
+// (one LL poll of 4 elements); the rotate-half partner of dim d is dim d ^ 64, i.e. lane ^ 16.
 template <int G>
 __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, const MegaStack& S, const float* q_norm, const float* k_norm, int rps,
                            bool talker, int cp_pos0, int l) {
@@ -421,15 +510,18 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
   float* ored = sc + G * kKeyTile;       // [kKeyGroups][G][128]
   float* stat = ored + kKeyGroups * G * 128;  // [G][2]
   const int heads = S.heads, kv_heads = S.kv_heads, nsplit = S.nsplit, cap = S.capacity;
-  const int qkv_ld = (heads + 2 * kv_heads) * 128;
   const int n_items = p.n_slots * kv_heads * nsplit;
   const float scale = 0.08838834764831845f;  // 1 / sqrt(128)
+  const uint32_t tag = cx.ph - 1u;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int slot = item / (kv_heads * nsplit);
     const int rem = item - slot * (kv_heads * nsplit);
     const int kvh = rem / nsplit, sp = rem - kvh * nsplit;
     int pos0 = cp_pos0, w0 = 0;
-    if (talker) { pos0 = __ldcg(&p.st[slot].pos); w0 = __ldcg(&p.st[slot].win_start); }
+    if (talker) {  // position / window of this frame's talker step: published by CTA 0 with code0
+      pos0 = (int)ll_load1(msg_at(p, cx.fseq, 0, slot) + 1, cx.fseq);
+      w0 = (int)ll_load1(msg_at(p, cx.fseq, 0, slot) + 2, cx.fseq);
+    }
     const int w0r = w0 % cap;  // ring index of the window start; later keys wrap with one conditional subtract
     float* kb = S.k + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
     float* vb = S.v + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
@@ -438,27 +530,32 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
       const int rr = cx.warp / (G + 2), role = cx.warp - rr * (G + 2);
       const int row = slot * rps + rr, pos = pos0 + rr;
       const int ring = pos % cap;
-      const float* rowp = p.gqkv + (size_t)row * qkv_ld;
+      const u64* rowp = p.ex_qkv + (size_t)row * p.ld_qkv;
       const int lane = cx.lane;
       if (role <= G) {
-        const float* src = rowp + (size_t)(role < G ? (kvh * G + role) : (heads + kvh)) * 128;
-        const float a0 = __ldcg(src + lane), a1 = __ldcg(src + lane + 32), b0 = __ldcg(src + lane + 64), b1 = __ldcg(src + lane + 96);
-        const float ss = warp_sum(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+        const int head = role < G ? (kvh * G + role) : (heads + kvh);
+        const float4 a = ll_load4(rowp + (size_t)head * 128 + lane * 4, tag);
+        const float ss = warp_sum(a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w);
         const float inv = rsqrtf(ss * (1.0f / 128.0f) + S.eps);
-        const float* nw = role < G ? q_norm : k_norm;
-        const float x0 = a0 * inv * nw[lane], x1 = a1 * inv * nw[lane + 32], y0 = b0 * inv * nw[lane + 64], y1 = b1 * inv * nw[lane + 96];
-        float s0, c0, s1, c1;
-        sincosf((float)pos * S.inv_freq[lane], &s0, &c0);
-        sincosf((float)pos * S.inv_freq[lane + 32], &s1, &c1);
-        const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
+        const float4 nw = __ldg(reinterpret_cast<const float4*>(role < G ? q_norm : k_norm) + lane);
+        const float4 x = make_float4(a.x * inv * nw.x, a.y * inv * nw.y, a.z * inv * nw.z, a.w * inv * nw.w);
+        const float4 fr = __ldg(reinterpret_cast<const float4*>(S.inv_freq) + (lane & 15));
+        float4 sn, cs;
+        sincosf((float)pos * fr.x, &sn.x, &cs.x);
+        sincosf((float)pos * fr.y, &sn.y, &cs.y);
+        sincosf((float)pos * fr.z, &sn.z, &cs.z);
+        sincosf((float)pos * fr.w, &sn.w, &cs.w);
+        float4 y;  // partner dims (d ^ 64)
+        y.x = __shfl_xor_sync(0xffffffffu, x.x, 16); y.y = __shfl_xor_sync(0xffffffffu, x.y, 16);
+        y.z = __shfl_xor_sync(0xffffffffu, x.z, 16); y.w = __shfl_xor_sync(0xffffffffu, x.w, 16);
+        // q*cos + rotate_half(q)*sin, rotate_half = [-x2, x1]  (Model/Qwen3Layers.swift:187-195)
+        const float sg = lane < 16 ? -1.0f : 1.0f;
+        const float4 o = make_float4(x.x * cs.x + sg * y.x * sn.x, x.y * cs.y + sg * y.y * sn.y, x.z * cs.z + sg * y.z * sn.z, x.w * cs.w + sg * y.w * sn.w);
         float* dst = role < G ? q + (rr * G + role) * 128 : kcur + rr * 128;
-        dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
-        if (role == G && sp == 0) {  // append k to the ring (Model/Qwen3Layers.swift:197-201)
-          float* kd = kb + (size_t)ring * 128;
-          kd[lane] = o0; kd[lane + 32] = o1; kd[lane + 64] = o2; kd[lane + 96] = o3;
-        }
+        reinterpret_cast<float4*>(dst)[lane] = o;
+        if (role == G && sp == 0) reinterpret_cast<float4*>(kb + (size_t)ring * 128)[lane] = o;  // append k (Model/Qwen3Layers.swift:197-201)
       } else {
-        const float4 v = ldcg4(rowp + (size_t)(heads + kv_heads + kvh) * 128 + lane * 4);
+        const float4 v = ll_load4(rowp + (size_t)(heads + kv_heads + kvh) * 128 + lane * 4, tag);
         reinterpret_cast<float4*>(vcur + rr * 128)[lane] = v;
         if (sp == 0) reinterpret_cast<float4*>(vb + (size_t)ring * 128)[lane] = v;
       }
@@ -539,38 +636,21 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
         for (int g = 0; g < G; ++g) ored[(kg * G + g) * 128 + d] = o[g];
       }
       cbar();
-      float* part = p.gpart + (size_t)(row * nsplit + sp) * p.part_stride;
+      u64* part = p.ex_part + (size_t)(row * nsplit + sp) * p.part_stride;
       if (cx.tid < G * 128) {
         const int g = cx.tid >> 7, d = cx.tid & 127;
         float o = 0.f;
 #pragma unroll
         for (int kg = 0; kg < kKeyGroups; ++kg) o += ored[(kg * G + g) * 128 + d];
-        part[(kvh * G + g) * 128 + d] = o;
+        ll_store(part + (kvh * G + g) * 128 + d, __float_as_uint(o), cx.ph);
       }
-      if (cx.tid < 2 * G) part[heads * 128 + 2 * kvh * G + cx.tid] = stat[cx.tid];
+      if (cx.tid < 2 * G) ll_store(part + heads * 128 + 2 * kvh * G + cx.tid, __float_as_uint(stat[cx.tid]), cx.ph);
       cbar();
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ bookkeeping (CTA 0)
-__device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, int group) {
-  if (blockIdx.x == 0) {
-    float* sl = reinterpret_cast<float*>(sm.xs);
-    BlockRed& br = *reinterpret_cast<BlockRed*>(sl + kMaxVocab);
-    SamplerParams sp;
-    sp.vocab = group == 0 ? p.V : p.Vc; sp.group = group; sp.codec_vocab = p.V; sp.eos_id = p.eos_id; sp.pad_id = p.pad_id;
-    sp.groups = 16; sp.set_words = p.set_words;
-    const float* logits = group == 0 ? p.logits0 : p.cplogits;
-    float* dump = group == 0 ? p.dump0 : p.dumpcp;
-    const int dump_stride = group == 0 ? p.V : 15 * p.Vc, dump_off = group == 0 ? 0 : (group - 1) * p.Vc;
-    for (int s = 0; s < p.n_slots; ++s) {
-      sample_slot<1, kCons>(s, logits, sp.vocab, p.st, sp, p.sets, p.cur_codes, p.forced, p.max_frames, dump, dump_stride, dump_off, 0, sl, br);
-      cbar();
-    }
-  }
-}
-
 // record the frame, add code0 to its set, advance the trailing-text cursor (Model/Qwen3Talker.swift:526-549)
 __device__ void finalize_bookkeeping(const MegaParams& p) {
   for (int slot = 0; slot < p.n_slots; ++slot) {
@@ -603,6 +683,45 @@ __device__ void step_advance(const MegaParams& p) {
   }
 }
 
+// CTA 0: code_u = sampleToken(logits of the previous unit); the id (and, for unit 0, position / window / text cursor of
+// this frame) is published to every CTA as a per-frame message.  All SlotState traffic stays inside CTA 0.
+__device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, int group, bool plain_logits) {
+  float* sl = reinterpret_cast<float*>(sm.xs);
+  BlockRed& br = *reinterpret_cast<BlockRed*>(sl + kMaxVocab);
+  float* lg = sl + kMaxVocab + 64;  // staged logits [n_slots][V]
+  SamplerParams sp;
+  sp.vocab = group == 0 ? p.V : p.Vc; sp.group = group; sp.codec_vocab = p.V; sp.eos_id = p.eos_id; sp.pad_id = p.pad_id;
+  sp.groups = 16; sp.set_words = p.set_words;
+  const int V = sp.vocab;
+  for (int s = 0; s < p.n_slots; ++s) {
+    if (plain_logits) {  // first unit of a launch: logits written by the prefill / the previous launch
+      for (int i = cx.tid; i < V; i += kCons) lg[s * V + i] = p.logits0[(size_t)s * V + i];
+    } else {
+      for (int f = cx.tid; f < (V >> 2); f += kCons)
+        reinterpret_cast<float4*>(lg + s * V)[f] = ll_load4(p.ex_logit + (size_t)s * p.ld_logit + (size_t)f * 4, cx.ph - 1u);
+    }
+  }
+  cbar();
+  float* dump = group == 0 ? p.dump0 : p.dumpcp;
+  const int dump_stride = group == 0 ? p.V : 15 * p.Vc, dump_off = group == 0 ? 0 : (group - 1) * p.Vc;
+  for (int s = 0; s < p.n_slots; ++s) {
+    sample_slot<1, kCons>(s, lg, V, p.st, sp, p.sets, p.cur_codes, p.forced, p.max_frames, dump, dump_stride, dump_off, 0, sl, br);
+    cbar();
+  }
+  if (cx.tid == 0) {
+    for (int s = 0; s < p.n_slots; ++s) {
+      const SlotState& st = p.st[s];
+      u64* m = msg_at(p, cx.fseq, group, s);
+      if (group == 0) {
+        ll_store(m + 1, (uint32_t)st.pos, cx.fseq);
+        ll_store(m + 2, (uint32_t)st.win_start, cx.fseq);
+        ll_store(m + 3, (uint32_t)(st.trailing_idx < st.total_text ? st.trailing_idx : -1), cx.fseq);
+      }
+      ll_store(m, (uint32_t)p.cur_codes[s * 16 + group], cx.fseq);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ the frame loop
 // ONE copy of every phase body: the 16 units of a frame (15 code-predictor passes + the talker step) run through the same
 // loop over linear phases [mtp?] + layers x {qkv, o, gate|up, down} + head.
@@ -620,6 +739,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
   sm.full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
   sm.empty = sm.full + p.n_ring;
   sm.dsc = reinterpret_cast<MegaLinear*>(smem + p.off_dsc);
+  sm.hl = reinterpret_cast<float*>(smem + p.off_hl);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kDscVec = (int)(sizeof(MegaLinear) / 16);
   if (tid == 0) {
@@ -628,13 +748,15 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[0])[tid] = __ldg(reinterpret_cast<const uint4*>(&p.lin[0]) + tid);
+  for (int s = 0; s < p.n_slots; ++s)  // h_last of the prefill / the previous launch
+    for (int i = tid; i < p.H; i += kMegaThreads) sm.hl[s * p.raw_ld + i] = p.hlast[(size_t)s * p.H + i];
   __syncthreads();
   if (warp == kCWarps) {
     if (lane == 0) producer_loop(p, sm.ring, sm.full, sm.empty);
     return;
   }
   Ctx cx;
-  cx.slot = 0; cx.ph = 0; cx.bar_target = 0; cx.tid = tid; cx.lane = lane; cx.warp = warp;
+  cx.slot = 0; cx.ring_ph = 0; cx.ph = 0; cx.fseq = 0; cx.tid = tid; cx.lane = lane; cx.warp = warp;
   cx.trace = nullptr; cx.wait_full = 0;
   if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
     cx.trace = p.trace + (size_t)(blockIdx.x == 0 ? 0 : 1) * p.trace_stride;
@@ -643,25 +765,31 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
 
   for (int f = 0; f < p.n_frames; ++f) {
     int li = 0;
+    cx.fseq = (uint32_t)f + 1u;
+    const bool last_frame = (f == p.n_frames - 1);
     for (int u = 0; u < 16; ++u) {   // units 0..14: code-predictor pass u (Model/Qwen3Talker.swift:501-523); 15: talker step
       const bool talker = (u == 15);
       const MegaStack& S = talker ? p.tk : p.cp;
-      if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
-      sample_phase(p, sm, u);        // code_u from the logits of the previous unit (code0: previous frame / prefill)
-      if (cx.trace) cx.trace[2] = clock64();
-      grid_sync(p, cx);
+      ++cx.ph;                       // ---- sample phase (CTA 0): code_u from the logits of the previous unit
+      if (blockIdx.x == 0) {
+        if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
+        sample_phase(p, sm, cx, u, f == 0 && u == 0);
+        if (cx.trace) cx.trace[2] = clock64();
+        trace_close(cx);
+        cbar();
+      }
       const int rps = (u == 0) ? 2 : 1;
       const int m = ns * rps;
       const int mtp = (!talker && p.has_mtp) ? 1 : 0;  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
       const int layers = S.layers, hidden = S.hidden, inter = S.inter, heads = S.heads;
       const int nj = mtp + 4 * layers + 1;
       const int first_kind = talker ? IN_TALKER : (u == 0 ? IN_CP0 : IN_CPG);
-      const int qkv_ld = (heads + 2 * S.kv_heads) * 128;
       const float eps = S.eps;
       for (int j = 0; j < nj; ++j) {
+        ++cx.ph;                     // ---- linear phase
         const MegaLinear& L = sm.dsc[cur];
         ++li;
-        // next phase's descriptor: loaded now, parked in the other slot before the barrier (never on the critical path)
+        // next phase's descriptor: loaded now, parked in the other slot at the end of the phase (never on the critical path)
         uint4 nd = make_uint4(0u, 0u, 0u, 0u);
         const int lnext = li < p.n_lin ? li : 0;
         if (tid < kDscVec) nd = __ldg(reinterpret_cast<const uint4*>(&p.lin[lnext]) + tid);
@@ -670,52 +798,62 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
         else if (j == nj - 1) kind = K_HEAD;
         else { l = (j - mtp) >> 2; kind = K_QKV + ((j - mtp) & 3); }
         InArgs in{};
-        in.pass = u; in.ld = hidden; in.nsplit = S.nsplit; in.heads = heads;
-        int rows = m, K = hidden, epi = E_STORE, ld_out = hidden;
-        float* out = p.gx;
+        in.pass = u; in.nsplit = S.nsplit; in.heads = heads;
+        int rows = m, K = hidden, epi = E_STORE, ld_out = p.ld_x;
+        u64* out = p.ex_x;
+        float* plain_out = nullptr;
         bool keep_raw = false;
         switch (kind) {
-          case K_MTP: in.kind = first_kind; K = p.H; ld_out = p.Hcp; break;
-          case K_QKV: in.kind = (l == 0 && !mtp) ? first_kind : IN_GX; keep_raw = true; out = p.gqkv; ld_out = qkv_ld; break;
+          case K_MTP: in.kind = first_kind; K = p.H; break;
+          case K_QKV: in.kind = (l == 0 && !mtp) ? first_kind : IN_GX; keep_raw = true; out = p.ex_qkv; ld_out = p.ld_qkv; break;
           case K_O: in.kind = IN_ATTN; K = heads * 128; epi = E_ADD_RAW; break;
-          case K_GU: in.kind = IN_GX; keep_raw = true; epi = E_SWIGLU; out = p.gact; ld_out = inter; break;
-          case K_DOWN: in.kind = IN_ACT; in.ld = inter; K = inter; epi = E_ADD_RAW; break;
+          case K_GU: in.kind = IN_GX; keep_raw = true; epi = E_SWIGLU; out = p.ex_act; ld_out = p.ld_act; break;
+          case K_DOWN: in.kind = IN_ACT; K = inter; epi = E_ADD_RAW; break;
           default:  // K_HEAD: final norm + lm_head[u] on the last position of each slot / codec_head (Qwen3CodePredictor.swift:207-212)
             in.kind = talker ? IN_GX : IN_GX_LAST; in.pass = rps; rows = ns; keep_raw = talker;
-            out = talker ? p.logits0 : p.cplogits; ld_out = talker ? p.V : p.Vc;
+            out = p.ex_logit; ld_out = p.ld_logit;
+            if (talker && last_frame) plain_out = p.logits0;  // the next launch (or the graph path) starts from plain logits
             break;
         }
         const float* norm_w = L.norm_w;
         if (cx.trace) { cx.trace[0] = clock64(); cx.wait_full = 0; }
         stage_rows<FMT>(p, sm, cx, in, rows, K, norm_w, keep_raw);
         if (cx.trace) cx.trace[1] = clock64();
-        if (kind == K_HEAD && talker && blockIdx.x == 0) {  // h_last = final norm of the talker step (next frame's pass-0 input)
+        if (kind == K_HEAD && talker) {  // h_last = final norm of the talker step: next frame's pass-0 input, kept per CTA
           for (int s = 0; s < ns; ++s) {
             float ss = 0.f;
             for (int w = 0; w < kCWarps; ++w) ss += sm.red[s * 16 + w];
             const float inv = rsqrtf(ss / (float)p.H + eps);
-            for (int i = tid; i < p.H; i += kCons) p.hlast[(size_t)s * p.H + i] = sm.xraw[s * p.raw_ld + i] * inv * norm_w[i];
+            for (int i = tid; i < p.H; i += kCons) {
+              const float hv = sm.xraw[s * p.raw_ld + i] * inv * norm_w[i];
+              sm.hl[s * p.raw_ld + i] = hv;
+              if (last_frame && blockIdx.x == 0) p.hlast[(size_t)s * p.H + i] = hv;
+            }
           }
         }
-        if (rps == 2 && kind != K_HEAD) gemv_rows<FMT, M>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out);
-        else gemv_rows<FMT, NS>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out);
+        if (rps == 2 && kind != K_HEAD) gemv_rows<FMT, M, 1>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out, plain_out, p.V);
+        else gemv_rows<FMT, NS, 2>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out, plain_out, p.V);
         if (cx.trace) { cx.trace[2] = clock64(); cx.trace[6] = cx.wait_full; cx.trace[7] = kind; }
         if (kind == K_HEAD && talker && blockIdx.x == 0 && tid == 0) step_advance(p);
         const float* q_norm = L.q_norm;
         const float* k_norm = L.k_norm;
         if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[cur ^ 1])[tid] = nd;
         cur ^= 1;
-        grid_sync(p, cx);
+        trace_close(cx);
+        cbar();  // xs / xraw / descriptors are reused by the next phase
         if (kind == K_QKV) {
+          ++cx.ph;                   // ---- attention phase (participants: one CTA per (slot, kv head, split))
           if (talker && l == 0 && blockIdx.x == 0 && tid == 0) finalize_bookkeeping(p);
-          if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
           const int G = heads / S.kv_heads;
-          const int cp_pos0 = u == 0 ? 0 : u + 1;
-          if (G == 2) attn_phase<2>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-          else if (G == 1) attn_phase<1>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-          else attn_phase<4>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-          if (cx.trace) cx.trace[2] = clock64();
-          grid_sync(p, cx);
+          if (blockIdx.x < (unsigned)(ns * S.kv_heads * S.nsplit)) {
+            if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
+            const int cp_pos0 = u == 0 ? 0 : u + 1;
+            if (G == 2) attn_phase<2>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+            else if (G == 1) attn_phase<1>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+            else attn_phase<4>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
+            if (cx.trace) cx.trace[2] = clock64();
+            trace_close(cx);
+          }
         }
       }
     }
@@ -762,7 +900,7 @@ void launch_frame_megakernel(const LaunchCtx& c, const MegaPlan& plan, int n_slo
   Q3_CHECK(plan.ok && n_slots >= 1 && n_slots <= kMegaMaxSlots && n_frames >= 1, Q3TTS_ERR_INVALID_ARG, "frame megakernel: bad launch");
   MegaParams p = plan.p;
   p.n_slots = n_slots; p.n_frames = n_frames; p.dump0 = dump0; p.dumpcp = dumpcp;
-  Q3_CUDA(cudaMemsetAsync(p.barrier, 0, sizeof(unsigned), c.stream));
+  Q3_CUDA(cudaMemsetAsync(p.ex_base, 0, p.ex_bytes, c.stream));  // LL tags start from 0 in every launch
   switch (plan.fmt) {
     case W_Q4: launch_fmt<W_Q4>(c, plan, p); break;
     case W_Q8: launch_fmt<W_Q8>(c, plan, p); break;

@@ -1,6 +1,6 @@
 // Persistent frame kernel ("megakernel") for the batch-1..NS decode loop: ONE cooperative launch runs n frames of
 // Model/Qwen3Talker.swift:464-562 — code0 sample, 15 code-predictor passes, frame finalize, talker step — with every
-// Qwen3DecoderLayer phase separated by a grid barrier instead of a kernel boundary.  Weights are streamed by a producer
+// Qwen3DecoderLayer phase handing its results to the next through tagged values in L2 instead of a kernel boundary.  Weights are streamed by a producer
 // warp (1-D TMA bulk copies into a shared-memory ring, several phases ahead of the math), so the dependency chain only
 // ever waits on L2-resident activations.
 #pragma once
@@ -62,13 +62,16 @@ struct MegaParams {
   int max_trailing;
   const float* tts_pad;
   float *hlast, *logits0, *cplogits, *dump0, *dumpcp;
-  float *gx, *gqkv, *gpart, *gact;
-  int part_stride;          // floats per (row, split) partial: heads*128 + 2*heads, padded to 4
-  unsigned* barrier;
+  // LL exchange buffers: 8-byte (value, tag) elements, zeroed per launch (ex_base, ex_bytes)
+  unsigned long long *ex_x, *ex_qkv, *ex_part, *ex_act, *ex_logit, *ex_msg;
+  int ld_x, ld_qkv, ld_act, ld_logit;
+  int part_stride;          // elements per (row, split) partial: heads*128 + 2*heads, padded to 4
+  void* ex_base;
+  size_t ex_bytes;
   int n_frames, window, eos_id, pad_id;
   // shared-memory plan (bytes from the 1024-aligned base)
   int slot_bytes, n_ring;
-  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc;
+  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc, off_hl;
   int raw_ld;               // floats per row of the raw residual copy
   long long* trace;         // diagnostics: [2 CTAs][trace_stride] cycle stamps, 8 per phase (null = off)
   int trace_stride;

@@ -204,11 +204,13 @@ void TalkerEngine::build_mega_plan() {
   const int nchunk = (kmax + kc - 1) / kc;
   const int hmax = std::max(T.hidden, P.hidden);
   auto up = [](int v, int a) { return (v + a - 1) / a * a; };
-  const int xs_bytes = up(std::max(MT * nchunk * kc * 4, 24 * 1024), 128);
+  // scratch floor: sampler (16 KB ids + reductions + staged logits of every slot) / attention tiles
+  const int xs_bytes = up(std::max(MT * nchunk * kc * 4, (4096 + 64 + NS * 4096) * 4), 128);
   const int xsum_bytes = up(MT * nchunk * 32 * 4, 128);
   const int xraw_bytes = up(MT * hmax * 4, 128);
   const int red_bytes = up(MT * 16 * 4, 128);
-  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 256 + 128;
+  const int hl_bytes = up(NS * hmax * 4, 128);
+  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 256 + hl_bytes + 128;
   const int budget = 226 * 1024;
   int n_ring = std::min(8, (budget - fixed) / slot_bytes);
   if (n_ring < 2) return;
@@ -220,8 +222,9 @@ void TalkerEngine::build_mega_plan() {
   p.off_red = p.off_xraw + xraw_bytes;
   p.off_bar = p.off_red + red_bytes;
   p.off_dsc = p.off_bar + 256;
+  p.off_hl = p.off_dsc + 256;
   p.raw_ld = hmax;
-  mega_.smem = (size_t)p.off_dsc + 256 + 128;
+  mega_.smem = (size_t)p.off_hl + hl_bytes + 128;
   mega_.fmt = fmt; mega_.G_cp = G_cp; mega_.G_tk = G_tk;
   int dev = 0, sms = 0, coop = 0;
   Q3_CUDA(cudaGetDevice(&dev));
@@ -230,7 +233,11 @@ void TalkerEngine::build_mega_plan() {
   if (!coop || sms < 1) return;
   init_mega_kernels();
   if (mega_max_blocks_per_sm(fmt, mega_.smem) < 1) return;
-  mega_.grid = sms;
+  // every CTA must own rows of every linear: the tagged exchange relies on all CTAs writing in every linear phase
+  int min_units = 1 << 30;
+  for (const MegaLinear& m : lin) min_units = std::min(min_units, m.out_eff / m.unit);
+  mega_.grid = std::min(sms, min_units);
+  if (mega_.grid < 1 || opt_.kv_capacity > 4 * 128) return;
   for (MegaLinear& m : lin) {
     const int U = m.out_eff / m.unit;
     m.ubase = U / mega_.grid; m.urem = U % mega_.grid;
@@ -246,7 +253,7 @@ void TalkerEngine::build_mega_plan() {
     s.slot_stride = slot_stride; s.layer_stride = layer_stride; s.capacity = cap; s.nsplit = nsplit;
     return s;
   };
-  const int nsplit_tk = std::max(4, (opt_.kv_capacity + 127) / 128);
+  const int nsplit_tk = 4;  // key splits of a talker attention item (each <= 128 keys: kv_capacity <= 512)
   p.lin = d_lin; p.n_lin = (int)lin.size();
   p.cp = stack_of(P, d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, 1);
   p.tk = stack_of(T, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, opt_.kv_capacity, nsplit_tk);
@@ -256,10 +263,22 @@ void TalkerEngine::build_mega_plan() {
   p.sets = d_sets_; p.set_words = set_words_;
   p.trailing = d_trailing_; p.max_trailing = opt_.max_trailing; p.tts_pad = d_tts_ + (size_t)2 * cfg_.hidden_size;
   p.hlast = d_hlast_; p.logits0 = d_logits0_; p.cplogits = d_cplogits_;
-  p.gx = d_x_; p.gqkv = d_qkv_; p.gact = d_act_;
   p.part_stride = up(std::max(T.heads, P.heads) * 130, 4);
-  p.gpart = arena_.alloc_n<float>((size_t)MT * nsplit_tk * p.part_stride);
-  p.barrier = arena_.alloc_n<unsigned>(64);
+  p.ld_x = up(hmax, 4);
+  p.ld_qkv = up(std::max((T.heads + 2 * T.kv_heads) * 128, (P.heads + 2 * P.kv_heads) * 128), 4);
+  p.ld_act = up(std::max(T.inter, P.inter), 4);
+  p.ld_logit = up(std::max(cfg_.vocab_size, cfg_.cp.vocab_size), 4);
+  const size_t n_x = (size_t)MT * p.ld_x, n_qkv = (size_t)MT * p.ld_qkv, n_part = (size_t)MT * nsplit_tk * p.part_stride;
+  const size_t n_act = (size_t)MT * p.ld_act, n_logit = (size_t)NS * p.ld_logit, n_msg = (size_t)2 * 16 * NS * 4;
+  p.ex_bytes = (n_x + n_qkv + n_part + n_act + n_logit + n_msg) * sizeof(unsigned long long);
+  unsigned long long* ex = arena_.alloc_n<unsigned long long>(n_x + n_qkv + n_part + n_act + n_logit + n_msg);
+  p.ex_base = ex;
+  p.ex_x = ex; ex += n_x;
+  p.ex_qkv = ex; ex += n_qkv;
+  p.ex_part = ex; ex += n_part;
+  p.ex_act = ex; ex += n_act;
+  p.ex_logit = ex; ex += n_logit;
+  p.ex_msg = ex;
   p.window = 192;  // maxKVCacheWindow (Model/Qwen3Layers.swift:108)
   p.eos_id = cfg_.codec_eos_token_id; p.pad_id = cfg_.codec_pad_id;
   if (getenv("Q3TTS_MEGA_TRACE")) {  // diagnostics: per-phase cycle stamps of one launch (frame_kernel.cu), dumped by run_frames
