@@ -19,6 +19,8 @@ Handle::~Handle() {
   if (ev_stop) cudaEventDestroy(ev_stop);
   if (h_pcm) cudaFreeHost(h_pcm);
   if (h_codes) cudaFreeHost(h_codes);
+  if (d_codes) cudaFree(d_codes);
+  if (d_pcm) cudaFree(d_pcm);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 }  // namespace q3
@@ -153,7 +155,7 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
   const int B = t.max_batch();
   raw.assign(n, {});
   n_raw.assign(n, 0);
-  std::vector<int> slot_req(B, -1);
+  std::vector<int> slot_req(B, -1), slot_limit(B, 0), slot_step(B, 0);
   int next = 0, active = 0;
   std::vector<SlotState> st;
   while (next < n || active > 0) {
@@ -172,6 +174,8 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
         rows += est;
         items.push_back({s, &rq});
         item_req.push_back(next);
+        slot_limit[s] = (rq.forced_codes && rq.n_forced_frames > 0) ? rq.n_forced_frames : std::min(std::max(rq.max_tokens, 0), t.max_frames());
+        slot_step[s] = 0;
         slot_req[s] = next++;
         ++active;
         break;
@@ -186,8 +190,13 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
     int hi = 0;
     for (int s = 0; s < B; ++s)
       if (slot_req[s] >= 0) hi = s + 1;
-    t.run_frames(hi, 8);
+    // frames still owed by the slowest active slot bound the chunk (no frame steps past max_tokens)
+    int need = 1;
+    for (int s = 0; s < hi; ++s)
+      if (slot_req[s] >= 0) need = std::max(need, slot_limit[s] - slot_step[s]);
+    t.run_frames(hi, std::min(8, need));
     t.fetch_states(hi, st);
+    for (int s = 0; s < hi; ++s) slot_step[s] = st[s].step;
     for (int s = 0; s < hi; ++s) {
       if (slot_req[s] < 0 || !st[s].finished) continue;
       const int r = slot_req[s];
@@ -224,6 +233,18 @@ void ensure_pinned(q3tts_handle* h, size_t pcm_floats, size_t code_ints) {
     Q3_CUDA(cudaMallocHost(&h->h_codes, code_ints * sizeof(int32_t)));
     h->h_codes_ints = code_ints;
   }
+  if (code_ints > h->d_codes_ints) {
+    if (h->d_codes) { Q3_CUDA(cudaStreamSynchronize(h->stream)); cudaFree(h->d_codes); }
+    h->d_codes = nullptr;
+    Q3_CUDA(cudaMalloc(&h->d_codes, code_ints * sizeof(int32_t)));
+    h->d_codes_ints = code_ints;
+  }
+  if (pcm_floats > h->d_pcm_floats) {
+    if (h->d_pcm) { Q3_CUDA(cudaStreamSynchronize(h->stream)); cudaFree(h->d_pcm); }
+    h->d_pcm = nullptr;
+    Q3_CUDA(cudaMalloc(&h->d_pcm, pcm_floats * sizeof(float)));
+    h->d_pcm_floats = pcm_floats;
+  }
 }
 
 // Decodes jobs grouped by equal T, each group in passes of up to pass_frames frames (jobs stacked on the batch axis).
@@ -246,10 +267,8 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
       const size_t code_ints = (size_t)nb * T * 16, pcm_floats = (size_t)nb * T * up;
       ensure_pinned(h, pcm_floats, code_ints);
       for (int b = 0; b < nb; ++b) memcpy(h->h_codes + (size_t)b * T * 16, jobs[idx[p0 + b]].frames, (size_t)T * 64);
-      int32_t* d_codes = nullptr;
-      float* d_pcm = nullptr;
-      Q3_CUDA(cudaMallocAsync(&d_codes, code_ints * 4, h->stream));
-      Q3_CUDA(cudaMallocAsync(&d_pcm, pcm_floats * 4, h->stream));
+      int32_t* d_codes = h->d_codes;
+      float* d_pcm = h->d_pcm;
       Q3_CUDA(cudaMemcpyAsync(d_codes, h->h_codes, code_ints * 4, cudaMemcpyHostToDevice, h->stream));
       h->timing.h2d_bytes += (int64_t)code_ints * 4;
       Q3_CUDA(cudaEventRecord(e0, h->stream));
@@ -257,8 +276,6 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
       Q3_CUDA(cudaEventRecord(e1, h->stream));
       Q3_CUDA(cudaMemcpyAsync(h->h_pcm, d_pcm, pcm_floats * 4, cudaMemcpyDeviceToHost, h->stream));
       h->timing.d2h_bytes += (int64_t)pcm_floats * 4;
-      Q3_CUDA(cudaFreeAsync(d_codes, h->stream));
-      Q3_CUDA(cudaFreeAsync(d_pcm, h->stream));
       Q3_CUDA(cudaStreamSynchronize(h->stream));
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
@@ -276,13 +293,10 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
   cudaEventDestroy(e1);
 }
 
-// NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732)
-void clean_samples(float* p, int64_t n) {
-  for (int64_t i = 0; i < n; ++i) {
-    const float v = p[i];
-    p[i] = (v != v || v > 3.0e38f || v < -3.0e38f) ? 0.0f : std::max(-1.0f, std::min(1.0f, v));
-  }
-}
+// NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732): done on the device by the codec's output kernel
+// (clip(-1, 1) maps +-Inf to +-1 before the Swift scrub sees it; NaN -> 0 is fused into out_conv_kernel), so the PCM that
+// reaches the host needs no second pass over every sample.
+void clean_samples(float*, int64_t) {}
 
 // Schedules the decode windows of one utterance's valid frames as `mode` prescribes; appends jobs writing into out.
 int64_t plan_decode(int mode, const int32_t* frames, int n, float* out, int64_t capacity, int up, std::vector<DecodeJob>& jobs) {

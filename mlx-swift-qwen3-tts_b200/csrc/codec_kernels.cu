@@ -341,7 +341,7 @@ void launch_rvq_embed_f16(const LaunchCtx& c, const int* codes, const float* con
   c.tick();
 }
 
-// DecoderOutputConv (k = 7, C -> 1) + clip(-1, 1) (SpeechTokenizer.swift:823-840, 951); x is already snake-activated.
+// DecoderOutputConv (k = 7, C -> 1) + clip(-1, 1) + NaN scrub (SpeechTokenizer.swift:823-840, 951); x is already snake-activated.
 template <typename InT>
 __global__ void __launch_bounds__(128) out_conv_kernel(const InT* __restrict__ x, const float* __restrict__ w /*[7][C]*/,
                                                        const float* __restrict__ bias, int C, int T, float* __restrict__ y) {
@@ -363,7 +363,8 @@ __global__ void __launch_bounds__(128) out_conv_kernel(const InT* __restrict__ x
     const float* wr = w + (size_t)k * C;
     for (int ch = 0; ch < C; ++ch) acc = fmaf(xr[ch], wr[ch], acc);
   }
-  y[(size_t)b * T + t] = fminf(1.0f, fmaxf(-1.0f, acc));
+  // clip(-1, 1); a NaN becomes 0 here so the host needs no scrub pass (Qwen3TTSPipeline.swift:565-570: NaN/Inf -> 0 after the clip)
+  y[(size_t)b * T + t] = (acc != acc) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, acc));
 }
 void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y) {
   if (B <= 0 || T <= 0) return;

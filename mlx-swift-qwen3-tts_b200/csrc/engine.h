@@ -148,6 +148,10 @@ struct Handle {
   size_t h_pcm_floats = 0;
   int32_t* h_codes = nullptr;
   size_t h_codes_ints = 0;
+  int32_t* d_codes = nullptr;  // grow-only device staging of the codec passes
+  size_t d_codes_ints = 0;
+  float* d_pcm = nullptr;
+  size_t d_pcm_floats = 0;
   ~Handle();
 };
 

@@ -115,6 +115,7 @@ struct Sm {   // byte offsets into smem (from MegaParams) resolved once
   float* red;       // [rows][16] partial sums of squares
   MegaLinear* dsc;  // [2] descriptor of the current / next linear
   float* hl;        // [slots][raw_ld] h_last of the previous talker step (every CTA keeps its own copy)
+  float* rope;      // [slots][2 rows][64 freqs][cos, sin] of the current unit's positions
 };
 
 struct Slice { int r0, rows, rch, nch; };
@@ -138,7 +139,13 @@ __device__ void producer_loop(const MegaParams& p, uint8_t* ring, uint64_t* full
       const MegaLinear L = p.lin[li];
       const Slice s = slice_of(L);
       for (int c = 0; c < s.nch; ++c) {
-        mbar_wait(&empty[slot], ph ^ 1u);
+        {  // the ring is usually full: sleep between probes so this lone thread does not steal issue slots from the consumers
+          uint32_t spins = 0;
+          while (!mbar_try_wait(&empty[slot], ph ^ 1u)) {
+            __nanosleep(256);
+            if (++spins > (1u << 24)) __trap();
+          }
+        }
         const int row0 = s.r0 + c * s.rch;
         const int rows = min(s.rch, s.rows - c * s.rch);
         const uint32_t wb = (uint32_t)rows * L.row_bytes, sb = (uint32_t)rows * L.srow_bytes;
@@ -169,11 +176,11 @@ struct Ctx {
   uint32_t fseq;     // 1 + frame index within the launch: tag of the per-frame messages
   int tid, lane, warp;
   long long* trace;  // per-phase cycle stamps of this CTA's thread 0 (diagnostics; null = off)
-  long long wait_full;
+  long long wait_full, wait_poll;
 };
 
 __device__ __forceinline__ void trace_close(Ctx& cx) {
-  if (cx.trace) { cx.trace[3] = cx.trace[4] = cx.trace[5] = clock64(); cx.trace += 8; }
+  if (cx.trace) { cx.trace[5] = clock64(); cx.trace += 8; }
 }
 
 // per-frame message of unit u for `slot`: 4 LL elements {code_u, pos, win_start, text row (-1: tts_pad)} (the last three: unit 0)
@@ -309,7 +316,9 @@ __device__ __forceinline__ void stage_rows(const MegaParams& p, const Sm& sm, co
       if (f < in4) {
         float4 nw = make_float4(1.f, 1.f, 1.f, 1.f);
         if (norm_w != nullptr) nw = __ldg(reinterpret_cast<const float4*>(norm_w) + f);  // in flight with the poll below
+        const long long tp0 = cx.trace ? clock64() : 0;
         v = load_in(p, cx, sm.hl, in, mi, f);
+        if (cx.trace) const_cast<Ctx&>(cx).wait_poll += clock64() - tp0;
         ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
         if (keep_raw) reinterpret_cast<float4*>(sm.xraw + mi * p.raw_ld)[f] = v;
         v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
@@ -373,7 +382,7 @@ __device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx
     const int slot = cx.slot;
     const long long tw0 = cx.trace ? clock64() : 0;
     mbar_wait(&sm.full[slot], cx.ring_ph);
-    if (cx.trace) cx.wait_full += clock64() - tw0;
+    if (cx.trace) { cx.wait_full += clock64() - tw0; cx.trace[3] = clock64(); }
     const int row0 = s.r0 + c * s.rch;
     const int rows = min(s.rch, s.rows - c * s.rch);
     const int wb = rows * row_bytes, sb = rows * srow_bytes;
@@ -465,6 +474,7 @@ __device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx
           }
         }
       }
+      if (cx.trace) cx.trace[4] = clock64();
 #pragma unroll
       for (int q = 0; q < R; ++q) {
         const int rq = r + q * kCWarps;
@@ -525,6 +535,16 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
     const int w0r = w0 % cap;  // ring index of the window start; later keys wrap with one conditional subtract
     float* kb = S.k + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
     float* vb = S.v + (size_t)slot * S.slot_stride + (size_t)l * S.layer_stride + (size_t)kvh * cap * 128;
+    if (l == 0) {  // cos / sin of this unit's position(s): once per unit, not once per layer (precise sincosf is ~100 instructions)
+      if (cx.tid < rps * 64) {
+        const int rr = cx.tid >> 6, i = cx.tid & 63;
+        float sn, cs;
+        sincosf((float)(pos0 + rr) * S.inv_freq[i], &sn, &cs);
+        sm.rope[cx.tid * 2] = cs;
+        sm.rope[cx.tid * 2 + 1] = sn;
+      }
+      cbar();
+    }
     // (a) per-head RMSNorm + rotate-half RoPE of q (G warps) and k (1 warp), v copy (1 warp) for each of the rps rows
     if (cx.warp < rps * (G + 2)) {
       const int rr = cx.warp / (G + 2), role = cx.warp - rr * (G + 2);
@@ -539,12 +559,9 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
         const float inv = rsqrtf(ss * (1.0f / 128.0f) + S.eps);
         const float4 nw = __ldg(reinterpret_cast<const float4*>(role < G ? q_norm : k_norm) + lane);
         const float4 x = make_float4(a.x * inv * nw.x, a.y * inv * nw.y, a.z * inv * nw.z, a.w * inv * nw.w);
-        const float4 fr = __ldg(reinterpret_cast<const float4*>(S.inv_freq) + (lane & 15));
-        float4 sn, cs;
-        sincosf((float)pos * fr.x, &sn.x, &cs.x);
-        sincosf((float)pos * fr.y, &sn.y, &cs.y);
-        sincosf((float)pos * fr.z, &sn.z, &cs.z);
-        sincosf((float)pos * fr.w, &sn.w, &cs.w);
+        const float4* cs4 = reinterpret_cast<const float4*>(sm.rope + (rr * 64 + 4 * (lane & 15)) * 2);  // [freq][cos, sin]
+        const float4 t0 = cs4[0], t1 = cs4[1];
+        const float4 cs = make_float4(t0.x, t0.z, t1.x, t1.z), sn = make_float4(t0.y, t0.w, t1.y, t1.w);
         float4 y;  // partner dims (d ^ 64)
         y.x = __shfl_xor_sync(0xffffffffu, x.x, 16); y.y = __shfl_xor_sync(0xffffffffu, x.y, 16);
         y.z = __shfl_xor_sync(0xffffffffu, x.z, 16); y.w = __shfl_xor_sync(0xffffffffu, x.w, 16);
@@ -725,7 +742,6 @@ __device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, 
 // ------------------------------------------------------------------------------------------------ the frame loop
 // ONE copy of every phase body: the 16 units of a frame (15 code-predictor passes + the talker step) run through the same
 // loop over linear phases [mtp?] + layers x {qkv, o, gate|up, down} + head.
-enum LinKind { K_MTP = 0, K_QKV = 1, K_O = 2, K_GU = 3, K_DOWN = 4, K_HEAD = 5 };
 
 template <int FMT, int NS>
 __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid_constant__ MegaParams p) {
@@ -740,6 +756,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
   sm.empty = sm.full + p.n_ring;
   sm.dsc = reinterpret_cast<MegaLinear*>(smem + p.off_dsc);
   sm.hl = reinterpret_cast<float*>(smem + p.off_hl);
+  sm.rope = reinterpret_cast<float*>(smem + p.off_rope);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kDscVec = (int)(sizeof(MegaLinear) / 16);
   if (tid == 0) {
@@ -757,103 +774,83 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
   }
   Ctx cx;
   cx.slot = 0; cx.ring_ph = 0; cx.ph = 0; cx.fseq = 0; cx.tid = tid; cx.lane = lane; cx.warp = warp;
-  cx.trace = nullptr; cx.wait_full = 0;
+  cx.trace = nullptr; cx.wait_full = 0; cx.wait_poll = 0;
   if (p.trace != nullptr && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
     cx.trace = p.trace + (size_t)(blockIdx.x == 0 ? 0 : 1) * p.trace_stride;
   const int ns = p.n_slots;
   int cur = 0;  // which of the two descriptor slots holds the current linear
 
   for (int f = 0; f < p.n_frames; ++f) {
-    int li = 0;
     cx.fseq = (uint32_t)f + 1u;
     const bool last_frame = (f == p.n_frames - 1);
-    for (int u = 0; u < 16; ++u) {   // units 0..14: code-predictor pass u (Model/Qwen3Talker.swift:501-523); 15: talker step
-      const bool talker = (u == 15);
+    for (int li = 0; li < p.n_lin; ++li) {
+      const MegaLinear& L = sm.dsc[cur];
+      const int flags = L.flags;
+      const bool talker = (flags & MF_TALKER) != 0;
       const MegaStack& S = talker ? p.tk : p.cp;
-      ++cx.ph;                       // ---- sample phase (CTA 0): code_u from the logits of the previous unit
-      if (blockIdx.x == 0) {
-        if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
-        sample_phase(p, sm, cx, u, f == 0 && u == 0);
-        if (cx.trace) cx.trace[2] = clock64();
-        trace_close(cx);
-        cbar();
+      // next phase's descriptor: loaded now, parked in the other slot at the end of the phase (never on the critical path)
+      uint4 nd = make_uint4(0u, 0u, 0u, 0u);
+      if (tid < kDscVec) nd = __ldg(reinterpret_cast<const uint4*>(&p.lin[li + 1 < p.n_lin ? li + 1 : 0]) + tid);
+      if (flags & MF_UNIT_START) {  // ---- sample phase (CTA 0): code_u from the logits of the previous unit
+        ++cx.ph;
+        if (blockIdx.x == 0) {
+          if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
+          sample_phase(p, sm, cx, L.uidx, f == 0 && li == 0);
+          if (cx.trace) cx.trace[2] = clock64();
+          trace_close(cx);
+          cbar();
+        }
       }
-      const int rps = (u == 0) ? 2 : 1;
-      const int m = ns * rps;
-      const int mtp = (!talker && p.has_mtp) ? 1 : 0;  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
-      const int layers = S.layers, hidden = S.hidden, inter = S.inter, heads = S.heads;
-      const int nj = mtp + 4 * layers + 1;
-      const int first_kind = talker ? IN_TALKER : (u == 0 ? IN_CP0 : IN_CPG);
+      ++cx.ph;                       // ---- linear phase
+      const int rps = (flags & MF_ROWS2) ? 2 : 1;
+      const int rows = (flags & MF_HEAD) ? ns : ns * rps;
+      const bool head0 = (flags & (MF_HEAD | MF_TALKER)) == (MF_HEAD | MF_TALKER);
+      InArgs in;
+      in.kind = L.in_kind; in.pass = L.pass; in.nsplit = S.nsplit; in.heads = S.heads;
+      const int out_sel = L.out_sel;
+      u64* out = out_sel == 0 ? p.ex_x : (out_sel == 1 ? p.ex_qkv : (out_sel == 2 ? p.ex_act : p.ex_logit));
+      const int ld_out = out_sel == 0 ? p.ld_x : (out_sel == 1 ? p.ld_qkv : (out_sel == 2 ? p.ld_act : p.ld_logit));
+      float* plain_out = (head0 && last_frame) ? p.logits0 : nullptr;  // the next launch (or the graph path) starts from plain logits
+      const float* norm_w = L.norm_w;
       const float eps = S.eps;
-      for (int j = 0; j < nj; ++j) {
-        ++cx.ph;                     // ---- linear phase
-        const MegaLinear& L = sm.dsc[cur];
-        ++li;
-        // next phase's descriptor: loaded now, parked in the other slot at the end of the phase (never on the critical path)
-        uint4 nd = make_uint4(0u, 0u, 0u, 0u);
-        const int lnext = li < p.n_lin ? li : 0;
-        if (tid < kDscVec) nd = __ldg(reinterpret_cast<const uint4*>(&p.lin[lnext]) + tid);
-        int kind, l = 0;
-        if (j < mtp) kind = K_MTP;
-        else if (j == nj - 1) kind = K_HEAD;
-        else { l = (j - mtp) >> 2; kind = K_QKV + ((j - mtp) & 3); }
-        InArgs in{};
-        in.pass = u; in.nsplit = S.nsplit; in.heads = heads;
-        int rows = m, K = hidden, epi = E_STORE, ld_out = p.ld_x;
-        u64* out = p.ex_x;
-        float* plain_out = nullptr;
-        bool keep_raw = false;
-        switch (kind) {
-          case K_MTP: in.kind = first_kind; K = p.H; break;
-          case K_QKV: in.kind = (l == 0 && !mtp) ? first_kind : IN_GX; keep_raw = true; out = p.ex_qkv; ld_out = p.ld_qkv; break;
-          case K_O: in.kind = IN_ATTN; K = heads * 128; epi = E_ADD_RAW; break;
-          case K_GU: in.kind = IN_GX; keep_raw = true; epi = E_SWIGLU; out = p.ex_act; ld_out = p.ld_act; break;
-          case K_DOWN: in.kind = IN_ACT; K = inter; epi = E_ADD_RAW; break;
-          default:  // K_HEAD: final norm + lm_head[u] on the last position of each slot / codec_head (Qwen3CodePredictor.swift:207-212)
-            in.kind = talker ? IN_GX : IN_GX_LAST; in.pass = rps; rows = ns; keep_raw = talker;
-            out = p.ex_logit; ld_out = p.ld_logit;
-            if (talker && last_frame) plain_out = p.logits0;  // the next launch (or the graph path) starts from plain logits
-            break;
-        }
-        const float* norm_w = L.norm_w;
-        if (cx.trace) { cx.trace[0] = clock64(); cx.wait_full = 0; }
-        stage_rows<FMT>(p, sm, cx, in, rows, K, norm_w, keep_raw);
-        if (cx.trace) cx.trace[1] = clock64();
-        if (kind == K_HEAD && talker) {  // h_last = final norm of the talker step: next frame's pass-0 input, kept per CTA
-          for (int s = 0; s < ns; ++s) {
-            float ss = 0.f;
-            for (int w = 0; w < kCWarps; ++w) ss += sm.red[s * 16 + w];
-            const float inv = rsqrtf(ss / (float)p.H + eps);
-            for (int i = tid; i < p.H; i += kCons) {
-              const float hv = sm.xraw[s * p.raw_ld + i] * inv * norm_w[i];
-              sm.hl[s * p.raw_ld + i] = hv;
-              if (last_frame && blockIdx.x == 0) p.hlast[(size_t)s * p.H + i] = hv;
-            }
+      if (cx.trace) { cx.trace[0] = clock64(); cx.wait_full = 0; cx.wait_poll = 0; cx.trace[3] = cx.trace[4] = 0; }
+      stage_rows<FMT>(p, sm, cx, in, rows, L.in, norm_w, (flags & MF_KEEP_RAW) != 0);
+      if (cx.trace) cx.trace[1] = clock64();
+      if (head0) {  // h_last = final norm of the talker step: next frame's pass-0 input, kept per CTA
+        for (int s = 0; s < ns; ++s) {
+          float ss = 0.f;
+          for (int w = 0; w < kCWarps; ++w) ss += sm.red[s * 16 + w];
+          const float inv = rsqrtf(ss / (float)p.H + eps);
+          for (int i = tid; i < p.H; i += kCons) {
+            const float hv = sm.xraw[s * p.raw_ld + i] * inv * norm_w[i];
+            sm.hl[s * p.raw_ld + i] = hv;
+            if (last_frame && blockIdx.x == 0) p.hlast[(size_t)s * p.H + i] = hv;
           }
         }
-        if (rps == 2 && kind != K_HEAD) gemv_rows<FMT, M, 1>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out, plain_out, p.V);
-        else gemv_rows<FMT, NS, 2>(p, sm, cx, L, rows, norm_w != nullptr, eps, epi, out, ld_out, plain_out, p.V);
-        if (cx.trace) { cx.trace[2] = clock64(); cx.trace[6] = cx.wait_full; cx.trace[7] = kind; }
-        if (kind == K_HEAD && talker && blockIdx.x == 0 && tid == 0) step_advance(p);
-        const float* q_norm = L.q_norm;
-        const float* k_norm = L.k_norm;
-        if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[cur ^ 1])[tid] = nd;
-        cur ^= 1;
-        trace_close(cx);
-        cbar();  // xs / xraw / descriptors are reused by the next phase
-        if (kind == K_QKV) {
-          ++cx.ph;                   // ---- attention phase (participants: one CTA per (slot, kv head, split))
-          if (talker && l == 0 && blockIdx.x == 0 && tid == 0) finalize_bookkeeping(p);
-          const int G = heads / S.kv_heads;
-          if (blockIdx.x < (unsigned)(ns * S.kv_heads * S.nsplit)) {
-            if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
-            const int cp_pos0 = u == 0 ? 0 : u + 1;
-            if (G == 2) attn_phase<2>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-            else if (G == 1) attn_phase<1>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-            else attn_phase<4>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, l);
-            if (cx.trace) cx.trace[2] = clock64();
-            trace_close(cx);
-          }
+      }
+      if (rps == 2 && !(flags & MF_HEAD)) gemv_rows<FMT, M, 1>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+      else gemv_rows<FMT, NS, 2>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+      if (cx.trace) { cx.trace[2] = clock64(); cx.trace[6] = cx.wait_full; cx.trace[7] = L.tkind + (cx.wait_poll << 8); }
+      if (head0 && blockIdx.x == 0 && tid == 0) step_advance(p);
+      const float* q_norm = L.q_norm;
+      const float* k_norm = L.k_norm;
+      const int layer = L.layer, unit = L.uidx;
+      if (tid < kDscVec) reinterpret_cast<uint4*>(&sm.dsc[cur ^ 1])[tid] = nd;
+      cur ^= 1;
+      trace_close(cx);
+      cbar();  // xs / xraw / descriptors are reused by the next phase
+      if (flags & MF_ATTN) {
+        ++cx.ph;                     // ---- attention phase (participants: one CTA per (slot, kv head, split))
+        if ((flags & MF_FINALIZE) && blockIdx.x == 0 && tid == 0) finalize_bookkeeping(p);
+        if (blockIdx.x < (unsigned)(ns * S.kv_heads * S.nsplit)) {
+          if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
+          const int G = S.heads / S.kv_heads;
+          const int cp_pos0 = unit == 0 ? 0 : unit + 1;
+          if (G == 2) attn_phase<2>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, layer);
+          else if (G == 1) attn_phase<1>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, layer);
+          else attn_phase<4>(p, sm, cx, S, q_norm, k_norm, rps, talker, cp_pos0, layer);
+          if (cx.trace) cx.trace[2] = clock64();
+          trace_close(cx);
         }
       }
     }

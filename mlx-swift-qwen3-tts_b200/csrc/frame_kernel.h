@@ -27,7 +27,25 @@ struct MegaLinear {       // one QuantizedLayerFactory.linear leaf in execution 
   const float* norm_w;    // RMSNorm weight fused into this linear's prologue (qkv, gate|up, heads), or null
   const float* q_norm;    // qkv entries: per-head norms of the attention phase that follows
   const float* k_norm;
-  int pad_[2];            // sizeof == 112: the kernel moves descriptors as 16-byte vectors
+  // ---- the phase this linear runs in, precomputed so the kernel's loop top is a handful of shared-memory reads
+  int in_kind;            // InKind of the staged rows
+  int pass;               // code-predictor pass / unit index 0..15 (15 = talker); rows per slot for the head's IN_GX_LAST
+  int epi;                // EpiKind
+  int out_sel;            // 0 residual x, 1 qkv, 2 SwiGLU activations, 3 logits
+  int flags;              // MegaFlags
+  int layer;
+  int uidx;               // 0..14 code-predictor pass, 15 talker step
+  int tkind;              // trace label: 0 mtp, 1 qkv, 2 o, 3 gate|up, 4 down, 5 head
+  int pad_[2];            // sizeof == 144: the kernel moves descriptors as 16-byte vectors
+};
+enum MegaFlags {
+  MF_UNIT_START = 1,      // first linear of a unit: the code of this unit is sampled before it
+  MF_ATTN = 2,            // qkv: an attention phase follows
+  MF_TALKER = 4,
+  MF_HEAD = 8,            // lm_head / codec_head: rows = one per slot
+  MF_KEEP_RAW = 16,       // staged rows are the residual of the following o / down projection
+  MF_ROWS2 = 32,          // two rows per slot (code-predictor pass 0)
+  MF_FINALIZE = 64        // talker layer 0: CTA 0 records the finished frame before the attention phase
 };
 static_assert(sizeof(MegaLinear) % 16 == 0, "MegaLinear must be a whole number of 16-byte vectors");
 
@@ -71,7 +89,7 @@ struct MegaParams {
   int n_frames, window, eos_id, pad_id;
   // shared-memory plan (bytes from the 1024-aligned base)
   int slot_bytes, n_ring;
-  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc, off_hl;
+  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc, off_hl, off_rope;
   int raw_ld;               // floats per row of the raw residual copy
   long long* trace;         // diagnostics: [2 CTAs][trace_stride] cycle stamps, 8 per phase (null = off)
   int trace_stride;

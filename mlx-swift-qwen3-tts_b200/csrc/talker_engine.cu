@@ -143,20 +143,35 @@ void TalkerEngine::build_mega_plan() {
   std::vector<const Linear*> order;
   std::vector<int> swiglu;
   struct Norms { const float *norm_w, *q_norm, *k_norm; };
+  struct PhaseInfo { int in_kind, pass, epi, out_sel, flags, layer, unit, tkind; };
   std::vector<Norms> norms;
-  auto push = [&](const Linear& L, bool sw, const float* nw = nullptr, const float* qn = nullptr, const float* kn = nullptr) {
-    order.push_back(&L); swiglu.push_back(sw ? 1 : 0); norms.push_back({nw, qn, kn});
+  std::vector<PhaseInfo> phase;
+  // InKind / EpiKind values of frame_kernel.cu
+  enum { IN_GX = 0, IN_GX_LAST, IN_CP0, IN_CPG, IN_TALKER, IN_ATTN, IN_ACT };
+  enum { E_STORE = 0, E_ADD_RAW = 1, E_SWIGLU = 2 };
+  auto push = [&](const Linear& L, bool sw, PhaseInfo ph, const float* nw = nullptr, const float* qn = nullptr, const float* kn = nullptr) {
+    order.push_back(&L); swiglu.push_back(sw ? 1 : 0); norms.push_back({nw, qn, kn}); phase.push_back(ph);
   };
-  auto push_layer = [&](const LayerWeights& l) {
-    push(l.qkv, false, l.in_norm, l.q_norm, l.k_norm); push(l.o, false); push(l.gate_up, true, l.post_norm); push(l.down, false);
-  };
-  for (int g = 0; g < 15; ++g) {
-    if (w_.has_mtp) push(w_.small_to_mtp, false);
-    for (int l = 0; l < P.layers; ++l) push_layer(P.layer[l]);
-    push(w_.lm_head[g], false, P.final_norm);
+  for (int u = 0; u < 16; ++u) {  // units 0..14: code-predictor passes, 15: the talker step
+    const bool talker = (u == 15);
+    const StackWeights& S = talker ? T : P;
+    const int base = (talker ? MF_TALKER : 0) | (u == 0 ? MF_ROWS2 : 0);
+    const int first_kind = talker ? IN_TALKER : (u == 0 ? IN_CP0 : IN_CPG);
+    bool first = true;
+    auto flags_of = [&](int extra) { const int f = base | extra | (first ? MF_UNIT_START : 0); first = false; return f; };
+    const bool mtp = !talker && w_.has_mtp;
+    if (mtp) push(w_.small_to_mtp, false, {first_kind, u, E_STORE, 0, flags_of(0), 0, u, 0});
+    for (int l = 0; l < S.layers; ++l) {
+      const LayerWeights& lw = S.layer[l];
+      const int qkv_in = (l == 0 && !mtp) ? first_kind : IN_GX;
+      push(lw.qkv, false, {qkv_in, u, E_STORE, 1, flags_of(MF_ATTN | MF_KEEP_RAW | ((talker && l == 0) ? MF_FINALIZE : 0)), l, u, 1}, lw.in_norm, lw.q_norm, lw.k_norm);
+      push(lw.o, false, {IN_ATTN, u, E_ADD_RAW, 0, flags_of(0), l, u, 2});
+      push(lw.gate_up, true, {IN_GX, u, E_SWIGLU, 2, flags_of(MF_KEEP_RAW), l, u, 3}, lw.post_norm);
+      push(lw.down, false, {IN_ACT, u, E_ADD_RAW, 0, flags_of(0), l, u, 4});
+    }
+    if (talker) push(w_.codec_head, false, {IN_GX, u, E_STORE, 3, flags_of(MF_HEAD | MF_KEEP_RAW), 0, u, 5}, T.final_norm);
+    else push(w_.lm_head[u], false, {IN_GX_LAST, u == 0 ? 2 : 1, E_STORE, 3, flags_of(MF_HEAD), 0, u, 5}, P.final_norm);
   }
-  for (int l = 0; l < T.layers; ++l) push_layer(T.layer[l]);
-  push(w_.codec_head, false, T.final_norm);
   // one weight format for the whole frame
   const Linear& L0 = *order[0];
   int fmt = -1;
@@ -188,6 +203,8 @@ void TalkerEngine::build_mega_plan() {
     if (u > 16 || m.out_eff % u != 0) return;
     m.unit = u;
     m.norm_w = norms[i].norm_w; m.q_norm = norms[i].q_norm; m.k_norm = norms[i].k_norm;
+    m.in_kind = phase[i].in_kind; m.pass = phase[i].pass; m.epi = phase[i].epi; m.out_sel = phase[i].out_sel; m.flags = phase[i].flags;
+    m.layer = phase[i].layer; m.uidx = phase[i].unit; m.tkind = phase[i].tkind;
     need_slot = std::max(need_slot, u * m.nsub * (m.row_bytes + 2 * m.srow_bytes));
     kmax = std::max(kmax, L.in);
     lin.push_back(m);
@@ -210,7 +227,7 @@ void TalkerEngine::build_mega_plan() {
   const int xraw_bytes = up(MT * hmax * 4, 128);
   const int red_bytes = up(MT * 16 * 4, 128);
   const int hl_bytes = up(NS * hmax * 4, 128);
-  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 256 + hl_bytes + 128;
+  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 512 + hl_bytes + 1024 + 128;
   const int budget = 226 * 1024;
   int n_ring = std::min(8, (budget - fixed) / slot_bytes);
   if (n_ring < 2) return;
@@ -222,9 +239,11 @@ void TalkerEngine::build_mega_plan() {
   p.off_red = p.off_xraw + xraw_bytes;
   p.off_bar = p.off_red + red_bytes;
   p.off_dsc = p.off_bar + 256;
-  p.off_hl = p.off_dsc + 256;
+  static_assert(2 * sizeof(MegaLinear) <= 512, "descriptor slots");
+  p.off_hl = p.off_dsc + 512;
   p.raw_ld = hmax;
-  mega_.smem = (size_t)p.off_hl + hl_bytes + 128;
+  p.off_rope = p.off_hl + hl_bytes;
+  mega_.smem = (size_t)p.off_rope + 1024 + 128;
   mega_.fmt = fmt; mega_.G_cp = G_cp; mega_.G_tk = G_tk;
   int dev = 0, sms = 0, coop = 0;
   Q3_CUDA(cudaGetDevice(&dev));

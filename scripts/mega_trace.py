@@ -18,17 +18,26 @@ tm = eng.timing()
 print(json.dumps({"frames": len(fr), "device_ms": tm.device_ms, "prefill_ms": tm.prefill_ms, "ms_per_frame": (tm.device_ms - tm.prefill_ms) / max(1, len(fr))}))
 t = np.fromfile(path, dtype=np.int64).reshape(2, -1, 8)
 names = {0: "mtp", 1: "qkv", 2: "o", 3: "gate_up", 4: "down", 5: "head", 10: "attention", 20: "sample"}
+us = lambda x: x / 1.965e3
 for cta in range(2):
     a = t[cta]
     n = int((a[:, 5] != 0).sum())
     a = a[:n]
-    print(f"--- CTA {'0' if cta == 0 else 'grid/2'}: {n} phases, total {(a[-1,5]-a[0,0])/1.965e3:.1f} us at 1.965 GHz")
+    kind = a[:, 7] & 0xFF
+    poll = a[:, 7] >> 8
+    print(f"--- CTA {'0' if cta == 0 else 'grid/2'}: {n} phases, total {us(a[-1,5]-a[0,0]):.1f} us at 1.965 GHz (thread 0 = warp 0)")
     gap = np.zeros(n); gap[1:] = a[1:, 0] - a[:-1, 5]
     for k, name in names.items():
-        m = a[:, 7] == k
+        m = kind == k
         if not m.any():
             continue
-        f = lambda x: f"{x[m].mean() / 1.965e3:7.2f}"
-        print(f"{name:10s} n={int(m.sum()):5d}  stage {f(a[:,1]-a[:,0])}  body {f(a[:,2]-a[:,1])}  (wait_full {f(a[:,6])})  to-barrier {f(a[:,3]-a[:,2])}  fence+atomic {f(a[:,4]-a[:,3])}"
-              f"  spin {f(a[:,5]-a[:,4])}  gap-before {f(gap)}  total {f(a[:,5]-a[:,0]+gap)} us")
+        f = lambda x: f"{us(x[m].mean()):6.2f}"
+        lin = k < 10
+        line = f"{name:10s} n={int(m.sum()):5d}  gap {f(gap)}  stage {f(a[:,1]-a[:,0])} (poll {f(poll)})  body {f(a[:,2]-a[:,1])}"
+        if lin:
+            mm = m & (a[:, 3] != 0) & (a[:, 4] != 0)
+            g = lambda x: f"{us(x[mm].mean()):6.2f}" if mm.any() else "   n/a"
+            line += f" [pre {g(a[:,3]-a[:,1])} (mbar {f(a[:,6])}) math {g(a[:,4]-a[:,3])} epilogue {g(a[:,2]-a[:,4])}]"
+        line += f"  tail {f(a[:,5]-a[:,2])}  total {f(a[:,5]-a[:,0]+gap)} us"
+        print(line)
 eng.close()
