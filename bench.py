@@ -92,7 +92,8 @@ def peaks():
 # --------------------------------------------------------------------------------------------------- CPU restatement arm
 def cpu_sample(ckpt_dir, frames, reps, warmup):
     """Times the CPU restatement of the reference graph (oracle/, torch-CPU fp32, all host threads) on a bounded sample of
-    the same workload: one utterance, `frames` frames of the stream-variant loop + one codec decode of those frames."""
+    the same workload: one utterance, `frames` frames of the stream-variant loop + one codec decode of those frames.
+    Warm-up runs are 3 frames long (they only page the weights in), timed runs `frames` long."""
     import torch
 
     from oracle import codec as ocodec, pipeline as opipe, talker as otalker
@@ -105,8 +106,8 @@ def cpu_sample(ckpt_dir, frames, reps, warmup):
     for it in range(warmup + reps):
         ids = rng.integers(0, 150000, size=20).tolist()
         t0 = time.perf_counter()
-        fr = orc.generate_codes(otalker.Request(text_ids=ids, speaker_id=2861, temperature=0.85, max_tokens=frames, seed=it, stream_variant=True),
-                                filter_invalid=False)
+        fr = orc.generate_codes(otalker.Request(text_ids=ids, speaker_id=2861, temperature=0.85, max_tokens=frames if it >= warmup else 3, seed=it,
+                                                stream_variant=True), filter_invalid=False)
         valid = [f for f in fr if 0 <= f[0] < 2048] or [[0] * 16]
         opipe.decode_whole(cdc, valid)
         dt = time.perf_counter() - t0
@@ -128,7 +129,7 @@ def main():
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--model", default="0.6b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=3)
+    ap.add_argument("--cpu-frames", type=int, default=60)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -149,13 +150,13 @@ def main():
         if rank != 0:
             return
         checkpoint.write_checkpoint(ckpt_dir, a.model, bits=a.bits, dtype="bf16", seed=0)
-        v, sec = cpu_sample(ckpt_dir, a.cpu_frames, a.steps, min(a.warmup, 1))
+        v, sec = cpu_sample(ckpt_dir, a.cpu_frames, max(1, a.steps), min(a.warmup, 1))
         cores = os.cpu_count() or 1
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"1 utterance x {a.cpu_frames} frames (stream loop) + 1 codec decode per step; CPU restatement of the reference graph (torch fp32), not MLX"},
+                                 "sample": f"1 utterance x {a.cpu_frames} frames (stream loop, batch 1 = the reference's only mode) + 1 whole-sequence codec decode per step; CPU restatement of the reference graph (torch fp32, all host threads), not MLX"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -223,8 +224,15 @@ def main():
         iters = 20
         ms, n, nbytes = eng.profile_linear(0, a.batch, iters)
         ach = nbytes * iters / (ms * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "linear_kernel (dequant-fused GEMV / small-M GEMM), one talker decode step, m = batch",
-                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None, "peak_source": src,
+        kname = ("tc_gemm_kernel (tcgen05 / TMEM, fp16 dense weight copies), the linears of one talker decode step at m = batch rows"
+                 if a.batch >= 16 else "linear_kernel (dequant-fused GEMV), the linears of one talker decode step at m = batch rows")
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch from the committed ncu --set full capture
+        if os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic = tj.get("tc_gemm_m64" if a.batch >= 16 else "linear_m1", {}).get("dram_bytes_per_launch")
+        roof = {"bound": "hbm", "kernel": kname,
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": src,
                 "launches_timed": n, "algorithmic_bytes_per_launch": nbytes / (n / iters), "avg_launch_us": ms * 1e3 / n}
         ms1, n1, nb1 = eng.profile_linear(0, 1, iters)
         msc, nc, nbc = eng.profile_linear(1, 1, iters)
@@ -235,15 +243,16 @@ def main():
         e1.generate_codes(r1)
         t1 = e1.timing()
         msf = (t1.talker_ms - t1.prefill_ms) / max(1, t1.frames)
-        lat = {"batch1_ms_per_frame": msf, "batch1_rtfx": 80.0 / msf, "batch1_prefill_ms": t1.prefill_ms,
+        lat = {"batch1_path": "persistent frame kernel (1 cooperative launch per 8 frames)" if t1.persistent_launches else "CUDA graph of per-op kernels",
+               "batch1_ms_per_frame": msf, "batch1_rtfx": 80.0 / msf, "batch1_prefill_ms": t1.prefill_ms,
                "batch1_frame_roofline_frac": (t1.weight_bytes_per_frame / (msf * 1e-3) / 1e9) / hbm,
                "batch1_linear_gbs_talker_step": nb1 * iters / (ms1 * 1e-3) / 1e9, "batch1_linear_gbs_cp_pass_L2": nbc * iters / (msc * 1e-3) / 1e9,
                "time_to_first_chunk_ms": t1.prefill_ms + 18 * msf}
         e1.close()
         if world == 1 and not a.no_cpu_baseline:
-            v, sec = cpu_sample(ckpt_dir, a.cpu_frames, 2, 1)
+            v, sec = cpu_sample(ckpt_dir, a.cpu_frames, 1, 1)
             cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": f"1 utterance x {a.cpu_frames} frames (stream loop) + 1 codec decode, 2 reps after 1 warm-up ({sec:.1f} s each); CPU restatement of the reference graph (torch fp32), not MLX"}
+                        "sample": f"1 utterance x {a.cpu_frames} frames (stream loop, batch 1 = the reference's only mode) + 1 whole-sequence codec decode, 1 timed run of {sec:.1f} s after a 3-frame warm-up; CPU restatement of the reference graph (torch fp32, all host threads), not MLX"}
 
     if rank == 0:
         codec_sps = samples / max(1e-9, sum(r["decode"] for r in res))
