@@ -43,6 +43,29 @@ struct Error : std::runtime_error {
 
 inline size_t dtype_size(int dt) { return dt == Q3TTS_F32 ? 4 : 2; }
 
+// Programmatic dependent launch (PDL): a kernel launched with `pdl` may start (prologue, weight prefetch) while its
+// predecessor in the stream is still draining; it calls pdl_wait() before touching anything the predecessor wrote.  Kernels
+// call pdl_launch_dependents() early so their successor can be scheduled.  Both instructions are no-ops without the attribute.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_kernel_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  Q3_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("Q3TTS_PDL"); return !(e && atoi(e) == 0); }();
+  return on;
+}
+#endif
+
 // Counts every kernel this library launches (reported as q3tts_timing.kernel_launches / bench gpu_launches).
 struct LaunchCounter {
   int64_t n = 0;

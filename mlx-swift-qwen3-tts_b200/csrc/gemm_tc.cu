@@ -130,6 +130,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int n0 = blockIdx.y * p.bn;
   const int num_kb = p.ntap * p.kb_per_tap;
 
+  pdl_launch_dependents();  // the next kernel of the stream may start its prologue / weight prefetch now
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
@@ -147,14 +148,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
+      // Weights never depend on the previous kernel: the first ring-full of B tiles is requested BEFORE the programmatic
+      // dependency is resolved, so the weight stream overlaps the predecessor's tail; activations (A) follow the wait.
+      // Every CTA of a column of the grid reads the SAME activation tiles: walking K from a per-CTA offset keeps the CTAs
+      // off each other's L2 lines (same-address storms serialise in one L2 slice and multiply the TMA latency).
+      const int rot = (int)((blockIdx.y * 5u + blockIdx.x * 3u) % (unsigned)num_kb);
+      const int pre = num_kb < p.stages ? num_kb : p.stages;
+      for (int kb = 0; kb < pre; ++kb) {
+        mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
+        const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
+        const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
+        tma_load_2d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0);
+      }
+      pdl_wait();
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-        const int tap = kb / p.kb_per_tap, c0 = (kb - tap * p.kb_per_tap) * kBlockK;
+        const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
+        const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
         const int shift = (p.ntap - 1 - tap) * p.dil;
+        if (kb >= pre) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+          tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
+        }
         tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
-        tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
       }
     }
   } else if (warp == 1) {
@@ -181,6 +198,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = t0 + row;
     const bool row_ok = t < p.T;
     const size_t m = (size_t)bidx * p.T + t;
+    pdl_wait();  // residual / bias-free inputs of the epilogue were written by earlier kernels
     mbar_wait(tmem_full, 0);
     tc_fence_after();
     for (int c = 0; c < p.bn; c += 32) {
@@ -350,12 +368,14 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 64 * 8;
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
   dim3 grid((unsigned)(g.Bt * p.tiles_per_batch), (unsigned)((g.N + p.bn - 1) / p.bn));
-  tc_gemm_kernel<<<grid, kThreads, smem, c.stream>>>(ma, mb, p);
+  launch_kernel_pdl(tc_gemm_kernel, grid, dim3(kThreads), smem, c.stream, pdl_enabled(), ma, mb, p);
   c.tick();
 }
 
 // ---------------------------------------------------------------------------------------------- small fp16 producers
 __global__ void f32_to_f16_kernel(const float* __restrict__ x, size_t n4, __half* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
     __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
@@ -369,13 +389,15 @@ void launch_f32_to_f16(const LaunchCtx& c, const float* x, size_t n, __half* y) 
   Q3_CHECK(n % 4 == 0, Q3TTS_ERR_INVALID_ARG, "f32_to_f16: length must be a multiple of 4");
   const size_t n4 = n / 4;
   const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 32);
-  f32_to_f16_kernel<<<blocks, 256, 0, c.stream>>>(x, n4, y);
+  launch_kernel_pdl(f32_to_f16_kernel, dim3(blocks), dim3(256), 0, c.stream, pdl_enabled(), x, n4, y);
   c.tick();
 }
 
 __global__ void __launch_bounds__(256) rmsnorm_f16_kernel(const float* __restrict__ x, int ldx, int dim, const float* __restrict__ w, float eps,
                                                           __half* __restrict__ y, int ldy) {
   __shared__ float red[8];
+  pdl_launch_dependents();
+  pdl_wait();
   const float* xr = x + (size_t)blockIdx.x * ldx;
   float ss = 0.f;
   for (int i = threadIdx.x; i < dim; i += 256) { const float v = xr[i]; ss += v * v; }
@@ -392,7 +414,7 @@ __global__ void __launch_bounds__(256) rmsnorm_f16_kernel(const float* __restric
 }
 void launch_rmsnorm_f16(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, __half* y, int ldy) {
   if (m <= 0) return;
-  rmsnorm_f16_kernel<<<m, 256, 0, c.stream>>>(x, ldx, dim, w, eps, y, ldy);
+  launch_kernel_pdl(rmsnorm_f16_kernel, dim3(m), dim3(256), 0, c.stream, pdl_enabled(), x, ldx, dim, w, eps, y, ldy);
   c.tick();
 }
 

@@ -429,6 +429,8 @@ __global__ void __launch_bounds__(128) rope_attention_kernel(const float* __rest
   float* vcur = kcur + 128;       // [128]
   float* sc = vcur + 128;         // [G][S]
   __shared__ float red_sum[G];
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = row_slot[row], pos = row_pos[row];
   const int w0 = win_start ? win_start[slot] : 0;
@@ -523,9 +525,10 @@ static void launch_rope_attention_t(const LaunchCtx& c, const float* qkv, int ld
   const size_t smem = (size_t)(G * 128 + 256 + G * kv.capacity) * sizeof(float);
   Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
   dim3 grid(m, kv_heads);
-  if (G == 1) rope_attention_kernel<1, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
-  else if (G == 2) rope_attention_kernel<2, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
-  else if (G == 4) rope_attention_kernel<4, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  const bool pdl = pdl_enabled();
+  if (G == 1) launch_kernel_pdl(rope_attention_kernel<1, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  else if (G == 2) launch_kernel_pdl(rope_attention_kernel<2, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
+  else if (G == 4) launch_kernel_pdl(rope_attention_kernel<4, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
   else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
   c.tick();
 }
