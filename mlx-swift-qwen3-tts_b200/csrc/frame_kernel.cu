@@ -116,6 +116,8 @@ struct Sm {   // byte offsets into smem (from MegaParams) resolved once
   MegaLinear* dsc;  // [2] descriptor of the current / next linear
   float* hl;        // [slots][raw_ld] h_last of the previous talker step (every CTA keeps its own copy)
   float* rope;      // [slots][2 rows][64 freqs][cos, sin] of the current unit's positions
+  __half* xh;       // tensor-core path: fp16 activation columns, permuted k (aliases xs)
+  float* part;      // tensor-core path: partial [16 x 8] tiles of the K slices
 };
 
 struct Slice { int r0, rows, rch, nch; };
@@ -505,6 +507,189 @@ __device__ __forceinline__ void gemv_rows(const MegaParams& p, const Sm& sm, Ctx
   }
 }
 
+// ------------------------------------------------------------------------------------------------ tensor-core GEMV (packed formats)
+// The packed 4/8-bit linears run on mma.sync.m16n8k16 (fp16 x fp16 -> fp32): 16 weight rows are the M side of the tile, up
+// to 8 activation rows (slots x rows-per-slot) are the N side, so several utterances cost the same issue slots as one.
+// Integer codes go to fp16 through the 0x6400 exponent trick (shift + LOP3 give 1024 + q for a PAIR of values, one exact
+// HSUB2 removes the 1024 — leaving it in costs the accumulator seven bits); the group scale / bias are applied once per
+// 64-wide group to the fp32 accumulator:  s * sum(q x) + b * sum(x)  =  s * C + b * sum(x).
+// K is split across the warps (whole groups), partial tiles meet in shared memory.  Within a block of 32 k the activations
+// are stored permuted (k -> (k % 4) * 8 + (k / 16) * 4 + (k % 16) / 4) so that the pair of nibbles (t, t + 4) a thread
+// peels off a packed word lines up with the (b0, b1) fragment it reads with one 128-bit load.
+__device__ __forceinline__ uint32_t hsub2_u32(uint32_t a, uint32_t b) {
+  uint32_t d;
+  asm("sub.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// Stage `m` activation rows as fp16 columns of the B operand (permuted k), their per-group sums, the raw fp32 residual copy
+// and sum(x^2) per row.
+__device__ __forceinline__ void stage_rows_mma(const MegaParams& p, const Sm& sm, const Ctx& cx, const InArgs& in, int m, int K, int gshift,
+                                               const float* norm_w, bool keep_raw) {
+  const int in4 = K >> 2;
+  const int ngroups = K >> gshift;
+  const int lanes_per_group = 1 << (gshift - 2);  // float4 chunks per scale group (16 for group 64)
+  for (int mi = 0; mi < m; ++mi) {
+    float ss = 0.f;
+    __half* xcol = sm.xh + (size_t)mi * p.xh_stride;
+    for (int f0 = 0; f0 < in4; f0 += kCons) {
+      const int f = f0 + cx.tid;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      float s4 = 0.f;
+      if (f < in4) {
+        float4 nw = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (norm_w != nullptr) nw = __ldg(reinterpret_cast<const float4*>(norm_w) + f);  // in flight with the poll below
+        const long long tp0 = cx.trace ? clock64() : 0;
+        v = load_in(p, cx, sm.hl, in, mi, f);
+        if (cx.trace) const_cast<Ctx&>(cx).wait_poll += clock64() - tp0;
+        ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        if (keep_raw) reinterpret_cast<float4*>(sm.xraw + mi * p.raw_ld)[f] = v;
+        v.x *= nw.x; v.y *= nw.y; v.z *= nw.z; v.w *= nw.w;
+        // x = hi + lo, both fp16: column mi carries hi, column mi + 4 carries lo, ONE MMA multiplies both (fp32-grade products)
+        const __half h0 = __float2half_rn(v.x), h1 = __float2half_rn(v.y), h2 = __float2half_rn(v.z), h3 = __float2half_rn(v.w);
+        const __half l0 = __float2half_rn(v.x - __half2float(h0)), l1 = __float2half_rn(v.y - __half2float(h1));
+        const __half l2 = __float2half_rn(v.z - __half2float(h2)), l3 = __float2half_rn(v.w - __half2float(h3));
+        s4 = (v.x + v.y) + (v.z + v.w);
+        // k = 4f + i  ->  block 32: (k % 4) * 8 + (k / 16 % 2) * 4 + (k % 16) / 4
+        const int blk = f >> 3, fin = f & 7;
+        __half* dst = xcol + blk * 32 + (fin >> 2) * 4 + (fin & 3);
+        dst[0] = h0; dst[8] = h1; dst[16] = h2; dst[24] = h3;
+        __half* dlo = dst + (size_t)4 * p.xh_stride;
+        dlo[0] = l0; dlo[8] = l1; dlo[16] = l2; dlo[24] = l3;
+      }
+      // per-group sums: the float4 chunks of one group sit in consecutive lanes
+      for (int o = 1; o < lanes_per_group && o < 32; o <<= 1) s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+      if (f < in4 && (cx.tid & (lanes_per_group - 1)) == 0) sm.xsum[mi * ngroups + (f >> (gshift - 2))] = s4;
+    }
+    if (norm_w != nullptr) {
+      ss = warp_sum(ss);
+      if (cx.lane == 0) sm.red[mi * 16 + cx.warp] = ss;
+    }
+  }
+  cbar();
+}
+
+template <int FMT>
+__device__ __forceinline__ void gemv_mma(const MegaParams& p, const Sm& sm, Ctx& cx, const MegaLinear& L, int m, bool has_norm, float eps, int epi,
+                                         u64* out, int ld_out, float* plain_out, int plain_ld) {
+  const int K = L.in;
+  const int row_bytes = L.row_bytes, srow_bytes = L.srow_bytes, nsub = L.nsub, sdt = L.sdt, gshift = L.group_shift;
+  const int ngroups = K >> gshift;
+  const int steps = 1 << (gshift - 5);  // 32-wide steps per group
+  const Slice s = slice_of(L);
+  const int g = cx.lane >> 2, t = cx.lane & 3;
+  float* part = sm.part;
+  for (int c = 0; c < s.nch; ++c) {
+    const int slot = cx.slot;
+    const long long tw0 = cx.trace ? clock64() : 0;
+    mbar_wait(&sm.full[slot], cx.ring_ph);
+    if (cx.trace) { cx.wait_full += clock64() - tw0; cx.trace[3] = clock64(); }
+    const int row0 = s.r0 + c * s.rch;
+    const int rows = min(s.rch, s.rows - c * s.rch);
+    const int wb = rows * row_bytes, sb = rows * srow_bytes;
+    const uint8_t* base = sm.ring + slot * p.slot_bytes;
+    const int tiles = (rows + 15) >> 4;
+    const int units = tiles * nsub;
+    int nks = kCWarps / units;           // K slices (whole groups) per (tile, sub)
+    if (nks > ngroups) nks = ngroups;
+    if (nks < 1) nks = 1;
+    // ---- partial tiles
+    for (int w = cx.warp; w < units * nks; w += kCWarps) {
+      const int unit = w / nks, ks = w - unit * nks;
+      const int sub = unit / tiles, tile = unit - sub * tiles;
+      const int g0 = (ks * ngroups) / nks, g1 = ((ks + 1) * ngroups) / nks;
+      const uint8_t* sbase = base + sub * (wb + 2 * sb);
+      const int ra = min(tile * 16 + g, rows - 1), rb = min(tile * 16 + g + 8, rows - 1);
+      const uint8_t* wa = sbase + ra * row_bytes;
+      const uint8_t* wbp = sbase + rb * row_bytes;
+      const uint8_t* sca = sbase + wb + ra * srow_bytes;
+      const uint8_t* scb = sbase + wb + rb * srow_bytes;
+      const __half* xcol = sm.xh + (size_t)g * p.xh_stride + t * 8;
+      const bool colv = (g & 3) < m;  // columns 0..3: hi halves of the activation rows, 4..7: their lo halves
+      const int c0 = 2 * t, c1 = 2 * t + 1;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int grp = g0; grp < g1; ++grp) {
+        float C[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int st = 0; st < steps; ++st) {
+          const int k32 = grp * steps + st;
+          uint4 xb = make_uint4(0u, 0u, 0u, 0u);
+          if (colv) xb = *reinterpret_cast<const uint4*>(xcol + k32 * 32);
+          if constexpr (FMT == W_Q4) {
+            const uint4 va = *reinterpret_cast<const uint4*>(wa + k32 * 16);
+            const uint4 vb = *reinterpret_cast<const uint4*>(wbp + k32 * 16);
+            const int sh = 4 * t;
+            auto dq = [&](uint32_t w) { return hsub2_u32(lop3_and_or(w >> sh, 0x000F000Fu, 0x64006400u), 0x64006400u); };  // (1024 + q) - 1024: exact
+            mma_16816(C, dq(va.x), dq(vb.x), dq(va.y), dq(vb.y), xb.x, xb.y);
+            mma_16816(C, dq(va.z), dq(vb.z), dq(va.w), dq(vb.w), xb.z, xb.w);
+          } else {  // W_Q8: 4 codes per word, the pair (t, t + 4) is byte t of two consecutive words
+            const uint4 va0 = *reinterpret_cast<const uint4*>(wa + k32 * 32), va1 = *reinterpret_cast<const uint4*>(wa + k32 * 32 + 16);
+            const uint4 vb0 = *reinterpret_cast<const uint4*>(wbp + k32 * 32), vb1 = *reinterpret_cast<const uint4*>(wbp + k32 * 32 + 16);
+            const uint32_t sel = (uint32_t)t | ((uint32_t)(4 + t) << 8);  // byte t of a -> byte 0, byte t of b -> byte 2
+            auto pk = [&](uint32_t lo, uint32_t hi) { return hsub2_u32(lop3_and_or(__byte_perm(lo, hi, sel), 0x00FF00FFu, 0x64006400u), 0x64006400u); };
+            mma_16816(C, pk(va0.x, va0.y), pk(vb0.x, vb0.y), pk(va0.z, va0.w), pk(vb0.z, vb0.w), xb.x, xb.y);
+            mma_16816(C, pk(va1.x, va1.y), pk(vb1.x, vb1.y), pk(va1.z, va1.w), pk(vb1.z, vb1.w), xb.z, xb.w);
+          }
+        }
+        float sa, ba, sbv, bb;
+        if (sdt == Q3TTS_F32) {
+          sa = reinterpret_cast<const float*>(sca)[grp]; ba = reinterpret_cast<const float*>(sca + sb)[grp];
+          sbv = reinterpret_cast<const float*>(scb)[grp]; bb = reinterpret_cast<const float*>(scb + sb)[grp];
+        } else {
+          sa = scale_to_f32(reinterpret_cast<const unsigned short*>(sca)[grp], sdt); ba = scale_to_f32(reinterpret_cast<const unsigned short*>(sca + sb)[grp], sdt);
+          sbv = scale_to_f32(reinterpret_cast<const unsigned short*>(scb)[grp], sdt); bb = scale_to_f32(reinterpret_cast<const unsigned short*>(scb + sb)[grp], sdt);
+        }
+        const float x0 = c0 < m ? sm.xsum[c0 * ngroups + grp] : 0.f, x1 = c1 < m ? sm.xsum[c1 * ngroups + grp] : 0.f;  // bias term: hi columns only
+        acc[0] += sa * C[0] + ba * x0; acc[1] += sa * C[1] + ba * x1;
+        acc[2] += sbv * C[2] + bb * x0; acc[3] += sbv * C[3] + bb * x1;
+      }
+      float* pt = part + w * 128;  // [16 rows][8 cols]
+      pt[g * 8 + c0] = acc[0]; pt[g * 8 + c1] = acc[1];
+      pt[(g + 8) * 8 + c0] = acc[2]; pt[(g + 8) * 8 + c1] = acc[3];
+    }
+    cbar();
+    if (cx.trace) cx.trace[4] = clock64();
+    // ---- reduce the K slices + epilogue: one thread per (row, activation row)
+    for (int e = cx.tid; e < rows * m; e += kCons) {
+      const int r = e / m, col = e - r * m;
+      const int tile = r >> 4, r16 = r & 15;
+      float inv_rms = 1.0f;
+      if (has_norm) {
+        float ssum = 0.f;
+#pragma unroll
+        for (int w = 0; w < kCWarps; ++w) ssum += sm.red[col * 16 + w];
+        inv_rms = rsqrtf(ssum / (float)K + eps);
+      }
+      float res[2] = {0.f, 0.f};
+      for (int sub = 0; sub < nsub; ++sub) {
+        const float* pt = part + ((sub * tiles + tile) * nks) * 128 + r16 * 8 + col;
+        float v = 0.f;
+        for (int ks = 0; ks < nks; ++ks) v += pt[ks * 128] + pt[ks * 128 + 4];  // hi + lo columns
+        res[sub] = v * inv_rms;
+      }
+      const int grow = row0 + r;
+      float v = res[0];
+      if (epi == E_SWIGLU) {
+        float gg = v, uu = res[1];
+        if (L.bias) { gg += L.bias[grow]; uu += L.bias[grow + L.out_eff]; }
+        v = silu_f(gg) * uu;
+      } else {
+        if (L.bias) v += L.bias[grow];
+        if (epi == E_ADD_RAW) v += sm.xraw[col * p.raw_ld + grow];
+      }
+      ll_store(out + (size_t)col * ld_out + grow, __float_as_uint(v), cx.ph);
+      if (plain_out) plain_out[(size_t)col * plain_ld + grow] = v;
+    }
+    cbar();  // `part` and the ring slot are free again
+    if (cx.lane == 0) mbar_arrive(&sm.empty[slot]);
+    if (++cx.slot == p.n_ring) { cx.slot = 0; cx.ring_ph ^= 1u; }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ attention phase
 // item = (slot, kv head, key split).  rps rows per slot (2 only in code-predictor pass 0).  Writes unnormalised partial
 // outputs + (max, sum) per head; the o-projection staging merges the splits.  A lane owns 4 consecutive head dims
@@ -540,8 +725,8 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
         const int rr = cx.tid >> 6, i = cx.tid & 63;
         float sn, cs;
         sincosf((float)(pos0 + rr) * S.inv_freq[i], &sn, &cs);
-        sm.rope[cx.tid * 2] = cs;
-        sm.rope[cx.tid * 2 + 1] = sn;
+        sm.rope[(slot * 128 + cx.tid) * 2] = cs;
+        sm.rope[(slot * 128 + cx.tid) * 2 + 1] = sn;
       }
       cbar();
     }
@@ -559,7 +744,7 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
         const float inv = rsqrtf(ss * (1.0f / 128.0f) + S.eps);
         const float4 nw = __ldg(reinterpret_cast<const float4*>(role < G ? q_norm : k_norm) + lane);
         const float4 x = make_float4(a.x * inv * nw.x, a.y * inv * nw.y, a.z * inv * nw.z, a.w * inv * nw.w);
-        const float4* cs4 = reinterpret_cast<const float4*>(sm.rope + (rr * 64 + 4 * (lane & 15)) * 2);  // [freq][cos, sin]
+        const float4* cs4 = reinterpret_cast<const float4*>(sm.rope + (slot * 128 + rr * 64 + 4 * (lane & 15)) * 2);  // [freq][cos, sin]
         const float4 t0 = cs4[0], t1 = cs4[1];
         const float4 cs = make_float4(t0.x, t0.z, t1.x, t1.z), sn = make_float4(t0.y, t0.w, t1.y, t1.w);
         float4 y;  // partner dims (d ^ 64)
@@ -669,10 +854,10 @@ __device__ void attn_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, con
 
 // ------------------------------------------------------------------------------------------------ bookkeeping (CTA 0)
 // record the frame, add code0 to its set, advance the trailing-text cursor (Model/Qwen3Talker.swift:526-549)
-__device__ void finalize_bookkeeping(const MegaParams& p) {
-  for (int slot = 0; slot < p.n_slots; ++slot) {
+__device__ void finalize_bookkeeping(const MegaParams& p, int slot) {
+  {
     SlotState& s = p.st[slot];
-    if (!s.frame_alive) continue;
+    if (!s.frame_alive) return;
     const int* codes = p.cur_codes + slot * 16;
     if (s.n_frames < p.max_frames) {
       for (int g = 0; g < 16; ++g) p.frames[((size_t)slot * p.max_frames + s.n_frames) * 16 + g] = codes[g];
@@ -688,10 +873,10 @@ __device__ void finalize_bookkeeping(const MegaParams& p) {
 }
 
 // pos++, step++, window trim every 15th step, max_tokens stop (Model/Qwen3Talker.swift:554-558; Qwen3Layers.swift:111-124)
-__device__ void step_advance(const MegaParams& p) {
-  for (int slot = 0; slot < p.n_slots; ++slot) {
+__device__ void step_advance(const MegaParams& p, int slot) {
+  {
     SlotState& s = p.st[slot];
-    if (!s.frame_alive) continue;
+    if (!s.frame_alive) return;
     s.pos += 1;
     s.step += 1;
     if (s.step % 15 == 0 && s.pos - s.win_start > p.window) s.win_start = s.pos - p.window;
@@ -705,37 +890,33 @@ __device__ void step_advance(const MegaParams& p) {
 __device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, const Ctx& cx, int group, bool plain_logits) {
   float* sl = reinterpret_cast<float*>(sm.xs);
   BlockRed& br = *reinterpret_cast<BlockRed*>(sl + kMaxVocab);
-  float* lg = sl + kMaxVocab + 64;  // staged logits [n_slots][V]
+  float* lg = sl + kMaxVocab + 64;  // staged logits of this CTA's slot
+  const int s = blockIdx.x;          // the slot this CTA owns
   SamplerParams sp;
   sp.vocab = group == 0 ? p.V : p.Vc; sp.group = group; sp.codec_vocab = p.V; sp.eos_id = p.eos_id; sp.pad_id = p.pad_id;
   sp.groups = 16; sp.set_words = p.set_words;
   const int V = sp.vocab;
-  for (int s = 0; s < p.n_slots; ++s) {
-    if (plain_logits) {  // first unit of a launch: logits written by the prefill / the previous launch
-      for (int i = cx.tid; i < V; i += kCons) lg[s * V + i] = p.logits0[(size_t)s * V + i];
-    } else {
-      for (int f = cx.tid; f < (V >> 2); f += kCons)
-        reinterpret_cast<float4*>(lg + s * V)[f] = ll_load4(p.ex_logit + (size_t)s * p.ld_logit + (size_t)f * 4, cx.ph - 1u);
-    }
+  if (plain_logits) {  // first unit of a launch: logits written by the prefill / the previous launch
+    for (int i = cx.tid; i < V; i += kCons) lg[i] = p.logits0[(size_t)s * V + i];
+  } else {
+    for (int f = cx.tid; f < (V >> 2); f += kCons)
+      reinterpret_cast<float4*>(lg)[f] = ll_load4(p.ex_logit + (size_t)s * p.ld_logit + (size_t)f * 4, cx.ph - 1u);
   }
   cbar();
   float* dump = group == 0 ? p.dump0 : p.dumpcp;
   const int dump_stride = group == 0 ? p.V : 15 * p.Vc, dump_off = group == 0 ? 0 : (group - 1) * p.Vc;
-  for (int s = 0; s < p.n_slots; ++s) {
-    sample_slot<1, kCons>(s, lg, V, p.st, sp, p.sets, p.cur_codes, p.forced, p.max_frames, dump, dump_stride, dump_off, 0, sl, br);
-    cbar();
-  }
+  // sample_slot indexes logits by slot: hand it a base that makes row `s` land on the staged copy
+  sample_slot<1, kCons>(s, lg - (size_t)s * V, V, p.st, sp, p.sets, p.cur_codes, p.forced, p.max_frames, dump, dump_stride, dump_off, 0, sl, br);
+  cbar();
   if (cx.tid == 0) {
-    for (int s = 0; s < p.n_slots; ++s) {
-      const SlotState& st = p.st[s];
-      u64* m = msg_at(p, cx.fseq, group, s);
-      if (group == 0) {
-        ll_store(m + 1, (uint32_t)st.pos, cx.fseq);
-        ll_store(m + 2, (uint32_t)st.win_start, cx.fseq);
-        ll_store(m + 3, (uint32_t)(st.trailing_idx < st.total_text ? st.trailing_idx : -1), cx.fseq);
-      }
-      ll_store(m, (uint32_t)p.cur_codes[s * 16 + group], cx.fseq);
+    const SlotState& st = p.st[s];
+    u64* m = msg_at(p, cx.fseq, group, s);
+    if (group == 0) {
+      ll_store(m + 1, (uint32_t)st.pos, cx.fseq);
+      ll_store(m + 2, (uint32_t)st.win_start, cx.fseq);
+      ll_store(m + 3, (uint32_t)(st.trailing_idx < st.total_text ? st.trailing_idx : -1), cx.fseq);
     }
+    ll_store(m, (uint32_t)p.cur_codes[s * 16 + group], cx.fseq);
   }
 }
 
@@ -746,6 +927,8 @@ __device__ __forceinline__ void sample_phase(const MegaParams& p, const Sm& sm, 
 template <int FMT, int NS>
 __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid_constant__ MegaParams p) {
   constexpr int M = 2 * NS;
+  // packed formats with more than one utterance per launch: tensor-core GEMV (one utterance stays on the fp32 SIMT GEMV)
+  constexpr bool kMma = (FMT == W_Q4 || FMT == W_Q8) && NS > 1;
   Sm sm;
   sm.ring = smem;
   sm.xs = reinterpret_cast<float4*>(smem + p.off_xs);
@@ -757,6 +940,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
   sm.dsc = reinterpret_cast<MegaLinear*>(smem + p.off_dsc);
   sm.hl = reinterpret_cast<float*>(smem + p.off_hl);
   sm.rope = reinterpret_cast<float*>(smem + p.off_rope);
+  sm.xh = reinterpret_cast<__half*>(smem + p.off_xs);
+  sm.part = reinterpret_cast<float*>(smem + p.off_part);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int kDscVec = (int)(sizeof(MegaLinear) / 16);
   if (tid == 0) {
@@ -793,7 +978,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
       if (tid < kDscVec) nd = __ldg(reinterpret_cast<const uint4*>(&p.lin[li + 1 < p.n_lin ? li + 1 : 0]) + tid);
       if (flags & MF_UNIT_START) {  // ---- sample phase (CTA 0): code_u from the logits of the previous unit
         ++cx.ph;
-        if (blockIdx.x == 0) {
+        if (blockIdx.x < (unsigned)ns) {  // CTA s owns slot s: its sampler state, its messages, its bookkeeping
           if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 20; }
           sample_phase(p, sm, cx, L.uidx, f == 0 && li == 0);
           if (cx.trace) cx.trace[2] = clock64();
@@ -814,7 +999,8 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
       const float* norm_w = L.norm_w;
       const float eps = S.eps;
       if (cx.trace) { cx.trace[0] = clock64(); cx.wait_full = 0; cx.wait_poll = 0; cx.trace[3] = cx.trace[4] = 0; }
-      stage_rows<FMT>(p, sm, cx, in, rows, L.in, norm_w, (flags & MF_KEEP_RAW) != 0);
+      if constexpr (kMma) stage_rows_mma(p, sm, cx, in, rows, L.in, L.group_shift, norm_w, (flags & MF_KEEP_RAW) != 0);
+      else stage_rows<FMT>(p, sm, cx, in, rows, L.in, norm_w, (flags & MF_KEEP_RAW) != 0);
       if (cx.trace) cx.trace[1] = clock64();
       if (head0) {  // h_last = final norm of the talker step: next frame's pass-0 input, kept per CTA
         for (int s = 0; s < ns; ++s) {
@@ -828,10 +1014,14 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
           }
         }
       }
-      if (rps == 2 && !(flags & MF_HEAD)) gemv_rows<FMT, M, 1>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
-      else gemv_rows<FMT, NS, 2>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+      if constexpr (kMma) {
+        gemv_mma<FMT>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+      } else {
+        if (rps == 2 && !(flags & MF_HEAD)) gemv_rows<FMT, M, 1>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+        else gemv_rows<FMT, NS, 2>(p, sm, cx, L, rows, norm_w != nullptr, eps, L.epi, out, ld_out, plain_out, p.V);
+      }
       if (cx.trace) { cx.trace[2] = clock64(); cx.trace[6] = cx.wait_full; cx.trace[7] = L.tkind + (cx.wait_poll << 8); }
-      if (head0 && blockIdx.x == 0 && tid == 0) step_advance(p);
+      if (head0 && blockIdx.x < (unsigned)ns && tid == 0) step_advance(p, blockIdx.x);
       const float* q_norm = L.q_norm;
       const float* k_norm = L.k_norm;
       const int layer = L.layer, unit = L.uidx;
@@ -841,7 +1031,7 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
       cbar();  // xs / xraw / descriptors are reused by the next phase
       if (flags & MF_ATTN) {
         ++cx.ph;                     // ---- attention phase (participants: one CTA per (slot, kv head, split))
-        if ((flags & MF_FINALIZE) && blockIdx.x == 0 && tid == 0) finalize_bookkeeping(p);
+        if ((flags & MF_FINALIZE) && blockIdx.x < (unsigned)ns && tid == 0) finalize_bookkeeping(p, blockIdx.x);
         if (blockIdx.x < (unsigned)(ns * S.kv_heads * S.nsplit)) {
           if (cx.trace) { cx.trace[0] = clock64(); cx.trace[1] = cx.trace[0]; cx.trace[6] = 0; cx.trace[7] = 10; }
           const int G = S.heads / S.kv_heads;
@@ -857,53 +1047,57 @@ __global__ void __launch_bounds__(kMegaThreads, 1) frame_megakernel(const __grid
   }
 }
 
-template <int FMT>
+template <int FMT, int NS>
 void launch_fmt(const LaunchCtx& c, const MegaPlan& plan, const MegaParams& p) {
   void* args[] = {const_cast<MegaParams*>(&p)};
-  Q3_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&frame_megakernel<FMT, kMegaMaxSlots>), dim3(plan.grid), dim3(kMegaThreads), args,
-                                      plan.smem, c.stream));
+  Q3_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&frame_megakernel<FMT, NS>), dim3(plan.grid), dim3(kMegaThreads), args, plan.smem, c.stream));
 }
 
-template <int FMT>
+template <int FMT, int NS>
 void init_fmt() {
-  Q3_CUDA(cudaFuncSetAttribute(frame_megakernel<FMT, kMegaMaxSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(frame_megakernel<FMT, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
 }
 
 }  // namespace
 
 void init_mega_kernels() {
-  init_fmt<W_Q4>();
-  init_fmt<W_Q8>();
-  init_fmt<W_BF16>();
-  init_fmt<W_F16>();
-  init_fmt<W_F32>();
+  init_fmt<W_Q4, 1>();
+  init_fmt<W_Q4, kMegaMaxSlots>();
+  init_fmt<W_Q8, 1>();
+  init_fmt<W_Q8, kMegaMaxSlots>();
+  init_fmt<W_BF16, 1>();
+  init_fmt<W_F16, 1>();
+  init_fmt<W_F32, 1>();
 }
 
-int mega_max_blocks_per_sm(int fmt, size_t smem_bytes) {
+int mega_max_blocks_per_sm(int fmt, int slots, size_t smem_bytes) {
   int n = 0;
   cudaError_t e = cudaErrorInvalidValue;
+  const bool multi = slots > 1;
   switch (fmt) {
-    case W_Q4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q4, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
-    case W_Q8: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q8, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
-    case W_BF16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_BF16, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
-    case W_F16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F16, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
-    case W_F32: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F32, kMegaMaxSlots>, kMegaThreads, smem_bytes); break;
+    case W_Q4: e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q4, kMegaMaxSlots>, kMegaThreads, smem_bytes)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q4, 1>, kMegaThreads, smem_bytes); break;
+    case W_Q8: e = multi ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q8, kMegaMaxSlots>, kMegaThreads, smem_bytes)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_Q8, 1>, kMegaThreads, smem_bytes); break;
+    case W_BF16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_BF16, 1>, kMegaThreads, smem_bytes); break;
+    case W_F16: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F16, 1>, kMegaThreads, smem_bytes); break;
+    case W_F32: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, frame_megakernel<W_F32, 1>, kMegaThreads, smem_bytes); break;
     default: break;
   }
   return e == cudaSuccess ? n : 0;
 }
 
 void launch_frame_megakernel(const LaunchCtx& c, const MegaPlan& plan, int n_slots, int n_frames, float* dump0, float* dumpcp) {
-  Q3_CHECK(plan.ok && n_slots >= 1 && n_slots <= kMegaMaxSlots && n_frames >= 1, Q3TTS_ERR_INVALID_ARG, "frame megakernel: bad launch");
+  Q3_CHECK(plan.ok && n_slots >= 1 && n_slots <= plan.max_slots && n_frames >= 1, Q3TTS_ERR_INVALID_ARG, "frame megakernel: bad launch");
   MegaParams p = plan.p;
   p.n_slots = n_slots; p.n_frames = n_frames; p.dump0 = dump0; p.dumpcp = dumpcp;
   Q3_CUDA(cudaMemsetAsync(p.ex_base, 0, p.ex_bytes, c.stream));  // LL tags start from 0 in every launch
   switch (plan.fmt) {
-    case W_Q4: launch_fmt<W_Q4>(c, plan, p); break;
-    case W_Q8: launch_fmt<W_Q8>(c, plan, p); break;
-    case W_BF16: launch_fmt<W_BF16>(c, plan, p); break;
-    case W_F16: launch_fmt<W_F16>(c, plan, p); break;
-    case W_F32: launch_fmt<W_F32>(c, plan, p); break;
+    case W_Q4: if (plan.max_slots > 1) launch_fmt<W_Q4, kMegaMaxSlots>(c, plan, p); else launch_fmt<W_Q4, 1>(c, plan, p); break;
+    case W_Q8: if (plan.max_slots > 1) launch_fmt<W_Q8, kMegaMaxSlots>(c, plan, p); else launch_fmt<W_Q8, 1>(c, plan, p); break;
+    case W_BF16: launch_fmt<W_BF16, 1>(c, plan, p); break;
+    case W_F16: launch_fmt<W_F16, 1>(c, plan, p); break;
+    case W_F32: launch_fmt<W_F32, 1>(c, plan, p); break;
     default: fail(Q3TTS_ERR_BAD_CONFIG, "frame megakernel: unknown weight format %d", plan.fmt);
   }
   c.tick();

@@ -89,13 +89,14 @@ struct MegaParams {
   int n_frames, window, eos_id, pad_id;
   // shared-memory plan (bytes from the 1024-aligned base)
   int slot_bytes, n_ring;
-  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc, off_hl, off_rope;
+  int off_xs, off_xsum, off_xraw, off_red, off_bar, off_dsc, off_hl, off_rope, off_part;
+  int xh_stride;            // halfs per activation column of the tensor-core path (K max + 32 padding)
   int raw_ld;               // floats per row of the raw residual copy
   long long* trace;         // diagnostics: [2 CTAs][trace_stride] cycle stamps, 8 per phase (null = off)
   int trace_stride;
 };
 
-constexpr int kMegaMaxSlots = 1;   // NS instantiated: rows per phase <= 2 * NS
+constexpr int kMegaMaxSlots = 2;   // utterances per launch on the tensor-core path: 2 x 2 rows, hi + lo fp16 halves = the 8 columns of one MMA n-tile
 
 // false when this checkpoint / option set is outside the kernel's envelope (the CUDA-graph path is used instead)
 struct MegaPlan {
@@ -105,6 +106,7 @@ struct MegaPlan {
   int G_cp = 0, G_tk = 0;
   size_t smem = 0;
   int grid = 0;
+  int max_slots = 1;  // utterances one launch can serve
 };
 
 void init_mega_kernels();

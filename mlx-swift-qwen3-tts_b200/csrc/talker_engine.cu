@@ -11,7 +11,7 @@
 namespace q3 {
 
 void init_talker_kernels();  // talker_kernels.cu: opt-in shared-memory attributes, once per device
-int mega_max_blocks_per_sm(int fmt, size_t smem);  // frame_kernel.cu
+int mega_max_blocks_per_sm(int fmt, int slots, size_t smem);  // frame_kernel.cu
 
 TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
                            LaunchCounter* counter)
@@ -215,22 +215,42 @@ void TalkerEngine::build_mega_plan() {
   if (T.heads % T.kv_heads || P.heads % P.kv_heads) return;
   if (cfg_.vocab_size > 4096 || cfg_.cp.vocab_size > 4096) return;
   if (T.hidden % 4 || P.hidden % 4 || T.inter % 4 || P.inter % 4) return;
-  constexpr int NS = kMegaMaxSlots, MT = 2 * NS;
   int slot_bytes = 32 * 1024;
   while (slot_bytes < need_slot) slot_bytes += 8 * 1024;
   const int nchunk = (kmax + kc - 1) / kc;
   const int hmax = std::max(T.hidden, P.hidden);
   auto up = [](int v, int a) { return (v + a - 1) / a * a; };
-  // scratch floor: sampler (16 KB ids + reductions + staged logits of every slot) / attention tiles
-  const int xs_bytes = up(std::max(MT * nchunk * kc * 4, (4096 + 64 + NS * 4096) * 4), 128);
-  const int xsum_bytes = up(MT * nchunk * 32 * 4, 128);
-  const int xraw_bytes = up(MT * hmax * 4, 128);
-  const int red_bytes = up(MT * 16 * 4, 128);
-  const int hl_bytes = up(NS * hmax * 4, 128);
-  const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 512 + hl_bytes + 1024 + 128;
+  // Handles that can hold >= 2 utterances (packed formats) run the tensor-core GEMV: kMegaMaxSlots utterances per launch;
+  // single-utterance handles keep the fp32 SIMT GEMV (lower latency at one row).
+  const bool mma = (fmt == 0 || fmt == 1);
+  int gmin = 1 << 30, gmax = 0, max_tiles = 0;
+  for (const MegaLinear& m : lin) {
+    gmin = std::min(gmin, m.group); gmax = std::max(gmax, m.group);
+    const int rch = (slot_bytes / (m.nsub * (m.row_bytes + 2 * m.srow_bytes))) / m.unit * m.unit;
+    max_tiles = std::max(max_tiles, ((rch + 15) / 16) * m.nsub);
+  }
+  if (mma && (gmin < 32 || gmax > 128 || kmax % 32 != 0)) return;
   const int budget = 226 * 1024;
-  int n_ring = std::min(8, (budget - fixed) / slot_bytes);
-  if (n_ring < 2) return;
+  int NS = 0, MT = 0, n_ring = 0, xs_bytes = 0, xsum_bytes = 0, xraw_bytes = 0, red_bytes = 0, hl_bytes = 0, rope_bytes = 0, part_bytes = 0;
+  const int scratch = (4096 + 64 + 4096) * 4;  // sampler: ids + reductions + staged logits of the CTA's slot; attention tiles fit too
+  for (int cand : {kMegaMaxSlots, 1}) {
+    if (cand > 1 && (!mma || opt_.max_batch < 2)) continue;
+    NS = cand; MT = 2 * NS;
+    const bool tc = mma && cand > 1;  // one utterance: fp32 SIMT GEMV; several: tensor-core GEMV with hi/lo fp16 columns (8 columns)
+    xs_bytes = up(std::max(tc ? 8 * (kmax * 2 + 64) : MT * nchunk * kc * 4, scratch), 128);
+    xsum_bytes = up(tc ? MT * (kmax / gmin) * 4 : MT * nchunk * 32 * 4, 128);
+    xraw_bytes = up(MT * hmax * 4, 128);
+    red_bytes = up(MT * 16 * 4, 128);
+    hl_bytes = up(NS * hmax * 4, 128);
+    rope_bytes = up(NS * 128 * 2 * 4, 128);
+    part_bytes = tc ? up(std::max(32, max_tiles) * 128 * 4, 128) : 0;
+    const int fixed = xs_bytes + xsum_bytes + xraw_bytes + red_bytes + 256 + 512 + hl_bytes + rope_bytes + part_bytes + 128;
+    n_ring = std::min(8, (budget - fixed) / slot_bytes);
+    if (n_ring >= 3 || (cand == 1 && n_ring >= 2)) break;
+    NS = 0;
+  }
+  if (NS == 0) return;
+  mega_.max_slots = NS;
   MegaParams& p = mega_.p;
   p.slot_bytes = slot_bytes; p.n_ring = n_ring;
   p.off_xs = n_ring * slot_bytes;
@@ -243,7 +263,9 @@ void TalkerEngine::build_mega_plan() {
   p.off_hl = p.off_dsc + 512;
   p.raw_ld = hmax;
   p.off_rope = p.off_hl + hl_bytes;
-  mega_.smem = (size_t)p.off_rope + 1024 + 128;
+  p.off_part = p.off_rope + rope_bytes;
+  p.xh_stride = kmax + 32;
+  mega_.smem = (size_t)p.off_part + part_bytes + 128;
   mega_.fmt = fmt; mega_.G_cp = G_cp; mega_.G_tk = G_tk;
   int dev = 0, sms = 0, coop = 0;
   Q3_CUDA(cudaGetDevice(&dev));
@@ -251,7 +273,7 @@ void TalkerEngine::build_mega_plan() {
   Q3_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
   if (!coop || sms < 1) return;
   init_mega_kernels();
-  if (mega_max_blocks_per_sm(fmt, mega_.smem) < 1) return;
+  if (mega_max_blocks_per_sm(fmt, mega_.max_slots, mega_.smem) < 1) return;
   // every CTA must own rows of every linear: the tagged exchange relies on all CTAs writing in every linear phase
   int min_units = 1 << 30;
   for (const MegaLinear& m : lin) min_units = std::min(min_units, m.out_eff / m.unit);
@@ -288,7 +310,7 @@ void TalkerEngine::build_mega_plan() {
   p.ld_act = up(std::max(T.inter, P.inter), 4);
   p.ld_logit = up(std::max(cfg_.vocab_size, cfg_.cp.vocab_size), 4);
   const size_t n_x = (size_t)MT * p.ld_x, n_qkv = (size_t)MT * p.ld_qkv, n_part = (size_t)MT * nsplit_tk * p.part_stride;
-  const size_t n_act = (size_t)MT * p.ld_act, n_logit = (size_t)NS * p.ld_logit, n_msg = (size_t)2 * 16 * NS * 4;
+  const size_t n_act = (size_t)MT * p.ld_act, n_logit = (size_t)NS * p.ld_logit, n_msg = (size_t)2 * 16 * kMegaMaxSlots * 4;
   p.ex_bytes = (n_x + n_qkv + n_part + n_act + n_logit + n_msg) * sizeof(unsigned long long);
   unsigned long long* ex = arena_.alloc_n<unsigned long long>(n_x + n_qkv + n_part + n_act + n_logit + n_msg);
   p.ex_base = ex;
@@ -672,7 +694,7 @@ void TalkerEngine::run_frames(int n_slots, int n) {
     for (int i = 0; i < n; ++i) issue_frame(n_slots);
     return;
   }
-  if (mega_.ok && n_slots <= kMegaMaxSlots && !use_tc(n_slots)) {  // batch-1 decode: one persistent cooperative launch for all n frames
+  if (mega_.ok && n_slots <= mega_.max_slots && !use_tc(n_slots)) {  // small batches: one persistent cooperative launch for all n frames
     if (mega_.p.trace) Q3_CUDA(cudaMemsetAsync(mega_.p.trace, 0, sizeof(long long) * 2 * mega_.p.trace_stride, stream_));
     launch_frame_megakernel(ctx(), mega_, n_slots, n, dump_enabled_ ? d_dump0_ : nullptr, dump_enabled_ ? d_dumpcp_ : nullptr);
     ++mega_launches;

@@ -240,6 +240,39 @@ def test_persistent_kernel_equals_graph_path(ck, request, engines, monkeypatch):
         graph.close()
 
 
+@pytest.mark.parametrize("ck", ["tiny8", "tiny4"])
+def test_two_utterance_persistent_kernel(ck, request, engines, oracles):
+    """A handle holding two utterances (packed weights) runs both in ONE persistent launch on the tensor-core GEMV
+    (mma.sync, activations split into hi + lo fp16 halves): logits stay at fp32-grade error, ids follow the oracle."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    d = request.getfixturevalue(ck)
+    eng = engines(d, max_batch=2)
+    F = 12
+    forced = np.random.default_rng(5).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    rec = {}
+    oracles(d).generate_codes(_oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec, filter_invalid=False)
+    frames, lg = eng.generate_codes(q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced,
+                                                 keep_invalid_frames=True, want_logits=F))
+    assert eng.timing().persistent_launches >= 1
+    e0 = np.abs(lg["code0_logits"] - rec["code0_logits"]).max()
+    ec = np.abs(lg["cp_logits"] - rec["cp_logits"]).max()
+    print(f"[{ck}] two-utterance persistent kernel (tensor-core GEMV) max-abs logit error: code0 {e0:.3e}, code predictor {ec:.3e}")
+    assert e0 <= 1e-3 and ec <= 1e-3
+    # two different utterances side by side == the oracle's per-utterance greedy ids (near-tie flips tolerated)
+    reqs = [dict(text_ids=TEXT_IDS, speaker_id=2861), dict(text_ids=list(range(100, 124)), speaker_id=3066)]
+    got = eng.generate_codes_batch([q.GenRequest(temperature=0.0, max_tokens=20, keep_invalid_frames=True, **kw) for kw in reqs])
+    assert eng.timing().persistent_launches >= 1 and eng.timing().graph_replays == 0
+    for kw, g in zip(reqs, got):
+        r = {}
+        want = oracles(d).generate_codes(_oreq(otalker, temperature=0.0, max_tokens=20, **kw), record=r, filter_invalid=False)
+        try:
+            _compare_greedy(g.tolist(), want, r["margins"])
+        except pytest.skip.Exception:
+            pass
+
+
 @pytest.mark.slow
 def test_persistent_kernel_full_size_logits(engines, oracles):
     """0.6B dimensions, 4-bit g64 (BASELINE configs[1]): teacher-forced logits of the persistent kernel vs the oracle."""
