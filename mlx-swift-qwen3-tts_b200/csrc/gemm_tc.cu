@@ -250,12 +250,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       if (p.out16) {
         if (p.snake_ea) {  // SnakeBeta of the consumer layer, applied to the fp16 operand copy only
+          // One modulo per 32-column chunk (not per element), per-channel constants as float4, and the SFU sine: the result
+          // is rounded to fp16 (2^-11) right after, MUFU.SIN's ~2^-21 absolute error is invisible behind it.  The precise
+          // sinf + per-element modulo cost ~50 instructions per output value and made the thin-channel vocoder stages
+          // epilogue-issue bound.
+          const int ch0 = ob % p.snake_ch;
+          const bool vec = (p.snake_ch & 3) == 0 && (ch0 & 3) == 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
+          for (int j = 0; j < 32; j += 4) {
             if (j < width) {
-              const int ch = (ob + j) % p.snake_ch;
-              const float sn = sinf(v[j] * p.snake_ea[ch]);
-              v[j] = v[j] + p.snake_ieb[ch] * (sn * sn);
+              int c = ch0 + j;
+              while (c >= p.snake_ch) c -= p.snake_ch;
+              float ea[4], ib[4];
+              if (vec) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.snake_ea + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.snake_ieb + c));
+                ea[0] = a4.x; ea[1] = a4.y; ea[2] = a4.z; ea[3] = a4.w;
+                ib[0] = b4.x; ib[1] = b4.y; ib[2] = b4.z; ib[3] = b4.w;
+              } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  int ci = c + i;
+                  while (ci >= p.snake_ch) ci -= p.snake_ch;
+                  ea[i] = p.snake_ea[ci]; ib[i] = p.snake_ieb[ci];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float sn = __sinf(v[j + i] * ea[i]);
+                v[j + i] = v[j + i] + ib[i] * (sn * sn);
+              }
             }
           }
         }
