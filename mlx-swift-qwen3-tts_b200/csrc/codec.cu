@@ -322,6 +322,16 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
     out_w_ = d;
     out_b_ = load_vec(t, "decoder.decoder." + std::to_string(n_out + 1) + ".conv.bias", 1);
+    // tensor-core form: the single output channel padded to a 32-column tile ([7][32][C] fp16, bias [32]); 31 columns of
+    // zeros cost nothing next to streaming the activations once through the TMA pipeline instead of a SIMT smem loop
+    std::vector<float> wp((size_t)7 * 32 * out_ch_, 0.f);
+    for (int k = 0; k < 7; ++k)
+      for (int ch = 0; ch < out_ch_; ++ch) wp[((size_t)k * 32) * out_ch_ + ch] = r[(size_t)k * out_ch_ + ch];
+    std::vector<float> hb(32, 0.f);
+    Q3_CUDA(cudaMemcpy(hb.data(), out_b_, 4, cudaMemcpyDeviceToHost));
+    float* db = arena_.alloc_n<float>(32);
+    Q3_CUDA(cudaMemcpy(db, hb.data(), 32 * 4, cudaMemcpyHostToDevice));
+    out_tc_.w16 = upload_f16(wp); out_tc_.bias = db; out_tc_.n = 32; out_tc_.cin = out_ch_; out_tc_.ntap = 7; out_tc_.dil = 1;
   }
   // algorithmic flops per 12.5 Hz frame: 2 * MACs of every dense contraction
   int64_t fl = rvq_proj_.flops_per_row() + pre_conv_.flops_per_row() + tr_in_.flops_per_row() + tr_out_.flops_per_row();
@@ -465,7 +475,7 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
       launch_tc_gemm(lc, g);
     }
   }
-  launch_out_conv_f16(lc, cur, out_w_, out_b_, out_ch_, B, Tc, d_pcm);
+  { TcGemm g = gemm(out_tc_, cur, B, Tc); g.pcm = d_pcm; launch_tc_gemm(lc, g); }
 }
 
 void CodecDecoder::decode_pass_simt(const int32_t* d_codes, int B, int T, float* d_pcm) {

@@ -109,6 +109,7 @@ class CodecDecoder {
   std::vector<Block> blocks_;
   SnakeW out_snake_;
   const float *out_w_ = nullptr, *out_b_ = nullptr;  // [7][C], [1]
+  ConvW out_tc_;                                    // the same conv as a 32-column tcgen05 tile (column 0 real)
   int out_ch_ = 0;
 
   bool use_tc_ = true;  // every dense contraction fits the tcgen05 path (cin % 8 == 0, N % 32 == 0); else the fp32 SIMT pipeline runs

@@ -36,6 +36,7 @@ struct TcParams {
   const float* snake_ea;
   const float* snake_ieb;
   int snake_ch;
+  float* pcm;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -242,6 +243,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      if (p.pcm) {  // DecoderOutputConv: the tile's other 31 columns are zero padding of the 1-channel weight
+        if (nb == 0) p.pcm[m] = (v[0] != v[0]) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v[0]));
+        continue;
+      }
       if (p.out32) {
         float* op = p.out32 + m * p.ld32 + ob;
 #pragma unroll
@@ -378,6 +383,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
   p.snake_ea = g.snake_ea; p.snake_ieb = g.snake_ieb; p.snake_ch = g.snake_ch > 0 ? g.snake_ch : 1;
+  p.pcm = g.pcm;
 
   const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
   const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};

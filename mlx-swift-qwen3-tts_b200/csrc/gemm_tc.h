@@ -33,6 +33,7 @@ struct TcGemm {
   const float* snake_ea = nullptr;   // SnakeBeta of the NEXT layer fused into the fp16 copy: v + ieb[ch] * sin^2(v * ea[ch]),
   const float* snake_ieb = nullptr;  // ch = n % snake_ch (Vocoder/SpeechTokenizer.swift:105-109)
   int snake_ch = 0;
+  float* pcm = nullptr;              // output conv: column 0 only, clip(-1, 1) + NaN scrub, [M] (SpeechTokenizer.swift:823-840, 951)
 };
 
 // true when the tcgen05 path can run this shape (else the caller uses the SIMT kernel)
