@@ -251,6 +251,15 @@ q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t
 q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out,
                                   int64_t* launches_out, int64_t* bytes_per_iter_out);
 
+/* measurement hook (scripts/skinny_trace.py): `iters` back-to-back launches (one CUDA graph, programmatic dependent launch,
+ * a different weight matrix each) of the <= 128-row split-K cluster GEMM (csrc/gemm_skinny.cu) for an [M x K] . [N x K]^T
+ * linear; returns the average time per launch and, for the LAST launch, 16 stamps per CTA: [0]/[9] %globaltimer at entry /
+ * exit, [1..8] clock64 at entry, after setup, first operand stage landed, accumulator complete, partial sums shipped,
+ * peers' partial sums landed, epilogue done, exit.  No reference counterpart. */
+q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K, int32_t swiglu, int32_t residual, int32_t iters,
+                                uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out,
+                                int32_t* stages_out, double* avg_us_out);
+
 #ifdef __cplusplus
 }
 #endif

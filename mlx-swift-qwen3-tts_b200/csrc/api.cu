@@ -889,6 +889,75 @@ q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t
   }
 }
 
+q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K, int32_t swiglu, int32_t residual, int32_t iters,
+                                uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out, int32_t* stages_out,
+                                double* avg_us_out) {
+  try {
+    Q3_CHECK(M > 0 && N > 0 && K > 0 && iters > 0 && stamps_out && tiles_out && split_out && stages_out && avg_us_out, Q3TTS_ERR_INVALID_ARG,
+             "bad arguments");
+    require_device(device);
+    init_tc_gemm();
+    const int n_out = swiglu ? N / 2 : N;
+    __half *x = nullptr, *w = nullptr, *y16 = nullptr;
+    float* y32 = nullptr;
+    unsigned long long* tr = nullptr;
+    Q3_CUDA(cudaMalloc(&x, (size_t)M * K * 2));
+    // `iters` DIFFERENT weight matrices so every launch streams from HBM like consecutive layers do
+    Q3_CUDA(cudaMalloc(&w, (size_t)iters * N * K * 2));
+    Q3_CUDA(cudaMalloc(&y16, (size_t)M * n_out * 2));
+    Q3_CUDA(cudaMalloc(&y32, (size_t)M * n_out * 4));
+    Q3_CUDA(cudaMemset(x, 0, (size_t)M * K * 2));
+    Q3_CUDA(cudaMemset(w, 0, (size_t)iters * N * K * 2));
+    Q3_CUDA(cudaMemset(y32, 0, (size_t)M * n_out * 4));
+    TcGemm g;
+    g.a = x; g.w = w; g.Bt = 1; g.T = M; g.cin = K; g.N = N; g.swiglu = swiglu;
+    if (swiglu) { g.out16 = y16; g.ld16 = n_out; } else { g.out32 = y32; g.ld32 = n_out; }
+    if (residual) { g.res = y32; g.ld_res = n_out; g.out32 = y32; g.ld32 = n_out; }
+    Q3_CHECK(tc_skinny_supported(g), Q3TTS_ERR_INVALID_ARG, "shape is not on the skinny path");
+    tc_skinny_grid(g, tiles_out, split_out, stages_out);
+    const int ctas = *tiles_out * *split_out;
+    Q3_CHECK(ctas <= capacity_ctas, Q3TTS_ERR_CAPACITY, "stamps_out holds %d CTAs, the grid has %d", capacity_ctas, ctas);
+    Q3_CUDA(cudaMalloc(&tr, (size_t)ctas * 16 * 8));
+    Q3_CUDA(cudaMemset(tr, 0, (size_t)ctas * 16 * 8));
+    cudaStream_t st;
+    Q3_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cudaEvent_t e0, e1;
+    Q3_CUDA(cudaEventCreate(&e0));
+    Q3_CUDA(cudaEventCreate(&e1));
+    LaunchCtx c{st, nullptr};
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
+    tc_skinny_set_trace(tr);
+    Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    for (int i = 0; i < iters; ++i) {
+      g.w = w + (size_t)i * N * K;
+      launch_tc_skinny(c, g);
+    }
+    Q3_CUDA(cudaStreamEndCapture(st, &graph));
+    tc_skinny_set_trace(nullptr);
+    Q3_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    Q3_CUDA(cudaGraphLaunch(exec, st));
+    Q3_CUDA(cudaStreamSynchronize(st));
+    Q3_CUDA(cudaEventRecord(e0, st));
+    Q3_CUDA(cudaGraphLaunch(exec, st));
+    Q3_CUDA(cudaEventRecord(e1, st));
+    Q3_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us_out = (double)ms * 1e3 / iters;
+    Q3_CUDA(cudaMemcpy(stamps_out, tr, (size_t)ctas * 16 * 8, cudaMemcpyDeviceToHost));
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    cudaFree(x); cudaFree(w); cudaFree(y16); cudaFree(y32); cudaFree(tr);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    tc_skinny_set_trace(nullptr);
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
 q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out, int64_t* launches_out,
                                   int64_t* bytes_per_iter_out) {
   return guarded(h, [&] {

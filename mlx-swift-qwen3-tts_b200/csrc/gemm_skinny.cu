@@ -1,0 +1,411 @@
+// Skinny tcgen05 GEMM for <= 128 activation rows (sm_100a): the linears of a batched decode step
+// (Model/Qwen3Layers.swift:128-238 at L = 1 for many utterances at once) and of short codec windows.
+//
+//   Y[m, n] = epilogue( sum_k X[m, k] * W[n, k] ),   m < M <= 128
+//
+// At M <= 128 a [128 x bn] output tile per CTA (gemm_tc.cu) leaves N/bn CTAs each walking ALL of K and re-reading every
+// activation row: the launch is bound by per-SM load latency (13-24 us for a 4-12 MB weight matrix).  Here the roles are
+// swapped and K is split:
+//   * the WEIGHT tile (128 rows of W) is the UMMA A operand, the activation rows are the N dimension (m_pad = 32/64/128
+//     columns of the TMEM accumulator), so every weight byte enters exactly one CTA and the activation re-read is m_pad/128
+//     of the weight traffic;
+//   * the grid is (N/128 weight tiles) x (split K slices), one thread-block CLUSTER per weight tile; every CTA streams a
+//     128 x (K/split) slice through a short TMA ring, so ~all SMs pull weights concurrently;
+//   * the K slices are reduced through DISTRIBUTED SHARED MEMORY: CTA r of the cluster owns activation rows
+//     [r*mc, (r+1)*mc); every CTA stages its TMEM accumulator in its own shared memory grouped by owner and ships each
+//     owner's slice with ONE bulk copy (cp.async.bulk.shared::cluster, completion on the owner's mbarrier); the owner then
+//     finishes bias / activation / SwiGLU / residual for its rows in a fixed summation order (deterministic, no atomics, no
+//     zero-init, epilogues stay fused).  (Per-thread st.shared::cluster stores were measured at ~3 B/cycle: 2.9 us per 32
+//     accumulator columns; the bulk engine moves the same bytes in a fraction of that.)
+// Warp roles as in gemm_tc.cu: warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer, warps 2-5 epilogue.  Programmatic
+// dependent launch: the first ring-full of WEIGHT tiles is requested before griddepcontrol.wait.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+
+namespace q3 {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kRowsW = 128;                     // weight rows per CTA = UMMA M
+constexpr int kBlockK = 64;                     // fp16 elements per k-block = one 128-byte swizzle row
+constexpr int kWBytes = kRowsW * kBlockK * 2;   // 16 KB per stage
+constexpr int kThreads = 192;
+
+struct SkParams {
+  int M, N, K;
+  int m_pad, mc, mc_shift, split, stages, num_kb, tmem_cols;
+  const float* bias;
+  const float* res;
+  int ld_res;
+  const float* scale;
+  int act, swiglu;
+  float* out32;
+  int ld32;
+  __half* out16;
+  int ld16;
+  unsigned long long* trace;  // measurement hook (q3tts_skinny_trace): 16 stamps per CTA, or null
+};
+
+__device__ __forceinline__ unsigned long long sk_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define SK_STAMP(slot)                                                                                        \
+  do {                                                                                                        \
+    if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+
+__device__ __forceinline__ float sk_gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sk_silu(float v) { return v / (1.0f + expf(-v)); }
+// SwiGLU feeds an fp16 operand (2^-11 relative rounding): the SFU exponential and reciprocal (2 ulp each) are invisible behind it
+__device__ __forceinline__ float sk_silu_fast(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// Epilogue for `valid` (<= NC) consecutive activation rows m0.. of this thread's weight row (all 32 lanes call it together: the
+// SwiGLU pairing is a lane shuffle).  Residual loads are issued first, stores last, so the round trips overlap; row pointers
+// advance by their leading dimension (no 64-bit multiply per element: code size matters here, see below).
+// ACT / SWIGLU are template parameters on purpose: with the exact erf and exponential expanded inline for every element of an
+// unrolled chunk, one all-purpose epilogue was ~50 KB of SASS that ran once per launch at instruction-fetch speed (2.6 us
+// per 16-column chunk measured); each instantiation now carries only its own math, at ONE call site.
+template <int NC, int ACT, bool SWIGLU>
+__device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], int valid, int m0, int ob, float bias, float scale) {
+  float r[NC];
+  if (p.res) {
+    const float* rp = p.res + (size_t)m0 * p.ld_res + ob;
+#pragma unroll
+    for (int e = 0; e < NC; ++e, rp += p.ld_res) r[e] = e < valid ? *rp : 0.f;
+  }
+#pragma unroll
+  for (int e = 0; e < NC; ++e) {
+    float v = acc[e] + bias;
+    if (ACT == TC_ACT_GELU) v = sk_gelu_erf(v);
+    else if (ACT == TC_ACT_SILU) v = sk_silu(v);
+    if (SWIGLU) {  // weight rows (2i, 2i+1) = (gate_i, up_i): adjacent TMEM lanes = adjacent threads
+      const float up = __shfl_xor_sync(0xffffffffu, v, 1);
+      v = sk_silu_fast(v) * up;
+    }
+    if (p.res) v = r[e] + scale * v;
+    acc[e] = v;
+  }
+  if (p.out32) {
+    float* op = p.out32 + (size_t)m0 * p.ld32 + ob;
+#pragma unroll
+    for (int e = 0; e < NC; ++e, op += p.ld32)
+      if (e < valid) *op = acc[e];
+  }
+  if (p.out16) {
+    __half* hp = p.out16 + (size_t)m0 * p.ld16 + ob;
+#pragma unroll
+    for (int e = 0; e < NC; ++e, hp += p.ld16)
+      if (e < valid) *hp = __float2half_rn(acc[e]);
+  }
+}
+
+template <int ACT, bool SWIGLU>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B needs 1024-B aligned stages; the dynamic window starts at the same offset in every CTA of the kernel, so the
+  // aligned offsets (and with them the DSMEM addresses of `red`) agree across the cluster.
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int x_bytes = p.m_pad * kBlockK * 2;
+  uint8_t* sW = smem;
+  uint8_t* sX = smem + (size_t)p.stages * kWBytes;
+  float* red = reinterpret_cast<float*>(sX + (size_t)p.stages * x_bytes);            // [split][128][mc]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + (size_t)kRowsW * p.m_pad);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint64_t* red_full = tmem_full + 1;
+  uint64_t* ack = red_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ack + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;   // cluster = (1, split, 1): the K slices of one weight tile
+  const int n0 = blockIdx.x * kRowsW;
+  const int kb0 = (int)(((long long)rank * p.num_kb) / p.split);
+  const int kb1 = (int)(((long long)(rank + 1) * p.num_kb) / p.split);
+  const int nkb = kb1 - kb0;
+
+  pdl_launch_dependents();
+  if (threadIdx.x == 32) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 0] = sk_globaltimer();
+    SK_STAMP(1);
+    for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(red_full, 1);
+    mbar_init(ack, p.split > 1 ? p.split - 1 : 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) SK_STAMP(2);
+  // phase A of the cluster barrier: "this CTA is running" (its shared memory may be written by peers once they passed wait A)
+  if (p.split > 1) cluster_arrive_release();
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      const int pre = nkb < p.stages ? nkb : p.stages;
+      for (int i = 0; i < pre; ++i) {  // weights do not depend on the predecessor kernel
+        mbar_expect_tx(&full[i], (uint32_t)(kWBytes + x_bytes));
+        tma_load_2d(sW + (size_t)i * kWBytes, &tmW, &full[i], (kb0 + i) * kBlockK, n0);
+      }
+      pdl_wait();
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages, ph = (i / p.stages) & 1;
+        if (i >= pre) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], (uint32_t)(kWBytes + x_bytes));
+          tma_load_2d(sW + (size_t)s * kWBytes, &tmW, &full[s], (kb0 + i) * kBlockK, n0);
+        }
+        tma_load_2d(sX + (size_t)s * x_bytes, &tmX, &full[s], (kb0 + i) * kBlockK, 0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.m_pad >> 3) << 17) | ((uint32_t)(kRowsW >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % p.stages, ph = (i / p.stages) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        if (i == 0) SK_STAMP(3);
+        const uint64_t ad = umma_desc(smem_u32(sW + (size_t)s * kWBytes));
+        const uint64_t bd = umma_desc(smem_u32(sX + (size_t)s * x_bytes));
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+    __syncwarp();
+  } else {
+    // ---------------- epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); thread = one weight row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int n = n0 + row;
+    const bool n_ok = n < p.N;
+    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+    pdl_wait();  // residual rows were written by earlier kernels
+    const float bias = (p.bias && n_ok) ? p.bias[n] : 0.f;
+    const int so = SWIGLU ? (n >> 1) : n;
+    const float scale = (p.scale && n_ok) ? p.scale[so] : 1.f;
+    if (p.split > 1) cluster_wait_acquire();  // A: every peer CTA is resident, its mbarriers initialised (long complete by now)
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (threadIdx.x == 64) SK_STAMP(4);
+    {
+      // 1. TMEM -> local staging [owner][row][mc]; it aliases the operand ring (every MMA of this CTA has completed)
+      float* stage_out = reinterpret_cast<float*>(smem);
+      for (int c0 = 0; c0 < p.m_pad; c0 += 32) {
+        uint32_t raw[32];
+        tmem_ld32(taddr + (uint32_t)c0, raw);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const int col = c0 + j;
+          const int dst = col >> p.mc_shift;          // owner of activation rows [dst*mc, +mc)
+          const int off = col & (p.mc - 1);
+          // slice of owner dst = [mc/4 column groups][128 rows][4]: a warp writes 512 contiguous bytes (no bank conflicts)
+          *reinterpret_cast<float4*>(stage_out + (size_t)dst * kRowsW * p.mc + ((size_t)(off >> 2) * kRowsW + row) * 4) =
+              make_float4(__uint_as_float(raw[j]), __uint_as_float(raw[j + 1]), __uint_as_float(raw[j + 2]), __uint_as_float(raw[j + 3]));
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk-copy engine
+      asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps
+      // 2. one bulk DSMEM copy per peer: slice [owner = d] of my partial sums -> slot [src = rank] of d's `red`, signalling d's mbarrier
+      const uint32_t slice_bytes = (uint32_t)(kRowsW * p.mc * 4);
+      if (threadIdx.x == 64 && p.split > 1) {
+        mbar_expect_tx(red_full, slice_bytes * (uint32_t)(p.split - 1));
+        for (int i = 1; i < p.split; ++i) {
+          const uint32_t d = (rank + (uint32_t)i) % (uint32_t)p.split;
+          bulk_copy_to_rank(map_to_rank(smem_u32(red + (size_t)rank * kRowsW * p.mc), d), smem_u32(stage_out + (size_t)d * kRowsW * p.mc), slice_bytes,
+                            map_to_rank(smem_u32(red_full), d));
+        }
+      }
+      if (threadIdx.x == 64) SK_STAMP(5);
+      if (p.split > 1) mbar_wait(red_full, 0);  // the other K slices of MY activation rows have landed
+      if (threadIdx.x == 96) SK_STAMP(10);
+      if (threadIdx.x == 64) {
+        SK_STAMP(6);
+        // tell every peer that its copy into this CTA is complete (it may retire its staging buffer / exit)
+        for (int i = 1; i < p.split; ++i) mbar_arrive_remote_relaxed(map_to_rank(smem_u32(ack), (rank + (uint32_t)i) % (uint32_t)p.split));
+      }
+      const int m_base = (int)rank * p.mc;
+      const uint32_t own_s = smem_u32(stage_out), red_s = smem_u32(red);
+      for (int cb = 0; cb < p.mc; cb += 16) {
+        const int nc = p.mc - cb < 16 ? p.mc - cb : 16;
+        float a16[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a16[j] = 0.f;
+        for (int s = 0; s < p.split; ++s) {  // fixed order: deterministic
+          const uint32_t base = (s == (int)rank ? own_s : red_s) + (uint32_t)s * slice_bytes + (uint32_t)row * 16u;
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            if (c < nc) {
+              const float4 v = lds_f4(base + (uint32_t)((cb + c) >> 2) * (uint32_t)(kRowsW * 16));
+              a16[c] += v.x; a16[c + 1] += v.y; a16[c + 2] += v.z; a16[c + 3] += v.w;
+            }
+          }
+        }
+        if (threadIdx.x == 96 && cb == 0) SK_STAMP(11);
+        int valid = p.M - (m_base + cb);
+        valid = valid < nc ? valid : nc;
+        if (!(n_ok && (!SWIGLU || (n & 1) == 0))) valid = 0;  // lanes without an output column compute (shuffle partners) but do not touch memory
+        sk_finish<16, ACT, SWIGLU>(p, a16, valid, m_base + cb, so, bias, scale);
+        if (threadIdx.x == 96 && cb == 0) SK_STAMP(12);
+      }
+      if (threadIdx.x == 96) SK_STAMP(13);
+      if (threadIdx.x == 64 && p.split > 1) {
+        SK_STAMP(7);
+        mbar_wait(ack, 0);  // every peer has received my partial sums: my staging buffer is no longer being read
+      }
+    }
+  }
+  if (p.split > 1 && warp < 2) cluster_wait_acquire();  // A (the epilogue warps passed it above)
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x == 0 && p.trace) {
+    SK_STAMP(8);
+    p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 9] = sk_globaltimer();
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+struct SkPlan {
+  int m_pad, split, stages, num_kb, tiles;
+  size_t smem;
+};
+
+SkPlan plan(const TcGemm& g) {
+  static const int max_split = std::max(1, std::min(8, env_int("Q3TTS_SK_MAX_SPLIT", 8)));
+  // up to ~1.3 waves: 48 weight tiles (gate|up) take 4 K slices = 192 CTAs of 4 k-blocks (two co-resident per SM on 44 SMs)
+  // rather than 96 CTAs of 8 k-blocks; measured 13.5 -> ~9 us per launch at 64 rows
+  static const int cta_target = env_int("Q3TTS_SK_CTAS", 200);
+  static const int smem_kb = env_int("Q3TTS_SK_SMEM_KB", 108);
+  SkPlan s{};
+  const int M = g.Bt * g.T;
+  s.m_pad = M <= 32 ? 32 : (M <= 64 ? 64 : 128);
+  s.tiles = (g.N + kRowsW - 1) / kRowsW;
+  s.num_kb = (g.cin + kBlockK - 1) / kBlockK;
+  s.split = 1;
+  while (s.split * 2 <= max_split && s.tiles * s.split * 2 <= cta_target && s.split * 2 <= s.num_kb && s.m_pad / (s.split * 2) >= 4) s.split *= 2;
+  const int stage_bytes = kWBytes + s.m_pad * kBlockK * 2;
+  const int red_bytes = kRowsW * s.m_pad * 4;
+  const int nkb_max = (s.num_kb + s.split - 1) / s.split;
+  s.stages = std::max(2, (smem_kb * 1024 - red_bytes) / stage_bytes);
+  s.stages = std::max(1, std::min(s.stages, nkb_max));
+  // the ring doubles as the outgoing staging buffer [owner][128][mc] fp32 (= red_bytes) once the MMAs are done
+  while (s.stages * stage_bytes < red_bytes) ++s.stages;
+  s.smem = (size_t)s.stages * stage_bytes + red_bytes + 1024 + (2 * s.stages + 4) * 8 + 16;
+  return s;
+}
+
+}  // namespace
+
+bool tc_skinny_supported(const TcGemm& g) {
+  static const bool on = env_int("Q3TTS_SKINNY", 1) != 0;
+  const long long M = (long long)g.Bt * g.T;
+  return on && g.ntap == 1 && M >= 1 && M <= 128 && !g.snake_ea && !g.pcm && !(g.swiglu && g.act != TC_ACT_NONE) && tc_gemm_supported(g);
+}
+
+using SkKernel = void (*)(const CUtensorMap, const CUtensorMap, const SkParams);
+static SkKernel pick_kernel(int act, int swiglu) {
+  if (swiglu) return tc_skinny_kernel<TC_ACT_NONE, true>;
+  if (act == TC_ACT_GELU) return tc_skinny_kernel<TC_ACT_GELU, false>;
+  if (act == TC_ACT_SILU) return tc_skinny_kernel<TC_ACT_SILU, false>;
+  return tc_skinny_kernel<TC_ACT_NONE, false>;
+}
+
+void init_tc_skinny() {
+  tc_resolve_encode();
+  for (SkKernel k : {pick_kernel(0, 1), pick_kernel(TC_ACT_GELU, 0), pick_kernel(TC_ACT_SILU, 0), pick_kernel(0, 0)})
+    Q3_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+}
+
+unsigned long long* g_sk_trace = nullptr;  // set by tc_skinny_trace around its launches
+
+void tc_skinny_set_trace(unsigned long long* dev_buf) { g_sk_trace = dev_buf; }
+void tc_skinny_grid(const TcGemm& g, int* tiles, int* split, int* stages) {
+  const SkPlan s = plan(g);
+  *tiles = s.tiles; *split = s.split; *stages = s.stages;
+}
+
+void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g) {
+  Q3_CHECK(tc_skinny_supported(g), Q3TTS_ERR_INVALID_ARG, "tc_skinny: unsupported shape (rows %d, cin %d, N %d)", g.Bt * g.T, g.cin, g.N);
+  tc_resolve_encode();
+  const SkPlan s = plan(g);
+  SkParams p{};
+  p.M = g.Bt * g.T; p.N = g.N; p.K = g.cin;
+  p.m_pad = s.m_pad; p.split = s.split; p.mc = s.m_pad / s.split; p.stages = s.stages; p.num_kb = s.num_kb;
+  p.mc_shift = 0;
+  while ((1 << p.mc_shift) < p.mc) ++p.mc_shift;
+  p.tmem_cols = std::max(32, s.m_pad);
+  p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
+  p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
+  p.trace = g_sk_trace;
+
+  const uint64_t wdims[2] = {(uint64_t)g.cin, (uint64_t)g.N};
+  const uint64_t wstr[1] = {(uint64_t)g.cin * 2};
+  const uint32_t wbox[2] = {(uint32_t)kBlockK, (uint32_t)kRowsW};
+  const CUtensorMap mw = tc_make_map(g.w, 2, wdims, wstr, wbox);
+  const uint64_t xdims[2] = {(uint64_t)g.cin, (uint64_t)p.M};
+  const uint64_t xstr[1] = {(uint64_t)g.cin * 2};
+  const uint32_t xbox[2] = {(uint32_t)kBlockK, (uint32_t)s.m_pad};
+  const CUtensorMap mx = tc_make_map(g.a, 2, xdims, xstr, xbox);
+
+  Q3_CHECK(s.smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_skinny: shared memory request %zu too large", s.smem);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)s.tiles, (unsigned)s.split);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = s.smem;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (s.split > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = (unsigned)s.split; attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  Q3_CUDA(cudaLaunchKernelEx(&cfg, pick_kernel(g.act, g.swiglu), mw, mx, p));
+  c.tick();
+}
+
+}  // namespace q3

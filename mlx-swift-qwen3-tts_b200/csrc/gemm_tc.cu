@@ -11,10 +11,13 @@
 #include <mutex>
 
 #include "gemm_tc.h"
+#include "tc_ptx.cuh"
 
 namespace q3 {
 
 namespace {
+
+using namespace tcptx;
 
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // fp16 elements per k-block = one 128-byte swizzle row
@@ -38,77 +41,6 @@ struct TcParams {
   int snake_ch;
   float* pcm;
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as a trapped kernel (an error code on the host), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 22)) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
-               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor, version 1 = Blackwell):
-//   [0,14) start>>4   [16,30) LBO>>4 = 1 (unused for swizzled K-major)   [32,46) SBO>>4 = 64   [46,48) version = 1   [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
-  const uint32_t hi = 64u | (1u << 14) | (2u << 29);
-  return ((uint64_t)hi << 32) | lo;
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-        "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
@@ -310,30 +242,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
-PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
-std::once_flag g_encode_once;
-
-void resolve_encode() {
-  std::call_once(g_encode_once, [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
-      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
-  });
-  Q3_CHECK(g_encode != nullptr, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-}
-
-CUtensorMap make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
-  CUtensorMap m;
-  const uint32_t estr[3] = {1, 1, 1};
-  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank,
-           (unsigned long long)dims[0], (unsigned long long)dims[1]);
-  return m;
-}
-
 // Tile width: the largest multiple of 32 (<= 256) dividing N that still yields >= one CTA per SM; small-M problems (batched
 // decode) fall through to narrow tiles so the weight stream is spread over many SMs.
 int pick_bn(int N, int tiles_m) {
@@ -350,6 +258,32 @@ int pick_bn(int N, int tiles_m) {
 
 }  // namespace
 
+namespace {
+PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+std::once_flag g_encode_once;
+}  // namespace
+
+void tc_resolve_encode() {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  });
+  Q3_CHECK(g_encode != nullptr, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+}
+
+CUtensorMap tc_make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  CUtensorMap m;
+  const uint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, dims %llu x %llu)", (int)r, rank,
+           (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return m;
+}
+
 bool tc_gemm_supported(const TcGemm& g) {
   const int n_out = g.swiglu ? g.N / 2 : g.N;
   return g.cin % 8 == 0 && g.N % 32 == 0 && g.N >= 32 && g.T >= 1 && g.Bt >= 1 && (reinterpret_cast<uintptr_t>(g.a) & 15) == 0 &&
@@ -358,13 +292,15 @@ bool tc_gemm_supported(const TcGemm& g) {
 }
 
 void init_tc_gemm() {
-  resolve_encode();
+  tc_resolve_encode();
   Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  init_tc_skinny();
 }
 
 void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
+  if (tc_skinny_supported(g)) return launch_tc_skinny(c, g);  // <= 128 rows: split-K cluster kernel (gemm_skinny.cu)
   Q3_CHECK(tc_gemm_supported(g), Q3TTS_ERR_INVALID_ARG, "tc_gemm: unsupported shape (cin %d, N %d)", g.cin, g.N);
-  resolve_encode();
+  tc_resolve_encode();
   TcParams p{};
   p.Bt = g.Bt; p.T = g.T; p.cin = g.cin; p.N = g.N; p.ntap = g.ntap; p.dil = g.dil;
   p.kb_per_tap = (g.cin + kBlockK - 1) / kBlockK;
@@ -388,11 +324,11 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
   const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};
   const uint32_t abox[3] = {(uint32_t)kBlockK, (uint32_t)kTileM, 1};
-  const CUtensorMap ma = make_map(g.a, 3, adims, astr, abox);
+  const CUtensorMap ma = tc_make_map(g.a, 3, adims, astr, abox);
   const uint64_t bdims[2] = {(uint64_t)g.cin, (uint64_t)g.ntap * g.N};
   const uint64_t bstr[1] = {(uint64_t)g.cin * 2};
   const uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)p.bn};
-  const CUtensorMap mb = make_map(g.w, 2, bdims, bstr, bbox);
+  const CUtensorMap mb = tc_make_map(g.w, 2, bdims, bstr, bbox);
 
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 64 * 8;
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);

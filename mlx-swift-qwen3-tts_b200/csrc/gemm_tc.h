@@ -6,6 +6,7 @@
 // A: fp16 activations, channels-last [Bt, T, Cin]; rows with negative source time are zero-filled by TMA (causal padding).
 // W: fp16 weights [ntap][N][Cin] (K-major).  Accumulation fp32 in TMEM; epilogue in registers.
 #pragma once
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include "kernels.h"
@@ -40,6 +41,21 @@ struct TcGemm {
 bool tc_gemm_supported(const TcGemm& g);
 void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g);
 void init_tc_gemm();  // resolves cuTensorMapEncodeTiled, sets kernel attributes; once per process/device
+
+// Skinny variant for <= 128 activation rows (batched decode steps, short codec windows), gemm_skinny.cu: the WEIGHT tile is the
+// 128-row UMMA operand, the activation rows are the N dimension, K is split across a thread-block cluster and reduced through
+// distributed shared memory, so a [m <= 128] x N x K linear spreads over ~all SMs instead of N/bn CTAs walking all of K.
+// launch_tc_gemm routes to it when tc_skinny_supported(g).
+bool tc_skinny_supported(const TcGemm& g);
+void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g);
+void init_tc_skinny();
+// measurement hook: per-CTA phase stamps (10 x u64 per CTA) of the following launches go to dev_buf (null = off)
+void tc_skinny_set_trace(unsigned long long* dev_buf);
+void tc_skinny_grid(const TcGemm& g, int* tiles, int* split, int* stages);
+
+// shared host helpers (gemm_tc.cu)
+void tc_resolve_encode();
+CUtensorMap tc_make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 // fp32 -> fp16 helpers used around the tensor-core contractions
 void launch_f32_to_f16(const LaunchCtx& c, const float* x, size_t n, __half* y);

@@ -48,6 +48,14 @@ CASES = [
     (1, 130, 1024, 384, 1, 1),   # N = 384 -> 2 tiles of 192
     (64, 1, 1024, 3072, 1, 1),   # batched decode: 64 utterances x 1 row each (T = 1 per batch item)
     (1, 64, 1024, 2048, 1, 1),   # the same as one 64-row matrix
+    # <= 128 rows and one tap route to the split-K cluster kernel (gemm_skinny.cu)
+    (1, 17, 2048, 1024, 1, 1),   # o_proj shape: 8 weight tiles x 8 K slices, m_pad 32 (mc = 4)
+    (1, 64, 3072, 1024, 1, 1),   # down_proj shape: 48 k-blocks over 8 CTAs, ring wraps
+    (1, 128, 1024, 2048, 1, 1),  # m_pad 128 (code-predictor pass 0: two rows per utterance)
+    (1, 100, 1024, 6144, 1, 1),  # gate|up shape: 48 tiles x 2 slices of 8 k-blocks
+    (2, 33, 96, 96, 1, 1),       # N = 96 < one weight tile, cin = 96: second k-block half zero-filled; 66 rows -> m_pad 128
+    (1, 40, 64, 160, 1, 1),      # one k-block: no split possible
+    (1, 3, 320, 32, 1, 1),       # 5 k-blocks over 4 slices: uneven split
 ]
 
 
@@ -95,6 +103,43 @@ def test_tc_epilogues():
     ch = np.arange(N) % 64
     assert np.abs(y32 - base).max() < 2e-4
     assert np.abs(y16 - (base + ieb[ch] * np.sin(base * ea[ch]) ** 2)).max() < 4e-3
+
+
+@pytest.mark.parametrize("M", [20, 64, 128])
+def test_tc_skinny_epilogues(M):
+    """Same epilogues through the <= 128-row cluster kernel (rows owned by different CTAs of the cluster)."""
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(M)
+    cin, N = 1024, 512
+    x = rng.standard_normal((1, M, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, N, cin)) / np.sqrt(cin)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    y32, y16 = q.conv_probe(x, w, bias, act=1)
+    want = ref_conv(x, w, bias, 1, 1, act=1)
+    assert np.abs(y32 - want).max() < 2e-4 and np.abs(y16 - want).max() < 4e-3
+    y32, _ = q.conv_probe(x, w, bias, act=2)
+    assert np.abs(y32 - ref_conv(x, w, bias, 1, 1, act=2)).max() < 2e-4
+    res = rng.standard_normal((1, M, N)).astype(np.float32)
+    scale = rng.uniform(0.3, 0.7, N).astype(np.float32)
+    y32, _ = q.conv_probe(x, w, bias, res=res, scale=scale)
+    assert np.abs(y32 - ref_conv(x, w, bias, 1, 1, res=res, scale=scale)).max() < 2e-4
+    y32, _ = q.conv_probe(x, w, None, res=res)
+    assert np.abs(y32 - ref_conv(x, w, None, 1, 1, res=res)).max() < 2e-4
+    y32, y16 = q.conv_probe(x, w, None, swiglu=True)
+    want = ref_conv(x, w, None, 1, 1, swiglu=True)
+    assert y32.shape == (1, M, N // 2) and np.abs(y32 - want).max() < 2e-4 and np.abs(y16 - want).max() < 4e-3
+
+
+def test_tc_skinny_is_deterministic():
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((1, 64, 2048)).astype(np.float32)
+    w = (rng.standard_normal((1, 1024, 2048)) / 45).astype(np.float32)
+    a, _ = q.conv_probe(x, w, None)
+    b, _ = q.conv_probe(x, w, None)
+    assert np.array_equal(a, b)
 
 
 def test_simt_conv_matches_numpy():
