@@ -416,19 +416,23 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 }
 // Decode-step fusion of q/k norm + RoPE + KV append + window attention (one launch instead of two, no q/k round trip through
 // HBM).  Valid only when every slot contributes ONE row to the launch (talker step, code-predictor passes >= 1): the keys of
-// positions < pos were written by earlier launches, the current position's k/v are produced here and used from shared memory.
+// positions < pos were written by earlier launches, the current position's k/v are appended here (same CTA: visible after the
+// barrier).
+// Single pass, flash-decoding style: the 128 threads form 16 groups of 8 lanes; a group owns keys j = group, group + 16, ...
+// and each lane 16 of the 128 dims (4 x float4, so the 8 lanes of a group read one 512-byte K row and one V row fully
+// coalesced).  Per key: 8 independent 128-bit loads per lane (two keys in flight), a 3-step shuffle reduce of the partial dot
+// products, an online-softmax update of the lane's 16 output dims.  Groups are merged at the end (2 shuffle steps inside a
+// warp, shared memory across the 4 warps).  The previous version (thread-per-key score loop with 8 loads in flight, three
+// block barriers, 4 V loads in flight) spent ~11 us per launch on dependent round trips even for 2-17 keys.
 template <int G, typename OutT>
 __global__ void __launch_bounds__(128) rope_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                              const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
                                                              const float* __restrict__ inv_freq, const int* __restrict__ row_slot,
                                                              const int* __restrict__ row_pos, const int* __restrict__ win_start, KVLayout kv,
                                                              OutT* __restrict__ out, int ldo, float scale) {
-  extern __shared__ __align__(16) float sm[];
-  float* q = sm;                  // [G][128]
-  float* kcur = sm + G * 128;     // [128]
-  float* vcur = kcur + 128;       // [128]
-  float* sc = vcur + 128;         // [G][S]
-  __shared__ float red_sum[G];
+  __shared__ __align__(16) float q[G * 128];
+  __shared__ __align__(16) float part_o[4][G][128];
+  __shared__ float part_m[4][G], part_l[4][G];
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -452,67 +456,104 @@ __global__ void __launch_bounds__(128) rope_attention_kernel(const float* __rest
     sincosf((float)pos * inv_freq[lane], &s0, &c0);
     sincosf((float)pos * inv_freq[lane + 32], &s1, &c1);
     const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
-    float* dst = hh < G ? q + hh * 128 : kcur;
+    float* dst = hh < G ? q + hh * 128 : kb + (size_t)ring * 128;  // k is appended to the ring (:197-201)
     dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
-    if (hh == G) {  // append k to the ring (:197-201)
-      float* kd = kb + (size_t)ring * 128;
-      kd[lane] = o0; kd[lane + 32] = o1; kd[lane + 64] = o2; kd[lane + 96] = o3;
-    }
   }
-  {
-    const float v = rowp[(size_t)(heads + kv_heads + kvh) * 128 + tid];
-    vcur[tid] = v;
-    vb[(size_t)ring * 128 + tid] = v;
-  }
+  vb[(size_t)ring * 128 + tid] = rowp[(size_t)(heads + kv_heads + kvh) * 128 + tid];
   __syncthreads();
-  // phase 1: scores; the newest key comes from shared memory
-  for (int j = tid; j < S; j += 128) {
-    const float4* kr = (j == S - 1) ? reinterpret_cast<const float4*>(kcur) : reinterpret_cast<const float4*>(kb + (size_t)((w0 + j) % cap) * 128);
-    float acc[G];
+  // phase 1: one pass over the window
+  const int seg = lane & 7, grp = warp * 4 + (lane >> 3);
+  float qf[G][16];
 #pragma unroll
-    for (int g = 0; g < G; ++g) acc[g] = 0.f;
-#pragma unroll 8
-    for (int d = 0; d < 32; ++d) {
-      const float4 kk = kr[d];
+  for (int g = 0; g < G; ++g)
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float4 qq = reinterpret_cast<const float4*>(q + g * 128)[d];
-        acc[g] += kk.x * qq.x + kk.y * qq.y + kk.z * qq.z + kk.w * qq.w;
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(q + g * 128 + i * 32 + seg * 4);
+      qf[g][4 * i] = t.x * scale; qf[g][4 * i + 1] = t.y * scale; qf[g][4 * i + 2] = t.z * scale; qf[g][4 * i + 3] = t.w * scale;
+    }
+  float mx[G], l[G], o[G][16];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    mx[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) o[g][d] = 0.f;
+  }
+  for (int jb = 0; jb < S; jb += 32) {  // keys jb + grp and jb + grp + 16 of this group: 16 independent 128-bit loads in flight
+    const int j0 = jb + grp;              // (the trip count is the same for every lane: the shuffles below stay convergent)
+    float4 kk[2][4], vv[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + 16 * u;
+      const size_t base = (size_t)((w0 + (j < S ? j : 0)) % cap) * 128 + seg * 4;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        kk[u][i] = *reinterpret_cast<const float4*>(kb + base + i * 32);
+        vv[u][i] = *reinterpret_cast<const float4*>(vb + base + i * 32);
       }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) sc[g * S + j] = acc[g] * scale;
-  }
-  __syncthreads();
-  for (int g = warp; g < G; g += 4) {
-    float mx = -INFINITY;
-    for (int j = lane; j < S; j += 32) mx = fmaxf(mx, sc[g * S + j]);
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < S; j += 32) { const float e = expf(sc[g * S + j] - mx); sc[g * S + j] = e; sum += e; }
-    sum = warp_sum(sum);
-    if (lane == 0) red_sum[g] = sum;
-  }
-  __syncthreads();
-  float o[G];
+    for (int u = 0; u < 2; ++u) {
+      const bool valid = j0 + 16 * u < S;
 #pragma unroll
-  for (int g = 0; g < G; ++g) o[g] = 0.f;
-  int j = 0;
-  for (; j + 4 <= S - 1; j += 4) {  // 4 independent V loads in flight
-    const float v0 = vb[(size_t)((w0 + j) % cap) * 128 + tid], v1 = vb[(size_t)((w0 + j + 1) % cap) * 128 + tid];
-    const float v2 = vb[(size_t)((w0 + j + 2) % cap) * 128 + tid], v3 = vb[(size_t)((w0 + j + 3) % cap) * 128 + tid];
+      for (int g = 0; g < G; ++g) {
+        float sdot = 0.f;
 #pragma unroll
-    for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j + 3], v3, fmaf(sc[g * S + j + 2], v2, fmaf(sc[g * S + j + 1], v1, fmaf(sc[g * S + j], v0, o[g]))));
-  }
-  for (; j < S - 1; ++j) {
-    const float vv = vb[(size_t)((w0 + j) % cap) * 128 + tid];
+        for (int i = 0; i < 4; ++i)
+          sdot += kk[u][i].x * qf[g][4 * i] + kk[u][i].y * qf[g][4 * i + 1] + kk[u][i].z * qf[g][4 * i + 2] + kk[u][i].w * qf[g][4 * i + 3];
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+        sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+        if (!valid) sdot = -INFINITY;
+        const float mn = fmaxf(mx[g], sdot);
+        const bool none = mn == -INFINITY;  // no key seen yet and this one is out of range
+        const float corr = none ? 1.f : expf(mx[g] - mn), pr = none ? 0.f : expf(sdot - mn);
+        mx[g] = mn;
+        l[g] = l[g] * corr + pr;
 #pragma unroll
-    for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
+        for (int i = 0; i < 4; ++i) {
+          o[g][4 * i] = o[g][4 * i] * corr + pr * vv[u][i].x;
+          o[g][4 * i + 1] = o[g][4 * i + 1] * corr + pr * vv[u][i].y;
+          o[g][4 * i + 2] = o[g][4 * i + 2] * corr + pr * vv[u][i].z;
+          o[g][4 * i + 3] = o[g][4 * i + 3] * corr + pr * vv[u][i].w;
+        }
+      }
+    }
   }
+  // merge the 4 groups of a warp, then the 4 warps
 #pragma unroll
   for (int g = 0; g < G; ++g) {
-    o[g] = fmaf(sc[g * S + S - 1], vcur[tid], o[g]);
-    store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, o[g] / red_sum[g]);
+    float m_all = fmaxf(mx[g], __shfl_xor_sync(0xffffffffu, mx[g], 8));
+    m_all = fmaxf(m_all, __shfl_xor_sync(0xffffffffu, m_all, 16));
+    const float f = (mx[g] == -INFINITY) ? 0.f : expf(mx[g] - m_all);  // a warp with no key at all keeps m_all = -inf
+    float lw = l[g] * f;
+    lw += __shfl_xor_sync(0xffffffffu, lw, 8);
+    lw += __shfl_xor_sync(0xffffffffu, lw, 16);
+#pragma unroll
+    for (int d = 0; d < 16; ++d) {
+      float t = o[g][d] * f;
+      t += __shfl_xor_sync(0xffffffffu, t, 8);
+      t += __shfl_xor_sync(0xffffffffu, t, 16);
+      o[g][d] = t;
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(&part_o[warp][g][i * 32 + seg * 4]) = make_float4(o[g][4 * i], o[g][4 * i + 1], o[g][4 * i + 2], o[g][4 * i + 3]);
+      if (lane == 0) { part_m[warp][g] = m_all; part_l[warp][g] = lw; }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    float m_all = fmaxf(fmaxf(part_m[0][g], part_m[1][g]), fmaxf(part_m[2][g], part_m[3][g]));
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float f = (part_m[w][g] == -INFINITY) ? 0.f : expf(part_m[w][g] - m_all);
+      num += part_o[w][g][tid] * f;
+      den += part_l[w][g] * f;
+    }
+    store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, num / den);
   }
 }
 template <typename OutT>
@@ -522,8 +563,7 @@ static void launch_rope_attention_t(const LaunchCtx& c, const float* qkv, int ld
   if (m <= 0) return;
   const int G = heads / kv_heads;
   const float scale = 1.0f / sqrtf(128.0f);
-  const size_t smem = (size_t)(G * 128 + 256 + G * kv.capacity) * sizeof(float);
-  Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
+  const size_t smem = 0;
   dim3 grid(m, kv_heads);
   const bool pdl = pdl_enabled();
   if (G == 1) launch_kernel_pdl(rope_attention_kernel<1, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
