@@ -70,17 +70,18 @@ class TalkerEngine {
                    const int32_t* token_set, int n_set, uint64_t seed, uint64_t counter);
 
  private:
-  // one_row_per_slot: decode steps may fuse norm+RoPE+append into the attention launch (prefill / CP pass 0 may not)
+  // one_row_per_slot: decode steps may fuse norm+RoPE+append into the attention launch (prefill / CP pass 0 may not);
+  // decode_step: rows <= 128 may take the split-K cluster GEMM (prefill stays on the 128-row-tile kernel: batch invariance)
   void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
                      const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity,
-                     bool one_row_per_slot);
+                     bool one_row_per_slot, bool decode_step);
   void issue_frame(int n_slots);
   void build_tc_weights();
   void build_mega_plan();
-  TcLinear make_tc(const Linear& L, bool interleave_halves);
+  TcLinear make_tc(const Linear& L, bool interleave_halves, const float* fold = nullptr);
   bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }
   // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
-  void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu);
+  void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu, bool row_count_invariant = false);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
 
   TalkerConfig cfg_;
@@ -93,6 +94,8 @@ class TalkerEngine {
 
   int max_rows_ = 0, max_tp_rows_ = 0, set_words_ = 0;
   int tc_min_rows_ = 16;  // rows from which linears run on tensor cores (env Q3TTS_TC_MIN_ROWS; 0 disables)
+  float* d_rs_ = nullptr;                     // [max_rows] RMSNorm row factors for the 128-row-tile kernel (prefill)
+  static constexpr float kX16Div = 16.0f;     // the fp16 copy of the residual stream is x / 16 (range headroom; exact power of two)
   void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;
   // device buffers
   float *kcache_ = nullptr, *vcache_ = nullptr, *cp_k_ = nullptr, *cp_v_ = nullptr;

@@ -49,6 +49,9 @@ struct SkParams {
   int ld32;
   __half* out16;
   int ld16;
+  float out16_scale;
+  const __half* rms_x;      // folded RMSNorm: fp16 activation rows [M][K] (= the B operand), or null
+  float rms_a, rms_eps, rms_mult;  // row factor = rms_mult * rsqrt(sum(x16^2) * rms_a + rms_eps)
   unsigned long long* trace;  // measurement hook (q3tts_skinny_trace): 16 stamps per CTA, or null
 };
 
@@ -80,7 +83,8 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
 // unrolled chunk, one all-purpose epilogue was ~50 KB of SASS that ran once per launch at instruction-fetch speed (2.6 us
 // per 16-column chunk measured); each instantiation now carries only its own math, at ONE call site.
 template <int NC, int ACT, bool SWIGLU>
-__device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], int valid, int m0, int ob, float bias, float scale) {
+__device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], int valid, int m0, int ob, float bias, float scale,
+                                          const float* rowscale) {
   float r[NC];
   if (p.res) {
     const float* rp = p.res + (size_t)m0 * p.ld_res + ob;
@@ -89,7 +93,9 @@ __device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], i
   }
 #pragma unroll
   for (int e = 0; e < NC; ++e) {
-    float v = acc[e] + bias;
+    float v = acc[e];
+    if (rowscale) v *= rowscale[e];  // folded RMSNorm of the input rows (shared memory, same value for the whole warp)
+    v += bias;
     if (ACT == TC_ACT_GELU) v = sk_gelu_erf(v);
     else if (ACT == TC_ACT_SILU) v = sk_silu(v);
     if (SWIGLU) {  // weight rows (2i, 2i+1) = (gate_i, up_i): adjacent TMEM lanes = adjacent threads
@@ -109,7 +115,7 @@ __device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], i
     __half* hp = p.out16 + (size_t)m0 * p.ld16 + ob;
 #pragma unroll
     for (int e = 0; e < NC; ++e, hp += p.ld16)
-      if (e < valid) *hp = __float2half_rn(acc[e]);
+      if (e < valid) *hp = __float2half_rn(acc[e] * p.out16_scale);
   }
 }
 
@@ -130,6 +136,7 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   uint64_t* red_full = tmem_full + 1;
   uint64_t* ack = red_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ack + 1);
+  float* rowscale_s = reinterpret_cast<float*>(tmem_slot + 2);  // [mc] folded-RMSNorm factors of this CTA's activation rows
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;   // cluster = (1, split, 1): the K slices of one weight tile
@@ -213,6 +220,15 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     const float bias = (p.bias && n_ok) ? p.bias[n] : 0.f;
     const int so = SWIGLU ? (n >> 1) : n;
     const float scale = (p.scale && n_ok) ? p.scale[so] : 1.f;
+    if (p.rms_x) {  // while the operands stream in: 8 lanes per activation row of this CTA's slice, 16 rows per pass
+      const int m_lo = (int)rank * p.mc, j = lane & 7;
+      for (int r0 = 0; r0 < p.mc; r0 += 16) {
+        const int r = r0 + q * 4 + (lane >> 3), m = m_lo + r;
+        float ss = (r < p.mc && m < p.M) ? tc_row_sumsq_f16(p.rms_x + (size_t)m * p.K, p.K, j) : 0.f;
+        ss = tc_group8_sum(ss);
+        if (j == 0 && r < p.mc) rowscale_s[r] = p.rms_mult * rsqrtf(ss * p.rms_a + p.rms_eps);
+      }
+    }
     if (p.split > 1) cluster_wait_acquire();  // A: every peer CTA is resident, its mbarriers initialised (long complete by now)
     mbar_wait(tmem_full, 0);
     tc_fence_after();
@@ -274,7 +290,7 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         int valid = p.M - (m_base + cb);
         valid = valid < nc ? valid : nc;
         if (!(n_ok && (!SWIGLU || (n & 1) == 0))) valid = 0;  // lanes without an output column compute (shuffle partners) but do not touch memory
-        sk_finish<16, ACT, SWIGLU>(p, a16, valid, m_base + cb, so, bias, scale);
+        sk_finish<16, ACT, SWIGLU>(p, a16, valid, m_base + cb, so, bias, scale, p.rms_x ? rowscale_s + cb : nullptr);
         if (threadIdx.x == 96 && cb == 0) SK_STAMP(12);
       }
       if (threadIdx.x == 96) SK_STAMP(13);
@@ -327,16 +343,21 @@ SkPlan plan(const TcGemm& g) {
   s.stages = std::max(1, std::min(s.stages, nkb_max));
   // the ring doubles as the outgoing staging buffer [owner][128][mc] fp32 (= red_bytes) once the MMAs are done
   while (s.stages * stage_bytes < red_bytes) ++s.stages;
-  s.smem = (size_t)s.stages * stage_bytes + red_bytes + 1024 + (2 * s.stages + 4) * 8 + 16;
+  s.smem = (size_t)s.stages * stage_bytes + red_bytes + 1024 + (2 * s.stages + 4) * 8 + 16 + 128 * 4;
   return s;
 }
 
 }  // namespace
 
-bool tc_skinny_supported(const TcGemm& g) {
+bool tc_skinny_enabled() {
   static const bool on = env_int("Q3TTS_SKINNY", 1) != 0;
+  return on;
+}
+
+bool tc_skinny_supported(const TcGemm& g) {
+  const bool on = tc_skinny_enabled();
   const long long M = (long long)g.Bt * g.T;
-  return on && g.ntap == 1 && M >= 1 && M <= 128 && !g.snake_ea && !g.pcm && !(g.swiglu && g.act != TC_ACT_NONE) && tc_gemm_supported(g);
+  return on && g.allow_skinny && g.ntap == 1 && M >= 1 && M <= 128 && !g.snake_ea && !g.pcm && !(g.swiglu && g.act != TC_ACT_NONE) && tc_gemm_supported(g);
 }
 
 using SkKernel = void (*)(const CUtensorMap, const CUtensorMap, const SkParams);
@@ -373,6 +394,10 @@ void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g) {
   p.tmem_cols = std::max(32, s.m_pad);
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
+  p.out16_scale = g.out16_scale;
+  p.rms_x = g.rms_in ? g.a : nullptr;
+  p.rms_a = 1.0f / (g.in_scale * g.in_scale * (float)g.cin); p.rms_eps = g.rms_eps; p.rms_mult = 1.0f / g.in_scale;
+  Q3_CHECK(!g.row_scale, Q3TTS_ERR_INVALID_ARG, "tc_skinny: pass rms_in instead of precomputed row factors");
   p.trace = g_sk_trace;
 
   const uint64_t wdims[2] = {(uint64_t)g.cin, (uint64_t)g.N};

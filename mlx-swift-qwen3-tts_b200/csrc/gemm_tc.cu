@@ -40,6 +40,8 @@ struct TcParams {
   const float* snake_ieb;
   int snake_ch;
   float* pcm;
+  const float* row_scale;
+  int k_rotate;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
@@ -85,7 +87,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // dependency is resolved, so the weight stream overlaps the predecessor's tail; activations (A) follow the wait.
       // Every CTA of a column of the grid reads the SAME activation tiles: walking K from a per-CTA offset keeps the CTAs
       // off each other's L2 lines (same-address storms serialise in one L2 slice and multiply the TMA latency).
-      const int rot = (int)((blockIdx.y * 5u + blockIdx.x * 3u) % (unsigned)num_kb);
+      const int rot = p.k_rotate ? (int)((blockIdx.y * 5u + blockIdx.x * 3u) % (unsigned)num_kb) : 0;
       const int pre = num_kb < p.stages ? num_kb : p.stages;
       for (int kb = 0; kb < pre; ++kb) {
         mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
@@ -142,6 +144,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (p.row_scale) {  // folded RMSNorm of the input row (TcGemm::row_scale)
+        const float rs = p.row_scale[m];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= rs;
+      }
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -300,6 +307,7 @@ void init_tc_gemm() {
 void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   if (tc_skinny_supported(g)) return launch_tc_skinny(c, g);  // <= 128 rows: split-K cluster kernel (gemm_skinny.cu)
   Q3_CHECK(tc_gemm_supported(g), Q3TTS_ERR_INVALID_ARG, "tc_gemm: unsupported shape (cin %d, N %d)", g.cin, g.N);
+  Q3_CHECK(!g.rms_in && g.out16_scale == 1.0f, Q3TTS_ERR_INVALID_ARG, "tc_gemm: rms_in / out16_scale are features of the <= 128-row kernel (use row_scale)");
   tc_resolve_encode();
   TcParams p{};
   p.Bt = g.Bt; p.T = g.T; p.cin = g.cin; p.N = g.N; p.ntap = g.ntap; p.dil = g.dil;
@@ -320,6 +328,8 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
   p.snake_ea = g.snake_ea; p.snake_ieb = g.snake_ieb; p.snake_ch = g.snake_ch > 0 ? g.snake_ch : 1;
   p.pcm = g.pcm;
+  p.row_scale = g.row_scale;
+  p.k_rotate = g.k_rotate;
 
   const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
   const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};
@@ -375,11 +385,49 @@ __global__ void __launch_bounds__(256) rmsnorm_f16_kernel(const float* __restric
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = rsqrtf(tot / (float)dim + eps);
   __half* yr = y + (size_t)blockIdx.x * ldy;
-  for (int i = threadIdx.x; i < dim; i += 256) yr[i] = __float2half_rn(xr[i] * inv * w[i]);
+  for (int i = threadIdx.x; i < dim; i += 256) yr[i] = __float2half_rn(w ? xr[i] * inv * w[i] : xr[i] * inv);
 }
 void launch_rmsnorm_f16(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, __half* y, int ldy) {
   if (m <= 0) return;
   launch_kernel_pdl(rmsnorm_f16_kernel, dim3(m), dim3(256), 0, c.stream, pdl_enabled(), x, ldx, dim, w, eps, y, ldy);
+  c.tick();
+}
+
+__global__ void scale_to_f16_kernel(const float* __restrict__ x, size_t n4, float scale, __half* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(x)[i];
+    __half2 a = __floats2half2_rn(v.x * scale, v.y * scale), b = __floats2half2_rn(v.z * scale, v.w * scale);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+    reinterpret_cast<uint2*>(y)[i] = pk;
+  }
+}
+void launch_scale_to_f16(const LaunchCtx& c, const float* x, size_t n, float scale, __half* y) {
+  if (n == 0) return;
+  Q3_CHECK(n % 4 == 0, Q3TTS_ERR_INVALID_ARG, "scale_to_f16: length must be a multiple of 4");
+  const size_t n4 = n / 4;
+  const int blocks = (int)std::min<size_t>((n4 + 255) / 256, 148 * 32);
+  launch_kernel_pdl(scale_to_f16_kernel, dim3(blocks), dim3(256), 0, c.stream, pdl_enabled(), x, n4, scale, y);
+  c.tick();
+}
+
+// one 8-lane group per row (tc_row_sumsq_f16 order: bit-identical to the factors the skinny kernel derives for itself)
+__global__ void __launch_bounds__(128) row_scale_kernel(const __half* __restrict__ a, int m, int dim, float rms_a, float eps, float mult,
+                                                        float* __restrict__ rs) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * 16 + (threadIdx.x >> 3), j = threadIdx.x & 7;
+  float ss = row < m ? tc_row_sumsq_f16(a + (size_t)row * dim, dim, j) : 0.f;
+  ss = tc_group8_sum(ss);
+  if (j == 0 && row < m) rs[row] = mult * rsqrtf(ss * rms_a + eps);
+}
+void launch_row_scale(const LaunchCtx& c, const __half* a, int m, int dim, float in_scale, float eps, float* rs) {
+  if (m <= 0) return;
+  Q3_CHECK(dim % 8 == 0, Q3TTS_ERR_INVALID_ARG, "row_scale: row length must be a multiple of 8");
+  launch_kernel_pdl(row_scale_kernel, dim3((m + 15) / 16), dim3(128), 0, c.stream, pdl_enabled(), a, m, dim, 1.0f / (in_scale * in_scale * (float)dim),
+                    eps, 1.0f / in_scale, rs);
   c.tick();
 }
 

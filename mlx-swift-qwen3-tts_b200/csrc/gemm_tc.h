@@ -35,6 +35,22 @@ struct TcGemm {
   const float* snake_ieb = nullptr;  // ch = n % snake_ch (Vocoder/SpeechTokenizer.swift:105-109)
   int snake_ch = 0;
   float* pcm = nullptr;              // output conv: column 0 only, clip(-1, 1) + NaN scrub, [M] (SpeechTokenizer.swift:823-840, 951)
+  // RMSNorm folded around the contraction (Model/Qwen3Layers.swift:8-26 with the norm WEIGHT multiplied into the columns of W at
+  // load, TalkerEngine::make_tc): the activation operand is a = fp16(x * in_scale) of the un-normalised residual stream x, and
+  // row m of the accumulator is multiplied by (1 / in_scale) * rsqrt(mean(x[m]^2) + rms_eps) before bias / activation.
+  //   rms_in = 1: the kernel computes the row factors itself from `a` (skinny kernel only: its epilogue warps do it while the
+  //               operands stream in, in the fixed order of tc_row_sumsq_f16);
+  //   row_scale : precomputed factors [M] (launch_row_scale, same summation order) for the 128-row-tile kernel.
+  int rms_in = 0;
+  float rms_eps = 0.0f, in_scale = 1.0f;
+  const float* row_scale = nullptr;
+  float out16_scale = 1.0f;          // out16 = fp16(y * out16_scale): the producer side of the same scheme
+  // 0: always the 128-row-tile kernel, whatever the row count.  Prefill uses it so that a request's numbers do not depend on
+  // how many rows of OTHER requests shared its GEMMs (the two kernels add the K dimension up in different orders).
+  int allow_skinny = 1;
+  // 0: every CTA of the 128-row-tile kernel walks K from 0 (default: from a per-CTA offset, which spreads same-address L2 reads
+  // but makes the fp32 summation order -- the low bits of a row's result -- depend on the tile shape, i.e. on the row count)
+  int k_rotate = 1;
 };
 
 // true when the tcgen05 path can run this shape (else the caller uses the SIMT kernel)
@@ -60,6 +76,12 @@ CUtensorMap tc_make_map(const void* base, int rank, const uint64_t* dims, const 
 // fp32 -> fp16 helpers used around the tensor-core contractions
 void launch_f32_to_f16(const LaunchCtx& c, const float* x, size_t n, __half* y);
 // RMSNorm (fp32 in) -> fp16 out
+// (w may be null = ones: the norm weight lives in the consumer's folded fp16 copy)
 void launch_rmsnorm_f16(const LaunchCtx& c, const float* x, int ldx, int m, int dim, const float* w, float eps, __half* y, int ldy);
+// y = fp16(x * scale), elementwise (entry of a stack on the folded-RMSNorm path)
+void launch_scale_to_f16(const LaunchCtx& c, const float* x, size_t n, float scale, __half* y);
+// rs[m] = (1 / in_scale) * rsqrt(sum(a[m][:]^2) / (in_scale^2 * dim) + eps) for fp16 rows a = fp16(x * in_scale)
+void launch_row_scale(const LaunchCtx& c, const __half* a, int m, int dim, float in_scale, float eps, float* rs);
+bool tc_skinny_enabled();  // Q3TTS_SKINNY != 0
 
 }  // namespace q3

@@ -55,7 +55,9 @@ void launch_rope_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int
 void launch_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                           const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, __half* out, int ldo);
 // dense weight (bf16 / f16 / f32) -> fp16 copy; optional row interleave of two halves ([gate ; up] -> gate_0, up_0, gate_1, ...)
-void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst);
+// col_scale (fp32 [cols], may be null): dst[r][c] = fp16(w[r][c] * col_scale[c]) -- an RMSNorm weight folded into the consumer linear
+void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst,
+                          const float* col_scale = nullptr);
 void launch_gather_rows_f16(const LaunchCtx& c, const Embedding& e, const int* ids, int n, __half* y, int ldy);
 
 // rows of an embedding table -> fp32: y[i][:] (= or +=) table[ids[i]][:]

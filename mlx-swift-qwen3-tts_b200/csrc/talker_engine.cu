@@ -80,6 +80,7 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
     d_h16_ = arena_.alloc((size_t)max_rows_ * std::max(wide_h, cfg_.text_hidden_size) * 2);
     d_attn16_ = arena_.alloc((size_t)max_rows_ * attn_w * 2);
     d_act16_ = arena_.alloc((size_t)max_rows_ * act_w * 2);
+    d_rs_ = arena_.alloc_n<float>((size_t)max_rows_);
     d_tpe16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
     d_tph16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
   }
@@ -347,12 +348,22 @@ void TalkerEngine::drop_graphs() {
 
 // fp16 dense copy of one Linear for the tcgen05 path.  Packed leaves go through the bit-exact dequant kernel (deq16 =
 // round(fp32(scale) * q + fp32(bias))), float leaves are rounded to fp16.
-TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves) {
+// `fold` (fp32 [in], may be null): the RMSNorm weight that precedes this linear, multiplied into its columns in fp32 before the
+// fp16 rounding (Model/Qwen3Layers.swift:8-26, 246-257: norm(x) * w feeds exactly this linear), so the norm's row factor can be
+// applied to the accumulator instead (TcGemm::ss_in).
+TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves, const float* fold) {
   const LaunchCtx c{stream_, nullptr};
   TcLinear t;
   t.out = L.out; t.in = L.in; t.bias = L.bias;
   __half* dst = (__half*)arena_.alloc((size_t)L.out * L.in * 2);
-  if (L.bits) {
+  if (L.bits && fold) {
+    float* tmp = nullptr;
+    Q3_CUDA(cudaMalloc(&tmp, (size_t)L.out * L.in * 4));
+    launch_dequantize(c, L.qw, L.scales, L.biases, L.sdt, L.out, L.in, L.group, L.bits, Q3TTS_F32, tmp);
+    launch_weight_to_f16(c, tmp, Q3TTS_F32, L.out, L.in, interleave_halves, dst, fold);
+    Q3_CUDA(cudaStreamSynchronize(stream_));
+    cudaFree(tmp);
+  } else if (L.bits) {
     if (!interleave_halves) {
       launch_dequantize(c, L.qw, L.scales, L.biases, L.sdt, L.out, L.in, L.group, L.bits, Q3TTS_F16, dst);
     } else {
@@ -364,7 +375,7 @@ TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves) {
       cudaFree(tmp);
     }
   } else {
-    launch_weight_to_f16(c, L.w, L.sdt, L.out, L.in, interleave_halves, dst);
+    launch_weight_to_f16(c, L.w, L.sdt, L.out, L.in, interleave_halves, dst, fold);
   }
   t.w = dst;
   return t;
@@ -380,24 +391,25 @@ void TalkerEngine::build_tc_weights() {
   for (StackWeights* S : {&w_.talker, &w_.cp}) {
     S->tc.resize(S->layers);
     for (int l = 0; l < S->layers; ++l) {
-      S->tc[l].qkv = make_tc(S->layer[l].qkv, false);
+      S->tc[l].qkv = make_tc(S->layer[l].qkv, false, S->layer[l].in_norm);         // input_layernorm folded in
       S->tc[l].o = make_tc(S->layer[l].o, false);
-      S->tc[l].gate_up_il = make_tc(S->layer[l].gate_up, true);
+      S->tc[l].gate_up_il = make_tc(S->layer[l].gate_up, true, S->layer[l].post_norm);  // post_attention_layernorm folded in
       S->tc[l].down = make_tc(S->layer[l].down, false);
     }
   }
   w_.fc1_tc = make_tc(w_.fc1, false);
   w_.fc2_tc = make_tc(w_.fc2, false);
   w_.codec_head_tc = make_tc(w_.codec_head, false);
-  for (auto& h : w_.lm_head) w_.lm_head_tc.push_back(make_tc(h, false));
+  for (auto& h : w_.lm_head) w_.lm_head_tc.push_back(make_tc(h, false, w_.cp.final_norm));  // code predictor's final norm folded in
   if (w_.has_mtp) w_.small_to_mtp_tc = make_tc(w_.small_to_mtp, false);
   Q3_CUDA(cudaStreamSynchronize(stream_));
   w_.has_tc = true;
 }
 
 void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res,
-                             int act, int swiglu) {
+                             int act, int swiglu, bool row_count_invariant) {
   TcGemm g;
+  if (row_count_invariant) { g.allow_skinny = 0; g.k_rotate = 0; }  // prefill: see forward_stack
   g.a = (const __half*)x16; g.w = (const __half*)L.w; g.Bt = 1; g.T = m; g.cin = L.in; g.N = L.out; g.ntap = 1; g.dil = 1;
   g.bias = L.bias; g.res = res; g.ld_res = ld32; g.act = act; g.swiglu = swiglu;
   g.out32 = out32; g.ld32 = ld32; g.out16 = (__half*)out16; g.ld16 = ld16;
@@ -407,18 +419,52 @@ void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* o
 // Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
 void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
                                  const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
-                                 size_t layer_stride, int capacity, bool one_row_per_slot) {
+                                 size_t layer_stride, int capacity, bool one_row_per_slot, bool decode_step) {
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
   if (use_tc(m) && !S.tc.empty()) {
-    // tcgen05 path (rows >= tc_min_rows_): fp16 operands, fp32 accumulate, fp32 residual stream; 8 launches per layer
+    // tcgen05 path (rows >= tc_min_rows_): fp16 operands, fp32 accumulate, fp32 residual stream.  RMSNorm is folded around the
+    // contractions: its WEIGHT lives in the fp16 copies of qkv / gate|up (make_tc), its per-row factor is applied to the
+    // accumulator, and the activation operand is d_h16_ = fp16(x / 16) of the un-normalised stream.
+    //   <= 128 rows (decode steps): 5 launches per layer -- the o / down GEMMs write fp16(x / 16) next to x, the qkv / gate|up
+    //      GEMMs derive the row factors from their own operand (TcGemm::rms_in);
+    //   prefill (any row count): the same arithmetic on the 128-row-tile kernel with precomputed factors (launch_row_scale).
+    //      Every output row of either kernel depends only on its own input row and on the weight shape, so a request's
+    //      result does not depend on which other requests shared its launches (tests: batched == single, bit for bit).
+    const bool fused = decode_step && m <= 128 && tc_skinny_enabled();
+    const float inv16 = 1.0f / kX16Div;
+    auto consumer = [&](const TcLinear& L, float* out32, int ld32, void* out16, int ld16, int swiglu) {
+      TcGemm g;
+      g.a = (const __half*)d_h16_; g.w = (const __half*)L.w; g.Bt = 1; g.T = m; g.cin = L.in; g.N = L.out;
+      g.bias = L.bias; g.swiglu = swiglu; g.out32 = out32; g.ld32 = ld32; g.out16 = (__half*)out16; g.ld16 = ld16;
+      g.rms_eps = S.eps; g.in_scale = inv16; g.allow_skinny = fused; g.k_rotate = fused;
+      if (fused) {
+        g.rms_in = 1;
+      } else {
+        launch_row_scale(c, (const __half*)d_h16_, m, S.hidden, inv16, S.eps, d_rs_);
+        g.row_scale = d_rs_;
+      }
+      launch_tc_gemm(c, g);
+    };
+    auto producer = [&](const TcLinear& L, const void* a16) {  // x += a . W^T, and refresh d_h16_ = fp16(x / 16)
+      TcGemm g;
+      g.a = (const __half*)a16; g.w = (const __half*)L.w; g.Bt = 1; g.T = m; g.cin = L.in; g.N = L.out;
+      g.bias = L.bias; g.res = x; g.ld_res = S.hidden; g.out32 = x; g.ld32 = S.hidden; g.allow_skinny = fused; g.k_rotate = fused;
+      if (fused) {
+        g.out16 = (__half*)d_h16_; g.ld16 = S.hidden; g.out16_scale = inv16;
+        launch_tc_gemm(c, g);
+      } else {
+        launch_tc_gemm(c, g);
+        launch_scale_to_f16(c, x, (size_t)m * S.hidden, inv16, (__half*)d_h16_);
+      }
+    };
+    launch_scale_to_f16(c, x, (size_t)m * S.hidden, inv16, (__half*)d_h16_);
     for (int l = 0; l < S.layers; ++l) {
       const LayerWeights& L = S.layer[l];
       const LayerTc& Tc = S.tc[l];
       KVLayout kv;
       kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
-      launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.in_norm, S.eps, (__half*)d_h16_, S.hidden);
-      linear_tc(Tc.qkv, d_h16_, m, d_qkv_, qkv_ld, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+      consumer(Tc.qkv, d_qkv_, qkv_ld, nullptr, 0, 0);
       if (one_row_per_slot) {
         launch_rope_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
                                   (__half*)d_attn16_, attn_ld);
@@ -427,10 +473,9 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
                                    row_pos, kv);
         launch_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, (__half*)d_attn16_, attn_ld);
       }
-      linear_tc(Tc.o, d_attn16_, m, x, S.hidden, nullptr, 0, x, TC_ACT_NONE, 0);
-      launch_rmsnorm_f16(c, x, S.hidden, m, S.hidden, L.post_norm, S.eps, (__half*)d_h16_, S.hidden);
-      linear_tc(Tc.gate_up_il, d_h16_, m, nullptr, 0, d_act16_, S.inter, nullptr, TC_ACT_NONE, 1);
-      linear_tc(Tc.down, d_act16_, m, x, S.hidden, nullptr, 0, x, TC_ACT_NONE, 0);
+      producer(Tc.o, d_attn16_);
+      consumer(Tc.gate_up_il, nullptr, 0, d_act16_, S.inter, 1);
+      producer(Tc.down, d_act16_);
     }
     return;
   }
@@ -558,8 +603,8 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
   // text_projection(text_embedding(ids)) (Model/Qwen3Talker.swift:103-106; Qwen3Layers.swift:276-279)
   if (use_tc(n_tp)) {
     launch_gather_rows_f16(c, w_.text_embedding, d_ids_, n_tp, (__half*)d_tpe16_, TH);
-    linear_tc(w_.fc1_tc, d_tpe16_, n_tp, nullptr, 0, d_tph16_, TH, nullptr, TC_ACT_SILU, 0);
-    linear_tc(w_.fc2_tc, d_tph16_, n_tp, d_tp_, H, nullptr, 0, nullptr, TC_ACT_NONE, 0);
+    linear_tc(w_.fc1_tc, d_tpe16_, n_tp, nullptr, 0, d_tph16_, TH, nullptr, TC_ACT_SILU, 0, true);
+    linear_tc(w_.fc2_tc, d_tph16_, n_tp, d_tp_, H, nullptr, 0, nullptr, TC_ACT_NONE, 0, true);
   } else {
     launch_gather_rows(c, w_.text_embedding, d_ids_, n_tp, d_tpe_, TH, false);
     launch_linear(c, w_.fc1, d_tpe_, TH, n_tp, d_tph_, TH, nullptr, 0.f, EPI_SILU);
@@ -573,7 +618,7 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
     Q3_CUDA(cudaMemcpyAsync(tr + (size_t)p.n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
   }
   // prefill: every row at its own (slot, position) (Model/Qwen3Talker.swift:437)
-  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false);
+  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false, false);
   // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
   for (const Plan& p : plans) {
     launch_rmsnorm(c, d_x_ + (size_t)(p.row0 + p.P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)p.slot * H, H);
@@ -659,10 +704,17 @@ void TalkerEngine::issue_frame(int n_slots) {
       x = d_cpx_;
     }
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
-                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0);
+                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
-    if (use_tc(n_slots)) {
-      launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, w_.cp.final_norm, w_.cp.eps, (__half*)d_h16_, Hcp);
+    if (use_tc(n_slots) && g != 0 && n_slots <= 128 && tc_skinny_enabled()) {
+      // the last layer's down GEMM left fp16(x / 16) in d_h16_: lm_head (final norm folded in) takes it as is
+      TcGemm hg;
+      hg.a = (const __half*)d_h16_; hg.w = (const __half*)w_.lm_head_tc[g].w; hg.Bt = 1; hg.T = n_slots; hg.cin = Hcp; hg.N = Vc;
+      hg.bias = w_.lm_head_tc[g].bias; hg.out32 = d_cplogits_; hg.ld32 = Vc;
+      hg.rms_in = 1; hg.rms_eps = w_.cp.eps; hg.in_scale = 1.0f / kX16Div;
+      launch_tc_gemm(c, hg);
+    } else if (use_tc(n_slots)) {
+      launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, nullptr, w_.cp.eps, (__half*)d_h16_, Hcp);
       linear_tc(w_.lm_head_tc[g], d_h16_, n_slots, d_cplogits_, Vc, nullptr, 0, nullptr, TC_ACT_NONE, 0);
     } else if (g == 0) {
       launch_linear(c, w_.lm_head[0], x + Hcp, 2 * Hcp, n_slots, d_cplogits_, Vc, w_.cp.final_norm, w_.cp.eps, EPI_STORE);
@@ -677,7 +729,7 @@ void TalkerEngine::issue_frame(int n_slots) {
                         d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_);
   launch_step_rows(c, n_slots, d_state_, d_step_slot_, d_step_pos_, d_win_);
   forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
-                kv_layer_stride_, opt_.kv_capacity, true);
+                kv_layer_stride_, opt_.kv_capacity, true, true);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
   if (use_tc(n_slots)) {
     launch_f32_to_f16(c, d_hlast_, (size_t)n_slots * H, (__half*)d_h16_);

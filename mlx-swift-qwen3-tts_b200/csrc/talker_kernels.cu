@@ -611,20 +611,23 @@ void launch_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int m, i
   launch_attention_t<__half>(c, qkv, ld, m, heads, kv_heads, head_dim, row_slot, row_pos, win_start, kv, out, ldo);
 }
 
-__global__ void weight_to_f16_kernel(const void* __restrict__ w, int dt, int rows, int cols, int interleave, __half* __restrict__ dst) {
+__global__ void weight_to_f16_kernel(const void* __restrict__ w, int dt, int rows, int cols, int interleave, const float* __restrict__ col_scale,
+                                     __half* __restrict__ dst) {
   const size_t total = (size_t)rows * cols;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), cidx = (int)(i - (size_t)r * cols);
     int dr = r;
     if (interleave) dr = r < rows / 2 ? 2 * r : 2 * (r - rows / 2) + 1;
-    dst[(size_t)dr * cols + cidx] = __float2half_rn(load_as_f32(w, i, dt));
+    const float v = load_as_f32(w, i, dt);
+    dst[(size_t)dr * cols + cidx] = __float2half_rn(col_scale ? v * col_scale[cidx] : v);
   }
 }
-void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst) {
+void launch_weight_to_f16(const LaunchCtx& c, const void* w, int dt, int rows, int cols, bool interleave_halves, __half* dst,
+                          const float* col_scale) {
   const size_t total = (size_t)rows * cols;
   if (total == 0) return;
   const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-  weight_to_f16_kernel<<<blocks, 256, 0, c.stream>>>(w, dt, rows, cols, interleave_halves ? 1 : 0, dst);
+  weight_to_f16_kernel<<<blocks, 256, 0, c.stream>>>(w, dt, rows, cols, interleave_halves ? 1 : 0, col_scale, dst);
   c.tick();
 }
 

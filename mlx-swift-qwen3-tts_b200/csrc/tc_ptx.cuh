@@ -2,6 +2,7 @@
 // issue / commit, TMEM loads, cluster barrier + DSMEM stores.  sm_100a only.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 namespace q3 {
@@ -112,6 +113,33 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t mbar_cluster_addr) {
 // ... without ordering any of this thread's earlier writes (a pure "I am done with your buffer" signal)
 __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t mbar_cluster_addr) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(mbar_cluster_addr) : "memory");
+}
+
+// Partial sum of squares of one fp16 row for lane j of an 8-lane group: 16-byte chunks j, j + 8, ... in order, the 8 halves
+// of a chunk in order; the caller adds the 8 partials with shuffles xor 1, 2, 4.  ONE definition so every kernel that derives
+// an RMSNorm factor from the fp16 copy of the residual stream produces the same bits.
+__device__ __forceinline__ float tc_row_sumsq_f16(const __half* row, int dim, int j) {
+  float acc = 0.f;
+  const uint4* p = reinterpret_cast<const uint4*>(row);
+  const int chunks = dim >> 3;
+#pragma unroll 4
+  for (int c = j; c < chunks; c += 8) {
+    const uint4 u = p[c];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      acc = fmaf(f.x, f.x, acc);
+      acc = fmaf(f.y, f.y, acc);
+    }
+  }
+  return acc;
+}
+__device__ __forceinline__ float tc_group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
 }
 
 }  // namespace tcptx
