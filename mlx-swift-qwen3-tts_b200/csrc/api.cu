@@ -1,6 +1,7 @@
 // extern "C" entry points of libqwen3tts_b200.so (declared in include/qwen3tts_b200.h).
 #include <algorithm>
 #include <deque>
+#include <chrono>
 #include <map>
 
 #include "codec.h"
@@ -221,6 +222,9 @@ struct DecodeJob {
 };
 
 void ensure_pinned(q3tts_handle* h, size_t pcm_floats, size_t code_ints) {
+  // grow in coarse steps (cudaMallocHost / cudaFree of tens of MB stall the call that first needs them)
+  pcm_floats = (pcm_floats + (size_t(1) << 20) - 1) >> 20 << 20;
+  code_ints = (code_ints + 8191) / 8192 * 8192;
   if (pcm_floats > h->h_pcm_floats) {
     if (h->h_pcm) cudaFreeHost(h->h_pcm);
     h->h_pcm = nullptr;
@@ -265,10 +269,14 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
     for (size_t p0 = 0; p0 < idx.size(); p0 += per_pass) {
       const int nb = (int)std::min<size_t>(per_pass, idx.size() - p0);
       const size_t code_ints = (size_t)nb * T * 16, pcm_floats = (size_t)nb * T * up;
-      ensure_pinned(h, pcm_floats, code_ints);
+      const auto h0 = std::chrono::steady_clock::now();
+      // sized once for a full pass (pass_frames x 1920 floats = 18 MB pinned at the default 2400 frames): growing on demand put a
+      // cudaMallocHost / cudaFree pair (27-800 ms measured) into whichever call first saw a slightly larger window batch
+      ensure_pinned(h, std::max(pcm_floats, (size_t)c.pass_frames() * up), std::max(code_ints, (size_t)c.pass_frames() * 16));
       for (int b = 0; b < nb; ++b) memcpy(h->h_codes + (size_t)b * T * 16, jobs[idx[p0 + b]].frames, (size_t)T * 64);
       int32_t* d_codes = h->d_codes;
       float* d_pcm = h->d_pcm;
+      const auto h1 = std::chrono::steady_clock::now();
       Q3_CUDA(cudaMemcpyAsync(d_codes, h->h_codes, code_ints * 4, cudaMemcpyHostToDevice, h->stream));
       h->timing.h2d_bytes += (int64_t)code_ints * 4;
       Q3_CUDA(cudaEventRecord(e0, h->stream));
@@ -276,11 +284,18 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
       Q3_CUDA(cudaEventRecord(e1, h->stream));
       Q3_CUDA(cudaMemcpyAsync(h->h_pcm, d_pcm, pcm_floats * 4, cudaMemcpyDeviceToHost, h->stream));
       h->timing.d2h_bytes += (int64_t)pcm_floats * 4;
+      const auto h2 = std::chrono::steady_clock::now();
       Q3_CUDA(cudaStreamSynchronize(h->stream));
+      const auto h3 = std::chrono::steady_clock::now();
       float ms = 0.f;
       cudaEventElapsedTime(&ms, e0, e1);
       h->timing.decode_ms += ms;
       h->timing.codec_flops += (int64_t)nb * T * c.flops_per_frame();
+      if (getenv("Q3TTS_HOST_TRACE")) {
+        auto wms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[q3tts host]   codec pass nb=%d T=%d: %.2f ms on the device; host: buffers %.2f, submit %.2f, wait %.2f ms\n", nb, T, ms,
+                wms(h0, h1), wms(h1, h2), wms(h2, h3));
+      }
       for (int b = 0; b < nb; ++b) {
         DecodeJob& j = jobs[idx[p0 + b]];
         const int64_t total = (int64_t)T * up;
@@ -395,6 +410,7 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
       // speech_tokenizer/{config...} + model.safetensors (Qwen3TTSPipeline.swift:191-208)
       // one pass holds up to codec_max_frames frames (batch x window); the workspace itself is allocated on first use
       h->codec.reset(new CodecDecoder(dir + "/speech_tokenizer", h->stream, &h->counter, h->opt.codec_max_frames));
+      h->codec->set_use_graph(h->opt.use_cuda_graph != 0);
     }
     Q3_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -735,9 +751,12 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
     Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
     CallTimer tm(h);
+    static const bool host_trace = getenv("Q3TTS_HOST_TRACE") != nullptr;  // wall-clock phases of this call on stderr
+    const auto w0 = std::chrono::steady_clock::now();
     std::vector<std::vector<int32_t>> raw;
     std::vector<int> n_raw;
     run_batch(h, reqs, n, raw, n_raw);
+    const auto w1 = std::chrono::steady_clock::now();
     std::vector<std::vector<int32_t>> valid(n);
     std::vector<DecodeJob> jobs;
     std::vector<int64_t> totals(n, 0);
@@ -750,12 +769,19 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
       totals[i] = plan_decode(mode, valid[i].data(), nv, pcm_out[i], capacity_samples, h->codec->total_upsample(), jobs);
       h->timing.h2d_bytes += (int64_t)reqs[i].n_text_ids * 4;
     }
+    const auto w2 = std::chrono::steady_clock::now();
     run_decode_jobs(h, jobs);
+    const auto w3 = std::chrono::steady_clock::now();
     for (int i = 0; i < n; ++i) {
       clean_samples(pcm_out[i], totals[i]);
       samples_out[i] = totals[i];
     }
     tm.finish();
+    if (host_trace) {
+      auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+      fprintf(stderr, "[q3tts host] generate_pcm_batch n=%d: talker loop %.1f ms (device %.1f), plan %.1f ms, decode jobs %.1f ms (device %.1f)\n", n,
+              ms(w0, w1), h->timing.talker_ms, ms(w1, w2), ms(w2, w3), h->timing.decode_ms);
+    }
   });
 }
 

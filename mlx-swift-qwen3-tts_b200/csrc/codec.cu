@@ -355,7 +355,14 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     if (e[0] == '1') use_tc_ = false;  // A/B switch: run the fp32 SIMT pipeline
 }
 
+void CodecDecoder::drop_graphs() {
+  for (auto& g : graphs_)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  graphs_.clear();
+}
+
 CodecDecoder::~CodecDecoder() {
+  drop_graphs();
   for (float*& p : ws_)
     if (p) { cudaFree(p); p = nullptr; }
   for (__half*& p : hs_)
@@ -364,6 +371,9 @@ CodecDecoder::~CodecDecoder() {
 
 void CodecDecoder::ensure_workspace(int frames) {
   if (frames <= ws_frames_) return;
+  // Regrowing frees and reallocates GBs behind a stream synchronize (measured: a 64 x 26-frame window after 63 x 26-frame ones
+  // cost 390 ms): grow in steps of 512 frames so that batches of nearly equal size share one allocation.
+  frames = std::min(std::max(pass_frames_, frames), (frames + 511) / 512 * 512);
   const CodecConfig& c = cfg_;
   // widest per-frame activation over all stages, in floats
   int64_t per = std::max<int64_t>({(int64_t)c.codebook_dim, (int64_t)c.latent_dim,
@@ -374,6 +384,8 @@ void CodecDecoder::ensure_workspace(int frames) {
   per = std::max(per, rate * c.decoder_dim);
   for (auto& b : blocks_) { per = std::max(per, rate * b.cin); rate *= b.rate; per = std::max(per, rate * b.cout); }
   Q3_CUDA(cudaStreamSynchronize(stream_));
+  drop_graphs();  // they hold the old workspace pointers
+  seen_.clear();
   for (float*& p : ws_)
     if (p) { cudaFree(p); p = nullptr; }
   for (__half*& p : hs_)
@@ -396,8 +408,46 @@ void CodecDecoder::rvq_embed(const int32_t* d_codes, int B, int T, float* d_firs
 }
 
 void CodecDecoder::decode_pass(const int32_t* d_codes, int B, int T, float* d_pcm) {
-  if (use_tc_) decode_pass_tc(d_codes, B, T, d_pcm);
-  else decode_pass_simt(d_codes, B, T, d_pcm);
+  // Opt-in (Q3TTS_CODEC_GRAPH=1): measured on B200, capture + instantiate of the ~110-node pass costs 100-500 ms, and the windows of
+  // a continuous batch rarely repeat their exact (B, T) (one utterance stopping early changes both), so replay seldom pays it back.
+  static const bool env_graph = [] { const char* e = getenv("Q3TTS_CODEC_GRAPH"); return e && atoi(e) != 0; }();
+  auto eager = [&] {
+    if (use_tc_) decode_pass_tc(d_codes, B, T, d_pcm);
+    else decode_pass_simt(d_codes, B, T, d_pcm);
+  };
+  if (!use_graph_ || !env_graph || B * T <= 0) return eager();
+  // ~110 launches (two host-encoded tensor maps each) per pass: replayed as one graph the pass does not depend on the host
+  // keeping up -- measured 47 ms -> 94-135 ms for the same pass whenever the submitting thread was stalled.
+  Q3_CHECK(B * T <= pass_frames_, Q3TTS_ERR_CAPACITY, "codec pass of %d frames exceeds pass capacity %d", B * T, pass_frames_);
+  ensure_workspace(B * T);  // may drop every cached graph; never runs inside a capture
+  const PassKey key{B, T, d_codes, d_pcm};
+  auto it = graphs_.find(key);
+  if (it == graphs_.end()) {
+    // capture + instantiate costs 100-400 ms: only shapes that keep coming back (steady serving windows) are worth it;
+    // one-off shapes (an utterance that stopped early changes the batch of a window) stay eager
+    if (++seen_[key] < 3) return eager();
+    if (graphs_.size() >= 64) drop_graphs();
+    PassGraph pg;
+    cudaGraph_t graph = nullptr;
+    const bool was = counter_ ? counter_->capturing : false;
+    if (counter_) { counter_->capturing = true; counter_->captured = 0; }
+    Q3_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      eager();
+    } catch (...) {
+      cudaStreamEndCapture(stream_, &graph);
+      if (graph) cudaGraphDestroy(graph);
+      if (counter_) counter_->capturing = was;
+      throw;
+    }
+    Q3_CUDA(cudaStreamEndCapture(stream_, &graph));
+    if (counter_) { pg.launches = counter_->captured; counter_->capturing = was; }
+    Q3_CUDA(cudaGraphInstantiate(&pg.exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = graphs_.emplace(key, pg).first;
+  }
+  Q3_CUDA(cudaGraphLaunch(it->second.exec, stream_));
+  if (counter_) counter_->n += it->second.launches;
 }
 
 // tcgen05 pipeline: every dense contraction is one launch of the implicit-GEMM kernel with its elementwise neighbours fused

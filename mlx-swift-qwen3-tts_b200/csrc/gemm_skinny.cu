@@ -324,7 +324,7 @@ struct SkPlan {
 };
 
 SkPlan plan(const TcGemm& g) {
-  static const int max_split = std::max(1, std::min(8, env_int("Q3TTS_SK_MAX_SPLIT", 8)));
+  static const int max_split = std::max(1, std::min(16, env_int("Q3TTS_SK_MAX_SPLIT", 8)));  // > 8: non-portable cluster size (B200 allows 16)
   // up to ~1.3 waves: 48 weight tiles (gate|up) take 4 K slices = 192 CTAs of 4 k-blocks (two co-resident per SM on 44 SMs)
   // rather than 96 CTAs of 8 k-blocks; measured 13.5 -> ~9 us per launch at 64 rows
   static const int cta_target = env_int("Q3TTS_SK_CTAS", 200);
@@ -372,6 +372,8 @@ void init_tc_skinny() {
   tc_resolve_encode();
   for (SkKernel k : {pick_kernel(0, 1), pick_kernel(TC_ACT_GELU, 0), pick_kernel(TC_ACT_SILU, 0), pick_kernel(0, 0)})
     Q3_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  for (SkKernel k : {pick_kernel(0, 1), pick_kernel(TC_ACT_GELU, 0), pick_kernel(TC_ACT_SILU, 0), pick_kernel(0, 0)})
+    Q3_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
 }
 
 unsigned long long* g_sk_trace = nullptr;  // set by tc_skinny_trace around its launches

@@ -854,12 +854,23 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
     if (count) { launches += 1; bytes_per_iter += (int64_t)head.weight_bytes(); }
   };
   pass(true);  // warm-up (and the per-iteration accounting)
+  // One pass as a CUDA graph, replayed `iters` times: the same submission path as the frame step (stream launches would add a
+  // host-side tensor-map encode + launch per kernel and measure the CPU instead of the kernels).
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  Q3_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+  pass(false);
+  Q3_CUDA(cudaStreamEndCapture(stream_, &graph));
+  Q3_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  Q3_CUDA(cudaGraphLaunch(exec, stream_));
   Q3_CUDA(cudaEventRecord(ev_a_, stream_));
-  for (int i = 0; i < iters; ++i) pass(false);
+  for (int i = 0; i < iters; ++i) Q3_CUDA(cudaGraphLaunch(exec, stream_));
   Q3_CUDA(cudaEventRecord(ev_b_, stream_));
   Q3_CUDA(cudaStreamSynchronize(stream_));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, ev_a_, ev_b_);
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
   launches *= iters;
   return ms;
 }
