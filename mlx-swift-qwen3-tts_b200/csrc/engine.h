@@ -79,7 +79,8 @@ class TalkerEngine {
   void build_tc_weights();
   void build_mega_plan();
   TcLinear make_tc(const Linear& L, bool interleave_halves, const float* fold = nullptr);
-  bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }
+  bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }            // prefill / prompt assembly
+  bool use_tc_step(int m) const { return w_.has_tc && m >= tc_min_rows_step_; }  // decode steps
   // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
   void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu, bool row_count_invariant = false);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
@@ -93,7 +94,11 @@ class TalkerEngine {
   int weight_dtype_ = Q3TTS_BF16, eff_bits_ = 0, eff_group_ = 64;
 
   int max_rows_ = 0, max_tp_rows_ = 0, set_words_ = 0;
-  int tc_min_rows_ = 16;  // rows from which linears run on tensor cores (env Q3TTS_TC_MIN_ROWS; 0 disables)
+  // rows from which linears run on tensor cores (env Q3TTS_TC_MIN_ROWS sets both; 0 disables).  Decode steps switch at 3
+  // utterances: measured per frame-step (0.6B 4-bit) 6.5 / 10.3 / 17.2 ms at 3 / 8 / 12 rows on the SIMT path against a flat
+  // 3.45-3.5 ms on the split-K cluster GEMM; 1-2 utterances stay on the persistent frame kernel (2.2 ms).
+  int tc_min_rows_ = 16, tc_min_rows_step_ = 3;
+  bool step_tc_ = false;  // set by issue_frame for the launches of the current frame step
   float* d_rs_ = nullptr;                     // [max_rows] RMSNorm row factors for the 128-row-tile kernel (prefill)
   static constexpr float kX16Div = 16.0f;     // the fp16 copy of the residual stream is x / 16 (range headroom; exact power of two)
   void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;

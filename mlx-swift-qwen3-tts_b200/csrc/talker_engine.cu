@@ -73,7 +73,7 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   d_ids_ = arena_.alloc_n<int>(max_tp_rows_);
   d_desc_ = arena_.alloc_n<int>((size_t)3 * max_rows_);
   // tensor-core copies: built when the handle can see >= tc_min_rows_ rows at once (batched decode, or any prefill)
-  if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) tc_min_rows_ = atoi(e);
+  if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) tc_min_rows_ = tc_min_rows_step_ = atoi(e);
   if (tc_min_rows_ > 0) {
     init_tc_gemm();
     build_tc_weights();
@@ -422,7 +422,7 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
                                  size_t layer_stride, int capacity, bool one_row_per_slot, bool decode_step) {
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
-  if (use_tc(m) && !S.tc.empty()) {
+  if ((decode_step ? step_tc_ : use_tc(m)) && !S.tc.empty()) {
     // tcgen05 path (rows >= tc_min_rows_): fp16 operands, fp32 accumulate, fp32 residual stream.  RMSNorm is folded around the
     // contractions: its WEIGHT lives in the fp16 copies of qkv / gate|up (make_tc), its per-row factor is applied to the
     // accumulator, and the activation operand is d_h16_ = fp16(x / 16) of the un-normalised stream.
@@ -682,6 +682,7 @@ void TalkerEngine::release(int slot) {
 // One 12.5 Hz frame for slots [0, n_slots): the loop body of Model/Qwen3Talker.swift:464-562 with every decision on device.
 void TalkerEngine::issue_frame(int n_slots) {
   const LaunchCtx c = ctx();
+  step_tc_ = use_tc_step(n_slots);  // one decision per frame step (by utterances, not by the rows of each launch)
   const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size, V = cfg_.vocab_size, Vc = cfg_.cp.vocab_size;
   const int B = opt_.max_batch, F = opt_.max_frames;
   SamplerParams p{};
@@ -695,7 +696,7 @@ void TalkerEngine::issue_frame(int n_slots) {
     const int m = g == 0 ? 2 * n_slots : n_slots;
     float* x = d_cpin_;
     if (w_.has_mtp) {  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
-      if (use_tc(m)) {
+      if (step_tc_) {
         launch_f32_to_f16(c, d_cpin_, (size_t)m * H, (__half*)d_h16_);
         linear_tc(w_.small_to_mtp_tc, d_h16_, m, d_cpx_, Hcp, nullptr, 0, nullptr, TC_ACT_NONE, 0);
       } else {
@@ -706,14 +707,14 @@ void TalkerEngine::issue_frame(int n_slots) {
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
                   d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
-    if (use_tc(n_slots) && g != 0 && n_slots <= 128 && tc_skinny_enabled()) {
+    if (step_tc_ && g != 0 && n_slots <= 128 && tc_skinny_enabled()) {
       // the last layer's down GEMM left fp16(x / 16) in d_h16_: lm_head (final norm folded in) takes it as is
       TcGemm hg;
       hg.a = (const __half*)d_h16_; hg.w = (const __half*)w_.lm_head_tc[g].w; hg.Bt = 1; hg.T = n_slots; hg.cin = Hcp; hg.N = Vc;
       hg.bias = w_.lm_head_tc[g].bias; hg.out32 = d_cplogits_; hg.ld32 = Vc;
       hg.rms_in = 1; hg.rms_eps = w_.cp.eps; hg.in_scale = 1.0f / kX16Div;
       launch_tc_gemm(c, hg);
-    } else if (use_tc(n_slots)) {
+    } else if (step_tc_) {
       launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, nullptr, w_.cp.eps, (__half*)d_h16_, Hcp);
       linear_tc(w_.lm_head_tc[g], d_h16_, n_slots, d_cplogits_, Vc, nullptr, 0, nullptr, TC_ACT_NONE, 0);
     } else if (g == 0) {
@@ -731,7 +732,7 @@ void TalkerEngine::issue_frame(int n_slots) {
   forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
                 kv_layer_stride_, opt_.kv_capacity, true, true);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
-  if (use_tc(n_slots)) {
+  if (step_tc_) {
     launch_f32_to_f16(c, d_hlast_, (size_t)n_slots * H, (__half*)d_h16_);
     linear_tc(w_.codec_head_tc, d_h16_, n_slots, d_logits0_, V, nullptr, 0, nullptr, TC_ACT_NONE, 0);
   } else {
@@ -746,7 +747,7 @@ void TalkerEngine::run_frames(int n_slots, int n) {
     for (int i = 0; i < n; ++i) issue_frame(n_slots);
     return;
   }
-  if (mega_.ok && n_slots <= mega_.max_slots && !use_tc(n_slots)) {  // small batches: one persistent cooperative launch for all n frames
+  if (mega_.ok && n_slots <= mega_.max_slots && !use_tc_step(n_slots)) {  // small batches: one persistent cooperative launch for all n frames
     if (mega_.p.trace) Q3_CUDA(cudaMemsetAsync(mega_.p.trace, 0, sizeof(long long) * 2 * mega_.p.trace_stride, stream_));
     launch_frame_megakernel(ctx(), mega_, n_slots, n, dump_enabled_ ? d_dump0_ : nullptr, dump_enabled_ ? d_dumpcp_ : nullptr);
     ++mega_launches;

@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 // warp, shared memory across the 4 warps).  The previous version (thread-per-key score loop with 8 loads in flight, three
 // block barriers, 4 V loads in flight) spent ~11 us per launch on dependent round trips even for 2-17 keys.
 template <int G, typename OutT>
-__global__ void __launch_bounds__(128) rope_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
+__global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                              const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
                                                              const float* __restrict__ inv_freq, const int* __restrict__ row_slot,
                                                              const int* __restrict__ row_pos, const int* __restrict__ win_start, KVLayout kv,

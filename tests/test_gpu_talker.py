@@ -181,17 +181,54 @@ def test_teacher_forced_logits(ck, request, engines, oracles):
 
 
 # ------------------------------------------------------------------------------------------------ batching == singles
-def test_batch_equals_single(tiny8, engines):
+def _mixed_requests():
     import qwen3tts_b200 as q
 
-    eng1 = engines(tiny8)
-    engB = engines(tiny8, max_batch=4)
     reqs = [q.GenRequest(text_ids=[11, 21, 22] + list(range(60 + i, 60 + i + 8 + 3 * i)), speaker_id=[2861, 3066, -1, 2873, 3010, 2864, 2875][i],
                          temperature=0.0, max_tokens=10 + 3 * i, keep_invalid_frames=True) for i in range(7)]
     reqs.insert(3, q.GenRequest(text_ids=[1, 2, 3], temperature=0.0, max_tokens=5))  # too short -> 0 frames, batch goes on
+    return reqs
+
+
+def test_batch_equals_single(tiny8, engines, monkeypatch):
+    """fp32-activation (SIMT) batch steps reproduce the single-utterance path bit for bit (tensor cores switched off: from 3
+    utterances on, decode steps otherwise run the fp16-operand tcgen05 path, covered by the two tests below)."""
+    import qwen3tts_b200 as q
+
+    monkeypatch.setenv("Q3TTS_TC_MIN_ROWS", "0")
+    eng1 = engines(tiny8)  # one slot: never on tensor cores in decode, whatever the switch says
+    engB = q.Engine(tiny8, max_batch=4, max_frames=256)  # not from the cache: built under the switch
+    reqs = _mixed_requests()
     singles = [eng1.generate_codes(r).tolist() for r in reqs]
     batch = [b.tolist() for b in engB.generate_codes_batch(reqs)]
+    engB.close()
     assert batch == singles
+
+
+def test_small_batch_takes_tensor_cores_and_stays_in_tolerance(tiny8, engines, oracles):
+    """Default engine, 4 slots: decode steps of >= 3 utterances run the split-K cluster GEMM; ids agree with the oracle wherever
+    its top-2 margin allows, and continuous batching (7 requests over 4 slots, one too short) delivers every utterance."""
+    from oracle import talker as otalker
+
+    eng = engines(tiny8, max_batch=4)
+    reqs = _mixed_requests()
+    outs = eng.generate_codes_batch(reqs)
+    assert len(outs[3]) == 0
+    for i, (r, o) in enumerate(zip(reqs, outs)):
+        if i == 3:
+            continue
+        rec = {}
+        want = oracles(tiny8).generate_codes(_oreq(otalker, text_ids=r.text_ids, speaker_id=r.speaker_id, temperature=0.0, max_tokens=r.max_tokens),
+                                             record=rec, filter_invalid=False)
+        got = o.tolist()
+        n = min(len(got), len(want))
+        for f in range(n):
+            if got[f] != want[f]:
+                g = next(k for k in range(16) if got[f][k] != want[f][k])
+                assert rec["margins"][f][g] < MARGIN_TOL, f"utterance {i} frame {f} group {g}: divergence at margin {rec['margins'][f][g]:.4f}"
+                break
+        else:
+            assert len(got) == len(want)
 
 
 def test_cuda_graph_equals_eager(tiny8, engines):
