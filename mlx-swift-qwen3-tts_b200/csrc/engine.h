@@ -74,7 +74,7 @@ class TalkerEngine {
   // decode_step: rows <= 128 may take the split-K cluster GEMM (prefill stays on the 128-row-tile kernel: batch invariance)
   void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
                      const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity,
-                     bool one_row_per_slot, bool decode_step);
+                     bool one_row_per_slot, bool decode_step, bool x16_ready);
   void issue_frame(int n_slots);
   void build_tc_weights();
   void build_mega_plan();

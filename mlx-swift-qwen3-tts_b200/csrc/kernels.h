@@ -98,11 +98,23 @@ struct SamplerParams {
   int set_words;         // uint32 words per token-set bitmap
 };
 // One block per slot: Qwen3Talker.sampleToken (:274-322) + the loop's EOS/pad logic for group 0 (:470-494).
+// What the sampler CTA of a slot writes once the group's token is known: the code predictor's next input rows
+// (Model/Qwen3Talker.swift:503-510).  mode 0: nothing; 1 (after group 0): rows (2s, 2s+1) = [h_last[s], codec_embedding[code0]];
+// 2 (after group g in 1..14): row s = cp_codec_embedding[g-1][code_g].  y16 (optional) = fp16(row * y16_scale).
+struct NextInput {
+  int mode = 0, H = 0;
+  const float* h_last = nullptr;
+  Embedding codec;
+  const Embedding* cp_emb = nullptr;  // device array of the 15 code-predictor tables
+  float* y32 = nullptr;
+  __half* y16 = nullptr;
+  float y16_scale = 1.0f;
+};
 void launch_sample(const LaunchCtx& c, const float* logits, int ld, int n_slots, SlotState* st, const SamplerParams& p,
                    unsigned* token_sets /*[slot][16][set_words]*/, int* cur_codes /*[slot][16]*/,
                    const int* forced /*[slot][max_frames][16] or null*/, int max_frames,
                    float* logits_dump /*[cap][...] of slot `dump_slot`, or null*/, int dump_stride_frame, int dump_offset,
-                   int dump_slot);
+                   int dump_slot, const NextInput& next = NextInput());
 
 // standalone sampler probe (q3tts_sample_token)
 void launch_sample_probe(const LaunchCtx& c, const float* logits, int vocab, int codec_vocab, float temperature, int top_k,
@@ -119,7 +131,7 @@ void launch_cp_input(const LaunchCtx& c, int pass, int n_slots, const float* h_l
 void launch_frame_finalize(const LaunchCtx& c, int n_slots, SlotState* st, const int* cur_codes, int* frames_out,
                            int max_frames, unsigned* token_sets, int set_words, const float* trailing /*[slot][max_trailing][H]*/,
                            int max_trailing, const float* tts_pad /*[H]*/, const Embedding& codec,
-                           const Embedding* cp_emb_dev, int H, float* x_next);
+                           const Embedding* cp_emb_dev, int H, float* x_next, __half* x16_next = nullptr, float x16_scale = 1.0f);
 // after the talker step: pos++, step++, window trim every 15th step, max_tokens stop
 void launch_step_advance(const LaunchCtx& c, int n_slots, SlotState* st, int window);
 // row metadata for the talker step: row s -> (slot s, pos[s])

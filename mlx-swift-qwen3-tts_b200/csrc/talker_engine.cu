@@ -419,7 +419,7 @@ void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* o
 // Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
 void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
                                  const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
-                                 size_t layer_stride, int capacity, bool one_row_per_slot, bool decode_step) {
+                                 size_t layer_stride, int capacity, bool one_row_per_slot, bool decode_step, bool x16_ready) {
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
   if ((decode_step ? step_tc_ : use_tc(m)) && !S.tc.empty()) {
@@ -458,7 +458,7 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
         launch_scale_to_f16(c, x, (size_t)m * S.hidden, inv16, (__half*)d_h16_);
       }
     };
-    launch_scale_to_f16(c, x, (size_t)m * S.hidden, inv16, (__half*)d_h16_);
+    if (!x16_ready) launch_scale_to_f16(c, x, (size_t)m * S.hidden, inv16, (__half*)d_h16_);  // else the producer of x wrote it
     for (int l = 0; l < S.layers; ++l) {
       const LayerWeights& L = S.layer[l];
       const LayerTc& Tc = S.tc[l];
@@ -618,7 +618,7 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
     Q3_CUDA(cudaMemcpyAsync(tr + (size_t)p.n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
   }
   // prefill: every row at its own (slot, position) (Model/Qwen3Talker.swift:437)
-  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false, false);
+  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false, false, false);
   // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
   for (const Plan& p : plans) {
     launch_rmsnorm(c, d_x_ + (size_t)(p.row0 + p.P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)p.slot * H, H);
@@ -690,14 +690,21 @@ void TalkerEngine::issue_frame(int n_slots) {
   p.groups = 16; p.set_words = set_words_;
   float* dump0 = dump_enabled_ ? d_dump0_ : nullptr;
   float* dumpcp = dump_enabled_ ? d_dumpcp_ : nullptr;
-  launch_sample(c, d_logits0_, V, n_slots, d_state_, p, d_sets_, d_cur_codes_, d_forced_, F, dump0, V, 0, 0);
+  // The sampler of group g also writes the code predictor's input rows of pass g (and, on the tensor-core path, their fp16
+  // operand copy: fp16(x) for the small_to_mtp GEMM, fp16(x / 16) when the rows enter the stack directly).
+  const bool x16_direct = step_tc_ && !w_.has_mtp;
+  auto next_input = [&](int mode) {
+    NextInput ni;
+    ni.mode = mode; ni.H = H; ni.h_last = d_hlast_; ni.codec = w_.codec_embedding; ni.cp_emb = d_cp_emb_; ni.y32 = d_cpin_;
+    if (step_tc_) { ni.y16 = (__half*)d_h16_; ni.y16_scale = w_.has_mtp ? 1.0f : 1.0f / kX16Div; }
+    return ni;
+  };
+  launch_sample(c, d_logits0_, V, n_slots, d_state_, p, d_sets_, d_cur_codes_, d_forced_, F, dump0, V, 0, 0, next_input(1));
   for (int g = 0; g < 15; ++g) {  // code predictor, strictly sequential (:501-523)
-    launch_cp_input(c, g, n_slots, d_hlast_, H, w_.codec_embedding, d_cp_emb_, d_cur_codes_, d_cpin_);
     const int m = g == 0 ? 2 * n_slots : n_slots;
     float* x = d_cpin_;
     if (w_.has_mtp) {  // small_to_mtp_projection (Qwen3CodePredictor.swift:183-185)
       if (step_tc_) {
-        launch_f32_to_f16(c, d_cpin_, (size_t)m * H, (__half*)d_h16_);
         linear_tc(w_.small_to_mtp_tc, d_h16_, m, d_cpx_, Hcp, nullptr, 0, nullptr, TC_ACT_NONE, 0);
       } else {
         launch_linear(c, w_.small_to_mtp, d_cpin_, H, m, d_cpx_, Hcp, nullptr, 0.f, EPI_STORE);
@@ -705,7 +712,7 @@ void TalkerEngine::issue_frame(int n_slots) {
       x = d_cpx_;
     }
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
-                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true);
+                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true, x16_direct);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
     if (step_tc_ && g != 0 && n_slots <= 128 && tc_skinny_enabled()) {
       // the last layer's down GEMM left fp16(x / 16) in d_h16_: lm_head (final norm folded in) takes it as is
@@ -724,13 +731,14 @@ void TalkerEngine::issue_frame(int n_slots) {
     }
     SamplerParams pg = p;
     pg.vocab = Vc; pg.group = g + 1;
-    launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, 0);
+    launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, 0,
+                  g < 14 ? next_input(2) : NextInput());
   }
   launch_frame_finalize(c, n_slots, d_state_, d_cur_codes_, d_frames_, F, d_sets_, set_words_, d_trailing_, opt_.max_trailing,
-                        d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_);
+                        d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_, step_tc_ ? (__half*)d_h16_ : nullptr, 1.0f / kX16Div);
   launch_step_rows(c, n_slots, d_state_, d_step_slot_, d_step_pos_, d_win_);
   forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
-                kv_layer_stride_, opt_.kv_capacity, true, true);
+                kv_layer_stride_, opt_.kv_capacity, true, true, step_tc_);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
   if (step_tc_) {
     launch_f32_to_f16(c, d_hlast_, (size_t)n_slots * H, (__half*)d_h16_);

@@ -681,21 +681,49 @@ void launch_assemble_rows(const LaunchCtx& c, const float* tp_rows, int H, const
 
 // ------------------------------------------------------------------------------------------------ sampler
 // (device code in sampler.cuh, shared with the frame megakernel)
+// After the group's token is known the same CTA writes the code predictor's NEXT input rows (Qwen3Talker.swift:501-523:
+// pass 0 = [last hidden, codec_embedding(code0)], pass g = cp.codec_embedding[g-1](code_g)) -- fp32, and optionally the fp16
+// operand copy the tensor-core stack reads -- so a frame has no separate input-row or conversion launches.
 __global__ void __launch_bounds__(kSampleThreads) sample_kernel(const float* __restrict__ logits, int ld, SlotState* __restrict__ st,
                                                                SamplerParams p, unsigned* __restrict__ token_sets,
                                                                int* __restrict__ cur_codes, const int* __restrict__ forced,
                                                                int max_frames, float* __restrict__ dump, int dump_stride_frame,
-                                                               int dump_offset, int dump_slot) {
+                                                               int dump_offset, int dump_slot, NextInput ni) {
   __shared__ float sl[kMaxVocab];
   __shared__ BlockRed br;
   sample_slot<0, kSampleThreads>(blockIdx.x, logits, ld, st, p, token_sets, cur_codes, forced, max_frames, dump, dump_stride_frame, dump_offset, dump_slot, sl, br);
+  if (ni.mode == 0) return;
+  __syncthreads();  // cur_codes[slot][group] written by thread 0 of this CTA
+  const int slot = blockIdx.x, H = ni.H;
+  const int code = cur_codes[slot * p.groups + p.group];
+  if (ni.mode == 1) {  // -> pass 0
+    const bool ok = code >= 0 && code < ni.codec.rows;
+    for (int d = threadIdx.x; d < H; d += kSampleThreads) {
+      const float a = ni.h_last[(size_t)slot * H + d];
+      const float b = ok ? load_as_f32(ni.codec.w, (size_t)code * H + d, ni.codec.dt) : 0.f;
+      ni.y32[(size_t)(2 * slot) * H + d] = a;
+      ni.y32[(size_t)(2 * slot + 1) * H + d] = b;
+      if (ni.y16) {
+        ni.y16[(size_t)(2 * slot) * H + d] = __float2half_rn(a * ni.y16_scale);
+        ni.y16[(size_t)(2 * slot + 1) * H + d] = __float2half_rn(b * ni.y16_scale);
+      }
+    }
+  } else {             // -> pass p.group (>= 1)
+    const Embedding e = ni.cp_emb[p.group - 1];
+    const bool ok = code >= 0 && code < e.rows;
+    for (int d = threadIdx.x; d < H; d += kSampleThreads) {
+      const float v = ok ? load_as_f32(e.w, (size_t)code * H + d, e.dt) : 0.f;
+      ni.y32[(size_t)slot * H + d] = v;
+      if (ni.y16) ni.y16[(size_t)slot * H + d] = __float2half_rn(v * ni.y16_scale);
+    }
+  }
 }
 void launch_sample(const LaunchCtx& c, const float* logits, int ld, int n_slots, SlotState* st, const SamplerParams& p,
                    unsigned* token_sets, int* cur_codes, const int* forced, int max_frames, float* logits_dump,
-                   int dump_stride_frame, int dump_offset, int dump_slot) {
+                   int dump_stride_frame, int dump_offset, int dump_slot, const NextInput& ni) {
   Q3_CHECK(p.vocab <= kMaxVocab, Q3TTS_ERR_BAD_CONFIG, "sampler supports vocab <= %d (got %d)", kMaxVocab, p.vocab);
   sample_kernel<<<n_slots, kSampleThreads, 0, c.stream>>>(logits, ld, st, p, token_sets, cur_codes, forced, max_frames, logits_dump,
-                                                          dump_stride_frame, dump_offset, dump_slot);
+                                                          dump_stride_frame, dump_offset, dump_slot, ni);
   c.tick();
 }
 
@@ -747,25 +775,37 @@ void launch_cp_input(const LaunchCtx& c, int pass, int n_slots, const float* h_l
 __global__ void frame_finalize_kernel(SlotState* __restrict__ st, const int* __restrict__ cur_codes, int* __restrict__ frames_out,
                                       int max_frames, unsigned* __restrict__ token_sets, int set_words,
                                       const float* __restrict__ trailing, int max_trailing, const float* __restrict__ tts_pad,
-                                      Embedding codec, const Embedding* __restrict__ cp_emb, int H, float* __restrict__ x_next) {
+                                      Embedding codec, const Embedding* __restrict__ cp_emb, int H, float* __restrict__ x_next,
+                                      __half* __restrict__ x16_next, float x16_scale) {
   const int slot = blockIdx.x;
   SlotState& s = st[slot];
   if (!s.frame_alive) return;
   constexpr int G = 16;
   __shared__ int codes[G];
-  if (threadIdx.x < G) codes[threadIdx.x] = cur_codes[slot * G + threadIdx.x];
+  __shared__ const void* rowp[G];  // embedding row of each group's code (null: out of range), resolved once per CTA
+  __shared__ int rowdt[G];
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x, code = cur_codes[slot * G + g];
+    codes[g] = code;
+    const Embedding e = g == 0 ? codec : cp_emb[g - 1];
+    const bool ok = code >= 0 && code < e.rows;
+    rowp[g] = ok ? static_cast<const char*>(e.w) + (size_t)code * H * (e.dt == Q3TTS_F32 ? 4 : 2) : nullptr;
+    rowdt[g] = e.dt;
+  }
   __syncthreads();
   const int ti = s.trailing_idx;
   const float* text = (ti < s.total_text) ? trailing + ((size_t)slot * max_trailing + ti) * H : tts_pad;
   for (int d = threadIdx.x; d < H; d += blockDim.x) {
     // codecEmbedSum = codec_embedding(code0) + sum_i cp.codec_embedding[i](code_{i+1}); input = text + sum (:531-548)
-    float sum = (codes[0] >= 0 && codes[0] < codec.rows) ? load_as_f32(codec.w, (size_t)codes[0] * H + d, codec.dt) : 0.f;
+    float v[G];
 #pragma unroll
-    for (int g = 1; g < G; ++g) {
-      const Embedding e = cp_emb[g - 1];
-      if (codes[g] >= 0 && codes[g] < e.rows) sum += load_as_f32(e.w, (size_t)codes[g] * H + d, e.dt);
-    }
-    x_next[(size_t)slot * H + d] = text[d] + sum;
+    for (int g = 0; g < G; ++g) v[g] = rowp[g] ? load_as_f32(rowp[g], (size_t)d, rowdt[g]) : 0.f;  // 16 independent loads
+    float sum = v[0];
+#pragma unroll
+    for (int g = 1; g < G; ++g) sum += v[g];  // same order as before: code0, then groups 1..15
+    const float x = text[d] + sum;
+    x_next[(size_t)slot * H + d] = x;
+    if (x16_next) x16_next[(size_t)slot * H + d] = __float2half_rn(x * x16_scale);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -782,9 +822,10 @@ __global__ void frame_finalize_kernel(SlotState* __restrict__ st, const int* __r
 }
 void launch_frame_finalize(const LaunchCtx& c, int n_slots, SlotState* st, const int* cur_codes, int* frames_out,
                            int max_frames, unsigned* token_sets, int set_words, const float* trailing, int max_trailing,
-                           const float* tts_pad, const Embedding& codec, const Embedding* cp_emb_dev, int H, float* x_next) {
+                           const float* tts_pad, const Embedding& codec, const Embedding* cp_emb_dev, int H, float* x_next,
+                           __half* x16_next, float x16_scale) {
   frame_finalize_kernel<<<n_slots, 256, 0, c.stream>>>(st, cur_codes, frames_out, max_frames, token_sets, set_words, trailing,
-                                                       max_trailing, tts_pad, codec, cp_emb_dev, H, x_next);
+                                                       max_trailing, tts_pad, codec, cp_emb_dev, H, x_next, x16_next, x16_scale);
   c.tick();
 }
 
