@@ -335,6 +335,37 @@ def test_persistent_kernel_full_size_logits(engines, oracles):
     assert e0 <= LOGIT_TOL and ec <= LOGIT_TOL
 
 
+@pytest.mark.slow
+def test_tensor_core_step_full_size_logits(oracles, monkeypatch):
+    """0.6B dimensions, 4-bit g64: the decode-step path of >= 3 utterances (split-K cluster GEMM at K = 1024 / 2048 / 3072,
+    RMSNorm folded around the contractions, one-pass attention) forced onto a single utterance, teacher-forced logits vs the oracle."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    d = ckpt("0.6b", 4)
+    F = 3
+    forced = np.random.default_rng(4).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    rec = {}
+    ids = list(range(1000, 1016))
+    oracles(d).generate_codes(otalker.Request(text_ids=ids, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec, filter_invalid=False)
+    eng = _tc_engine(d, monkeypatch, load_codec=False, max_frames=64)
+    try:
+        frames, lg = eng.generate_codes(q.GenRequest(text_ids=ids, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced,
+                                                     keep_invalid_frames=True, want_logits=F))
+        assert eng.timing().persistent_launches == 0
+    finally:
+        eng.close()
+    e0 = np.abs(lg["code0_logits"] - rec["code0_logits"]).max()
+    ec = np.abs(lg["cp_logits"] - rec["cp_logits"]).max()
+    rms0, rmsc = float(rec["code0_logits"].std()), float(rec["cp_logits"].std())
+    print(f"[0.6b 4-bit] tensor-core step teacher-forced max-abs logit error: code0 {e0:.3e} (logit rms {rms0:.2f}), code predictor {ec:.3e} (rms {rmsc:.2f})")
+    # fp16 operands (weights AND activations rounded to 2^-11 relative) through 28 + 5 layers: the error scales with the
+    # logits.  The synthetic heads (N(0, 0.25^2) rows on a unit-RMS hidden state of width 1024) give logits of rms ~8, three to
+    # four times a trained model's, so the 1e-2 bar of the fp32-activation paths is stated here relative to that scale:
+    # max-abs <= 1e-2 at logit rms 2, i.e. 5e-3 x rms (measured: 3.2e-3 x rms for code0, 3.9e-3 x rms for the code predictor).
+    assert e0 <= max(LOGIT_TOL, 5e-3 * rms0) and ec <= max(LOGIT_TOL, 5e-3 * rmsc)
+
+
 # ------------------------------------------------------------------------------------------------ sampler probe
 @pytest.mark.parametrize("mode", ["greedy", "temp", "topk", "topp", "topk_topp"])
 @pytest.mark.parametrize("vocab", [3072, 2048])
