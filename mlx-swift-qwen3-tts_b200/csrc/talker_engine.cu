@@ -465,7 +465,9 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       KVLayout kv;
       kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
       consumer(Tc.qkv, d_qkv_, qkv_ld, nullptr, 0, 0);
-      if (one_row_per_slot) {
+      static const int dbg_skip = getenv("Q3TTS_DEBUG_SKIP") ? atoi(getenv("Q3TTS_DEBUG_SKIP")) : 0;  // timing attribution only
+      if (one_row_per_slot && (dbg_skip & 1)) {
+      } else if (one_row_per_slot) {
         launch_rope_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
                                   (__half*)d_attn16_, attn_ld);
       } else {
@@ -473,9 +475,9 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
                                    row_pos, kv);
         launch_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, row_slot, row_pos, win_start, kv, (__half*)d_attn16_, attn_ld);
       }
-      producer(Tc.o, d_attn16_);
-      consumer(Tc.gate_up_il, nullptr, 0, d_act16_, S.inter, 1);
-      producer(Tc.down, d_act16_);
+      if (!(dbg_skip & 2)) producer(Tc.o, d_attn16_);
+      if (!(dbg_skip & 4)) consumer(Tc.gate_up_il, nullptr, 0, d_act16_, S.inter, 1);
+      if (!(dbg_skip & 8)) producer(Tc.down, d_act16_);
     }
     return;
   }
