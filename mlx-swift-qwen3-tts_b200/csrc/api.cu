@@ -886,6 +886,9 @@ q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t
       Q3_CHECK(nx % 4 == 0 && nw % 4 == 0, Q3TTS_ERR_INVALID_ARG, "probe needs element counts divisible by 4");
       launch_f32_to_f16(c, dx, nx, dx16);
       launch_f32_to_f16(c, dw, nw, dw16);
+      // the GEMM kernels request WEIGHT tiles before their programmatic dependency resolves (weights are static in the engine):
+      // here the weights come from the launch just above, so it must have retired first
+      Q3_CUDA(cudaDeviceSynchronize());
       TcGemm g;
       g.a = dx16; g.w = dw16; g.Bt = B; g.T = T; g.cin = cin; g.N = N; g.ntap = ntap; g.dil = dil;
       g.bias = dbias; g.res = dres; g.ld_res = (int)n_out; g.scale = dscale; g.act = act; g.swiglu = swiglu;

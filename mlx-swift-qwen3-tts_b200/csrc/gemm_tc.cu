@@ -42,6 +42,10 @@ struct TcParams {
   float* pcm;
   const float* row_scale;
   int k_rotate;
+  // tile schedule: a CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the (tiles_m x tiles_n) grid, n fastest.  One tile
+  // per CTA (gridDim.x == tiles) is the classic launch; with fewer CTAs than tiles the kernel is PERSISTENT: the TMA ring runs on
+  // across tile boundaries and two TMEM accumulators (n_acc = 2) let the epilogue of tile i overlap the MMAs of tile i + 1.
+  int tiles_m, tiles_n, n_acc, acc_cols;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
@@ -56,23 +60,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sB = smem + (size_t)p.stages * kABytes;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)p.stages * b_bytes);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty + p.stages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bidx = blockIdx.x / p.tiles_per_batch;
-  const int t0 = (blockIdx.x - bidx * p.tiles_per_batch) * kTileM;
-  const int n0 = blockIdx.y * p.bn;
   const int num_kb = p.ntap * p.kb_per_tap;
+  const int total_tiles = p.tiles_m * p.tiles_n;
 
   pdl_launch_dependents();  // the next kernel of the stream may start its prologue / weight prefetch now
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  if (warp == 1) {  // one warp allocates TMEM columns for the fp32 accumulator tile and later frees them
+  if (warp == 1) {  // one warp allocates TMEM columns for the fp32 accumulator tile(s) and later frees them
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -87,58 +91,80 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // dependency is resolved, so the weight stream overlaps the predecessor's tail; activations (A) follow the wait.
       // Every CTA of a column of the grid reads the SAME activation tiles: walking K from a per-CTA offset keeps the CTAs
       // off each other's L2 lines (same-address storms serialise in one L2 slice and multiply the TMA latency).
-      const int rot = p.k_rotate ? (int)((blockIdx.y * 5u + blockIdx.x * 3u) % (unsigned)num_kb) : 0;
-      const int pre = num_kb < p.stages ? num_kb : p.stages;
-      for (int kb = 0; kb < pre; ++kb) {
-        mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
-        const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
-        const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
-        tma_load_2d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0);
-      }
-      pdl_wait();
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-        const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
-        const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
-        const int shift = (p.ntap - 1 - tap) * p.dil;
-        if (kb >= pre) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-          tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
+      int it = 0;  // k-blocks issued by this CTA so far (the ring does not care about tile boundaries)
+      for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
+        const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
+        const int rot = p.k_rotate ? (int)(((unsigned)n_tile * 5u + (unsigned)m_tile * 3u) % (unsigned)num_kb) : 0;
+        int pre = 0;
+        if (ti == 0) {
+          pre = num_kb < p.stages ? num_kb : p.stages;
+          for (int kb = 0; kb < pre; ++kb) {
+            mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
+            const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
+            const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
+            tma_load_2d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0);
+          }
+          pdl_wait();
         }
-        tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages, ph = (it / p.stages) & 1;
+          const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
+          const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
+          const int shift = (p.ntap - 1 - tap) * p.dil;
+          if (kb >= pre) {
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+            tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
+          }
+          tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {  // ---------------- MMA issuer
       // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (bit 4), a = b = F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % p.stages, ph = (kb / p.stages) & 1;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kABytes));
-        const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * b_bytes));
+      int it = 0;
+      for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
+        const int a = p.n_acc == 2 ? (ti & 1) : 0, use = p.n_acc == 2 ? (ti >> 1) : ti;
+        if (use > 0) {  // the epilogue must have drained this accumulator's previous tile
+          mbar_wait(&tmem_empty[a], (uint32_t)((use - 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t acc = tmem_base + (uint32_t)(a * p.acc_cols);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % p.stages, ph = (it / p.stages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kABytes));
+          const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * b_bytes));
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+          for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+            umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+        }
+        umma_commit(&tmem_full[a]);  // accumulator complete
       }
-      umma_commit(tmem_full);    // accumulator complete
     }
   } else {
     // ---------------- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    pdl_wait();  // residual / bias-free inputs of the epilogue were written by earlier kernels
+    for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
+    const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
+    const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
+    const int acc_i = p.n_acc == 2 ? (ti & 1) : 0, use = p.n_acc == 2 ? (ti >> 1) : ti;
+    const uint32_t acc = tmem_base + (uint32_t)(acc_i * p.acc_cols);
     const int t = t0 + row;
     const bool row_ok = t < p.T;
     const size_t m = (size_t)bidx * p.T + t;
-    pdl_wait();  // residual / bias-free inputs of the epilogue were written by earlier kernels
-    mbar_wait(tmem_full, 0);
+    mbar_wait(&tmem_full[acc_i], (uint32_t)(use & 1));
     tc_fence_after();
     for (int c = 0; c < p.bn; c += 32) {
       uint32_t raw[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       const int nb = n0 + c;
       if (!row_ok || nb >= p.N) continue;
       float v[32];
@@ -240,6 +266,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    // this warp has read its quarter of the accumulator: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&tmem_empty[acc_i]);
+    }  // tile loop
   }
   tc_fence_before();
   __syncthreads();
@@ -315,15 +346,26 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.tiles_per_batch = (g.T + kTileM - 1) / kTileM;
   p.bn = pick_bn(g.N, g.Bt * p.tiles_per_batch);
   const int stage_bytes = kABytes + p.bn * kBlockK * 2;
-  const long long ctas = (long long)g.Bt * p.tiles_per_batch * ((g.N + p.bn - 1) / p.bn);
-  // Bytes in flight per SM bound a latency-limited K loop: big grids run 2 CTAs/SM with ~100 KB rings each, small grids
-  // (batched decode: one CTA per SM at most) take the whole shared memory for one deep ring.
-  const int ring_budget = ctas > 148 ? 100 * 1024 : 200 * 1024;
-  p.stages = std::max(2, std::min(12, ring_budget / stage_bytes));
-  p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));
+  p.tiles_m = g.Bt * p.tiles_per_batch;
+  p.tiles_n = (g.N + p.bn - 1) / p.bn;
+  const long long tiles = (long long)p.tiles_m * p.tiles_n;
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
-  p.tmem_cols = cols;
+  p.acc_cols = cols;
+  // Persistent schedule for grids of many tiles (the codec's thin-channel stages launch up to 25 000): per-CTA set-up / tear-down
+  // and the exposed epilogue of a one-tile CTA (a 128 x 96 tile lived ~14 us for ~2 us of MMA) are paid once per SM instead of
+  // once per tile.  Two CTAs per SM when two accumulators of each fit the 512 TMEM columns, so 8 epilogue warps share an SM.
+  static const int persist_min = [] { const char* e = getenv("Q3TTS_TC_PERSIST_MIN_TILES"); return e ? atoi(e) : 4; }();
+  const int ctas_per_sm = 4 * cols <= 512 ? 2 : 1;
+  const long long resident = 148LL * ctas_per_sm;
+  const bool persistent = persist_min > 0 && tiles >= persist_min * resident;
+  p.n_acc = persistent ? 2 : 1;
+  p.tmem_cols = cols * p.n_acc;
+  // Bytes in flight per SM bound a latency-limited K loop: big grids run 2 CTAs/SM with ~100 KB rings each, small grids
+  // (one CTA per SM at most) take the whole shared memory for one deep ring.
+  const int ring_budget = (persistent ? ctas_per_sm == 2 : tiles > 148) ? 100 * 1024 : 200 * 1024;
+  p.stages = std::max(2, std::min(12, ring_budget / stage_bytes));
+  if (!persistent) p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
   p.snake_ea = g.snake_ea; p.snake_ieb = g.snake_ieb; p.snake_ch = g.snake_ch > 0 ? g.snake_ch : 1;
@@ -342,7 +384,8 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
 
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 64 * 8;
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
-  dim3 grid((unsigned)(g.Bt * p.tiles_per_batch), (unsigned)((g.N + p.bn - 1) / p.bn));
+  Q3_CHECK(2 * p.stages + 5 <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
+  dim3 grid((unsigned)(persistent ? std::min<long long>(tiles, resident) : tiles));
   launch_kernel_pdl(tc_gemm_kernel, grid, dim3(kThreads), smem, c.stream, pdl_enabled(), ma, mb, p);
   c.tick();
 }

@@ -56,6 +56,9 @@ CASES = [
     (2, 33, 96, 96, 1, 1),       # N = 96 < one weight tile, cin = 96: second k-block half zero-filled; 66 rows -> m_pad 128
     (1, 40, 64, 160, 1, 1),      # one k-block: no split possible
     (1, 3, 320, 32, 1, 1),       # 5 k-blocks over 4 slices: uneven split
+    # many tiles: the persistent schedule (ring running across tile boundaries, two TMEM accumulators)
+    (16, 9600, 96, 96, 7, 3),    # 1200 tiles over 296 CTAs (2 per SM), thin-channel vocoder shape
+    (5, 16000, 192, 192, 1, 1),  # 625 tiles over 148 CTAs (256-column accumulators: one CTA per SM)
 ]
 
 
@@ -73,6 +76,24 @@ def test_tc_conv_matches_numpy(B, T, cin, N, ntap, dil):
     print(f"B{B} T{T} cin{cin} N{N} taps{ntap} dil{dil}: max err {err:.2e}")
     assert err < 2e-4 * max(1.0, np.abs(want).max())
     assert np.abs(y16 - want).max() < 2e-3 * max(1.0, np.abs(want).max())
+
+
+def test_tc_persistent_epilogue_residual_in_place():
+    """Persistent schedule with the residual epilogue (per-channel scale) over many tiles; rows past T in the last tile of each
+    batch item are masked."""
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(11)
+    B, T, cin, N = 7, 22000, 96, 96   # 172 tiles per item (the last one 112 rows), 1204 tiles
+    x = rng.standard_normal((B, T, cin)).astype(np.float32)
+    w = (rng.standard_normal((1, N, cin)) / np.sqrt(cin)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32) * 0.1
+    res = rng.standard_normal((B, T, N)).astype(np.float32)
+    scale = rng.uniform(0.3, 0.7, N).astype(np.float32)
+    y32, y16 = q.conv_probe(x, w, bias, res=res, scale=scale)
+    want = ref_conv(x, w, bias, 1, 1, res=res, scale=scale)
+    assert np.abs(y32 - want).max() < 2e-4 * max(1.0, np.abs(want).max())
+    assert np.abs(y16 - want).max() < 4e-3 * max(1.0, np.abs(want).max())
 
 
 def test_tc_epilogues():
