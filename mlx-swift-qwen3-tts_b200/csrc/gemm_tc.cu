@@ -22,7 +22,8 @@ using namespace tcptx;
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // fp16 elements per k-block = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KB per stage
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;      // warps 0-1 + one set of 4 epilogue warps
+constexpr int kMaxThreads = 448;   // ... up to three sets (persistent schedule)
 
 struct TcParams {
   int Bt, T, cin, N, ntap, dil;
@@ -46,12 +47,13 @@ struct TcParams {
   // per CTA (gridDim.x == tiles) is the classic launch; with fewer CTAs than tiles the kernel is PERSISTENT: the TMA ring runs on
   // across tile boundaries and two TMEM accumulators (n_acc = 2) let the epilogue of tile i overlap the MMAs of tile i + 1.
   int tiles_m, tiles_n, n_acc, acc_cols;
+  int epi_sets;  // sets of 4 epilogue warps; set e handles the 32-column chunks e, e + epi_sets, ... of every tile
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kMaxThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024-B aligned
@@ -72,7 +74,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);  // one arrival per epilogue warp
+    mbar_init(&tmem_empty[0], 4 * p.epi_sets); mbar_init(&tmem_empty[1], 4 * p.epi_sets);  // one arrival per epilogue warp
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -162,7 +164,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const size_t m = (size_t)bidx * p.T + t;
     mbar_wait(&tmem_full[acc_i], (uint32_t)(use & 1));
     tc_fence_after();
-    for (int c = 0; c < p.bn; c += 32) {
+    for (int c = ((warp - 2) >> 2) * 32; c < p.bn; c += 32 * p.epi_sets) {
       uint32_t raw[32];
       tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       const int nb = n0 + c;
@@ -354,13 +356,19 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.acc_cols = cols;
   // Persistent schedule for grids of many tiles (the codec's thin-channel stages launch up to 25 000): per-CTA set-up / tear-down
   // and the exposed epilogue of a one-tile CTA (a 128 x 96 tile lived ~14 us for ~2 us of MMA) are paid once per SM instead of
-  // once per tile.  Two CTAs per SM when two accumulators of each fit the 512 TMEM columns, so 8 epilogue warps share an SM.
+  // once per tile.
   static const int persist_min = [] { const char* e = getenv("Q3TTS_TC_PERSIST_MIN_TILES"); return e ? atoi(e) : 4; }();
-  const int ctas_per_sm = 4 * cols <= 512 ? 2 : 1;
+  static const int persist_two = [] { const char* e = getenv("Q3TTS_TC_PERSIST_2CTA"); return e ? atoi(e) : 0; }();
+  const int ctas_per_sm = (persist_two && 4 * cols <= 512) ? 2 : 1;  // default: one CTA per SM with up to 3 sets of epilogue warps
   const long long resident = 148LL * ctas_per_sm;
   const bool persistent = persist_min > 0 && tiles >= persist_min * resident;
   p.n_acc = persistent ? 2 : 1;
   p.tmem_cols = cols * p.n_acc;
+  // The epilogue (TMEM -> registers -> bias / activation / SnakeBeta / residual -> global) is the latency-bound pipe of the thin
+  // stages (ncu: 3 active warps per scheduler, 0.25 eligible): a persistent CTA gets up to three sets of epilogue warps, each
+  // taking every third 32-column chunk of a tile.
+  static const int max_sets = [] { const char* e = getenv("Q3TTS_TC_EPI_SETS"); return e ? std::max(1, std::min(3, atoi(e))) : 3; }();
+  p.epi_sets = (persistent && ctas_per_sm == 1) ? std::max(1, std::min(max_sets, p.bn / 32)) : 1;
   // Bytes in flight per SM bound a latency-limited K loop: big grids run 2 CTAs/SM with ~100 KB rings each, small grids
   // (one CTA per SM at most) take the whole shared memory for one deep ring.
   const int ring_budget = (persistent ? ctas_per_sm == 2 : tiles > 148) ? 100 * 1024 : 200 * 1024;
@@ -386,7 +394,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
   Q3_CHECK(2 * p.stages + 5 <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
   dim3 grid((unsigned)(persistent ? std::min<long long>(tiles, resident) : tiles));
-  launch_kernel_pdl(tc_gemm_kernel, grid, dim3(kThreads), smem, c.stream, pdl_enabled(), ma, mb, p);
+  launch_kernel_pdl(tc_gemm_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, mb, p);
   c.tick();
 }
 
