@@ -166,9 +166,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_after();
     for (int c = ((warp - 2) >> 2) * 32; c < p.bn; c += 32 * p.epi_sets) {
       uint32_t raw[32];
-      tmem_ld32(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
+      tmem_ld32_issue(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       const int nb = n0 + c;
-      if (!row_ok || nb >= p.N) continue;
+      const bool live = row_ok && nb < p.N;
+      // the residual row segment is requested while the TMEM load is in flight (the epilogue is latency bound: ncu showed its
+      // warps waiting on exactly these global loads)
+      const int width0 = p.swiglu ? 16 : 32, ob0 = p.swiglu ? (nb >> 1) : nb;
+      float4 rres[8];
+      if (p.res && live) {
+        const float* rp = p.res + m * p.ld_res + ob0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (4 * j < width0) rres[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+      }
+      tmem_ld_wait32(raw);
+      if (!live) continue;
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -199,11 +211,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ob = nb >> 1;
       }
       if (p.res) {
-        const float* rp = p.res + m * p.ld_res + ob;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < width) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rp + j);
+            const float4 r4 = rres[j >> 2];
             float s0 = 1.f, s1 = 1.f, s2 = 1.f, s3 = 1.f;
             if (p.scale) { const float4 s4 = *reinterpret_cast<const float4*>(p.scale + ob + j); s0 = s4.x; s1 = s4.y; s2 = s4.z; s3 = s4.w; }
             v[j] = r4.x + s0 * v[j]; v[j + 1] = r4.y + s1 * v[j + 1]; v[j + 2] = r4.z + s2 * v[j + 2]; v[j + 3] = r4.w + s3 * v[j + 3];
