@@ -508,17 +508,33 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
     launch_tc_gemm(lc, g);
   }
   std::swap(cur, oa);  // cur = snake(init conv output)
+  // The blocks' residual stream lives in fp16 (R0, carved out of the fp32 buffer F0): at 96-192 channels and 640-1920 samples per
+  // frame it was the largest HBM stream of the pass (fp32: 1.2 GB read + 1.2 GB written per 1x1 conv at 64 x 26 frames); the
+  // arithmetic stays fp32, one more fp16 rounding per unit (Q3TTS_CODEC_RES32=1 keeps the fp32 stream).
+  static const bool res32 = [] { const char* e = getenv("Q3TTS_CODEC_RES32"); return e && atoi(e) != 0; }();
+  __half* R0 = reinterpret_cast<__half*>(F0);
   for (size_t bi = 0; bi < blocks_.size(); ++bi) {  // DecoderBlock (:753-784)
     Block& b = blocks_[bi];
-    // polyphase transposed conv: y (fp32 residual stream, F0) and snake_act1(y) (fp16 operand)
-    { TcGemm g = gemm(b.convT, cur, B, Tc); g.out32 = F0; g.ld32 = b.convT.n; g.out16 = oa; g.ld16 = b.convT.n; with_snake(g, b.unit[0].act1); launch_tc_gemm(lc, g); }
+    // polyphase transposed conv: y (residual stream) and snake_act1(y) (fp16 operand)
+    {
+      TcGemm g = gemm(b.convT, cur, B, Tc);
+      if (res32) { g.out32 = F0; } else { g.outr16 = R0; g.allow_skinny = 0; }
+      g.ld32 = b.convT.n; g.out16 = oa; g.ld16 = b.convT.n; with_snake(g, b.unit[0].act1);
+      launch_tc_gemm(lc, g);
+    }
     Tc *= b.rate;
     for (int j = 0; j < 3; ++j) {  // DecoderResidualUnit (:696-718)
       { TcGemm g = gemm(b.unit[j].conv1, oa, B, Tc); g.out16 = ob; g.ld16 = b.cout; with_snake(g, b.unit[j].act2); launch_tc_gemm(lc, g); }
       TcGemm g = gemm(b.unit[j].conv2, ob, B, Tc);
-      g.res = F0; g.ld_res = b.cout;
+      g.ld_res = b.cout; g.ld32 = b.cout;
       const bool last_unit = j == 2;
-      if (!last_unit) { g.out32 = F0; g.ld32 = b.cout; }
+      if (res32) {
+        g.res = F0;
+        if (!last_unit) g.out32 = F0;
+      } else {
+        g.res16 = R0; g.allow_skinny = 0;
+        if (!last_unit) g.outr16 = R0;
+      }
       g.out16 = last_unit ? cur : oa; g.ld16 = b.cout;
       const SnakeW& next = !last_unit ? b.unit[j + 1].act1 : (bi + 1 < blocks_.size() ? blocks_[bi + 1].snake : out_snake_);
       with_snake(g, next);

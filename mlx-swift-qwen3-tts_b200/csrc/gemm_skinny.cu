@@ -357,7 +357,7 @@ bool tc_skinny_enabled() {
 bool tc_skinny_supported(const TcGemm& g) {
   const bool on = tc_skinny_enabled();
   const long long M = (long long)g.Bt * g.T;
-  return on && g.allow_skinny && g.ntap == 1 && M >= 1 && M <= 128 && !g.snake_ea && !g.pcm && !(g.swiglu && g.act != TC_ACT_NONE) && tc_gemm_supported(g);
+  return on && g.allow_skinny && !g.res16 && !g.outr16 && g.ntap == 1 && M >= 1 && M <= 128 && !g.snake_ea && !g.pcm && !(g.swiglu && g.act != TC_ACT_NONE) && tc_gemm_supported(g);
 }
 
 using SkKernel = void (*)(const CUtensorMap, const CUtensorMap, const SkParams);

@@ -47,6 +47,8 @@ struct TcParams {
   // per CTA (gridDim.x == tiles) is the classic launch; with fewer CTAs than tiles the kernel is PERSISTENT: the TMA ring runs on
   // across tile boundaries and two TMEM accumulators (n_acc = 2) let the epilogue of tile i overlap the MMAs of tile i + 1.
   int tiles_m, tiles_n, n_acc, acc_cols;
+  const __half* res16;
+  __half* outr16;
   int epi_sets;  // sets of 4 epilogue warps; set e handles the 32-column chunks e, e + epi_sets, ... of every tile
 };
 
@@ -178,6 +180,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (4 * j < width0) rres[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+      } else if (p.res16 && live) {  // fp16 residual stream: 8 halves per 16-byte load, widened once they have arrived
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.ld_res + ob0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (8 * j < width0) reinterpret_cast<uint4*>(rres)[j] = rp[j];
       }
       tmem_ld_wait32(raw);
       if (!live) continue;
@@ -210,7 +217,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         width = 16;
         ob = nb >> 1;
       }
-      if (p.res) {
+      if (p.res16) {  // widen in place, back to front (rres[j] takes halves 4j..4j+3 = the low/high half of 16-byte word j/2)
+#pragma unroll
+        for (int j = 7; j >= 0; --j) {
+          if (4 * j < width) {
+            const uint4 w16 = reinterpret_cast<const uint4*>(rres)[j >> 1];
+            const uint32_t lo = (j & 1) ? w16.z : w16.x, hi = (j & 1) ? w16.w : w16.y;
+            const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&lo)), f1 = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+            rres[j] = make_float4(f0.x, f0.y, f1.x, f1.y);
+          }
+        }
+      }
+      if (p.res || p.res16) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
           if (j < width) {
@@ -224,6 +242,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.pcm) {  // DecoderOutputConv: the tile's other 31 columns are zero padding of the 1-channel weight
         if (nb == 0) p.pcm[m] = (v[0] != v[0]) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v[0]));
         continue;
+      }
+      if (p.outr16) {
+        __half* hp = p.outr16 + m * p.ld32 + ob;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (j < width) {
+            __half2 h0 = __floats2half2_rn(v[j], v[j + 1]), h1 = __floats2half2_rn(v[j + 2], v[j + 3]);
+            __half2 h2 = __floats2half2_rn(v[j + 4], v[j + 5]), h3 = __floats2half2_rn(v[j + 6], v[j + 7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(hp + j) = pk;
+          }
+        }
       }
       if (p.out32) {
         float* op = p.out32 + m * p.ld32 + ob;
@@ -391,6 +423,8 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.pcm = g.pcm;
   p.row_scale = g.row_scale;
   p.k_rotate = g.k_rotate;
+  p.res16 = g.res16; p.outr16 = g.outr16;
+  Q3_CHECK(!(g.res && g.res16) && !(g.res16 && g.ld_res % 8) && !(g.outr16 && g.ld32 % 8), Q3TTS_ERR_INVALID_ARG, "tc_gemm: bad fp16 residual arguments");
 
   const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
   const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};

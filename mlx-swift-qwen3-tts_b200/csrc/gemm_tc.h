@@ -29,6 +29,11 @@ struct TcGemm {
   int swiglu = 0;                // columns (2i, 2i+1) = (gate_i, up_i): out column i = silu(gate) * up, N_out = N / 2
   float* out32 = nullptr;        // [M][ld32] or null
   int ld32 = 0;
+  // fp16 storage of a residual stream (128-row-tile kernel only; the codec's vocoder blocks, whose fp32 stream was the largest
+  // HBM consumer of a pass): res16 [M][ld_res] replaces res, outr16 [M][ld32] replaces out32 (the value BEFORE the SnakeBeta
+  // transform that out16 carries); arithmetic stays fp32
+  const __half* res16 = nullptr;
+  __half* outr16 = nullptr;
   __half* out16 = nullptr;       // [M][ld16] or null: fp16 copy (operand of the next contraction)
   int ld16 = 0;
   const float* snake_ea = nullptr;   // SnakeBeta of the NEXT layer fused into the fp16 copy: v + ieb[ch] * sin^2(v * ea[ch]),
