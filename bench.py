@@ -233,7 +233,7 @@ def main():
 
     # roofline of the dominant kernel (dequant-fused linear), live, on rank 0
     hbm, tf, src = peaks()
-    roof = lat = None
+    roof = lat = codec4 = None
     cpu_base = None
     if rank == 0:
         iters = 20
@@ -264,6 +264,15 @@ def main():
                "batch1_linear_gbs_talker_step": nb1 * iters / (ms1 * 1e-3) / 1e9, "batch1_linear_gbs_cp_pass_L2": nbc * iters / (msc * 1e-3) / 1e9,
                "time_to_first_chunk_ms": t1.prefill_ms + 18 * msf}
         e1.close()
+        # BASELINE.json configs[3] (codec decode only, 16-codebook 12.5 Hz codes -> 24 kHz, 60 s clips, chunkedDecode(100, 10)) on a
+        # bounded sample of its 128 clips: 16 clips x 750 frames -> 128 chunks of 110 frames, device time of the passes
+        clips = np.random.default_rng(3).integers(0, 2048, size=(16, 750, 16)).astype(np.int32)
+        eng.decode_chunked(clips[:2])
+        eng.decode_chunked(clips)
+        tc = eng.timing()
+        codec4 = {"workload": "configs[3] sample: 16 of 128 clips x 750 frames, chunkedDecode(100, 10) = 128 chunks x 110 frames",
+                  "samples_per_s": 16 * 750 * up / max(1e-9, tc.decode_ms * 1e-3), "decode_ms": tc.decode_ms,
+                  "tflops": tc.codec_flops / max(1e-9, tc.decode_ms * 1e-3) / 1e12, "peak_tflops": tf}
         if world == 1 and not a.no_cpu_baseline:
             v, sec = cpu_sample(ckpt_dir, a.cpu_frames, 1, 1)
             cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
@@ -279,6 +288,7 @@ def main():
                 "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "latency": lat,
                 "codec": {"samples_per_s_rank0": codec_sps, "tflops_rank0": sum(r["codec_flops"] for r in res) / max(1e-9, sum(r["decode"] for r in res)) / 1e12,
                           "peak_tflops": tf, "share_of_step": sum(r["decode"] for r in res) / max(1e-9, dev)},
+                "codec_decode_only": codec4,
                 "talker": {"ms_per_frame_batch": sum(r["talker"] for r in res) / a.steps / a.frames * 1e3, "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev)},
                 "wall_s_timed_region": total_max}
         print(json.dumps(line), flush=True)

@@ -76,21 +76,24 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
   return v;
 }
 
-// Epilogue for `valid` (<= NC) consecutive activation rows m0.. of this thread's weight row (all 32 lanes call it together: the
+// sk_load_res: the residual values of the chunk (issued by the caller BEFORE it waits for the peers' partial sums).
+// sk_finish: epilogue for `valid` (<= NC) consecutive activation rows m0.. of this thread's weight row (all 32 lanes call it together: the
 // SwiGLU pairing is a lane shuffle).  Residual loads are issued first, stores last, so the round trips overlap; row pointers
 // advance by their leading dimension (no 64-bit multiply per element: code size matters here, see below).
 // ACT / SWIGLU are template parameters on purpose: with the exact erf and exponential expanded inline for every element of an
 // unrolled chunk, one all-purpose epilogue was ~50 KB of SASS that ran once per launch at instruction-fetch speed (2.6 us
 // per 16-column chunk measured); each instantiation now carries only its own math, at ONE call site.
-template <int NC, int ACT, bool SWIGLU>
-__device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], int valid, int m0, int ob, float bias, float scale,
-                                          const float* rowscale) {
-  float r[NC];
+template <int NC>
+__device__ __forceinline__ void sk_load_res(const SkParams& p, float (&r)[NC], int valid, int m0, int ob) {
   if (p.res) {
     const float* rp = p.res + (size_t)m0 * p.ld_res + ob;
 #pragma unroll
     for (int e = 0; e < NC; ++e, rp += p.ld_res) r[e] = e < valid ? *rp : 0.f;
   }
+}
+template <int NC, int ACT, bool SWIGLU>
+__device__ __forceinline__ void sk_finish(const SkParams& p, float (&acc)[NC], const float (&r)[NC], int valid, int m0, int ob, float bias,
+                                          float scale, const float* rowscale) {
 #pragma unroll
   for (int e = 0; e < NC; ++e) {
     float v = acc[e];
@@ -262,6 +265,16 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         }
       }
       if (threadIdx.x == 64) SK_STAMP(5);
+      // residual rows of the first chunk: requested now, they arrive while the peers' partial sums are still in flight
+      const int m_base = (int)rank * p.mc;
+      const bool lane_out = n_ok && (!SWIGLU || (n & 1) == 0);  // lanes without an output column compute (shuffle partners) but do not touch memory
+      float r16[16];
+      {
+        int valid0 = p.M - m_base;
+        valid0 = valid0 < 16 ? valid0 : 16;
+        valid0 = valid0 < p.mc ? valid0 : p.mc;
+        sk_load_res<16>(p, r16, lane_out ? valid0 : 0, m_base, so);
+      }
       if (p.split > 1) mbar_wait(red_full, 0);  // the other K slices of MY activation rows have landed
       if (threadIdx.x == 96) SK_STAMP(10);
       if (threadIdx.x == 64) {
@@ -269,7 +282,6 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         // tell every peer that its copy into this CTA is complete (it may retire its staging buffer / exit)
         for (int i = 1; i < p.split; ++i) mbar_arrive_remote_relaxed(map_to_rank(smem_u32(ack), (rank + (uint32_t)i) % (uint32_t)p.split));
       }
-      const int m_base = (int)rank * p.mc;
       const uint32_t own_s = smem_u32(stage_out), red_s = smem_u32(red);
       for (int cb = 0; cb < p.mc; cb += 16) {
         const int nc = p.mc - cb < 16 ? p.mc - cb : 16;
@@ -289,8 +301,9 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         if (threadIdx.x == 96 && cb == 0) SK_STAMP(11);
         int valid = p.M - (m_base + cb);
         valid = valid < nc ? valid : nc;
-        if (!(n_ok && (!SWIGLU || (n & 1) == 0))) valid = 0;  // lanes without an output column compute (shuffle partners) but do not touch memory
-        sk_finish<16, ACT, SWIGLU>(p, a16, valid, m_base + cb, so, bias, scale, p.rms_x ? rowscale_s + cb : nullptr);
+        if (!lane_out) valid = 0;
+        if (cb > 0) sk_load_res<16>(p, r16, valid, m_base + cb, so);
+        sk_finish<16, ACT, SWIGLU>(p, a16, r16, valid, m_base + cb, so, bias, scale, p.rms_x ? rowscale_s + cb : nullptr);
         if (threadIdx.x == 96 && cb == 0) SK_STAMP(12);
       }
       if (threadIdx.x == 96) SK_STAMP(13);
