@@ -167,6 +167,9 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
+    # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image) would precede it
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     import torch
     import torch.distributed as dist
 
