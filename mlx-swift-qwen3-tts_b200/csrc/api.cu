@@ -258,54 +258,66 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
   std::map<int, std::vector<size_t>> by_t;
   for (size_t i = 0; i < jobs.size(); ++i)
     if (jobs[i].T > 0) by_t[jobs[i].T].push_back(i);
-  cudaEvent_t e0, e1;
-  Q3_CUDA(cudaEventCreate(&e0));
-  Q3_CUDA(cudaEventCreate(&e1));
+  // Passes are double-buffered: while pass k runs on the device, the host copies pass k-1's PCM from pinned staging into the
+  // caller's buffers (10-13 MB per window batch: 2-3 ms during which the GPU used to idle).
+  struct Pass { int T, nb; size_t p0; const std::vector<size_t>* idx; };
+  std::vector<Pass> passes;
   for (auto& kv : by_t) {
     const int T = kv.first;
     Q3_CHECK(T <= c.pass_frames(), Q3TTS_ERR_CAPACITY, "decode window of %d frames exceeds codec pass capacity %d (q3tts_options.codec_max_frames)", T, c.pass_frames());
     const int per_pass = std::max(1, c.pass_frames() / T);
-    const auto& idx = kv.second;
-    for (size_t p0 = 0; p0 < idx.size(); p0 += per_pass) {
-      const int nb = (int)std::min<size_t>(per_pass, idx.size() - p0);
-      const size_t code_ints = (size_t)nb * T * 16, pcm_floats = (size_t)nb * T * up;
-      const auto h0 = std::chrono::steady_clock::now();
-      // sized once for a full pass (pass_frames x 1920 floats = 18 MB pinned at the default 2400 frames): growing on demand put a
-      // cudaMallocHost / cudaFree pair (27-800 ms measured) into whichever call first saw a slightly larger window batch
-      ensure_pinned(h, std::max(pcm_floats, (size_t)c.pass_frames() * up), std::max(code_ints, (size_t)c.pass_frames() * 16));
-      for (int b = 0; b < nb; ++b) memcpy(h->h_codes + (size_t)b * T * 16, jobs[idx[p0 + b]].frames, (size_t)T * 64);
-      int32_t* d_codes = h->d_codes;
-      float* d_pcm = h->d_pcm;
-      const auto h1 = std::chrono::steady_clock::now();
-      Q3_CUDA(cudaMemcpyAsync(d_codes, h->h_codes, code_ints * 4, cudaMemcpyHostToDevice, h->stream));
-      h->timing.h2d_bytes += (int64_t)code_ints * 4;
-      Q3_CUDA(cudaEventRecord(e0, h->stream));
-      c.decode_pass(d_codes, nb, T, d_pcm);
-      Q3_CUDA(cudaEventRecord(e1, h->stream));
-      Q3_CUDA(cudaMemcpyAsync(h->h_pcm, d_pcm, pcm_floats * 4, cudaMemcpyDeviceToHost, h->stream));
-      h->timing.d2h_bytes += (int64_t)pcm_floats * 4;
-      const auto h2 = std::chrono::steady_clock::now();
-      Q3_CUDA(cudaStreamSynchronize(h->stream));
-      const auto h3 = std::chrono::steady_clock::now();
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0, e1);
-      h->timing.decode_ms += ms;
-      h->timing.codec_flops += (int64_t)nb * T * c.flops_per_frame();
-      if (getenv("Q3TTS_HOST_TRACE")) {
-        auto wms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-        fprintf(stderr, "[q3tts host]   codec pass nb=%d T=%d: %.2f ms on the device; host: buffers %.2f, submit %.2f, wait %.2f ms\n", nb, T, ms,
-                wms(h0, h1), wms(h1, h2), wms(h2, h3));
-      }
-      for (int b = 0; b < nb; ++b) {
-        DecodeJob& j = jobs[idx[p0 + b]];
-        const int64_t total = (int64_t)T * up;
-        const int64_t n = std::max<int64_t>(0, std::min<int64_t>(total - j.drop, j.max_out));
-        if (n > 0) memcpy(j.out, h->h_pcm + (size_t)b * total + j.drop, (size_t)n * sizeof(float));
-      }
-    }
+    for (size_t p0 = 0; p0 < kv.second.size(); p0 += per_pass)
+      passes.push_back({T, (int)std::min<size_t>(per_pass, kv.second.size() - p0), p0, &kv.second});
   }
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  if (passes.empty()) return;
+  // staging sized once for two full passes (pass_frames x 1920 floats = 18 MB pinned each at the default 2400 frames): growing on
+  // demand put a cudaMallocHost / cudaFree pair (27-800 ms measured) into whichever call first saw a slightly larger window batch
+  const size_t pcm_cap = (size_t)c.pass_frames() * up, code_cap = (size_t)c.pass_frames() * 16;
+  ensure_pinned(h, 2 * pcm_cap, 2 * code_cap);
+  cudaEvent_t e0[2], e1[2], done[2];
+  for (int i = 0; i < 2; ++i) {
+    Q3_CUDA(cudaEventCreate(&e0[i]));
+    Q3_CUDA(cudaEventCreate(&e1[i]));
+    Q3_CUDA(cudaEventCreate(&done[i]));
+  }
+  const bool trace = getenv("Q3TTS_HOST_TRACE") != nullptr;
+  auto drain = [&](size_t k) {  // wait for pass k's PCM, account its device time, scatter it to the jobs' destinations
+    const Pass& ps = passes[k];
+    const int buf = (int)(k & 1);
+    Q3_CUDA(cudaEventSynchronize(done[buf]));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0[buf], e1[buf]);
+    h->timing.decode_ms += ms;
+    h->timing.codec_flops += (int64_t)ps.nb * ps.T * c.flops_per_frame();
+    if (trace) fprintf(stderr, "[q3tts host]   codec pass nb=%d T=%d: %.2f ms on the device\n", ps.nb, ps.T, ms);
+    const float* src = h->h_pcm + (size_t)buf * pcm_cap;
+    for (int b = 0; b < ps.nb; ++b) {
+      DecodeJob& j = jobs[(*ps.idx)[ps.p0 + b]];
+      const int64_t total = (int64_t)ps.T * up;
+      const int64_t n = std::max<int64_t>(0, std::min<int64_t>(total - j.drop, j.max_out));
+      if (n > 0) memcpy(j.out, src + (size_t)b * total + j.drop, (size_t)n * sizeof(float));
+    }
+  };
+  for (size_t k = 0; k < passes.size(); ++k) {
+    const Pass& ps = passes[k];
+    const int buf = (int)(k & 1), T = ps.T, nb = ps.nb;
+    const size_t code_ints = (size_t)nb * T * 16, pcm_floats = (size_t)nb * T * up;
+    int32_t* hc = h->h_codes + (size_t)buf * code_cap;   // buffer `buf` was last used by pass k-2, drained during iteration k-1
+    int32_t* d_codes = h->d_codes + (size_t)buf * code_cap;
+    float* d_pcm = h->d_pcm + (size_t)buf * pcm_cap;
+    for (int b = 0; b < nb; ++b) memcpy(hc + (size_t)b * T * 16, jobs[(*ps.idx)[ps.p0 + b]].frames, (size_t)T * 64);
+    Q3_CUDA(cudaMemcpyAsync(d_codes, hc, code_ints * 4, cudaMemcpyHostToDevice, h->stream));
+    h->timing.h2d_bytes += (int64_t)code_ints * 4;
+    Q3_CUDA(cudaEventRecord(e0[buf], h->stream));
+    c.decode_pass(d_codes, nb, T, d_pcm);
+    Q3_CUDA(cudaEventRecord(e1[buf], h->stream));
+    Q3_CUDA(cudaMemcpyAsync(h->h_pcm + (size_t)buf * pcm_cap, d_pcm, pcm_floats * 4, cudaMemcpyDeviceToHost, h->stream));
+    Q3_CUDA(cudaEventRecord(done[buf], h->stream));
+    h->timing.d2h_bytes += (int64_t)pcm_floats * 4;
+    if (k >= 1) drain(k - 1);
+  }
+  drain(passes.size() - 1);
+  for (int i = 0; i < 2; ++i) { cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]); cudaEventDestroy(done[i]); }
 }
 
 // NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732): done on the device by the codec's output kernel
