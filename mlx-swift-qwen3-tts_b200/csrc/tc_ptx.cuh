@@ -57,6 +57,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   const uint32_t hi = 64u | (1u << 14) | (2u << 29);
   return ((uint64_t)hi << 32) | lo;
 }
+// An operand whose first row is NOT at the start of an 8-row swizzle atom (start shifted by whole 128-byte rows inside a
+// 1024-B aligned tile) takes the SAME descriptor with the shifted start address: the 128-byte swizzle is a function of absolute
+// shared-memory address bits ([4,7) ^= [7,10)), for the TMA unit that wrote the tile and for the MMA unit that reads it alike.
+// Measured on B200: with the "matrix base offset" field (bits [49,52)) set to the row phase the results are wrong; without it
+// they are exact (tests/test_gpu_gemm_tc.py, 2-, 3- and 7-tap convolutions at dilations 1, 3, 9).
+__device__ __forceinline__ uint64_t umma_desc_rows(uint32_t saddr) { return umma_desc(saddr); }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
