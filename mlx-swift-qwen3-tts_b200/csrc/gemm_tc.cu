@@ -81,6 +81,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = p.ntap * p.kb_per_tap;
   const int total_tiles = p.tiles_m * p.tiles_n;
 
+  // Per-column epilogue constants (bias, the consumer's SnakeBeta pair) of this CTA's columns in shared memory: every epilogue
+  // thread needs the same 32 values per chunk -- as global loads they were 24 of the 32 load instructions of a chunk.  One
+  // column tile per kernel (tiles_n == 1: every thin vocoder layer) so the table is filled once; static parameters, no
+  // dependency on the predecessor kernel.
+  __shared__ __align__(16) float s_bias[256], s_ea[256], s_ieb[256];
+  const bool tab = p.tiles_n == 1 && !p.swiglu;
+  if (tab) {
+    for (int cidx = threadIdx.x; cidx < p.bn; cidx += blockDim.x) {
+      const bool in = cidx < p.N;
+      s_bias[cidx] = (p.bias && in) ? p.bias[cidx] : 0.f;
+      if (p.snake_ea) {
+        const int ch = cidx % p.snake_ch;
+        s_ea[cidx] = p.snake_ea[ch];
+        s_ieb[cidx] = p.snake_ieb[ch];
+      }
+    }
+  }
   pdl_launch_dependents();  // the next kernel of the stream may start its prologue / weight prefetch now
   if (threadIdx.x == 0) {
     for (int s = 0; s < (p.halo ? a_st + b_st : p.stages); ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -265,7 +282,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p.bias + nb + j);
+          const float4 b4 = tab ? *reinterpret_cast<const float4*>(s_bias + c + j) : *reinterpret_cast<const float4*>(p.bias + nb + j);
           v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
         }
       }
@@ -335,15 +352,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // is rounded to fp16 (2^-11) right after, MUFU.SIN's ~2^-21 absolute error is invisible behind it.  The precise
           // sinf + per-element modulo cost ~50 instructions per output value and made the thin-channel vocoder stages
           // epilogue-issue bound.
-          const int ch0 = ob % p.snake_ch;
+          const int ch0 = tab ? 0 : ob % p.snake_ch;
           const bool vec = (p.snake_ch & 3) == 0 && (ch0 & 3) == 0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             if (j < width) {
               int c = ch0 + j;
-              while (c >= p.snake_ch) c -= p.snake_ch;
+              while (!tab && c >= p.snake_ch) c -= p.snake_ch;
               float ea[4], ib[4];
-              if (vec) {
+              if (tab) {  // column ob + j of the tile (n0 == 0): shared-memory table
+                const float4 a4 = *reinterpret_cast<const float4*>(s_ea + ob + j), b4 = *reinterpret_cast<const float4*>(s_ieb + ob + j);
+                ea[0] = a4.x; ea[1] = a4.y; ea[2] = a4.z; ea[3] = a4.w;
+                ib[0] = b4.x; ib[1] = b4.y; ib[2] = b4.z; ib[3] = b4.w;
+              } else if (vec) {
                 const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.snake_ea + c)), b4 = __ldg(reinterpret_cast<const float4*>(p.snake_ieb + c));
                 ea[0] = a4.x; ea[1] = a4.y; ea[2] = a4.z; ea[3] = a4.w;
                 ib[0] = b4.x; ib[1] = b4.y; ib[2] = b4.z; ib[3] = b4.w;
