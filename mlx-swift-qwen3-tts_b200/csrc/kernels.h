@@ -39,6 +39,10 @@ void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, i
                                 const float* q_norm, const float* k_norm, float eps, const float* inv_freq,
                                 const int* row_slot, const int* row_pos, const KVLayout& kv);
 
+// code-predictor pass 0 on the decode path: rows (2s, 2s+1) = positions (0, 1) of slot s; norm + RoPE + append + causal attention
+void launch_cp_pass0_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int n_slots, int heads, int kv_heads, const float* q_norm,
+                                   const float* k_norm, float eps, const float* inv_freq, const KVLayout& kv, __half* out, int ldo);
+
 // softmax(q k^T / sqrt(d)) v over keys [win_start[slot], row_pos] of the row's slot, GQA by head / group (:203-216)
 void launch_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                       const int* row_slot, const int* row_pos, const int* win_start, const KVLayout& kv, float* out,

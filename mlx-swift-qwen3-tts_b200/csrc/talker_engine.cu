@@ -432,6 +432,8 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
     //      Every output row of either kernel depends only on its own input row and on the weight shape, so a request's
     //      result does not depend on which other requests shared its launches (tests: batched == single, bit for bit).
     const bool fused = decode_step && m <= 128 && tc_skinny_enabled();
+    // decode step with two rows per slot and no window = code-predictor pass 0: rows (2s, 2s+1) at positions (0, 1)
+    const bool pass0_pairs = decode_step && !one_row_per_slot && win_start == nullptr && row_pos == d_cp_pos2_ && (m % 2) == 0;
     const float inv16 = 1.0f / kX16Div;
     auto consumer = [&](const TcLinear& L, float* out32, int ld32, void* out16, int ld16, int swiglu) {
       TcGemm g;
@@ -470,6 +472,8 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       } else if (one_row_per_slot) {
         launch_rope_attention_f16(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
                                   (__half*)d_attn16_, attn_ld);
+      } else if (pass0_pairs) {
+        launch_cp_pass0_attention_f16(c, d_qkv_, qkv_ld, m / 2, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, kv, (__half*)d_attn16_, attn_ld);
       } else {
         launch_qk_norm_rope_append(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, S.head_dim, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot,
                                    row_pos, kv);

@@ -556,6 +556,90 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
     store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, num / den);
   }
 }
+// Code-predictor pass 0 (Qwen3CodePredictor.swift:183-212 with L = 2): rows (2s, 2s+1) of slot s sit at positions 0 and 1 of a
+// cache that is reset every frame, so norm + RoPE + append + causal attention of BOTH rows is one small CTA per (slot, kv head):
+// position 0 attends to itself (output = v0), position 1 to keys {0, 1}.  Replaces qk_norm_rope_append + attention_kernel
+// (two launches, ~28 us under ncu) on the decode path.
+template <int G>
+__global__ void __launch_bounds__(128) cp_pass0_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
+                                                                 const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
+                                                                 const float* __restrict__ inv_freq, KVLayout kv, __half* __restrict__ out,
+                                                                 int ldo, float scale) {
+  __shared__ __align__(16) float q1[G * 128];   // roped query heads of position 1
+  __shared__ __align__(16) float kk[2][128];    // roped keys of positions 0 and 1
+  __shared__ __align__(16) float vv[2][128];
+  __shared__ float w0[G], w1[G];                // softmax weights of position 1 over keys {0, 1}
+  pdl_launch_dependents();
+  pdl_wait();
+  const int slot = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;
+  float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;
+  // work items: (pos, head) with head in {q heads of pos 1 (G), k of pos 0, k of pos 1}; the q heads of position 0 are not needed
+  // (a single key: its softmax weight is 1 whatever the score)
+  for (int item = warp; item < G + 2; item += 4) {
+    const int pos = item < G ? 1 : item - G;
+    const float* rowp = qkv + (size_t)(2 * slot + pos) * ld;
+    const float* src = rowp + (size_t)(item < G ? (kvh * G + item) : (heads + kvh)) * 128;
+    const float a0 = src[lane], a1 = src[lane + 32], b0 = src[lane + 64], b1 = src[lane + 96];
+    const float ss = warp_sum(a0 * a0 + a1 * a1 + b0 * b0 + b1 * b1);
+    const float inv = rsqrtf(ss * (1.0f / 128.0f) + eps);
+    const float* nw = item < G ? q_norm : k_norm;
+    const float x0 = a0 * inv * nw[lane], x1 = a1 * inv * nw[lane + 32], y0 = b0 * inv * nw[lane + 64], y1 = b1 * inv * nw[lane + 96];
+    float s0 = 0.f, c0 = 1.f, s1 = 0.f, c1 = 1.f;   // position 0: identity rotation (sincosf(0) is exactly (0, 1))
+    if (pos == 1) {
+      sincosf(inv_freq[lane], &s0, &c0);
+      sincosf(inv_freq[lane + 32], &s1, &c1);
+    }
+    const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
+    float* dst = item < G ? q1 + item * 128 : kk[pos];
+    dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+    if (item >= G) {  // append k to the cache (ring index == position: the cache holds 17 positions at most)
+      float* kd = kb + (size_t)pos * 128;
+      kd[lane] = o0; kd[lane + 32] = o1; kd[lane + 64] = o2; kd[lane + 96] = o3;
+    }
+  }
+#pragma unroll
+  for (int pos = 0; pos < 2; ++pos) {
+    const float v = qkv[(size_t)(2 * slot + pos) * ld + (size_t)(heads + kv_heads + kvh) * 128 + tid];
+    vv[pos][tid] = v;
+    vb[(size_t)pos * 128 + tid] = v;
+  }
+  __syncthreads();
+  for (int g = warp; g < G; g += 4) {
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float qv = q1[g * 128 + lane + 32 * i];
+      d0 = fmaf(qv, kk[0][lane + 32 * i], d0);
+      d1 = fmaf(qv, kk[1][lane + 32 * i], d1);
+    }
+    d0 = warp_sum(d0) * scale;
+    d1 = warp_sum(d1) * scale;
+    const float mx = fmaxf(d0, d1);
+    const float e0 = expf(d0 - mx), e1 = expf(d1 - mx);
+    if (lane == 0) { w0[g] = e0 / (e0 + e1); w1[g] = e1 / (e0 + e1); }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    out[(size_t)(2 * slot) * ldo + (size_t)(kvh * G + g) * 128 + tid] = __float2half_rn(vv[0][tid]);
+    out[(size_t)(2 * slot + 1) * ldo + (size_t)(kvh * G + g) * 128 + tid] = __float2half_rn(w0[g] * vv[0][tid] + w1[g] * vv[1][tid]);
+  }
+}
+void launch_cp_pass0_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int n_slots, int heads, int kv_heads, const float* q_norm,
+                                   const float* k_norm, float eps, const float* inv_freq, const KVLayout& kv, __half* out, int ldo) {
+  if (n_slots <= 0) return;
+  const int G = heads / kv_heads;
+  const float scale = 1.0f / sqrtf(128.0f);
+  dim3 grid(n_slots, kv_heads);
+  const bool pdl = pdl_enabled();
+  if (G == 1) launch_kernel_pdl(cp_pass0_attention_kernel<1>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
+  else if (G == 2) launch_kernel_pdl(cp_pass0_attention_kernel<2>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
+  else if (G == 4) launch_kernel_pdl(cp_pass0_attention_kernel<4>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
+  else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
+  c.tick();
+}
+
 template <typename OutT>
 static void launch_rope_attention_t(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
                                     const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
