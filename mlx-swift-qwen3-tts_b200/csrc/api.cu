@@ -274,7 +274,17 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
   // demand put a cudaMallocHost / cudaFree pair (27-800 ms measured) into whichever call first saw a slightly larger window batch
   const size_t pcm_cap = (size_t)c.pass_frames() * up, code_cap = (size_t)c.pass_frames() * 16;
   ensure_pinned(h, 2 * pcm_cap, 2 * code_cap);
-  cudaEvent_t e0[2], e1[2], done[2];
+  struct Events {  // destroyed on every exit path (a failing pass throws)
+    cudaEvent_t e0[2] = {nullptr, nullptr}, e1[2] = {nullptr, nullptr}, done[2] = {nullptr, nullptr};
+    ~Events() {
+      for (int i = 0; i < 2; ++i) {
+        if (e0[i]) cudaEventDestroy(e0[i]);
+        if (e1[i]) cudaEventDestroy(e1[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+      }
+    }
+  } ev;
+  cudaEvent_t (&e0)[2] = ev.e0, (&e1)[2] = ev.e1, (&done)[2] = ev.done;
   for (int i = 0; i < 2; ++i) {
     Q3_CUDA(cudaEventCreate(&e0[i]));
     Q3_CUDA(cudaEventCreate(&e1[i]));
@@ -317,7 +327,6 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
     if (k >= 1) drain(k - 1);
   }
   drain(passes.size() - 1);
-  for (int i = 0; i < 2; ++i) { cudaEventDestroy(e0[i]); cudaEventDestroy(e1[i]); cudaEventDestroy(done[i]); }
 }
 
 // NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732): done on the device by the codec's output kernel
