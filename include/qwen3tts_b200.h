@@ -172,7 +172,10 @@ q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* re
                                         int32_t* const* codes_out, int32_t capacity_frames, int32_t* frames_out);
 
 /* replaces Qwen3Talker.generateStream (Model/Qwen3Talker.swift:633-885): code chunks of `chunk_size` frames
- * (:831-835), final partial chunk (:871-873).  q3tts_stream_next is the cancellation point (:771). */
+ * (:831-835), final partial chunk (:871-873).  q3tts_stream_next is the cancellation point (:771).
+ * A stream owns talker slot 0 of its handle from q3tts_stream_begin until q3tts_stream_free: meanwhile a second
+ * q3tts_stream_begin and every q3tts_generate_* call on that handle fail with Q3TTS_ERR_INVALID_ARG (the codec calls
+ * q3tts_decode* stay available).  q3tts_stream_cancel may be called from any thread. */
 q3tts_status q3tts_stream_begin(q3tts_handle* h, const q3tts_request* req, int32_t chunk_size, q3tts_stream** out);
 q3tts_status q3tts_stream_next(q3tts_stream* s, int32_t* codes_out /*[chunk_size][16]*/, int32_t* frames_out,
                                int32_t* done_out);
@@ -230,6 +233,12 @@ q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vo
  * (rvq_first and rvq_rest sums before their 1x1 output projections). */
 q3tts_status q3tts_rvq_embed(q3tts_handle* h, const int32_t* codes, int32_t batch, int32_t frames, float* first_out,
                              float* rest_out, int32_t* dim_out);
+
+/* `MLX.loadArrays(url:)` front end (Qwen3TTSPipeline.swift:142; Vocoder/AudioDecoder.swift:141) without a device: parses and
+ * bounds-checks the header of a .safetensors file exactly as q3tts_create does (every offset inside the file, byte count ==
+ * product(shape) * sizeof(dtype)), so a corrupt checkpoint is rejected before anything is sized from it.
+ * Returns Q3TTS_OK and the tensor count, Q3TTS_ERR_FILE_NOT_FOUND or Q3TTS_ERR_BAD_WEIGHTS (text via q3tts_last_error(NULL)). */
+q3tts_status q3tts_safetensors_check(const char* path, int32_t* n_tensors_out, int64_t* data_bytes_out);
 
 /* MLX `Conv1d` / `ConvTransposed1d` (polyphase) / `Linear` as the codec calls them (Vocoder/SpeechTokenizer.swift:142, 179,
  * 230, 726, 791), through the engine's implicit-GEMM kernels:  y[b,t,n] = epi(bias[n] + sum_tap x[b, t-(ntap-1-tap)*dil, :] . w[tap][n][:])

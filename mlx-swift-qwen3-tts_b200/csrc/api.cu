@@ -1,5 +1,6 @@
 // extern "C" entry points of libqwen3tts_b200.so (declared in include/qwen3tts_b200.h).
 #include <algorithm>
+#include <atomic>
 #include <deque>
 #include <chrono>
 #include <map>
@@ -90,6 +91,11 @@ struct CallTimer {
   }
 };
 
+void require_no_open_stream(q3tts_handle* h) {
+  Q3_CHECK(h->open_stream == nullptr, Q3TTS_ERR_INVALID_ARG,
+           "a stream is open on this handle (it owns talker slot 0): finish or free it before another talker call");
+}
+
 bool frame_valid(const int32_t* f) { return f[0] >= 0 && f[0] < 2048; }  // Model/Qwen3Talker.swift:571-576
 
 // ---- talker drivers ------------------------------------------------------------------------------------------
@@ -157,7 +163,7 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
   raw.assign(n, {});
   n_raw.assign(n, 0);
   std::vector<int> slot_req(B, -1), slot_limit(B, 0), slot_step(B, 0);
-  int next = 0, active = 0;
+  int next = 0, active = 0, logit_req = -1;
   std::vector<SlotState> st;
   while (next < n || active > 0) {
     // admit as many pending utterances as there are free slots, in ONE concatenated prefill pass
@@ -168,7 +174,10 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
       if (slot_req[s] >= 0) continue;
       while (next < n) {
         const q3tts_request& rq = reqs[next];
-        Q3_CHECK(!(rq.code0_logits_out || rq.cp_logits_out), Q3TTS_ERR_INVALID_ARG, "logit dumps are only available through q3tts_generate_codes");
+        if (rq.code0_logits_out || rq.cp_logits_out) {
+          Q3_CHECK(logit_req < 0 || logit_req == next, Q3TTS_ERR_INVALID_ARG, "at most one request of a batch may ask for logit dumps");
+          logit_req = next;
+        }
         if (rq.n_text_ids < 9) { ++next; continue; }  // too short: zero frames, like the reference's [] (Model/Qwen3Talker.swift:348-352)
         const int est = rq.n_instruct_ids + rq.n_ref_text_ids + std::max(rq.ref_frames, 0) + 10;
         if (!items.empty() && rows + est > t.max_prefill_rows()) break;
@@ -205,6 +214,8 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
       h->timing.frames += n_raw[r];
       raw[r].resize((size_t)std::max(n_raw[r], 1) * 16);
       t.fetch_frames(s, 0, n_raw[r], raw[r].data());
+      if (r == logit_req && t.dump_slot() == s)  // before the slot can be re-admitted
+        t.fetch_logits(std::min(st[s].step + 1, reqs[r].logits_capacity_frames), reqs[r].code0_logits_out, reqs[r].cp_logits_out);
       t.release(s);
       slot_req[s] = -1;
       --active;
@@ -329,10 +340,9 @@ void run_decode_jobs(q3tts_handle* h, std::vector<DecodeJob>& jobs) {
   drain(passes.size() - 1);
 }
 
-// NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732): done on the device by the codec's output kernel
-// (clip(-1, 1) maps +-Inf to +-1 before the Swift scrub sees it; NaN -> 0 is fused into out_conv_kernel), so the PCM that
+// NaN/Inf -> 0, clamp (Qwen3TTSPipeline.swift:565-570, 726-732) happen on the device in the codec's output kernel
+// (clip(-1, 1) maps +-Inf to +-1 before the Swift scrub would see it; NaN -> 0 is fused into out_conv_kernel), so the PCM that
 // reaches the host needs no second pass over every sample.
-void clean_samples(float*, int64_t) {}
 
 // Schedules the decode windows of one utterance's valid frames as `mode` prescribes; appends jobs writing into out.
 int64_t plan_decode(int mode, const int32_t* frames, int n, float* out, int64_t capacity, int up, std::vector<DecodeJob>& jobs) {
@@ -522,6 +532,7 @@ q3tts_status q3tts_generate_codes(q3tts_handle* h, const q3tts_request* req, int
   return guarded(h, [&] {
     Q3_CHECK(req && frames_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    require_no_open_stream(h);
     *frames_out = 0;
     CallTimer tm(h);
     std::vector<int32_t> raw;
@@ -539,6 +550,7 @@ q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* re
   return guarded(h, [&] {
     Q3_CHECK(reqs && frames_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    require_no_open_stream(h);
     CallTimer tm(h);
     std::vector<std::vector<int32_t>> raw;
     std::vector<int> n_raw;
@@ -560,7 +572,8 @@ struct q3tts_stream {
   int chunk_size = 12;
   int limit = 0;
   int emitted = 0;     // raw frames already delivered
-  bool talker_done = false, cancelled = false, too_short = false;
+  bool talker_done = false, too_short = false;
+  std::atomic<bool> cancelled{false};  // q3tts_stream_cancel may be called from another thread than the one pulling chunks
   // consumer state of _generateStreamImpl (Qwen3TTSPipeline.swift:520-563)
   std::deque<std::vector<int32_t>> code_buffer;  // valid frames
   std::vector<int32_t> left_context;             // up to 8 frames
@@ -601,6 +614,7 @@ q3tts_status q3tts_stream_begin(q3tts_handle* h, const q3tts_request* req, int32
   return guarded(h, [&] {
     Q3_CHECK(req && out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    require_no_open_stream(h);
     h->timing = q3tts_timing{};
     std::unique_ptr<q3tts_stream> s(new q3tts_stream());
     s->h = h;
@@ -610,6 +624,7 @@ q3tts_status q3tts_stream_begin(q3tts_handle* h, const q3tts_request* req, int32
     Admission a = h->talker->admit(0, r);
     s->too_short = a.too_short;
     s->limit = std::min(std::max(r.max_tokens, 0), h->talker->max_frames());
+    h->open_stream = s.get();
     *out = s.release();
   });
 }
@@ -629,6 +644,8 @@ q3tts_status q3tts_stream_next_audio(q3tts_stream* s, float* pcm_out, int32_t ca
     q3tts_handle* h = s->h;
     Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
     const int DECODE_CHUNK = 18, LEFT = 8, up = h->codec->total_upsample();
+    // checked BEFORE any stream state changes: a too-small buffer must not consume frames
+    Q3_CHECK((int64_t)capacity_samples >= (int64_t)DECODE_CHUNK * up, Q3TTS_ERR_CAPACITY, "pcm_out holds %d samples, a chunk needs %d", capacity_samples, DECODE_CHUNK * up);
     *samples_out = 0;
     *done_out = 0;
     int tok0 = s->total_processed, tok1 = s->total_processed, is_final = 0;
@@ -644,10 +661,8 @@ q3tts_status q3tts_stream_next_audio(q3tts_stream* s, float* pcm_out, int32_t ca
       }
       win.insert(win.end(), batch.begin(), batch.end());
       const int T = (int)win.size() / 16;
-      Q3_CHECK((int64_t)count * up <= capacity_samples, Q3TTS_ERR_CAPACITY, "pcm_out too small for a %d-frame chunk", count);
       std::vector<DecodeJob> jobs{{win.data(), T, pcm_out, (int64_t)ctx * up, (int64_t)count * up}};
       run_decode_jobs(h, jobs);
-      clean_samples(pcm_out, (int64_t)count * up);
       const int keep = std::min(LEFT, count);  // leftContext = codes.suffix(8) (:561)
       s->left_context.assign(batch.end() - (size_t)keep * 16, batch.end());
       *samples_out = count * up;
@@ -680,14 +695,17 @@ q3tts_status q3tts_stream_next_audio(q3tts_stream* s, float* pcm_out, int32_t ca
 
 q3tts_status q3tts_stream_cancel(q3tts_stream* s) {
   if (!s) return Q3TTS_ERR_INVALID_ARG;
-  s->cancelled = true;
+  s->cancelled.store(true);
   return Q3TTS_OK;
 }
 
 void q3tts_stream_free(q3tts_stream* s) {
   if (!s) return;
-  if (s->h && s->h->talker && !s->released) {
-    guarded(s->h, [&] { s->h->talker->release(0); });
+  if (s->h) {
+    guarded(s->h, [&] {
+      if (s->h->talker && !s->released) s->h->talker->release(0);
+      if (s->h->open_stream == s) s->h->open_stream = nullptr;
+    });
   }
   delete s;
 }
@@ -743,6 +761,7 @@ q3tts_status q3tts_generate_pcm(q3tts_handle* h, const q3tts_request* req, int32
   return guarded(h, [&] {
     Q3_CHECK(req && pcm_out && samples_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    require_no_open_stream(h);
     Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
     *samples_out = 0;
     if (frames_out) *frames_out = 0;
@@ -757,7 +776,6 @@ q3tts_status q3tts_generate_pcm(q3tts_handle* h, const q3tts_request* req, int32
     std::vector<DecodeJob> jobs;
     const int64_t total = plan_decode(mode, valid.data(), n, pcm_out, capacity_samples, h->codec->total_upsample(), jobs);
     run_decode_jobs(h, jobs);
-    clean_samples(pcm_out, total);
     *samples_out = total;
     if (frames_out) *frames_out = n;
     h->timing.h2d_bytes += (int64_t)req->n_text_ids * 4;
@@ -770,6 +788,7 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
   return guarded(h, [&] {
     Q3_CHECK(reqs && pcm_out && samples_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
+    require_no_open_stream(h);
     Q3_CHECK(h->codec != nullptr, Q3TTS_ERR_DECODER_LOAD_FAILED, "Failed to load MLX audio decoder");
     CallTimer tm(h);
     static const bool host_trace = getenv("Q3TTS_HOST_TRACE") != nullptr;  // wall-clock phases of this call on stderr
@@ -793,10 +812,7 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
     const auto w2 = std::chrono::steady_clock::now();
     run_decode_jobs(h, jobs);
     const auto w3 = std::chrono::steady_clock::now();
-    for (int i = 0; i < n; ++i) {
-      clean_samples(pcm_out[i], totals[i]);
-      samples_out[i] = totals[i];
-    }
+    for (int i = 0; i < n; ++i) samples_out[i] = totals[i];
     tm.finish();
     if (host_trace) {
       auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
@@ -870,6 +886,24 @@ q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, c
     g_create_error = e.what();
     cudaGetLastError();
     return e.status;
+  }
+}
+
+q3tts_status q3tts_safetensors_check(const char* path, int32_t* n_tensors_out, int64_t* data_bytes_out) {
+  try {
+    Q3_CHECK(path != nullptr, Q3TTS_ERR_INVALID_ARG, "path is NULL");
+    SafeTensors st(path);
+    int64_t bytes = 0;
+    for (auto& kv : st.tensors()) bytes += (int64_t)kv.second.nbytes;
+    if (n_tensors_out) *n_tensors_out = (int32_t)st.tensors().size();
+    if (data_bytes_out) *data_bytes_out = bytes;
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    return Q3TTS_ERR_BAD_WEIGHTS;
   }
 }
 

@@ -46,6 +46,7 @@ class TalkerEngine {
   // Copy raw frames [first, first+count) of `slot` into host memory (synchronises).
   void fetch_frames(int slot, int first, int count, int32_t* dst);
   void fetch_logits(int frames, float* code0_out, float* cp_out);
+  int dump_slot() const { return dump_enabled_ ? dump_slot_ : -1; }
   void release(int slot);
   void drop_graphs();
 
@@ -80,7 +81,12 @@ class TalkerEngine {
   void build_mega_plan();
   TcLinear make_tc(const Linear& L, bool interleave_halves, const float* fold = nullptr);
   bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }            // prefill / prompt assembly
-  bool use_tc_step(int m) const { return w_.has_tc && m >= tc_min_rows_step_; }  // decode steps
+  // decode steps: ONE numeric path per handle, fixed at creation from max_batch (not from how many slots happen to be live in a
+  // frame), so a request's codes do not depend on what it is co-batched with or on utterances finishing around it:
+  //   max_batch >= tc_min_rows_step_ (3)  -> every decode step on the tcgen05 GEMMs (fp16 operands, fp32 accumulate)
+  //   max_batch <= 2                      -> the persistent frame kernel (fp32 activations), else the SIMT graph path
+  bool use_tc_step(int) const { return handle_tc_; }
+  bool use_mega(int n_slots) const { return mega_.ok && !handle_tc_ && opt_.max_batch <= mega_.max_slots && n_slots <= mega_.max_slots; }
   // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
   void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu, bool row_count_invariant = false);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
@@ -99,6 +105,7 @@ class TalkerEngine {
   // 3.45-3.5 ms on the split-K cluster GEMM; 1-2 utterances stay on the persistent frame kernel (2.2 ms).
   int tc_min_rows_ = 16, tc_min_rows_step_ = 3;
   bool step_tc_ = false;  // set by issue_frame for the launches of the current frame step
+  bool handle_tc_ = false;  // decode steps of this handle run on tensor cores (see use_tc_step)
   float* d_rs_ = nullptr;                     // [max_rows] RMSNorm row factors for the 128-row-tile kernel (prefill)
   static constexpr float kX16Div = 16.0f;     // the fp16 copy of the residual stream is x / 16 (range headroom; exact power of two)
   void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;
@@ -120,7 +127,7 @@ class TalkerEngine {
   Embedding* d_cp_emb_ = nullptr;
   float *d_inv_freq_ = nullptr, *d_cp_inv_freq_ = nullptr;
   float *d_dump0_ = nullptr, *d_dumpcp_ = nullptr;  // logits dumps of slot 0 (allocated on first use)
-  int dump_cap_ = 0;
+  int dump_cap_ = 0, dump_slot_ = 0;  // the slot whose logits are dumped (one request per handle at a time)
   bool dump_enabled_ = false;
   float* d_probe_logits_ = nullptr;
   unsigned* d_probe_set_ = nullptr;
@@ -135,7 +142,7 @@ class TalkerEngine {
     cudaGraphExec_t exec = nullptr;
     int64_t nodes = 0;
   };
-  std::map<int, Graph> graphs_;  // key: n_slots * 2 + dump_enabled
+  std::map<long long, Graph> graphs_;  // key: n_slots * 8192 + (dump_enabled ? 1 + dump_slot : 0)
   MegaPlan mega_;                // persistent frame kernel (batch-1 decode); !ok -> graph path
 };
 
@@ -160,6 +167,9 @@ struct Handle {
   size_t d_codes_ints = 0;
   float* d_pcm = nullptr;
   size_t d_pcm_floats = 0;
+  // A stream owns talker slot 0 from q3tts_stream_begin to q3tts_stream_free: while it is open, every other talker call on
+  // the handle (and a second stream) fails with Q3TTS_ERR_INVALID_ARG instead of silently re-admitting the slot.
+  void* open_stream = nullptr;
   ~Handle();
 };
 

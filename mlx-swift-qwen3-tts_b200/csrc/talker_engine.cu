@@ -84,6 +84,7 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
     d_tpe16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
     d_tph16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
   }
+  handle_tc_ = w_.has_tc && tc_min_rows_step_ > 0 && B >= tc_min_rows_step_;
   d_probe_logits_ = arena_.alloc_n<float>(4096);
   d_probe_set_ = arena_.alloc_n<unsigned>(128);
   d_probe_out_ = arena_.alloc_n<int>(1);
@@ -639,7 +640,9 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
       Q3_CUDA(cudaMemcpyAsync(d_forced_ + (size_t)slot * F * 16, r.forced_codes, sizeof(int) * 16 * r.n_forced_frames, cudaMemcpyHostToDevice, stream_));
     }
     int logits_cap = 0;
-    if (slot == 0 && (r.code0_logits_out != nullptr || r.cp_logits_out != nullptr) && r.logits_capacity_frames > 0) {
+    if ((r.code0_logits_out != nullptr || r.cp_logits_out != nullptr) && r.logits_capacity_frames > 0) {
+      Q3_CHECK(slot == 0 || !use_mega(opt_.max_batch), Q3TTS_ERR_INVALID_ARG, "logit dumps on a handle of <= 2 slots are only available for slot 0");
+      Q3_CHECK(slot < 4096, Q3TTS_ERR_INVALID_ARG, "logit dumps are limited to slots < 4096");
       logits_cap = std::min(r.logits_capacity_frames, F);
       if (logits_cap > dump_cap_) {
         Q3_CUDA(cudaStreamSynchronize(stream_));
@@ -653,7 +656,8 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
       Q3_CUDA(cudaMemsetAsync(d_dump0_, 0, sizeof(float) * (size_t)logits_cap * cfg_.vocab_size, stream_));
       Q3_CUDA(cudaMemsetAsync(d_dumpcp_, 0, sizeof(float) * (size_t)logits_cap * 15 * cfg_.cp.vocab_size, stream_));
     }
-    if (slot == 0) dump_enabled_ = logits_cap > 0;
+    if (logits_cap > 0) { dump_slot_ = slot; dump_enabled_ = true; }
+    else if (slot == dump_slot_) dump_enabled_ = false;
     SlotState s{};
     s.active = 1;
     s.pos = p.P;  // positionOffset = inputEmbeds.shape[1] (:438)
@@ -705,7 +709,7 @@ void TalkerEngine::issue_frame(int n_slots) {
     if (step_tc_) { ni.y16 = (__half*)d_h16_; ni.y16_scale = w_.has_mtp ? 1.0f : 1.0f / kX16Div; }
     return ni;
   };
-  launch_sample(c, d_logits0_, V, n_slots, d_state_, p, d_sets_, d_cur_codes_, d_forced_, F, dump0, V, 0, 0, next_input(1));
+  launch_sample(c, d_logits0_, V, n_slots, d_state_, p, d_sets_, d_cur_codes_, d_forced_, F, dump0, V, 0, dump_slot_, next_input(1));
   for (int g = 0; g < 15; ++g) {  // code predictor, strictly sequential (:501-523)
     const int m = g == 0 ? 2 * n_slots : n_slots;
     float* x = d_cpin_;
@@ -737,7 +741,7 @@ void TalkerEngine::issue_frame(int n_slots) {
     }
     SamplerParams pg = p;
     pg.vocab = Vc; pg.group = g + 1;
-    launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, 0,
+    launch_sample(c, d_cplogits_, Vc, n_slots, d_state_, pg, d_sets_, d_cur_codes_, d_forced_, F, dumpcp, 15 * Vc, g * Vc, dump_slot_,
                   g < 14 ? next_input(2) : NextInput());
   }
   launch_frame_finalize(c, n_slots, d_state_, d_cur_codes_, d_frames_, F, d_sets_, set_words_, d_trailing_, opt_.max_trailing,
@@ -761,7 +765,7 @@ void TalkerEngine::run_frames(int n_slots, int n) {
     for (int i = 0; i < n; ++i) issue_frame(n_slots);
     return;
   }
-  if (mega_.ok && n_slots <= mega_.max_slots && !use_tc_step(n_slots)) {  // small batches: one persistent cooperative launch for all n frames
+  if (use_mega(n_slots)) {  // handles of <= 2 slots: one persistent cooperative launch for all n frames
     if (mega_.p.trace) Q3_CUDA(cudaMemsetAsync(mega_.p.trace, 0, sizeof(long long) * 2 * mega_.p.trace_stride, stream_));
     launch_frame_megakernel(ctx(), mega_, n_slots, n, dump_enabled_ ? d_dump0_ : nullptr, dump_enabled_ ? d_dumpcp_ : nullptr);
     ++mega_launches;
@@ -773,7 +777,7 @@ void TalkerEngine::run_frames(int n_slots, int n) {
     }
     return;
   }
-  const int key = n_slots * 2 + (dump_enabled_ ? 1 : 0);
+  const long long key = (long long)n_slots * 8192 + (dump_enabled_ ? 1 + dump_slot_ : 0);
   auto it = graphs_.find(key);
   if (it == graphs_.end()) {
     cudaGraph_t g = nullptr;
@@ -839,7 +843,7 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
   }
   launches = 0;
   bytes_per_iter = 0;
-  const bool tc = use_tc(m) && !S.tc.empty();
+  const bool tc = handle_tc_ && m >= tc_min_rows_step_ && !S.tc.empty();  // the launches a decode step of this handle issues at m rows
   auto pass = [&](bool count) {
     for (int l = 0; l < S.layers; ++l) {
       const LayerWeights& L = S.layer[l];
@@ -849,7 +853,8 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
         linear_tc(T.o, d_attn16_, m, d_x_, S.hidden, nullptr, 0, nullptr, TC_ACT_NONE, 0);
         linear_tc(T.gate_up_il, d_h16_, m, nullptr, 0, d_act16_, S.inter, nullptr, TC_ACT_NONE, 1);
         linear_tc(T.down, d_act16_, m, d_x_, S.hidden, nullptr, 0, nullptr, TC_ACT_NONE, 0);
-        if (count) { launches += 4; bytes_per_iter += (int64_t)2 * ((int64_t)T.qkv.out * T.qkv.in + (int64_t)T.o.out * T.o.in + (int64_t)T.gate_up_il.out * T.gate_up_il.in + (int64_t)T.down.out * T.down.in); }
+        // algorithmic bytes: the weights as the checkpoint stores them (packed codes + scales + biases)
+        if (count) { launches += 4; bytes_per_iter += (int64_t)(L.qkv.weight_bytes() + L.o.weight_bytes() + L.gate_up.weight_bytes() + L.down.weight_bytes()); }
         continue;
       }
       launch_linear(c, L.qkv, d_x_, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
@@ -861,7 +866,7 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
     if (tc) {
       const TcLinear& head = which == 0 ? w_.codec_head_tc : w_.lm_head_tc[0];
       linear_tc(head, d_h16_, m, which == 0 ? d_logits0_ : d_cplogits_, head.out, nullptr, 0, nullptr, TC_ACT_NONE, 0);
-      if (count) { launches += 1; bytes_per_iter += (int64_t)2 * head.out * head.in; }
+      if (count) { launches += 1; bytes_per_iter += (int64_t)(which == 0 ? w_.codec_head : w_.lm_head[0]).weight_bytes(); }
       return;
     }
     const Linear& head = which == 0 ? w_.codec_head : w_.lm_head[0];

@@ -158,7 +158,9 @@ struct Loader {
              "embedding '%s' has the wrong shape", k.c_str());
     Embedding e;
     e.rows = rows; e.dim = dim; e.dt = s.q3_dtype();
-    e.w = upload(s.data, s.nbytes);
+    const size_t bytes = (size_t)rows * dim * dtype_size(e.dt);
+    Q3_CHECK(s.nbytes == bytes, Q3TTS_ERR_BAD_WEIGHTS, "embedding '%s' has the wrong byte size", k.c_str());
+    e.w = upload(s.data, bytes);
     return e;
   }
 
@@ -190,9 +192,13 @@ struct Loader {
         Q3_CHECK(s.q3_dtype() == sdt && b.q3_dtype() == sdt && (size_t)s.numel() == outs[i] * row_groups &&
                      (size_t)b.numel() == outs[i] * row_groups,
                  Q3TTS_ERR_BAD_WEIGHTS, "scales/biases of '%s' have the wrong shape or dtype", prefixes[i].c_str());
-        Q3_CUDA(cudaMemcpyAsync(qw + r0 * row_words, w.data, w.nbytes, cudaMemcpyHostToDevice, stream));
-        Q3_CUDA(cudaMemcpyAsync(sc + r0 * row_groups * ssz, s.data, s.nbytes, cudaMemcpyHostToDevice, stream));
-        Q3_CUDA(cudaMemcpyAsync(bi + r0 * row_groups * ssz, b.data, b.nbytes, cudaMemcpyHostToDevice, stream));
+        // copy the byte counts the destination was sized for (SafeTensors already proved nbytes == numel * element size)
+        const size_t wbytes = (size_t)outs[i] * row_words * 4, sbytes = (size_t)outs[i] * row_groups * ssz;
+        Q3_CHECK((w.dtype == "U32" || w.dtype == "I32") && w.nbytes == wbytes && s.nbytes == sbytes && b.nbytes == sbytes, Q3TTS_ERR_BAD_WEIGHTS,
+                 "packed leaf '%s' has the wrong dtype or byte size", prefixes[i].c_str());
+        Q3_CUDA(cudaMemcpyAsync(qw + r0 * row_words, w.data, wbytes, cudaMemcpyHostToDevice, stream));
+        Q3_CUDA(cudaMemcpyAsync(sc + r0 * row_groups * ssz, s.data, sbytes, cudaMemcpyHostToDevice, stream));
+        Q3_CUDA(cudaMemcpyAsync(bi + r0 * row_groups * ssz, b.data, sbytes, cudaMemcpyHostToDevice, stream));
         r0 += outs[i];
       }
       if (weight_dtype < 0) weight_dtype = sdt;
@@ -215,7 +221,8 @@ struct Loader {
         const STensor& s = get(prefixes[i] + ".weight");
         Q3_CHECK(s.q3_dtype() == sdt && s.shape.size() == 2 && s.shape[0] == outs[i] && s.shape[1] == in, Q3TTS_ERR_BAD_WEIGHTS,
                  "dense weight '%s' has the wrong shape or dtype", prefixes[i].c_str());
-        Q3_CUDA(cudaMemcpyAsync(w + r0 * in * esz, s.data, s.nbytes, cudaMemcpyHostToDevice, stream));
+        Q3_CHECK(s.nbytes == (size_t)outs[i] * in * esz, Q3TTS_ERR_BAD_WEIGHTS, "dense weight '%s' has the wrong byte size", prefixes[i].c_str());
+        Q3_CUDA(cudaMemcpyAsync(w + r0 * in * esz, s.data, (size_t)outs[i] * in * esz, cudaMemcpyHostToDevice, stream));
         r0 += outs[i];
       }
       if (weight_dtype < 0) weight_dtype = sdt;

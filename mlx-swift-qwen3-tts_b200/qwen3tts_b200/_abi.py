@@ -85,6 +85,7 @@ SYMBOLS = {
                                  C.POINTER(C.c_double)]),
     "q3tts_sample_token": (i32, [C.c_void_p, p_f32, i32, f32, i32, f32, f32, p_i32, i32, u64, u64, p_i32]),
     "q3tts_rvq_embed": (i32, [C.c_void_p, p_i32, i32, i32, p_f32, p_f32, p_i32]),
+    "q3tts_safetensors_check": (i32, [C.c_char_p, p_i32, C.POINTER(i64)]),
 }
 
 _lib = None

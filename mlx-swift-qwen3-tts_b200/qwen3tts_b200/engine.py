@@ -7,7 +7,7 @@ chunking, WAV files) lives in `pipeline.py`, as it lives in Swift on the referen
 from __future__ import annotations
 
 import ctypes as C
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 import numpy as np
 
@@ -32,14 +32,16 @@ class GenRequest:
     stream_variant: bool = False
     forced_codes: np.ndarray | None = None  # [F][16]
     keep_invalid_frames: bool = False
-    want_logits: int = 0  # frames of logits to capture (q3tts_generate_codes only)
-    _keep: list = field(default_factory=list, repr=False)
+    want_logits: int = 0  # frames of logits to capture (one request per call)
 
     def to_c(self) -> A.Request:
+        """-> q3tts_request whose pointers reference numpy buffers kept alive by the returned struct itself (`r._keep`): the
+        caller holds the struct for as long as the C side may read it (a call, or the lifetime of a stream).  Nothing is
+        stored on the dataclass, so the same GenRequest may appear several times in one batch."""
         r = A.Request()
         A.lib().q3tts_default_request(C.byref(r))
-        keep = self._keep
-        keep.clear()
+        keep = []
+        r._keep = keep
 
         def ints(a):
             arr = np.ascontiguousarray(np.asarray(a, dtype=np.int32))
@@ -76,6 +78,16 @@ class GenRequest:
             r.n_forced_frames = int(fc.shape[0])
         r.keep_invalid_frames = 1 if self.keep_invalid_frames else 0
         return r
+
+
+def _attach_logits(r: "A.Request", frames: int, info) -> dict:
+    l0 = np.zeros((frames, info.vocab_size), dtype=np.float32)
+    lc = np.zeros((frames, 15, info.cp_vocab_size), dtype=np.float32)
+    r.code0_logits_out = l0.ctypes.data_as(A.p_f32)
+    r.cp_logits_out = lc.ctypes.data_as(A.p_f32)
+    r.logits_capacity_frames = frames
+    r._keep.extend([l0, lc])
+    return {"code0_logits": l0, "cp_logits": lc}
 
 
 class CodeStream:
@@ -174,33 +186,34 @@ class Engine:
         r = req.to_c()
         out = np.zeros((cap, 16), dtype=np.int32)
         n = A.i32(0)
-        logits = None
-        if req.want_logits:
-            l0 = np.zeros((req.want_logits, self.info.vocab_size), dtype=np.float32)
-            lc = np.zeros((req.want_logits, 15, self.info.cp_vocab_size), dtype=np.float32)
-            r.code0_logits_out = l0.ctypes.data_as(A.p_f32)
-            r.cp_logits_out = lc.ctypes.data_as(A.p_f32)
-            r.logits_capacity_frames = req.want_logits
-            logits = {"code0_logits": l0, "cp_logits": lc}
+        logits = _attach_logits(r, req.want_logits, self.info) if req.want_logits else None
         A.check(A.lib().q3tts_generate_codes(self._h, C.byref(r), out.ctypes.data_as(A.p_i32), cap, C.byref(n)), self._h)
         frames = out[: n.value].copy()
         return (frames, logits) if req.want_logits else frames
 
     def generate_codes_batch(self, reqs: list, capacity: int | None = None):
+        """-> list of frames [F_i,16]; when ONE request has want_logits set: (list, logits dict of that request)."""
         n = len(reqs)
-        cap = capacity or max([max(r.max_tokens, 1) for r in reqs] + [1])
-        arr = (A.Request * n)(*[r.to_c() for r in reqs])
+        cap = capacity or max([max(r.max_tokens, 0 if r.forced_codes is None else len(r.forced_codes), 1) for r in reqs] + [1])
+        structs = [r.to_c() for r in reqs]  # held until the call returns (they own the buffers the C side reads)
+        logits = None
+        for r, st in zip(reqs, structs):
+            if r.want_logits:
+                logits = _attach_logits(st, r.want_logits, self.info)
+        arr = (A.Request * n)(*structs)
         outs = [np.zeros((cap, 16), dtype=np.int32) for _ in range(n)]
         ptrs = (A.p_i32 * n)(*[o.ctypes.data_as(A.p_i32) for o in outs])
         counts = (A.i32 * n)()
         A.check(A.lib().q3tts_generate_codes_batch(self._h, arr, n, ptrs, cap, counts), self._h)
-        return [outs[i][: counts[i]].copy() for i in range(n)]
+        del structs
+        res = [outs[i][: counts[i]].copy() for i in range(n)]
+        return (res, logits) if logits is not None else res
 
     def stream(self, req: GenRequest, chunk_size: int = 12) -> CodeStream:
         r = req.to_c()
         p = C.c_void_p()
         A.check(A.lib().q3tts_stream_begin(self._h, C.byref(r), chunk_size, C.byref(p)), self._h)
-        return CodeStream(self, p, chunk_size, req)
+        return CodeStream(self, p, chunk_size, r)  # the stream keeps the struct (and with it the id buffers) alive
 
     # ---- codec
     def decode(self, codes: np.ndarray) -> np.ndarray:
@@ -254,7 +267,8 @@ class Engine:
         n = len(reqs)
         cap = max([max(r.max_tokens, 1) for r in reqs] + [1]) * self.info.codec_total_upsample
         outs = out_buffers or [np.zeros(cap, dtype=np.float32) for _ in range(n)]
-        arr = (A.Request * n)(*[r.to_c() for r in reqs])
+        structs = [r.to_c() for r in reqs]
+        arr = (A.Request * n)(*structs)
         ptrs = (A.p_f32 * n)(*[o.ctypes.data_as(A.p_f32) for o in outs])
         ns = (A.i64 * n)()
         fr = (A.i32 * n)()
@@ -277,6 +291,13 @@ class Engine:
 
 
 _DT = {"f32": A.F32, "f16": A.F16, "bf16": A.BF16}
+
+
+def safetensors_check(path: str):
+    """`q3tts_safetensors_check`: (n_tensors, data_bytes) of a well-formed file, raises Q3Error otherwise.  Needs no GPU."""
+    n, b = A.i32(0), A.i64(0)
+    A.check(A.lib().q3tts_safetensors_check(str(path).encode(), C.byref(n), C.byref(b)), None)
+    return n.value, b.value
 
 
 def _raw16(a, dtype: str) -> np.ndarray:

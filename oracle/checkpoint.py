@@ -159,52 +159,65 @@ def _put_linear(out: dict, key: str, w: torch.Tensor, bias: torch.Tensor | None,
         out[key + ".bias"] = bias.to(_TDT[dt])
 
 
-def talker_tensors(t: TalkerDims, bits: int, dtype: str, seed: int, group: int = 64, head_std: float = 0.25) -> dict:
+def talker_tensors(t: TalkerDims, bits: int, dtype: str, seed: int, group: int = 64, head_std: float = 0.25,
+                   init: str = "stress") -> dict:
     """Seeded random-init talker + code-predictor weights under the reference's checkpoint keys.
 
-    Linears N(0, 0.02^2); `codec_head` / `lm_head` N(0, head_std^2) so greedy
-    margins are far above fp noise; norm weights U(0.8, 1.2) so they are numerically visible.
+    init = "stress" (default of the unit tests): linears N(0, 0.02^2); `codec_head` / `lm_head` N(0, head_std^2) so greedy
+    margins are far above fp noise (logit rms ~8 at full size); embeddings N(0, 0.5^2); norm weights U(0.8, 1.2) so they are
+    numerically visible.
+    init = "baseline" (BASELINE.md §3 / SURVEY.md §8d config 1, the init the north-star tolerances are quoted on): EVERY
+    matrix, head, embedding and bias N(0, 0.02^2), norm weights = 1 (logit rms ~0.6 at full size).
     """
+    assert init in ("stress", "baseline")
+    base = init == "baseline"
     r = _Rng(seed)
     o: dict = {}
     dt = _TDT[dtype]
     H, cp = t.hidden_size, t.code_predictor
-    o["talker.model.text_embedding.weight"] = r.normal((t.text_vocab_size, t.text_hidden_size), 0.5).to(dt)
-    o["talker.model.codec_embedding.weight"] = r.normal((t.vocab_size, H), 0.5).to(dt)
+    emb_std = 0.02 if base else 0.5
+    if base:
+        head_std = 0.02
+
+    def norm_w(n):
+        return (torch.ones(n) if base else r.uniform((n,), 0.8, 1.2)).to(dt)
+
+    o["talker.model.text_embedding.weight"] = r.normal((t.text_vocab_size, t.text_hidden_size), emb_std).to(dt)
+    o["talker.model.codec_embedding.weight"] = r.normal((t.vocab_size, H), emb_std).to(dt)
     _put_linear(o, "talker.text_projection.linear_fc1", r.normal((t.text_hidden_size, t.text_hidden_size), 0.02),
                 r.normal((t.text_hidden_size,), 0.02), bits, group, dtype)
-    _put_linear(o, "talker.text_projection.linear_fc2", r.normal((H, t.text_hidden_size), 0.04),
+    _put_linear(o, "talker.text_projection.linear_fc2", r.normal((H, t.text_hidden_size), 0.02 if base else 0.04),
                 r.normal((H,), 0.02), bits, group, dtype)
 
     def layer(prefix, hid, nh, nkv, hd, inter):
-        o[prefix + ".input_layernorm.weight"] = r.uniform((hid,), 0.8, 1.2).to(dt)
-        o[prefix + ".post_attention_layernorm.weight"] = r.uniform((hid,), 0.8, 1.2).to(dt)
+        o[prefix + ".input_layernorm.weight"] = norm_w(hid)
+        o[prefix + ".post_attention_layernorm.weight"] = norm_w(hid)
         _put_linear(o, prefix + ".self_attn.q_proj", r.normal((nh * hd, hid), 0.02), None, bits, group, dtype)
         _put_linear(o, prefix + ".self_attn.k_proj", r.normal((nkv * hd, hid), 0.02), None, bits, group, dtype)
         _put_linear(o, prefix + ".self_attn.v_proj", r.normal((nkv * hd, hid), 0.02), None, bits, group, dtype)
         _put_linear(o, prefix + ".self_attn.o_proj", r.normal((hid, nh * hd), 0.02), None, bits, group, dtype)
-        o[prefix + ".self_attn.q_norm.weight"] = r.uniform((hd,), 0.8, 1.2).to(dt)
-        o[prefix + ".self_attn.k_norm.weight"] = r.uniform((hd,), 0.8, 1.2).to(dt)
+        o[prefix + ".self_attn.q_norm.weight"] = norm_w(hd)
+        o[prefix + ".self_attn.k_norm.weight"] = norm_w(hd)
         _put_linear(o, prefix + ".mlp.gate_proj", r.normal((inter, hid), 0.02), None, bits, group, dtype)
         _put_linear(o, prefix + ".mlp.up_proj", r.normal((inter, hid), 0.02), None, bits, group, dtype)
         _put_linear(o, prefix + ".mlp.down_proj", r.normal((hid, inter), 0.02), None, bits, group, dtype)
 
     for i in range(t.num_hidden_layers):
         layer(f"talker.model.layers.{i}", H, t.num_attention_heads, t.num_key_value_heads, t.head_dim, t.intermediate_size)
-    o["talker.model.norm.weight"] = r.uniform((H,), 0.8, 1.2).to(dt)
+    o["talker.model.norm.weight"] = norm_w(H)
     _put_linear(o, "talker.codec_head", r.normal((t.vocab_size, H), head_std), None, bits, group, dtype)
 
     for i in range(cp.num_code_groups - 1):
-        o[f"talker.code_predictor.model.codec_embedding.{i}.weight"] = r.normal((cp.vocab_size, H), 0.5).to(dt)
+        o[f"talker.code_predictor.model.codec_embedding.{i}.weight"] = r.normal((cp.vocab_size, H), emb_std).to(dt)
     for i in range(cp.num_hidden_layers):
         layer(f"talker.code_predictor.model.layers.{i}", cp.hidden_size, cp.num_attention_heads,
               cp.num_key_value_heads, cp.head_dim, cp.intermediate_size)
-    o["talker.code_predictor.model.norm.weight"] = r.uniform((cp.hidden_size,), 0.8, 1.2).to(dt)
+    o["talker.code_predictor.model.norm.weight"] = norm_w(cp.hidden_size)
     for i in range(cp.num_code_groups - 1):
         _put_linear(o, f"talker.code_predictor.lm_head.{i}", r.normal((cp.vocab_size, cp.hidden_size), head_std),
                     None, bits, group, dtype)
     if cp.hidden_size != H:  # Qwen3CodePredictor.swift:171-175
-        _put_linear(o, "talker.code_predictor.small_to_mtp_projection", r.normal((cp.hidden_size, H), 0.03),
+        _put_linear(o, "talker.code_predictor.small_to_mtp_projection", r.normal((cp.hidden_size, H), 0.02 if base else 0.03),
                     r.normal((cp.hidden_size,), 0.02), bits, group, dtype)
     return o
 
@@ -331,11 +344,14 @@ def codec_config_json(c: CodecDims) -> dict:
 
 def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = "bf16", seed: int = 0,
                      codec_seed: int | None = None, visible: bool = True, with_codec: bool = True,
-                     normalize_codec: bool = True) -> str:
-    """Write a complete synthetic model directory; returns `path`.  Idempotent via a stamp file."""
+                     normalize_codec: bool = True, init: str = "stress", quant_key: str = "quantization") -> str:
+    """Write a complete synthetic model directory; returns `path`.  Idempotent via a stamp file.
+
+    init: see `talker_tensors`.  quant_key = "quantization_config" writes the packed leaves WITHOUT a top-level
+    `quantization` block, i.e. the checkpoint form `Qwen3Talker.load` dequantises offline to fp16 (Qwen3Talker.swift:139-175)."""
     t, c = preset(name)
     stamp = {"name": name, "bits": bits, "dtype": dtype, "seed": seed, "codec_seed": codec_seed, "visible": visible,
-             "with_codec": with_codec, "normalize_codec": normalize_codec, "v": 3}
+             "with_codec": with_codec, "normalize_codec": normalize_codec, "init": init, "quant_key": quant_key, "v": 4}
     stamp_path = os.path.join(path, "synthetic_stamp.json")
     if os.path.exists(stamp_path):
         try:
@@ -344,8 +360,11 @@ def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = 
         except Exception:
             pass
     os.makedirs(os.path.join(path, "speech_tokenizer"), exist_ok=True)
-    json.dump(talker_config_json(t, bits), open(os.path.join(path, "config.json"), "w"), indent=1)
-    save_file(talker_tensors(t, bits, dtype, seed), os.path.join(path, "model.safetensors"))
+    cfg = talker_config_json(t, bits)
+    if bits and quant_key != "quantization":
+        cfg[quant_key] = cfg.pop("quantization")
+    json.dump(cfg, open(os.path.join(path, "config.json"), "w"), indent=1)
+    save_file(talker_tensors(t, bits, dtype, seed, init=init), os.path.join(path, "model.safetensors"))
     if with_codec:
         json.dump(codec_config_json(c), open(os.path.join(path, "speech_tokenizer", "config.json"), "w"), indent=1)
         ct = codec_tensors(c, seed + 1000 if codec_seed is None else codec_seed, visible=visible)

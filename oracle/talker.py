@@ -96,9 +96,13 @@ class TalkerOracle:
     def __init__(self, model_dir: str):
         self.cfg, extra = load_config(model_dir)
         self.spk_id = extra["spk_id"]
-        q = extra["quantization"] or extra["quantization_config"]
-        self.bits = int(q["bits"]) if q and q.get("bits") else 0
-        self.group = int(q.get("group_size", 64)) if q else 64
+        # usePreQuantized = config.quantization != nil (Qwen3Talker.swift:139); otherwise packed leaves are dequantised offline
+        # to fp16 with quantization_config's (group_size ?? 64, bits ?? 8) (:141-164)
+        self.pre_quantized = extra["quantization"] is not None
+        q = extra["quantization"] if self.pre_quantized else (extra["quantization_config"] or {})
+        self.bits = int(q.get("bits") or (0 if self.pre_quantized else 8))
+        self.group = int(q.get("group_size", 64))
+        deq_dtype = "f32" if self.pre_quantized else "f16"
         raw = load_file(os.path.join(model_dir, "model.safetensors"))
         self.w: dict[str, torch.Tensor] = {}
         # key remap of Qwen3Talker.load (:117-137)
@@ -119,7 +123,7 @@ class TalkerOracle:
                 base = k[:-7]
                 packed = v.view(torch.int32).numpy().view(np.uint32)
                 self.w[k] = torch.from_numpy(mlx_quant.dequantize(packed, tmp[base + ".scales"], tmp[base + ".biases"],
-                                                                  self.group, self.bits, "f32"))
+                                                                  self.group, self.bits, deq_dtype))
             else:
                 self.w[k] = v.to(torch.float32)
         c = self.cfg

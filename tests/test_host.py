@@ -133,3 +133,93 @@ def test_checkpoint_writer_key_scheme(tmp_path):
             assert k in keys, k
         assert tuple(f.get_tensor("decoder.decoder.1.block.1.conv.weight").shape) == (192, 96, 16)  # transposed conv [C_in, C_out, 2s]
         assert tuple(f.get_tensor("decoder.upsample.0.1.dwconv.conv.weight").shape) == (128, 1, 7)
+
+
+def test_safetensors_header_is_bounds_checked_without_a_gpu(tmp_path):
+    """Untrusted checkpoint parsing (csrc/safetensors.h): header length, dimensions, offsets and byte counts are validated before
+    anything is sized from them; q3tts_safetensors_check exposes the parser without a device."""
+    import json
+    import struct
+
+    import qwen3tts_b200 as q
+    from qwen3tts_b200 import _abi as A
+
+    def write(name, hdr, data=b"\0" * 64, hlen=None):
+        h = json.dumps(hdr).encode()
+        p = tmp_path / name
+        p.write_bytes(struct.pack("<Q", len(h) if hlen is None else hlen) + h + data)
+        return str(p)
+
+    good = {"a": {"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 64]}, "__metadata__": {"format": "pt"}}
+    assert q.safetensors_check(write("ok.safetensors", good)) == (1, 64)
+    bad = {
+        "huge_header_length": (good, dict(hlen=2 ** 63 + 5)),          # hlen + 8 would wrap around
+        "negative_dims": ({"a": {"dtype": "F32", "shape": [-4, -4], "data_offsets": [0, 64]}}, {}),
+        "bytes_vs_shape": ({"a": {"dtype": "F32", "shape": [4, 8], "data_offsets": [0, 64]}}, {}),
+        "past_the_end": ({"a": {"dtype": "F32", "shape": [4, 4], "data_offsets": [32, 96]}}, {}),
+        "reversed_offsets": ({"a": {"dtype": "F32", "shape": [4, 4], "data_offsets": [64, 0]}}, {}),
+        "unknown_dtype": ({"a": {"dtype": "Q7", "shape": [64], "data_offsets": [0, 64]}}, {}),
+    }
+    for name, (hdr, kw) in bad.items():
+        with pytest.raises(q.Q3Error) as e:
+            q.safetensors_check(write(name + ".safetensors", hdr, **kw))
+        assert e.value.status == A.ERR_BAD_WEIGHTS, name
+    with pytest.raises(q.Q3Error) as e:
+        q.safetensors_check(str(tmp_path / "missing.safetensors"))
+    assert e.value.status == A.ERR_FILE_NOT_FOUND
+    # many failing opens must not leak descriptors / mappings (the constructor cleans up on every failing path)
+    import os
+    before = len(os.listdir("/proc/self/fd"))
+    for _ in range(200):
+        with pytest.raises(q.Q3Error):
+            q.safetensors_check(write("again.safetensors", bad["bytes_vs_shape"][0]))
+    assert len(os.listdir("/proc/self/fd")) <= before + 2
+
+
+def test_request_structs_own_their_buffers():
+    """GenRequest.to_c() must not share keep-alive state between calls (the same request may appear several times in a batch)."""
+    import qwen3tts_b200 as q
+
+    r = q.GenRequest(text_ids=list(range(100, 120)), speaker_id=2861, forced_codes=np.arange(32, dtype=np.int32).reshape(2, 16))
+    a, b = r.to_c(), r.to_c()
+    assert a.text_ids[0] == 100 and b.text_ids[19] == 119 and a.n_text_ids == b.n_text_ids == 20
+    assert [a.text_ids[i] for i in range(20)] == list(range(100, 120))  # still valid after the second to_c()
+    assert a.forced_codes[31] == 31 and a.n_forced_frames == 2
+    assert not hasattr(r, "_keep")
+
+
+def test_baseline_init_checkpoint_statistics(tmp_path):
+    """init="baseline" = BASELINE.md §3: every matrix, head and embedding N(0, 0.02^2), norm weights 1."""
+    import torch
+    from oracle import checkpoint
+
+    t, _ = checkpoint.preset("tiny")
+    w = checkpoint.talker_tensors(t, 0, "f32", 0, init="baseline")
+    for k, v in w.items():
+        if "norm" in k:
+            assert torch.all(v == 1.0), k
+        elif v.ndim == 2:
+            assert abs(float(v.std()) - 0.02) < 0.004, (k, float(v.std()))
+    s = checkpoint.talker_tensors(t, 0, "f32", 0)
+    assert float(s["talker.codec_head.weight"].std()) > 0.2  # the stress init keeps its wide heads
+
+
+def test_offline_dequant_checkpoint_form(tmp_path):
+    """quant_key="quantization_config": packed leaves without `quantization` -> the oracle dequantises them to fp16 at load
+    (Qwen3Talker.swift:139-175)."""
+    import json
+    from oracle import checkpoint, mlx_quant, talker as otalker
+    from safetensors.numpy import load_file
+
+    d = checkpoint.write_checkpoint(str(tmp_path / "qc"), "tiny", bits=4, quant_key="quantization_config", with_codec=False)
+    cfg = json.load(open(d + "/config.json"))
+    assert "quantization" not in cfg and cfg["quantization_config"] == {"group_size": 64, "bits": 4}
+    o = otalker.TalkerOracle(d)
+    assert not o.pre_quantized and o.bits == 4
+    import torch
+    from safetensors.torch import load_file as tload
+    raw = tload(d + "/model.safetensors")
+    k = "talker.model.layers.0.self_attn.q_proj"
+    want = mlx_quant.dequantize(raw[k + ".weight"].view(torch.int32).numpy().view(np.uint32), raw[k + ".scales"], raw[k + ".biases"], 64, 4, "f16")
+    assert np.array_equal(o.w["layers.0.self_attn.q_proj.weight"].numpy(), want)
+    assert np.array_equal(want, want.astype(np.float16).astype(np.float32))  # fp16-representable
