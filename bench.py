@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py — BASELINE.json metric on the B200 engine (and, with --impl reference, on the CPU restatement).
 
-Workload (BASELINE.json configs[1]): Qwen3-TTS-12Hz-0.6B, MLX 4-bit g64, `generateStream` semantics (stream sampler variant,
-temperature 0.85, chunk 12, codec windows 18 / 8+18), `--batch` independent utterances per GPU (default 64) with 8-40 text
-ids from seed 1 and different speakers, `--frames` frames each (default 36 = two decode windows).  Synthetic seeded weights
-(no network).  One *step* = one such batch: prompt assembly + prefill + 36 frame steps + windowed codec decode to PCM.
+Workload of the headline line (BASELINE.json configs[1]): Qwen3-TTS-12Hz-0.6B, MLX 4-bit g64, `generateStream` semantics (stream
+sampler variant, temperature 0.85, chunk 12, codec windows 18 / 8+18), `--batch` independent utterances per GPU (default 64) with
+8-40 text ids from seed 1 and different speakers, `--frames` frames each (default 36 = two decode windows).  Synthetic seeded weights
+drawn with BASELINE.md's init (every matrix N(0, 0.02^2), norms 1; no network).  One *step* = one such batch: prompt assembly +
+prefill + 36 frame steps + windowed codec decode to PCM.
 
-  value  = audio seconds produced by all GPUs / device time of the step (CUDA events on the engine's stream: talker span +
-           codec passes; ids are tiny so "inputs resident" only excludes the PCM read-back);
-  e2e    = the same through the public C-ABI call (`q3tts_generate_pcm_batch`) with host buffers, wall clock, including the
-           H2D of ids/codes and the D2H of every PCM sample;
-  roofline = the dequant-fused linear kernel (dominant: >97 % of bytes), measured live with CUDA events over the launches of
-           one talker decode step (q3tts_profile_linear), against MEASURED_PEAKS.json hbm_gbs.
+  value    = audio seconds produced by all GPUs / device time of the step (CUDA events on the engine's stream: talker span + codec
+             passes; ids are tiny so "inputs resident" only excludes the PCM read-back);
+  e2e      = the same through the public C-ABI call (`q3tts_generate_pcm_batch`) with host buffers, wall clock, including the H2D
+             of ids/codes and the D2H of every PCM sample;
+  roofline = the dominant kernel of the step (the <= 128-row tcgen05 GEMM that streams the packed weights), measured live with CUDA
+             events over the 113 linear launches of one talker decode step (q3tts_profile_linear): ALGORITHMIC bytes (packed codes +
+             scales + biases) / average launch time, against MEASURED_PEAKS.json hbm_gbs; `traffic` = ncu dram bytes
+             per launch of the same kernel, keyed by (model, bits) in profiles/traffic.json;
+  latency  = batch-1 view (the reference's only mode): ms per frame of the persistent frame kernel and the MEASURED wall-clock
+             time to the first audio chunk through q3tts_stream_begin -> q3tts_stream_next_audio;
+  config3  = BASELINE.json configs[2]: 1.7B bf16, 512 utterances x 125 frames sharded over the ranks, whole-sequence decode, with the
+             NCCL gather of lengths + PCM to rank 0 AFTER the timed region (its time reported separately);
+  config4  = BASELINE.json configs[3]: codec decode only, 128 clips x 750 frames sharded over the ranks, chunkedDecode(100, 10) and
+             whole-sequence T = 750.
 
-Multi-GPU: request-parallel replicas — one process per GPU (torchrun), each with its own shard of
-utterances (weak scaling); NCCL is used only for the barrier, the max-over-ranks time and the gather of per-rank counts.
+Multi-GPU: request-parallel replicas — one process per GPU (torchrun), each with its own shard of utterances (weak
+scaling on the headline line); NCCL carries only the barrier, the max-over-ranks time, the sums, and the result gather.
 """
 from __future__ import annotations
 
@@ -35,16 +44,17 @@ import numpy as np  # noqa: E402
 METRIC = "audio-sec generated per sec (RTFx)"
 UNIT = "audio-sec/s"
 SPEAKERS = [3066, 3065, 3010, 3061, 2861, 2873, 2864, 2875, 2878]
+INIT = "baseline"  # oracle.checkpoint init: BASELINE.md §3
 
 
-def make_requests(q, n, frames, seed, rank=0):
+def make_requests(q, n, frames, seed, rank=0, lo=8, hi=41, temperature=0.85, stream=True):
     rng = np.random.default_rng(seed * 1000 + rank)
     reqs = []
     for i in range(n):
-        n_ids = int(rng.integers(8, 41)) + 9  # 8-40 text ids + the 9 template ids
+        n_ids = int(rng.integers(lo, hi)) + 9  # text ids + the 9 template ids
         ids = rng.integers(0, 150000, size=n_ids).tolist()
-        reqs.append(q.GenRequest(text_ids=ids, speaker_id=SPEAKERS[i % len(SPEAKERS)], temperature=0.85, max_tokens=frames,
-                                 seed=seed * 100000 + rank * 1000 + i, stream_variant=True))
+        reqs.append(q.GenRequest(text_ids=ids, speaker_id=SPEAKERS[i % len(SPEAKERS)], temperature=temperature, max_tokens=frames,
+                                 seed=seed * 100000 + rank * 1000 + i, stream_variant=stream))
     return reqs
 
 
@@ -71,10 +81,8 @@ class ClockSampler:
         for line in self.p.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
-        if self.p:
-            self.p.terminate()
-        rows = self.rows[self.first:] or self.rows[-1:]
+    def snapshot(self, last=None):
+        rows = self.rows[self.first:last] or self.rows[-1:]
         sm = [float(r[0]) for r in rows if r and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -85,6 +93,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
                 "samples": len(sm)}
 
+    def stop(self):
+        if self.p:
+            self.p.terminate()
+
+
+def ckpt_path(model, bits):
+    """Same cache layout as tests/conftest.py::ckpt, so a box that already ran the GPU tests does not write the 1-6 GB files twice."""
+    root = os.environ.get("Q3TTS_TEST_CKPT", "/tmp/q3tts_test_ckpt")
+    return os.path.join(root, f"{model}_b{bits}_bf16_s0_init{INIT}")
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -94,11 +112,21 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def workload_config(a, world):
+    wfmt = f"{a.bits}-bit g64" if a.bits else "bf16"
+    return {"workload": f"Qwen3-TTS-12Hz-{a.model} {wfmt} generateStream: {a.batch} utterances/GPU x {a.frames} frames, 8-40 text ids, stream windows 18/8+18 "
+                        f"(BASELINE.json configs[1]; weights N(0, 0.02^2), norms 1)",
+            "model": a.model, "bits": a.bits, "batch_per_gpu": a.batch, "frames": a.frames, "parallelism": f"request-parallel x{world}",
+            "cache": "a frame-step streams 0.93 GB of packed weights (0.6B 4-bit) + the KV rings of 64 utterances, >> L2 126 MB only for the talker "
+                     "stack (249 MB); the code predictor's 45 MB stay L2-resident by design; no explicit flush between steps (each step = 36 frame-steps)"}
+
+
 # --------------------------------------------------------------------------------------------------- CPU restatement arm
 def cpu_sample(ckpt_dir, frames, reps, warmup):
-    """Times the CPU restatement of the reference graph (oracle/, torch-CPU fp32, all host threads) on a bounded sample of
-    the same workload: one utterance, `frames` frames of the stream-variant loop + one codec decode of those frames.
-    Warm-up runs are 3 frames long (they only page the weights in), timed runs `frames` long."""
+    """Times the CPU restatement of the reference graph (oracle/, torch-CPU fp32, all host threads) on a bounded sample of the SAME
+    workload: ONE of the step's utterances at a time (batch 1 is the reference's only mode, Qwen3TTSPipeline.swift:484-624) — the
+    stream-variant loop for `frames` frames, then the stream's codec windows (18, then 8 + 18).  Audio is counted like the GPU arm
+    counts it: decoded PCM samples / 24000 (frames whose code0 is outside [0, 2048) produce none)."""
     import torch
 
     from oracle import codec as ocodec, pipeline as opipe, talker as otalker
@@ -109,18 +137,123 @@ def cpu_sample(ckpt_dir, frames, reps, warmup):
     rng = np.random.default_rng(1)
     times = []
     for it in range(warmup + reps):
-        ids = rng.integers(0, 150000, size=20).tolist()
+        ids = rng.integers(0, 150000, size=int(rng.integers(8, 41)) + 9).tolist()
+        n = frames if it >= warmup else 3  # warm-up runs only page the weights in
         t0 = time.perf_counter()
-        fr = orc.generate_codes(otalker.Request(text_ids=ids, speaker_id=2861, temperature=0.85, max_tokens=frames if it >= warmup else 3, seed=it,
+        fr = orc.generate_codes(otalker.Request(text_ids=ids, speaker_id=SPEAKERS[it % len(SPEAKERS)], temperature=0.85, max_tokens=n, seed=it,
                                                 stream_variant=True), filter_invalid=False)
-        valid = [f for f in fr if 0 <= f[0] < 2048] or [[0] * 16]
-        opipe.decode_whole(cdc, valid)
+        chunks = opipe.stream_chunks(cdc, [fr[i:i + 12] for i in range(0, len(fr), 12)])
+        samples = sum(int(c["samples"].size) for c in chunks)
         dt = time.perf_counter() - t0
         if it >= warmup:
-            times.append((len(fr) * 0.08, dt))
+            times.append((samples / 24000.0, dt))
     audio = sum(a for a, _ in times)
     secs = sum(t for _, t in times)
-    return audio / secs, secs / max(1, len(times))
+    return audio / max(secs, 1e-9), secs / max(1, len(times))
+
+
+def cpu_sample_text(frames):
+    return (f"1 of the step's utterances per timed run (batch 1 = the reference's only mode): {frames} frames of the stream-variant loop + the stream's "
+            f"codec windows (18, 8+18), audio counted as decoded PCM samples / 24000; CPU restatement of the reference graph (torch fp32, all host "
+            f"threads), not MLX")
+
+
+# --------------------------------------------------------------------------------------------------- extra blocks (all ranks)
+def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
+    """BASELINE.json configs[2]: 1.7B bf16, 512 synthetic utterances (ids 20-60 long, seed 2), 125 frames each, request-parallel."""
+    import torch
+
+    from qwen3tts_b200 import parallel
+
+    d = ckpt_path("1.7b", 0)
+    if rank == 0:
+        checkpoint.write_checkpoint(d, "1.7b", bits=0, dtype="bf16", seed=0, init=INIT)
+    if world > 1:
+        dist.barrier()
+    total, frames, B = a.config3_utterances, 125, 64
+    idx = parallel.shard_indices(total, rank, world)
+    eng = q.Engine(d, device=local_rank, max_batch=B, max_frames=128, kv_capacity=512)
+    up = eng.info.codec_total_upsample
+    allreq = make_requests(q, total, frames, 2, 0, lo=20, hi=61, temperature=0.85, stream=False)
+    mine = [allreq[i] for i in idx]
+    eng.generate_pcm_batch(mine[:B], q.DECODE_WHOLE)  # warm-up: graphs, workspaces
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pcm, dev_s, launches = [], 0.0, 0
+    for b0 in range(0, len(mine), B):  # continuous batching inside each call; calls of <= B keep host buffers bounded
+        outs, _ = eng.generate_pcm_batch(mine[b0:b0 + B], q.DECODE_WHOLE)
+        tm = eng.timing()
+        dev_s += (tm.talker_ms + tm.decode_ms) * 1e-3
+        launches += int(tm.kernel_launches)
+        pcm += list(outs)  # fresh host buffers per call
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    samples = sum(int(p.size) for p in pcm)
+    dev = torch.device("cuda", local_rank)
+    t_wall, sums = parallel.aggregate(dist if world > 1 else None, dev, wall, samples, (launches,))
+    t_dev, _ = parallel.aggregate(dist if world > 1 else None, dev, dev_s, 0)
+    # result gather (north star: "NCCL only to gather results"): lengths + PCM of all 512 utterances to rank 0, outside the timed region
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    g0 = time.perf_counter()
+    allpcm, lengths, moved = parallel.gather_pcm(dist if world > 1 else None, dev, pcm, total, rank, world)
+    torch.cuda.synchronize()
+    gather_s = time.perf_counter() - g0
+    eng.close()
+    if rank != 0:
+        return None
+    assert allpcm is not None and len(allpcm) == total and all(int(p.size) == l for p, l in zip(allpcm, lengths))
+    return {"workload": f"BASELINE.json configs[2]: Qwen3-TTS-12Hz-1.7B (assumed dims H 2048 / MLP 6144, 2048->1024 code-predictor projection) bf16, "
+                        f"{total} utterances x 125 frames sharded over {world} GPU(s), batches of {B} per GPU, whole-sequence decode",
+            "value": sums[0] / 24000.0 / t_dev, "e2e": sums[0] / 24000.0 / t_wall, "unit": UNIT, "n_gpus": world, "utterances": total,
+            "device_s": t_dev, "wall_s": t_wall, "gpu_launches": int(sums[1]), "dtype": "bf16 weights -> f16 operands x f32 accumulate",
+            "result_gather": {"collective": "all_reduce(lengths) + gather(PCM) to rank 0 over NCCL" if world > 1 else "single rank: no collective",
+                              "seconds": gather_s, "bytes_into_rank0": moved, "utterances_on_rank0": len(allpcm)}}
+
+
+def run_config4(q, ckpt_dir, dist, a, rank, local_rank, world, tf):
+    """BASELINE.json configs[3]: codec decode only, codes int32 [128, 750, 16] uniform in [0, 2048), seed 3; batch axis split over ranks."""
+    import torch
+
+    from qwen3tts_b200 import parallel
+
+    clips_total, T = a.config4_clips, 750
+    idx = parallel.shard_indices(clips_total, rank, world)
+    codes = np.random.default_rng(3).integers(0, 2048, size=(clips_total, T, 16)).astype(np.int32)[idx]
+    eng = q.Engine(ckpt_dir, device=local_rank, load_talker=False, codec_max_frames=3000)
+    up = eng.info.codec_total_upsample
+    res = {}
+    dev = torch.device("cuda", local_rank)
+    for mode in ("chunked", "whole"):
+        fn = (lambda c: eng.decode_chunked(c, 100, 10)) if mode == "chunked" else eng.decode
+        fn(codes[: min(4, len(codes))])  # warm-up at the measured window shape
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        dev_ms, flops = 0.0, 0
+        part = 32  # clips per call: bounds the host PCM buffer (32 x 1.44 M floats = 184 MB)
+        for b0 in range(0, len(codes), part):
+            fn(codes[b0:b0 + part])
+            tm = eng.timing()
+            dev_ms += tm.decode_ms
+            flops += int(tm.codec_flops)
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        samples = len(codes) * T * up
+        t_dev, sums = parallel.aggregate(dist if world > 1 else None, dev, dev_ms * 1e-3, samples, (flops,))
+        t_wall, _ = parallel.aggregate(dist if world > 1 else None, dev, wall, 0)
+        res[mode] = {"samples_per_s": sums[0] / t_dev, "e2e_samples_per_s": sums[0] / t_wall, "device_s": t_dev, "wall_s": t_wall,
+                     "tflops": sums[1] / t_dev / 1e12, "tensor_frac_of_peak": sums[1] / t_dev / 1e12 / (tf * world)}
+    eng.close()
+    if rank != 0:
+        return None
+    return {"workload": f"BASELINE.json configs[3]: speech_tokenizer decode only, {clips_total} clips x 750 frames (60 s) sharded over {world} GPU(s); "
+                        "chunked = chunkedDecode(100, 10) -> windows of 110 stacked on the batch axis; whole = one T = 750 pass per clip",
+            "unit": "samples/s", "peak_tflops_per_gpu": tf, "n_gpus": world, **res}
 
 
 def main():
@@ -134,35 +267,36 @@ def main():
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--model", default="0.6b")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-frames", type=int, default=60)
+    ap.add_argument("--no-extras", action="store_true", help="headline line only (no latency / config3 / config4 blocks)")
+    ap.add_argument("--config3", default="on", choices=["on", "off"])
+    ap.add_argument("--config4", default="on", choices=["on", "off"])
+    ap.add_argument("--config3-utterances", type=int, default=512)
+    ap.add_argument("--config4-clips", type=int, default=128)
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == max(1, a.gpus) or world == 1, f"WORLD_SIZE {world} != --gpus {a.gpus}"
-    wfmt = f"{a.bits}-bit g64" if a.bits else "bf16"
-    config = {"workload": f"Qwen3-TTS-12Hz-{a.model} {wfmt} generateStream: {a.batch} utterances/GPU x {a.frames} frames, stream windows 18/8+18",
-              "model": a.model, "bits": a.bits, "batch_per_gpu": a.batch, "frames": a.frames, "parallelism": f"request-parallel x{world}",
-              "cache": "batched steps stream 3.3 GB of fp16 weight copies per frame-step (0.6B) >> L2 126 MB; no explicit flush"}
+    config = workload_config(a, max(1, a.gpus))
 
     from oracle import checkpoint
 
-    ckpt_dir = f"/tmp/q3tts_bench_{a.model}_{a.bits}"
+    ckpt_dir = ckpt_path(a.model, a.bits)
 
     if a.impl == "reference":
         # The reference's own implementation of the path cannot run here (Swift + MLX): this arm times the CPU
-        # restatement (oracle/) on the host cores, rank 0 only.
+        # restatement (oracle/) on the host cores, rank 0 only, on a bounded sample of the SAME workload (see cpu_sample).
         if rank != 0:
             return
-        checkpoint.write_checkpoint(ckpt_dir, a.model, bits=a.bits, dtype="bf16", seed=0)
-        v, sec = cpu_sample(ckpt_dir, a.cpu_frames, max(1, a.steps), min(a.warmup, 1))
+        checkpoint.write_checkpoint(ckpt_dir, a.model, bits=a.bits, dtype="bf16", seed=0, init=INIT)
+        steps = max(1, a.steps)  # ~4 s of CPU work per step
+        v, sec = cpu_sample(ckpt_dir, a.frames, steps, min(a.warmup, 1))
         cores = os.cpu_count() or 1
-        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": min(a.warmup, 1),
+        line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1),
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
-                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"1 utterance x {a.cpu_frames} frames (stream loop, batch 1 = the reference's only mode) + 1 whole-sequence codec decode per step; CPU restatement of the reference graph (torch fp32, all host threads), not MLX"},
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": cpu_sample_text(a.frames)},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), flush=True)
         return
@@ -179,7 +313,7 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if rank == 0:
-        checkpoint.write_checkpoint(ckpt_dir, a.model, bits=a.bits, dtype="bf16", seed=0)
+        checkpoint.write_checkpoint(ckpt_dir, a.model, bits=a.bits, dtype="bf16", seed=0, init=INIT)
     if world > 1:
         dist.barrier()
 
@@ -201,7 +335,7 @@ def main():
         samples = int(sum(p.size for p in pcm))
         return {"wall": wall, "dev": (tm.talker_ms + tm.decode_ms) * 1e-3, "talker": tm.talker_ms * 1e-3, "decode": tm.decode_ms * 1e-3,
                 "samples": samples, "frames": int(tm.frames), "launches": int(tm.kernel_launches), "h2d": int(tm.h2d_bytes), "d2h": int(tm.d2h_bytes),
-                "codec_flops": int(tm.codec_flops), "bytes_frame": int(tm.weight_bytes_per_frame)}
+                "codec_flops": int(tm.codec_flops), "bytes_frame": int(tm.weight_bytes_per_frame), "prefill": tm.prefill_ms * 1e-3}
 
     # nvidia-smi is started BEFORE the warm-up steps: its start-up (NVML init takes driver locks for tens to hundreds of ms on a
     # box without persistence mode) would otherwise stall kernel submission inside the first timed step; it keeps sampling
@@ -220,7 +354,8 @@ def main():
     if world > 1:
         dist.barrier()
     t_total = time.perf_counter() - t_begin
-    clocks = sampler.stop()
+    clocks = sampler.snapshot()
+    n_clock_rows = len(sampler.rows)
 
     dev = sum(r["dev"] for r in res)
     wall = sum(r["wall"] for r in res)
@@ -234,68 +369,96 @@ def main():
     samples_all, launches_all, h2d_all, d2h_all = [float(x) for x in sums.tolist()]
     audio_s = samples_all / 24000.0
 
-    # roofline of the dominant kernel (dequant-fused linear), live, on rank 0
     hbm, tf, src = peaks()
-    roof = lat = codec4 = None
-    cpu_base = None
-    if rank == 0:
+    roof = lat = cpu_base = None
+    extras = not a.no_extras
+    if rank == 0 and extras:
+        # ---- roofline of the dominant kernel, live (algorithmic bytes = the weights as stored)
         iters = 20
         ms, n, nbytes = eng.profile_linear(0, a.batch, iters)
-        ach = nbytes * iters / (ms * 1e-3) / 1e9
-        kname = ("tc_skinny_kernel (tcgen05 / TMEM split-K cluster GEMM over fp16 dense weight copies), the 113 linears of one talker decode step at m = batch rows, replayed as a CUDA graph"
-                 if 16 <= a.batch <= 128 else "tc_gemm_kernel" if a.batch > 128 else "linear_kernel (dequant-fused GEMV), the linears of one talker decode step at m = batch rows")
+        packed = eng.info.quant_bits in (4, 8)
+        if 3 <= a.batch <= 128:
+            kname = ("tc_skinny_q_kernel (tcgen05 / TMEM split-K cluster GEMM, MLX-packed weights streamed and dequantised in-kernel)" if packed
+                     else "tc_skinny_kernel (tcgen05 / TMEM split-K cluster GEMM over the dense weights)")
+        elif a.batch > 128:
+            kname = "tc_gemm_kernel (128-row-tile tcgen05 GEMM)"
+        else:
+            kname = "linear_kernel (dequant-fused GEMV)"
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch from the committed ncu --set full capture
+        tp = os.path.join(ROOT, "profiles", "traffic.json")  # dram__bytes_read+write per launch from the committed ncu --set full captures
+        key = f"{a.model}:{a.bits}:m{a.batch}"
         if os.path.exists(tp):
-            tj = json.load(open(tp))
-            traffic = tj.get("tc_skinny_m64" if a.batch >= 16 else "linear_m1", {}).get("dram_bytes_per_launch")
-        roof = {"bound": "hbm", "kernel": kname,
-                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "peak_source": src,
-                "launches_timed": n, "algorithmic_bytes_per_launch": nbytes / (n / iters), "avg_launch_us": ms * 1e3 / n}
-        ms1, n1, nb1 = eng.profile_linear(0, 1, iters)
-        msc, nc, nbc = eng.profile_linear(1, 1, iters)
-        # batch-1 latency view of the same path (the reference's only mode)
-        e1 = q.Engine(ckpt_dir, device=local_rank, max_batch=1, max_frames=64, load_codec=False)
+            traffic = (json.load(open(tp)).get(key) or {}).get("dram_bytes_per_launch")
+        alg = nbytes / (n / iters)
+        ach = nbytes * iters / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": kname + f"; the {n // iters} linear launches of one talker decode step at m = {a.batch} rows, replayed as a CUDA graph",
+                "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "traffic_key": key,
+                "traffic_over_algorithmic": (traffic / alg) if traffic else None, "peak_source": src, "launches_timed": n,
+                "algorithmic_bytes_per_launch": alg, "avg_launch_us": ms * 1e3 / n,
+                "note": "latency-bound: ~600 dependent launches per frame-step, each far below the bytes one launch could move (DESIGN.md §3.2)"}
+        # ---- batch-1 latency view (the reference's only mode), max_batch = 1 handle: persistent frame kernel + codec
+        e1 = q.Engine(ckpt_dir, device=local_rank, max_batch=1, max_frames=64)
         r1 = q.GenRequest(text_ids=list(range(1000, 1024)), speaker_id=2861, temperature=0.85, max_tokens=36, stream_variant=True, keep_invalid_frames=True)
         e1.generate_codes(r1)
         e1.generate_codes(r1)
         t1 = e1.timing()
         msf = (t1.talker_ms - t1.prefill_ms) / max(1, t1.frames)
-        lat = {"batch1_path": "persistent frame kernel (1 cooperative launch per 8 frames)" if t1.persistent_launches else "CUDA graph of per-op kernels",
+        ttfc = []
+        for rep in range(4):  # wall clock: q3tts_stream_begin -> first q3tts_stream_next_audio returns (prefill + 18 frames + first window + D2H)
+            w0 = time.perf_counter()
+            st = e1.stream(r1, 12)
+            s0, _, _, _ = st.next_audio()
+            w1 = time.perf_counter()
+            st.close()
+            if rep:
+                ttfc.append(((w1 - w0) * 1e3, int(s0.size)))
+        ms1, n1, nb1 = eng.profile_linear(0, 1, iters)
+        msc, nc, nbc = eng.profile_linear(1, 1, iters)
+        lat = {"batch1_path": "persistent frame kernel (1 cooperative launch per run of frames)" if t1.persistent_launches else "CUDA graph of per-op kernels",
                "batch1_ms_per_frame": msf, "batch1_rtfx": 80.0 / msf, "batch1_prefill_ms": t1.prefill_ms,
                "batch1_frame_roofline_frac": (t1.weight_bytes_per_frame / (msf * 1e-3) / 1e9) / hbm,
+               "batch1_frame_algorithmic_bytes": int(t1.weight_bytes_per_frame),
                "batch1_linear_gbs_talker_step": nb1 * iters / (ms1 * 1e-3) / 1e9, "batch1_linear_gbs_cp_pass_L2": nbc * iters / (msc * 1e-3) / 1e9,
-               "time_to_first_chunk_ms": t1.prefill_ms + 18 * msf}
+               "time_to_first_chunk_ms": float(np.median([t for t, _ in ttfc])), "time_to_first_chunk_samples": ttfc[0][1],
+               "time_to_first_chunk_how": "measured wall clock, q3tts_stream_begin -> first q3tts_stream_next_audio (18-frame window), median of 3",
+               "like_for_like_single_stream_rtfx": 80.0 / msf}
         e1.close()
-        # BASELINE.json configs[3] (codec decode only, 16-codebook 12.5 Hz codes -> 24 kHz, 60 s clips, chunkedDecode(100, 10)) on a
-        # bounded sample of its 128 clips: 16 clips x 750 frames -> 128 chunks of 110 frames, device time of the passes
-        clips = np.random.default_rng(3).integers(0, 2048, size=(16, 750, 16)).astype(np.int32)
-        eng.decode_chunked(clips)  # warm-up at the measured shape (workspace growth, first-use kernels)
-        eng.decode_chunked(clips)
-        tc = eng.timing()
-        codec4 = {"workload": "configs[3] sample: 16 of 128 clips x 750 frames, chunkedDecode(100, 10) = 128 chunks x 110 frames",
-                  "samples_per_s": 16 * 750 * up / max(1e-9, tc.decode_ms * 1e-3), "decode_ms": tc.decode_ms,
-                  "tflops": tc.codec_flops / max(1e-9, tc.decode_ms * 1e-3) / 1e12, "peak_tflops": tf}
         if world == 1 and not a.no_cpu_baseline:
-            v, sec = cpu_sample(ckpt_dir, a.cpu_frames, 1, 1)
+            v, sec = cpu_sample(ckpt_dir, a.frames, 2, 1)
             cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-                        "sample": f"1 utterance x {a.cpu_frames} frames (stream loop, batch 1 = the reference's only mode) + 1 whole-sequence codec decode, 1 timed run of {sec:.1f} s after a 3-frame warm-up; CPU restatement of the reference graph (torch fp32, all host threads), not MLX"}
+                        "sample": cpu_sample_text(a.frames) + f"; 2 timed runs of {sec:.1f} s after a 3-frame warm-up",
+                        "single_stream_gpu_over_cpu": (80.0 / msf) / max(v, 1e-9)}
+    eng_bytes = int(res[0]["bytes_frame"])
+    talker_ms_frame = (sum(r["talker"] - r["prefill"] for r in res)) / a.steps / a.frames * 1e3
+    eng.close()
+
+    cfg3 = cfg4 = None
+    if extras and a.config4 == "on":
+        cfg4 = run_config4(q, ckpt_dir, dist, a, rank, local_rank, world, tf)
+    if extras and a.config3 == "on":
+        cfg3 = run_config3(q, checkpoint, dist, a, rank, local_rank, world)
+    clocks_all = sampler.snapshot()
+    sampler.stop()
 
     if rank == 0:
         codec_sps = samples / max(1e-9, sum(r["decode"] for r in res))
+        packed = a.bits in (4, 8)
         line = {"metric": METRIC, "value": audio_s / dev_max, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-                "ms_per_step": dev_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16 operands (dequantised once at load) x f32 accumulate, f32 residual stream" if a.batch >= 16 else "f32 activations, u4 g64 weights",
+                "ms_per_step": dev_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": (f"u{a.bits} g64 weights dequantised inside the GEMM to f16 operands x f32 accumulate, f32 residual stream" if packed
+                          else "bf16 weights -> f16 operands x f32 accumulate, f32 residual stream") if a.batch >= 3 else "f32 activations, packed weights",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": audio_s / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d_all / world / a.steps, "d2h_bytes_per_step": d2h_all / world / a.steps,
                         "ms_per_step": wall_max / a.steps * 1e3},
-                "gpu_launches": int(launches_all), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base, "latency": lat,
+                "gpu_launches": int(launches_all), "clocks": clocks, "clocks_whole_run": clocks_all, "roofline": roof, "cpu_baseline": cpu_base, "latency": lat,
                 "codec": {"samples_per_s_rank0": codec_sps, "tflops_rank0": sum(r["codec_flops"] for r in res) / max(1e-9, sum(r["decode"] for r in res)) / 1e12,
                           "peak_tflops": tf, "share_of_step": sum(r["decode"] for r in res) / max(1e-9, dev)},
-                "codec_decode_only": codec4,
-                "talker": {"ms_per_frame_batch": sum(r["talker"] for r in res) / a.steps / a.frames * 1e3, "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev)},
+                "talker": {"ms_per_frame_step_batch": talker_ms_frame, "prefill_ms_per_step": sum(r["prefill"] for r in res) / a.steps * 1e3,
+                           "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev), "algorithmic_weight_bytes_per_frame_step": eng_bytes,
+                           "frame_step_hbm_frac": (eng_bytes / max(1e-9, talker_ms_frame * 1e-3) / 1e9) / hbm},
+                "config3": cfg3, "config4": cfg4,
                 "wall_s_timed_region": total_max}
         print(json.dumps(line), flush=True)
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -223,6 +223,15 @@ q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, c
                                     const void* scales, const void* biases, int32_t scale_dtype,
                                     int32_t out_features, int32_t in_features, int32_t group_size, int32_t bits,
                                     float* y);
+/* The same contraction on the tensor-core path batched decode takes (csrc/gemm_skinny_q.cu): the packed matrix is the streamed
+ * operand of a tcgen05 GEMM for m <= 128 rows, dequantised inside the kernel; activations rounded to fp16, fp32 accumulate.
+ * fold (fp32 [in_features] or NULL): multiplied into the dequantised columns before their fp16 rounding (a folded RMSNorm weight).
+ * swiglu_halves = 1: the packed rows are [gate ; up] (out_features / 2 each) and y[m][i] = silu(gate_i . x) * up_i . x for
+ * i < out_features / 2 (Model/Qwen3Layers.swift:236); 0: y[m][out_features].  residual (fp32 [m][out] or NULL) is added. */
+q3tts_status q3tts_quantized_matmul_tc(int32_t device, const float* x, int32_t m, const uint32_t* packed, const void* scales,
+                                       const void* biases, int32_t scale_dtype, int32_t out_features, int32_t in_features,
+                                       int32_t group_size, int32_t bits, const float* fold, int32_t swiglu_halves,
+                                       const float* residual, float* y);
 /* Qwen3Talker.sampleToken (Model/Qwen3Talker.swift:274-322) on one logits row; `counter` selects the position in
  * the request's sampler stream; token_set = ids already generated for this group (may be NULL). */
 q3tts_status q3tts_sample_token(q3tts_handle* h, const float* logits, int32_t vocab, float temperature, int32_t top_k,

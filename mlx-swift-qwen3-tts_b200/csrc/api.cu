@@ -889,6 +889,52 @@ q3tts_status q3tts_quantized_matmul(int32_t device, const float* x, int32_t m, c
   }
 }
 
+q3tts_status q3tts_quantized_matmul_tc(int32_t device, const float* x, int32_t m, const uint32_t* packed, const void* scales, const void* biases,
+                                       int32_t scale_dtype, int32_t out_f, int32_t in_f, int32_t group, int32_t bits, const float* fold,
+                                       int32_t swiglu_halves, const float* residual, float* y) {
+  try {
+    Q3_CHECK(x && packed && scales && biases && y && m > 0 && m <= 128, Q3TTS_ERR_INVALID_ARG, "bad arguments (1 <= m <= 128)");
+    require_device(device);
+    init_tc_gemm();
+    const int n_out = swiglu_halves ? out_f / 2 : out_f;
+    const size_t wbytes = (size_t)out_f * in_f * bits / 8, sbytes = (size_t)out_f * (in_f / group) * dtype_size(scale_dtype);
+    std::vector<void*> allocs;
+    auto dev = [&](const void* src, size_t bytes) -> void* {
+      void* d = nullptr;
+      Q3_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+      allocs.push_back(d);
+      if (src) Q3_CUDA(cudaMemcpy(d, src, bytes, cudaMemcpyHostToDevice));
+      return d;
+    };
+    void *dw = dev(packed, wbytes), *ds = dev(scales, sbytes), *db = dev(biases, sbytes);
+    float* dx = (float*)dev(x, (size_t)m * in_f * 4);
+    float* dfold = fold ? (float*)dev(fold, (size_t)in_f * 4) : nullptr;
+    float* dy = (float*)dev(residual, (size_t)m * n_out * 4);
+    if (!residual) Q3_CUDA(cudaMemset(dy, 0, (size_t)m * n_out * 4));
+    __half* dx16 = (__half*)dev(nullptr, (size_t)m * in_f * 2);
+    LaunchCtx c{nullptr, nullptr};
+    Q3_CHECK(((size_t)m * in_f) % 4 == 0, Q3TTS_ERR_INVALID_ARG, "m * in_features must be divisible by 4");
+    launch_f32_to_f16(c, dx, (size_t)m * in_f, dx16);
+    Q3_CUDA(cudaDeviceSynchronize());
+    TcGemm g;
+    g.a = dx16; g.Bt = 1; g.T = m; g.cin = in_f; g.N = out_f; g.swiglu = swiglu_halves ? 1 : 0;
+    g.q_w = (const uint32_t*)dw; g.q_scales = ds; g.q_biases = db; g.q_fold = dfold; g.q_bits = bits; g.q_group = group; g.q_sdt = scale_dtype;
+    g.q_halves = swiglu_halves ? 1 : 0;
+    g.out32 = dy; g.ld32 = n_out;
+    if (residual) { g.res = dy; g.ld_res = n_out; }
+    Q3_CHECK(tc_skinny_q_supported(g), Q3TTS_ERR_INVALID_ARG, "shape not supported by the dequant-fused tensor-core GEMM");
+    launch_tc_skinny_q(c, g);
+    Q3_CUDA(cudaDeviceSynchronize());
+    Q3_CUDA(cudaMemcpy(y, dy, (size_t)m * n_out * 4, cudaMemcpyDeviceToHost));
+    for (void* d : allocs) cudaFree(d);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
 q3tts_status q3tts_safetensors_check(const char* path, int32_t* n_tensors_out, int64_t* data_bytes_out) {
   try {
     Q3_CHECK(path != nullptr, Q3TTS_ERR_INVALID_ARG, "path is NULL");

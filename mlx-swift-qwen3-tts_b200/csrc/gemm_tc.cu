@@ -443,6 +443,11 @@ void tc_resolve_encode() {
   Q3_CHECK(g_encode != nullptr, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
 }
 
+TcEncodeFn tc_encode_fn() {
+  tc_resolve_encode();
+  return reinterpret_cast<TcEncodeFn>(g_encode);
+}
+
 CUtensorMap tc_make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
   CUtensorMap m;
   const uint32_t estr[3] = {1, 1, 1};

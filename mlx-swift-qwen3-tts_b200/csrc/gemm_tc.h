@@ -56,6 +56,17 @@ struct TcGemm {
   // 0: every CTA of the 128-row-tile kernel walks K from 0 (default: from a per-CTA offset, which spreads same-address L2 reads
   // but makes the fp32 summation order -- the low bits of a row's result -- depend on the tile shape, i.e. on the row count)
   int k_rotate = 1;
+  // Packed weights as the streamed operand (<= 128-row kernel, gemm_skinny_q.cu): when q_w is set and the shape qualifies
+  // (tc_skinny_q_supported) the kernel reads the MLX-packed matrix [N][cin * q_bits / 32] uint32 + scales / biases [N][cin / q_group]
+  // of dtype q_sdt and dequantises inside; `w` (the fp16 copy of the same matrix) is the fallback operand and may be null only if
+  // the caller checked tc_skinny_q_supported first.  q_fold (fp32 [cin], may be null) is multiplied into the dequantised columns
+  // before the fp16 rounding -- the RMSNorm weight in front of this linear, exactly what TalkerEngine::make_tc folds into `w`.
+  // q_halves: the packed matrix is [gate ; up] (N / 2 rows each) while the kernel's tile rows are interleaved (gate_i, up_i), as in `w`.
+  const uint32_t* q_w = nullptr;
+  const void* q_scales = nullptr;
+  const void* q_biases = nullptr;
+  const float* q_fold = nullptr;
+  int q_bits = 0, q_group = 64, q_sdt = Q3TTS_BF16, q_halves = 0;
 };
 
 // true when the tcgen05 path can run this shape (else the caller uses the SIMT kernel)
@@ -70,12 +81,19 @@ void init_tc_gemm();  // resolves cuTensorMapEncodeTiled, sets kernel attributes
 bool tc_skinny_supported(const TcGemm& g);
 void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g);
 void init_tc_skinny();
+bool tc_skinny_q_supported(const TcGemm& g);
+void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g);
+void init_tc_skinny_q();
+unsigned long long* tc_skinny_trace_buf();
 // measurement hook: per-CTA phase stamps (10 x u64 per CTA) of the following launches go to dev_buf (null = off)
 void tc_skinny_set_trace(unsigned long long* dev_buf);
 void tc_skinny_grid(const TcGemm& g, int* tiles, int* split, int* stages);
 
 // shared host helpers (gemm_tc.cu)
 void tc_resolve_encode();
+typedef CUresult (*TcEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TcEncodeFn tc_encode_fn();  // cuTensorMapEncodeTiled resolved through the runtime (after tc_resolve_encode)
 CUtensorMap tc_make_map(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 
 // fp32 -> fp16 helpers used around the tensor-core contractions

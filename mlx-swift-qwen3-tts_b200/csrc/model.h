@@ -58,6 +58,14 @@ struct TcLinear {
   const void* w = nullptr;  // __half [out][in]
   int out = 0, in = 0;
   const float* bias = nullptr;
+  // the packed leaf this copy was made from (bits == 0: dense checkpoint): decode steps of <= 128 rows stream THESE bytes and
+  // dequantise inside the GEMM (gemm_skinny_q.cu); `w` remains the operand of prefill (128-row-tile kernel)
+  const uint32_t* qw = nullptr;
+  const void* qscales = nullptr;
+  const void* qbiases = nullptr;
+  const float* fold = nullptr;   // RMSNorm weight folded into the columns (same as in `w`), or null
+  int qbits = 0, qgroup = 64, qsdt = Q3TTS_BF16;
+  bool halves = false;           // packed rows are [gate ; up]; `w` rows are interleaved (gate_i, up_i)
 };
 
 struct Embedding {

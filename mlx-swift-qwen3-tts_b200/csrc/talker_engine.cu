@@ -356,6 +356,7 @@ TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves, const fl
   const LaunchCtx c{stream_, nullptr};
   TcLinear t;
   t.out = L.out; t.in = L.in; t.bias = L.bias;
+  if (L.bits) { t.qw = L.qw; t.qscales = L.scales; t.qbiases = L.biases; t.qbits = L.bits; t.qgroup = L.group; t.qsdt = L.sdt; t.fold = fold; t.halves = interleave_halves; }
   __half* dst = (__half*)arena_.alloc((size_t)L.out * L.in * 2);
   if (L.bits && fold) {
     float* tmp = nullptr;
@@ -407,6 +408,13 @@ void TalkerEngine::build_tc_weights() {
   w_.has_tc = true;
 }
 
+// decode-step GEMMs read the checkpoint's packed bytes when the leaf is quantised (a9: dequant fused into the GEMM)
+static inline void attach_packed(TcGemm& g, const TcLinear& L) {
+  if (!L.qbits) return;
+  g.q_w = L.qw; g.q_scales = L.qscales; g.q_biases = L.qbiases; g.q_fold = L.fold;
+  g.q_bits = L.qbits; g.q_group = L.qgroup; g.q_sdt = L.qsdt; g.q_halves = L.halves ? 1 : 0;
+}
+
 void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res,
                              int act, int swiglu, bool row_count_invariant) {
   TcGemm g;
@@ -414,6 +422,7 @@ void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* o
   g.a = (const __half*)x16; g.w = (const __half*)L.w; g.Bt = 1; g.T = m; g.cin = L.in; g.N = L.out; g.ntap = 1; g.dil = 1;
   g.bias = L.bias; g.res = res; g.ld_res = ld32; g.act = act; g.swiglu = swiglu;
   g.out32 = out32; g.ld32 = ld32; g.out16 = (__half*)out16; g.ld16 = ld16;
+  if (!row_count_invariant) attach_packed(g, L);
   launch_tc_gemm(ctx(), g);
 }
 
@@ -443,6 +452,7 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       g.rms_eps = S.eps; g.in_scale = inv16; g.allow_skinny = fused; g.k_rotate = fused;
       if (fused) {
         g.rms_in = 1;
+        attach_packed(g, L);
       } else {
         launch_row_scale(c, (const __half*)d_h16_, m, S.hidden, inv16, S.eps, d_rs_);
         g.row_scale = d_rs_;
@@ -455,6 +465,7 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       g.bias = L.bias; g.res = x; g.ld_res = S.hidden; g.out32 = x; g.ld32 = S.hidden; g.allow_skinny = fused; g.k_rotate = fused;
       if (fused) {
         g.out16 = (__half*)d_h16_; g.ld16 = S.hidden; g.out16_scale = inv16;
+        attach_packed(g, L);
         launch_tc_gemm(c, g);
       } else {
         launch_tc_gemm(c, g);
@@ -730,6 +741,7 @@ void TalkerEngine::issue_frame(int n_slots) {
       hg.a = (const __half*)d_h16_; hg.w = (const __half*)w_.lm_head_tc[g].w; hg.Bt = 1; hg.T = n_slots; hg.cin = Hcp; hg.N = Vc;
       hg.bias = w_.lm_head_tc[g].bias; hg.out32 = d_cplogits_; hg.ld32 = Vc;
       hg.rms_in = 1; hg.rms_eps = w_.cp.eps; hg.in_scale = 1.0f / kX16Div;
+      attach_packed(hg, w_.lm_head_tc[g]);
       launch_tc_gemm(c, hg);
     } else if (step_tc_) {
       launch_rmsnorm_f16(c, g == 0 ? x + Hcp : x, g == 0 ? 2 * Hcp : Hcp, n_slots, Hcp, nullptr, w_.cp.eps, (__half*)d_h16_, Hcp);

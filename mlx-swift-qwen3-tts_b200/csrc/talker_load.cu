@@ -211,6 +211,7 @@ struct Loader {
         LaunchCtx lc{stream, nullptr};
         launch_dequantize(lc, qw, sc, bi, sdt, L.out, in, group, bits, Q3TTS_F16, dense);
         L.bits = 0; L.sdt = Q3TTS_F16; L.w = dense;
+        weight_dtype = Q3TTS_F16;  // what the handle computes with after the load (q3tts_info.weight_dtype)
       }
     } else {
       const int sdt = w0.q3_dtype();

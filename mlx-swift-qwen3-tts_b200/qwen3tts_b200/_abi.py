@@ -79,6 +79,7 @@ SYMBOLS = {
     "q3tts_generate_pcm_batch": (i32, [C.c_void_p, C.POINTER(Request), i32, i32, C.POINTER(p_f32), i64, C.POINTER(i64), p_i32]),
     "q3tts_dequantize": (i32, [i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "q3tts_quantized_matmul": (i32, [i32, p_f32, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, p_f32]),
+    "q3tts_quantized_matmul_tc": (i32, [i32, p_f32, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, p_f32, i32, p_f32, p_f32]),
     "q3tts_conv_probe": (i32, [i32, p_f32, i32, i32, i32, p_f32, p_f32, i32, i32, i32, i32, i32, p_f32, p_f32, p_f32, p_f32, i32, i32, p_f32, p_f32]),
     "q3tts_profile_linear": (i32, [C.c_void_p, i32, i32, i32, C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(i64)]),
     "q3tts_skinny_trace": (i32, [i32, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_uint64), i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32),

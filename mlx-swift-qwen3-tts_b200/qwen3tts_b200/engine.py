@@ -350,6 +350,23 @@ def quantized_matmul(x, packed, scales, biases, group_size=64, bits=4, scale_dty
     return y
 
 
+def quantized_matmul_tc(x, packed, scales, biases, group_size=64, bits=4, scale_dtype="bf16", fold=None, swiglu_halves=False, residual=None, device=0):
+    """`q3tts_quantized_matmul_tc` probe: the dequant-fused tcgen05 GEMM of batched decode (m <= 128 rows)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    m, in_f = x.shape
+    w = np.ascontiguousarray(packed, dtype=np.uint32)
+    out_f = w.shape[0]
+    s, b = _raw16(scales, scale_dtype), _raw16(biases, scale_dtype)
+    n_out = out_f // 2 if swiglu_halves else out_f
+    y = np.zeros((m, n_out), dtype=np.float32)
+    f = None if fold is None else np.ascontiguousarray(fold, dtype=np.float32)
+    r = None if residual is None else np.ascontiguousarray(residual, dtype=np.float32)
+    pf = lambda a: None if a is None else a.ctypes.data_as(A.p_f32)
+    A.check(A.lib().q3tts_quantized_matmul_tc(device, x.ctypes.data_as(A.p_f32), m, w.ctypes.data, s.ctypes.data, b.ctypes.data, _DT[scale_dtype], out_f, in_f,
+                                              group_size, bits, pf(f), 1 if swiglu_halves else 0, pf(r), y.ctypes.data_as(A.p_f32)), None)
+    return y
+
+
 def conv_probe(x, w, bias=None, ntap=1, dil=1, act=0, swiglu=False, res=None, scale=None, snake=None, use_tensor_cores=True, device=0):
     """`q3tts_conv_probe`: x [B,T,cin], w [ntap,N,cin] -> (y32, y16) each [B,T,N or N/2] (fp32 numpy)."""
     x = np.ascontiguousarray(x, dtype=np.float32)

@@ -309,16 +309,26 @@ class Qwen3TTSPipeline:
         if not chunks:
             return 0
         writer = StreamingWAVWriter(output_url)
-        for i, tc in enumerate(chunks):
+        # Every text chunk is an independent generation with a fresh KV cache (Qwen3TTSPipeline.swift:668-691), so a handle with
+        # several slots runs `max_batch` chunks at a time through the batched path; a handle's numeric path is fixed at creation,
+        # so the samples of a chunk do not depend on how many chunks shared its steps.  The file is written in chunk order.
+        group = max(1, int(self.info.max_batch))
+        for g0 in range(0, len(chunks), group):
+            part = chunks[g0: g0 + group]
             if on_progress:
-                on_progress(i / len(chunks))
-            req = self._request(tc, speaker=speaker, instruct=instruct, speaker_embedding=speaker_embedding,
-                                reference_transcript=reference_transcript, reference_audio_codes=reference_audio_codes,
-                                temperature=temperature, max_tokens=600)  # :690
-            pcm, frames = self.engine.generate_pcm(req, A.DECODE_FILE)
-            if frames == 0 or pcm.size == 0:
-                continue
-            writer.write(pcm)
+                on_progress(g0 / len(chunks))
+            reqs = [self._request(tc, speaker=speaker, instruct=instruct, speaker_embedding=speaker_embedding,
+                                  reference_transcript=reference_transcript, reference_audio_codes=reference_audio_codes,
+                                  temperature=temperature, max_tokens=600) for tc in part]  # :690
+            if len(reqs) == 1:
+                outs = [self.engine.generate_pcm(reqs[0], A.DECODE_FILE)]
+            else:
+                pcms, frames = self.engine.generate_pcm_batch(reqs, A.DECODE_FILE)
+                outs = list(zip(pcms, frames))
+            for pcm, frames in outs:
+                if frames == 0 or pcm.size == 0:
+                    continue
+                writer.write(pcm)
         if on_progress:
             on_progress(1.0)
         return writer.finalize()

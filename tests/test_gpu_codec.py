@@ -186,3 +186,106 @@ def test_chunked_decode_tensor_core(engines, oracles):
     got = engines(d).decode_chunked(codes, 20, 4)
     want = oracles(d, "codec").chunked_decode(torch.as_tensor(codes).transpose(1, 2).contiguous(), 20, 4).reshape(2, -1).numpy()
     assert snr_db(got, want) >= SNR_DB
+
+
+# ------------------------------------------------------------------------------------------------ long-text drivers (§8 f3)
+LONG_TEXT = ("The quick brown fox jumps over the lazy dog near the quiet river bank. " * 9 + "Then it rests. ") * 2
+
+
+def _oracle_file_pcm(p, oracles, d, text, steps, mode_chunk):
+    """What generateToFile / generateBatch decode per text chunk: greedy codes of the oracle, windows of `mode_chunk` + 8."""
+    from oracle import pipeline as opipe, talker as otalker
+    import qwen3tts_b200 as q
+
+    outs, margins = [], []
+    for tc in q.TextChunker.chunk(text, q.TextChunker.default_max_words):
+        r = p._request(tc, speaker="aiden", temperature=0.0, max_tokens=steps)
+        rec = {}
+        raw = oracles(d).generate_codes(otalker.Request(text_ids=r.text_ids, speaker_id=r.speaker_id, temperature=0.0, max_tokens=steps), record=rec,
+                                        filter_invalid=False)
+        frames = opipe.valid_frames(raw)
+        pcm = np.concatenate([w for w, _ in opipe.decode_windowed(oracles(d, "codec"), frames, mode_chunk, 8)]) if frames else np.zeros(0, np.float32)
+        outs.append((raw, pcm))
+        margins.append(rec["margins"])
+    return outs, margins
+
+
+def test_generate_to_file_bytes_vs_oracle(tiny8, oracles, tmp_path):
+    """generateToFile (Qwen3TTSPipeline.swift:644-757): TextChunker -> per-chunk generateCodes (maxTokens 600; shortened here through
+    the configuration) -> 16 + 8 windows -> StreamingWAVWriter int16 PCM.  Header and sample count exact, int16 payload >= 40 dB
+    against the oracle's; a 4-slot handle (chunks generated side by side) writes the SAME BYTES as a 1-slot handle of the same
+    numeric path would -- compared here against its own sequential run."""
+    import struct
+
+    import qwen3tts_b200 as q
+
+    steps = 40
+    p = q.Qwen3TTSPipeline(tiny8, q.Qwen3TTSPipelineConfiguration(max_batch=4))
+    try:
+        chunks = q.TextChunker.chunk(LONG_TEXT, q.TextChunker.default_max_words)
+        assert len(chunks) >= 3
+        # the driver hard-codes maxTokens 600 (:690); keep the test short by capping frames through the request factory
+        orig = p._request
+        p._request = lambda *a, **kw: orig(*a, **{**kw, "max_tokens": steps, "temperature": 0.0})
+        n = p.generate_to_file(LONG_TEXT, tmp_path / "par.wav", speaker="aiden", temperature=0.0)
+        par = (tmp_path / "par.wav").read_bytes()
+        # the same handle, one chunk at a time
+        seq_pcm = []
+        for tc in chunks:
+            pcm, fr = p.engine.generate_pcm(p._request(tc, speaker="aiden"), q.DECODE_FILE)
+            seq_pcm.append(pcm)
+        w = q.StreamingWAVWriter(tmp_path / "seq.wav")
+        for pcm in seq_pcm:
+            if pcm.size:
+                w.write(pcm)
+        assert w.finalize() == n
+        assert par == (tmp_path / "seq.wav").read_bytes(), "chunk-parallel generation changed the file"
+        # header (AudioSampleWriter.swift:44-106): 44 bytes, PCM16 mono 24 kHz
+        assert par[:4] == b"RIFF" and par[8:16] == b"WAVEfmt " and struct.unpack("<IHHIIHH", par[16:36]) == (16, 1, 1, 24000, 48000, 2, 16)
+        assert struct.unpack("<I", par[40:44])[0] == 2 * n and len(par) == 44 + 2 * n
+        want, margins = _oracle_file_pcm(p, oracles, tiny8, LONG_TEXT, steps, 16)
+        got16 = np.frombuffer(par[44:], dtype="<i2").astype(np.float64)
+        off = 0
+        compared = 0
+        for (raw, pcm), tc in zip(want, chunks):
+            mine = p.engine.generate_codes(q.GenRequest(**{**p._request(tc, speaker="aiden").__dict__, "keep_invalid_frames": True})).tolist()
+            k = pcm.size
+            if mine == raw:  # greedy ids identical: the PCM of this chunk is comparable
+                ref16 = np.trunc(np.clip(pcm, -1, 1) * 32767.0)  # Int16(clamped * 32767) truncation (AudioSampleWriter.swift:93-96)
+                seg = got16[off: off + k]
+                err = np.sum((seg - ref16) ** 2)
+                assert 10 * np.log10(np.sum(ref16 ** 2) / max(err, 1e-9)) >= 40.0
+                compared += 1
+            off += len(opipe_valid(mine)) * 1920
+        assert off == n and compared >= 1
+    finally:
+        p.close()
+
+
+def opipe_valid(frames):
+    from oracle import pipeline as opipe
+
+    return opipe.valid_frames(frames)
+
+
+def test_generate_batch_crossfade_vs_oracle(tiny8, oracles):
+    """generateBatch (Qwen3TTSPipeline.swift:774-898): windows of 24 + 8 per chunk, 480-sample linear crossfade between chunks."""
+    import qwen3tts_b200 as q
+    from oracle import pipeline as opipe
+
+    steps = 30
+    p = q.Qwen3TTSPipeline(tiny8, q.Qwen3TTSPipelineConfiguration())
+    try:
+        orig = p._request
+        p._request = lambda *a, **kw: orig(*a, **{**kw, "max_tokens": steps, "temperature": 0.0})
+        got = p.generate_batch(LONG_TEXT, speaker="aiden", temperature=0.0)
+        want, _ = _oracle_file_pcm(p, oracles, tiny8, LONG_TEXT, steps, 24)
+        chunks = q.TextChunker.chunk(LONG_TEXT, q.TextChunker.default_max_words)
+        same = all(p.engine.generate_codes(q.GenRequest(**{**p._request(tc, speaker="aiden").__dict__, "keep_invalid_frames": True})).tolist() == raw
+                   for tc, (raw, _) in zip(chunks, want))
+        ref = opipe.crossfade_concat([pcm for _, pcm in want], p.config.crossfade_samples)
+        if not same:
+            pytest.skip("greedy ids diverged at a near-tie in one chunk; covered by test_generate_codes_greedy")
+        assert got.shape == ref.shape and snr_db(got, ref) >= SNR_DB
+    finally:
+        p.close()

@@ -180,3 +180,54 @@ def test_simt_conv_matches_numpy():
             z[:, sh:] = xs[:, : 37 - sh]
             want += z @ ws[tap].T
     assert np.abs(y32 - (want + bias)).max() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ dequant-fused GEMM (a9)
+@pytest.mark.parametrize("bits,sdt,group", [(4, "bf16", 64), (8, "bf16", 64), (4, "f16", 32), (8, "f32", 128), (4, "f32", 128), (8, "f16", 32)])
+@pytest.mark.parametrize("shape", [(1, 1024, 1024), (3, 4096, 1024), (24, 1024, 2048), (64, 1024, 3072), (64, 3072, 1024), (100, 2048, 1024), (128, 256, 512),
+                                   (7, 128, 256), (33, 2048, 6144), (5, 160, 256)])
+def test_dequant_fused_tensor_core_gemm(bits, sdt, group, shape):
+    """MLX-packed weights streamed and dequantised INSIDE the tcgen05 GEMM (csrc/gemm_skinny_q.cu) == fp16(x) . fp16(dequant(W))^T:
+    the operand bits are those of q3tts_dequantize(out_dtype=f16), accumulation is fp32."""
+    import qwen3tts_b200 as q
+    from oracle import mlx_quant
+
+    m, out_f, in_f = shape
+    rng = np.random.default_rng(m * 7 + out_f + bits + group)
+    w = (rng.standard_normal((out_f, in_f)) * 0.02).astype(np.float32)
+    w[5] = 0.0
+    x = rng.standard_normal((m, in_f)).astype(np.float32)
+    packed, s, b = mlx_quant.quantize(w, group, bits, sdt)
+    wd = mlx_quant.dequantize(packed, s, b, group, bits, "f16").astype(np.float64)
+    x16 = x.astype(np.float16).astype(np.float64)
+    got = q.quantized_matmul_tc(x, packed, s, b, group, bits, sdt)
+    want = x16 @ wd.T
+    bound = 4e-6 * (np.abs(x16) @ np.abs(wd).T) + 1e-6  # fp32 accumulation of exact fp16 x fp16 products
+    assert got.shape == want.shape
+    assert np.all(np.abs(got - want) <= bound), f"max err {np.abs(got - want).max():.3e} (bound {bound.max():.3e})"
+
+
+@pytest.mark.parametrize("bits", [4, 8])
+def test_dequant_fused_gemm_fold_swiglu_residual(bits):
+    """The three fused features the decode step uses: RMSNorm weight folded into the dequantised columns (one fp16 rounding of
+    deq32 * fold), SwiGLU over a [gate ; up] packed matrix, residual add."""
+    import qwen3tts_b200 as q
+    from oracle import mlx_quant
+
+    rng = np.random.default_rng(bits)
+    m, inter, in_f = 48, 1536, 1024
+    w = (rng.standard_normal((2 * inter, in_f)) * 0.03).astype(np.float32)
+    fold = rng.uniform(0.8, 1.2, in_f).astype(np.float32)
+    x = rng.standard_normal((m, in_f)).astype(np.float32)
+    packed, s, b = mlx_quant.quantize(w, 64, bits, "bf16")
+    wd = (mlx_quant.dequantize(packed, s, b, 64, bits, "f32") * fold[None, :]).astype(np.float32).astype(np.float16).astype(np.float64)
+    x16 = x.astype(np.float16).astype(np.float64)
+    z = x16 @ wd.T
+    gate, up = z[:, :inter], z[:, inter:]
+    want = gate / (1 + np.exp(-gate)) * up
+    got = q.quantized_matmul_tc(x, packed, s, b, 64, bits, "bf16", fold=fold, swiglu_halves=True)
+    assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max())
+    # plain rows + residual
+    res = rng.standard_normal((m, 2 * inter)).astype(np.float32)
+    got2 = q.quantized_matmul_tc(x, packed, s, b, 64, bits, "bf16", fold=fold, residual=res)
+    assert np.abs(got2 - (z + res)).max() <= 2e-5 * max(1.0, np.abs(z).max())
