@@ -74,7 +74,7 @@ class TalkerEngine {
   // one_row_per_slot: decode steps may fuse norm+RoPE+append into the attention launch (prefill / CP pass 0 may not);
   // decode_step: rows <= 128 may take the split-K cluster GEMM (prefill stays on the 128-row-tile kernel: batch invariance)
   void forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos, const int* win_start,
-                     const float* inv_freq, float* kbase, float* vbase, size_t slot_stride, size_t layer_stride, int capacity,
+                     const float* inv_freq, void* kbase, void* vbase, int kv_f16, size_t slot_stride, size_t layer_stride, int capacity,
                      bool one_row_per_slot, bool decode_step, bool x16_ready);
   void issue_frame(int n_slots);
   void build_tc_weights();
@@ -89,7 +89,7 @@ class TalkerEngine {
   bool use_mega(int n_slots) const { return mega_.ok && !handle_tc_ && opt_.max_batch <= mega_.max_slots && n_slots <= mega_.max_slots; }
   // y = epilogue(x16 . W^T): one tcgen05 GEMM launch over m rows
   void linear_tc(const TcLinear& L, const void* x16, int m, float* out32, int ld32, void* out16, int ld16, const float* res, int act, int swiglu, bool row_count_invariant = false);
-  LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
+  LaunchCtx ctx() { return LaunchCtx{stream_, counter_, chain_on_ ? &chain_ : nullptr}; }
 
   TalkerConfig cfg_;
   EngineOptions opt_;
@@ -106,11 +106,19 @@ class TalkerEngine {
   int tc_min_rows_ = 16, tc_min_rows_step_ = 3;
   bool step_tc_ = false;  // set by issue_frame for the launches of the current frame step
   bool handle_tc_ = false;  // decode steps of this handle run on tensor cores (see use_tc_step)
+  // chain signals (common.h): counters of one frame graph + the link state while issue_frame records its launches
+  static constexpr int kChainCounters = 1024;
+  ChainState chain_;
+  bool chain_on_ = false, chain_enabled_ = true;
   float* d_rs_ = nullptr;                     // [max_rows] RMSNorm row factors for the 128-row-tile kernel (prefill)
   static constexpr float kX16Div = 16.0f;     // the fp16 copy of the residual stream is x / 16 (range headroom; exact power of two)
   void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;
   // device buffers
-  float *kcache_ = nullptr, *vcache_ = nullptr, *cp_k_ = nullptr, *cp_v_ = nullptr;
+  // talker KV rings: fp16 on handles whose decode steps run on tensor cores (half the bytes of every window walk; K / V rounded once
+  // at append, like every other fp16 operand of that path), fp32 on the <= 2-slot handles of the persistent frame kernel
+  void *kcache_ = nullptr, *vcache_ = nullptr;
+  int kv_f16_ = 0;
+  float *cp_k_ = nullptr, *cp_v_ = nullptr;
   size_t kv_slot_stride_ = 0, kv_layer_stride_ = 0, cpkv_slot_stride_ = 0, cpkv_layer_stride_ = 0;
   static constexpr int kCpCapacity = 32;
   SlotState* d_state_ = nullptr;

@@ -91,7 +91,7 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
         mbar_expect_tx(&full[i], (uint32_t)(kWBytes + x_bytes));
         tma_load_2d(sW + (size_t)i * kWBytes, &tmW, &full[i], (kb0 + i) * kBlockK, n0);
       }
-      pdl_wait();
+      sk_wait_dependency_tma(p);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % p.stages, ph = (i / p.stages) & 1;
         if (i >= pre) {
@@ -123,7 +123,7 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
     __syncwarp();
   } else {
     // ---------------- epilogue warps: warp w may touch TMEM lanes [32*(w%4), +32); thread = one weight row
-    pdl_wait();  // residual rows were written by earlier kernels
+    sk_wait_dependency_warp(p);  // residual rows were written by earlier kernels
     if (p.rms_x) sk_row_factors(p, rowscale_s, rank);  // while the operands stream in
     if (p.split > 1) cluster_wait_acquire();  // A: every peer CTA is resident, its mbarriers initialised (long complete by now)
     mbar_wait(tmem_full, 0);
@@ -236,6 +236,7 @@ void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g) {
   p.rms_a = 1.0f / (g.in_scale * g.in_scale * (float)g.cin); p.rms_eps = g.rms_eps; p.rms_mult = 1.0f / g.in_scale;
   Q3_CHECK(!g.row_scale, Q3TTS_ERR_INVALID_ARG, "tc_skinny: pass rms_in instead of precomputed row factors");
   p.trace = g_sk_trace;
+  p.sig = c.chain_link((unsigned)(s.tiles * s.split));
 
   const uint64_t wdims[2] = {(uint64_t)g.cin, (uint64_t)g.N};
   const uint64_t wstr[1] = {(uint64_t)g.cin * 2};
@@ -267,7 +268,7 @@ void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g) {
   cfg.attrs = attr;
   cfg.numAttrs = na;
   Q3_CUDA(cudaLaunchKernelEx(&cfg, pick_kernel(g.act, g.swiglu), mw, mx, p));
-  c.tick();
+  c.tick_chained();
 }
 
 }  // namespace q3

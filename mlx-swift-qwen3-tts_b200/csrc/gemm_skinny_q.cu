@@ -59,11 +59,11 @@ __device__ __forceinline__ uint4 lds_u4(uint32_t saddr) {
   return v;
 }
 
-// 8 consecutive k of one weight row -> one 16-byte chunk of fp16.  q[8] are the integer codes as floats.
+// 8 consecutive k of one weight row -> four packed fp16 pairs (one 16-byte chunk of the row).  q[8] are the integer codes as floats.
 // MLX `dequantized` rounds the product and the sum separately (q3tts_dequantize contract).  With 16-bit scales the product s * q has
 // <= 19 significant bits, i.e. it is exact, and one FMA gives the same bits; fp32 scales (24 + 8 bits) need the two roundings.
 template <bool F32S>
-__device__ __forceinline__ void store_chunk(uint32_t arow, int j, int rsw, const float (&q)[8], float sc, float bi, const float* fold8) {
+__device__ __forceinline__ void pack_chunk(uint32_t* out4, const float (&q)[8], float sc, float bi, const float* fold8) {
   float v[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) v[e] = F32S ? __fadd_rn(__fmul_rn(sc, q[e]), bi) : fmaf(sc, q[e], bi);
@@ -72,15 +72,14 @@ __device__ __forceinline__ void store_chunk(uint32_t arow, int j, int rsw, const
     v[0] *= f0.x; v[1] *= f0.y; v[2] *= f0.z; v[3] *= f0.w;
     v[4] *= f1.x; v[5] *= f1.y; v[6] *= f1.z; v[7] *= f1.w;
   }
-  sts_v4(arow + (uint32_t)((j ^ rsw) << 4), pack_f16x2(v[0], v[1]), pack_f16x2(v[2], v[3]), pack_f16x2(v[4], v[5]), pack_f16x2(v[6], v[7]));
+  out4[0] = pack_f16x2(v[0], v[1]); out4[1] = pack_f16x2(v[2], v[3]); out4[2] = pack_f16x2(v[4], v[5]); out4[3] = pack_f16x2(v[6], v[7]);
 }
 
-// One weight row of one k-block (64 k): packed bytes in shared memory -> 128 bytes of the swizzled A tile.
+// One weight row of one k-block (64 k): packed bytes in shared memory -> 64 fp16 values in registers (out[4j .. 4j+3] = chunk j).
 //   prow_s : shared address of the row's packed bytes (32 B at 4 bits, 64 B at 8 bits)
-//   arow   : shared address of row `row` of the A tile (row * 128 from a 1024-byte aligned tile base); rsw = row & 7
 //   sc/bi  : scale and bias of the (up to two) groups the k-block touches: index 0 = k in [0, 32), 1 = k in [32, 64)
 template <int BITS, bool F32S>
-__device__ __forceinline__ void dequant_row(uint32_t prow_s, uint32_t arow, int rsw, const float (&sc)[2], const float (&bi)[2], const float* fold64) {
+__device__ __forceinline__ void dequant_row(uint32_t prow_s, const float (&sc)[2], const float (&bi)[2], const float* fold64, uint32_t (&out)[32]) {
   if constexpr (BITS == 4) {
     const uint4 w0 = lds_u4(prow_s), w1 = lds_u4(prow_s + 16);
     const uint32_t w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -95,7 +94,7 @@ __device__ __forceinline__ void dequant_row(uint32_t prow_s, uint32_t arow, int 
         q[n] = f.x;
         q[n + 4] = f.y;
       }
-      store_chunk<F32S>(arow, j, rsw, q, sc[j >> 2], bi[j >> 2], fold64 ? fold64 + 8 * j : nullptr);
+      pack_chunk<F32S>(out + 4 * j, q, sc[j >> 2], bi[j >> 2], fold64 ? fold64 + 8 * j : nullptr);
     }
   } else {
 #pragma unroll
@@ -109,10 +108,16 @@ __device__ __forceinline__ void dequant_row(uint32_t prow_s, uint32_t arow, int 
         for (int e = 0; e < 8; ++e)  // byte -> mantissa of 2^23 in one PRMT, exact subtraction
           q[e] = __uint_as_float(__byte_perm(w[2 * jj + (e >> 2)], 0x4B000000u, 0x7440u + (uint32_t)(e & 3))) - 8388608.0f;
         const int j = half * 4 + jj;
-        store_chunk<F32S>(arow, j, rsw, q, sc[half], bi[half], fold64 ? fold64 + 8 * j : nullptr);
+        pack_chunk<F32S>(out + 4 * j, q, sc[half], bi[half], fold64 ? fold64 + 8 * j : nullptr);
       }
     }
   }
+}
+
+// 64 fp16 values of tile row `row` -> the 128-byte-swizzled K-major A tile: 16-byte chunk j at chunk position j ^ (row & 7)
+__device__ __forceinline__ void store_row_swizzled(uint32_t arow, int rsw, const uint32_t (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sts_v4(arow + (uint32_t)((j ^ rsw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
 template <int BITS, bool SWIGLU>
@@ -187,7 +192,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
           tma_load_2d(dst, &tmP, &pfull[i], (kb0 + i) * wpk, n0);
         }
       }
-      pdl_wait();
+      sk_wait_dependency_tma(p);
       for (int i = 0; i < nkb; ++i) {
         const int s = i % AS;
         if (i >= AS) mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read X[s]
@@ -251,24 +256,42 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     }
     const uint32_t arow0 = smem_u32(sA) + (uint32_t)row * 128u;
     const uint32_t prow0 = smem_u32(sP) + (uint32_t)prow * (uint32_t)kPRow;
+    // Every k-block is dequantised NOW, ahead of the dependency on the predecessor kernel: the first AS blocks straight into the A
+    // ring, the rest PARKED in spare TMEM columns (thread = TMEM lane, 32 columns of packed fp16 pairs per block; written and read
+    // back by the same thread with tcgen05.st / tcgen05.ld, so no operand layout is involved).  Once the MMAs release an A stage,
+    // re-staging a parked block is one TMEM load + eight shared-memory stores instead of a dequantisation on the critical path.
+    const uint32_t park0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.m_pad;
     for (int i = 0; i < nkb; ++i) {
-      const int s = i % AS;
       float scn[2], bin[2];
       if (i + 1 < nkb) load_sb(kb0 + i + 1, scn, bin);  // next k-block's scale / bias: in flight behind this block's work
       mbar_wait(&pfull[i], 0);
-      if (i >= AS) mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read A[s]
-      if (p.q_sdt == Q3TTS_F32)
-        dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPBytes, arow0 + (uint32_t)s * (uint32_t)kWBytes, row & 7, sc, bi,
-                                p.q_fold ? fold_s + i * kBlockK : nullptr);
-      else
-        dequant_row<BITS, false>(prow0 + (uint32_t)i * (uint32_t)kPBytes, arow0 + (uint32_t)s * (uint32_t)kWBytes, row & 7, sc, bi,
-                                 p.q_fold ? fold_s + i * kBlockK : nullptr);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&afull[s]);
+      uint32_t v[32];
+      const float* fold = p.q_fold ? fold_s + i * kBlockK : nullptr;
+      if (p.q_sdt == Q3TTS_F32) dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPBytes, sc, bi, fold, v);
+      else dequant_row<BITS, false>(prow0 + (uint32_t)i * (uint32_t)kPBytes, sc, bi, fold, v);
+      if (i < AS) {
+        store_row_swizzled(arow0 + (uint32_t)i * (uint32_t)kWBytes, row & 7, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[i]);
+      } else {
+        tmem_st32(park0 + (uint32_t)(i - AS) * 32u, v);
+      }
       if (i + 1 < nkb) { sc[0] = scn[0]; sc[1] = scn[1]; bi[0] = bin[0]; bi[1] = bin[1]; }
     }
-    pdl_wait();  // residual rows and the activation rows were written by earlier kernels
+    if (nkb > AS) tmem_st_wait();
+    for (int i = AS; i < nkb; ++i) {
+      const int s = i % AS;
+      uint32_t v[32];
+      tmem_ld32_issue(park0 + (uint32_t)(i - AS) * 32u, v);
+      mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read A[s]
+      tmem_ld_wait32(v);
+      store_row_swizzled(arow0 + (uint32_t)s * (uint32_t)kWBytes, row & 7, v);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&afull[s]);
+    }
+    sk_wait_dependency_warp(p);  // residual rows and the activation rows were written by earlier kernels
     if (p.rms_x) sk_row_factors(p, rowscale_s, rank);
     if (p.split > 1) cluster_wait_acquire();  // A: every peer CTA is resident, its mbarriers initialised
     mbar_wait(tmem_full, 0);
@@ -296,7 +319,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct SkqPlan {
-  int m_pad, split, tiles, num_kb, nkb_max, a_stages;
+  int m_pad, split, tiles, num_kb, nkb_max, a_stages, tmem_cols;
   size_t smem;
   bool ok;
 };
@@ -318,7 +341,11 @@ SkqPlan plan(const TcGemm& g) {
   while (s.a_stages * (kWBytes + x_bytes) < red_bytes) ++s.a_stages;  // the rings double as the outgoing staging buffer
   s.smem = (size_t)s.a_stages * (kWBytes + x_bytes) + (size_t)s.nkb_max * p_bytes + red_bytes + 1024 + (size_t)(3 * s.a_stages + s.nkb_max + 3) * 8 + 16 +
            kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
-  s.ok = s.smem <= 220 * 1024;
+  // TMEM: the fp32 accumulator [128 lanes x m_pad columns] + 32 columns per k-block parked beyond the A ring
+  int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);
+  s.tmem_cols = 32;
+  while (s.tmem_cols < cols) s.tmem_cols <<= 1;
+  s.ok = s.smem <= 220 * 1024 && s.tmem_cols <= 512;
   return s;
 }
 
@@ -375,13 +402,14 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   p.m_pad = s.m_pad; p.split = s.split; p.mc = s.m_pad / s.split; p.stages = s.a_stages; p.num_kb = s.num_kb;
   p.mc_shift = 0;
   while ((1 << p.mc_shift) < p.mc) ++p.mc_shift;
-  p.tmem_cols = std::max(32, s.m_pad);
+  p.tmem_cols = s.tmem_cols;
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;
   p.out16_scale = g.out16_scale;
   p.rms_x = g.rms_in ? g.a : nullptr;
   p.rms_a = 1.0f / (g.in_scale * g.in_scale * (float)g.cin); p.rms_eps = g.rms_eps; p.rms_mult = 1.0f / g.in_scale;
   p.trace = tc_skinny_trace_buf();
+  p.sig = c.chain_link((unsigned)(s.tiles * s.split));
   p.q_scales = g.q_scales; p.q_biases = g.q_biases; p.q_fold = g.q_fold; p.q_group = g.q_group; p.q_sdt = g.q_sdt;
   p.q_pstages = s.nkb_max;
   p.q_half_rows = g.q_halves ? g.N / 2 : 0;
@@ -413,7 +441,7 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   cfg.attrs = attr;
   cfg.numAttrs = na;
   Q3_CUDA(cudaLaunchKernelEx(&cfg, pick_kernel(g.q_bits, g.swiglu), mp, mx, p));
-  c.tick();
+  c.tick_chained();
 }
 
 }  // namespace q3

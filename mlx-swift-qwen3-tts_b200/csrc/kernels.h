@@ -9,7 +9,19 @@ namespace q3 {
 struct LaunchCtx {
   cudaStream_t stream = nullptr;
   LaunchCounter* counter = nullptr;
-  inline void tick() const { if (counter) counter->tick(); }
+  ChainState* chain = nullptr;   // non-null while a decode step is being issued with chain signals (common.h)
+  // a launch that does not signal breaks the chain: its successor falls back to griddepcontrol.wait / stream order
+  inline void tick() const { if (counter) counter->tick(); if (chain) chain->prev = nullptr; }
+  // chained launchers: call chain_link BEFORE the launch (grid size in CTAs), tick_chained after it
+  inline ChainSig chain_link(unsigned ctas) const {
+    ChainSig s;
+    if (!chain || chain->next >= chain->capacity) { if (chain) chain->prev = nullptr; return s; }
+    s.in = chain->prev; s.in_target = chain->prev_ctas;
+    s.out = chain->base + chain->next++;
+    chain->prev = s.out; chain->prev_ctas = ctas;
+    return s;
+  }
+  inline void tick_chained() const { if (counter) counter->tick(); }
 };
 
 enum Epilogue { EPI_STORE = 0, EPI_ADD = 1, EPI_SILU = 2, EPI_SWIGLU = 3 };
@@ -30,10 +42,11 @@ void launch_rmsnorm(const LaunchCtx& c, const float* x, int ldx, int m, int dim,
 // Per (row, head): q/k per-head RMSNorm (:174-175), rotate-half RoPE at the row's absolute position (:187-195),
 // q written back in place, k and v appended to the KV ring of the row's slot (:197-201).
 struct KVLayout {
-  float* k = nullptr;      // base of this layer's K cache for slot 0: [kv_heads][capacity][head_dim]
-  float* v = nullptr;
-  size_t slot_stride = 0;  // floats between consecutive slots
+  void* k = nullptr;       // base of this layer's K cache for slot 0: [kv_heads][capacity][head_dim] of float, or of __half when f16
+  void* v = nullptr;
+  size_t slot_stride = 0;  // ELEMENTS between consecutive slots
   int capacity = 0;        // ring size in positions
+  int f16 = 0;             // element type: 0 fp32 (handles of <= 2 slots, code predictor), 1 fp16 (talker KV of batched handles)
 };
 void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                                 const float* q_norm, const float* k_norm, float eps, const float* inv_freq,

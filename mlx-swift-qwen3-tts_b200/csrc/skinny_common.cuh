@@ -32,6 +32,7 @@ struct SkParams {
   const __half* rms_x;      // folded RMSNorm: fp16 activation rows [M][K] (= the B operand), or null
   float rms_a, rms_eps, rms_mult;  // row factor = rms_mult * rsqrt(sum(x16^2) * rms_a + rms_eps)
   unsigned long long* trace;  // measurement hook (q3tts_skinny_trace): 16 stamps per CTA, or null
+  ChainSig sig;               // chain signals (common.h): flag hand-off from / to the neighbouring launches of a decode step
   // ---- packed-weight kernel only (gemm_skinny_q.cu)
   const void* q_scales;     // [N][K / q_group] of q_sdt
   const void* q_biases;
@@ -192,9 +193,31 @@ __device__ __forceinline__ void sk_reduce_epilogue(const SkParams& p, float* sta
     if (threadIdx.x == 96 && cb == 0) SK_STAMP(12);
   }
   if (threadIdx.x == 96) SK_STAMP(13);
+  if (p.sig.out) {  // every global store (and every global read) of this CTA is done: hand over to the next launch
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) chain_signal(p.sig.out);
+  }
   if (threadIdx.x == 64 && p.split > 1) {
     SK_STAMP(7);
     mbar_wait(ack, 0);  // every peer has received my partial sums: my staging buffer is no longer being read
+  }
+}
+
+// the dependency on the predecessor launch: its chain signal when there is one, else programmatic-dependent-launch completion
+__device__ __forceinline__ void sk_wait_dependency_warp(const SkParams& p) {  // a whole warp
+  if (p.sig.in) {
+    if ((threadIdx.x & 31) == 0) chain_wait(p.sig.in, p.sig.in_target);
+    __syncwarp();
+  } else {
+    pdl_wait();
+  }
+}
+__device__ __forceinline__ void sk_wait_dependency_tma(const SkParams& p) {  // the single TMA-issuing thread
+  if (p.sig.in) {
+    chain_wait(p.sig.in, p.sig.in_target);
+    asm volatile("fence.proxy.async;" ::: "memory");  // the tensor loads that follow (async proxy) are ordered after the acquire
+  } else {
+    pdl_wait();
   }
 }
 

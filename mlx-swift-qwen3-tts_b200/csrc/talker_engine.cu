@@ -29,8 +29,16 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
 
   kv_layer_stride_ = (size_t)T.kv_heads * C * 128;
   kv_slot_stride_ = kv_layer_stride_ * T.layers;
-  kcache_ = arena_.alloc_n<float>(kv_slot_stride_ * B);
-  vcache_ = arena_.alloc_n<float>(kv_slot_stride_ * B);
+  // decided here (before the tensor-core copies exist) from the same inputs handle_tc_ is decided from below
+  {
+    int min_rows = 3;
+    if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) min_rows = atoi(e);
+    const char* e16 = getenv("Q3TTS_KV_F16");
+    kv_f16_ = (min_rows > 0 && B >= min_rows && !(e16 && atoi(e16) == 0)) ? 1 : 0;
+  }
+  const size_t kv_elem = kv_f16_ ? 2 : 4;
+  kcache_ = arena_.alloc(kv_slot_stride_ * B * kv_elem);
+  vcache_ = arena_.alloc(kv_slot_stride_ * B * kv_elem);
   cpkv_layer_stride_ = (size_t)P.kv_heads * kCpCapacity * 128;
   cpkv_slot_stride_ = cpkv_layer_stride_ * P.layers;
   cp_k_ = arena_.alloc_n<float>(cpkv_slot_stride_ * B);
@@ -85,6 +93,12 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
     d_tph16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
   }
   handle_tc_ = w_.has_tc && tc_min_rows_step_ > 0 && B >= tc_min_rows_step_;
+  Q3_CHECK(!kv_f16_ || handle_tc_ || !w_.has_tc, Q3TTS_ERR_BAD_CONFIG, "internal: fp16 KV rings on a handle without the tensor-core step");
+  chain_.base = arena_.alloc_n<unsigned>(kChainCounters);
+  chain_.capacity = kChainCounters;
+  Q3_CUDA(cudaMemsetAsync(chain_.base, 0, sizeof(unsigned) * kChainCounters, stream_));
+  if (const char* e = getenv("Q3TTS_CHAIN")) chain_enabled_ = atoi(e) != 0;
+  if (!pdl_enabled()) chain_enabled_ = false;  // a consumer may only spin on its producer when it was launched as its programmatic dependent
   d_probe_logits_ = arena_.alloc_n<float>(4096);
   d_probe_set_ = arena_.alloc_n<unsigned>(128);
   d_probe_out_ = arena_.alloc_n<int>(1);
@@ -299,7 +313,8 @@ void TalkerEngine::build_mega_plan() {
   const int nsplit_tk = 4;  // key splits of a talker attention item (each <= 128 keys: kv_capacity <= 512)
   p.lin = d_lin; p.n_lin = (int)lin.size();
   p.cp = stack_of(P, d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, 1);
-  p.tk = stack_of(T, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, opt_.kv_capacity, nsplit_tk);
+  if (kv_f16_) return;  // the persistent frame kernel reads fp32 rings (it only ever runs on handles of <= 2 slots, which keep them)
+  p.tk = stack_of(T, d_inv_freq_, (float*)kcache_, (float*)vcache_, kv_slot_stride_, kv_layer_stride_, opt_.kv_capacity, nsplit_tk);
   p.has_mtp = w_.has_mtp ? 1 : 0; p.H = cfg_.hidden_size; p.Hcp = cfg_.cp.hidden_size; p.V = cfg_.vocab_size; p.Vc = cfg_.cp.vocab_size;
   p.codec = w_.codec_embedding; p.cp_emb = d_cp_emb_;
   p.st = d_state_; p.cur_codes = d_cur_codes_; p.frames = d_frames_; p.forced = d_forced_; p.max_frames = opt_.max_frames;
@@ -428,8 +443,9 @@ void TalkerEngine::linear_tc(const TcLinear& L, const void* x16, int m, float* o
 
 // Qwen3DecoderLayer x layers (Model/Qwen3Layers.swift:242-262; Qwen3CodePredictor.swift:118-138): 6 launches per layer.
 void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const int* row_slot, const int* row_pos,
-                                 const int* win_start, const float* inv_freq, float* kbase, float* vbase, size_t slot_stride,
+                                 const int* win_start, const float* inv_freq, void* kbase, void* vbase, int kv_f16, size_t slot_stride,
                                  size_t layer_stride, int capacity, bool one_row_per_slot, bool decode_step, bool x16_ready) {
+  const size_t kv_elem = kv_f16 ? 2 : 4;
   const LaunchCtx c = ctx();
   const int qkv_ld = (S.heads + 2 * S.kv_heads) * 128, attn_ld = S.heads * 128;
   if ((decode_step ? step_tc_ : use_tc(m)) && !S.tc.empty()) {
@@ -477,7 +493,8 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
       const LayerWeights& L = S.layer[l];
       const LayerTc& Tc = S.tc[l];
       KVLayout kv;
-      kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
+      kv.k = static_cast<char*>(kbase) + l * layer_stride * kv_elem; kv.v = static_cast<char*>(vbase) + l * layer_stride * kv_elem;
+      kv.slot_stride = slot_stride; kv.capacity = capacity; kv.f16 = kv_f16;
       consumer(Tc.qkv, d_qkv_, qkv_ld, nullptr, 0, 0);
       static const int dbg_skip = getenv("Q3TTS_DEBUG_SKIP") ? atoi(getenv("Q3TTS_DEBUG_SKIP")) : 0;  // timing attribution only
       if (one_row_per_slot && (dbg_skip & 1)) {
@@ -500,7 +517,8 @@ void TalkerEngine::forward_stack(const StackWeights& S, float* x, int m, const i
   for (int l = 0; l < S.layers; ++l) {
     const LayerWeights& L = S.layer[l];
     KVLayout kv;
-    kv.k = kbase + l * layer_stride; kv.v = vbase + l * layer_stride; kv.slot_stride = slot_stride; kv.capacity = capacity;
+    kv.k = static_cast<char*>(kbase) + l * layer_stride * kv_elem; kv.v = static_cast<char*>(vbase) + l * layer_stride * kv_elem;
+    kv.slot_stride = slot_stride; kv.capacity = capacity; kv.f16 = kv_f16;
     launch_linear(c, L.qkv, x, S.hidden, m, d_qkv_, qkv_ld, L.in_norm, S.eps, EPI_STORE);
     if (one_row_per_slot) {
       launch_rope_attention(c, d_qkv_, qkv_ld, m, S.heads, S.kv_heads, L.q_norm, L.k_norm, S.eps, inv_freq, row_slot, row_pos, win_start, kv,
@@ -636,7 +654,7 @@ void TalkerEngine::admit_batch(const std::vector<AdmitItem>& items, std::vector<
     Q3_CUDA(cudaMemcpyAsync(tr + (size_t)p.n_trailing * H, d_tp_ + (size_t)TP_EOS * H, sizeof(float) * H, cudaMemcpyDeviceToDevice, stream_));
   }
   // prefill: every row at its own (slot, position) (Model/Qwen3Talker.swift:437)
-  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_, kv_layer_stride_, C, false, false, false);
+  forward_stack(w_.talker, d_x_, R, d_pf_slot_, d_pf_pos_, d_pf_win_, d_inv_freq_, kcache_, vcache_, kv_f16_, kv_slot_stride_, kv_layer_stride_, C, false, false, false);
   // final norm + codec_head on the last position only (the reference computes all, :449, and samples the last, :284-286)
   for (const Plan& p : plans) {
     launch_rmsnorm(c, d_x_ + (size_t)(p.row0 + p.P - 1) * H, H, 1, H, w_.talker.final_norm, w_.talker.eps, d_hlast_ + (size_t)p.slot * H, H);
@@ -702,8 +720,20 @@ void TalkerEngine::release(int slot) {
 
 // One 12.5 Hz frame for slots [0, n_slots): the loop body of Model/Qwen3Talker.swift:464-562 with every decision on device.
 void TalkerEngine::issue_frame(int n_slots) {
-  const LaunchCtx c = ctx();
   step_tc_ = use_tc_step(n_slots);  // one decision per frame step (by utterances, not by the rows of each launch)
+  // chain signals between the consecutive tensor-core launches of this frame (GEMM -> attention -> GEMM ...): only inside a
+  // captured graph, where consecutive kernel nodes are programmatic dependents of each other
+  struct ChainScope {
+    bool& on;
+    explicit ChainScope(bool& f, bool v) : on(f) { on = v; }
+    ~ChainScope() { on = false; }
+  } chain_scope(chain_on_, step_tc_ && chain_enabled_ && opt_.use_cuda_graph != 0);
+  if (chain_on_) {
+    chain_.next = 0;
+    chain_.prev = nullptr;
+    Q3_CUDA(cudaMemsetAsync(chain_.base, 0, sizeof(unsigned) * kChainCounters, stream_));
+  }
+  const LaunchCtx c = ctx();
   const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size, V = cfg_.vocab_size, Vc = cfg_.cp.vocab_size;
   const int B = opt_.max_batch, F = opt_.max_frames;
   SamplerParams p{};
@@ -733,7 +763,7 @@ void TalkerEngine::issue_frame(int n_slots) {
       x = d_cpx_;
     }
     forward_stack(w_.cp, x, m, g == 0 ? d_cp_slot2_ : d_iota_, g == 0 ? d_cp_pos2_ : d_cp_pos_ + (size_t)g * B, nullptr,
-                  d_cp_inv_freq_, cp_k_, cp_v_, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true, x16_direct);
+                  d_cp_inv_freq_, cp_k_, cp_v_, 0, cpkv_slot_stride_, cpkv_layer_stride_, kCpCapacity, g != 0, true, x16_direct);
     // norm + lm_head[g] on the last position of each slot (Qwen3CodePredictor.swift:207-212)
     if (step_tc_ && g != 0 && n_slots <= 128 && tc_skinny_enabled()) {
       // the last layer's down GEMM left fp16(x / 16) in d_h16_: lm_head (final norm folded in) takes it as is
@@ -759,7 +789,7 @@ void TalkerEngine::issue_frame(int n_slots) {
   launch_frame_finalize(c, n_slots, d_state_, d_cur_codes_, d_frames_, F, d_sets_, set_words_, d_trailing_, opt_.max_trailing,
                         d_tts_ + (size_t)2 * H, w_.codec_embedding, d_cp_emb_, H, d_xstep_, step_tc_ ? (__half*)d_h16_ : nullptr, 1.0f / kX16Div);
   launch_step_rows(c, n_slots, d_state_, d_step_slot_, d_step_pos_, d_win_);
-  forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_slot_stride_,
+  forward_stack(w_.talker, d_xstep_, n_slots, d_step_slot_, d_step_pos_, d_win_, d_inv_freq_, kcache_, vcache_, kv_f16_, kv_slot_stride_,
                 kv_layer_stride_, opt_.kv_capacity, true, true, step_tc_);
   launch_rmsnorm(c, d_xstep_, H, n_slots, H, w_.talker.final_norm, w_.talker.eps, d_hlast_, H);
   if (step_tc_) {
@@ -886,11 +916,22 @@ double TalkerEngine::profile_linears(int which, int m, int iters, int64_t& launc
     if (count) { launches += 1; bytes_per_iter += (int64_t)head.weight_bytes(); }
   };
   pass(true);  // warm-up (and the per-iteration accounting)
+  // the captured pass hands over between its GEMMs exactly like a frame step does (chain signals)
+  struct ChainScope {
+    bool& on;
+    explicit ChainScope(bool& f, bool v) : on(f) { on = v; }
+    ~ChainScope() { on = false; }
+  } chain_scope(chain_on_, tc && chain_enabled_);
   // One pass as a CUDA graph, replayed `iters` times: the same submission path as the frame step (stream launches would add a
   // host-side tensor-map encode + launch per kernel and measure the CPU instead of the kernels).
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   Q3_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+  if (chain_on_) {
+    chain_.next = 0;
+    chain_.prev = nullptr;
+    Q3_CUDA(cudaMemsetAsync(chain_.base, 0, sizeof(unsigned) * kChainCounters, stream_));
+  }
   pass(false);
   Q3_CUDA(cudaStreamEndCapture(stream_, &graph));
   Q3_CUDA(cudaGraphInstantiate(&exec, graph, 0));

@@ -303,6 +303,19 @@ void launch_rmsnorm(const LaunchCtx& c, const float* x, int ldx, int m, int dim,
 // ------------------------------------------------------------------------------------------------ q/k norm + RoPE + KV append
 // One warp per (row, head).  head < heads: q;  < heads+kv: k;  else v.  head_dim == 128: lane l owns dims l, l+32 and
 // their rotate-half partners l+64, l+96.
+// KV cache element access: fp32 rings, or fp16 rings on batched handles (half the bytes of the window walk; K and V are rounded
+// once when they are appended, everything downstream stays fp32)
+__device__ __forceinline__ float4 kv_ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 kv_ld4(const __half* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float kv_ld(const float* p) { return *p; }
+__device__ __forceinline__ float kv_ld(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void kv_st(float* p, float v) { *p = v; }
+__device__ __forceinline__ void kv_st(__half* p, float v) { *p = __float2half_rn(v); }
+template <typename KvT>
 __global__ void __launch_bounds__(128) qk_norm_rope_append_kernel(float* __restrict__ qkv, int ld, int m, int heads, int kv_heads,
                                                                   const float* __restrict__ q_norm, const float* __restrict__ k_norm,
                                                                   float eps, const float* __restrict__ inv_freq,
@@ -317,8 +330,9 @@ __global__ void __launch_bounds__(128) qk_norm_rope_append_kernel(float* __restr
   const int slot = row_slot[row], pos = row_pos[row];
   const int ring = pos % kv.capacity;
   if (head >= heads + kv_heads) {  // v: plain append
-    float* dst = kv.v + (size_t)slot * kv.slot_stride + ((size_t)(head - heads - kv_heads) * kv.capacity + ring) * 128;
-    reinterpret_cast<float4*>(dst)[lane] = reinterpret_cast<const float4*>(p)[lane];
+    KvT* dst = static_cast<KvT*>(kv.v) + (size_t)slot * kv.slot_stride + ((size_t)(head - heads - kv_heads) * kv.capacity + ring) * 128;
+    const float4 v4 = reinterpret_cast<const float4*>(p)[lane];
+    kv_st(dst + 4 * lane, v4.x); kv_st(dst + 4 * lane + 1, v4.y); kv_st(dst + 4 * lane + 2, v4.z); kv_st(dst + 4 * lane + 3, v4.w);
     return;
   }
   const float a0 = p[lane], a1 = p[lane + 32], b0 = p[lane + 64], b1 = p[lane + 96];
@@ -334,10 +348,12 @@ __global__ void __launch_bounds__(128) qk_norm_rope_append_kernel(float* __restr
   // q*cos + rotate_half(q)*sin with rotate_half = [-x2, x1]  (Model/Qwen3Layers.swift:187-195)
   const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1;
   const float o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
-  float* dst = p;
-  if (head >= heads)
-    dst = kv.k + (size_t)slot * kv.slot_stride + ((size_t)(head - heads) * kv.capacity + ring) * 128;
-  dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+  if (head >= heads) {
+    KvT* dst = static_cast<KvT*>(kv.k) + (size_t)slot * kv.slot_stride + ((size_t)(head - heads) * kv.capacity + ring) * 128;
+    kv_st(dst + lane, o0); kv_st(dst + lane + 32, o1); kv_st(dst + lane + 64, o2); kv_st(dst + lane + 96, o3);
+  } else {
+    p[lane] = o0; p[lane + 32] = o1; p[lane + 64] = o2; p[lane + 96] = o3;
+  }
 }
 void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, int heads, int kv_heads, int head_dim,
                                 const float* q_norm, const float* k_norm, float eps, const float* inv_freq,
@@ -345,8 +361,10 @@ void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, i
   Q3_CHECK(head_dim == 128, Q3TTS_ERR_BAD_CONFIG, "talker kernels are specialised for head_dim 128 (got %d)", head_dim);
   const int warps = m * (heads + 2 * kv_heads);
   if (warps <= 0) return;
-  qk_norm_rope_append_kernel<<<(warps + 3) / 4, 128, 0, c.stream>>>(qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq,
-                                                                    row_slot, row_pos, kv);
+  if (kv.f16)
+    qk_norm_rope_append_kernel<__half><<<(warps + 3) / 4, 128, 0, c.stream>>>(qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, kv);
+  else
+    qk_norm_rope_append_kernel<float><<<(warps + 3) / 4, 128, 0, c.stream>>>(qkv, ld, m, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, kv);
   c.tick();
 }
 
@@ -356,7 +374,7 @@ void launch_qk_norm_rope_append(const LaunchCtx& c, float* qkv, int ld, int m, i
 __device__ __forceinline__ void store_act(float* p, float v) { *p = v; }
 __device__ __forceinline__ void store_act(__half* p, float v) { *p = __float2half_rn(v); }
 
-template <int G, typename OutT>
+template <int G, typename OutT, typename KvT>
 __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                         const int* __restrict__ row_slot, const int* __restrict__ row_pos,
                                                         const int* __restrict__ win_start, KVLayout kv, OutT* __restrict__ out,
@@ -370,19 +388,19 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   const int w0 = win_start ? win_start[slot] : 0;
   const int S = pos - w0 + 1;
   const int cap = kv.capacity;
-  const float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
-  const float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  const KvT* kb = static_cast<const KvT*>(kv.k) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  const KvT* vb = static_cast<const KvT*>(kv.v) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
 #pragma unroll
   for (int g = 0; g < G; ++g) q[g * 128 + tid] = qkv[(size_t)row * ld + (size_t)(kvh * G + g) * 128 + tid];
   __syncthreads();
   for (int j = tid; j < S; j += 128) {
-    const float4* kr = reinterpret_cast<const float4*>(kb + (size_t)((w0 + j) % cap) * 128);
+    const KvT* kr = kb + (size_t)((w0 + j) % cap) * 128;
     float acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = 0.f;
 #pragma unroll 8
     for (int d = 0; d < 32; ++d) {
-      const float4 kk = kr[d];
+      const float4 kk = kv_ld4(kr + 4 * d);
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         const float4 qq = reinterpret_cast<const float4*>(q + g * 128)[d];
@@ -407,7 +425,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
   for (int g = 0; g < G; ++g) o[g] = 0.f;
   for (int j = 0; j < S; ++j) {
-    const float vv = vb[(size_t)((w0 + j) % cap) * 128 + tid];
+    const float vv = kv_ld(vb + (size_t)((w0 + j) % cap) * 128 + tid);
 #pragma unroll
     for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
   }
@@ -424,25 +442,30 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 // products, an online-softmax update of the lane's 16 output dims.  Groups are merged at the end (2 shuffle steps inside a
 // warp, shared memory across the 4 warps).  The previous version (thread-per-key score loop with 8 loads in flight, three
 // block barriers, 4 V loads in flight) spent ~11 us per launch on dependent round trips even for 2-17 keys.
-template <int G, typename OutT>
+template <int G, typename OutT, typename KvT>
 __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                              const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
                                                              const float* __restrict__ inv_freq, const int* __restrict__ row_slot,
                                                              const int* __restrict__ row_pos, const int* __restrict__ win_start, KVLayout kv,
-                                                             OutT* __restrict__ out, int ldo, float scale) {
+                                                             OutT* __restrict__ out, int ldo, float scale, const ChainSig sig) {
   __shared__ __align__(16) float q[G * 128];
   __shared__ __align__(16) float part_o[4][G][128];
   __shared__ float part_m[4][G], part_l[4][G];
   pdl_launch_dependents();
-  pdl_wait();
+  if (sig.in) {  // chain signal of the qkv GEMM (common.h) instead of its grid completion
+    if (threadIdx.x == 0) chain_wait(sig.in, sig.in_target);
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   const int row = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slot = row_slot[row], pos = row_pos[row];
   const int w0 = win_start ? win_start[slot] : 0;
   const int S = pos - w0 + 1;
   const int cap = kv.capacity;
   const int ring = pos % cap;
-  float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
-  float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  KvT* kb = static_cast<KvT*>(kv.k) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
+  KvT* vb = static_cast<KvT*>(kv.v) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
   const float* rowp = qkv + (size_t)row * ld;
   // phase 0: per-head RMSNorm + rotate-half RoPE (Model/Qwen3Layers.swift:174-195); warp hh < G -> q head, hh == G -> k head
   for (int hh = warp; hh <= G; hh += 4) {
@@ -456,10 +479,15 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
     sincosf((float)pos * inv_freq[lane], &s0, &c0);
     sincosf((float)pos * inv_freq[lane + 32], &s1, &c1);
     const float o0 = x0 * c0 - y0 * s0, o1 = x1 * c1 - y1 * s1, o2 = y0 * c0 + x0 * s0, o3 = y1 * c1 + x1 * s1;
-    float* dst = hh < G ? q + hh * 128 : kb + (size_t)ring * 128;  // k is appended to the ring (:197-201)
-    dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+    if (hh < G) {
+      float* dst = q + hh * 128;
+      dst[lane] = o0; dst[lane + 32] = o1; dst[lane + 64] = o2; dst[lane + 96] = o3;
+    } else {  // k is appended to the ring (:197-201)
+      KvT* dst = kb + (size_t)ring * 128;
+      kv_st(dst + lane, o0); kv_st(dst + lane + 32, o1); kv_st(dst + lane + 64, o2); kv_st(dst + lane + 96, o3);
+    }
   }
-  vb[(size_t)ring * 128 + tid] = rowp[(size_t)(heads + kv_heads + kvh) * 128 + tid];
+  kv_st(vb + (size_t)ring * 128 + tid, rowp[(size_t)(heads + kv_heads + kvh) * 128 + tid]);
   __syncthreads();
   // phase 1: one pass over the window
   const int seg = lane & 7, grp = warp * 4 + (lane >> 3);
@@ -487,8 +515,8 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
       const size_t base = (size_t)((w0 + (j < S ? j : 0)) % cap) * 128 + seg * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        kk[u][i] = *reinterpret_cast<const float4*>(kb + base + i * 32);
-        vv[u][i] = *reinterpret_cast<const float4*>(vb + base + i * 32);
+        kk[u][i] = kv_ld4(kb + base + i * 32);
+        vv[u][i] = kv_ld4(vb + base + i * 32);
       }
     }
 #pragma unroll
@@ -555,6 +583,10 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
     }
     store_act(out + (size_t)row * ldo + (size_t)(kvh * G + g) * 128 + tid, num / den);
   }
+  if (sig.out) {  // K / V appended, outputs stored, every read of qkv done: hand over to the o projection
+    __syncthreads();
+    if (threadIdx.x == 0) chain_signal(sig.out);
+  }
 }
 // Code-predictor pass 0 (Qwen3CodePredictor.swift:183-212 with L = 2): rows (2s, 2s+1) of slot s sit at positions 0 and 1 of a
 // cache that is reset every frame, so norm + RoPE + append + causal attention of BOTH rows is one small CTA per (slot, kv head):
@@ -564,16 +596,21 @@ template <int G>
 __global__ void __launch_bounds__(128) cp_pass0_attention_kernel(const float* __restrict__ qkv, int ld, int heads, int kv_heads,
                                                                  const float* __restrict__ q_norm, const float* __restrict__ k_norm, float eps,
                                                                  const float* __restrict__ inv_freq, KVLayout kv, __half* __restrict__ out,
-                                                                 int ldo, float scale) {
+                                                                 int ldo, float scale, const ChainSig sig) {
   __shared__ __align__(16) float q1[G * 128];   // roped query heads of position 1
   __shared__ __align__(16) float kk[2][128];    // roped keys of positions 0 and 1
   __shared__ __align__(16) float vv[2][128];
   __shared__ float w0[G], w1[G];                // softmax weights of position 1 over keys {0, 1}
   pdl_launch_dependents();
-  pdl_wait();
+  if (sig.in) {
+    if (threadIdx.x == 0) chain_wait(sig.in, sig.in_target);
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   const int slot = blockIdx.x, kvh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float* kb = kv.k + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;
-  float* vb = kv.v + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;
+  float* kb = static_cast<float*>(kv.k) + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;  // the code predictor's cache is fp32
+  float* vb = static_cast<float*>(kv.v) + (size_t)slot * kv.slot_stride + (size_t)kvh * kv.capacity * 128;
   // work items: (pos, head) with head in {q heads of pos 1 (G), k of pos 0, k of pos 1}; the q heads of position 0 are not needed
   // (a single key: its softmax weight is 1 whatever the score)
   for (int item = warp; item < G + 2; item += 4) {
@@ -625,6 +662,10 @@ __global__ void __launch_bounds__(128) cp_pass0_attention_kernel(const float* __
     out[(size_t)(2 * slot) * ldo + (size_t)(kvh * G + g) * 128 + tid] = __float2half_rn(vv[0][tid]);
     out[(size_t)(2 * slot + 1) * ldo + (size_t)(kvh * G + g) * 128 + tid] = __float2half_rn(w0[g] * vv[0][tid] + w1[g] * vv[1][tid]);
   }
+  if (sig.out) {
+    __syncthreads();
+    if (threadIdx.x == 0) chain_signal(sig.out);
+  }
 }
 void launch_cp_pass0_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int n_slots, int heads, int kv_heads, const float* q_norm,
                                    const float* k_norm, float eps, const float* inv_freq, const KVLayout& kv, __half* out, int ldo) {
@@ -633,11 +674,12 @@ void launch_cp_pass0_attention_f16(const LaunchCtx& c, const float* qkv, int ld,
   const float scale = 1.0f / sqrtf(128.0f);
   dim3 grid(n_slots, kv_heads);
   const bool pdl = pdl_enabled();
-  if (G == 1) launch_kernel_pdl(cp_pass0_attention_kernel<1>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
-  else if (G == 2) launch_kernel_pdl(cp_pass0_attention_kernel<2>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
-  else if (G == 4) launch_kernel_pdl(cp_pass0_attention_kernel<4>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale);
-  else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
-  c.tick();
+  Q3_CHECK(G == 1 || G == 2 || G == 4, Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
+  const ChainSig sig = pdl ? c.chain_link((unsigned)(n_slots * kv_heads)) : ChainSig();
+  if (G == 1) launch_kernel_pdl(cp_pass0_attention_kernel<1>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale, sig);
+  else if (G == 2) launch_kernel_pdl(cp_pass0_attention_kernel<2>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale, sig);
+  else launch_kernel_pdl(cp_pass0_attention_kernel<4>, grid, dim3(128), 0, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, kv, out, ldo, scale, sig);
+  if (sig.out) c.tick_chained(); else c.tick();
 }
 
 template <typename OutT>
@@ -650,11 +692,20 @@ static void launch_rope_attention_t(const LaunchCtx& c, const float* qkv, int ld
   const size_t smem = 0;
   dim3 grid(m, kv_heads);
   const bool pdl = pdl_enabled();
-  if (G == 1) launch_kernel_pdl(rope_attention_kernel<1, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
-  else if (G == 2) launch_kernel_pdl(rope_attention_kernel<2, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
-  else if (G == 4) launch_kernel_pdl(rope_attention_kernel<4, OutT>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale);
-  else fail(Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
-  c.tick();
+  Q3_CHECK(G == 1 || G == 2 || G == 4, Q3TTS_ERR_BAD_CONFIG, "unsupported GQA group size %d", G);
+  const ChainSig sig = pdl ? c.chain_link((unsigned)(m * kv_heads)) : ChainSig();
+#define RA_LAUNCH(GV)                                                                                                                              \
+  {                                                                                                                                                \
+    if (kv.f16) launch_kernel_pdl(rope_attention_kernel<GV, OutT, __half>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps, \
+                                  inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale, sig);                                               \
+    else launch_kernel_pdl(rope_attention_kernel<GV, OutT, float>, grid, dim3(128), smem, c.stream, pdl, qkv, ld, heads, kv_heads, q_norm, k_norm, eps,         \
+                           inv_freq, row_slot, row_pos, win_start, kv, out, ldo, scale, sig);                                                      \
+  }
+  if (G == 1) RA_LAUNCH(1)
+  else if (G == 2) RA_LAUNCH(2)
+  else RA_LAUNCH(4)
+#undef RA_LAUNCH
+  if (sig.out) c.tick_chained(); else c.tick();
 }
 void launch_rope_attention(const LaunchCtx& c, const float* qkv, int ld, int m, int heads, int kv_heads, const float* q_norm,
                            const float* k_norm, float eps, const float* inv_freq, const int* row_slot, const int* row_pos,
@@ -678,7 +729,8 @@ static void launch_attention_t(const LaunchCtx& c, const float* qkv, int ld, int
   dim3 grid(m, kv_heads);
 #define Q3_ATT(GV)                                                                                                     \
   {                                                                                                                    \
-    attention_kernel<GV, OutT><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
+    if (kv.f16) attention_kernel<GV, OutT, __half><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
+    else attention_kernel<GV, OutT, float><<<grid, 128, smem, c.stream>>>(qkv, ld, heads, kv_heads, row_slot, row_pos, win_start, kv, out, ldo, scale); \
   }
   Q3_CHECK(smem <= 160 * 1024, Q3TTS_ERR_CAPACITY, "kv_capacity %d too large for the attention kernel", kv.capacity);
   if (G == 1) Q3_ATT(1) else if (G == 2) Q3_ATT(2) else if (G == 4) Q3_ATT(4)
@@ -957,18 +1009,12 @@ void init_talker_kernels() {
   init_linear_fmt<W_BF16>();
   init_linear_fmt<W_F16>();
   init_linear_fmt<W_F32>();
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<1, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<2, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(rope_attention_kernel<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<1, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<2, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  Q3_CUDA(cudaFuncSetAttribute(attention_kernel<4, __half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  // rope_attention_kernel uses static shared memory only; attention_kernel keeps [G][128 + window] floats in dynamic shared memory
+#define Q3_ATT_ATTR(GV, OT, KT) Q3_CUDA(cudaFuncSetAttribute(attention_kernel<GV, OT, KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+#define Q3_ATT_ATTR_G(OT, KT) Q3_ATT_ATTR(1, OT, KT) Q3_ATT_ATTR(2, OT, KT) Q3_ATT_ATTR(4, OT, KT)
+  Q3_ATT_ATTR_G(float, float) Q3_ATT_ATTR_G(float, __half) Q3_ATT_ATTR_G(__half, float) Q3_ATT_ATTR_G(__half, __half)
+#undef Q3_ATT_ATTR_G
+#undef Q3_ATT_ATTR
 }
 
 }  // namespace q3

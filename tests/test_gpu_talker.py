@@ -537,3 +537,32 @@ def test_same_request_object_many_times_in_one_batch(tiny8, engines):
     r = q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=9, keep_invalid_frames=True)
     outs = eng.generate_codes_batch([r] * 6)
     assert all(o.tolist() == outs[0].tolist() for o in outs) and len(outs[0]) == 9
+
+
+def test_fp16_kv_rings_long_window(tiny8, oracles, monkeypatch):
+    """Batched handles keep the talker's K / V rings in fp16 (csrc/talker_kernels.cu kv_ld4 / kv_st): teacher-forced logits stay inside
+    the 1e-2 bar over a window that wraps (230 steps > 192 + 15, trim cadence exercised), and the fp32-ring build of the same handle
+    (Q3TTS_KV_F16=0) agrees with it far inside the bar."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    F = 230
+    forced = np.random.default_rng(12).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    rec = {}
+    oracles(tiny8).generate_codes(_oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec, filter_invalid=False)
+    req = q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced, keep_invalid_frames=True, want_logits=F)
+    e16 = q.Engine(tiny8, max_batch=4, max_frames=256, load_codec=False)
+    monkeypatch.setenv("Q3TTS_KV_F16", "0")
+    e32 = q.Engine(tiny8, max_batch=4, max_frames=256, load_codec=False)
+    monkeypatch.delenv("Q3TTS_KV_F16")
+    try:
+        _, l16 = e16.generate_codes(req)
+        _, l32 = e32.generate_codes(req)
+    finally:
+        e16.close()
+        e32.close()
+    e0 = np.abs(l16["code0_logits"] - rec["code0_logits"]).max()
+    ec = np.abs(l16["cp_logits"] - rec["cp_logits"]).max()
+    d0 = np.abs(l16["code0_logits"] - l32["code0_logits"]).max()
+    print(f"[tiny8, 230 steps] fp16 KV rings: max-abs logit error vs oracle code0 {e0:.3e}, code predictor {ec:.3e}; fp16 vs fp32 rings {d0:.3e}")
+    assert e0 <= LOGIT_TOL and ec <= LOGIT_TOL and d0 <= 5e-3
