@@ -204,7 +204,11 @@ void run_batch(q3tts_handle* h, const q3tts_request* reqs, int n, std::vector<st
     int need = 1;
     for (int s = 0; s < hi; ++s)
       if (slot_req[s] >= 0) need = std::max(need, slot_limit[s] - slot_step[s]);
-    t.run_frames(hi, std::min(8, need));
+    // slots beyond `hi` are inactive (their sampler / finalize / advance are no-ops): running a few more rows costs nothing on the
+    // tensor-core step, while every distinct slot count is its own CUDA graph (capture + instantiate: tens of ms) -- utterances
+    // finishing one by one must not trigger a capture each
+    const int run_slots = t.step_slots(hi);
+    t.run_frames(run_slots, std::min(8, need));
     t.fetch_states(hi, st);
     for (int s = 0; s < hi; ++s) slot_step[s] = st[s].step;
     for (int s = 0; s < hi; ++s) {

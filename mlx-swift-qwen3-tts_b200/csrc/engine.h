@@ -39,6 +39,13 @@ class TalkerEngine {
   // Several utterances at once: one concatenated prefill pass (rows carry their own slot / position).
   void admit_batch(const std::vector<AdmitItem>& items, std::vector<Admission>& out);
   int max_prefill_rows() const { return max_rows_; }
+  // slot count a frame step is issued for when `hi` slots are in use: the row bucket of the tensor-core GEMMs (32 / 64 / 128 ...)
+  // on batched handles, `hi` itself on the <= 2-slot handles of the persistent frame kernel
+  int step_slots(int hi) const {
+    if (!handle_tc_) return hi;
+    int b = hi <= 32 ? 32 : (hi <= 64 ? 64 : (hi + 127) / 128 * 128);
+    return b < opt_.max_batch ? b : opt_.max_batch;
+  }
   // Run `n` frame steps for slots [0, n_slots) — CUDA-graph replay when enabled.
   void run_frames(int n_slots, int n);
   // Read back slot states (synchronises the stream).
@@ -80,7 +87,10 @@ class TalkerEngine {
   void build_tc_weights();
   void build_mega_plan();
   TcLinear make_tc(const Linear& L, bool interleave_halves, const float* fold = nullptr);
-  bool use_tc(int m) const { return w_.has_tc && m >= tc_min_rows_; }            // prefill / prompt assembly
+  // prefill / prompt assembly: the SAME per-handle rule as decode steps, never the row count of the call -- a request prefilled
+  // alone and the same request prefilled next to others must see the same arithmetic.  Batched handles prefill on the 128-row-tile
+  // tcgen05 kernel (row-count invariant); handles of <= 2 slots keep fp32 activations end to end (dequant-fused SIMT linears)
+  bool use_tc(int) const { return handle_tc_; }
   // decode steps: ONE numeric path per handle, fixed at creation from max_batch (not from how many slots happen to be live in a
   // frame), so a request's codes do not depend on what it is co-batched with or on utterances finishing around it:
   //   max_batch >= tc_min_rows_step_ (3)  -> every decode step on the tcgen05 GEMMs (fp16 operands, fp32 accumulate)
@@ -109,7 +119,7 @@ class TalkerEngine {
   // chain signals (common.h): counters of one frame graph + the link state while issue_frame records its launches
   static constexpr int kChainCounters = 1024;
   ChainState chain_;
-  bool chain_on_ = false, chain_enabled_ = true;
+  bool chain_on_ = false, chain_enabled_ = false;
   float* d_rs_ = nullptr;                     // [max_rows] RMSNorm row factors for the 128-row-tile kernel (prefill)
   static constexpr float kX16Div = 16.0f;     // the fp16 copy of the residual stream is x / 16 (range headroom; exact power of two)
   void *d_h16_ = nullptr, *d_attn16_ = nullptr, *d_act16_ = nullptr, *d_tpe16_ = nullptr, *d_tph16_ = nullptr;

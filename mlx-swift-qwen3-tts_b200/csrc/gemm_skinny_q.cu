@@ -128,16 +128,22 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   constexpr int kPBytes = kRowsW * kBlockK * BITS / 8;   // packed bytes of one k-block: 4 KB / 8 KB
   constexpr int kPRow = kBlockK * BITS / 8;              // per row: 32 B / 64 B
   const int x_bytes = p.m_pad * kBlockK * 2;
-  const int AS = p.stages, PS = p.q_pstages;
+  const int AS = p.stages, PS = p.q_pstages, XS = p.q_xstages, XOWN = p.q_xown;
   uint8_t* sA = smem;                                            // [AS][128 rows][128 B] swizzled fp16 weight tiles
-  uint8_t* sX = sA + (size_t)AS * kWBytes;                        // [AS][m_pad rows][128 B] activation tiles (TMA, swizzled)
-  uint8_t* sP = sX + (size_t)AS * x_bytes;                        // [PS][128 rows][kPRow] packed weight k-blocks (TMA, dense)
+  uint8_t* sX = sA + (size_t)AS * kWBytes;                        // [XOWN][m_pad rows][128 B] activation tiles (TMA, swizzled)
+  uint8_t* sP = sX + (size_t)XOWN * x_bytes;                      // [PS][128 rows][kPRow] packed weight k-blocks (TMA, dense)
   float* red = reinterpret_cast<float*>(sP + (size_t)PS * kPBytes);  // [split][128][mc] landing buffer of the peers' partial sums
+  // Activation stages XOWN .. XS-1 ALIAS the packed-weight region: every packed block has been dequantised (and is dead) before the
+  // first activation tile is requested -- the producer waits for `pdone` -- so all XS = min(nkb, ...) activation k-blocks are in
+  // flight at once after the dependency resolves, instead of two at a time behind the MMAs (measured: +0.9 us per launch).
+  auto x_stage = [&](int xs) -> uint8_t* { return xs < XOWN ? sX + (size_t)xs * x_bytes : sP + (size_t)(xs - XOWN) * x_bytes; };
   uint64_t* afull = reinterpret_cast<uint64_t*>(red + (size_t)kRowsW * p.m_pad);
   uint64_t* aempty = afull + AS;
   uint64_t* xfull = aempty + AS;
-  uint64_t* pfull = xfull + AS;
-  uint64_t* tmem_full = pfull + PS;
+  uint64_t* xempty = xfull + XS;
+  uint64_t* pfull = xempty + XS;
+  uint64_t* pdone = pfull + PS;
+  uint64_t* tmem_full = pdone + 1;
   uint64_t* red_full = tmem_full + 1;
   uint64_t* ack = red_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ack + 1);
@@ -160,8 +166,10 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (threadIdx.x == 0) {
     if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 0] = sk_globaltimer();
     SK_STAMP(1);
-    for (int s = 0; s < AS; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); mbar_init(&xfull[s], 1); }
+    for (int s = 0; s < AS; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
     for (int s = 0; s < PS; ++s) mbar_init(&pfull[s], 1);
+    mbar_init(pdone, 4);
     mbar_init(tmem_full, 1);
     mbar_init(red_full, 1);
     mbar_init(ack, p.split > 1 ? p.split - 1 : 1);
@@ -194,10 +202,11 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       }
       sk_wait_dependency_tma(p);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % AS;
-        if (i >= AS) mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read X[s]
-        mbar_expect_tx(&xfull[s], (uint32_t)x_bytes);
-        tma_load_2d(sX + (size_t)s * x_bytes, &tmX, &xfull[s], (kb0 + i) * kBlockK, 0);
+        const int xs = i % XS;
+        if (xs >= XOWN && i < XS) mbar_wait(pdone, 0);                        // the packed region is dead: its bytes may be overwritten
+        if (i >= XS) mbar_wait(&xempty[xs], (uint32_t)(((i / XS) - 1) & 1));  // the MMAs of k-block i - XS have read this stage
+        mbar_expect_tx(&xfull[xs], (uint32_t)x_bytes);
+        tma_load_2d(x_stage(xs), &tmX, &xfull[xs], (kb0 + i) * kBlockK, 0);
       }
     }
     __syncwarp();
@@ -205,18 +214,18 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     if (lane == 0) {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.m_pad >> 3) << 17) | ((uint32_t)(kRowsW >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % AS;
-        const uint32_t ph = (uint32_t)((i / AS) & 1);
-        mbar_wait(&afull[s], ph);
-        mbar_wait(&xfull[s], ph);
+        const int s = i % AS, xs = i % XS;
+        mbar_wait(&afull[s], (uint32_t)((i / AS) & 1));
+        mbar_wait(&xfull[xs], (uint32_t)((i / XS) & 1));
         tc_fence_after();
         if (i == 0) SK_STAMP(3);
         const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kWBytes));
-        const uint64_t bd = umma_desc(smem_u32(sX + (size_t)s * x_bytes));
+        const uint64_t bd = umma_desc(smem_u32(x_stage(xs)));
 #pragma unroll
         for (int k = 0; k < kBlockK / 16; ++k)
           umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
         umma_commit(&aempty[s]);
+        if (i + XS < nkb) umma_commit(&xempty[xs]);
       }
       umma_commit(tmem_full);
     }
@@ -280,6 +289,8 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       if (i + 1 < nkb) { sc[0] = scn[0]; sc[1] = scn[1]; bi[0] = bin[0]; bi[1] = bin[1]; }
     }
     if (nkb > AS) tmem_st_wait();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(pdone);  // this warp has read its last packed byte
     for (int i = AS; i < nkb; ++i) {
       const int s = i % AS;
       uint32_t v[32];
@@ -319,7 +330,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct SkqPlan {
-  int m_pad, split, tiles, num_kb, nkb_max, a_stages, tmem_cols;
+  int m_pad, split, tiles, num_kb, nkb_max, a_stages, x_own, x_stages, tmem_cols;
   size_t smem;
   bool ok;
 };
@@ -339,8 +350,10 @@ SkqPlan plan(const TcGemm& g) {
   const int p_bytes = kRowsW * kBlockK * g.q_bits / 8;
   s.a_stages = std::min(s.nkb_max, s.m_pad <= 32 ? 3 : 2);
   while (s.a_stages * (kWBytes + x_bytes) < red_bytes) ++s.a_stages;  // the rings double as the outgoing staging buffer
-  s.smem = (size_t)s.a_stages * (kWBytes + x_bytes) + (size_t)s.nkb_max * p_bytes + red_bytes + 1024 + (size_t)(3 * s.a_stages + s.nkb_max + 3) * 8 + 16 +
-           kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
+  s.x_own = s.a_stages;                                                                  // activation stages of their own ...
+  s.x_stages = std::min(s.nkb_max, s.x_own + (s.nkb_max * p_bytes) / x_bytes);           // ... plus those that alias the packed region
+  s.smem = (size_t)s.a_stages * kWBytes + (size_t)s.x_own * x_bytes + (size_t)s.nkb_max * p_bytes + red_bytes + 1024 +
+           (size_t)(2 * s.a_stages + 2 * s.x_stages + s.nkb_max + 4) * 8 + 16 + kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
   // TMEM: the fp32 accumulator [128 lanes x m_pad columns] + 32 columns per k-block parked beyond the A ring
   int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);
   s.tmem_cols = 32;
@@ -412,6 +425,7 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   p.sig = c.chain_link((unsigned)(s.tiles * s.split));
   p.q_scales = g.q_scales; p.q_biases = g.q_biases; p.q_fold = g.q_fold; p.q_group = g.q_group; p.q_sdt = g.q_sdt;
   p.q_pstages = s.nkb_max;
+  p.q_xstages = s.x_stages; p.q_xown = s.x_own;
   p.q_half_rows = g.q_halves ? g.N / 2 : 0;
 
   const uint32_t wpk = (uint32_t)(kBlockK * g.q_bits / 32);

@@ -39,6 +39,7 @@ struct SkParams {
   const float* q_fold;      // fp32 [K] multiplied into the dequantised columns (the RMSNorm weight in front of this linear), or null
   int q_group, q_sdt;
   int q_pstages;            // packed-tile ring depth
+  int q_xstages, q_xown;    // activation stages in total / outside the (dead after dequantisation) packed region
   int q_half_rows;          // SwiGLU over a [gate ; up] matrix: rows of one half (N / 2); tile row 2i = gate i, 2i + 1 = up i.  0: plain rows
 };
 

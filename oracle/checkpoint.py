@@ -320,6 +320,77 @@ def codec_tensors(c: CodecDims, seed: int, gain: float = 0.6, visible: bool = Tr
     return o
 
 
+def encoder_preset(name: str):
+    """ICL reference-audio encoder dimensions: 'full' = Qwen3TTSTokenizerEncoderConfig defaults (SpeechTokenizer.swift:9-40); 'tiny' = CPU-test size."""
+    from .audio_encoder import EncoderDims
+
+    if name == "full":
+        return EncoderDims()
+    if name == "tiny":
+        return EncoderDims(codebook_dim=32, codebook_size=256, hidden_size=128, intermediate_size=256, num_filters=8, num_hidden_layers=2,
+                           num_quantizers=32, num_attention_heads=2, num_key_value_heads=2, vector_quantization_hidden_dimension=32)
+    raise ValueError(name)
+
+
+def encoder_tensors(e, seed: int) -> dict:
+    """Seeded ICL-encoder weights under the `encoder.*` keys `Qwen3TTSAudioEncoder.sanitizeEncoderWeights` reads
+    (Vocoder/Qwen3TTSAudioEncoder.swift:589-648; module tree :120-460), PyTorch layouts (conv [out, in, k])."""
+    r = _Rng(seed)
+    o: dict = {}
+
+    def conv(key, cout, cin, k, g=1.0):
+        o[key + ".weight"] = r.normal((cout, cin, k), g / np.sqrt(cin * k))
+        o[key + ".bias"] = r.normal((cout,), 0.02)
+
+    li = 0
+    conv(f"encoder.encoder.layers.{li}.conv", e.num_filters, e.audio_channels, e.kernel_size)
+    li += 1
+    cur = e.num_filters
+    for i, ratio in enumerate(reversed(e.upsampling_ratios)):
+        for _ in range(e.num_residual_layers):
+            conv(f"encoder.encoder.layers.{li}.block.1.conv", cur // 2, cur, 3)
+            conv(f"encoder.encoder.layers.{li}.block.3.conv", cur, cur // 2, 1, g=0.5)
+            li += 1
+        li += 1  # ELU
+        conv(f"encoder.encoder.layers.{li}.conv", e.num_filters * 2 ** (i + 1), cur, 2 * ratio)
+        cur = e.num_filters * 2 ** (i + 1)
+        li += 1
+    li += 1  # ELU
+    conv(f"encoder.encoder.layers.{li}.conv", e.hidden_size, cur, e.last_kernel_size)
+    H = e.hidden_size
+    for n in range(e.num_hidden_layers):
+        p = f"encoder.encoder_transformer.layers.{n}"
+        for ln in ("input_layernorm", "post_attention_layernorm"):
+            o[f"{p}.{ln}.weight"] = r.uniform((H,), 0.8, 1.2)
+            o[f"{p}.{ln}.bias"] = r.normal((H,), 0.05)
+        for nm, od in (("q_proj", e.num_attention_heads * e.head_dim), ("k_proj", e.num_key_value_heads * e.head_dim),
+                       ("v_proj", e.num_key_value_heads * e.head_dim)):
+            o[f"{p}.self_attn.{nm}.weight"] = r.normal((od, H), 1.0 / np.sqrt(H))
+        o[f"{p}.self_attn.o_proj.weight"] = r.normal((H, e.num_attention_heads * e.head_dim), 0.6 / np.sqrt(e.num_attention_heads * e.head_dim))
+        o[f"{p}.mlp.fc1.weight"] = r.normal((e.intermediate_size, H), 1.0 / np.sqrt(H))
+        o[f"{p}.mlp.fc1.bias"] = r.normal((e.intermediate_size,), 0.02)
+        o[f"{p}.mlp.fc2.weight"] = r.normal((H, e.intermediate_size), 0.6 / np.sqrt(e.intermediate_size))
+        o[f"{p}.mlp.fc2.bias"] = r.normal((H,), 0.02)
+        o[f"{p}.self_attn_layer_scale.scale"] = r.uniform((H,), 0.3, 0.7)
+        o[f"{p}.mlp_layer_scale.scale"] = r.uniform((H,), 0.3, 0.7)
+    conv("encoder.downsample.conv.conv", H, H, 2 * e.compress)
+    D = e.vector_quantization_hidden_dimension
+    for name, n in (("semantic", e.num_semantic_quantizers), ("acoustic", e.num_quantizers - e.num_semantic_quantizers)):
+        p = f"encoder.quantizer.{name}_residual_vector_quantizer"
+        o[p + ".input_proj.weight"] = r.normal((D, H, 1), 1.0 / np.sqrt(H))
+        o[p + ".output_proj.weight"] = r.normal((H, D, 1), 1.0 / np.sqrt(D))
+        for i in range(n):
+            usage = r.uniform((e.codebook_size,), 0.5, 50.0)
+            emb = r.normal((e.codebook_size, D), 1.0 / (1.0 + 0.35 * i))  # residual codebooks shrink like a trained RVQ's
+            dead = torch.arange(e.codebook_size) % 89 == 7               # clip(cluster_usage, 1e-5) path
+            usage[dead] = 0.0
+            esum = emb * usage[:, None]
+            esum[dead] = r.normal((int(dead.sum()), D), 1e-6)
+            o[f"{p}.layers.{i}._codebook.embedding_sum"] = esum
+            o[f"{p}.layers.{i}._codebook.cluster_usage"] = usage
+    return o
+
+
 def talker_config_json(t: TalkerDims, bits: int, group: int = 64) -> dict:
     tc = {k: v for k, v in asdict(t).items()
           if k not in ("code_predictor", "mrope_section", "tts_model_type", "tts_bos_token_id", "tts_eos_token_id", "tts_pad_token_id")}
@@ -344,14 +415,14 @@ def codec_config_json(c: CodecDims) -> dict:
 
 def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = "bf16", seed: int = 0,
                      codec_seed: int | None = None, visible: bool = True, with_codec: bool = True,
-                     normalize_codec: bool = True, init: str = "stress", quant_key: str = "quantization") -> str:
+                     normalize_codec: bool = True, init: str = "stress", quant_key: str = "quantization", encoder: str | None = None) -> str:
     """Write a complete synthetic model directory; returns `path`.  Idempotent via a stamp file.
 
     init: see `talker_tensors`.  quant_key = "quantization_config" writes the packed leaves WITHOUT a top-level
     `quantization` block, i.e. the checkpoint form `Qwen3Talker.load` dequantises offline to fp16 (Qwen3Talker.swift:139-175)."""
     t, c = preset(name)
     stamp = {"name": name, "bits": bits, "dtype": dtype, "seed": seed, "codec_seed": codec_seed, "visible": visible,
-             "with_codec": with_codec, "normalize_codec": normalize_codec, "init": init, "quant_key": quant_key, "v": 4}
+             "with_codec": with_codec, "normalize_codec": normalize_codec, "init": init, "quant_key": quant_key, "encoder": encoder, "v": 5}
     stamp_path = os.path.join(path, "synthetic_stamp.json")
     if os.path.exists(stamp_path):
         try:
@@ -366,13 +437,42 @@ def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = 
     json.dump(cfg, open(os.path.join(path, "config.json"), "w"), indent=1)
     save_file(talker_tensors(t, bits, dtype, seed, init=init), os.path.join(path, "model.safetensors"))
     if with_codec:
-        json.dump(codec_config_json(c), open(os.path.join(path, "speech_tokenizer", "config.json"), "w"), indent=1)
+        cj = codec_config_json(c)
         ct = codec_tensors(c, seed + 1000 if codec_seed is None else codec_seed, visible=visible)
         if normalize_codec:
             _normalize_codec_output(c, ct)
+        if encoder:  # ICL reference-audio encoder weights live in the same file under `encoder.*` (Qwen3TTSAudioEncoder.swift:587-603)
+            ed = encoder_preset(encoder)
+            cj["encoder_config"] = asdict(ed)
+            et = encoder_tensors(ed, seed + 2000)
+            _normalize_encoder_latent(ed, et)
+            ct.update(et)
+        json.dump(cj, open(os.path.join(path, "speech_tokenizer", "config.json"), "w"), indent=1)
         save_file({k: v.contiguous() for k, v in ct.items()}, os.path.join(path, "speech_tokenizer", "model.safetensors"))
     json.dump(stamp, open(stamp_path, "w"))
     return path
+
+
+def _normalize_encoder_latent(e, et: dict, seconds: float = 1.0):
+    """Rescale the quantizers' input projections so the projected latent has unit RMS on noise input: with the codebooks drawn at
+    O(1) scale the nearest-neighbour search then spreads over the codebook instead of collapsing onto its smallest entries."""
+    import tempfile
+
+    from .audio_encoder import AudioEncoderOracle
+
+    with tempfile.TemporaryDirectory() as td:
+        json.dump({"encoder_config": asdict(e)}, open(os.path.join(td, "config.json"), "w"))
+        save_file({k: v.contiguous() for k, v in et.items()}, os.path.join(td, "model.safetensors"))
+        orc = AudioEncoderOracle(td)
+    g = torch.Generator().manual_seed(4321)
+    audio = (torch.randn(int(24000 * seconds), generator=g) * 0.1).numpy()
+    rec: dict = {}
+    orc.encode(audio, rec)
+    lat = torch.from_numpy(rec["latent"])[0]  # [T, hidden]
+    for name in ("semantic", "acoustic"):
+        k = f"encoder.quantizer.{name}_residual_vector_quantizer.input_proj.weight"
+        proj = lat @ et[k][:, :, 0].T
+        et[k] = et[k] / max(float(proj.pow(2).mean().sqrt()), 1e-12)
 
 
 def _normalize_codec_output(c: CodecDims, ct: dict, target_rms: float = 0.2, frames: int = 6):
