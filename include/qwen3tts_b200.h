@@ -80,7 +80,9 @@ typedef struct q3tts_info {
   int32_t codec_eos_id, codec_pad_id;
   int32_t max_batch, kv_capacity, max_frames;
   int64_t device_bytes; /* HBM held by the handle */
-  int32_t reserved[8];
+  int32_t has_audio_encoder;    /* supportsICL (Qwen3TTSPipeline.swift:87-89): speech_tokenizer/model.safetensors carries `encoder.*` */
+  int32_t audio_encoder_hidden; /* width of the quantiser input (q3tts_encode_reference_audio latent_out) */
+  int32_t reserved[6];
 } q3tts_info;
 
 /* ---- one utterance; replaces the argument list of Qwen3Talker.generateCodes / generateStream
@@ -198,6 +200,18 @@ q3tts_status q3tts_decode_chunked(q3tts_handle* h, const int32_t* codes, int32_t
                                   int32_t chunk_size, int32_t left_context, float* pcm_out);
 
 /* ------------------------------------------------------------------------------------------------------
+ * ICL reference-audio encoder -- replaces Qwen3TTSPipeline.encodeReferenceAudio (Qwen3TTSPipeline.swift:924-945), i.e.
+ * Qwen3TTSAudioEncoder.encode (Vocoder/Qwen3TTSAudioEncoder.swift:526-572): 24 kHz mono PCM -> SEANet CNN -> bidirectional
+ * transformer -> stride-2 downsample -> split residual vector quantiser (nearest codeword per layer) -> the first 16 code rows.
+ * codes_out: [quantizers][frames] int32 row-major -- exactly the `ref_codes` layout q3tts_request takes; *frames_out =
+ * ceil(ceil(n / 960) / 2) (one frame per 1920 samples, the last one completed by zero padding).  Without encoder weights in the
+ * checkpoint the call returns Q3TTS_OK with *frames_out = 0 (the reference returns nil).  latent_out (optional,
+ * [frames][audio_encoder_hidden] fp32) receives the quantiser's input, for parity probes.
+ * ---------------------------------------------------------------------------------------------------- */
+q3tts_status q3tts_encode_reference_audio(q3tts_handle* h, const float* samples, int64_t n_samples, int32_t* codes_out,
+                                          int32_t capacity_frames, int32_t* frames_out, int32_t* quantizers_out, float* latent_out);
+
+/* ------------------------------------------------------------------------------------------------------
  * fused text -> PCM — the bodies of Qwen3TTSPipeline.generate (:244-306), generateToFile's per-text-chunk work
  * (:681-744) and generateBatch's (:813-864): generateCodes, then decode as `mode` schedules it, NaN/Inf scrub
  * and clamp (:565-570, 726-732).  *samples_out <= capacity_samples; needs frames*1920 floats.
@@ -277,6 +291,13 @@ q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int
 q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K, int32_t swiglu, int32_t residual, int32_t iters,
                                 uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out,
                                 int32_t* stages_out, double* avg_us_out);
+
+/* the same measurement for the dequant-fused kernel (csrc/gemm_skinny_q.cu): bits = 4 / 8 streams MLX-packed weights (group 64, fp16
+ * scales), bits = 0 is q3tts_skinny_trace.  Extra stamps: [14] all k-blocks dequantised (warp 3), [15] dependency on the predecessor
+ * launch resolved (warp 3). */
+q3tts_status q3tts_skinny_trace_q(int32_t device, int32_t M, int32_t N, int32_t K, int32_t bits, int32_t swiglu, int32_t residual, int32_t iters,
+                                  uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out,
+                                  int32_t* stages_out, double* avg_us_out);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <map>
 
+#include "audio_encoder.h"
 #include "codec.h"
 #include "codec_kernels.h"
 #include "engine.h"
@@ -17,6 +18,7 @@ void init_talker_kernels();
 Handle::~Handle() {
   talker.reset();
   codec.reset();
+  audio_encoder.reset();
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_stop) cudaEventDestroy(ev_stop);
   if (h_pcm) cudaFreeHost(h_pcm);
@@ -446,6 +448,15 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
       // one pass holds up to codec_max_frames frames (batch x window); the workspace itself is allocated on first use
       h->codec.reset(new CodecDecoder(dir + "/speech_tokenizer", h->stream, &h->counter, h->opt.codec_max_frames));
       h->codec->set_use_graph(h->opt.use_cuda_graph != 0);
+      // audio encoder for ICL, optional: a failing load leaves ICL unavailable, it does not fail the pipeline (Qwen3TTSPipeline.swift:210-218)
+      if (AudioEncoder::present(dir + "/speech_tokenizer")) {
+        try {
+          h->audio_encoder.reset(new AudioEncoder(dir + "/speech_tokenizer", h->stream, &h->counter));
+        } catch (const Error& e) {
+          g_create_error = std::string("audio encoder not loaded: ") + e.what();
+          cudaGetLastError();
+        }
+      }
     }
     Q3_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;
@@ -494,6 +505,11 @@ q3tts_status q3tts_get_info(const q3tts_handle* hc, q3tts_info* out) {
     out->codec_num_quantizers = hc->codec->config().num_quantizers;
     out->codec_total_upsample = hc->codec->total_upsample();
     out->device_bytes += (int64_t)hc->codec->device_bytes();
+  }
+  if (hc->audio_encoder) {
+    out->has_audio_encoder = 1;
+    out->audio_encoder_hidden = hc->audio_encoder->config().hidden_size;
+    out->device_bytes += (int64_t)hc->audio_encoder->device_bytes();
   }
   return Q3TTS_OK;
 }
@@ -755,6 +771,25 @@ q3tts_status q3tts_decode_chunked(q3tts_handle* h, const int32_t* codes, int32_t
                         std::min<int64_t>((int64_t)chunk_size * up, (int64_t)frames * up - o0)});
       }
     run_decode_jobs(h, jobs);
+    tm.finish();
+  });
+}
+
+// =================================================================================================== ICL reference-audio encoder
+q3tts_status q3tts_encode_reference_audio(q3tts_handle* h, const float* samples, int64_t n_samples, int32_t* codes_out, int32_t capacity_frames,
+                                          int32_t* frames_out, int32_t* quantizers_out, float* latent_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(frames_out != nullptr, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    *frames_out = 0;
+    if (quantizers_out) *quantizers_out = 0;
+    if (!h->audio_encoder) return;  // encodeReferenceAudio returns nil without an encoder (Qwen3TTSPipeline.swift:925)
+    Q3_CHECK(samples != nullptr && n_samples > 0 && codes_out != nullptr, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    CallTimer tm(h);
+    const int f = h->audio_encoder->encode(samples, n_samples, codes_out, capacity_frames, latent_out);
+    *frames_out = f;
+    if (quantizers_out) *quantizers_out = h->audio_encoder->quantizers_out();
+    h->timing.h2d_bytes += n_samples * 4;
+    h->timing.d2h_bytes += (int64_t)f * h->audio_encoder->quantizers_out() * 4;
     tm.finish();
   });
 }
@@ -1023,32 +1058,53 @@ q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t
   }
 }
 
-q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K, int32_t swiglu, int32_t residual, int32_t iters,
-                                uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out, int32_t* stages_out,
-                                double* avg_us_out) {
+static q3tts_status skinny_trace_impl(int32_t device, int32_t M, int32_t N, int32_t K, int32_t bits, int32_t swiglu, int32_t residual, int32_t iters,
+                                      uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out, int32_t* stages_out,
+                                      double* avg_us_out) {
   try {
     Q3_CHECK(M > 0 && N > 0 && K > 0 && iters > 0 && stamps_out && tiles_out && split_out && stages_out && avg_us_out, Q3TTS_ERR_INVALID_ARG,
              "bad arguments");
+    Q3_CHECK(bits == 0 || bits == 4 || bits == 8, Q3TTS_ERR_INVALID_ARG, "bits must be 0 (fp16 weights), 4 or 8");
     require_device(device);
     init_tc_gemm();
     const int n_out = swiglu ? N / 2 : N;
     __half *x = nullptr, *w = nullptr, *y16 = nullptr;
     float* y32 = nullptr;
+    uint32_t* qw = nullptr;
+    __half *qs = nullptr, *qb = nullptr;
     unsigned long long* tr = nullptr;
+    const size_t wbytes = bits ? (size_t)N * K * bits / 8 : (size_t)N * K * 2, sbytes = (size_t)N * (K / 64) * 2;
     Q3_CUDA(cudaMalloc(&x, (size_t)M * K * 2));
     // `iters` DIFFERENT weight matrices so every launch streams from HBM like consecutive layers do
-    Q3_CUDA(cudaMalloc(&w, (size_t)iters * N * K * 2));
+    if (bits) {
+      Q3_CUDA(cudaMalloc(&qw, (size_t)iters * wbytes));
+      Q3_CUDA(cudaMalloc(&qs, (size_t)iters * sbytes));
+      Q3_CUDA(cudaMalloc(&qb, (size_t)iters * sbytes));
+      Q3_CUDA(cudaMemset(qw, 0x5A, (size_t)iters * wbytes));
+      Q3_CUDA(cudaMemset(qs, 0x1C, (size_t)iters * sbytes));  // fp16 0x1C1C ~ 4e-3
+      Q3_CUDA(cudaMemset(qb, 0x00, (size_t)iters * sbytes));
+    } else {
+      Q3_CUDA(cudaMalloc(&w, (size_t)iters * wbytes));
+      Q3_CUDA(cudaMemset(w, 0, (size_t)iters * wbytes));
+    }
     Q3_CUDA(cudaMalloc(&y16, (size_t)M * n_out * 2));
     Q3_CUDA(cudaMalloc(&y32, (size_t)M * n_out * 4));
     Q3_CUDA(cudaMemset(x, 0, (size_t)M * K * 2));
-    Q3_CUDA(cudaMemset(w, 0, (size_t)iters * N * K * 2));
     Q3_CUDA(cudaMemset(y32, 0, (size_t)M * n_out * 4));
     TcGemm g;
     g.a = x; g.w = w; g.Bt = 1; g.T = M; g.cin = K; g.N = N; g.swiglu = swiglu;
+    if (bits) { g.q_bits = bits; g.q_group = 64; g.q_sdt = Q3TTS_F16; g.q_halves = swiglu ? 1 : 0; g.q_w = qw; g.q_scales = qs; g.q_biases = qb; }
     if (swiglu) { g.out16 = y16; g.ld16 = n_out; } else { g.out32 = y32; g.ld32 = n_out; }
     if (residual) { g.res = y32; g.ld_res = n_out; g.out32 = y32; g.ld32 = n_out; }
-    Q3_CHECK(tc_skinny_supported(g), Q3TTS_ERR_INVALID_ARG, "shape is not on the skinny path");
-    tc_skinny_grid(g, tiles_out, split_out, stages_out);
+    if (bits) {
+      Q3_CHECK(tc_skinny_q_supported(g), Q3TTS_ERR_INVALID_ARG, "shape is not on the dequant-fused skinny path");
+      TcGemm gd = g;  // same split rule as the dense kernel: report it through the dense planner
+      gd.q_w = nullptr; gd.w = x;
+      tc_skinny_grid(gd, tiles_out, split_out, stages_out);
+    } else {
+      Q3_CHECK(tc_skinny_supported(g), Q3TTS_ERR_INVALID_ARG, "shape is not on the skinny path");
+      tc_skinny_grid(g, tiles_out, split_out, stages_out);
+    }
     const int ctas = *tiles_out * *split_out;
     Q3_CHECK(ctas <= capacity_ctas, Q3TTS_ERR_CAPACITY, "stamps_out holds %d CTAs, the grid has %d", capacity_ctas, ctas);
     Q3_CUDA(cudaMalloc(&tr, (size_t)ctas * 16 * 8));
@@ -1064,8 +1120,13 @@ q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K,
     tc_skinny_set_trace(tr);
     Q3_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
     for (int i = 0; i < iters; ++i) {
-      g.w = w + (size_t)i * N * K;
-      launch_tc_skinny(c, g);
+      if (bits) {
+        g.q_w = qw + (size_t)i * wbytes / 4; g.q_scales = qs + (size_t)i * sbytes / 2; g.q_biases = qb + (size_t)i * sbytes / 2;
+        launch_tc_skinny_q(c, g);
+      } else {
+        g.w = w + (size_t)i * N * K;
+        launch_tc_skinny(c, g);
+      }
     }
     Q3_CUDA(cudaStreamEndCapture(st, &graph));
     tc_skinny_set_trace(nullptr);
@@ -1082,7 +1143,7 @@ q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K,
     Q3_CUDA(cudaMemcpy(stamps_out, tr, (size_t)ctas * 16 * 8, cudaMemcpyDeviceToHost));
     cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
-    cudaFree(x); cudaFree(w); cudaFree(y16); cudaFree(y32); cudaFree(tr);
+    cudaFree(x); cudaFree(w); cudaFree(qw); cudaFree(qs); cudaFree(qb); cudaFree(y16); cudaFree(y32); cudaFree(tr);
     return Q3TTS_OK;
   } catch (const Error& e) {
     tc_skinny_set_trace(nullptr);
@@ -1090,6 +1151,18 @@ q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K,
     cudaGetLastError();
     return e.status;
   }
+}
+
+q3tts_status q3tts_skinny_trace(int32_t device, int32_t M, int32_t N, int32_t K, int32_t swiglu, int32_t residual, int32_t iters,
+                                uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out, int32_t* stages_out,
+                                double* avg_us_out) {
+  return skinny_trace_impl(device, M, N, K, 0, swiglu, residual, iters, stamps_out, capacity_ctas, tiles_out, split_out, stages_out, avg_us_out);
+}
+
+q3tts_status q3tts_skinny_trace_q(int32_t device, int32_t M, int32_t N, int32_t K, int32_t bits, int32_t swiglu, int32_t residual, int32_t iters,
+                                  uint64_t* stamps_out, int32_t capacity_ctas, int32_t* tiles_out, int32_t* split_out, int32_t* stages_out,
+                                  double* avg_us_out) {
+  return skinny_trace_impl(device, M, N, K, bits, swiglu, residual, iters, stamps_out, capacity_ctas, tiles_out, split_out, stages_out, avg_us_out);
 }
 
 q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out, int64_t* launches_out,

@@ -220,7 +220,7 @@ void launch_codec_rope(const LaunchCtx& c, float* qkv, int ld, int M, int T, int
 // Full-causal MHA, head_dim 64, online softmax; grid (q tiles of 16, heads, batch), 4 warps x 4 query rows.
 template <typename OutT>
 __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __restrict__ qkv, int ld, int T, int nh, int nkv, float scale,
-                                                              OutT* __restrict__ out, int ldo) {
+                                                              OutT* __restrict__ out, int ldo, int causal) {
   __shared__ float Ks[32][65];
   __shared__ float Vs[32][64];
   __shared__ float Qs[16][64];
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
 #pragma unroll
   for (int i = 0; i < 4; ++i) { mi[i] = -INFINITY; li[i] = 0.f; acc[i][0] = acc[i][1] = 0.f; }
   const int koff = nh * 64 + kvh * 64, voff = nh * 64 + nkv * 64 + kvh * 64;
-  const int last = min(T, r0 + 16);
+  const int last = causal ? min(T, r0 + 16) : T;  // causal = 0: the ICL encoder's bidirectional attention (Qwen3TTSAudioEncoder.swift:331)
   for (int kt = 0; kt < last; kt += 32) {
     __syncthreads();
     for (int i = tid; i < 32 * 64; i += 128) {
@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
 #pragma unroll 16
       for (int d = 0; d < 64; ++d) s = fmaf(Qs[rl][d], Ks[lane][d], s);
       const int j = kt + lane;
-      s = (j <= row && j < T) ? s * scale : -INFINITY;
+      s = ((j <= row || !causal) && j < T) ? s * scale : -INFINITY;
       const float mt = warp_max_c(s);
       const float mnew = fmaxf(mi[i], mt);
       if (mnew == -INFINITY) continue;  // whole tile masked for this row
@@ -284,13 +284,19 @@ __global__ void __launch_bounds__(128) codec_attention_kernel(const float* __res
 void launch_codec_attention(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo) {
   if (B <= 0 || T <= 0) return;
   dim3 grid((T + 15) / 16, nh, B);
-  codec_attention_kernel<float><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
+  codec_attention_kernel<float><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 1);
+  c.tick();
+}
+void launch_codec_attention_bidir(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo) {
+  if (B <= 0 || T <= 0) return;
+  dim3 grid((T + 15) / 16, nh, B);
+  codec_attention_kernel<float><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 0);
   c.tick();
 }
 void launch_codec_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, __half* out, int ldo) {
   if (B <= 0 || T <= 0) return;
   dim3 grid((T + 15) / 16, nh, B);
-  codec_attention_kernel<__half><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo);
+  codec_attention_kernel<__half><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 1);
   c.tick();
 }
 
@@ -382,6 +388,86 @@ void launch_out_conv_f16(const LaunchCtx& c, const __half* x, const float* w, co
 void init_codec_kernels() {
   Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+}
+
+// ---------------------------------------------------------------------------------------------- ICL audio encoder pieces
+// ELUActivation (Vocoder/Qwen3TTSAudioEncoder.swift:8-20): max(x, 0) + min(alpha * (exp(x) - 1), 0), alpha = 1
+__global__ void elu_kernel(const float* __restrict__ x, size_t total, float* __restrict__ y) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    y[i] = fmaxf(v, 0.f) + fminf(expf(v) - 1.0f, 0.f);
+  }
+}
+void launch_elu(const LaunchCtx& c, const float* x, size_t total, float* y) {
+  if (total == 0) return;
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  elu_kernel<<<blocks, 256, 0, c.stream>>>(x, total, y);
+  c.tick();
+}
+
+// EncoderSplitResidualVectorQuantizer.encode (:424-460) for one frame per CTA: the semantic chain (layers [0, n_sem)) starts from
+// lat_sem[t], the acoustic chain (layers [n_sem, n_out)) from lat_ac[t]; per layer the nearest codeword by
+// (|x|^2 - 2 x.e) + |e|^2 (EuclideanCodebook.encode, Vocoder/SpeechTokenizer.swift:511-519; first index on ties), then
+// residual -= e[idx] (:408-412).  A warp owns codewords w, w + 8, ...: lanes stride the D dims of a row (coalesced), shuffle reduce.
+__global__ void __launch_bounds__(256) rvq_encode_kernel(const float* __restrict__ lat_sem, const float* __restrict__ lat_ac,
+                                                         const float* const* __restrict__ books, const float* const* __restrict__ books_sq, int n_sem,
+                                                         int n_out, int D, int size, int T, int* __restrict__ codes) {
+  extern __shared__ float rvq_sm[];
+  float* res = rvq_sm;  // [D]
+  __shared__ float red[8];
+  __shared__ float best_d[8];
+  __shared__ int best_i[8];
+  __shared__ int chosen;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = 0; q < n_out; ++q) {
+    if (q == 0 || q == n_sem) {  // start of a chain: its own projection of the frame
+      const float* src = (q < n_sem ? lat_sem : lat_ac) + (size_t)t * D;
+      __syncthreads();
+      for (int d = tid; d < D; d += 256) res[d] = src[d];
+      __syncthreads();
+    }
+    float ss = 0.f;
+    for (int d = tid; d < D; d += 256) ss = fmaf(res[d], res[d], ss);
+    ss = warp_sum_c(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float xsq = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) xsq += red[w];
+    const float* E = books[q];
+    const float* Esq = books_sq[q];
+    float bd = INFINITY;
+    int bi = 0x7fffffff;
+    for (int cidx = warp; cidx < size; cidx += 8) {
+      const float* e = E + (size_t)cidx * D;
+      float dot = 0.f;
+      for (int d = lane; d < D; d += 32) dot = fmaf(res[d], e[d], dot);
+      dot = warp_sum_c(dot);
+      const float dist = (xsq - 2.0f * dot) + Esq[cidx];
+      if (dist < bd) { bd = dist; bi = cidx; }  // ascending cidx inside a warp: strict < keeps the first minimum
+    }
+    if (lane == 0) { best_d[warp] = bd; best_i[warp] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      float d0 = best_d[0];
+      int i0 = best_i[0];
+      for (int w = 1; w < 8; ++w)
+        if (best_d[w] < d0 || (best_d[w] == d0 && best_i[w] < i0)) { d0 = best_d[w]; i0 = best_i[w]; }
+      if (i0 < 0 || i0 >= size) i0 = 0;  // all-NaN distances: keep the walk in bounds
+      chosen = i0;
+      codes[(size_t)q * T + t] = i0;
+    }
+    __syncthreads();
+    const float* e = E + (size_t)chosen * D;
+    for (int d = tid; d < D; d += 256) res[d] -= e[d];
+    __syncthreads();
+  }
+}
+void launch_rvq_encode(const LaunchCtx& c, const float* lat_sem, const float* lat_ac, const float* const* books, const float* const* books_sq, int n_sem,
+                       int n_out, int D, int size, int T, int* codes) {
+  if (T <= 0) return;
+  rvq_encode_kernel<<<T, 256, sizeof(float) * D, c.stream>>>(lat_sem, lat_ac, books, books_sq, n_sem, n_out, D, size, T, codes);
+  c.tick();
 }
 
 }  // namespace q3

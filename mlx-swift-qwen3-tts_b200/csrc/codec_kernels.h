@@ -18,6 +18,11 @@ void launch_silu_mul(const LaunchCtx& c, const float* gu, size_t rows, int I, fl
 void launch_codec_rope(const LaunchCtx& c, float* qkv, int ld, int M, int T, int n_rot_heads, const float* inv_freq);
 void launch_codec_attention(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo);
 void launch_codec_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, __half* out, int ldo);
+// ICL audio encoder (audio_encoder.cu)
+void launch_codec_attention_bidir(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, float* out, int ldo);
+void launch_elu(const LaunchCtx& c, const float* x, size_t total, float* y);
+void launch_rvq_encode(const LaunchCtx& c, const float* lat_sem, const float* lat_ac, const float* const* books, const float* const* books_sq, int n_sem,
+                       int n_out, int D, int size, int T, int* codes);
 void launch_rvq_embed(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
                       float* emb);
 void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y);

@@ -12,6 +12,7 @@
 namespace q3 {
 
 class CodecDecoder;  // codec.h
+class AudioEncoder;  // audio_encoder.h
 
 struct EngineOptions {
   int device = 0;
@@ -175,6 +176,7 @@ struct Handle {
   bool has_talker = false;
   std::unique_ptr<TalkerEngine> talker;
   std::unique_ptr<CodecDecoder> codec;
+  std::unique_ptr<AudioEncoder> audio_encoder;  // ICL reference-audio encoder, when the checkpoint carries one
   q3tts_timing timing{};
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   float* h_pcm = nullptr;  // pinned staging for PCM read-back

@@ -126,7 +126,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int kPBytes = kRowsW * kBlockK * BITS / 8;   // packed bytes of one k-block: 4 KB / 8 KB
-  constexpr int kPRow = kBlockK * BITS / 8;              // per row: 32 B / 64 B
+  constexpr int kPRow = kBlockK * BITS / 8;              // per row and k-block: 32 B / 64 B
   const int x_bytes = p.m_pad * kBlockK * 2;
   const int AS = p.stages, PS = p.q_pstages, XS = p.q_xstages, XOWN = p.q_xown;
   uint8_t* sA = smem;                                            // [AS][128 rows][128 B] swizzled fp16 weight tiles
@@ -141,7 +141,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   uint64_t* aempty = afull + AS;
   uint64_t* xfull = aempty + AS;
   uint64_t* xempty = xfull + XS;
-  uint64_t* pfull = xempty + XS;
+  uint64_t* pfull = xempty + XS;   // [0] only: the whole packed slice arrives with one (two: gate | up) tensor load(s)
   uint64_t* pdone = pfull + PS;
   uint64_t* tmem_full = pdone + 1;
   uint64_t* red_full = tmem_full + 1;
@@ -189,16 +189,16 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
+      // The packed K slice of this CTA's 128 weight rows, now (weights are static): ONE box of [128 rows][PS k-blocks] -- rows of
+      // PS * 32 B (4-bit) are whole 128-byte lines at PS = 4, where per-k-block boxes of 32-byte rows cost the TMA unit and DRAM a
+      // request per row and k-block (measured: the dominant part of +2.7 us per launch against the fp16-copy kernel).
       const int wpk = kBlockK * BITS / 32;  // uint32 words of one packed row of a k-block
-      for (int i = 0; i < nkb; ++i) {       // every packed k-block of the slice, now: weights are static
-        mbar_expect_tx(&pfull[i], (uint32_t)kPBytes);
-        uint8_t* dst = sP + (size_t)i * kPBytes;
-        if (p.q_half_rows) {  // tile rows (2i, 2i+1) = (gate_i, up_i): 64 rows of each half of the [gate ; up] matrix
-          tma_load_2d(dst, &tmP, &pfull[i], (kb0 + i) * wpk, n0 / 2);
-          tma_load_2d(dst + kPBytes / 2, &tmP, &pfull[i], (kb0 + i) * wpk, p.q_half_rows + n0 / 2);
-        } else {
-          tma_load_2d(dst, &tmP, &pfull[i], (kb0 + i) * wpk, n0);
-        }
+      mbar_expect_tx(&pfull[0], (uint32_t)(PS * kPBytes));
+      if (p.q_half_rows) {  // tile rows (2i, 2i+1) = (gate_i, up_i): 64 rows of each half of the [gate ; up] matrix
+        tma_load_2d(sP, &tmP, &pfull[0], kb0 * wpk, n0 / 2);
+        tma_load_2d(sP + (size_t)PS * kPBytes / 2, &tmP, &pfull[0], kb0 * wpk, p.q_half_rows + n0 / 2);
+      } else {
+        tma_load_2d(sP, &tmP, &pfull[0], kb0 * wpk, n0);
       }
       sk_wait_dependency_tma(p);
       for (int i = 0; i < nkb; ++i) {
@@ -264,7 +264,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     const uint32_t arow0 = smem_u32(sA) + (uint32_t)row * 128u;
-    const uint32_t prow0 = smem_u32(sP) + (uint32_t)prow * (uint32_t)kPRow;
+    const uint32_t prow0 = smem_u32(sP) + (uint32_t)prow * (uint32_t)(PS * kPRow);  // row pitch = the whole slice: PS k-blocks
     // Every k-block is dequantised NOW, ahead of the dependency on the predecessor kernel: the first AS blocks straight into the A
     // ring, the rest PARKED in spare TMEM columns (thread = TMEM lane, 32 columns of packed fp16 pairs per block; written and read
     // back by the same thread with tcgen05.st / tcgen05.ld, so no operand layout is involved).  Once the MMAs release an A stage,
@@ -273,11 +273,11 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     for (int i = 0; i < nkb; ++i) {
       float scn[2], bin[2];
       if (i + 1 < nkb) load_sb(kb0 + i + 1, scn, bin);  // next k-block's scale / bias: in flight behind this block's work
-      mbar_wait(&pfull[i], 0);
+      if (i == 0) mbar_wait(&pfull[0], 0);
       uint32_t v[32];
       const float* fold = p.q_fold ? fold_s + i * kBlockK : nullptr;
-      if (p.q_sdt == Q3TTS_F32) dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPBytes, sc, bi, fold, v);
-      else dequant_row<BITS, false>(prow0 + (uint32_t)i * (uint32_t)kPBytes, sc, bi, fold, v);
+      if (p.q_sdt == Q3TTS_F32) dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPRow, sc, bi, fold, v);
+      else dequant_row<BITS, false>(prow0 + (uint32_t)i * (uint32_t)kPRow, sc, bi, fold, v);
       if (i < AS) {
         store_row_swizzled(arow0 + (uint32_t)i * (uint32_t)kWBytes, row & 7, v);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
@@ -291,6 +291,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     if (nkb > AS) tmem_st_wait();
     __syncwarp();
     if (lane == 0) mbar_arrive(pdone);  // this warp has read its last packed byte
+    if (threadIdx.x == 96) SK_STAMP(14);
     for (int i = AS; i < nkb; ++i) {
       const int s = i % AS;
       uint32_t v[32];
@@ -303,6 +304,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       if (lane == 0) mbar_arrive(&afull[s]);
     }
     sk_wait_dependency_warp(p);  // residual rows and the activation rows were written by earlier kernels
+    if (threadIdx.x == 96) SK_STAMP(15);
     if (p.rms_x) sk_row_factors(p, rowscale_s, rank);
     if (p.split > 1) cluster_wait_acquire();  // A: every peer CTA is resident, its mbarriers initialised
     mbar_wait(tmem_full, 0);
@@ -358,7 +360,8 @@ SkqPlan plan(const TcGemm& g) {
   int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);
   s.tmem_cols = 32;
   while (s.tmem_cols < cols) s.tmem_cols <<= 1;
-  s.ok = s.smem <= 220 * 1024 && s.tmem_cols <= 512;
+  // the packed slice is one TMA box: <= 256 elements in the inner dimension
+  s.ok = s.smem <= 220 * 1024 && s.tmem_cols <= 512 && s.nkb_max * (kBlockK * g.q_bits / 32) <= 256;
   return s;
 }
 
@@ -428,7 +431,7 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   p.q_xstages = s.x_stages; p.q_xown = s.x_own;
   p.q_half_rows = g.q_halves ? g.N / 2 : 0;
 
-  const uint32_t wpk = (uint32_t)(kBlockK * g.q_bits / 32);
+  const uint32_t wpk = (uint32_t)(kBlockK * g.q_bits / 32) * (uint32_t)s.nkb_max;  // one box = the whole K slice of a row
   const CUtensorMap mp = make_packed_map(g.q_w, (uint64_t)g.cin * g.q_bits / 32, (uint64_t)g.N, wpk, (uint32_t)(g.q_halves ? kRowsW / 2 : kRowsW));
   const uint64_t xdims[2] = {(uint64_t)g.cin, (uint64_t)p.M};
   const uint64_t xstr[1] = {(uint64_t)g.cin * 2};

@@ -254,6 +254,22 @@ class Engine:
                                         rest.ctypes.data_as(A.p_f32), C.byref(dim)), self._h)
         return first.reshape(B, F, -1), rest.reshape(B, F, -1)
 
+    # ---- ICL reference-audio encoder
+    def encode_reference_audio(self, samples, want_latent: bool = False):
+        """24 kHz mono float32 samples -> codes int32 [16, T] (the `ref_codes` layout), or None without encoder weights
+        (`Qwen3TTSPipeline.encodeReferenceAudio`).  want_latent: also return the quantiser input [T, hidden]."""
+        if not self.info.has_audio_encoder:
+            return (None, None) if want_latent else None
+        a = np.ascontiguousarray(np.asarray(samples, dtype=np.float32).reshape(-1))
+        cap = (a.size + 1919) // 1920 + 2
+        codes = np.zeros((64, cap), dtype=np.int32)
+        lat = np.zeros((cap, self.info.audio_encoder_hidden), dtype=np.float32) if want_latent else None
+        n, nq = A.i32(0), A.i32(0)
+        A.check(A.lib().q3tts_encode_reference_audio(self._h, a.ctypes.data_as(A.p_f32), a.size, codes.ctypes.data_as(A.p_i32), cap, C.byref(n), C.byref(nq),
+                                                     lat.ctypes.data_as(A.p_f32) if want_latent else None), self._h)
+        out = codes.reshape(-1)[: nq.value * n.value].reshape(nq.value, n.value).copy()
+        return (out, lat[: n.value].copy()) if want_latent else out
+
     # ---- fused
     def generate_pcm(self, req: GenRequest, mode: int = A.DECODE_WHOLE):
         cap = max(req.max_tokens, 1) * self.info.codec_total_upsample

@@ -231,7 +231,7 @@ class Qwen3TTSPipeline:
 
     @property
     def supports_icl(self):
-        return False  # reference-audio ENCODER is a "next" row; pre-encoded reference codes are accepted
+        return bool(self.info.has_audio_encoder)  # audioEncoder != nil (Qwen3TTSPipeline.swift:87-89)
 
     @property
     def model_type(self):
@@ -373,13 +373,15 @@ class Qwen3TTSPipeline:
             on_progress(1.0)
         return np.concatenate(all_s) if all_s else np.zeros(0, np.float32)
 
-    # ---- voice cloning inputs (:906-945): encoders are "next" rows; the API reports them as unavailable like the
-    # reference does when the weights are absent (returns nil)
+    # ---- voice cloning inputs (:906-945).  The ICL reference-audio encoder runs on the device when the checkpoint carries it; the
+    # ECAPA speaker encoder is not built: like the reference without `speaker_encoder.*` weights, the call returns nil
     def extract_speaker_embedding(self, audio_samples):
         return None
 
     def encode_reference_audio(self, audio_samples):
-        return None
+        """[[Int32]] [num_quantizers][time] of 24 kHz reference audio, or None without an encoder (Qwen3TTSPipeline.swift:924-945)."""
+        codes = self.engine.encode_reference_audio(audio_samples)
+        return None if codes is None or codes.size == 0 else codes
 
     def clear_cache(self):  # :951-956
         self.engine.clear_cache()
