@@ -120,7 +120,10 @@ __device__ __forceinline__ void store_row_swizzled(uint32_t arow, int rsw, const
   for (int j = 0; j < 8; ++j) sts_v4(arow + (uint32_t)((j ^ rsw) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
 }
 
-template <int BITS, bool SWIGLU>
+// TS = true: the dequantised weight tile is the MMA's A operand straight from TENSOR MEMORY (every k-block is written there once by
+// its row's thread, tcgen05.st; no shared-memory A ring, no re-staging behind the MMAs); TS = false: A through a 2-3 stage
+// shared-memory ring in the 128-byte-swizzled layout, later k-blocks parked in TMEM and re-staged as stages free up.
+template <int BITS, bool SWIGLU, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmX, const SkParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -128,7 +131,8 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   constexpr int kPBytes = kRowsW * kBlockK * BITS / 8;   // packed bytes of one k-block: 4 KB / 8 KB
   constexpr int kPRow = kBlockK * BITS / 8;              // per row and k-block: 32 B / 64 B
   const int x_bytes = p.m_pad * kBlockK * 2;
-  const int AS = p.stages, PS = p.q_pstages, XS = p.q_xstages, XOWN = p.q_xown;
+  const int AS = p.stages, PS = p.q_pstages, XS = p.q_xstages, XOWN = p.q_xown;  // TS: AS == 0 (no shared-memory A ring)
+  const int NA = AS > 0 ? AS : 1;                                                // barrier slots of the A hand-off
   uint8_t* sA = smem;                                            // [AS][128 rows][128 B] swizzled fp16 weight tiles
   uint8_t* sX = sA + (size_t)AS * kWBytes;                        // [XOWN][m_pad rows][128 B] activation tiles (TMA, swizzled)
   uint8_t* sP = sX + (size_t)XOWN * x_bytes;                      // [PS][128 rows][kPRow] packed weight k-blocks (TMA, dense)
@@ -138,8 +142,8 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   // flight at once after the dependency resolves, instead of two at a time behind the MMAs (measured: +0.9 us per launch).
   auto x_stage = [&](int xs) -> uint8_t* { return xs < XOWN ? sX + (size_t)xs * x_bytes : sP + (size_t)(xs - XOWN) * x_bytes; };
   uint64_t* afull = reinterpret_cast<uint64_t*>(red + (size_t)kRowsW * p.m_pad);
-  uint64_t* aempty = afull + AS;
-  uint64_t* xfull = aempty + AS;
+  uint64_t* aempty = afull + NA;
+  uint64_t* xfull = aempty + NA;
   uint64_t* xempty = xfull + XS;
   uint64_t* pfull = xempty + XS;   // [0] only: the whole packed slice arrives with one (two: gate | up) tensor load(s)
   uint64_t* pdone = pfull + PS;
@@ -166,7 +170,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   if (threadIdx.x == 0) {
     if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + 0] = sk_globaltimer();
     SK_STAMP(1);
-    for (int s = 0; s < AS; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
+    for (int s = 0; s < NA; ++s) { mbar_init(&afull[s], 4); mbar_init(&aempty[s], 1); }
     for (int s = 0; s < XS; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
     for (int s = 0; s < PS; ++s) mbar_init(&pfull[s], 1);
     mbar_init(pdone, 4);
@@ -214,17 +218,27 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     if (lane == 0) {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.m_pad >> 3) << 17) | ((uint32_t)(kRowsW >> 4) << 24);
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % AS, xs = i % XS;
-        mbar_wait(&afull[s], (uint32_t)((i / AS) & 1));
+        const int s = TS ? 0 : i % NA, xs = i % XS;
+        if (TS) {
+          if (i == 0) mbar_wait(&afull[0], 0);  // every k-block of A sits in tensor memory
+        } else {
+          mbar_wait(&afull[s], (uint32_t)((i / AS) & 1));
+        }
         mbar_wait(&xfull[xs], (uint32_t)((i / XS) & 1));
         tc_fence_after();
         if (i == 0) SK_STAMP(3);
-        const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kWBytes));
         const uint64_t bd = umma_desc(smem_u32(x_stage(xs)));
+        if (TS) {
+          const uint32_t at = tmem_base + (uint32_t)p.m_pad + (uint32_t)i * 32u;  // k-block i: 32 columns = 64 fp16 per lane
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
-        umma_commit(&aempty[s]);
+          for (int k = 0; k < kBlockK / 16; ++k) umma_f16_ts(tmem_base, at + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+        } else {
+          const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kWBytes));
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit(&aempty[s]);
+        }
         if (i + XS < nkb) umma_commit(&xempty[xs]);
       }
       umma_commit(tmem_full);
@@ -270,6 +284,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     // back by the same thread with tcgen05.st / tcgen05.ld, so no operand layout is involved).  Once the MMAs release an A stage,
     // re-staging a parked block is one TMEM load + eight shared-memory stores instead of a dequantisation on the critical path.
     const uint32_t park0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.m_pad;
+    const int n_direct = TS ? 0 : AS;  // k-blocks written straight into the shared-memory A ring
     for (int i = 0; i < nkb; ++i) {
       float scn[2], bin[2];
       if (i + 1 < nkb) load_sb(kb0 + i + 1, scn, bin);  // next k-block's scale / bias: in flight behind this block's work
@@ -278,30 +293,36 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       const float* fold = p.q_fold ? fold_s + i * kBlockK : nullptr;
       if (p.q_sdt == Q3TTS_F32) dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPRow, sc, bi, fold, v);
       else dequant_row<BITS, false>(prow0 + (uint32_t)i * (uint32_t)kPRow, sc, bi, fold, v);
-      if (i < AS) {
+      if (i < n_direct) {
         store_row_swizzled(arow0 + (uint32_t)i * (uint32_t)kWBytes, row & 7, v);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core's reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&afull[i]);
       } else {
-        tmem_st32(park0 + (uint32_t)(i - AS) * 32u, v);
+        tmem_st32(park0 + (uint32_t)(i - n_direct) * 32u, v);  // TS: column block i; SS: parked block i - AS
       }
       if (i + 1 < nkb) { sc[0] = scn[0]; sc[1] = scn[1]; bi[0] = bin[0]; bi[1] = bin[1]; }
     }
-    if (nkb > AS) tmem_st_wait();
+    if (nkb > n_direct) tmem_st_wait();
+    if (TS) tc_fence_before();  // the tensor-memory writes are ordered before the barrier the MMA thread waits on
     __syncwarp();
-    if (lane == 0) mbar_arrive(pdone);  // this warp has read its last packed byte
+    if (lane == 0) {
+      mbar_arrive(pdone);  // this warp has read its last packed byte
+      if (TS) mbar_arrive(&afull[0]);
+    }
     if (threadIdx.x == 96) SK_STAMP(14);
-    for (int i = AS; i < nkb; ++i) {
-      const int s = i % AS;
-      uint32_t v[32];
-      tmem_ld32_issue(park0 + (uint32_t)(i - AS) * 32u, v);
-      mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read A[s]
-      tmem_ld_wait32(v);
-      store_row_swizzled(arow0 + (uint32_t)s * (uint32_t)kWBytes, row & 7, v);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&afull[s]);
+    if (!TS) {
+      for (int i = AS; i < nkb; ++i) {
+        const int s = i % NA;
+        uint32_t v[32];
+        tmem_ld32_issue(park0 + (uint32_t)(i - AS) * 32u, v);
+        mbar_wait(&aempty[s], (uint32_t)(((i / AS) - 1) & 1));  // the MMAs of k-block i - AS have read A[s]
+        tmem_ld_wait32(v);
+        store_row_swizzled(arow0 + (uint32_t)s * (uint32_t)kWBytes, row & 7, v);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&afull[s]);
+      }
     }
     sk_wait_dependency_warp(p);  // residual rows and the activation rows were written by earlier kernels
     if (threadIdx.x == 96) SK_STAMP(15);
@@ -337,6 +358,11 @@ struct SkqPlan {
   bool ok;
 };
 
+bool ts_mode() {
+  static const bool on = env_int("Q3TTS_SKQ_TS", 1) != 0;
+  return on;
+}
+
 SkqPlan plan(const TcGemm& g) {
   static const int max_split = std::max(1, std::min(16, env_int("Q3TTS_SK_MAX_SPLIT", 8)));
   static const int cta_target = env_int("Q3TTS_SK_CTAS", 200);
@@ -350,14 +376,20 @@ SkqPlan plan(const TcGemm& g) {
   s.nkb_max = (s.num_kb + s.split - 1) / s.split;
   const int x_bytes = s.m_pad * kBlockK * 2, red_bytes = kRowsW * s.m_pad * 4;
   const int p_bytes = kRowsW * kBlockK * g.q_bits / 8;
-  s.a_stages = std::min(s.nkb_max, s.m_pad <= 32 ? 3 : 2);
-  while (s.a_stages * (kWBytes + x_bytes) < red_bytes) ++s.a_stages;  // the rings double as the outgoing staging buffer
-  s.x_own = s.a_stages;                                                                  // activation stages of their own ...
+  if (ts_mode()) {  // A from tensor memory: no A ring; the activation stages + the (dead) packed region double as the outgoing staging buffer
+    s.a_stages = 0;
+    s.x_own = 2;
+    while (s.x_own * x_bytes + s.nkb_max * p_bytes < red_bytes) ++s.x_own;
+  } else {
+    s.a_stages = std::min(s.nkb_max, s.m_pad <= 32 ? 3 : 2);
+    while (s.a_stages * (kWBytes + x_bytes) < red_bytes) ++s.a_stages;  // the rings double as the outgoing staging buffer
+    s.x_own = s.a_stages;                                                                // activation stages of their own ...
+  }
   s.x_stages = std::min(s.nkb_max, s.x_own + (s.nkb_max * p_bytes) / x_bytes);           // ... plus those that alias the packed region
   s.smem = (size_t)s.a_stages * kWBytes + (size_t)s.x_own * x_bytes + (size_t)s.nkb_max * p_bytes + red_bytes + 1024 +
-           (size_t)(2 * s.a_stages + 2 * s.x_stages + s.nkb_max + 4) * 8 + 16 + kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
+           (size_t)(2 * std::max(1, s.a_stages) + 2 * s.x_stages + s.nkb_max + 4) * 8 + 16 + kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
   // TMEM: the fp32 accumulator [128 lanes x m_pad columns] + 32 columns per k-block parked beyond the A ring
-  int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);
+  int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);  // TS: every k-block lives in tensor memory
   s.tmem_cols = 32;
   while (s.tmem_cols < cols) s.tmem_cols <<= 1;
   // the packed slice is one TMA box: <= 256 elements in the inner dimension
@@ -366,9 +398,13 @@ SkqPlan plan(const TcGemm& g) {
 }
 
 using SkqKernel = void (*)(const CUtensorMap, const CUtensorMap, const SkParams);
-SkqKernel pick_kernel(int bits, int swiglu) {
-  if (bits == 4) return swiglu ? tc_skinny_q_kernel<4, true> : tc_skinny_q_kernel<4, false>;
-  return swiglu ? tc_skinny_q_kernel<8, true> : tc_skinny_q_kernel<8, false>;
+SkqKernel pick_kernel(int bits, int swiglu, bool ts) {
+  if (ts) {
+    if (bits == 4) return swiglu ? tc_skinny_q_kernel<4, true, true> : tc_skinny_q_kernel<4, false, true>;
+    return swiglu ? tc_skinny_q_kernel<8, true, true> : tc_skinny_q_kernel<8, false, true>;
+  }
+  if (bits == 4) return swiglu ? tc_skinny_q_kernel<4, true, false> : tc_skinny_q_kernel<4, false, false>;
+  return swiglu ? tc_skinny_q_kernel<8, true, false> : tc_skinny_q_kernel<8, false, false>;
 }
 
 CUtensorMap make_packed_map(const void* base, uint64_t words_per_row, uint64_t rows, uint32_t box_words, uint32_t box_rows) {
@@ -402,10 +438,11 @@ bool tc_skinny_q_supported(const TcGemm& g) {
 void init_tc_skinny_q() {
   tc_resolve_encode();
   for (int bits : {4, 8})
-    for (int sw : {0, 1}) {
-      Q3_CUDA(cudaFuncSetAttribute(pick_kernel(bits, sw), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-      Q3_CUDA(cudaFuncSetAttribute(pick_kernel(bits, sw), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    }
+    for (int sw : {0, 1})
+      for (bool ts : {false, true}) {
+        Q3_CUDA(cudaFuncSetAttribute(pick_kernel(bits, sw, ts), cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        Q3_CUDA(cudaFuncSetAttribute(pick_kernel(bits, sw, ts), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      }
 }
 
 void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
@@ -457,7 +494,7 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  Q3_CUDA(cudaLaunchKernelEx(&cfg, pick_kernel(g.q_bits, g.swiglu), mp, mx, p));
+  Q3_CUDA(cudaLaunchKernelEx(&cfg, pick_kernel(g.q_bits, g.swiglu, ts_mode()), mp, mx, p));
   c.tick_chained();
 }
 

@@ -56,13 +56,18 @@ struct TcParams {
   // [t*dil, t*dil + 128) of it through a UMMA descriptor whose start address is shifted by whole 128-byte rows -- instead of one
   // shifted 128-row TMA box per tap (ntap x the L2 -> SM traffic for the activations).
   int halo, a_stages, b_stages, halo_rows;
+  // residual ring (fp16 residual stream, classic schedule): the [128 rows x bn] residual tile of a tile is fetched by the TMA producer
+  // res_stages tiles ahead of the epilogue that adds it.  Per-thread residual loads kept ONE 2 KB batch per epilogue warp in flight
+  // (12 warps x 2 KB / ~1.2 us of DRAM latency = 20 GB/s per SM -- exactly what the 1x1 convolutions of the vocoder ran at, 30-45 %
+  // of their HBM roofline); through the ring the bytes in flight are res_stages whole tiles.
+  int res_stages, res_bytes;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float v) { return v / (1.0f + expf(-v)); }
 
 __global__ void __launch_bounds__(kMaxThreads, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmR, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);  // SWIZZLE_128B: 1024-B aligned
   const int b_bytes = p.bn * kBlockK * 2;
@@ -71,11 +76,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)a_st * a_stage_bytes;
   // classic: full[s] / empty[s] guard stage s of both rings.  halo: full/empty[0, a_st) guard the A ring, [a_st, a_st + b_st) the B ring
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + (size_t)b_st * b_bytes);
+  uint8_t* sR = sB + (size_t)b_st * b_bytes;   // [res_stages][128 rows][bn] fp16 residual tiles (dense rows, no swizzle)
+  uint64_t* full = reinterpret_cast<uint64_t*>(sR + (size_t)p.res_stages * p.res_bytes);
   uint64_t* empty = full + (p.halo ? a_st + b_st : p.stages);
   uint64_t* tmem_full = empty + (p.halo ? a_st + b_st : p.stages);   // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* rfull = tmem_empty + 2;         // [res_stages]
+  uint64_t* rempty = rfull + p.res_stages;  // [res_stages]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + p.res_stages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.ntap * p.kb_per_tap;
@@ -103,6 +111,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int s = 0; s < (p.halo ? a_st + b_st : p.stages); ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 4 * p.epi_sets); mbar_init(&tmem_empty[1], 4 * p.epi_sets);  // one arrival per epilogue warp
+    for (int s = 0; s < p.res_stages; ++s) { mbar_init(&rfull[s], 1); mbar_init(&rempty[s], 4 * p.epi_sets); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -156,10 +165,34 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {
       int it = 0;  // k-blocks issued by this CTA so far (the ring does not care about tile boundaries)
+      int rt = 0;  // residual tiles issued so far (tile sequence numbers of this CTA)
+      // residual tiles of this CTA's tiles [rt, upto].  blocking: wait for a stage's previous tenant to be consumed (only ever for the
+      // tile the CTA is about to work on: its predecessors' loads are all issued, so their epilogues will run); otherwise stop at the
+      // first stage that is still occupied -- the look-ahead must never stall the operand stream
+      auto issue_residuals = [&](int upto, bool blocking) {
+        for (; rt <= upto; ++rt) {
+          const long long tl = (long long)blockIdx.x + (long long)rt * gridDim.x;
+          if (tl >= total_tiles) { rt = 1 << 30; break; }
+          const int mt = (int)(tl / p.tiles_n), nt = (int)(tl - (long long)mt * p.tiles_n);
+          const int bi = mt / p.tiles_per_batch, tt0 = (mt - bi * p.tiles_per_batch) * kTileM;
+          const int rs = rt % p.res_stages;
+          if (rt >= p.res_stages) {
+            const uint32_t par = (uint32_t)(((rt / p.res_stages) - 1) & 1);
+            if (blocking) mbar_wait(&rempty[rs], par);
+            else if (!mbar_try_wait(&rempty[rs], par)) break;
+          }
+          mbar_expect_tx(&rfull[rs], (uint32_t)p.res_bytes);
+          tma_load_3d(sR + (size_t)rs * p.res_bytes, &tmR, &rfull[rs], nt * p.bn, tt0, bi);
+        }
+      };
       for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
         const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
         const int rot = p.k_rotate ? (int)(((unsigned)n_tile * 5u + (unsigned)m_tile * 3u) % (unsigned)num_kb) : 0;
+        if (p.res_stages && ti > 0 && rt < (1 << 30)) {
+          issue_residuals(ti, true);
+          if (rt < (1 << 30)) issue_residuals(ti + p.res_stages - 1, false);
+        }
         int pre = 0;
         if (ti == 0) {
           pre = num_kb < p.stages ? num_kb : p.stages;
@@ -170,6 +203,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tma_load_2d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0);
           }
           pdl_wait();
+          if (p.res_stages) issue_residuals(p.res_stages - 1, true);  // the residual stream was written by the predecessor: after the wait
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % p.stages, ph = (it / p.stages) & 1;
@@ -247,6 +281,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = t0 + row;
     const bool row_ok = t < p.T;
     const size_t m = (size_t)bidx * p.T + t;
+    const int rs = p.res_stages ? ti % p.res_stages : 0;
+    if (p.res_stages) mbar_wait(&rfull[rs], (uint32_t)((ti / p.res_stages) & 1));  // this tile's residual rows are in shared memory
     mbar_wait(&tmem_full[acc_i], (uint32_t)(use & 1));
     tc_fence_after();
     for (int c = ((warp - 2) >> 2) * 32; c < p.bn; c += 32 * p.epi_sets) {
@@ -263,6 +299,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (4 * j < width0) rres[j] = *reinterpret_cast<const float4*>(rp + 4 * j);
+      } else if (p.res_stages && live) {  // residual ring: row `row` of the staged [128][bn] tile, columns c .. c + 31
+        const uint4* rp = reinterpret_cast<const uint4*>(sR + (size_t)rs * p.res_bytes + ((size_t)row * p.bn + (size_t)c) * 2);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (8 * j < width0) reinterpret_cast<uint4*>(rres)[j] = rp[j];
       } else if (p.res16 && live) {  // fp16 residual stream: 8 halves per 16-byte load, widened once they have arrived
         const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.ld_res + ob0);
 #pragma unroll
@@ -402,6 +443,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&tmem_empty[acc_i]);
+    if (p.res_stages && lane == 0) mbar_arrive(&rempty[rs]);  // ... and its rows of the residual tile
     }  // tile loop
   }
   tc_fence_before();
@@ -531,6 +573,14 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.row_scale = g.row_scale;
   p.k_rotate = g.k_rotate;
   p.res16 = g.res16; p.outr16 = g.outr16;
+  // residual ring: persistent classic schedule, fp16 residual stream, no SwiGLU column pairing
+  static const bool res_ring_on = [] { const char* e = getenv("Q3TTS_TC_RES_RING"); return !(e && atoi(e) == 0); }();
+  p.res_stages = 0; p.res_bytes = kTileM * p.bn * 2;
+  if (res_ring_on && g.res16 && persistent && !p.halo && !g.swiglu && p.bn % 8 == 0 && g.N % p.bn == 0) {
+    int rs = std::max(1, std::min(4, (ring_budget / 2) / p.res_bytes));
+    int st = (ring_budget - rs * p.res_bytes) / stage_bytes;
+    if (st >= 2) { p.res_stages = rs; p.stages = std::min(p.stages, st); ring_bytes = p.stages * stage_bytes; }
+  }
   Q3_CHECK(!(g.res && g.res16) && !(g.res16 && g.ld_res % 8) && !(g.outr16 && g.ld32 % 8), Q3TTS_ERR_INVALID_ARG, "tc_gemm: bad fp16 residual arguments");
 
   const uint64_t adims[3] = {(uint64_t)g.cin, (uint64_t)g.T, (uint64_t)g.Bt};
@@ -542,11 +592,21 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)p.bn};
   const CUtensorMap mb = tc_make_map(g.w, 2, bdims, bstr, bbox);
 
-  const size_t smem = (size_t)ring_bytes + 1024 + 64 * 8;
+  CUtensorMap mr = mb;  // unused unless the residual ring is on
+  if (p.res_stages) {
+    const uint64_t rdims[3] = {(uint64_t)g.ld_res, (uint64_t)g.T, (uint64_t)g.Bt};
+    const uint64_t rstr[2] = {(uint64_t)g.ld_res * 2, (uint64_t)g.T * g.ld_res * 2};
+    const uint32_t rbox[3] = {(uint32_t)p.bn, (uint32_t)kTileM, 1};
+    const uint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(&mr, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(g.res16), rdims, rstr, rbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled (residual tiles) failed with CUresult %d", (int)r);
+  }
+  const size_t smem = (size_t)ring_bytes + (size_t)p.res_stages * p.res_bytes + 1024 + 64 * 8;
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
-  Q3_CHECK(2 * (p.halo ? p.a_stages + p.b_stages : p.stages) + 5 <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
+  Q3_CHECK(2 * (p.halo ? p.a_stages + p.b_stages : p.stages) + 5 + 2 * p.res_stages <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
   dim3 grid((unsigned)(persistent ? std::min<long long>(tiles, resident) : tiles));
-  launch_kernel_pdl(tc_gemm_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, mb, p);
+  launch_kernel_pdl(tc_gemm_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, mb, mr, p);
   c.tick();
 }
 
