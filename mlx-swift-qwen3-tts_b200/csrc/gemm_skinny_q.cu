@@ -45,10 +45,37 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {  // round-t
   asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
 }
-__device__ __forceinline__ float ld_scale(const void* p, size_t i, int sdt) {
-  if (sdt == Q3TTS_F32) return __ldg(reinterpret_cast<const float*>(p) + i);
-  const unsigned short raw = __ldg(reinterpret_cast<const unsigned short*>(p) + i);
-  return sdt == Q3TTS_F16 ? __half2float(__ushort_as_half(raw)) : __uint_as_float((uint32_t)raw << 16);
+// Scales and biases of `ng` consecutive groups of one weight row -> column `my_sb` of the [2 * group + (0: scale, 1: bias)][128] table.
+// SDT: 0 = bf16, 1 = f16, 2 = f32.  Batches of 8 groups: sixteen independent loads in flight, then the conversions and stores.
+template <int SDT>
+__device__ __forceinline__ void fill_sb_table(float* my_sb, const void* scales, const void* biases, size_t g_first, int ng, bool live) {
+  for (int j0 = 0; j0 < ng; j0 += 8) {
+    uint32_t rs[8], rb[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      rs[u] = rb[u] = 0u;
+      if (live && j0 + u < ng) {
+        if constexpr (SDT == 2) {
+          rs[u] = __ldg(reinterpret_cast<const uint32_t*>(scales) + g_first + j0 + u);
+          rb[u] = __ldg(reinterpret_cast<const uint32_t*>(biases) + g_first + j0 + u);
+        } else {
+          rs[u] = __ldg(reinterpret_cast<const unsigned short*>(scales) + g_first + j0 + u);
+          rb[u] = __ldg(reinterpret_cast<const unsigned short*>(biases) + g_first + j0 + u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (j0 + u < ng) {
+        float fs, fb;
+        if constexpr (SDT == 2) { fs = __uint_as_float(rs[u]); fb = __uint_as_float(rb[u]); }
+        else if constexpr (SDT == 1) { fs = __half2float(__ushort_as_half((unsigned short)rs[u])); fb = __half2float(__ushort_as_half((unsigned short)rb[u])); }
+        else { fs = __uint_as_float(rs[u] << 16); fb = __uint_as_float(rb[u] << 16); }
+        my_sb[(2 * (j0 + u)) * kRowsW] = fs;
+        my_sb[(2 * (j0 + u) + 1) * kRowsW] = fb;
+      }
+    }
+  }
 }
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -154,6 +181,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   // 16-byte aligned whatever the barrier count: rowscale [mc <= 128], then the [PS * 64] slice of the folded norm weight
   float* rowscale_s = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
   float* fold_s = rowscale_s + kRowsW;
+  float* sb_s = fold_s + PS * kBlockK;  // [2 * q_ngm][128] scale / bias table of the CTA's K slice (thread = row owns a column)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;
@@ -255,21 +283,32 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     const int gpk = p.q_group >= kBlockK ? 1 : kBlockK / p.q_group;          // groups per k-block: 1 or 2
     const int gdiv = p.q_group >= kBlockK ? p.q_group / kBlockK : 1;         // k-blocks per group: 1 or 2
     const size_t srow = (size_t)grow * (size_t)(p.K / p.q_group);
-    auto load_sb = [&](int kb, float (&sc)[2], float (&bi)[2]) {
-      if (!row_ok) { sc[0] = sc[1] = bi[0] = bi[1] = 0.f; return; }
-      const size_t g0 = srow + (size_t)((kb * gpk) / gdiv);
-      sc[0] = ld_scale(p.q_scales, g0, p.q_sdt);
-      bi[0] = ld_scale(p.q_biases, g0, p.q_sdt);
+    // Scales and biases of this row for EVERY k-block of the CTA's K slice, requested up front: all the loads of a batch of 8 groups are
+    // in flight together and land in this thread's column of a shared-memory table.  (One k-block ahead, as the first version did, left
+    // two dependent DRAM round trips in front of the first block and one L2 round trip inside every later one: measured 2000 of the 4600
+    // cycles before the first block and 850 of the 1950 cycles of each later block.)
+    const int g_lo = (kb0 * gpk) / gdiv;
+    const int ng = nkb > 0 ? ((kb1 - 1) * gpk + gpk - 1) / gdiv - g_lo + 1 : 0;
+    float* my_sb = sb_s + row;  // [2 * group + (0: scale, 1: bias)][128 rows]
+    {
+      const size_t g_first = srow + (size_t)g_lo;
+      const bool live = row_ok && !(p.q_dbg & 2);
+      if (p.q_sdt == Q3TTS_F32) fill_sb_table<2>(my_sb, p.q_scales, p.q_biases, g_first, ng, live);
+      else if (p.q_sdt == Q3TTS_F16) fill_sb_table<1>(my_sb, p.q_scales, p.q_biases, g_first, ng, live);
+      else fill_sb_table<0>(my_sb, p.q_scales, p.q_biases, g_first, ng, live);
+    }
+    auto load_sb = [&](int kb, float (&sc)[2], float (&bi)[2]) {  // this thread's own table column: no barrier needed
+      const int gi = (kb * gpk) / gdiv - g_lo;
+      sc[0] = my_sb[(2 * gi) * kRowsW];
+      bi[0] = my_sb[(2 * gi + 1) * kRowsW];
       if (gpk == 2) {
-        sc[1] = ld_scale(p.q_scales, g0 + 1, p.q_sdt);
-        bi[1] = ld_scale(p.q_biases, g0 + 1, p.q_sdt);
+        sc[1] = my_sb[(2 * gi + 2) * kRowsW];
+        bi[1] = my_sb[(2 * gi + 3) * kRowsW];
       } else {
         sc[1] = sc[0];
         bi[1] = bi[0];
       }
     };
-    float sc[2], bi[2];
-    load_sb(kb0, sc, bi);  // in flight while the fold slice is staged
     if (p.q_fold) {
       for (int e = (int)threadIdx.x - 64; e < nkb * kBlockK; e += 128) {
         const int k = kb0 * kBlockK + e;
@@ -286,9 +325,13 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     const uint32_t park0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.m_pad;
     const int n_direct = TS ? 0 : AS;  // k-blocks written straight into the shared-memory A ring
     for (int i = 0; i < nkb; ++i) {
-      float scn[2], bin[2];
-      if (i + 1 < nkb) load_sb(kb0 + i + 1, scn, bin);  // next k-block's scale / bias: in flight behind this block's work
-      if (i == 0) mbar_wait(&pfull[0], 0);
+      float sc[2], bi[2];
+      load_sb(kb0 + i, sc, bi);
+      if (i == 0) {
+        if (threadIdx.x == 96 && (p.q_dbg & 1)) SK_STAMP(10);
+        mbar_wait(&pfull[0], 0);
+        if (threadIdx.x == 96 && (p.q_dbg & 1)) SK_STAMP(11);
+      }
       uint32_t v[32];
       const float* fold = p.q_fold ? fold_s + i * kBlockK : nullptr;
       if (p.q_sdt == Q3TTS_F32) dequant_row<BITS, true>(prow0 + (uint32_t)i * (uint32_t)kPRow, sc, bi, fold, v);
@@ -301,7 +344,7 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       } else {
         tmem_st32(park0 + (uint32_t)(i - n_direct) * 32u, v);  // TS: column block i; SS: parked block i - AS
       }
-      if (i + 1 < nkb) { sc[0] = scn[0]; sc[1] = scn[1]; bi[0] = bin[0]; bi[1] = bin[1]; }
+      if (threadIdx.x == 96 && (p.q_dbg & 1) && i < 2) SK_STAMP(12 + i);
     }
     if (nkb > n_direct) tmem_st_wait();
     if (TS) tc_fence_before();  // the tensor-memory writes are ordered before the barrier the MMA thread waits on
@@ -353,7 +396,7 @@ int env_int(const char* name, int dflt) {
 }
 
 struct SkqPlan {
-  int m_pad, split, tiles, num_kb, nkb_max, a_stages, x_own, x_stages, tmem_cols;
+  int m_pad, split, tiles, num_kb, nkb_max, a_stages, x_own, x_stages, tmem_cols, ngm;
   size_t smem;
   bool ok;
 };
@@ -376,6 +419,8 @@ SkqPlan plan(const TcGemm& g) {
   s.nkb_max = (s.num_kb + s.split - 1) / s.split;
   const int x_bytes = s.m_pad * kBlockK * 2, red_bytes = kRowsW * s.m_pad * 4;
   const int p_bytes = kRowsW * kBlockK * g.q_bits / 8;
+  // quantisation groups a CTA's K slice can touch (scale / bias table rows)
+  s.ngm = g.q_group == 32 ? 2 * s.nkb_max : (g.q_group == 64 ? s.nkb_max : s.nkb_max / 2 + 1);
   if (ts_mode()) {  // A from tensor memory: no A ring; the activation stages + the (dead) packed region double as the outgoing staging buffer
     s.a_stages = 0;
     s.x_own = 2;
@@ -387,7 +432,7 @@ SkqPlan plan(const TcGemm& g) {
   }
   s.x_stages = std::min(s.nkb_max, s.x_own + (s.nkb_max * p_bytes) / x_bytes);           // ... plus those that alias the packed region
   s.smem = (size_t)s.a_stages * kWBytes + (size_t)s.x_own * x_bytes + (size_t)s.nkb_max * p_bytes + red_bytes + 1024 +
-           (size_t)(2 * std::max(1, s.a_stages) + 2 * s.x_stages + s.nkb_max + 4) * 8 + 16 + kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + 64;
+           (size_t)(2 * std::max(1, s.a_stages) + 2 * s.x_stages + s.nkb_max + 4) * 8 + 16 + kRowsW * 4 + (size_t)s.nkb_max * kBlockK * 4 + (size_t)2 * s.ngm * kRowsW * 4 + 64;
   // TMEM: the fp32 accumulator [128 lanes x m_pad columns] + 32 columns per k-block parked beyond the A ring
   int cols = s.m_pad + 32 * std::max(0, s.nkb_max - s.a_stages);  // TS: every k-block lives in tensor memory
   s.tmem_cols = 32;
@@ -467,6 +512,10 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   p.q_pstages = s.nkb_max;
   p.q_xstages = s.x_stages; p.q_xown = s.x_own;
   p.q_half_rows = g.q_halves ? g.N / 2 : 0;
+  {
+    static const int dbg = [] { const char* e = getenv("Q3TTS_SKQ_DBG"); return e ? atoi(e) : 0; }();
+    p.q_dbg = dbg;
+  }
 
   const uint32_t wpk = (uint32_t)(kBlockK * g.q_bits / 32) * (uint32_t)s.nkb_max;  // one box = the whole K slice of a row
   const CUtensorMap mp = make_packed_map(g.q_w, (uint64_t)g.cin * g.q_bits / 32, (uint64_t)g.N, wpk, (uint32_t)(g.q_halves ? kRowsW / 2 : kRowsW));

@@ -41,6 +41,7 @@ struct SkParams {
   int q_pstages;            // packed-tile ring depth
   int q_xstages, q_xown;    // activation stages in total / outside the (dead after dequantisation) packed region
   int q_half_rows;          // SwiGLU over a [gate ; up] matrix: rows of one half (N / 2); tile row 2i = gate i, 2i + 1 = up i.  0: plain rows
+  int q_dbg;                // measurement only (Q3TTS_SKQ_DBG): bit 0 = stamps 10-13 follow the dequantisation instead of the epilogue
 };
 
 __device__ __forceinline__ unsigned long long sk_globaltimer() {
@@ -48,6 +49,7 @@ __device__ __forceinline__ unsigned long long sk_globaltimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#define SK_STAMP_EPI(slot) do { if (!(p.q_dbg & 1)) SK_STAMP(slot); } while (0)
 #define SK_STAMP(slot)                                                                                        \
   do {                                                                                                        \
     if (p.trace) p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = (unsigned long long)clock64(); \
@@ -163,7 +165,7 @@ __device__ __forceinline__ void sk_reduce_epilogue(const SkParams& p, float* sta
     sk_load_res<16>(p, r16, lane_out ? valid0 : 0, m_base, so);
   }
   if (p.split > 1) mbar_wait(red_full, 0);  // the other K slices of MY activation rows have landed
-  if (threadIdx.x == 96) SK_STAMP(10);
+  if (threadIdx.x == 96) SK_STAMP_EPI(10);
   if (threadIdx.x == 64) {
     SK_STAMP(6);
     // tell every peer that its copy into this CTA is complete (it may retire its staging buffer / exit)
@@ -185,15 +187,15 @@ __device__ __forceinline__ void sk_reduce_epilogue(const SkParams& p, float* sta
         }
       }
     }
-    if (threadIdx.x == 96 && cb == 0) SK_STAMP(11);
+    if (threadIdx.x == 96 && cb == 0) SK_STAMP_EPI(11);
     int valid = p.M - (m_base + cb);
     valid = valid < nc ? valid : nc;
     if (!lane_out) valid = 0;
     if (cb > 0) sk_load_res<16>(p, r16, valid, m_base + cb, so);
     sk_finish<16, ACT, SWIGLU>(p, a16, r16, valid, m_base + cb, so, bias, scale, p.rms_x ? rowscale_s + cb : nullptr);
-    if (threadIdx.x == 96 && cb == 0) SK_STAMP(12);
+    if (threadIdx.x == 96 && cb == 0) SK_STAMP_EPI(12);
   }
-  if (threadIdx.x == 96) SK_STAMP(13);
+  if (threadIdx.x == 96) SK_STAMP_EPI(13);
   if (p.sig.out) {  // every global store (and every global read) of this CTA is done: hand over to the next launch
     asm volatile("bar.sync 1, 128;" ::: "memory");
     if (threadIdx.x == 64) chain_signal(p.sig.out);
