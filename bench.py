@@ -117,8 +117,9 @@ def workload_config(a, world):
     return {"workload": f"Qwen3-TTS-12Hz-{a.model} {wfmt} generateStream: {a.batch} utterances/GPU x {a.frames} frames, 8-40 text ids, stream windows 18/8+18 "
                         f"(BASELINE.json configs[1]; weights N(0, 0.02^2), norms 1)",
             "model": a.model, "bits": a.bits, "batch_per_gpu": a.batch, "frames": a.frames, "parallelism": f"request-parallel x{world}",
-            "cache": "a frame-step streams 0.93 GB of packed weights (0.6B 4-bit) + the KV rings of 64 utterances, >> L2 126 MB only for the talker "
-                     "stack (249 MB); the code predictor's 45 MB stay L2-resident by design; no explicit flush between steps (each step = 36 frame-steps)"}
+            "cache": "a frame-step walks 103 layer passes of weights (0.6B 4-bit: 0.93 GB packed = the algorithmic bytes; 3.3 GB as the fp16 operand copies the "
+                     "default GEMM mode streams) + the KV rings of 64 utterances, >> L2 126 MB for the talker stack; the code predictor's five layers "
+                     "are re-read 15x per frame and stay L2-resident by design; no explicit flush between steps (each step = 36 frame-steps)"}
 
 
 # --------------------------------------------------------------------------------------------------- CPU restatement arm
@@ -272,6 +273,8 @@ def main():
     ap.add_argument("--config4", default="on", choices=["on", "off"])
     ap.add_argument("--config3-utterances", type=int, default=512)
     ap.add_argument("--config4-clips", type=int, default=128)
+    ap.add_argument("--packed-gemm", type=int, default=0, choices=[0, 1, 2],
+                    help="q3tts_options.packed_gemm of the measured handle: 1 = packed weights dequantised inside the tcgen05 GEMM, 2 / 0 = fp16 operand copies")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,6 +282,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert world == max(1, a.gpus) or world == 1, f"WORLD_SIZE {world} != --gpus {a.gpus}"
     config = workload_config(a, max(1, a.gpus))
+    fused_mode = a.bits in (4, 8) and (a.packed_gemm == 1 or (a.packed_gemm == 0 and os.environ.get("Q3TTS_SKINNY_Q", "0") not in ("", "0")))
 
     from oracle import checkpoint
 
@@ -322,7 +326,7 @@ def main():
     torch.cuda.set_device(local_rank)
     torch.zeros(8, device="cuda").sum().item()
     torch.cuda.synchronize()
-    eng = q.Engine(ckpt_dir, device=local_rank, max_batch=a.batch, max_frames=max(64, a.frames), kv_capacity=512)
+    eng = q.Engine(ckpt_dir, device=local_rank, max_batch=a.batch, max_frames=max(64, a.frames), kv_capacity=512, packed_gemm=a.packed_gemm)
     up = eng.info.codec_total_upsample
     out_bufs = [np.zeros(a.frames * up, dtype=np.float32) for _ in range(a.batch)]
 
@@ -377,9 +381,13 @@ def main():
         iters = 20
         ms, n, nbytes = eng.profile_linear(0, a.batch, iters)
         packed = eng.info.quant_bits in (4, 8)
+        fused = fused_mode
+        streamed = nbytes  # bytes one launch set streams from HBM: the packed weights, or their fp16 copies (2 B / parameter)
+        if packed and not fused and 3 <= a.batch <= 128:
+            streamed = int(nbytes * 2.0 / (a.bits / 8.0 + 4.0 / 64.0))  # packed = bits/8 + (2+2)/64 B per parameter
         if 3 <= a.batch <= 128:
-            kname = ("tc_skinny_q_kernel (tcgen05 / TMEM split-K cluster GEMM, MLX-packed weights streamed and dequantised in-kernel)" if packed
-                     else "tc_skinny_kernel (tcgen05 / TMEM split-K cluster GEMM over the dense weights)")
+            kname = ("tc_skinny_q_kernel (tcgen05 / TMEM split-K cluster GEMM, MLX-packed weights streamed and dequantised in-kernel)" if fused
+                     else "tc_skinny_kernel (tcgen05 / TMEM split-K cluster GEMM over fp16 operand copies of the weights)")
         elif a.batch > 128:
             kname = "tc_gemm_kernel (128-row-tile tcgen05 GEMM)"
         else:
@@ -394,7 +402,7 @@ def main():
         roof = {"bound": "hbm", "kernel": kname + f"; the {n // iters} linear launches of one talker decode step at m = {a.batch} rows, replayed as a CUDA graph",
                 "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": traffic, "traffic_key": key,
                 "traffic_over_algorithmic": (traffic / alg) if traffic else None, "peak_source": src, "launches_timed": n,
-                "algorithmic_bytes_per_launch": alg, "avg_launch_us": ms * 1e3 / n,
+                "algorithmic_bytes_per_launch": alg, "streamed_bytes_per_launch": streamed / (n / iters), "avg_launch_us": ms * 1e3 / n,
                 "note": "latency-bound: ~600 dependent launches per frame-step, each far below the bytes one launch could move (DESIGN.md §3.2)"}
         # ---- batch-1 latency view (the reference's only mode), max_batch = 1 handle: persistent frame kernel + codec
         e1 = q.Engine(ckpt_dir, device=local_rank, max_batch=1, max_frames=64)
@@ -431,6 +439,17 @@ def main():
     eng_bytes = int(res[0]["bytes_frame"])
     talker_ms_frame = (sum(r["talker"] - r["prefill"] for r in res)) / a.steps / a.frames * 1e3
     eng.close()
+    ab = None
+    if rank == 0 and extras and a.bits in (4, 8) and 3 <= a.batch <= 128:
+        # the other weight-operand mode of the 3..128-row GEMMs on the same workload (2 steps after 1 warm-up): SURVEY.md §8 row a9
+        other = 2 if a.packed_gemm == 1 else 1
+        eng = q.Engine(ckpt_dir, device=local_rank, max_batch=a.batch, max_frames=max(64, a.frames), kv_capacity=512, packed_gemm=other)
+        step(2000)
+        r2 = [step(2001 + i) for i in range(2)]
+        ab = {"packed_gemm": other, "what": "packed 4/8-bit weights dequantised inside the tcgen05 GEMM" if other == 1 else "fp16 operand copies",
+              "value": sum(r["samples"] for r in r2) / 24000.0 / sum(r["dev"] for r in r2), "unit": UNIT,
+              "ms_per_frame_step_batch": sum(r["talker"] - r["prefill"] for r in r2) / 2 / a.frames * 1e3}
+        eng.close()
 
     cfg3 = cfg4 = None
     if extras and a.config4 == "on":
@@ -445,7 +464,8 @@ def main():
         packed = a.bits in (4, 8)
         line = {"metric": METRIC, "value": audio_s / dev_max, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": dev_max / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": (f"u{a.bits} g64 weights dequantised inside the GEMM to f16 operands x f32 accumulate, f32 residual stream" if packed
+                "dtype": ((f"u{a.bits} g64 weights dequantised inside the GEMM to f16 operands x f32 accumulate, f32 residual stream" if fused_mode else
+                           f"u{a.bits} g64 weights dequantised at load to f16 operands x f32 accumulate, f32 residual stream") if packed
                           else "bf16 weights -> f16 operands x f32 accumulate, f32 residual stream") if a.batch >= 3 else "f32 activations, packed weights",
                 "data": "synthetic", "config": config,
                 "e2e": {"value": audio_s / wall_max, "unit": UNIT, "h2d_bytes_per_step": h2d_all / world / a.steps, "d2h_bytes_per_step": d2h_all / world / a.steps,
@@ -456,7 +476,7 @@ def main():
                 "talker": {"ms_per_frame_step_batch": talker_ms_frame, "prefill_ms_per_step": sum(r["prefill"] for r in res) / a.steps * 1e3,
                            "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev), "algorithmic_weight_bytes_per_frame_step": eng_bytes,
                            "frame_step_hbm_frac": (eng_bytes / max(1e-9, talker_ms_frame * 1e-3) / 1e9) / hbm},
-                "config3": cfg3, "config4": cfg4,
+                "other_weight_operand_mode": ab, "config3": cfg3, "config4": cfg4,
                 "wall_s_timed_region": total_max}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -65,7 +65,11 @@ typedef struct q3tts_options {
   int32_t load_talker;      /* 0: codec only (BASELINE config 4) */
   int32_t codec_max_frames; /* largest T of one codec decode window; 0 = 2400 */
   int32_t codec_max_batch;  /* largest B of one codec decode call; 0 = 8 */
-  int32_t reserved[8];
+  int32_t packed_gemm;      /* 3..128-row decode GEMMs of a quantised checkpoint: 1 = stream the PACKED 4/8-bit weights and dequantise
+                               inside the tcgen05 kernel (QuantizedLayerFactory.swift:56's quantizedMatmul; 0.5625 B/param from HBM),
+                               2 = fp16 operand copies made at load (2 B/param), 0 = the faster of the two as measured (DESIGN.md 3.2;
+                               today 2; env Q3TTS_SKINNY_Q=1 flips it).  Same bits either way (the copies ARE the dequantised values). */
+  int32_t reserved[7];
 } q3tts_options;
 
 typedef struct q3tts_info {

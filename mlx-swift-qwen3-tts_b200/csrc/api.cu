@@ -426,6 +426,8 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
     h->opt.load_talker = o.load_talker;
     h->opt.codec_max_frames = o.codec_max_frames > 0 ? o.codec_max_frames : 2400;
     h->opt.codec_max_batch = o.codec_max_batch > 0 ? o.codec_max_batch : 8;
+    Q3_CHECK(o.packed_gemm >= 0 && o.packed_gemm <= 2, Q3TTS_ERR_INVALID_ARG, "options.packed_gemm must be 0, 1 or 2");
+    h->opt.packed_gemm = o.packed_gemm;
     if (o.cuda_stream) {
       h->stream = (cudaStream_t)o.cuda_stream;
     } else {

@@ -20,6 +20,7 @@ struct EngineOptions {
   int max_batch = 1, kv_capacity = 512, max_frames = 2400, use_cuda_graph = 1;
   int load_codec = 1, load_talker = 1, codec_max_frames = 2400, codec_max_batch = 8;
   int max_trailing = 1024;
+  int packed_gemm = 0;  // q3tts_options::packed_gemm
 };
 
 // Result of admitting one request into a slot.
@@ -117,6 +118,11 @@ class TalkerEngine {
   int tc_min_rows_ = 16, tc_min_rows_step_ = 3;
   bool step_tc_ = false;  // set by issue_frame for the launches of the current frame step
   bool handle_tc_ = false;  // decode steps of this handle run on tensor cores (see use_tc_step)
+  // 3..128-row GEMMs of a quantised checkpoint read the packed weights (gemm_skinny_q.cu) instead of the fp16 copies: q3tts_options::
+  // packed_gemm.  Off by default: at 64 rows the frame step is a chain of ~570 dependent launches, not a bandwidth problem, and the
+  // dequantisation in front of the MMAs lengthens every link (measured 4.95-5.4 ms against 4.18 ms per frame-step).
+  bool packed_gemm_ = false;
+  void attach_packed(struct TcGemm& g, const TcLinear& L) const;
   // chain signals (common.h): counters of one frame graph + the link state while issue_frame records its launches
   static constexpr int kChainCounters = 1024;
   ChainState chain_;

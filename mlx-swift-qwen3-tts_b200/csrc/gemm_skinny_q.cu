@@ -283,6 +283,15 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
     const int gpk = p.q_group >= kBlockK ? 1 : kBlockK / p.q_group;          // groups per k-block: 1 or 2
     const int gdiv = p.q_group >= kBlockK ? p.q_group / kBlockK : 1;         // k-blocks per group: 1 or 2
     const size_t srow = (size_t)grow * (size_t)(p.K / p.q_group);
+    // The fold slice (the RMSNorm weight of the K slice) is requested FIRST and parked in registers, so that its DRAM round trip overlaps
+    // the scale / bias loads' instead of following them (the stores of the table fill wait for their loads).
+    constexpr int kFoldRegs = 8;  // nkb <= 16 (host plan): 16 * 64 / 128 threads
+    float fv[kFoldRegs];
+#pragma unroll
+    for (int u = 0; u < kFoldRegs; ++u) {
+      const int e = (int)threadIdx.x - 64 + u * 128, k = kb0 * kBlockK + e;
+      fv[u] = (p.q_fold && e < nkb * kBlockK && k < p.K) ? __ldg(p.q_fold + k) : 0.f;
+    }
     // Scales and biases of this row for EVERY k-block of the CTA's K slice, requested up front: all the loads of a batch of 8 groups are
     // in flight together and land in this thread's column of a shared-memory table.  (One k-block ahead, as the first version did, left
     // two dependent DRAM round trips in front of the first block and one L2 round trip inside every later one: measured 2000 of the 4600
@@ -310,9 +319,10 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
       }
     };
     if (p.q_fold) {
-      for (int e = (int)threadIdx.x - 64; e < nkb * kBlockK; e += 128) {
-        const int k = kb0 * kBlockK + e;
-        fold_s[e] = k < p.K ? __ldg(p.q_fold + k) : 0.f;
+#pragma unroll
+      for (int u = 0; u < kFoldRegs; ++u) {
+        const int e = (int)threadIdx.x - 64 + u * 128;
+        if (e < nkb * kBlockK) fold_s[e] = fv[u];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -438,7 +448,7 @@ SkqPlan plan(const TcGemm& g) {
   s.tmem_cols = 32;
   while (s.tmem_cols < cols) s.tmem_cols <<= 1;
   // the packed slice is one TMA box: <= 256 elements in the inner dimension
-  s.ok = s.smem <= 220 * 1024 && s.tmem_cols <= 512 && s.nkb_max * (kBlockK * g.q_bits / 32) <= 256;
+  s.ok = s.smem <= 220 * 1024 && s.tmem_cols <= 512 && s.nkb_max * (kBlockK * g.q_bits / 32) <= 256 && s.nkb_max <= 16;
   return s;
 }
 
@@ -476,8 +486,7 @@ bool tc_skinny_q_supported(const TcGemm& g) {
   if (g.cin % kBlockK != 0 || g.cin % g.q_group != 0 || g.N % 32 != 0) return false;
   if (g.q_halves && (!g.swiglu || (g.N / 2) % (kRowsW / 2) != 0)) return false;
   if ((reinterpret_cast<uintptr_t>(g.q_w) & 15) != 0 || (reinterpret_cast<uintptr_t>(g.a) & 15) != 0) return false;
-  static const bool on = env_int("Q3TTS_SKINNY_Q", 1) != 0;
-  return on && plan(g).ok;
+  return plan(g).ok;
 }
 
 void init_tc_skinny_q() {

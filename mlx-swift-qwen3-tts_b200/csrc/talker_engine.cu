@@ -93,6 +93,10 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
     d_tph16_ = arena_.alloc((size_t)max_tp_rows_ * cfg_.text_hidden_size * 2);
   }
   handle_tc_ = w_.has_tc && tc_min_rows_step_ > 0 && B >= tc_min_rows_step_;
+  {
+    const char* e = getenv("Q3TTS_SKINNY_Q");
+    packed_gemm_ = opt_.packed_gemm == 1 || (opt_.packed_gemm == 0 && e && atoi(e) != 0);
+  }
   Q3_CHECK(!kv_f16_ || handle_tc_ || !w_.has_tc, Q3TTS_ERR_BAD_CONFIG, "internal: fp16 KV rings on a handle without the tensor-core step");
   chain_.base = arena_.alloc_n<unsigned>(kChainCounters);
   chain_.capacity = kChainCounters;
@@ -427,8 +431,8 @@ void TalkerEngine::build_tc_weights() {
 }
 
 // decode-step GEMMs read the checkpoint's packed bytes when the leaf is quantised (a9: dequant fused into the GEMM)
-static inline void attach_packed(TcGemm& g, const TcLinear& L) {
-  if (!L.qbits) return;
+void TalkerEngine::attach_packed(TcGemm& g, const TcLinear& L) const {
+  if (!L.qbits || !packed_gemm_) return;
   g.q_w = L.qw; g.q_scales = L.qscales; g.q_biases = L.qbiases; g.q_fold = L.fold;
   g.q_bits = L.qbits; g.q_group = L.qgroup; g.q_sdt = L.qsdt; g.q_halves = L.halves ? 1 : 0;
 }

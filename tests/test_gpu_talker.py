@@ -449,6 +449,28 @@ def test_default_batch_engine_uses_tensor_cores_and_stays_in_tolerance(tiny8, en
     print(f"{bad}/32 utterances diverged at a near-tie (margin < {MARGIN_TOL})")
 
 
+@pytest.mark.parametrize("ck", ["tiny8", "tiny4"])
+def test_packed_weight_gemm_mode_equals_fp16_copy_mode(ck, request, engines):
+    """q3tts_options.packed_gemm: 1 streams the checkpoint's packed 4/8-bit weights and dequantises them inside the tcgen05 GEMM
+    (csrc/gemm_skinny_q.cu), 2 reads fp16 copies made at load.  The copies ARE the dequantised values and the K split is the same, so
+    teacher-forced logits and sampled frames must agree bit for bit."""
+    import qwen3tts_b200 as q
+
+    d = request.getfixturevalue(ck)
+    F = 12
+    forced = np.random.default_rng(9).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    out = {}
+    for mode in (1, 2):
+        eng = engines(d, max_batch=8, load_codec=False, packed_gemm=mode)
+        _, lg = eng.generate_codes(q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced,
+                                                keep_invalid_frames=True, want_logits=F))
+        reqs = [q.GenRequest(text_ids=TEXT_IDS[:3] + [50 + i] + TEXT_IDS[4:], speaker_id=2861, temperature=0.7, top_k=30, seed=i, max_tokens=10,
+                             keep_invalid_frames=True) for i in range(8)]
+        out[mode] = (lg["code0_logits"].copy(), lg["cp_logits"].copy(), [o.tolist() for o in eng.generate_codes_batch(reqs)])
+    assert np.array_equal(out[1][0], out[2][0]) and np.array_equal(out[1][1], out[2][1])
+    assert out[1][2] == out[2][2]
+
+
 # ------------------------------------------------------------------------------------------------ path pinning / hand-offs
 def test_batch_draining_to_one_slot_equals_singles_on_the_same_handle(tiny8, engines):
     """Default thresholds, a 4-slot handle: 7 requests of very different lengths, so the batch drains from 4 live slots to 1 while
