@@ -3,6 +3,7 @@
 #include <cmath>
 
 #include "codec_kernels.h"
+#include "codec_unit.h"
 #include "gemm_tc.h"
 
 namespace q3 {
@@ -524,6 +525,23 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
     }
     Tc *= b.rate;
     for (int j = 0; j < 3; ++j) {  // DecoderResidualUnit (:696-718)
+      const bool last = j == 2;
+      const SnakeW& nxt = !last ? b.unit[j + 1].act1 : (bi + 1 < blocks_.size() ? blocks_[bi + 1].snake : out_snake_);
+      if (!res32) {  // thin stages: the whole unit in one persistent kernel (codec_unit.cu), the intermediate never leaves the SM
+        CodecUnit u;
+        u.Bt = B; u.T = Tc; u.C = b.cout; u.dil = b.unit[j].conv1.dil;
+        u.a = oa; u.w7 = b.unit[j].conv1.w16; u.b7 = b.unit[j].conv1.bias;
+        u.snake2_ea = b.unit[j].act2.alpha; u.snake2_ieb = b.unit[j].act2.beta;
+        u.w1 = b.unit[j].conv2.w16; u.b1 = b.unit[j].conv2.bias;
+        u.res16 = R0; u.outr16 = last ? nullptr : R0;
+        u.out16 = last ? cur : ob;  // never in place: other tiles still read their halo rows from `oa`
+        u.next_ea = nxt.alpha; u.next_ieb = nxt.beta;
+        if (b.unit[j].conv1.ntap == 7 && b.unit[j].conv2.ntap == 1 && b.unit[j].conv1.cin == b.cout && nxt.ch == b.cout && codec_unit_supported(u)) {
+          launch_codec_unit(lc, u);
+          if (!last) std::swap(oa, ob);
+          continue;
+        }
+      }
       { TcGemm g = gemm(b.unit[j].conv1, oa, B, Tc); g.out16 = ob; g.ld16 = b.cout; with_snake(g, b.unit[j].act2); launch_tc_gemm(lc, g); }
       TcGemm g = gemm(b.unit[j].conv2, ob, B, Tc);
       g.ld_res = b.cout; g.ld32 = b.cout;

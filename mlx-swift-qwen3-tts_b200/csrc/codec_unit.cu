@@ -1,0 +1,365 @@
+// One DecoderResidualUnit of the vocoder (Vocoder/SpeechTokenizer.swift:696-718) as ONE persistent tcgen05 kernel:
+//
+//     x' = x + conv1x1( snake2( conv7_dilated( snake1(x) ) ) ),      also emitted: snake_next(x') as the next contraction's operand
+//
+// for the thin stages (C = 96 / 192 channels, 16 640 - 49 920 rows per 26-frame window) where the two-kernel form was bound by
+// its HBM round trips and epilogues, not by the tensor pipe (ncu, profiles/r01_ncu_full_codec_tc_gemm.md: the 1x1 convolutions ran
+// at 4-5 % tensor / 35 % DRAM, and every unit wrote and re-read a [rows, C] fp16 intermediate).  Per 128-row tile:
+//
+//   warp 0    TMA producer: the snake1(x) tile WITH its causal halo (128 + 6*dil rows, once per 64-channel block -- every tap reads it
+//             through a UMMA descriptor whose start is shifted by tap*dil rows), the 7 x kcs weight tiles of the dilated
+//             convolution and the kcs weight tiles of the 1x1, all through one ring
+//   warp 1    MMA issuer: conv7 of tile i+1 is issued BEFORE the 1x1 of tile i (two accumulators), so the tensor pipe works on the
+//             next tile while the epilogue warps turn accumulator i into the 1x1's operand
+//   warps 2+  epilogue sets (4 warps each, 32-column chunks round-robin):
+//             E1: acc1 (+bias) -> snake2 -> fp16 -> TENSOR MEMORY (tcgen05.st): the intermediate is the A operand of the 1x1 straight
+//                 from TMEM (tcgen05.mma with a TMEM A operand); it never touches shared or global memory
+//             E2: acc2 (+bias) + residual x -> x' (fp16 stream) and snake_next(x') (fp16 operand of the next unit / block)
+//
+// HBM traffic per unit: read snake1(x) (+42 % halo, mostly L2) and x, write x' and snake_next(x'): 4 tile-sized streams instead of 7.
+#include <cuda.h>
+
+#include <algorithm>
+
+#include "codec_unit.h"
+#include "gemm_tc.h"
+#include "tc_ptx.cuh"
+
+namespace q3 {
+
+namespace {
+
+using namespace tcptx;
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;
+constexpr int kHaloRowsMax = 192;
+constexpr int kHaloBytes = kHaloRowsMax * kBlockK * 2;  // 24 KB
+constexpr int kTaps = 7;
+constexpr int kMaxThreads = 448;
+constexpr int kMaxC = 192;
+
+struct UnitParams {
+  int Bt, T, C, dil;
+  int tiles_per_batch, total_tiles, kcs, halo_rows;
+  int b_stages, b_bytes;
+  int h_col0, tmem_cols, epi_sets;
+  const float *b7, *ea2, *ieb2, *b1, *ea3, *ieb3;
+  const __half* res16;
+  __half* outr16;
+  __half* out16;
+};
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]),
+      "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 1)
+codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7, const __grid_constant__ CUtensorMap tmW1,
+                  const UnitParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int AST = 2;
+  uint8_t* sA = smem;                                   // [2][192 rows][128 B] halo tiles of snake1(x)
+  uint8_t* sB = smem + (size_t)AST * kHaloBytes;        // [b_stages][C rows][128 B] weight tiles (conv7 taps, then the 1x1)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.b_stages * p.b_bytes);
+  uint64_t* a_empty = a_full + AST;
+  uint64_t* b_full = a_empty + AST;
+  uint64_t* b_empty = b_full + p.b_stages;
+  uint64_t* acc1_full = b_empty + p.b_stages;  // [2] conv7 accumulator of a tile complete            (MMA -> epilogue)
+  uint64_t* acc2_full = acc1_full + 2;         // [2] 1x1 accumulator complete                         (MMA -> epilogue)
+  uint64_t* acc_empty = acc2_full + 2;         // [2] accumulator drained by E2                        (epilogue -> MMA)
+  uint64_t* h_full = acc_empty + 2;            // [1] intermediate of a tile written to tensor memory   (epilogue -> MMA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 1);
+
+  __shared__ __align__(16) float s_b7[kMaxC], s_ea2[kMaxC], s_ieb2[kMaxC], s_b1[kMaxC], s_ea3[kMaxC], s_ieb3[kMaxC];
+  for (int c = threadIdx.x; c < p.C; c += blockDim.x) {  // static parameters: no dependency on the predecessor kernel
+    s_b7[c] = p.b7 ? p.b7[c] : 0.f;
+    s_ea2[c] = p.ea2[c]; s_ieb2[c] = p.ieb2[c];
+    s_b1[c] = p.b1 ? p.b1[c] : 0.f;
+    s_ea3[c] = p.ea3[c]; s_ieb3[c] = p.ieb3[c];
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc2_full[s], 1); mbar_init(&acc_empty[s], 4 * p.epi_sets); }
+    mbar_init(h_full, 4 * p.epi_sets);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int n_local = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  // k-steps (K = 16 each) of channel block kc that hold real channels (C = 96: the second block is half zero fill)
+  auto ksteps = [&](int kc) { const int left = p.C - kc * kBlockK; return left >= kBlockK ? kBlockK / 16 : (left + 15) / 16; };
+
+  if (warp == 0) {
+    if (lane == 0) {  // ---------------- TMA producer
+      int ia = 0, ib = 0;
+      bool waited = false;
+      auto issue_b = [&](const CUtensorMap* map, int c0, int c1) {
+        const int sb = ib % p.b_stages;
+        if (ib >= p.b_stages) mbar_wait(&b_empty[sb], (uint32_t)(((ib / p.b_stages) & 1) ^ 1));
+        mbar_expect_tx(&b_full[sb], (uint32_t)p.b_bytes);
+        tma_load_2d(sB + (size_t)sb * p.b_bytes, map, &b_full[sb], c0, c1);
+        ++ib;
+      };
+      for (int ti = 0; ti <= n_local; ++ti) {
+        if (ti < n_local) {  // operands of conv7(ti)
+          const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+          const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
+          for (int kc = 0; kc < p.kcs; ++kc) {
+            int tap0 = 0;
+            if (!waited) {  // the first weight tiles do not depend on the predecessor kernel
+              const int pre = p.b_stages < kTaps ? p.b_stages : kTaps;
+              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, tap0 * p.C);
+              pdl_wait();
+              waited = true;
+            }
+            const int sa = ia % AST;
+            if (ia >= AST) mbar_wait(&a_empty[sa], (uint32_t)(((ia / AST) & 1) ^ 1));
+            mbar_expect_tx(&a_full[sa], (uint32_t)(p.halo_rows * kBlockK * 2));
+            tma_load_3d(sA + (size_t)sa * kHaloBytes, &tmA, &a_full[sa], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
+            ++ia;
+            for (int tap = tap0; tap < kTaps; ++tap) issue_b(&tmW7, kc * kBlockK, tap * p.C);
+          }
+        }
+        if (ti > 0)  // operands of conv1(ti - 1)
+          for (int kc = 0; kc < p.kcs; ++kc) issue_b(&tmW1, kc * kBlockK, 0);
+      }
+      if (!waited) pdl_wait();
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {  // ---------------- MMA issuer
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t h_base = tmem_base + (uint32_t)p.h_col0;
+      int ia = 0, ib = 0;
+      for (int ti = 0; ti <= n_local; ++ti) {
+        if (ti < n_local) {  // conv7(ti) -> accumulator ti & 1
+          const int buf = ti & 1, use = ti >> 1;
+          if (use > 0) {
+            mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
+            tc_fence_after();
+          }
+          const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
+          for (int kc = 0; kc < p.kcs; ++kc, ++ia) {
+            const int sa = ia % AST, ks = ksteps(kc);
+            for (int tap = 0; tap < kTaps; ++tap, ++ib) {
+              const int sb = ib % p.b_stages;
+              mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));
+              if (tap == 0) mbar_wait(&a_full[sa], (uint32_t)((ia / AST) & 1));
+              tc_fence_after();
+              const uint64_t ad = umma_desc_rows(smem_u32(sA + (size_t)sa * kHaloBytes) + (uint32_t)(tap * p.dil) * 128u);
+              const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
+              for (int k = 0; k < ks; ++k) umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              umma_commit(&b_empty[sb]);
+            }
+            umma_commit(&a_empty[sa]);
+          }
+          umma_commit(&acc1_full[buf]);
+        }
+        if (ti > 0) {  // conv1(ti - 1): A = the intermediate in tensor memory, D = the same accumulator columns (drained by E1)
+          const int j = ti - 1, buf = j & 1;
+          const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
+          mbar_wait(h_full, (uint32_t)(j & 1));
+          tc_fence_after();
+          for (int kc = 0; kc < p.kcs; ++kc, ++ib) {
+            const int sb = ib % p.b_stages, ks = ksteps(kc);
+            mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));
+            tc_fence_after();
+            const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
+            for (int k = 0; k < ks; ++k)
+              umma_f16_ts(acc, h_base + (uint32_t)(kc * 32 + 8 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+            umma_commit(&b_empty[sb]);
+          }
+          umma_commit(&acc2_full[buf]);
+        }
+      }
+    }
+  } else {
+    // ---------------- epilogue warps: warp w touches TMEM lanes [32*(w%4), +32); set e takes chunks e, e + sets, ...
+    const int q = warp & 3, set = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    const uint32_t h_base = tmem_base + (uint32_t)p.h_col0 + lane_off;
+    pdl_wait();
+    for (int ti = 0; ti < n_local; ++ti) {
+      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
+      const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
+      const int buf = ti & 1, use = ti >> 1;
+      const uint32_t acc = tmem_base + (uint32_t)(buf * p.C) + lane_off;
+      const int t = t0 + row;
+      const bool row_ok = t < p.T;
+      const size_t m = (size_t)bidx * p.T + t;
+      // the residual rows of this thread's first two chunks are requested now: their DRAM round trip hides behind E1
+      uint4 rpre[2][4];
+      if (row_ok) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int c = (set + u * p.epi_sets) * 32;
+          if (c < p.C) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.C + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rpre[u][j] = rp[j];
+          }
+        }
+      }
+      // ---- E1: conv7 accumulator -> bias -> snake2 -> fp16 pairs -> tensor memory
+      mbar_wait(&acc1_full[buf], (uint32_t)(use & 1));
+      tc_fence_after();
+      for (int c = set * 32; c < p.C; c += 32 * p.epi_sets) {
+        uint32_t raw[32];
+        tmem_ld32(acc + (uint32_t)c, raw);
+        uint32_t h[16];
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_b7 + c + j), a4 = *reinterpret_cast<const float4*>(s_ea2 + c + j),
+                       i4 = *reinterpret_cast<const float4*>(s_ieb2 + c + j);
+          float v0 = __uint_as_float(raw[j]) + b4.x, v1 = __uint_as_float(raw[j + 1]) + b4.y, v2 = __uint_as_float(raw[j + 2]) + b4.z,
+                v3 = __uint_as_float(raw[j + 3]) + b4.w;
+          const float s0 = __sinf(v0 * a4.x), s1 = __sinf(v1 * a4.y), s2 = __sinf(v2 * a4.z), s3 = __sinf(v3 * a4.w);
+          v0 += i4.x * (s0 * s0); v1 += i4.y * (s1 * s1); v2 += i4.z * (s2 * s2); v3 += i4.w * (s3 * s3);
+          h[j >> 1] = pack_h2(v0, v1);
+          h[(j >> 1) + 1] = pack_h2(v2, v3);
+        }
+        tmem_st16(h_base + (uint32_t)(c >> 1), h);
+      }
+      tmem_st_wait();
+      tc_fence_before();  // the accumulator reads and the tensor-memory writes are ordered before the barrier the MMA thread waits on
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_full);
+      // ---- E2: 1x1 accumulator -> bias + residual -> x' (fp16 stream) and snake_next(x') (fp16 operand)
+      mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
+      tc_fence_after();
+      int ci = 0;
+      for (int c = set * 32; c < p.C; c += 32 * p.epi_sets, ++ci) {
+        uint32_t raw[32];
+        tmem_ld32_issue(acc + (uint32_t)c, raw);
+        uint4 rres[4];
+        if (row_ok) {
+          if (ci < 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rres[j] = ci == 0 ? rpre[0][j] : rpre[1][j];
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.C + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rres[j] = rp[j];
+          }
+        }
+        tmem_ld_wait32(raw);
+        if (!row_ok) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t w4[4] = {rres[j].x, rres[j].y, rres[j].z, rres[j].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+            const int e = 8 * j + 2 * i;
+            v[e] = r2.x + (__uint_as_float(raw[e]) + s_b1[c + e]);
+            v[e + 1] = r2.y + (__uint_as_float(raw[e + 1]) + s_b1[c + e + 1]);
+          }
+        }
+        if (p.outr16) {
+          uint4* op = reinterpret_cast<uint4*>(p.outr16 + m * p.C + c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            op[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+                               pack_h2(v[8 * j + 6], v[8 * j + 7]));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(s_ea3 + c + j), i4 = *reinterpret_cast<const float4*>(s_ieb3 + c + j);
+          const float s0 = __sinf(v[j] * a4.x), s1 = __sinf(v[j + 1] * a4.y), s2 = __sinf(v[j + 2] * a4.z), s3 = __sinf(v[j + 3] * a4.w);
+          v[j] += i4.x * (s0 * s0); v[j + 1] += i4.y * (s1 * s1); v[j + 2] += i4.z * (s2 * s2); v[j + 3] += i4.w * (s3 * s3);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out16 + m * p.C + c);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          op[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+                             pack_h2(v[8 * j + 6], v[8 * j + 7]));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace
+
+bool codec_unit_supported(const CodecUnit& u) {
+  const char* e = getenv("Q3TTS_CODEC_UNIT");  // read per call: the A/B test flips it between two handles of one process
+  if (e && atoi(e) == 0) return false;
+  if (u.C % 32 != 0 || u.C < 32 || u.C > kMaxC) return false;       // one CTA owns all C columns; 2.5 * C tensor-memory columns
+  if (kTileM + (kTaps - 1) * u.dil > kHaloRowsMax) return false;     // the halo tile is one 192-row stage
+  if (!u.res16 || !u.out16 || !u.a || !u.w7 || !u.w1 || !u.snake2_ea || !u.next_ea) return false;
+  if ((long long)u.Bt * ((u.T + kTileM - 1) / kTileM) < 32) return false;  // a few tiles: the two-kernel form (its <= 128-row variants) is fine
+  return true;
+}
+
+void init_codec_unit() {
+  tc_resolve_encode();
+  Q3_CUDA(cudaFuncSetAttribute(codec_unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+}
+
+void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
+  Q3_CHECK(codec_unit_supported(u), Q3TTS_ERR_INVALID_ARG, "codec_unit: unsupported shape (C %d, dilation %d, %d x %d rows)", u.C, u.dil, u.Bt, u.T);
+  UnitParams p{};
+  p.Bt = u.Bt; p.T = u.T; p.C = u.C; p.dil = u.dil;
+  p.tiles_per_batch = (u.T + kTileM - 1) / kTileM;
+  p.total_tiles = u.Bt * p.tiles_per_batch;
+  p.kcs = (u.C + kBlockK - 1) / kBlockK;
+  p.halo_rows = kTileM + (kTaps - 1) * u.dil;
+  p.b_bytes = u.C * kBlockK * 2;
+  p.b_stages = std::max(3, std::min(12, (200 * 1024 - 2 * kHaloBytes) / p.b_bytes));
+  p.h_col0 = 2 * u.C;
+  int cols = 32;
+  while (cols < 2 * u.C + u.C / 2) cols <<= 1;
+  p.tmem_cols = cols;
+  static const int max_sets = [] { const char* e = getenv("Q3TTS_TC_EPI_SETS"); return e ? std::max(1, std::min(3, atoi(e))) : 3; }();
+  p.epi_sets = std::max(1, std::min(max_sets, u.C / 32));
+  p.b7 = u.b7; p.ea2 = u.snake2_ea; p.ieb2 = u.snake2_ieb; p.b1 = u.b1; p.ea3 = u.next_ea; p.ieb3 = u.next_ieb;
+  p.res16 = u.res16; p.outr16 = u.outr16; p.out16 = u.out16;
+
+  const uint64_t adims[3] = {(uint64_t)u.C, (uint64_t)u.T, (uint64_t)u.Bt};
+  const uint64_t astr[2] = {(uint64_t)u.C * 2, (uint64_t)u.T * u.C * 2};
+  const uint32_t abox[3] = {(uint32_t)kBlockK, (uint32_t)p.halo_rows, 1};
+  const CUtensorMap ma = tc_make_map(u.a, 3, adims, astr, abox);
+  const uint64_t w7dims[2] = {(uint64_t)u.C, (uint64_t)kTaps * u.C};
+  const uint64_t wstr[1] = {(uint64_t)u.C * 2};
+  const uint32_t wbox[2] = {(uint32_t)kBlockK, (uint32_t)u.C};
+  const CUtensorMap m7 = tc_make_map(u.w7, 2, w7dims, wstr, wbox);
+  const uint64_t w1dims[2] = {(uint64_t)u.C, (uint64_t)u.C};
+  const CUtensorMap m1 = tc_make_map(u.w1, 2, w1dims, wstr, wbox);
+
+  const size_t smem = (size_t)2 * kHaloBytes + (size_t)p.b_stages * p.b_bytes + 1024 + (size_t)(4 + 2 * p.b_stages + 8) * 8 + 64;
+  Q3_CHECK(smem <= 220 * 1024 && p.tmem_cols <= 512, Q3TTS_ERR_CAPACITY, "codec_unit: resources (smem %zu, tmem %d)", smem, p.tmem_cols);
+  dim3 grid((unsigned)std::min(p.total_tiles, 148));
+  launch_kernel_pdl(codec_unit_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, m7, m1, p);
+  c.tick();
+}
+
+}  // namespace q3

@@ -180,6 +180,26 @@ def test_tensor_core_vs_simt_pipeline(engines, monkeypatch):
     assert snr_db(a, b) >= 45.0
 
 
+@pytest.mark.parametrize("preset,B,T", [("tcsmall", 1, 140), ("tcsmall", 3, 70), ("codecfull", 2, 16)])
+def test_fused_residual_unit_vs_two_kernel_form(preset, B, T, oracles, monkeypatch):
+    """DecoderResidualUnit as one persistent kernel (csrc/codec_unit.cu: conv7 -> SnakeBeta -> 1x1 with the intermediate in tensor
+    memory) against the two-launch form of the same unit: same parity bar against the oracle, and the two agree far inside it."""
+    import qwen3tts_b200 as q
+
+    d = ckpt(preset, 8)
+    codes = rand_codes(B, T, 77 + T)
+    want = oracle_decode(oracles(d, "codec"), codes)
+    out = {}
+    for unit in ("1", "0"):
+        monkeypatch.setenv("Q3TTS_CODEC_UNIT", unit)
+        e = q.Engine(d, max_frames=256, load_talker=False)
+        out[unit] = e.decode(codes)
+        e.close()
+    s1, s0, sab = snr_db(out["1"], want), snr_db(out["0"], want), snr_db(out["1"], out["0"])
+    print(f"[{preset} B={B} T={T}] fused unit {s1:.1f} dB, two-kernel {s0:.1f} dB vs oracle; fused vs two-kernel {sab:.1f} dB")
+    assert s1 >= SNR_DB and s0 >= SNR_DB and sab >= 45.0
+
+
 def test_chunked_decode_tensor_core(engines, oracles):
     d = ckpt("tcsmall", 8)
     codes = rand_codes(2, 45, 3)
