@@ -49,12 +49,21 @@ const STensor& need(const std::map<std::string, STensor>& t, const std::string& 
 }
 }  // namespace
 
-const __half* CodecDecoder::upload_f16(const std::vector<float>& h) {
+const __half* CodecDecoder::upload_f16(const std::vector<float>& h, int reps, size_t* rep_stride) {
   std::vector<__half> r(h.size());
   for (size_t i = 0; i < h.size(); ++i) r[i] = __float2half_rn(h[i]);
-  __half* d = (__half*)arena_.alloc(r.size() * sizeof(__half));
-  Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  const size_t stride = (r.size() * sizeof(__half) + 255) / 256 * 256;  // bytes between copies
+  __half* d = (__half*)arena_.alloc(stride * (size_t)reps);
+  for (int i = 0; i < reps; ++i)
+    Q3_CUDA(cudaMemcpy(reinterpret_cast<uint8_t*>(d) + (size_t)i * stride, r.data(), r.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  if (rep_stride) *rep_stride = stride / sizeof(__half);
   return d;
+}
+
+// copies of a conv weight for the L2-slice spreading described at ConvW::w16_reps: only matrices small enough that the re-reads matter
+static int weight_reps(size_t halves) {
+  static const int env = [] { const char* e = getenv("Q3TTS_CODEC_WREP"); return e ? std::max(1, std::min(32, atoi(e))) : 8; }();
+  return halves * 2 <= (size_t)(2u << 20) ? env : 1;
 }
 
 // A contraction can take the tcgen05 path when its K rows are 16-byte multiples (TMA) and N is a multiple of 32 (epilogue chunks).
@@ -82,7 +91,8 @@ ConvW CodecDecoder::load_conv(const std::map<std::string, STensor>& t, const std
   float* d = arena_.alloc_n<float>(r.size());
   Q3_CUDA(cudaMemcpy(d, r.data(), r.size() * 4, cudaMemcpyHostToDevice));
   ConvW w;
-  w.w = d; w.w16 = upload_f16(r); w.ntap = k; w.dil = dil; w.cin = cin; w.n = cout;
+  w.w16_reps = weight_reps(r.size());
+  w.w = d; w.w16 = upload_f16(r, w.w16_reps, &w.w16_rep_stride); w.ntap = k; w.dil = dil; w.cin = cin; w.n = cout;
   if (bias) w.bias = load_vec(t, key + ".bias", cout);
   finish_weight(w);
   return w;
@@ -114,7 +124,8 @@ ConvW CodecDecoder::load_convT(const std::map<std::string, STensor>& t, const st
   float* db = arena_.alloc_n<float>(rb.size());
   Q3_CUDA(cudaMemcpy(db, rb.data(), rb.size() * 4, cudaMemcpyHostToDevice));
   ConvW w;
-  w.w = d; w.w16 = upload_f16(r); w.bias = db; w.ntap = ntap; w.dil = 1; w.cin = cin; w.n = n;
+  w.w16_reps = weight_reps(r.size());
+  w.w = d; w.w16 = upload_f16(r, w.w16_reps, &w.w16_rep_stride); w.bias = db; w.ntap = ntap; w.dil = 1; w.cin = cin; w.n = n;
   finish_weight(w);
   return w;
 }
@@ -152,6 +163,7 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     : stream_(stream), counter_(counter), pass_frames_(pass_frames) {
   init_codec_kernels();
   init_tc_gemm();
+  init_codec_unit();
   // config candidates (Qwen3TTSPipeline.swift:191-199)
   std::string cfg_path;
   for (const char* name : {"config.json", "configuration.json", "speech_tokenizer_config.json"}) {
@@ -332,7 +344,8 @@ CodecDecoder::CodecDecoder(const std::string& dir, cudaStream_t stream, LaunchCo
     Q3_CUDA(cudaMemcpy(hb.data(), out_b_, 4, cudaMemcpyDeviceToHost));
     float* db = arena_.alloc_n<float>(32);
     Q3_CUDA(cudaMemcpy(db, hb.data(), 32 * 4, cudaMemcpyHostToDevice));
-    out_tc_.w16 = upload_f16(wp); out_tc_.bias = db; out_tc_.n = 32; out_tc_.cin = out_ch_; out_tc_.ntap = 7; out_tc_.dil = 1;
+    out_tc_.w16_reps = weight_reps(wp.size());
+    out_tc_.w16 = upload_f16(wp, out_tc_.w16_reps, &out_tc_.w16_rep_stride); out_tc_.bias = db; out_tc_.n = 32; out_tc_.cin = out_ch_; out_tc_.ntap = 7; out_tc_.dil = 1;
   }
   // algorithmic flops per 12.5 Hz frame: 2 * MACs of every dense contraction
   int64_t fl = rvq_proj_.flops_per_row() + pre_conv_.flops_per_row() + tr_in_.flops_per_row() + tr_out_.flops_per_row();
@@ -468,6 +481,7 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
   auto gemm = [&](const ConvW& w, const __half* a, int Bt, int Tt) {
     TcGemm g;
     g.a = a; g.w = w.w16; g.Bt = Bt; g.T = Tt; g.cin = w.cin; g.N = w.n; g.ntap = w.ntap; g.dil = w.dil; g.bias = w.bias;
+    g.w_reps = w.w16_reps; g.w_rep_stride = w.w16_rep_stride;
     return g;
   };
   auto with_snake = [](TcGemm& g, const SnakeW& s) { g.snake_ea = s.alpha; g.snake_ieb = s.beta; g.snake_ch = s.ch; };
@@ -533,6 +547,8 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
         u.a = oa; u.w7 = b.unit[j].conv1.w16; u.b7 = b.unit[j].conv1.bias;
         u.snake2_ea = b.unit[j].act2.alpha; u.snake2_ieb = b.unit[j].act2.beta;
         u.w1 = b.unit[j].conv2.w16; u.b1 = b.unit[j].conv2.bias;
+        u.w7_reps = b.unit[j].conv1.w16_reps; u.w7_rep_stride = b.unit[j].conv1.w16_rep_stride;
+        u.w1_reps = b.unit[j].conv2.w16_reps; u.w1_rep_stride = b.unit[j].conv2.w16_rep_stride;
         u.res16 = R0; u.outr16 = last ? nullptr : R0;
         u.out16 = last ? cur : ob;  // never in place: other tiles still read their halo rows from `oa`
         u.next_ea = nxt.alpha; u.next_ieb = nxt.beta;

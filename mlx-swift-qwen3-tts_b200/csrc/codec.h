@@ -34,6 +34,11 @@ CodecConfig parse_codec_config(const Json& root);
 struct ConvW {
   const float* w = nullptr;   // [ntap][n][cin] fp32
   const __half* w16 = nullptr;  // same, fp16: B operand of the tcgen05 path
+  // Small weights that EVERY CTA re-reads once per 128-row tile are stored w16_reps times, w16_rep_stride halves apart; CTA i reads copy
+  // i % reps.  One copy of a 130-520 KB matrix maps unevenly onto the 184 L2 slices, and 148 SMs x ~170 tiles of re-reads then queue on the
+  // fullest slice (measured: the thin vocoder stages ran at 1 800 B/clk of the ~6 300 B/clk the L2 can deliver).
+  int w16_reps = 1;
+  size_t w16_rep_stride = 0;
   const float* bias = nullptr;  // [n] or null
   int ntap = 1, dil = 1, cin = 0, n = 0;
   int64_t flops_per_row() const { return 2ll * ntap * cin * n; }
@@ -70,7 +75,7 @@ class CodecDecoder {
   void decode_pass_simt(const int32_t* d_codes, int B, int T, float* d_pcm);
   void decode_pass_tc(const int32_t* d_codes, int B, int T, float* d_pcm);
   void finish_weight(ConvW& w);           // uploads the fp16 copy, updates use_tc_
-  const __half* upload_f16(const std::vector<float>& h);
+  const __half* upload_f16(const std::vector<float>& h, int reps = 1, size_t* rep_stride = nullptr);
   LaunchCtx ctx() const { return LaunchCtx{stream_, counter_}; }
   ConvW load_conv(const std::map<std::string, STensor>& t, const std::string& key, int cout, int cin_per_group, int k, int dil, bool bias);
   ConvW load_convT(const std::map<std::string, STensor>& t, const std::string& key, int cin, int cout, int k, int stride);

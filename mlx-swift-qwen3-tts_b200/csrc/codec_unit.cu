@@ -20,8 +20,11 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <vector>
 
 #include "codec_unit.h"
+#include "epi_io.cuh"
 #include "gemm_tc.h"
 #include "tc_ptx.cuh"
 
@@ -38,12 +41,19 @@ constexpr int kHaloBytes = kHaloRowsMax * kBlockK * 2;  // 24 KB
 constexpr int kTaps = 7;
 constexpr int kMaxThreads = 448;
 constexpr int kMaxC = 192;
+constexpr int kTraceTiles = 8;
+constexpr int kTraceSlots = 12;
+#define UNIT_STAMP(ti, slot)                                                                                              \
+  do {                                                                                                                    \
+    if (p.trace && (ti) < kTraceTiles) p.trace[((size_t)blockIdx.x * kTraceTiles + (ti)) * kTraceSlots + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
 
 struct UnitParams {
   int Bt, T, C, dil;
   int tiles_per_batch, total_tiles, kcs, halo_rows;
-  int b_stages, b_bytes;
-  int h_col0, tmem_cols, epi_sets;
+  int a_stages, n_acc, b_stages, b_bytes;
+  int h_col0, tmem_cols, epi_sets, rotate, dbg, w7_reps, w1_reps;
+  unsigned long long* trace;  // measurement hook (Q3TTS_CODEC_UNIT_TRACE): [CTA][kTraceTiles][kTraceSlots] clock stamps, or null
   const float *b7, *ea2, *ieb2, *b1, *ea3, *ieb3;
   const __half* res16;
   __half* outr16;
@@ -67,18 +77,19 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                   const UnitParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int AST = 2;
+  const int AST = p.a_stages, NACC = p.n_acc;
   uint8_t* sA = smem;                                   // [2][192 rows][128 B] halo tiles of snake1(x)
   uint8_t* sB = smem + (size_t)AST * kHaloBytes;        // [b_stages][C rows][128 B] weight tiles (conv7 taps, then the 1x1)
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.b_stages * p.b_bytes);
   uint64_t* a_empty = a_full + AST;
   uint64_t* b_full = a_empty + AST;
   uint64_t* b_empty = b_full + p.b_stages;
-  uint64_t* acc1_full = b_empty + p.b_stages;  // [2] conv7 accumulator of a tile complete            (MMA -> epilogue)
-  uint64_t* acc2_full = acc1_full + 2;         // [2] 1x1 accumulator complete                         (MMA -> epilogue)
-  uint64_t* acc_empty = acc2_full + 2;         // [2] accumulator drained by E2                        (epilogue -> MMA)
-  uint64_t* h_full = acc_empty + 2;            // [1] intermediate of a tile written to tensor memory   (epilogue -> MMA)
+  uint64_t* acc1_full = b_empty + p.b_stages;  // [NACC] conv7 accumulator of a tile complete         (MMA -> epilogue)
+  uint64_t* acc2_full = acc1_full + 3;         // [NACC] 1x1 accumulator complete                      (MMA -> epilogue)
+  uint64_t* acc_empty = acc2_full + 3;         // [NACC] accumulator drained by E2                     (epilogue -> MMA)
+  uint64_t* h_full = acc_empty + 3;            // [1] intermediate of a tile written to tensor memory   (epilogue -> MMA)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(h_full + 1);
+  uint8_t* patches = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);  // [epilogue warps][2 KB]
 
   __shared__ __align__(16) float s_b7[kMaxC], s_ea2[kMaxC], s_ieb2[kMaxC], s_b1[kMaxC], s_ea3[kMaxC], s_ieb3[kMaxC];
   for (int c = threadIdx.x; c < p.C; c += blockDim.x) {  // static parameters: no dependency on the predecessor kernel
@@ -92,7 +103,7 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < p.b_stages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc2_full[s], 1); mbar_init(&acc_empty[s], 4 * p.epi_sets); }
+    for (int s = 0; s < 3; ++s) { mbar_init(&acc1_full[s], 1); mbar_init(&acc2_full[s], 1); mbar_init(&acc_empty[s], 4 * p.epi_sets); }
     mbar_init(h_full, 4 * p.epi_sets);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -107,41 +118,53 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int n_local = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   // k-steps (K = 16 each) of channel block kc that hold real channels (C = 96: the second block is half zero fill)
+  // Every CTA streams the SAME weight tiles once per 128-row tile: in lock step, 148 SMs would ask the same L2 lines for the same 12-24 KB
+  // at the same time (measured: 3.6 TB/s aggregate L2 -> SM, the unit no faster than its two-kernel form).  Each CTA walks taps and
+  // channel blocks from its own offset; the fp32 summation order of a tile then depends on the CTA that computes it (deterministic for
+  // a given shape: tile -> CTA is fixed).
+  const int tap_rot = p.rotate ? (int)(blockIdx.x % kTaps) : 0, kc_rot = p.rotate ? (int)((blockIdx.x / kTaps) % (unsigned)p.kcs) : 0;
   auto ksteps = [&](int kc) { const int left = p.C - kc * kBlockK; return left >= kBlockK ? kBlockK / 16 : (left + 15) / 16; };
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
       int ia = 0, ib = 0;
       bool waited = false;
-      auto issue_b = [&](const CUtensorMap* map, int c0, int c1) {
+      const int rep7 = (int)(blockIdx.x % (unsigned)p.w7_reps), rep1 = (int)(blockIdx.x % (unsigned)p.w1_reps);
+      auto issue_b = [&](const CUtensorMap* map, int c0, int c1, int rep) {
         const int sb = ib % p.b_stages;
         if (ib >= p.b_stages) mbar_wait(&b_empty[sb], (uint32_t)(((ib / p.b_stages) & 1) ^ 1));
         mbar_expect_tx(&b_full[sb], (uint32_t)p.b_bytes);
-        tma_load_2d(sB + (size_t)sb * p.b_bytes, map, &b_full[sb], c0, c1);
+        tma_load_3d(sB + (size_t)sb * p.b_bytes, map, &b_full[sb], c0, c1, rep);
         ++ib;
       };
       for (int ti = 0; ti <= n_local; ++ti) {
         if (ti < n_local) {  // operands of conv7(ti)
           const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
           const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
-          for (int kc = 0; kc < p.kcs; ++kc) {
+          for (int kci = 0; kci < p.kcs; ++kci) {
+            const int kc = (kci + kc_rot) % p.kcs;
             int tap0 = 0;
             if (!waited) {  // the first weight tiles do not depend on the predecessor kernel
               const int pre = p.b_stages < kTaps ? p.b_stages : kTaps;
-              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, tap0 * p.C);
+              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, ((tap0 + tap_rot) % kTaps) * p.C, rep7);
               pdl_wait();
               waited = true;
             }
             const int sa = ia % AST;
             if (ia >= AST) mbar_wait(&a_empty[sa], (uint32_t)(((ia / AST) & 1) ^ 1));
+            if (kci == 0) UNIT_STAMP(ti, 10);  // producer: halo tile of the first channel block requested
             mbar_expect_tx(&a_full[sa], (uint32_t)(p.halo_rows * kBlockK * 2));
             tma_load_3d(sA + (size_t)sa * kHaloBytes, &tmA, &a_full[sa], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
             ++ia;
-            for (int tap = tap0; tap < kTaps; ++tap) issue_b(&tmW7, kc * kBlockK, tap * p.C);
+            for (int tap = tap0; tap < kTaps; ++tap) {
+              issue_b(&tmW7, kc * kBlockK, ((tap + tap_rot) % kTaps) * p.C, rep7);
+              if (kci == 0 && tap == tap0) UNIT_STAMP(ti, 7);  // producer: first weight tile of conv7(ti) requested
+            }
+            if (kci == p.kcs - 1) UNIT_STAMP(ti, 8);  // producer: last weight tile of conv7(ti) requested
           }
         }
         if (ti > 0)  // operands of conv1(ti - 1)
-          for (int kc = 0; kc < p.kcs; ++kc) issue_b(&tmW1, kc * kBlockK, 0);
+          for (int kci = 0; kci < p.kcs; ++kci) issue_b(&tmW1, ((kci + kc_rot) % p.kcs) * kBlockK, 0, rep1);
       }
       if (!waited) pdl_wait();
     }
@@ -151,41 +174,50 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t h_base = tmem_base + (uint32_t)p.h_col0;
       int ia = 0, ib = 0;
       for (int ti = 0; ti <= n_local; ++ti) {
-        if (ti < n_local) {  // conv7(ti) -> accumulator ti & 1
-          const int buf = ti & 1, use = ti >> 1;
+        if (ti < n_local) {  // conv7(ti) -> accumulator ti % NACC
+          const int buf = ti % NACC, use = ti / NACC;
           if (use > 0) {
             mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
             tc_fence_after();
           }
           const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
-          for (int kc = 0; kc < p.kcs; ++kc, ++ia) {
+          UNIT_STAMP(ti, 0);  // conv7(ti): accumulator free, issue starts
+          for (int kci = 0; kci < p.kcs; ++kci, ++ia) {
+            const int kc = (kci + kc_rot) % p.kcs;
             const int sa = ia % AST, ks = ksteps(kc);
-            for (int tap = 0; tap < kTaps; ++tap, ++ib) {
+            for (int tapi = 0; tapi < kTaps; ++tapi, ++ib) {
+              const int tap = (tapi + tap_rot) % kTaps;
               const int sb = ib % p.b_stages;
-              mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));
-              if (tap == 0) mbar_wait(&a_full[sa], (uint32_t)((ia / AST) & 1));
+              if (!(p.dbg & 4)) mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));  // dbg 4: timing experiment, MMAs do not wait for operands
+              if (kci == 0 && tapi == 0) UNIT_STAMP(ti, 9);  // MMA: first weight tile of conv7(ti) has landed
+              if (tapi == 0 && !(p.dbg & 4)) mbar_wait(&a_full[sa], (uint32_t)((ia / AST) & 1));
+              if (kci == 0 && tapi == 0) UNIT_STAMP(ti, 11);  // MMA: ... and the halo tile
               tc_fence_after();
-              const uint64_t ad = umma_desc_rows(smem_u32(sA + (size_t)sa * kHaloBytes) + (uint32_t)(tap * p.dil) * 128u);
+              const int shift_rows = (p.dbg & 1) ? 0 : ((p.dbg & 2) ? tap * 8 : tap * p.dil);  // dbg: timing experiments only (wrong numerics)
+              const uint64_t ad = umma_desc_rows(smem_u32(sA + (size_t)sa * kHaloBytes) + (uint32_t)shift_rows * 128u);
               const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
-              for (int k = 0; k < ks; ++k) umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < ks; ++k) umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kci | tapi | k) != 0 ? 1u : 0u);
               umma_commit(&b_empty[sb]);
             }
             umma_commit(&a_empty[sa]);
           }
           umma_commit(&acc1_full[buf]);
+          UNIT_STAMP(ti, 1);  // conv7(ti): all MMAs issued
         }
         if (ti > 0) {  // conv1(ti - 1): A = the intermediate in tensor memory, D = the same accumulator columns (drained by E1)
-          const int j = ti - 1, buf = j & 1;
+          const int j = ti - 1, buf = j % NACC;
           const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
           mbar_wait(h_full, (uint32_t)(j & 1));
           tc_fence_after();
-          for (int kc = 0; kc < p.kcs; ++kc, ++ib) {
+          UNIT_STAMP(j, 2);  // conv1(j): intermediate ready, issue starts
+          for (int kci = 0; kci < p.kcs; ++kci, ++ib) {
+            const int kc = (kci + kc_rot) % p.kcs;
             const int sb = ib % p.b_stages, ks = ksteps(kc);
             mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));
             tc_fence_after();
             const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
             for (int k = 0; k < ks; ++k)
-              umma_f16_ts(acc, h_base + (uint32_t)(kc * 32 + 8 * k), bd + (uint64_t)(2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+              umma_f16_ts(acc, h_base + (uint32_t)(kc * 32 + 8 * k), bd + (uint64_t)(2 * k), idesc, (kci | k) != 0 ? 1u : 0u);
             umma_commit(&b_empty[sb]);
           }
           umma_commit(&acc2_full[buf]);
@@ -198,31 +230,30 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int row = q * 32 + lane;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
     const uint32_t h_base = tmem_base + (uint32_t)p.h_col0 + lane_off;
+    const uint32_t patch = smem_u32(patches + (size_t)(warp - 2) * epiio::kPatchBytes);
     pdl_wait();
     for (int ti = 0; ti < n_local; ++ti) {
       const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
       const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
-      const int buf = ti & 1, use = ti >> 1;
+      const int buf = ti % NACC, use = ti / NACC;
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.C) + lane_off;
       const int t = t0 + row;
       const bool row_ok = t < p.T;
       const size_t m = (size_t)bidx * p.T + t;
-      // the residual rows of this thread's first two chunks are requested now: their DRAM round trip hides behind E1
+      // global memory is touched 8 rows x 64 B per warp instruction (epi_io.cuh), never one row per lane.  The residual rows of this
+      // warp's first two chunks are requested now: their DRAM round trip hides behind E1
+      const size_t wrow0 = (size_t)bidx * p.T + (size_t)(t0 + q * 32);
+      const int wvalid = min(32, max(0, p.T - (t0 + q * 32)));
       uint4 rpre[2][4];
-      if (row_ok) {
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int c = (set + u * p.epi_sets) * 32;
-          if (c < p.C) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.C + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rpre[u][j] = rp[j];
-          }
-        }
+      for (int u = 0; u < 2; ++u) {
+        const int c = (set + u * p.epi_sets) * 32;
+        if (c < p.C) epiio::warp_load_64B_rows_issue(reinterpret_cast<const uint8_t*>(p.res16), wrow0, (size_t)p.C * 2, c * 2, rpre[u], lane, wvalid);
       }
       // ---- E1: conv7 accumulator -> bias -> snake2 -> fp16 pairs -> tensor memory
       mbar_wait(&acc1_full[buf], (uint32_t)(use & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) UNIT_STAMP(ti, 3);  // conv7(ti) complete (seen by the epilogue)
       for (int c = set * 32; c < p.C; c += 32 * p.epi_sets) {
         uint32_t raw[32];
         tmem_ld32(acc + (uint32_t)c, raw);
@@ -244,26 +275,25 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       tc_fence_before();  // the accumulator reads and the tensor-memory writes are ordered before the barrier the MMA thread waits on
       __syncwarp();
       if (lane == 0) mbar_arrive(h_full);
+      if (threadIdx.x == 64) UNIT_STAMP(ti, 4);  // E1 done
       // ---- E2: 1x1 accumulator -> bias + residual -> x' (fp16 stream) and snake_next(x') (fp16 operand)
       mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
       tc_fence_after();
+      if (threadIdx.x == 64) UNIT_STAMP(ti, 5);  // conv1(ti) complete
       int ci = 0;
       for (int c = set * 32; c < p.C; c += 32 * p.epi_sets, ++ci) {
         uint32_t raw[32];
         tmem_ld32_issue(acc + (uint32_t)c, raw);
         uint4 rres[4];
-        if (row_ok) {
-          if (ci < 2) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rres[j] = ci == 0 ? rpre[0][j] : rpre[1][j];
-          } else {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.C + c);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) rres[j] = rp[j];
-          }
+        if (ci < 2) {
+          if (ci == 0) epiio::warp_load_64B_rows_complete(rpre[0], rres, patch, lane);
+          else epiio::warp_load_64B_rows_complete(rpre[1], rres, patch, lane);
+        } else {
+          uint4 tmp[4];
+          epiio::warp_load_64B_rows_issue(reinterpret_cast<const uint8_t*>(p.res16), wrow0, (size_t)p.C * 2, c * 2, tmp, lane, wvalid);
+          epiio::warp_load_64B_rows_complete(tmp, rres, patch, lane);
         }
         tmem_ld_wait32(raw);
-        if (!row_ok) continue;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -276,12 +306,13 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             v[e + 1] = r2.y + (__uint_as_float(raw[e + 1]) + s_b1[c + e + 1]);
           }
         }
+        uint4 o4[4];
         if (p.outr16) {
-          uint4* op = reinterpret_cast<uint4*>(p.outr16 + m * p.C + c);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            op[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+            o4[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
                                pack_h2(v[8 * j + 6], v[8 * j + 7]));
+          epiio::warp_store_64B_rows(reinterpret_cast<uint8_t*>(p.outr16), wrow0, (size_t)p.C * 2, c * 2, o4, patch, lane, wvalid);
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -289,15 +320,16 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const float s0 = __sinf(v[j] * a4.x), s1 = __sinf(v[j + 1] * a4.y), s2 = __sinf(v[j + 2] * a4.z), s3 = __sinf(v[j + 3] * a4.w);
           v[j] += i4.x * (s0 * s0); v[j + 1] += i4.y * (s1 * s1); v[j + 2] += i4.z * (s2 * s2); v[j + 3] += i4.w * (s3 * s3);
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out16 + m * p.C + c);
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          op[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
+          o4[j] = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]), pack_h2(v[8 * j + 4], v[8 * j + 5]),
                              pack_h2(v[8 * j + 6], v[8 * j + 7]));
+        epiio::warp_store_64B_rows(reinterpret_cast<uint8_t*>(p.out16), wrow0, (size_t)p.C * 2, c * 2, o4, patch, lane, wvalid);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
+      if (threadIdx.x == 64) UNIT_STAMP(ti, 6);  // E2 done
     }
   }
   tc_fence_before();
@@ -334,13 +366,30 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   p.kcs = (u.C + kBlockK - 1) / kBlockK;
   p.halo_rows = kTileM + (kTaps - 1) * u.dil;
   p.b_bytes = u.C * kBlockK * 2;
-  p.b_stages = std::max(3, std::min(12, (200 * 1024 - 2 * kHaloBytes) / p.b_bytes));
-  p.h_col0 = 2 * u.C;
+  // three accumulators when tensor memory allows (C <= 128): conv7 of tile i+2 runs while E2 drains tile i (with two, the tensor
+  // pipe idles for the length of an E2 per tile); the halo ring holds two tiles' worth of channel blocks so that the next tile's
+  // activations are in flight while this tile's MMAs run
+  static const int acc_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_NACC"); return e ? atoi(e) : 3; }();
+  static const int ast_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ASTAGES"); return e ? atoi(e) : 4; }();
+  p.n_acc = (acc_env >= 3 && 3 * u.C + u.C / 2 <= 512) ? 3 : 2;
+  p.a_stages = std::max(2, std::min(ast_env, 4));
+  const int ring_budget = 212 * 1024 - 12 * epiio::kPatchBytes;  // 188 KB for the two operand rings
+  if (p.b_bytes * 4 + p.a_stages * kHaloBytes > ring_budget) p.a_stages = std::max(2, (ring_budget - 4 * p.b_bytes) / kHaloBytes);
+  p.b_stages = std::max(3, std::min(12, (ring_budget - p.a_stages * kHaloBytes) / p.b_bytes));
+  {
+    static const int bs_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_BSTAGES"); return e ? atoi(e) : 0; }();
+    if (bs_env > 0) p.b_stages = std::min(p.b_stages, bs_env);
+  }
+  p.h_col0 = p.n_acc * u.C;
   int cols = 32;
-  while (cols < 2 * u.C + u.C / 2) cols <<= 1;
+  while (cols < p.n_acc * u.C + u.C / 2) cols <<= 1;
   p.tmem_cols = cols;
   static const int max_sets = [] { const char* e = getenv("Q3TTS_TC_EPI_SETS"); return e ? std::max(1, std::min(3, atoi(e))) : 3; }();
   p.epi_sets = std::max(1, std::min(max_sets, u.C / 32));
+  static const int rot = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ROTATE"); return e ? atoi(e) : 1; }();
+  p.rotate = rot;
+  static const int dbg = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_DBG"); return e ? atoi(e) : 0; }();
+  p.dbg = dbg;
   p.b7 = u.b7; p.ea2 = u.snake2_ea; p.ieb2 = u.snake2_ieb; p.b1 = u.b1; p.ea3 = u.next_ea; p.ieb3 = u.next_ieb;
   p.res16 = u.res16; p.outr16 = u.outr16; p.out16 = u.out16;
 
@@ -348,18 +397,44 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   const uint64_t astr[2] = {(uint64_t)u.C * 2, (uint64_t)u.T * u.C * 2};
   const uint32_t abox[3] = {(uint32_t)kBlockK, (uint32_t)p.halo_rows, 1};
   const CUtensorMap ma = tc_make_map(u.a, 3, adims, astr, abox);
-  const uint64_t w7dims[2] = {(uint64_t)u.C, (uint64_t)kTaps * u.C};
-  const uint64_t wstr[1] = {(uint64_t)u.C * 2};
-  const uint32_t wbox[2] = {(uint32_t)kBlockK, (uint32_t)u.C};
-  const CUtensorMap m7 = tc_make_map(u.w7, 2, w7dims, wstr, wbox);
-  const uint64_t w1dims[2] = {(uint64_t)u.C, (uint64_t)u.C};
-  const CUtensorMap m1 = tc_make_map(u.w1, 2, w1dims, wstr, wbox);
+  p.w7_reps = std::max(1, u.w7_reps); p.w1_reps = std::max(1, u.w1_reps);
+  const uint64_t w7dims[3] = {(uint64_t)u.C, (uint64_t)kTaps * u.C, (uint64_t)p.w7_reps};
+  const uint64_t w7str[2] = {(uint64_t)u.C * 2, p.w7_reps > 1 ? (uint64_t)u.w7_rep_stride * 2 : (uint64_t)kTaps * u.C * u.C * 2};
+  const uint32_t wbox[3] = {(uint32_t)kBlockK, (uint32_t)u.C, 1};
+  const CUtensorMap m7 = tc_make_map(u.w7, 3, w7dims, w7str, wbox);
+  const uint64_t w1dims[3] = {(uint64_t)u.C, (uint64_t)u.C, (uint64_t)p.w1_reps};
+  const uint64_t w1str[2] = {(uint64_t)u.C * 2, p.w1_reps > 1 ? (uint64_t)u.w1_rep_stride * 2 : (uint64_t)u.C * u.C * 2};
+  const CUtensorMap m1 = tc_make_map(u.w1, 3, w1dims, w1str, wbox);
 
-  const size_t smem = (size_t)2 * kHaloBytes + (size_t)p.b_stages * p.b_bytes + 1024 + (size_t)(4 + 2 * p.b_stages + 8) * 8 + 64;
+  const size_t smem = (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * p.b_bytes + 1024 + (size_t)(2 * p.a_stages + 2 * p.b_stages + 12) * 8 + 256 + (size_t)4 * p.epi_sets * epiio::kPatchBytes;
   Q3_CHECK(smem <= 220 * 1024 && p.tmem_cols <= 512, Q3TTS_ERR_CAPACITY, "codec_unit: resources (smem %zu, tmem %d)", smem, p.tmem_cols);
   dim3 grid((unsigned)std::min(p.total_tiles, 148));
+  // measurement hook: Q3TTS_CODEC_UNIT_TRACE=<file> dumps the per-tile clock stamps of the first launch with C == Q3TTS_CODEC_UNIT_TRACE_C (96)
+  static const char* trace_path = getenv("Q3TTS_CODEC_UNIT_TRACE");
+  static bool traced = false;
+  static const int trace_c = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_TRACE_C"); return e ? atoi(e) : 96; }();
+  unsigned long long* tbuf = nullptr;
+  const size_t tn = (size_t)grid.x * kTraceTiles * kTraceSlots;
+  if (trace_path && !traced && u.C == trace_c && !(c.counter && c.counter->capturing)) {
+    traced = true;
+    Q3_CUDA(cudaMalloc(&tbuf, tn * 8));
+    Q3_CUDA(cudaMemsetAsync(tbuf, 0, tn * 8, c.stream));
+  }
+  p.trace = tbuf;
   launch_kernel_pdl(codec_unit_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, m7, m1, p);
   c.tick();
+  if (tbuf) {
+    std::vector<unsigned long long> h(tn);
+    Q3_CUDA(cudaStreamSynchronize(c.stream));
+    Q3_CUDA(cudaMemcpy(h.data(), tbuf, tn * 8, cudaMemcpyDeviceToHost));
+    cudaFree(tbuf);
+    if (FILE* f = fopen(trace_path, "w")) {
+      fprintf(f, "{\"C\": %d, \"dil\": %d, \"ctas\": %u, \"tiles\": %d, \"slots\": %d, \"b_stages\": %d, \"a_stages\": %d, \"stamps\": [", u.C, u.dil, grid.x, kTraceTiles, kTraceSlots, p.b_stages, p.a_stages);
+      for (size_t i = 0; i < tn; ++i) fprintf(f, "%s%llu", i ? "," : "", h[i]);
+      fprintf(f, "]}\n");
+      fclose(f);
+    }
+  }
 }
 
 }  // namespace q3

@@ -14,6 +14,8 @@ struct CodecUnit {
   const float* snake2_ea = nullptr;   // act2: v + ieb[c] * sin^2(v * ea[c])
   const float* snake2_ieb = nullptr;
   const __half* w1 = nullptr;   // [C][C] fp16 (conv2 of the unit, kernel 1)
+  int w7_reps = 1, w1_reps = 1;  // copies of the weights (ConvW::w16_reps), *_rep_stride halves apart: CTA i reads copy i % reps
+  size_t w7_rep_stride = 0, w1_rep_stride = 0;
   const float* b1 = nullptr;
   const __half* res16 = nullptr;  // [Bt*T][C] x, the fp16 residual stream
   __half* outr16 = nullptr;       // x' (may alias res16: a tile reads its own rows before it writes them); null: not needed

@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "gemm_tc.h"
+#include "epi_io.cuh"
 #include "tc_ptx.cuh"
 
 namespace q3 {
@@ -61,6 +62,10 @@ struct TcParams {
   // (12 warps x 2 KB / ~1.2 us of DRAM latency = 20 GB/s per SM -- exactly what the 1x1 convolutions of the vocoder ran at, 30-45 %
   // of their HBM roofline); through the ring the bytes in flight are res_stages whole tiles.
   int res_stages, res_bytes;
+  // fp16 rows (res16 / outr16 / out16) move 8 rows x 64 B per warp instruction through a warp-private shared-memory patch (epi_io.cuh)
+  // instead of one row per lane: the thin vocoder stages were bound by the load/store unit's line visits, not by HBM
+  int tio;
+  int w_reps;
 };
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
@@ -84,6 +89,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* rfull = tmem_empty + 2;         // [res_stages]
   uint64_t* rempty = rfull + p.res_stages;  // [res_stages]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + p.res_stages);
+  uint8_t* patches = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 127) & ~(uintptr_t)127);  // tio: [epilogue warps][2 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_kb = p.ntap * p.kb_per_tap;
@@ -126,6 +132,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
+      const int w_rep = (int)(blockIdx.x % (unsigned)p.w_reps);  // this CTA's copy of the weights (TcGemm::w_reps)
       // Weights never depend on the previous kernel: the first ring-full of B tiles is requested BEFORE the programmatic
       // dependency is resolved, so the weight stream overlaps the predecessor's tail; activations (A) follow the wait.
       // Every CTA of a column of the grid reads the SAME activation tiles: walking K from a per-CTA offset keeps the CTAs
@@ -143,7 +150,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               const int sb = ib % b_st;
               if (ib >= b_st) mbar_wait(&b_empty[sb], (uint32_t)(((ib / b_st) & 1) ^ 1));
               mbar_expect_tx(&b_full[sb], (uint32_t)b_bytes);
-              tma_load_2d(sB + (size_t)sb * b_bytes, &tmB, &b_full[sb], kc * kBlockK, tap * p.N + n0);
+              tma_load_3d(sB + (size_t)sb * b_bytes, &tmB, &b_full[sb], kc * kBlockK, tap * p.N + n0, w_rep);
               ++ib;
             };
             int tap0 = 0;
@@ -200,7 +207,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
             const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
             const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
-            tma_load_2d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0);
+            tma_load_3d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0, w_rep);
           }
           pdl_wait();
           if (p.res_stages) issue_residuals(p.res_stages - 1, true);  // the residual stream was written by the predecessor: after the wait
@@ -213,7 +220,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (kb >= pre) {
             mbar_wait(&empty[s], ph ^ 1);
             mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-            tma_load_2d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0);
+            tma_load_3d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0, w_rep);
           }
           tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
         }
@@ -272,6 +279,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------- epilogue: warp w may touch TMEM lanes [32*(w%4), +32)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const uint32_t patch = smem_u32(patches + (size_t)(warp - 2) * epiio::kPatchBytes);
     pdl_wait();  // residual / bias-free inputs of the epilogue were written by earlier kernels
     for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
     const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
@@ -281,6 +289,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int t = t0 + row;
     const bool row_ok = t < p.T;
     const size_t m = (size_t)bidx * p.T + t;
+    const size_t wrow0 = (size_t)bidx * p.T + (size_t)(t0 + q * 32);   // tio: this warp's first row and how many of its 32 exist
+    const int wvalid = min(32, max(0, p.T - (t0 + q * 32)));
     const int rs = p.res_stages ? ti % p.res_stages : 0;
     if (p.res_stages) mbar_wait(&rfull[rs], (uint32_t)((ti / p.res_stages) & 1));  // this tile's residual rows are in shared memory
     mbar_wait(&tmem_full[acc_i], (uint32_t)(use & 1));
@@ -289,7 +299,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t raw[32];
       tmem_ld32_issue(acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, raw);
       const int nb = n0 + c;
-      const bool live = row_ok && nb < p.N;
+      const bool col_ok = nb < p.N;
+      const bool live = row_ok && col_ok;
       // the residual row segment is requested while the TMEM load is in flight (the epilogue is latency bound: ncu showed its
       // warps waiting on exactly these global loads)
       const int width0 = p.swiglu ? 16 : 32, ob0 = p.swiglu ? (nb >> 1) : nb;
@@ -304,6 +315,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (8 * j < width0) reinterpret_cast<uint4*>(rres)[j] = rp[j];
+      } else if (p.res16 && p.tio && col_ok) {  // all lanes: four lanes fetch 64 contiguous bytes of one row, 8 rows per instruction
+        uint4 tmp[4];
+        epiio::warp_load_64B_rows_issue(reinterpret_cast<const uint8_t*>(p.res16), wrow0, (size_t)p.ld_res * 2, ob0 * 2, tmp, lane, wvalid);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(rres)[j] = tmp[j];
       } else if (p.res16 && live) {  // fp16 residual stream: 8 halves per 16-byte load, widened once they have arrived
         const uint4* rp = reinterpret_cast<const uint4*>(p.res16 + m * p.ld_res + ob0);
 #pragma unroll
@@ -311,12 +327,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (8 * j < width0) reinterpret_cast<uint4*>(rres)[j] = rp[j];
       }
       tmem_ld_wait32(raw);
-      if (!live) continue;
+      if (p.tio ? !col_ok : !live) continue;
+      if (p.tio && p.res16 && !p.res_stages) {  // hand every lane the 64 bytes of ITS row
+        uint4 tmp[4], mine[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tmp[j] = reinterpret_cast<uint4*>(rres)[j];
+        epiio::warp_load_64B_rows_complete(tmp, mine, patch, lane);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(rres)[j] = mine[j];
+      }
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
       if (p.row_scale) {  // folded RMSNorm of the input row (TcGemm::row_scale)
-        const float rs = p.row_scale[m];
+        const float rs = row_ok ? p.row_scale[m] : 0.f;
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] *= rs;
       }
@@ -367,7 +391,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (nb == 0) p.pcm[m] = (v[0] != v[0]) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v[0]));
         continue;
       }
-      if (p.outr16) {
+      if (p.outr16 && p.tio) {
+        uint4 o4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+          __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+          o4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
+        epiio::warp_store_64B_rows(reinterpret_cast<uint8_t*>(p.outr16), wrow0, (size_t)p.ld32 * 2, ob * 2, o4, patch, lane, wvalid);
+      } else if (p.outr16) {
         __half* hp = p.outr16 + m * p.ld32 + ob;
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
@@ -426,6 +459,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         __half* hp = p.out16 + m * p.ld16 + ob;
+        if (p.tio) {
+          uint4 o4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            __half2 h0 = __floats2half2_rn(v[8 * j], v[8 * j + 1]), h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+            __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]), h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+          epiio::warp_store_64B_rows(reinterpret_cast<uint8_t*>(p.out16), wrow0, (size_t)p.ld16 * 2, ob * 2, o4, patch, lane, wvalid);
+        } else
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (j < width) {
@@ -548,7 +591,11 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   p.epi_sets = (persistent && ctas_per_sm == 1) ? std::max(1, std::min(max_sets, p.bn / 32)) : 1;
   // Bytes in flight per SM bound a latency-limited K loop: big grids run 2 CTAs/SM with ~100 KB rings each, small grids
   // (one CTA per SM at most) take the whole shared memory for one deep ring.
-  const int ring_budget = (persistent ? ctas_per_sm == 2 : tiles > 148) ? 100 * 1024 : 200 * 1024;
+  static const bool tio_on = [] { const char* e = getenv("Q3TTS_TC_TIO"); return !(e && atoi(e) == 0); }();
+  p.tio = tio_on && (g.out16 || g.outr16) && !g.swiglu && !g.res && !g.out32 && !g.pcm && g.N % 32 == 0 && g.ld16 % 8 == 0 && (!g.outr16 || g.ld32 % 8 == 0) &&
+          (!g.res16 || g.ld_res % 8 == 0);
+  const int tio_bytes = p.tio ? 256 + 4 * p.epi_sets * epiio::kPatchBytes : 0;
+  const int ring_budget = ((persistent ? ctas_per_sm == 2 : tiles > 148) ? 100 * 1024 : 200 * 1024) - tio_bytes;
   p.stages = std::max(2, std::min(12, ring_budget / stage_bytes));
   if (!persistent) p.stages = std::min(p.stages, std::max(2, g.ntap * p.kb_per_tap));
   // halo mode for multi-tap convolutions whose 128 + (ntap-1)*dil rows fit a 192-row stage.  Opt-in (Q3TTS_TC_HALO=1): exact on
@@ -576,7 +623,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   // residual ring: persistent classic schedule, fp16 residual stream, no SwiGLU column pairing
   static const bool res_ring_on = [] { const char* e = getenv("Q3TTS_TC_RES_RING"); return !(e && atoi(e) == 0); }();
   p.res_stages = 0; p.res_bytes = kTileM * p.bn * 2;
-  if (res_ring_on && g.res16 && persistent && !p.halo && !g.swiglu && p.bn % 8 == 0 && g.N % p.bn == 0) {
+  if (res_ring_on && !p.tio && g.res16 && persistent && !p.halo && !g.swiglu && p.bn % 8 == 0 && g.N % p.bn == 0) {
     int rs = std::max(1, std::min(4, (ring_budget / 2) / p.res_bytes));
     int st = (ring_budget - rs * p.res_bytes) / stage_bytes;
     if (st >= 2) { p.res_stages = rs; p.stages = std::min(p.stages, st); ring_bytes = p.stages * stage_bytes; }
@@ -587,10 +634,11 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const uint64_t astr[2] = {(uint64_t)g.cin * 2, (uint64_t)g.T * g.cin * 2};
   const uint32_t abox[3] = {(uint32_t)kBlockK, (uint32_t)(p.halo ? p.halo_rows : kTileM), 1};
   const CUtensorMap ma = tc_make_map(g.a, 3, adims, astr, abox);
-  const uint64_t bdims[2] = {(uint64_t)g.cin, (uint64_t)g.ntap * g.N};
-  const uint64_t bstr[1] = {(uint64_t)g.cin * 2};
-  const uint32_t bbox[2] = {(uint32_t)kBlockK, (uint32_t)p.bn};
-  const CUtensorMap mb = tc_make_map(g.w, 2, bdims, bstr, bbox);
+  p.w_reps = std::max(1, g.w_reps);
+  const uint64_t bdims[3] = {(uint64_t)g.cin, (uint64_t)g.ntap * g.N, (uint64_t)p.w_reps};
+  const uint64_t bstr[2] = {(uint64_t)g.cin * 2, p.w_reps > 1 ? (uint64_t)g.w_rep_stride * 2 : (uint64_t)g.ntap * g.N * g.cin * 2};
+  const uint32_t bbox[3] = {(uint32_t)kBlockK, (uint32_t)p.bn, 1};
+  const CUtensorMap mb = tc_make_map(g.w, 3, bdims, bstr, bbox);
 
   CUtensorMap mr = mb;  // unused unless the residual ring is on
   if (p.res_stages) {
@@ -602,7 +650,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled (residual tiles) failed with CUresult %d", (int)r);
   }
-  const size_t smem = (size_t)ring_bytes + (size_t)p.res_stages * p.res_bytes + 1024 + 64 * 8;
+  const size_t smem = (size_t)ring_bytes + (size_t)p.res_stages * p.res_bytes + 1024 + 64 * 8 + (size_t)tio_bytes;
   Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
   Q3_CHECK(2 * (p.halo ? p.a_stages + p.b_stages : p.stages) + 5 + 2 * p.res_stages <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
   dim3 grid((unsigned)(persistent ? std::min<long long>(tiles, resident) : tiles));

@@ -19,6 +19,8 @@ struct TcGemm {
   // problem
   const __half* a = nullptr;  // [Bt][T][cin]
   const __half* w = nullptr;  // [ntap][N][cin]
+  int w_reps = 1;             // copies of w, w_rep_stride halves apart (codec.h ConvW::w16_reps): CTA i of the 128-row-tile kernel reads copy i % reps
+  size_t w_rep_stride = 0;
   int Bt = 1, T = 0, cin = 0, N = 0, ntap = 1, dil = 1;
   // epilogue
   const float* bias = nullptr;   // [N]
