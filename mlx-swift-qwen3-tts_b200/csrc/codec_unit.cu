@@ -52,7 +52,7 @@ struct UnitParams {
   int Bt, T, C, dil;
   int tiles_per_batch, total_tiles, kcs, halo_rows;
   int a_stages, n_acc, b_stages, b_bytes;
-  int h_col0, tmem_cols, epi_sets, rotate, dbg, w7_reps, w1_reps;
+  int h_col0, tmem_cols, epi_sets, rotate, w7_reps, w1_reps;
   unsigned long long* trace;  // measurement hook (Q3TTS_CODEC_UNIT_TRACE): [CTA][kTraceTiles][kTraceSlots] clock stamps, or null
   const float *b7, *ea2, *ieb2, *b1, *ea3, *ieb3;
   const __half* res16;
@@ -123,104 +123,145 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // channel blocks from its own offset; the fp32 summation order of a tile then depends on the CTA that computes it (deterministic for
   // a given shape: tile -> CTA is fixed).
   const int tap_rot = p.rotate ? (int)(blockIdx.x % kTaps) : 0, kc_rot = p.rotate ? (int)((blockIdx.x / kTaps) % (unsigned)p.kcs) : 0;
-  auto ksteps = [&](int kc) { const int left = p.C - kc * kBlockK; return left >= kBlockK ? kBlockK / 16 : (left + 15) / 16; };
+  auto ksteps = [&](int kc) { return p.C - kc * kBlockK >= kBlockK ? 4 : 2; };  // C % 32 == 0: a tail block holds 32 channels
+
+  // Ring positions are counters that wrap (stage, parity of the round), never `it % stages` / `it / stages`: a runtime integer division is
+  // ~35 dependent instructions (I2F, MUFU.RCP, F2I, fix-ups), and five of them per 12 KB weight stage in the single MMA-issuing thread WERE
+  // the stage time of the first version (1 000 cycles per stage whatever the ring depth, tap alignment or L2 placement: the thread, not
+  // the memory system or the tensor pipe, was the bottleneck -- tensor pipe 13 % active, L2 20 %).
+  struct Ring {
+    int s = 0, n;
+    uint32_t ph = 0;
+    bool wrapped = false;
+    __device__ explicit Ring(int stages) : n(stages) {}
+    __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; wrapped = true; } }
+  };
+  auto rot_kc = [&](int kci) { const int k = kci + kc_rot; return k >= p.kcs ? k - p.kcs : k; };
+  auto rot_tap = [&](int tapi) { const int t = tapi + tap_rot; return t >= kTaps ? t - kTaps : t; };
 
   if (warp == 0) {
     if (lane == 0) {  // ---------------- TMA producer
-      int ia = 0, ib = 0;
+      Ring ra(AST), rb(p.b_stages);
       bool waited = false;
       const int rep7 = (int)(blockIdx.x % (unsigned)p.w7_reps), rep1 = (int)(blockIdx.x % (unsigned)p.w1_reps);
       auto issue_b = [&](const CUtensorMap* map, int c0, int c1, int rep) {
-        const int sb = ib % p.b_stages;
-        if (ib >= p.b_stages) mbar_wait(&b_empty[sb], (uint32_t)(((ib / p.b_stages) & 1) ^ 1));
-        mbar_expect_tx(&b_full[sb], (uint32_t)p.b_bytes);
-        tma_load_3d(sB + (size_t)sb * p.b_bytes, map, &b_full[sb], c0, c1, rep);
-        ++ib;
+        if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);  // the MMAs of this stage's previous tenant have read it
+        mbar_expect_tx(&b_full[rb.s], (uint32_t)p.b_bytes);
+        tma_load_3d(sB + (size_t)rb.s * p.b_bytes, map, &b_full[rb.s], c0, c1, rep);
+        rb.next();
       };
+      int tile = (int)blockIdx.x;
+      int bidx = tile / p.tiles_per_batch, tin = tile - bidx * p.tiles_per_batch;  // the only divisions: once per CTA
+      const int step_b = (int)gridDim.x / p.tiles_per_batch, step_t = (int)gridDim.x - step_b * p.tiles_per_batch;
       for (int ti = 0; ti <= n_local; ++ti) {
         if (ti < n_local) {  // operands of conv7(ti)
-          const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-          const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
+          const int t0 = tin * kTileM;
           for (int kci = 0; kci < p.kcs; ++kci) {
-            const int kc = (kci + kc_rot) % p.kcs;
+            const int kc = rot_kc(kci);
             int tap0 = 0;
             if (!waited) {  // the first weight tiles do not depend on the predecessor kernel
               const int pre = p.b_stages < kTaps ? p.b_stages : kTaps;
-              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, ((tap0 + tap_rot) % kTaps) * p.C, rep7);
+              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, rot_tap(tap0) * p.C, rep7);
               pdl_wait();
               waited = true;
             }
-            const int sa = ia % AST;
-            if (ia >= AST) mbar_wait(&a_empty[sa], (uint32_t)(((ia / AST) & 1) ^ 1));
+            if (ra.wrapped) mbar_wait(&a_empty[ra.s], ra.ph ^ 1u);
             if (kci == 0) UNIT_STAMP(ti, 10);  // producer: halo tile of the first channel block requested
-            mbar_expect_tx(&a_full[sa], (uint32_t)(p.halo_rows * kBlockK * 2));
-            tma_load_3d(sA + (size_t)sa * kHaloBytes, &tmA, &a_full[sa], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
-            ++ia;
+            mbar_expect_tx(&a_full[ra.s], (uint32_t)(p.halo_rows * kBlockK * 2));
+            tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
+            ra.next();
             for (int tap = tap0; tap < kTaps; ++tap) {
-              issue_b(&tmW7, kc * kBlockK, ((tap + tap_rot) % kTaps) * p.C, rep7);
+              issue_b(&tmW7, kc * kBlockK, rot_tap(tap) * p.C, rep7);
               if (kci == 0 && tap == tap0) UNIT_STAMP(ti, 7);  // producer: first weight tile of conv7(ti) requested
             }
             if (kci == p.kcs - 1) UNIT_STAMP(ti, 8);  // producer: last weight tile of conv7(ti) requested
           }
+          bidx += step_b; tin += step_t;  // next tile of this CTA: tile + gridDim.x
+          if (tin >= p.tiles_per_batch) { tin -= p.tiles_per_batch; ++bidx; }
         }
         if (ti > 0)  // operands of conv1(ti - 1)
-          for (int kci = 0; kci < p.kcs; ++kci) issue_b(&tmW1, ((kci + kc_rot) % p.kcs) * kBlockK, 0, rep1);
+          for (int kci = 0; kci < p.kcs; ++kci) issue_b(&tmW1, rot_kc(kci) * kBlockK, 0, rep1);
       }
       if (!waited) pdl_wait();
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
+    {  // ---------------- MMA issuer: the whole warp walks the loop, one elected lane issues
+      const bool lead = elect_one();
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.C >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t h_base = tmem_base + (uint32_t)p.h_col0;
-      int ia = 0, ib = 0;
+      const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
+      Ring ra(AST), rb(p.b_stages);
+      int buf7 = 0, buf1 = 0;            // accumulator of conv7(ti) / conv1(ti - 1): ti % NACC without the division
+      uint32_t use_par = 1;              // parity of (ti / NACC - 1): flips each time buf7 wraps
+      bool reuse = false;                // ti >= NACC: the accumulator had a previous tenant
+      uint32_t hpar = 0;
       for (int ti = 0; ti <= n_local; ++ti) {
-        if (ti < n_local) {  // conv7(ti) -> accumulator ti % NACC
-          const int buf = ti % NACC, use = ti / NACC;
-          if (use > 0) {
-            mbar_wait(&acc_empty[buf], (uint32_t)((use - 1) & 1));
+        if (ti < n_local) {  // conv7(ti) -> accumulator buf7
+          if (reuse) {
+            mbar_wait(&acc_empty[buf7], use_par);
             tc_fence_after();
           }
-          const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
-          UNIT_STAMP(ti, 0);  // conv7(ti): accumulator free, issue starts
-          for (int kci = 0; kci < p.kcs; ++kci, ++ia) {
-            const int kc = (kci + kc_rot) % p.kcs;
-            const int sa = ia % AST, ks = ksteps(kc);
-            for (int tapi = 0; tapi < kTaps; ++tapi, ++ib) {
-              const int tap = (tapi + tap_rot) % kTaps;
-              const int sb = ib % p.b_stages;
-              if (!(p.dbg & 4)) mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));  // dbg 4: timing experiment, MMAs do not wait for operands
-              if (kci == 0 && tapi == 0) UNIT_STAMP(ti, 9);  // MMA: first weight tile of conv7(ti) has landed
-              if (tapi == 0 && !(p.dbg & 4)) mbar_wait(&a_full[sa], (uint32_t)((ia / AST) & 1));
-              if (kci == 0 && tapi == 0) UNIT_STAMP(ti, 11);  // MMA: ... and the halo tile
+          const uint32_t acc = tmem_base + (uint32_t)(buf7 * p.C);
+          if (lead) UNIT_STAMP(ti, 0);  // conv7(ti): accumulator free, issue starts
+          for (int kci = 0; kci < p.kcs; ++kci) {
+            const int kc = rot_kc(kci);
+            const int ks = ksteps(kc);
+            const uint32_t a_base = sA0 + (uint32_t)ra.s * (uint32_t)kHaloBytes;
+            for (int tapi = 0; tapi < kTaps; ++tapi) {
+              const int tap = rot_tap(tapi);
+              mbar_wait(&b_full[rb.s], rb.ph);
+              if (lead && kci == 0 && tapi == 0) UNIT_STAMP(ti, 9);  // MMA: first weight tile of conv7(ti) has landed
+              if (tapi == 0) mbar_wait(&a_full[ra.s], ra.ph);
+              if (lead && kci == 0 && tapi == 0) UNIT_STAMP(ti, 11);  // MMA: ... and the halo tile
               tc_fence_after();
-              const int shift_rows = (p.dbg & 1) ? 0 : ((p.dbg & 2) ? tap * 8 : tap * p.dil);  // dbg: timing experiments only (wrong numerics)
-              const uint64_t ad = umma_desc_rows(smem_u32(sA + (size_t)sa * kHaloBytes) + (uint32_t)shift_rows * 128u);
-              const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
-              for (int k = 0; k < ks; ++k) umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kci | tapi | k) != 0 ? 1u : 0u);
-              umma_commit(&b_empty[sb]);
+              const uint64_t ad = umma_desc_rows(a_base + (uint32_t)(tap * p.dil) * 128u);
+              const uint64_t bd = umma_desc(sB0 + (uint32_t)rb.s * (uint32_t)p.b_bytes);
+              if (lead) {
+                umma_f16(acc, ad, bd, idesc, (kci | tapi) != 0 ? 1u : 0u);
+                umma_f16(acc, ad + 2u, bd + 2u, idesc, 1u);
+                if (ks == 4) {
+                  umma_f16(acc, ad + 4u, bd + 4u, idesc, 1u);
+                  umma_f16(acc, ad + 6u, bd + 6u, idesc, 1u);
+                }
+                umma_commit(&b_empty[rb.s]);
+              }
+              rb.next();
             }
-            umma_commit(&a_empty[sa]);
+            if (lead) umma_commit(&a_empty[ra.s]);
+            ra.next();
           }
-          umma_commit(&acc1_full[buf]);
-          UNIT_STAMP(ti, 1);  // conv7(ti): all MMAs issued
+          if (lead) {
+            umma_commit(&acc1_full[buf7]);
+            UNIT_STAMP(ti, 1);  // conv7(ti): all MMAs issued
+          }
+          if (++buf7 == NACC) { buf7 = 0; reuse = true; use_par ^= 1u; }
         }
         if (ti > 0) {  // conv1(ti - 1): A = the intermediate in tensor memory, D = the same accumulator columns (drained by E1)
-          const int j = ti - 1, buf = j % NACC;
-          const uint32_t acc = tmem_base + (uint32_t)(buf * p.C);
-          mbar_wait(h_full, (uint32_t)(j & 1));
+          const uint32_t acc = tmem_base + (uint32_t)(buf1 * p.C);
+          mbar_wait(h_full, hpar);
+          hpar ^= 1u;
           tc_fence_after();
-          UNIT_STAMP(j, 2);  // conv1(j): intermediate ready, issue starts
-          for (int kci = 0; kci < p.kcs; ++kci, ++ib) {
-            const int kc = (kci + kc_rot) % p.kcs;
-            const int sb = ib % p.b_stages, ks = ksteps(kc);
-            mbar_wait(&b_full[sb], (uint32_t)((ib / p.b_stages) & 1));
+          if (lead) UNIT_STAMP(ti - 1, 2);  // conv1(ti - 1): intermediate ready, issue starts
+          for (int kci = 0; kci < p.kcs; ++kci) {
+            const int kc = rot_kc(kci);
+            const int ks = ksteps(kc);
+            mbar_wait(&b_full[rb.s], rb.ph);
             tc_fence_after();
-            const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * p.b_bytes));
-            for (int k = 0; k < ks; ++k)
-              umma_f16_ts(acc, h_base + (uint32_t)(kc * 32 + 8 * k), bd + (uint64_t)(2 * k), idesc, (kci | k) != 0 ? 1u : 0u);
-            umma_commit(&b_empty[sb]);
+            const uint64_t bd = umma_desc(sB0 + (uint32_t)rb.s * (uint32_t)p.b_bytes);
+            if (lead) {
+              const uint32_t ha = h_base + (uint32_t)(kc * 32);
+              umma_f16_ts(acc, ha, bd, idesc, kci != 0 ? 1u : 0u);
+              umma_f16_ts(acc, ha + 8u, bd + 2u, idesc, 1u);
+              if (ks == 4) {
+                umma_f16_ts(acc, ha + 16u, bd + 4u, idesc, 1u);
+                umma_f16_ts(acc, ha + 24u, bd + 6u, idesc, 1u);
+              }
+              umma_commit(&b_empty[rb.s]);
+            }
+            rb.next();
           }
-          umma_commit(&acc2_full[buf]);
+          if (lead) umma_commit(&acc2_full[buf1]);
+          if (++buf1 == NACC) buf1 = 0;
         }
       }
     }
@@ -232,10 +273,12 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const uint32_t h_base = tmem_base + (uint32_t)p.h_col0 + lane_off;
     const uint32_t patch = smem_u32(patches + (size_t)(warp - 2) * epiio::kPatchBytes);
     pdl_wait();
+    int bidx = (int)blockIdx.x / p.tiles_per_batch, tin = (int)blockIdx.x - bidx * p.tiles_per_batch;
+    const int step_b = (int)gridDim.x / p.tiles_per_batch, step_t = (int)gridDim.x - step_b * p.tiles_per_batch;
+    int buf = 0;
+    uint32_t upar = 0;  // parity of ti / NACC
     for (int ti = 0; ti < n_local; ++ti) {
-      const int tile = (int)blockIdx.x + ti * (int)gridDim.x;
-      const int bidx = tile / p.tiles_per_batch, t0 = (tile - bidx * p.tiles_per_batch) * kTileM;
-      const int buf = ti % NACC, use = ti / NACC;
+      const int t0 = tin * kTileM;
       const uint32_t acc = tmem_base + (uint32_t)(buf * p.C) + lane_off;
       const int t = t0 + row;
       const bool row_ok = t < p.T;
@@ -251,7 +294,7 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (c < p.C) epiio::warp_load_64B_rows_issue(reinterpret_cast<const uint8_t*>(p.res16), wrow0, (size_t)p.C * 2, c * 2, rpre[u], lane, wvalid);
       }
       // ---- E1: conv7 accumulator -> bias -> snake2 -> fp16 pairs -> tensor memory
-      mbar_wait(&acc1_full[buf], (uint32_t)(use & 1));
+      mbar_wait(&acc1_full[buf], upar);
       tc_fence_after();
       if (threadIdx.x == 64) UNIT_STAMP(ti, 3);  // conv7(ti) complete (seen by the epilogue)
       for (int c = set * 32; c < p.C; c += 32 * p.epi_sets) {
@@ -277,7 +320,7 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) mbar_arrive(h_full);
       if (threadIdx.x == 64) UNIT_STAMP(ti, 4);  // E1 done
       // ---- E2: 1x1 accumulator -> bias + residual -> x' (fp16 stream) and snake_next(x') (fp16 operand)
-      mbar_wait(&acc2_full[buf], (uint32_t)(use & 1));
+      mbar_wait(&acc2_full[buf], upar);
       tc_fence_after();
       if (threadIdx.x == 64) UNIT_STAMP(ti, 5);  // conv1(ti) complete
       int ci = 0;
@@ -330,6 +373,9 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[buf]);
       if (threadIdx.x == 64) UNIT_STAMP(ti, 6);  // E2 done
+      if (++buf == NACC) { buf = 0; upar ^= 1u; }
+      bidx += step_b; tin += step_t;
+      if (tin >= p.tiles_per_batch) { tin -= p.tiles_per_batch; ++bidx; }
     }
   }
   tc_fence_before();
@@ -388,8 +434,6 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   p.epi_sets = std::max(1, std::min(max_sets, u.C / 32));
   static const int rot = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ROTATE"); return e ? atoi(e) : 1; }();
   p.rotate = rot;
-  static const int dbg = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_DBG"); return e ? atoi(e) : 0; }();
-  p.dbg = dbg;
   p.b7 = u.b7; p.ea2 = u.snake2_ea; p.ieb2 = u.snake2_ieb; p.b1 = u.b1; p.ea3 = u.next_ea; p.ieb3 = u.next_ieb;
   p.res16 = u.res16; p.outr16 = u.outr16; p.out16 = u.out16;
 

@@ -53,8 +53,9 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;   // cluster = (1, split, 1): the K slices of one weight tile
   const int n0 = blockIdx.x * kRowsW;
-  const int kb0 = (int)(((long long)rank * p.num_kb) / p.split);
-  const int kb1 = (int)(((long long)(rank + 1) * p.num_kb) / p.split);
+  // split is a power of two (host plan): shifts, not divisions -- a 64-bit division is ~100 instructions in front of the first weight request
+  const int kb0 = (int)((rank * (uint32_t)p.num_kb) >> p.split_shift);
+  const int kb1 = (int)(((rank + 1u) * (uint32_t)p.num_kb) >> p.split_shift);
   const int nkb = kb1 - kb0;
 
   pdl_launch_dependents();
@@ -85,40 +86,58 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
   if (p.split > 1) cluster_arrive_release();
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
+    {  // ---------------- TMA producer: warp-uniform loop, one elected lane issues (tc_ptx.cuh elect_one)
+      const bool lead = elect_one();
       const int pre = nkb < p.stages ? nkb : p.stages;
-      for (int i = 0; i < pre; ++i) {  // weights do not depend on the predecessor kernel
-        mbar_expect_tx(&full[i], (uint32_t)(kWBytes + x_bytes));
-        tma_load_2d(sW + (size_t)i * kWBytes, &tmW, &full[i], (kb0 + i) * kBlockK, n0);
-      }
-      sk_wait_dependency_tma(p);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages, ph = (i / p.stages) & 1;
-        if (i >= pre) {
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], (uint32_t)(kWBytes + x_bytes));
-          tma_load_2d(sW + (size_t)s * kWBytes, &tmW, &full[s], (kb0 + i) * kBlockK, n0);
+      if (lead) {
+        for (int i = 0; i < pre; ++i) {  // weights do not depend on the predecessor kernel
+          mbar_expect_tx(&full[i], (uint32_t)(kWBytes + x_bytes));
+          tma_load_2d(sW + (size_t)i * kWBytes, &tmW, &full[i], (kb0 + i) * kBlockK, n0);
         }
-        tma_load_2d(sX + (size_t)s * x_bytes, &tmX, &full[s], (kb0 + i) * kBlockK, 0);
+      }
+      if (p.sig.in) {
+        if (lead) sk_wait_dependency_tma(p);
+        __syncwarp();
+      } else {
+        pdl_wait();
+      }
+      int s = 0;
+      uint32_t ph = 0;  // ring position as wrapping counters: no integer division per k-block in the issuing threads
+      for (int i = 0; i < nkb; ++i) {
+        if (i >= pre) mbar_wait(&empty[s], ph ^ 1u);
+        if (lead) {
+          if (i >= pre) {
+            mbar_expect_tx(&full[s], (uint32_t)(kWBytes + x_bytes));
+            tma_load_2d(sW + (size_t)s * kWBytes, &tmW, &full[s], (kb0 + i) * kBlockK, n0);
+          }
+          tma_load_2d(sX + (size_t)s * x_bytes, &tmX, &full[s], (kb0 + i) * kBlockK, 0);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T
+    {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T.  The whole warp walks the loop
+       // (uniform registers), one elected lane issues (tc_ptx.cuh elect_one)
+      const bool lead = elect_one();
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.m_pad >> 3) << 17) | ((uint32_t)(kRowsW >> 4) << 24);
+      int s = 0;
+      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % p.stages, ph = (i / p.stages) & 1;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (i == 0) SK_STAMP(3);
+        if (lead && i == 0) SK_STAMP(3);
         const uint64_t ad = umma_desc(smem_u32(sW + (size_t)s * kWBytes));
         const uint64_t bd = umma_desc(smem_u32(sX + (size_t)s * x_bytes));
+        if (lead) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
-        umma_commit(&empty[s]);
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+          umma_commit(&empty[s]);
+        }
+        if (++s == p.stages) { s = 0; ph ^= 1u; }
       }
-      umma_commit(tmem_full);
+      if (lead) umma_commit(tmem_full);
     }
     __syncwarp();
   } else {
@@ -228,6 +247,8 @@ void launch_tc_skinny(const LaunchCtx& c, const TcGemm& g) {
   p.m_pad = s.m_pad; p.split = s.split; p.mc = s.m_pad / s.split; p.stages = s.stages; p.num_kb = s.num_kb;
   p.mc_shift = 0;
   while ((1 << p.mc_shift) < p.mc) ++p.mc_shift;
+  p.split_shift = 0;
+  while ((1 << p.split_shift) < p.split) ++p.split_shift;
   p.tmem_cols = std::max(32, s.m_pad);
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;

@@ -186,8 +186,8 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = p.split > 1 ? cluster_ctarank() : 0u;
   const int n0 = blockIdx.x * kRowsW;
-  const int kb0 = (int)(((long long)rank * p.num_kb) / p.split);
-  const int kb1 = (int)(((long long)(rank + 1) * p.num_kb) / p.split);
+  const int kb0 = (int)((rank * (uint32_t)p.num_kb) >> p.split_shift);  // split is a power of two: no 64-bit division in front of the first request
+  const int kb1 = (int)(((rank + 1u) * (uint32_t)p.num_kb) >> p.split_shift);
   const int nkb = kb1 - kb0;   // <= PS (host plan)
 
   pdl_launch_dependents();
@@ -233,43 +233,53 @@ tc_skinny_q_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constan
         tma_load_2d(sP, &tmP, &pfull[0], kb0 * wpk, n0);
       }
       sk_wait_dependency_tma(p);
+      int xs = 0;
+      uint32_t xph = 1;  // parity of (round - 1): ring positions are wrapping counters, no integer division per k-block
       for (int i = 0; i < nkb; ++i) {
-        const int xs = i % XS;
         if (xs >= XOWN && i < XS) mbar_wait(pdone, 0);                        // the packed region is dead: its bytes may be overwritten
-        if (i >= XS) mbar_wait(&xempty[xs], (uint32_t)(((i / XS) - 1) & 1));  // the MMAs of k-block i - XS have read this stage
+        if (i >= XS) mbar_wait(&xempty[xs], xph);                             // the MMAs of k-block i - XS have read this stage
         mbar_expect_tx(&xfull[xs], (uint32_t)x_bytes);
         tma_load_2d(x_stage(xs), &tmX, &xfull[xs], (kb0 + i) * kBlockK, 0);
+        if (++xs == XS) { xs = 0; xph ^= 1u; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T
+    {  // ---------------- MMA issuer: D[128 weight rows, m_pad activation rows] (+)= W_tile . X^T; warp-uniform loop, one elected lane issues
+      const bool lead = elect_one();
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.m_pad >> 3) << 17) | ((uint32_t)(kRowsW >> 4) << 24);
+      int s = 0, xs = 0;
+      uint32_t aph = 0, xph = 0;
       for (int i = 0; i < nkb; ++i) {
-        const int s = TS ? 0 : i % NA, xs = i % XS;
         if (TS) {
           if (i == 0) mbar_wait(&afull[0], 0);  // every k-block of A sits in tensor memory
         } else {
-          mbar_wait(&afull[s], (uint32_t)((i / AS) & 1));
+          mbar_wait(&afull[s], aph);
         }
-        mbar_wait(&xfull[xs], (uint32_t)((i / XS) & 1));
+        mbar_wait(&xfull[xs], xph);
         tc_fence_after();
-        if (i == 0) SK_STAMP(3);
+        if (lead && i == 0) SK_STAMP(3);
         const uint64_t bd = umma_desc(smem_u32(x_stage(xs)));
         if (TS) {
           const uint32_t at = tmem_base + (uint32_t)p.m_pad + (uint32_t)i * 32u;  // k-block i: 32 columns = 64 fp16 per lane
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) umma_f16_ts(tmem_base, at + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBlockK / 16; ++k) umma_f16_ts(tmem_base, at + (uint32_t)(8 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+          }
         } else {
           const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kWBytes));
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
-          umma_commit(&aempty[s]);
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_f16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (i | k) != 0 ? 1u : 0u);
+            umma_commit(&aempty[s]);
+          }
         }
-        if (i + XS < nkb) umma_commit(&xempty[xs]);
+        if (lead && i + XS < nkb) umma_commit(&xempty[xs]);
+        if (++xs == XS) { xs = 0; xph ^= 1u; }
+        if (!TS && ++s == NA) { s = 0; aph ^= 1u; }
       }
-      umma_commit(tmem_full);
+      if (lead) umma_commit(tmem_full);
     }
     __syncwarp();
   } else {
@@ -509,6 +519,8 @@ void launch_tc_skinny_q(const LaunchCtx& c, const TcGemm& g) {
   p.m_pad = s.m_pad; p.split = s.split; p.mc = s.m_pad / s.split; p.stages = s.a_stages; p.num_kb = s.num_kb;
   p.mc_shift = 0;
   while ((1 << p.mc_shift) < p.mc) ++p.mc_shift;
+  p.split_shift = 0;
+  while ((1 << p.split_shift) < p.split) ++p.split_shift;
   p.tmem_cols = s.tmem_cols;
   p.bias = g.bias; p.res = g.res; p.ld_res = g.ld_res; p.scale = g.scale; p.act = g.act; p.swiglu = g.swiglu;
   p.out32 = g.out32; p.ld32 = g.ld32; p.out16 = g.out16; p.ld16 = g.ld16;

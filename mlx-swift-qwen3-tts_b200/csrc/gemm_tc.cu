@@ -28,6 +28,17 @@ constexpr int kHaloBytes = kHaloRowsMax * kBlockK * 2;  // 24 KB per activation 
 constexpr int kThreads = 192;      // warps 0-1 + one set of 4 epilogue warps
 constexpr int kMaxThreads = 448;   // ... up to three sets (persistent schedule)
 
+// Ring position as counters that wrap (stage, parity of the round) instead of `it % stages` / `(it / stages) & 1`: a runtime integer
+// division is ~35 dependent instructions, and one or two per k-block in the single MMA-issuing (or TMA-issuing) thread cost more than
+// the four MMAs of the k-block (measured in codec_unit.cu: the issuing thread, not memory or the tensor pipe, set the stage time).
+struct TcRing {
+  int s = 0, n;
+  uint32_t ph = 0;
+  bool wrapped = false;
+  __device__ explicit TcRing(int stages) : n(stages) {}
+  __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; wrapped = true; } }
+};
+
 struct TcParams {
   int Bt, T, cin, N, ntap, dil;
   int bn, stages, tiles_per_batch, kb_per_tap, tmem_cols;
@@ -140,18 +151,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.halo) {
         const uint32_t a_tx = (uint32_t)(p.halo_rows * kBlockK * 2);
         uint64_t *a_full = full, *a_empty = empty, *b_full = full + a_st, *b_empty = empty + a_st;
-        int ia = 0, ib = 0;  // activation / weight stages issued so far
+        TcRing ra(a_st), rb(b_st);  // activation / weight rings
         bool waited = false;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
           const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
           const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             auto issue_b = [&](int tap) {
-              const int sb = ib % b_st;
-              if (ib >= b_st) mbar_wait(&b_empty[sb], (uint32_t)(((ib / b_st) & 1) ^ 1));
-              mbar_expect_tx(&b_full[sb], (uint32_t)b_bytes);
-              tma_load_3d(sB + (size_t)sb * b_bytes, &tmB, &b_full[sb], kc * kBlockK, tap * p.N + n0, w_rep);
-              ++ib;
+              if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);
+              mbar_expect_tx(&b_full[rb.s], (uint32_t)b_bytes);
+              tma_load_3d(sB + (size_t)rb.s * b_bytes, &tmB, &b_full[rb.s], kc * kBlockK, tap * p.N + n0, w_rep);
+              rb.next();
             };
             int tap0 = 0;
             if (!waited) {  // the very first weight tiles are requested before the programmatic dependency resolves
@@ -162,16 +172,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             // the activation tile goes out BEFORE the weight tiles that may have to wait for a free stage (the MMA issuer
             // releases weight stages only once it also holds the activation tile)
-            const int sa = ia % a_st;
-            if (ia >= a_st) mbar_wait(&a_empty[sa], (uint32_t)(((ia / a_st) & 1) ^ 1));
-            mbar_expect_tx(&a_full[sa], a_tx);
-            tma_load_3d(sA + (size_t)sa * kHaloBytes, &tmA, &a_full[sa], kc * kBlockK, t0 - (p.ntap - 1) * p.dil, bidx);
-            ++ia;
+            if (ra.wrapped) mbar_wait(&a_empty[ra.s], ra.ph ^ 1u);
+            mbar_expect_tx(&a_full[ra.s], a_tx);
+            tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (p.ntap - 1) * p.dil, bidx);
+            ra.next();
             for (int tap = tap0; tap < p.ntap; ++tap) issue_b(tap);
           }
         }
       } else {
-      int it = 0;  // k-blocks issued by this CTA so far (the ring does not care about tile boundaries)
+      TcRing rg(p.stages);  // the ring does not care about tile boundaries
       int rt = 0;  // residual tiles issued so far (tile sequence numbers of this CTA)
       // residual tiles of this CTA's tiles [rt, upto].  blocking: wait for a stage's previous tenant to be consumed (only ever for the
       // tile the CTA is about to work on: its predecessors' loads are all issued, so their epilogues will run); otherwise stop at the
@@ -203,35 +212,38 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int pre = 0;
         if (ti == 0) {
           pre = num_kb < p.stages ? num_kb : p.stages;
+          int tp = rot / p.kb_per_tap, kc = rot - tp * p.kb_per_tap;  // (tap, channel block) of k-block `rot`, then counted up
           for (int kb = 0; kb < pre; ++kb) {
             mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
-            const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
-            const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
-            tma_load_3d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], c0, tap * p.N + n0, w_rep);
+            tma_load_3d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], kc * kBlockK, tp * p.N + n0, w_rep);
+            if (++kc == p.kb_per_tap) { kc = 0; if (++tp == p.ntap) tp = 0; }
           }
           pdl_wait();
           if (p.res_stages) issue_residuals(p.res_stages - 1, true);  // the residual stream was written by the predecessor: after the wait
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages, ph = (it / p.stages) & 1;
-          const int kr = kb + rot < num_kb ? kb + rot : kb + rot - num_kb;
-          const int tap = kr / p.kb_per_tap, c0 = (kr - tap * p.kb_per_tap) * kBlockK;
+        int tap = rot / p.kb_per_tap, kcb = rot - tap * p.kb_per_tap;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = rg.s, c0 = kcb * kBlockK;
           const int shift = (p.ntap - 1 - tap) * p.dil;
           if (kb >= pre) {
-            mbar_wait(&empty[s], ph ^ 1);
+            if (rg.wrapped) mbar_wait(&empty[s], rg.ph ^ 1u);
             mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
             tma_load_3d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0, w_rep);
           }
           tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
+          rg.next();
+          if (++kcb == p.kb_per_tap) { kcb = 0; if (++tap == p.ntap) tap = 0; }
         }
       }
       }  // classic schedule
     }
   } else if (warp == 1) {
-    if (lane == 0) {  // ---------------- MMA issuer
+    {  // ---------------- MMA issuer: the whole warp walks the loop (uniform registers), one elected lane issues (tc_ptx.cuh elect_one)
+      const bool lead = elect_one();
       // instruction descriptor (cute::UMMA::InstrDescriptor): c = F32 (bit 4), a = b = F16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc = (1u << 4) | ((uint32_t)(p.bn >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      int it = 0, itb = 0;
+      TcRing rg(p.halo ? a_st : p.stages), rb(b_st);  // classic: rg = the one ring; halo: rg = activation ring, rb = weight ring
+      const uint32_t sA0 = smem_u32(sA), sB0 = smem_u32(sB);
       for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
         const int a = p.n_acc == 2 ? (ti & 1) : 0, use = p.n_acc == 2 ? (ti >> 1) : ti;
         if (use > 0) {  // the epilogue must have drained this accumulator's previous tile
@@ -241,38 +253,45 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t acc = tmem_base + (uint32_t)(a * p.acc_cols);
         if (p.halo) {
           uint64_t *a_full = full, *a_empty = empty, *b_full = full + a_st, *b_empty = empty + a_st;
-          for (int kc = 0; kc < p.kb_per_tap; ++kc, ++it) {  // `it` counts activation stages here
-            const int sa = it % a_st;
+          for (int kc = 0; kc < p.kb_per_tap; ++kc) {
+            const int sa = rg.s;
             // the weight stages of this channel block arrive first (the producer issues them first), then the halo tile
-            for (int tap = 0; tap < p.ntap; ++tap, ++itb) {
-              const int sb = itb % b_st;
-              mbar_wait(&b_full[sb], (uint32_t)((itb / b_st) & 1));
-              if (tap == 0) mbar_wait(&a_full[sa], (uint32_t)((it / a_st) & 1));
+            for (int tap = 0; tap < p.ntap; ++tap) {
+              const int sb = rb.s;
+              mbar_wait(&b_full[sb], rb.ph);
+              if (tap == 0) mbar_wait(&a_full[sa], rg.ph);
               tc_fence_after();
-              const uint64_t ad = umma_desc_rows(smem_u32(sA + (size_t)sa * kHaloBytes) + (uint32_t)(tap * p.dil) * 128u);
-              const uint64_t bd = umma_desc(smem_u32(sB + (size_t)sb * b_bytes));
+              const uint64_t ad = umma_desc_rows(sA0 + (uint32_t)sa * (uint32_t)kHaloBytes + (uint32_t)(tap * p.dil) * 128u);
+              const uint64_t bd = umma_desc(sB0 + (uint32_t)sb * (uint32_t)b_bytes);
+              if (lead) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
-              umma_commit(&b_empty[sb]);
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kc | tap | k) != 0 ? 1u : 0u);
+                umma_commit(&b_empty[sb]);
+              }
+              rb.next();
             }
-            umma_commit(&a_empty[sa]);
+            if (lead) umma_commit(&a_empty[sa]);
+            rg.next();
           }
-          umma_commit(&tmem_full[a]);
+          if (lead) umma_commit(&tmem_full[a]);
           continue;
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
-          const int s = it % p.stages, ph = (it / p.stages) & 1;
-          mbar_wait(&full[s], ph);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const int s = rg.s;
+          mbar_wait(&full[s], rg.ph);
           tc_fence_after();
-          const uint64_t ad = umma_desc(smem_u32(sA + (size_t)s * kABytes));
-          const uint64_t bd = umma_desc(smem_u32(sB + (size_t)s * b_bytes));
+          const uint64_t ad = umma_desc(sA0 + (uint32_t)s * (uint32_t)kABytes);
+          const uint64_t bd = umma_desc(sB0 + (uint32_t)s * (uint32_t)b_bytes);
+          if (lead) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
-            umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+            for (int k = 0; k < kBlockK / 16; ++k)  // +32 bytes along K inside the swizzle atom = +2 in the (addr >> 4) field
+              umma_f16(acc, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);  // frees the smem stage when these MMAs have read it
+          }
+          rg.next();
         }
-        umma_commit(&tmem_full[a]);  // accumulator complete
+        if (lead) umma_commit(&tmem_full[a]);  // accumulator complete
       }
     }
   } else {

@@ -41,6 +41,7 @@ struct SkParams {
   int q_pstages;            // packed-tile ring depth
   int q_xstages, q_xown;    // activation stages in total / outside the (dead after dequantisation) packed region
   int q_half_rows;          // SwiGLU over a [gate ; up] matrix: rows of one half (N / 2); tile row 2i = gate i, 2i + 1 = up i.  0: plain rows
+  int split_shift;          // log2(split)
   int q_dbg;                // measurement only (Q3TTS_SKQ_DBG): bit 0 = stamps 10-13 follow the dequantisation instead of the epilogue
 };
 

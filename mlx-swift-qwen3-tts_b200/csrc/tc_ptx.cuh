@@ -47,6 +47,15 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                : "memory");
 }
+// One lane of a converged warp (the others skip the guarded statement).  The MMA / TMA issue loops run WARP-UNIFORM with this as the guard
+// of the tcgen05 / TMA instructions only: ring positions, descriptors and loop counters then live in uniform registers.  Under
+// `if (lane == 0)` the same code is per-thread arithmetic followed by register -> uniform-register moves and single-lane waterfall loops
+// around every such instruction, ~800 cycles per k-block in the one thread the whole CTA waits for (measured, codec_unit.cu).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
