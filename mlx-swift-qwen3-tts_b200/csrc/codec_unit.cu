@@ -140,14 +140,17 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   auto rot_tap = [&](int tapi) { const int t = tapi + tap_rot; return t >= kTaps ? t - kTaps : t; };
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
+    {  // ---------------- TMA producer: warp-uniform loop, one elected lane issues
+      const bool lead = elect_one();
       Ring ra(AST), rb(p.b_stages);
       bool waited = false;
       const int rep7 = (int)(blockIdx.x % (unsigned)p.w7_reps), rep1 = (int)(blockIdx.x % (unsigned)p.w1_reps);
       auto issue_b = [&](const CUtensorMap* map, int c0, int c1, int rep) {
         if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);  // the MMAs of this stage's previous tenant have read it
-        mbar_expect_tx(&b_full[rb.s], (uint32_t)p.b_bytes);
-        tma_load_3d(sB + (size_t)rb.s * p.b_bytes, map, &b_full[rb.s], c0, c1, rep);
+        if (lead) {
+          mbar_expect_tx(&b_full[rb.s], (uint32_t)p.b_bytes);
+          tma_load_3d(sB + (size_t)rb.s * p.b_bytes, map, &b_full[rb.s], c0, c1, rep);
+        }
         rb.next();
       };
       int tile = (int)blockIdx.x;
@@ -166,15 +169,17 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               waited = true;
             }
             if (ra.wrapped) mbar_wait(&a_empty[ra.s], ra.ph ^ 1u);
-            if (kci == 0) UNIT_STAMP(ti, 10);  // producer: halo tile of the first channel block requested
-            mbar_expect_tx(&a_full[ra.s], (uint32_t)(p.halo_rows * kBlockK * 2));
-            tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
+            if (lead) {
+              if (kci == 0) UNIT_STAMP(ti, 10);  // producer: halo tile of the first channel block requested
+              mbar_expect_tx(&a_full[ra.s], (uint32_t)(p.halo_rows * kBlockK * 2));
+              tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
+            }
             ra.next();
             for (int tap = tap0; tap < kTaps; ++tap) {
               issue_b(&tmW7, kc * kBlockK, rot_tap(tap) * p.C, rep7);
-              if (kci == 0 && tap == tap0) UNIT_STAMP(ti, 7);  // producer: first weight tile of conv7(ti) requested
+              if (lead && kci == 0 && tap == tap0) UNIT_STAMP(ti, 7);  // producer: first weight tile of conv7(ti) requested
             }
-            if (kci == p.kcs - 1) UNIT_STAMP(ti, 8);  // producer: last weight tile of conv7(ti) requested
+            if (lead && kci == p.kcs - 1) UNIT_STAMP(ti, 8);  // producer: last weight tile of conv7(ti) requested
           }
           bidx += step_b; tin += step_t;  // next tile of this CTA: tile + gridDim.x
           if (tin >= p.tiles_per_batch) { tin -= p.tiles_per_batch; ++bidx; }

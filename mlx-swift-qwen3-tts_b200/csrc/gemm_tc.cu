@@ -142,7 +142,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {  // ---------------- TMA producer
+    {  // ---------------- TMA producer: warp-uniform loop, one elected lane issues (tc_ptx.cuh elect_one)
+      const bool lead = elect_one();
       const int w_rep = (int)(blockIdx.x % (unsigned)p.w_reps);  // this CTA's copy of the weights (TcGemm::w_reps)
       // Weights never depend on the previous kernel: the first ring-full of B tiles is requested BEFORE the programmatic
       // dependency is resolved, so the weight stream overlaps the predecessor's tail; activations (A) follow the wait.
@@ -159,8 +160,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             auto issue_b = [&](int tap) {
               if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);
-              mbar_expect_tx(&b_full[rb.s], (uint32_t)b_bytes);
-              tma_load_3d(sB + (size_t)rb.s * b_bytes, &tmB, &b_full[rb.s], kc * kBlockK, tap * p.N + n0, w_rep);
+              if (lead) {
+                mbar_expect_tx(&b_full[rb.s], (uint32_t)b_bytes);
+                tma_load_3d(sB + (size_t)rb.s * b_bytes, &tmB, &b_full[rb.s], kc * kBlockK, tap * p.N + n0, w_rep);
+              }
               rb.next();
             };
             int tap0 = 0;
@@ -173,8 +176,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // the activation tile goes out BEFORE the weight tiles that may have to wait for a free stage (the MMA issuer
             // releases weight stages only once it also holds the activation tile)
             if (ra.wrapped) mbar_wait(&a_empty[ra.s], ra.ph ^ 1u);
-            mbar_expect_tx(&a_full[ra.s], a_tx);
-            tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (p.ntap - 1) * p.dil, bidx);
+            if (lead) {
+              mbar_expect_tx(&a_full[ra.s], a_tx);
+              tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (p.ntap - 1) * p.dil, bidx);
+            }
             ra.next();
             for (int tap = tap0; tap < p.ntap; ++tap) issue_b(tap);
           }
@@ -195,10 +200,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (rt >= p.res_stages) {
             const uint32_t par = (uint32_t)(((rt / p.res_stages) - 1) & 1);
             if (blocking) mbar_wait(&rempty[rs], par);
-            else if (!mbar_try_wait(&rempty[rs], par)) break;
+            else if (__shfl_sync(0xffffffffu, (int)mbar_try_wait(&rempty[rs], par), 0) == 0) break;  // one lane's answer for the whole warp
           }
-          mbar_expect_tx(&rfull[rs], (uint32_t)p.res_bytes);
-          tma_load_3d(sR + (size_t)rs * p.res_bytes, &tmR, &rfull[rs], nt * p.bn, tt0, bi);
+          if (lead) {
+            mbar_expect_tx(&rfull[rs], (uint32_t)p.res_bytes);
+            tma_load_3d(sR + (size_t)rs * p.res_bytes, &tmR, &rfull[rs], nt * p.bn, tt0, bi);
+          }
         }
       };
       for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
@@ -214,8 +221,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           pre = num_kb < p.stages ? num_kb : p.stages;
           int tp = rot / p.kb_per_tap, kc = rot - tp * p.kb_per_tap;  // (tap, channel block) of k-block `rot`, then counted up
           for (int kb = 0; kb < pre; ++kb) {
-            mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
-            tma_load_3d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], kc * kBlockK, tp * p.N + n0, w_rep);
+            if (lead) {
+              mbar_expect_tx(&full[kb], (uint32_t)(kABytes + b_bytes));
+              tma_load_3d(sB + (size_t)kb * b_bytes, &tmB, &full[kb], kc * kBlockK, tp * p.N + n0, w_rep);
+            }
             if (++kc == p.kb_per_tap) { kc = 0; if (++tp == p.ntap) tp = 0; }
           }
           pdl_wait();
@@ -225,12 +234,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           const int s = rg.s, c0 = kcb * kBlockK;
           const int shift = (p.ntap - 1 - tap) * p.dil;
-          if (kb >= pre) {
-            if (rg.wrapped) mbar_wait(&empty[s], rg.ph ^ 1u);
-            mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
-            tma_load_3d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0, w_rep);
+          if (kb >= pre && rg.wrapped) mbar_wait(&empty[s], rg.ph ^ 1u);
+          if (lead) {
+            if (kb >= pre) {
+              mbar_expect_tx(&full[s], (uint32_t)(kABytes + b_bytes));
+              tma_load_3d(sB + (size_t)s * b_bytes, &tmB, &full[s], c0, tap * p.N + n0, w_rep);
+            }
+            tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
           }
-          tma_load_3d(sA + (size_t)s * kABytes, &tmA, &full[s], c0, t0 - shift, bidx);
           rg.next();
           if (++kcb == p.kb_per_tap) { kcb = 0; if (++tap == p.ntap) tap = 0; }
         }

@@ -149,7 +149,7 @@ __device__ __forceinline__ void sk_reduce_epilogue(const SkParams& p, float* sta
   if (threadIdx.x == 64 && p.split > 1) {
     mbar_expect_tx(red_full, slice_bytes * (uint32_t)(p.split - 1));
     for (int i = 1; i < p.split; ++i) {
-      const uint32_t d = (rank + (uint32_t)i) % (uint32_t)p.split;
+      const uint32_t d = (rank + (uint32_t)i) & (uint32_t)(p.split - 1);
       bulk_copy_to_rank(map_to_rank(smem_u32(red + (size_t)rank * kRowsW * p.mc), d), smem_u32(stage_out + (size_t)d * kRowsW * p.mc), slice_bytes,
                         map_to_rank(smem_u32(red_full), d));
     }
@@ -170,7 +170,7 @@ __device__ __forceinline__ void sk_reduce_epilogue(const SkParams& p, float* sta
   if (threadIdx.x == 64) {
     SK_STAMP(6);
     // tell every peer that its copy into this CTA is complete (it may retire its staging buffer / exit)
-    for (int i = 1; i < p.split; ++i) mbar_arrive_remote_relaxed(map_to_rank(smem_u32(ack), (rank + (uint32_t)i) % (uint32_t)p.split));
+    for (int i = 1; i < p.split; ++i) mbar_arrive_remote_relaxed(map_to_rank(smem_u32(ack), (rank + (uint32_t)i) & (uint32_t)(p.split - 1)));
   }
   const uint32_t own_s = smem_u32(stage_out), red_s = smem_u32(red);
   for (int cb = 0; cb < p.mc; cb += 16) {

@@ -388,13 +388,15 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
   const int w0 = win_start ? win_start[slot] : 0;
   const int S = pos - w0 + 1;
   const int cap = kv.capacity;
+  const int r0 = w0 % cap;  // ring index of the window's first key: ONE division; key j sits at r0 + j (- cap), never a modulo per key
   const KvT* kb = static_cast<const KvT*>(kv.k) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
   const KvT* vb = static_cast<const KvT*>(kv.v) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
 #pragma unroll
   for (int g = 0; g < G; ++g) q[g * 128 + tid] = qkv[(size_t)row * ld + (size_t)(kvh * G + g) * 128 + tid];
   __syncthreads();
   for (int j = tid; j < S; j += 128) {
-    const KvT* kr = kb + (size_t)((w0 + j) % cap) * 128;
+    const int rj = r0 + j;
+    const KvT* kr = kb + (size_t)(rj >= cap ? rj - cap : rj) * 128;
     float acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = 0.f;
@@ -425,7 +427,8 @@ __global__ void __launch_bounds__(128) attention_kernel(const float* __restrict_
 #pragma unroll
   for (int g = 0; g < G; ++g) o[g] = 0.f;
   for (int j = 0; j < S; ++j) {
-    const float vv = kv_ld(vb + (size_t)((w0 + j) % cap) * 128 + tid);
+    const int rj = r0 + j;
+    const float vv = kv_ld(vb + (size_t)(rj >= cap ? rj - cap : rj) * 128 + tid);
 #pragma unroll
     for (int g = 0; g < G; ++g) o[g] = fmaf(sc[g * S + j], vv, o[g]);
   }
@@ -463,7 +466,8 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
   const int w0 = win_start ? win_start[slot] : 0;
   const int S = pos - w0 + 1;
   const int cap = kv.capacity;
-  const int ring = pos % cap;
+  const int r0 = w0 % cap;  // see attention_kernel: key j of the window sits at ring index r0 + j (- cap)
+  const int ring = (r0 + S - 1 >= cap) ? r0 + S - 1 - cap : r0 + S - 1;  // == pos % cap (S <= cap)
   KvT* kb = static_cast<KvT*>(kv.k) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
   KvT* vb = static_cast<KvT*>(kv.v) + (size_t)slot * kv.slot_stride + (size_t)kvh * cap * 128;
   const float* rowp = qkv + (size_t)row * ld;
@@ -512,7 +516,8 @@ __global__ void __launch_bounds__(128, 4) rope_attention_kernel(const float* __r
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int j = j0 + 16 * u;
-      const size_t base = (size_t)((w0 + (j < S ? j : 0)) % cap) * 128 + seg * 4;
+      const int rj = r0 + (j < S ? j : 0);
+      const size_t base = (size_t)(rj >= cap ? rj - cap : rj) * 128 + seg * 4;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         kk[u][i] = kv_ld4(kb + base + i * 32);
