@@ -297,6 +297,12 @@ def main():
         steps = max(1, a.steps)  # ~4 s of CPU work per step
         v, sec = cpu_sample(ckpt_dir, a.frames, steps, min(a.warmup, 1))
         cores = os.cpu_count() or 1
+        # what THIS arm runs, in its own words: one utterance of the GPU arm's workload per step, batch 1
+        config = dict(config)
+        config["sampled_from"] = config["workload"]
+        config["workload"] = (f"bounded sample of the GPU arm's workload: 1 utterance x {a.frames} frames per step (batch 1 = the reference's only mode), "
+                              f"same stream windows 18/8+18, audio counted as decoded PCM samples; CPU restatement of the reference graph (oracle/), all host cores")
+        config["batch_per_gpu"] = 1
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps, "warmup": min(a.warmup, 1),
                 "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,

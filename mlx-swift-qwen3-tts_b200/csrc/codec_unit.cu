@@ -159,6 +159,7 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int ti = 0; ti <= n_local; ++ti) {
         if (ti < n_local) {  // operands of conv7(ti)
           const int t0 = tin * kTileM;
+          if (lead) UNIT_STAMP(ti, 7);  // producer: starts requesting the operands of conv7(ti)
           for (int kci = 0; kci < p.kcs; ++kci) {
             const int kc = rot_kc(kci);
             int tap0 = 0;
@@ -170,17 +171,13 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             if (ra.wrapped) mbar_wait(&a_empty[ra.s], ra.ph ^ 1u);
             if (lead) {
-              if (kci == 0) UNIT_STAMP(ti, 10);  // producer: halo tile of the first channel block requested
               mbar_expect_tx(&a_full[ra.s], (uint32_t)(p.halo_rows * kBlockK * 2));
               tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
             }
             ra.next();
-            for (int tap = tap0; tap < kTaps; ++tap) {
-              issue_b(&tmW7, kc * kBlockK, rot_tap(tap) * p.C, rep7);
-              if (lead && kci == 0 && tap == tap0) UNIT_STAMP(ti, 7);  // producer: first weight tile of conv7(ti) requested
-            }
-            if (lead && kci == p.kcs - 1) UNIT_STAMP(ti, 8);  // producer: last weight tile of conv7(ti) requested
+            for (int tap = tap0; tap < kTaps; ++tap) issue_b(&tmW7, kc * kBlockK, rot_tap(tap) * p.C, rep7);
           }
+          if (lead) UNIT_STAMP(ti, 8);  // producer: last operand of conv7(ti) requested (stamps stay OUT of the per-stage loops)
           bidx += step_b; tin += step_t;  // next tile of this CTA: tile + gridDim.x
           if (tin >= p.tiles_per_batch) { tin -= p.tiles_per_batch; ++bidx; }
         }
@@ -215,9 +212,7 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int tapi = 0; tapi < kTaps; ++tapi) {
               const int tap = rot_tap(tapi);
               mbar_wait(&b_full[rb.s], rb.ph);
-              if (lead && kci == 0 && tapi == 0) UNIT_STAMP(ti, 9);  // MMA: first weight tile of conv7(ti) has landed
               if (tapi == 0) mbar_wait(&a_full[ra.s], ra.ph);
-              if (lead && kci == 0 && tapi == 0) UNIT_STAMP(ti, 11);  // MMA: ... and the halo tile
               tc_fence_after();
               const uint64_t ad = umma_desc_rows(a_base + (uint32_t)(tap * p.dil) * 128u);
               const uint64_t bd = umma_desc(sB0 + (uint32_t)rb.s * (uint32_t)p.b_bytes);

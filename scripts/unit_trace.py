@@ -4,7 +4,7 @@ import numpy as np
 d = json.load(open(sys.argv[1]))
 S = d.get("slots", 8)
 s = np.array(d["stamps"], dtype=np.int64).reshape(d["ctas"], d["tiles"], S)
-names = ["c7_issue_start", "c7_issued", "c1_issue_start", "c7_done_seen", "e1_done", "c1_done_seen", "e2_done", "P_firstB_req", "P_lastB_req", "M_firstB_in", "P_A_req", "M_A_in"][:S]
+names = ["c7_issue_start", "c7_issued", "c1_issue_start", "c7_done_seen", "e1_done", "c1_done_seen", "e2_done", "P_tile_start", "P_tile_requested", "unused9", "unused10", "unused11"][:S]
 t0 = s[:, 0, 0][:, None, None]
 rel = s - t0
 print(f"C={d['C']} dil={d['dil']} ctas={d['ctas']} b_stages={d.get('b_stages')} a_stages={d.get('a_stages')}")
