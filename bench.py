@@ -311,9 +311,14 @@ def main():
         print(json.dumps(line), flush=True)
         return
 
-    # stdout carries exactly one JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION in this image) would precede it
+    # stdout carries exactly ONE JSON line.  Native libraries write there too (NCCL prints "NCCL version ..." from C on its first
+    # communicator in this image, whatever NCCL_DEBUG says): file descriptor 1 points at stderr for the whole run and the JSON line
+    # goes to the saved descriptor at the end.
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
 
@@ -484,7 +489,9 @@ def main():
                            "frame_step_hbm_frac": (eng_bytes / max(1e-9, talker_ms_frame * 1e-3) / 1e9) / hbm},
                 "other_weight_operand_mode": ab, "config3": cfg3, "config4": cfg4,
                 "wall_s_timed_region": total_max}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    os.close(json_fd)
     if world > 1:
         dist.destroy_process_group()
 
