@@ -52,7 +52,7 @@ struct UnitParams {
   int Bt, T, C, dil;
   int tiles_per_batch, total_tiles, kcs, halo_rows;
   int a_stages, n_acc, b_stages, b_bytes;
-  int h_col0, tmem_cols, epi_sets, rotate, w7_reps, w1_reps;
+  int h_col0, tmem_cols, epi_sets, tps, w7_reps, w1_reps;
   unsigned long long* trace;  // measurement hook (Q3TTS_CODEC_UNIT_TRACE): [CTA][kTraceTiles][kTraceSlots] clock stamps, or null
   const float *b7, *ea2, *ieb2, *b1, *ea3, *ieb3;
   const __half* res16;
@@ -79,8 +79,8 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int AST = p.a_stages, NACC = p.n_acc;
   uint8_t* sA = smem;                                   // [2][192 rows][128 B] halo tiles of snake1(x)
-  uint8_t* sB = smem + (size_t)AST * kHaloBytes;        // [b_stages][C rows][128 B] weight tiles (conv7 taps, then the 1x1)
-  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.b_stages * p.b_bytes);
+  uint8_t* sB = smem + (size_t)AST * kHaloBytes;        // [b_stages][tps][C rows][128 B] weight tiles (conv7 taps, then the 1x1)
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(sB + (size_t)p.b_stages * p.tps * p.b_bytes);
   uint64_t* a_empty = a_full + AST;
   uint64_t* b_full = a_empty + AST;
   uint64_t* b_empty = b_full + p.b_stages;
@@ -118,11 +118,6 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;
   const int n_local = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   // k-steps (K = 16 each) of channel block kc that hold real channels (C = 96: the second block is half zero fill)
-  // Every CTA streams the SAME weight tiles once per 128-row tile: in lock step, 148 SMs would ask the same L2 lines for the same 12-24 KB
-  // at the same time (measured: 3.6 TB/s aggregate L2 -> SM, the unit no faster than its two-kernel form).  Each CTA walks taps and
-  // channel blocks from its own offset; the fp32 summation order of a tile then depends on the CTA that computes it (deterministic for
-  // a given shape: tile -> CTA is fixed).
-  const int tap_rot = p.rotate ? (int)(blockIdx.x % kTaps) : 0, kc_rot = p.rotate ? (int)((blockIdx.x / kTaps) % (unsigned)p.kcs) : 0;
   auto ksteps = [&](int kc) { return p.C - kc * kBlockK >= kBlockK ? 4 : 2; };  // C % 32 == 0: a tail block holds 32 channels
 
   // Ring positions are counters that wrap (stage, parity of the round), never `it % stages` / `it / stages`: a runtime integer division is
@@ -136,8 +131,11 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     __device__ explicit Ring(int stages) : n(stages) {}
     __device__ void next() { if (++s == n) { s = 0; ph ^= 1u; wrapped = true; } }
   };
-  auto rot_kc = [&](int kci) { const int k = kci + kc_rot; return k >= p.kcs ? k - p.kcs : k; };
-  auto rot_tap = [&](int tapi) { const int t = tapi + tap_rot; return t >= kTaps ? t - kTaps : t; };
+  // A ring stage holds p.tps weight tiles (two taps of one channel block, or two channel blocks of the 1x1, when a tile is <= 16 KB):
+  // every wait / fence / commit / descriptor set-up of the issuing warps is paid once per stage, and at C <= 128 a single 12-16 KB
+  // tile carries only ~150 cycles of tensor work against ~500 cycles of issue overhead.
+  const int TPS = p.tps;
+  const int stage_bytes = TPS * p.b_bytes;
 
   if (warp == 0) {
     {  // ---------------- TMA producer: warp-uniform loop, one elected lane issues
@@ -145,11 +143,13 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       Ring ra(AST), rb(p.b_stages);
       bool waited = false;
       const int rep7 = (int)(blockIdx.x % (unsigned)p.w7_reps), rep1 = (int)(blockIdx.x % (unsigned)p.w1_reps);
-      auto issue_b = [&](const CUtensorMap* map, int c0, int c1, int rep) {
+      // n (<= TPS) weight tiles into the next ring stage: tile u = rows [row0 + u * row_step, + C) x channels [c0 + u * c_step, + 64)
+      auto issue_stage = [&](const CUtensorMap* map, int n, int c0, int c_step, int row0, int row_step, int rep) {
         if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);  // the MMAs of this stage's previous tenant have read it
         if (lead) {
-          mbar_expect_tx(&b_full[rb.s], (uint32_t)p.b_bytes);
-          tma_load_3d(sB + (size_t)rb.s * p.b_bytes, map, &b_full[rb.s], c0, c1, rep);
+          uint8_t* dst = sB + (size_t)rb.s * stage_bytes;
+          mbar_expect_tx(&b_full[rb.s], (uint32_t)(n * p.b_bytes));
+          for (int u = 0; u < n; ++u) tma_load_3d(dst + (size_t)u * p.b_bytes, map, &b_full[rb.s], c0 + u * c_step, row0 + u * row_step, rep);
         }
         rb.next();
       };
@@ -160,12 +160,14 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (ti < n_local) {  // operands of conv7(ti)
           const int t0 = tin * kTileM;
           if (lead) UNIT_STAMP(ti, 7);  // producer: starts requesting the operands of conv7(ti)
-          for (int kci = 0; kci < p.kcs; ++kci) {
-            const int kc = rot_kc(kci);
-            int tap0 = 0;
-            if (!waited) {  // the first weight tiles do not depend on the predecessor kernel
-              const int pre = p.b_stages < kTaps ? p.b_stages : kTaps;
-              for (; tap0 < pre; ++tap0) issue_b(&tmW7, kc * kBlockK, rot_tap(tap0) * p.C, rep7);
+          for (int kc = 0; kc < p.kcs; ++kc) {
+            int tap = 0;
+            if (!waited) {  // the first weight stages do not depend on the predecessor kernel
+              for (int st = 0; st < p.b_stages && tap < kTaps; ++st) {
+                const int n = kTaps - tap < TPS ? kTaps - tap : TPS;
+                issue_stage(&tmW7, n, kc * kBlockK, 0, tap * p.C, p.C, rep7);
+                tap += n;
+              }
               pdl_wait();
               waited = true;
             }
@@ -175,14 +177,18 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               tma_load_3d(sA + (size_t)ra.s * kHaloBytes, &tmA, &a_full[ra.s], kc * kBlockK, t0 - (kTaps - 1) * p.dil, bidx);
             }
             ra.next();
-            for (int tap = tap0; tap < kTaps; ++tap) issue_b(&tmW7, kc * kBlockK, rot_tap(tap) * p.C, rep7);
+            while (tap < kTaps) {
+              const int n = kTaps - tap < TPS ? kTaps - tap : TPS;
+              issue_stage(&tmW7, n, kc * kBlockK, 0, tap * p.C, p.C, rep7);
+              tap += n;
+            }
           }
           if (lead) UNIT_STAMP(ti, 8);  // producer: last operand of conv7(ti) requested (stamps stay OUT of the per-stage loops)
           bidx += step_b; tin += step_t;  // next tile of this CTA: tile + gridDim.x
           if (tin >= p.tiles_per_batch) { tin -= p.tiles_per_batch; ++bidx; }
         }
-        if (ti > 0)  // operands of conv1(ti - 1)
-          for (int kci = 0; kci < p.kcs; ++kci) issue_b(&tmW1, rot_kc(kci) * kBlockK, 0, rep1);
+        if (ti > 0)  // operands of conv1(ti - 1): the channel blocks of the 1x1 weight, TPS per stage
+          for (int kc = 0; kc < p.kcs; kc += TPS) issue_stage(&tmW1, p.kcs - kc < TPS ? p.kcs - kc : TPS, kc * kBlockK, kBlockK, 0, 0, rep1);
       }
       if (!waited) pdl_wait();
     }
@@ -205,23 +211,25 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           const uint32_t acc = tmem_base + (uint32_t)(buf7 * p.C);
           if (lead) UNIT_STAMP(ti, 0);  // conv7(ti): accumulator free, issue starts
-          for (int kci = 0; kci < p.kcs; ++kci) {
-            const int kc = rot_kc(kci);
+          for (int kc = 0; kc < p.kcs; ++kc) {
             const int ks = ksteps(kc);
             const uint32_t a_base = sA0 + (uint32_t)ra.s * (uint32_t)kHaloBytes;
-            for (int tapi = 0; tapi < kTaps; ++tapi) {
-              const int tap = rot_tap(tapi);
+            for (int tap = 0; tap < kTaps; tap += TPS) {
+              const int n = kTaps - tap < TPS ? kTaps - tap : TPS;
               mbar_wait(&b_full[rb.s], rb.ph);
-              if (tapi == 0) mbar_wait(&a_full[ra.s], ra.ph);
+              if (tap == 0) mbar_wait(&a_full[ra.s], ra.ph);
               tc_fence_after();
-              const uint64_t ad = umma_desc_rows(a_base + (uint32_t)(tap * p.dil) * 128u);
-              const uint64_t bd = umma_desc(sB0 + (uint32_t)rb.s * (uint32_t)p.b_bytes);
+              const uint32_t b_base = sB0 + (uint32_t)rb.s * (uint32_t)stage_bytes;
               if (lead) {
-                umma_f16(acc, ad, bd, idesc, (kci | tapi) != 0 ? 1u : 0u);
-                umma_f16(acc, ad + 2u, bd + 2u, idesc, 1u);
-                if (ks == 4) {
-                  umma_f16(acc, ad + 4u, bd + 4u, idesc, 1u);
-                  umma_f16(acc, ad + 6u, bd + 6u, idesc, 1u);
+                for (int u = 0; u < n; ++u) {
+                  const uint64_t ad = umma_desc_rows(a_base + (uint32_t)((tap + u) * p.dil) * 128u);
+                  const uint64_t bd = umma_desc(b_base + (uint32_t)u * (uint32_t)p.b_bytes);
+                  umma_f16(acc, ad, bd, idesc, (kc | tap | u) != 0 ? 1u : 0u);
+                  umma_f16(acc, ad + 2u, bd + 2u, idesc, 1u);
+                  if (ks == 4) {
+                    umma_f16(acc, ad + 4u, bd + 4u, idesc, 1u);
+                    umma_f16(acc, ad + 6u, bd + 6u, idesc, 1u);
+                  }
                 }
                 umma_commit(&b_empty[rb.s]);
               }
@@ -242,19 +250,22 @@ codec_unit_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           hpar ^= 1u;
           tc_fence_after();
           if (lead) UNIT_STAMP(ti - 1, 2);  // conv1(ti - 1): intermediate ready, issue starts
-          for (int kci = 0; kci < p.kcs; ++kci) {
-            const int kc = rot_kc(kci);
-            const int ks = ksteps(kc);
+          for (int kc0 = 0; kc0 < p.kcs; kc0 += TPS) {
+            const int n = p.kcs - kc0 < TPS ? p.kcs - kc0 : TPS;
             mbar_wait(&b_full[rb.s], rb.ph);
             tc_fence_after();
-            const uint64_t bd = umma_desc(sB0 + (uint32_t)rb.s * (uint32_t)p.b_bytes);
+            const uint32_t b_base = sB0 + (uint32_t)rb.s * (uint32_t)stage_bytes;
             if (lead) {
-              const uint32_t ha = h_base + (uint32_t)(kc * 32);
-              umma_f16_ts(acc, ha, bd, idesc, kci != 0 ? 1u : 0u);
-              umma_f16_ts(acc, ha + 8u, bd + 2u, idesc, 1u);
-              if (ks == 4) {
-                umma_f16_ts(acc, ha + 16u, bd + 4u, idesc, 1u);
-                umma_f16_ts(acc, ha + 24u, bd + 6u, idesc, 1u);
+              for (int u = 0; u < n; ++u) {
+                const int kc = kc0 + u;
+                const uint64_t bd = umma_desc(b_base + (uint32_t)u * (uint32_t)p.b_bytes);
+                const uint32_t ha = h_base + (uint32_t)(kc * 32);
+                umma_f16_ts(acc, ha, bd, idesc, kc != 0 ? 1u : 0u);
+                umma_f16_ts(acc, ha + 8u, bd + 2u, idesc, 1u);
+                if (ksteps(kc) == 4) {
+                  umma_f16_ts(acc, ha + 16u, bd + 4u, idesc, 1u);
+                  umma_f16_ts(acc, ha + 24u, bd + 6u, idesc, 1u);
+                }
               }
               umma_commit(&b_empty[rb.s]);
             }
@@ -416,12 +427,15 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   // pipe idles for the length of an E2 per tile); the halo ring holds two tiles' worth of channel blocks so that the next tile's
   // activations are in flight while this tile's MMAs run
   static const int acc_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_NACC"); return e ? atoi(e) : 3; }();
-  static const int ast_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ASTAGES"); return e ? atoi(e) : 4; }();
+  static const int ast_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ASTAGES"); return e ? atoi(e) : 3; }();
   p.n_acc = (acc_env >= 3 && 3 * u.C + u.C / 2 <= 512) ? 3 : 2;
   p.a_stages = std::max(2, std::min(ast_env, 4));
   const int ring_budget = 212 * 1024 - 12 * epiio::kPatchBytes;  // 188 KB for the two operand rings
-  if (p.b_bytes * 4 + p.a_stages * kHaloBytes > ring_budget) p.a_stages = std::max(2, (ring_budget - 4 * p.b_bytes) / kHaloBytes);
-  p.b_stages = std::max(3, std::min(12, (ring_budget - p.a_stages * kHaloBytes) / p.b_bytes));
+  static const int tps_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_TPS"); return e ? atoi(e) : 2; }();
+  p.tps = (tps_env >= 2 && p.b_bytes <= 16 * 1024) ? 2 : 1;  // C <= 128: two weight tiles per ring stage
+  const int sbytes = p.tps * p.b_bytes;
+  if (sbytes * 3 + p.a_stages * kHaloBytes > ring_budget) p.a_stages = std::max(2, (ring_budget - 3 * sbytes) / kHaloBytes);
+  p.b_stages = std::max(2, std::min(12, (ring_budget - p.a_stages * kHaloBytes) / sbytes));
   {
     static const int bs_env = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_BSTAGES"); return e ? atoi(e) : 0; }();
     if (bs_env > 0) p.b_stages = std::min(p.b_stages, bs_env);
@@ -432,8 +446,6 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   p.tmem_cols = cols;
   static const int max_sets = [] { const char* e = getenv("Q3TTS_TC_EPI_SETS"); return e ? std::max(1, std::min(3, atoi(e))) : 3; }();
   p.epi_sets = std::max(1, std::min(max_sets, u.C / 32));
-  static const int rot = [] { const char* e = getenv("Q3TTS_CODEC_UNIT_ROTATE"); return e ? atoi(e) : 1; }();
-  p.rotate = rot;
   p.b7 = u.b7; p.ea2 = u.snake2_ea; p.ieb2 = u.snake2_ieb; p.b1 = u.b1; p.ea3 = u.next_ea; p.ieb3 = u.next_ieb;
   p.res16 = u.res16; p.outr16 = u.outr16; p.out16 = u.out16;
 
@@ -450,7 +462,7 @@ void launch_codec_unit(const LaunchCtx& c, const CodecUnit& u) {
   const uint64_t w1str[2] = {(uint64_t)u.C * 2, p.w1_reps > 1 ? (uint64_t)u.w1_rep_stride * 2 : (uint64_t)u.C * u.C * 2};
   const CUtensorMap m1 = tc_make_map(u.w1, 3, w1dims, w1str, wbox);
 
-  const size_t smem = (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * p.b_bytes + 1024 + (size_t)(2 * p.a_stages + 2 * p.b_stages + 12) * 8 + 256 + (size_t)4 * p.epi_sets * epiio::kPatchBytes;
+  const size_t smem = (size_t)p.a_stages * kHaloBytes + (size_t)p.b_stages * p.tps * p.b_bytes + 1024 + (size_t)(2 * p.a_stages + 2 * p.b_stages + 12) * 8 + 256 + (size_t)4 * p.epi_sets * epiio::kPatchBytes;
   Q3_CHECK(smem <= 220 * 1024 && p.tmem_cols <= 512, Q3TTS_ERR_CAPACITY, "codec_unit: resources (smem %zu, tmem %d)", smem, p.tmem_cols);
   dim3 grid((unsigned)std::min(p.total_tiles, 148));
   // measurement hook: Q3TTS_CODEC_UNIT_TRACE=<file> dumps the per-tile clock stamps of the first launch with C == Q3TTS_CODEC_UNIT_TRACE_C (96)

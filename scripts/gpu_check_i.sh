@@ -1,7 +1,7 @@
 #!/bin/bash
-# call B: ncu --set full of the decode-step GEMM at 64 rows (eager frame steps so every launch is visible)
 set -x
 mkdir -p gpurun_out
-python scripts/frame_profile.py 64 2 > gpurun_out/r2_fp_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:tc_skinny_kernel --launch-skip 300 -c 10 -o gpurun_out/r2_skinny64 -f python scripts/frame_profile.py 64 2 > gpurun_out/r2_ncu_skinny.log 2>&1
-tail -2 gpurun_out/r2_ncu_skinny.log; ls -la gpurun_out/r2_skinny64.ncu-rep
+timeout 900 python -m pytest tests/test_gpu_codec.py tests/test_gpu_fullsize.py -x -q -m gpu -k "tensor_core or fused or codec" > gpurun_out/r2_t14.log 2>&1; tail -2 gpurun_out/r2_t14.log
+Q3TTS_CODEC_UNIT_TRACE=gpurun_out/r2_unit_trace96_tps2.json python scripts/codec_probe.py 64 26 3 | tail -n 1
+python scripts/unit_trace.py gpurun_out/r2_unit_trace96_tps2.json | tail -3
+Q3TTS_CODEC_UNIT_TPS=1 python scripts/codec_probe.py 64 26 3 | tail -n 1
