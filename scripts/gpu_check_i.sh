@@ -1,7 +1,6 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_codec.py tests/test_gpu_fullsize.py -x -q -m gpu -k "tensor_core or fused or codec" > gpurun_out/r2_t14.log 2>&1; tail -2 gpurun_out/r2_t14.log
-Q3TTS_CODEC_UNIT_TRACE=gpurun_out/r2_unit_trace96_tps2.json python scripts/codec_probe.py 64 26 3 | tail -n 1
-python scripts/unit_trace.py gpurun_out/r2_unit_trace96_tps2.json | tail -3
-Q3TTS_CODEC_UNIT_TPS=1 python scripts/codec_probe.py 64 26 3 | tail -n 1
+python scripts/codec_probe.py 64 26 2 > gpurun_out/r2_g_plain.jsonl 2> gpurun_out/r2_g.err && \
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_codec_final.csv python scripts/codec_probe.py 64 26 1 > gpurun_out/r2_g_ncu.log 2>&1
+python scripts/summarize_launches.py gpurun_out/r2_launches_codec_final.csv 2>/dev/null | head -6
