@@ -94,6 +94,9 @@ tc_skinny_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant_
           mbar_expect_tx(&full[i], (uint32_t)(kWBytes + x_bytes));
           tma_load_2d(sW + (size_t)i * kWBytes, &tmW, &full[i], (kb0 + i) * kBlockK, n0);
         }
+        // the k-blocks beyond the ring depth cannot be requested before a stage frees (after the dependency): prefetch their weight
+        // tiles into L2 now, so that request is an L2 hit instead of a DRAM round trip on the critical path
+        for (int i = pre; i < nkb; ++i) tma_prefetch_2d(&tmW, (kb0 + i) * kBlockK, n0);
       }
       if (p.sig.in) {
         if (lead) sk_wait_dependency_tma(p);

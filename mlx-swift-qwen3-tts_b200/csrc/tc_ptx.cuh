@@ -42,6 +42,11 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
                : "memory");
 }
+// L2 prefetch of a tensor tile (no shared-memory destination, no barrier): operands beyond the ring depth are pulled from DRAM into L2
+// while the kernel still waits for its predecessor, so their later TMA load is an L2 hit
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
                "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
