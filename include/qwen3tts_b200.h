@@ -69,7 +69,10 @@ typedef struct q3tts_options {
                                inside the tcgen05 kernel (QuantizedLayerFactory.swift:56's quantizedMatmul; 0.5625 B/param from HBM),
                                2 = fp16 operand copies made at load (2 B/param), 0 = the faster of the two as measured (DESIGN.md 3.2;
                                today 2; env Q3TTS_SKINNY_Q=1 flips it).  Same bits either way (the copies ARE the dequantised values). */
-  int32_t reserved[7];
+  int32_t runtime_quantization; /* Qwen3TTSPipelineConfiguration.applyRuntimeQuantization (Qwen3TTSPipeline.swift:25, 184, 961-980): a checkpoint
+                               without a `quantization` block is MLX-quantised at load, group 64, 6 bits for embeddings / q,k,v projections /
+                               heads, 4 bits for the rest (codes held in an 8-bit container).  0 = run the checkpoint as stored */
+  int32_t reserved[6];
 } q3tts_options;
 
 typedef struct q3tts_info {
@@ -232,6 +235,12 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
 /* MLX `dequantized(w, scales:, biases:, groupSize:, bits:, dtype:)` as called at Model/Qwen3Talker.swift:156.
  * packed [out][in*bits/32] uint32, scales/biases [out][in/group] of `scale_dtype`; out [out][in] of `out_dtype`.
  * Contract: deq32 = fp32(scale)*q (rounded) + fp32(bias) (rounded); result = round_to_nearest_even(deq32). */
+/* MLX `quantize(w, group_size: 64, bits)` (affine) on the device -- the quantiser behind q3tts_options.runtime_quantization
+ * (Qwen3TTSPipeline.applyMixedQuantization, Qwen3TTSPipeline.swift:961-980; bits 4, 6 or 8).  w: [out_f][in_f] of w_dtype (host);
+ * codes8_out: [out_f][in_f] bytes, one code per byte (the 8-bit container, = MLX-packed 8-bit words); scales_out / biases_out:
+ * [out_f][in_f / 64] of w_dtype.  Bit-exact against oracle/mlx_quant.py:quantize_codes. */
+q3tts_status q3tts_mlx_quantize(int32_t device, const void* w, int32_t w_dtype, int32_t out_f, int32_t in_f, int32_t bits, uint32_t* codes8_out,
+                                void* scales_out, void* biases_out);
 q3tts_status q3tts_dequantize(int32_t device, const uint32_t* packed, const void* scales, const void* biases,
                               int32_t scale_dtype, int32_t out_features, int32_t in_features, int32_t group_size,
                               int32_t bits, int32_t out_dtype, void* out);

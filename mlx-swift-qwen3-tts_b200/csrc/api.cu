@@ -428,6 +428,7 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
     h->opt.codec_max_batch = o.codec_max_batch > 0 ? o.codec_max_batch : 8;
     Q3_CHECK(o.packed_gemm >= 0 && o.packed_gemm <= 2, Q3TTS_ERR_INVALID_ARG, "options.packed_gemm must be 0, 1 or 2");
     h->opt.packed_gemm = o.packed_gemm;
+    h->opt.runtime_quantization = o.runtime_quantization != 0;
     if (o.cuda_stream) {
       h->stream = (cudaStream_t)o.cuda_stream;
     } else {
@@ -883,6 +884,32 @@ q3tts_status q3tts_dequantize(int32_t device, const uint32_t* packed, const void
     Q3_CUDA(cudaDeviceSynchronize());
     Q3_CUDA(cudaMemcpy(out, dout, obytes, cudaMemcpyDeviceToHost));
     cudaFree(dw); cudaFree(ds); cudaFree(db); cudaFree(dout);
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    return e.status;
+  }
+}
+
+q3tts_status q3tts_mlx_quantize(int32_t device, const void* w, int32_t w_dtype, int32_t out_f, int32_t in_f, int32_t bits, uint32_t* codes8_out,
+                                void* scales_out, void* biases_out) {
+  try {
+    Q3_CHECK(w && codes8_out && scales_out && biases_out, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    Q3_CHECK((bits == 4 || bits == 6 || bits == 8) && in_f > 0 && in_f % 64 == 0 && out_f > 0, Q3TTS_ERR_INVALID_ARG, "unsupported bits / shape (%d, %d x %d)", bits,
+             out_f, in_f);
+    require_device(device);
+    const size_t wbytes = (size_t)out_f * in_f * dtype_size(w_dtype), gbytes = (size_t)out_f * (in_f / 64) * dtype_size(w_dtype), cbytes = (size_t)out_f * in_f;
+    void *dw = nullptr, *ds = nullptr, *db = nullptr, *dc = nullptr;
+    Q3_CUDA(cudaMalloc(&dw, wbytes)); Q3_CUDA(cudaMalloc(&ds, gbytes)); Q3_CUDA(cudaMalloc(&db, gbytes)); Q3_CUDA(cudaMalloc(&dc, cbytes));
+    Q3_CUDA(cudaMemcpy(dw, w, wbytes, cudaMemcpyHostToDevice));
+    LaunchCtx c{nullptr, nullptr};
+    launch_mlx_quantize(c, dw, w_dtype, out_f, in_f, bits, (uint32_t*)dc, ds, db, nullptr);
+    Q3_CUDA(cudaDeviceSynchronize());
+    Q3_CUDA(cudaMemcpy(codes8_out, dc, cbytes, cudaMemcpyDeviceToHost));
+    Q3_CUDA(cudaMemcpy(scales_out, ds, gbytes, cudaMemcpyDeviceToHost));
+    Q3_CUDA(cudaMemcpy(biases_out, db, gbytes, cudaMemcpyDeviceToHost));
+    cudaFree(dw); cudaFree(ds); cudaFree(db); cudaFree(dc);
     return Q3TTS_OK;
   } catch (const Error& e) {
     g_create_error = e.what();

@@ -21,6 +21,7 @@ struct EngineOptions {
   int load_codec = 1, load_talker = 1, codec_max_frames = 2400, codec_max_batch = 8;
   int max_trailing = 1024;
   int packed_gemm = 0;  // q3tts_options::packed_gemm
+  int runtime_quantization = 0;  // q3tts_options::runtime_quantization
 };
 
 // Result of admitting one request into a slot.

@@ -27,6 +27,9 @@ struct LaunchCtx {
 enum Epilogue { EPI_STORE = 0, EPI_ADD = 1, EPI_SILU = 2, EPI_SWIGLU = 3 };
 
 // MLX dequantized() — bit-exact contract in include/qwen3tts_b200.h.  dst [out][in] of out_dt.
+// MLX affine quantiser (group 64, bits 4 / 6 / 8) into an 8-bit container + scales / biases in the weight dtype; `fake`: dequantised copy
+void launch_mlx_quantize(const LaunchCtx& c, const void* w, int wdt, int out, int in, int bits, uint32_t* qw8, void* scales, void* biases,
+                         void* fake);
 void launch_dequantize(const LaunchCtx& c, const uint32_t* qw, const void* scales, const void* biases, int sdt, int out,
                        int in, int group, int bits, int out_dt, void* dst);
 

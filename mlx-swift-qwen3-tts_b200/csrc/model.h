@@ -107,8 +107,8 @@ struct TalkerWeights {
 };
 
 // Loads `model.safetensors` with the key remap of Qwen3Talker.load (Model/Qwen3Talker.swift:117-137).
-void load_talker_weights(const std::string& model_dir, const TalkerConfig& cfg, DeviceArena& arena, cudaStream_t stream,
-                         TalkerWeights& out, int& weight_dtype, int& eff_bits, int& eff_group);
+void load_talker_weights(const std::string& model_dir, const TalkerConfig& cfg, DeviceArena& arena, cudaStream_t stream,  // NOLINT
+                         TalkerWeights& out, int& weight_dtype, int& eff_bits, int& eff_group, bool runtime_quantization = false);
 
 // host float conversions
 inline float bf16_to_f32(uint16_t v) {

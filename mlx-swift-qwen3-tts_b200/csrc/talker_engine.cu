@@ -17,7 +17,7 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
                            LaunchCounter* counter)
     : cfg_(cfg), opt_(opt), stream_(stream), counter_(counter) {
   init_talker_kernels();
-  load_talker_weights(model_dir, cfg_, arena_, stream_, w_, weight_dtype_, eff_bits_, eff_group_);
+  load_talker_weights(model_dir, cfg_, arena_, stream_, w_, weight_dtype_, eff_bits_, eff_group_, opt_.runtime_quantization != 0);
   const int B = opt_.max_batch, C = opt_.kv_capacity, F = opt_.max_frames;
   const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size;
   Q3_CHECK(B >= 1 && C >= 208 && F >= 1, Q3TTS_ERR_INVALID_ARG, "bad options: max_batch %d kv_capacity %d max_frames %d", B, C, F);

@@ -49,6 +49,70 @@ void launch_dequantize(const LaunchCtx& c, const uint32_t* qw, const void* scale
   c.tick();
 }
 
+// ------------------------------------------------------------------------------------------------ runtime quantisation
+// MLX `quantize(w, group_size: 64, bits)` (affine), one thread per group of 64 weights, restated operation for operation from
+// oracle/mlx_quant.py:quantize (every fp32 step rounded on its own: no FMA contraction, IEEE division, round-half-even):
+//     s = max((max - min) / (2^bits - 1), 1e-7), sign by the larger-magnitude edge; q0 = rint(edge / s); s = edge / q0 if q0 != 0;
+//     b = q0 == 0 ? 0 : edge; s, b rounded to the weight dtype; q = clip(rint((w - b) / s), 0, 2^bits - 1)
+// The codes go into an 8-BIT container whatever `bits` is (4 or 6: Qwen3TTSPipeline.applyMixedQuantization, :961-980), so every 8-bit
+// kernel of the engine runs them; `fake` (optional) receives dequantised values in the weight dtype (quantised embeddings).
+__global__ void mlx_quantize_kernel(const void* __restrict__ w, int wdt, size_t groups, int in, int bits, uint32_t* __restrict__ qw8,
+                                    void* __restrict__ scales, void* __restrict__ biases, void* __restrict__ fake) {
+  const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= groups) return;
+  const int gpr = in / 64;
+  const size_t row = g / gpr;
+  const size_t e0 = row * (size_t)in + (size_t)(g - row * gpr) * 64;
+  float v[64];
+  float mx = -INFINITY, mn = INFINITY;
+#pragma unroll 8
+  for (int j = 0; j < 64; ++j) {
+    v[j] = load_as_f32(w, e0 + j, wdt);
+    mx = fmaxf(mx, v[j]);
+    mn = fminf(mn, v[j]);
+  }
+  const float n_bins = (float)((1 << bits) - 1);
+  const bool side = fabsf(mn) > fabsf(mx);
+  float s = fmaxf(__fdiv_rn(__fsub_rn(mx, mn), n_bins), 1e-7f);
+  s = side ? s : -s;
+  const float edge = side ? mn : mx;
+  const float q0 = rintf(__fdiv_rn(edge, s));
+  if (q0 != 0.f) s = __fdiv_rn(edge, q0);
+  float b = q0 == 0.f ? 0.f : edge;
+  // round to the weight dtype (MLX returns scales / biases in the dtype of w)
+  if (wdt == Q3TTS_BF16) { s = __bfloat162float(__float2bfloat16_rn(s)); b = __bfloat162float(__float2bfloat16_rn(b)); }
+  else if (wdt == Q3TTS_F16) { s = __half2float(__float2half_rn(s)); b = __half2float(__float2half_rn(b)); }
+  const float s_safe = s == 0.f ? 1e-7f : s;
+  if (wdt == Q3TTS_F32) { reinterpret_cast<float*>(scales)[g] = s; reinterpret_cast<float*>(biases)[g] = b; }
+  else if (wdt == Q3TTS_F16) { reinterpret_cast<__half*>(scales)[g] = __float2half_rn(s); reinterpret_cast<__half*>(biases)[g] = __float2half_rn(b); }
+  else { reinterpret_cast<__nv_bfloat16*>(scales)[g] = __float2bfloat16_rn(s); reinterpret_cast<__nv_bfloat16*>(biases)[g] = __float2bfloat16_rn(b); }
+#pragma unroll 4
+  for (int j = 0; j < 64; j += 4) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float q = fminf(fmaxf(rintf(__fdiv_rn(__fsub_rn(v[j + u], b), s_safe)), 0.f), n_bins);
+      word |= (uint32_t)q << (8 * u);
+      if (fake) {
+        const float d = __fadd_rn(__fmul_rn(s, q), b);  // the q3tts_dequantize contract
+        const size_t o = e0 + j + u;
+        if (wdt == Q3TTS_F32) reinterpret_cast<float*>(fake)[o] = d;
+        else if (wdt == Q3TTS_F16) reinterpret_cast<__half*>(fake)[o] = __float2half_rn(d);
+        else reinterpret_cast<__nv_bfloat16*>(fake)[o] = __float2bfloat16_rn(d);
+      }
+    }
+    if (qw8) qw8[(e0 + j) >> 2] = word;
+  }
+}
+
+void launch_mlx_quantize(const LaunchCtx& c, const void* w, int wdt, int out, int in, int bits, uint32_t* qw8, void* scales, void* biases,
+                         void* fake) {
+  Q3_CHECK(in % 64 == 0 && (bits == 4 || bits == 6 || bits == 8), Q3TTS_ERR_INVALID_ARG, "mlx_quantize: in %d / bits %d unsupported", in, bits);
+  const size_t groups = (size_t)out * (in / 64);
+  mlx_quantize_kernel<<<(unsigned)((groups + 127) / 128), 128, 0, c.stream>>>(w, wdt, groups, in, bits, qw8, scales, biases, fake);
+  c.tick();
+}
+
 // ------------------------------------------------------------------------------------------------ GEMV / small-M linear
 struct LinearKArgs {
   const void* w;        // packed or dense weights, row-major

@@ -128,7 +128,17 @@ struct Loader {
   bool packed;          // use uint32 leaves as they are
   bool offline_dequant; // uint32 leaves -> fp16 dense at load (Qwen3Talker.swift:139-175)
   int bits, group;
+  // Qwen3TTSPipeline.applyMixedQuantization (:961-980): every dense Linear / Embedding is MLX-quantised at load, group 64, 6 bits for
+  // embeddings, q/k/v projections and the heads, 4 bits for the rest; the codes live in an 8-bit container (launch_mlx_quantize)
+  bool runtime_quant = false;
   int weight_dtype = -1;
+  static bool six_bit(const std::string& path) {
+    std::string p = path;
+    for (char& ch : p) ch = (char)tolower((unsigned char)ch);
+    for (const char* k : {"embed", "qproj", "kproj", "vproj", "q_proj", "k_proj", "v_proj", "lm_head", "codec_head"})
+      if (p.find(k) != std::string::npos) return true;
+    return false;
+  }
 
   const STensor& get(const std::string& k) const {
     auto it = t.find(k);
@@ -160,7 +170,17 @@ struct Loader {
     e.rows = rows; e.dim = dim; e.dt = s.q3_dtype();
     const size_t bytes = (size_t)rows * dim * dtype_size(e.dt);
     Q3_CHECK(s.nbytes == bytes, Q3TTS_ERR_BAD_WEIGHTS, "embedding '%s' has the wrong byte size", k.c_str());
-    e.w = upload(s.data, bytes);
+    void* d = upload(s.data, bytes);
+    if (runtime_quant && dim % 64 == 0) {  // QuantizedEmbedding: rows dequantised to the storage dtype, 6 bits ("embed")
+      LaunchCtx lc{stream, nullptr};
+      void *sc = nullptr, *bi = nullptr;
+      const size_t gb = (size_t)rows * (dim / 64) * dtype_size(e.dt);
+      Q3_CUDA(cudaMalloc(&sc, gb)); Q3_CUDA(cudaMalloc(&bi, gb));
+      launch_mlx_quantize(lc, d, e.dt, rows, dim, 6, nullptr, sc, bi, d);  // in place: a group is read completely before it is written
+      Q3_CUDA(cudaStreamSynchronize(stream));
+      cudaFree(sc); cudaFree(bi);
+    }
+    e.w = d;
     return e;
   }
 
@@ -229,6 +249,16 @@ struct Loader {
       if (weight_dtype < 0) weight_dtype = sdt;
       L.bits = 0; L.sdt = sdt; L.w = w;
     }
+    if (runtime_quant && L.bits == 0 && in % 64 == 0) {  // the dense copy stays in the arena (load-time cost only; the kernels read the codes)
+      const int qbits = six_bit(prefixes[0]) ? 6 : 4;
+      const size_t gb = (size_t)L.out * (in / 64) * dtype_size(L.sdt);
+      uint32_t* qw = (uint32_t*)arena.alloc((size_t)L.out * in);
+      void* sc = arena.alloc(gb);
+      void* bi = arena.alloc(gb);
+      LaunchCtx lc{stream, nullptr};
+      launch_mlx_quantize(lc, L.w, L.sdt, L.out, in, qbits, qw, sc, bi, nullptr);
+      L.bits = 8; L.group = 64; L.qw = qw; L.scales = sc; L.biases = bi; L.w = nullptr;
+    }
     if (with_bias) {
       std::vector<float> hb;
       for (size_t i = 0; i < prefixes.size(); ++i) {
@@ -272,7 +302,7 @@ size_t stack_bytes(const StackWeights& s) {
 }  // namespace
 
 void load_talker_weights(const std::string& model_dir, const TalkerConfig& cfg, DeviceArena& arena, cudaStream_t stream,
-                         TalkerWeights& out, int& weight_dtype, int& eff_bits, int& eff_group) {
+                         TalkerWeights& out, int& weight_dtype, int& eff_bits, int& eff_group, bool runtime_quantization) {
   SafeTensors st(model_dir + "/model.safetensors");
   // key remap (Qwen3Talker.swift:117-137): drop audio_decoder.*, strip "talker.", "code_predictor.model." ->
   // "code_predictor.", strip "model."
@@ -293,6 +323,7 @@ void load_talker_weights(const std::string& model_dir, const TalkerConfig& cfg, 
   else if (cfg.has_quantization && cfg.q_bits) { bits = cfg.q_bits; group = cfg.q_group; }
   else if (!packed) { bits = 8; group = 64; }  // defaults of the offline path (:142-143)
   Loader L{t, arena, stream, packed, !packed, bits, group};
+  L.runtime_quant = runtime_quantization && !cfg.has_quantization;  // `modelConfig.quantization == nil && applyRuntimeQuantization` (:184)
 
   out.talker.hidden = cfg.hidden_size; out.talker.layers = cfg.num_hidden_layers; out.talker.heads = cfg.num_attention_heads;
   out.talker.kv_heads = cfg.num_key_value_heads; out.talker.head_dim = cfg.head_dim; out.talker.inter = cfg.intermediate_size;

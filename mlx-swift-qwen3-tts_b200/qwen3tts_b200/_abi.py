@@ -26,7 +26,7 @@ p_i32, p_f32 = C.POINTER(C.c_int32), C.POINTER(C.c_float)
 class Options(C.Structure):
     _fields_ = [("struct_size", i32), ("device", i32), ("cuda_stream", C.c_void_p), ("max_batch", i32), ("kv_capacity", i32),
                 ("max_frames", i32), ("use_cuda_graph", i32), ("load_codec", i32), ("load_talker", i32),
-                ("codec_max_frames", i32), ("codec_max_batch", i32), ("packed_gemm", i32), ("reserved", i32 * 7)]
+                ("codec_max_frames", i32), ("codec_max_batch", i32), ("packed_gemm", i32), ("runtime_quantization", i32), ("reserved", i32 * 6)]
 
 
 class Info(C.Structure):
@@ -77,6 +77,7 @@ SYMBOLS = {
     "q3tts_decode_chunked": (i32, [C.c_void_p, p_i32, i32, i32, i32, i32, p_f32]),
     "q3tts_generate_pcm": (i32, [C.c_void_p, C.POINTER(Request), i32, p_f32, i64, C.POINTER(i64), p_i32]),
     "q3tts_generate_pcm_batch": (i32, [C.c_void_p, C.POINTER(Request), i32, i32, C.POINTER(p_f32), i64, C.POINTER(i64), p_i32]),
+    "q3tts_mlx_quantize": (i32, [i32, C.c_void_p, i32, i32, i32, i32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "q3tts_dequantize": (i32, [i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, i32, C.c_void_p]),
     "q3tts_quantized_matmul": (i32, [i32, p_f32, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, p_f32]),
     "q3tts_quantized_matmul_tc": (i32, [i32, p_f32, i32, C.c_void_p, C.c_void_p, C.c_void_p, i32, i32, i32, i32, i32, p_f32, i32, p_f32, p_f32]),

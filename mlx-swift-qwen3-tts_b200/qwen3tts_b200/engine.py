@@ -131,7 +131,7 @@ class CodeStream:
 class Engine:
     def __init__(self, model_dir: str, device: int = 0, max_batch: int = 1, kv_capacity: int = 512, max_frames: int = 2400,
                  use_cuda_graph: bool = True, load_codec: bool = True, load_talker: bool = True, codec_max_frames: int = 2400,
-                 cuda_stream: int | None = None, packed_gemm: int = 0):
+                 cuda_stream: int | None = None, packed_gemm: int = 0, runtime_quantization: bool = False):
         L = A.lib()
         o = A.Options()
         L.q3tts_default_options(C.byref(o))
@@ -139,6 +139,7 @@ class Engine:
         o.use_cuda_graph = 1 if use_cuda_graph else 0
         o.load_codec, o.load_talker, o.codec_max_frames = int(load_codec), int(load_talker), codec_max_frames
         o.packed_gemm = int(packed_gemm)
+        o.runtime_quantization = 1 if runtime_quantization else 0
         if cuda_stream:
             o.cuda_stream = C.c_void_p(cuda_stream)
         h = C.c_void_p()
@@ -345,6 +346,24 @@ def dequantize(packed, scales, biases, group_size=64, bits=4, scale_dtype="bf16"
     if out_dtype == "bf16":
         return (out.astype(np.uint32) << 16).view(np.float32)
     return out
+
+
+def mlx_quantize(w, bits=4, dtype="bf16", device=0):
+    """`q3tts_mlx_quantize` probe: w fp32 numpy holding `dtype`-representable values -> (codes uint8 [out, in], scales, biases as fp32 numpy
+    holding the `dtype` values)."""
+    w = np.ascontiguousarray(w, dtype=np.float32)
+    out_f, in_f = w.shape
+    raw = _raw16(w, dtype) if dtype != "f32" else w
+    codes = np.zeros((out_f, in_f), dtype=np.uint8)
+    g = (out_f, in_f // 64)
+    s = np.zeros(g, dtype=np.float32 if dtype == "f32" else np.uint16)
+    b = np.zeros_like(s)
+    A.check(A.lib().q3tts_mlx_quantize(device, raw.ctypes.data, _DT[dtype], out_f, in_f, bits, codes.ctypes.data, s.ctypes.data, b.ctypes.data), None)
+    if dtype == "f16":
+        return codes, s.view(np.float16).astype(np.float32), b.view(np.float16).astype(np.float32)
+    if dtype == "bf16":
+        return codes, (s.astype(np.uint32) << 16).view(np.float32), (b.astype(np.uint32) << 16).view(np.float32)
+    return codes, s, b
 
 
 def quantized_matmul(x, packed, scales, biases, group_size=64, bits=4, scale_dtype="bf16", device=0) -> np.ndarray:

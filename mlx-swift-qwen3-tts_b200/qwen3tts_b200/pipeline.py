@@ -37,7 +37,7 @@ class AudioChunk:  # Qwen3TTSPipeline.swift:6-19
 
 @dataclass
 class Qwen3TTSPipelineConfiguration:  # Qwen3TTSPipeline.swift:22-54
-    apply_runtime_quantization: bool = True  # accepted for API parity; the engine runs checkpoints as stored
+    apply_runtime_quantization: bool = True  # :25, :184: a checkpoint without a `quantization` block is quantised 4/6-bit at load
     default_temperature: float = 0.85
     default_max_tokens: int = 2400
     default_streaming_chunk_size: int = 12
@@ -209,7 +209,7 @@ class Qwen3TTSPipeline:
         try:
             self.engine = Engine(model_path, device=self.config.device, max_batch=self.config.max_batch,
                                  kv_capacity=self.config.kv_capacity, max_frames=max(self.config.default_max_tokens, 600),
-                                 use_cuda_graph=self.config.use_cuda_graph)
+                                 use_cuda_graph=self.config.use_cuda_graph, runtime_quantization=self.config.apply_runtime_quantization)
         except A.Q3Error as e:
             if e.status == A.ERR_FILE_NOT_FOUND:
                 raise FileNotFound(e.message.split(": ", 1)[-1]) from e

@@ -17,7 +17,7 @@ public struct AudioChunk: Sendable {
 }
 
 public struct Qwen3TTSPipelineConfiguration: Sendable {
-    public var applyRuntimeQuantization: Bool   // accepted for source compatibility; the engine runs checkpoints as stored
+    public var applyRuntimeQuantization: Bool   // q3tts_options.runtime_quantization: mixed 4/6-bit MLX quantisation at load
     public var defaultTemperature: Float
     public var defaultMaxTokens: Int
     public var defaultStreamingChunkSize: Int
@@ -72,6 +72,7 @@ public final class Qwen3TTSPipeline: @unchecked Sendable {
         var opts = q3tts_options()
         q3tts_default_options(&opts)
         opts.device = configuration.device
+        opts.runtime_quantization = configuration.applyRuntimeQuantization ? 1 : 0
         opts.max_frames = Int32(max(configuration.defaultMaxTokens, 600))
         var h: OpaquePointer?
         let st = q3tts_create(modelPath.path, &opts, &h)

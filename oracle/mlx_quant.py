@@ -54,9 +54,16 @@ def quantize(w: np.ndarray, group_size: int = 64, bits: int = 4, scale_dtype: st
     triple on disk is self-consistent; they are returned as fp32 holding those rounded values.
     """
     assert bits in (4, 8) and 32 % bits == 0
+    q, s, b = quantize_codes(w, group_size, bits, scale_dtype)
+    return pack(q, bits), s, b
+
+
+def quantize_codes(w: np.ndarray, group_size: int = 64, bits: int = 4, scale_dtype: str = "bf16"):
+    """The quantiser itself for any bit width (4, 6, 8): integer codes [out, in] (uint32), scales, biases (fp32 holding `scale_dtype` values).
+    `pack(codes, 8)` is the 8-bit container the engine keeps runtime-quantised 4/6-bit leaves in (Qwen3TTSPipeline.swift:961-980)."""
     w = np.ascontiguousarray(w, dtype=np.float32)
     out, inn = w.shape
-    assert inn % group_size == 0 and group_size % (32 // bits) == 0
+    assert inn % group_size == 0
     g = w.reshape(out, inn // group_size, group_size)
     n_bins = np.float32((1 << bits) - 1)
     w_max = g.max(axis=-1)
@@ -72,7 +79,19 @@ def quantize(w: np.ndarray, group_size: int = 64, bits: int = 4, scale_dtype: st
     b = round_to_dtype(b, scale_dtype)
     s_safe = np.where(s == 0, np.float32(1e-7), s)
     q = np.clip(np.rint((g - b[..., None]) / s_safe[..., None]), 0, n_bins).astype(np.uint32)
-    return pack(q.reshape(out, inn), bits), s, b
+    return q.reshape(out, inn), s, b
+
+
+def runtime_bits(path: str) -> int:
+    """applyMixedQuantization's rule (Qwen3TTSPipeline.swift:966-980): 6 bits for embeddings, q/k/v projections and the heads, else 4."""
+    p = path.lower()
+    return 6 if any(k in p for k in ("embed", "qproj", "kproj", "vproj", "q_proj", "k_proj", "v_proj", "lm_head", "codec_head")) else 4
+
+
+def fake_quantize(w: np.ndarray, bits: int, scale_dtype: str = "bf16", out_dtype: str = "f32") -> np.ndarray:
+    """dequantize(quantize(w)) for group 64 and any bit width: what a runtime-quantised leaf multiplies with."""
+    q, s, b = quantize_codes(w, 64, bits, scale_dtype)
+    return dequantize(pack(q, 8), s, b, 64, 8, out_dtype)
 
 
 def pack(q: np.ndarray, bits: int) -> np.ndarray:

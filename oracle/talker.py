@@ -93,7 +93,10 @@ def counter_uniform(seed: int, counter: int, n: int) -> np.ndarray:
 
 
 class TalkerOracle:
-    def __init__(self, model_dir: str):
+    def __init__(self, model_dir: str, runtime_quantization: bool = False):
+        """runtime_quantization: `Qwen3TTSPipelineConfiguration.applyRuntimeQuantization` (Qwen3TTSPipeline.swift:25, 184, 961-980) -- a
+        checkpoint without a `quantization` block has every Linear / Embedding weight MLX-quantised at load (group 64; 6 bits for embeddings,
+        q/k/v projections and the heads, 4 bits for the rest); the oracle multiplies with the dequantised values."""
         self.cfg, extra = load_config(model_dir)
         self.spk_id = extra["spk_id"]
         # usePreQuantized = config.quantization != nil (Qwen3Talker.swift:139); otherwise packed leaves are dequantised offline
@@ -126,6 +129,17 @@ class TalkerOracle:
                                                                   self.group, self.bits, deq_dtype))
             else:
                 self.w[k] = v.to(torch.float32)
+        if runtime_quantization and not self.pre_quantized:
+            names = {torch.bfloat16: "bf16", torch.float16: "f16", torch.float32: "f32"}
+            for k in list(self.w):
+                w = self.w[k]
+                if not k.endswith(".weight") or w.ndim != 2 or w.shape[1] % 64 != 0:
+                    continue
+                raw = tmp[k]
+                sdt = "f16" if raw.dtype in (torch.uint32, torch.int32) else names[raw.dtype]  # offline-dequantised leaves are fp16
+                bits = mlx_quant.runtime_bits(k)
+                out_dt = sdt if "embed" in k.lower() else "f32"  # QuantizedEmbedding hands out rows in the storage dtype
+                self.w[k] = torch.from_numpy(mlx_quant.fake_quantize(w.numpy(), bits, sdt, out_dt))
         c = self.cfg
         self.inv_freq = self._inv_freq(c.rope_theta, c.head_dim)
         self.cp_inv_freq = self._inv_freq(c.code_predictor.rope_theta, c.code_predictor.head_dim)

@@ -471,6 +471,53 @@ def test_packed_weight_gemm_mode_equals_fp16_copy_mode(ck, request, engines):
     assert out[1][2] == out[2][2]
 
 
+# ------------------------------------------------------------------------------------------------ runtime mixed 4/6-bit quantisation (f4)
+@pytest.mark.parametrize("bits", [4, 6, 8])
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_device_mlx_quantizer_bit_exact(bits, dtype):
+    """q3tts_mlx_quantize == oracle/mlx_quant.quantize_codes: codes, scales and biases bit for bit (incl. an all-zero and a constant group)."""
+    import qwen3tts_b200 as q
+    from oracle import mlx_quant
+
+    rng = np.random.default_rng(bits * 11 + len(dtype))
+    w = (rng.standard_normal((40, 320)) * rng.uniform(0.001, 0.3, size=(40, 1))).astype(np.float32)
+    w[3, :64] = 0.0
+    w[4, 64:128] = 0.0371
+    w[5, :64] = -np.abs(w[5, :64])
+    w = mlx_quant.round_to_dtype(w, dtype)
+    want_q, want_s, want_b = mlx_quant.quantize_codes(w, 64, bits, dtype)
+    got_q, got_s, got_b = q.mlx_quantize(w, bits, dtype)
+    assert np.array_equal(got_s, want_s) and np.array_equal(got_b, want_b)
+    assert np.array_equal(got_q.astype(np.uint32), want_q)
+
+
+@pytest.mark.parametrize("slots", [1, 8])
+def test_runtime_quantization_matches_oracle(slots, tiny_bf16, oracles):
+    """q3tts_options.runtime_quantization = Qwen3TTSPipelineConfiguration.applyRuntimeQuantization (Qwen3TTSPipeline.swift:961-980): a bf16
+    checkpoint quantised 4/6-bit at load gives the oracle's logits (same quantiser, same dequantised values) within the 1e-2 bar, on the
+    persistent-kernel handle (1 slot) and on the tensor-core handle (8 slots); and it is NOT the unquantised model."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    F = 10
+    forced = np.random.default_rng(21).integers(0, 2048, size=(F, 16)).astype(np.int32)
+    rec, rec_plain = {}, {}
+    otalker.TalkerOracle(tiny_bf16, runtime_quantization=True).generate_codes(
+        _oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec, filter_invalid=False)
+    oracles(tiny_bf16).generate_codes(_oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=F), forced=forced, record=rec_plain, filter_invalid=False)
+    eng = q.Engine(tiny_bf16, max_batch=slots, max_frames=64, load_codec=False, runtime_quantization=True)
+    _, lg = eng.generate_codes(q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=F, forced_codes=forced,
+                                            keep_invalid_frames=True, want_logits=F))
+    assert eng.info.quant_bits == 8  # 4/6-bit codes in the 8-bit container
+    eng.close()
+    e0 = np.abs(lg["code0_logits"] - rec["code0_logits"]).max()
+    ec = np.abs(lg["cp_logits"] - rec["cp_logits"]).max()
+    d0 = np.abs(rec_plain["code0_logits"] - rec["code0_logits"]).max()
+    print(f"[runtime 4/6-bit, {slots} slot(s)] max-abs logit error code0 {e0:.3e}, code predictor {ec:.3e}; quantised vs plain oracle {d0:.3e}")
+    assert e0 <= LOGIT_TOL and ec <= LOGIT_TOL
+    assert d0 > 10 * max(e0, 1e-5)  # the quantisation is really applied
+
+
 # ------------------------------------------------------------------------------------------------ path pinning / hand-offs
 def test_batch_draining_to_one_slot_equals_singles_on_the_same_handle(tiny8, engines):
     """Default thresholds, a 4-slot handle: 7 requests of very different lengths, so the batch drains from 4 live slots to 1 while

@@ -91,3 +91,39 @@ def test_quantized_matmul_equals_dense():
     y = mlx_quant.quantized_matmul(x, packed, s, b, 64, 8)
     assert np.allclose(y, x @ mlx_quant.dequantize(packed, s, b, 64, 8).T)
     assert np.abs(y - x @ w.T).max() < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------ runtime mixed 4/6-bit quantisation (f4)
+@pytest.mark.parametrize("bits", [4, 6, 8])
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+def test_quantize_codes_any_width_is_self_consistent(bits, dtype):
+    """`quantize_codes` (the quantiser behind applyMixedQuantization, Qwen3TTSPipeline.swift:961-980): codes stay inside [0, 2^bits), the
+    error is at most one step (+ the rounding of scale / bias to the weight dtype), and
+    for 4 / 8 bits it is the packed quantiser the golden vectors pin."""
+    from oracle import mlx_quant as m
+
+    rng = np.random.default_rng(bits * 7 + len(dtype))
+    w = m.round_to_dtype((rng.standard_normal((24, 256)) * 0.05).astype(np.float32), dtype)
+    q, s, b = m.quantize_codes(w, 64, bits, dtype)
+    assert q.min() >= 0 and q.max() <= (1 << bits) - 1 and q.shape == w.shape
+    deq = m.dequantize(m.pack(q, 8), s, b, 64, 8, "f32")
+    step = np.abs(s)[..., None].repeat(64, -1).reshape(w.shape)
+    ulp = {"bf16": 2.0 ** -8, "f16": 2.0 ** -11, "f32": 2.0 ** -23}[dtype]  # relative rounding of scale and bias to the weight dtype
+    bias = np.abs(b)[..., None].repeat(64, -1).reshape(w.shape)
+    # half a step inside the grid; up to one step at the far edge (re-deriving the scale from the kept edge can shorten the grid)
+    tol = 1.0 * step + ((1 << bits) - 1) * step * ulp + bias * ulp
+    assert np.all(np.abs(deq - w) <= tol * 1.001 + 1e-7)
+    assert np.array_equal(deq, m.fake_quantize(w, bits, dtype))
+    if bits in (4, 8):
+        p2, s2, b2 = m.quantize(w, 64, bits, dtype)
+        assert np.array_equal(m.unpack(p2, bits), q) and np.array_equal(s2, s) and np.array_equal(b2, b)
+
+
+def test_runtime_bits_rule():
+    from oracle import mlx_quant as m
+
+    six = ["text_embedding", "codec_embedding", "code_predictor.codec_embedding.3", "layers.0.self_attn.q_proj", "layers.5.self_attn.k_proj",
+           "code_predictor.layers.1.self_attn.v_proj", "code_predictor.lm_head.7", "codec_head"]
+    four = ["layers.0.self_attn.o_proj", "layers.0.mlp.gate_proj", "layers.0.mlp.up_proj", "layers.0.mlp.down_proj", "text_projection.linear_fc1",
+            "code_predictor.small_to_mtp_projection"]
+    assert all(m.runtime_bits(p) == 6 for p in six) and all(m.runtime_bits(p) == 4 for p in four)
