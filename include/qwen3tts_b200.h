@@ -89,7 +89,9 @@ typedef struct q3tts_info {
   int64_t device_bytes; /* HBM held by the handle */
   int32_t has_audio_encoder;    /* supportsICL (Qwen3TTSPipeline.swift:87-89): speech_tokenizer/model.safetensors carries `encoder.*` */
   int32_t audio_encoder_hidden; /* width of the quantiser input (q3tts_encode_reference_audio latent_out) */
-  int32_t reserved[6];
+  int32_t has_speaker_encoder;   /* model.safetensors carries `speaker_encoder.*` (Qwen3TTSPipeline.swift:82-84, 155-169) */
+  int32_t speaker_embedding_dim; /* enc_dim of the ECAPA-TDNN (1024 in the reference) */
+  int32_t reserved[4];
 } q3tts_info;
 
 /* ---- one utterance; replaces the argument list of Qwen3Talker.generateCodes / generateStream
@@ -217,6 +219,15 @@ q3tts_status q3tts_decode_chunked(q3tts_handle* h, const int32_t* codes, int32_t
  * ---------------------------------------------------------------------------------------------------- */
 q3tts_status q3tts_encode_reference_audio(q3tts_handle* h, const float* samples, int64_t n_samples, int32_t* codes_out,
                                           int32_t capacity_frames, int32_t* frames_out, int32_t* quantizers_out, float* latent_out);
+
+/* ECAPA-TDNN speaker encoder -- replaces Qwen3TTSPipeline.extractSpeakerEmbedding (Qwen3TTSPipeline.swift:906-919), i.e.
+ * SpeakerEncoder.extractEmbedding (SpeakerEncoder/SpeakerEncoder.swift:526-542): 24 kHz mono PCM -> log-mel (reflect-padded STFT 1024 / hop
+ * 256, symmetric Hann, 128 Slaney mel bins, log(clip(., 1e-5))) -> TimeDelayNet / SE-Res2Net blocks -> attentive statistics pooling -> 1x1
+ * conv.  embedding_out: [speaker_embedding_dim] fp32 -- exactly what q3tts_request.speaker_embedding takes.  Without the weights the call
+ * returns Q3TTS_OK with *dim_out = 0 (the reference returns nil).  mels_out (optional, [n_samples / 256 + 1][128] fp32) receives the
+ * log-mel input, for parity probes.  Needs at least 1024 samples (5 frames: the reflect padding of the dilation-4 block indexes frame 4). */
+q3tts_status q3tts_extract_speaker_embedding(q3tts_handle* h, const float* samples, int64_t n_samples, float* embedding_out, int32_t capacity,
+                                             int32_t* dim_out, float* mels_out);
 
 /* ------------------------------------------------------------------------------------------------------
  * fused text -> PCM — the bodies of Qwen3TTSPipeline.generate (:244-306), generateToFile's per-text-chunk work

@@ -6,6 +6,7 @@
 #include <map>
 
 #include "audio_encoder.h"
+#include "speaker_encoder.h"
 #include "codec.h"
 #include "codec_kernels.h"
 #include "engine.h"
@@ -19,6 +20,7 @@ Handle::~Handle() {
   talker.reset();
   codec.reset();
   audio_encoder.reset();
+  speaker_encoder.reset();
   if (ev_start) cudaEventDestroy(ev_start);
   if (ev_stop) cudaEventDestroy(ev_stop);
   if (h_pcm) cudaFreeHost(h_pcm);
@@ -445,6 +447,15 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
       h->cfg = parse_talker_config(root);
       h->talker.reset(new TalkerEngine(dir, h->cfg, h->opt, h->stream, &h->counter));
       h->has_talker = true;
+      // speaker encoder, optional (Qwen3TTSPipeline.swift:155-169): present only in checkpoints that carry `speaker_encoder.*`
+      if (SpeakerEncoderDev::present(dir)) {
+        try {
+          h->speaker_encoder.reset(new SpeakerEncoderDev(dir, h->stream, &h->counter));
+        } catch (const Error& e) {
+          g_create_error = std::string("speaker encoder not loaded: ") + e.what();
+          cudaGetLastError();
+        }
+      }
     }
     if (h->opt.load_codec) {
       // speech_tokenizer/{config...} + model.safetensors (Qwen3TTSPipeline.swift:191-208)
@@ -508,6 +519,11 @@ q3tts_status q3tts_get_info(const q3tts_handle* hc, q3tts_info* out) {
     out->codec_num_quantizers = hc->codec->config().num_quantizers;
     out->codec_total_upsample = hc->codec->total_upsample();
     out->device_bytes += (int64_t)hc->codec->device_bytes();
+  }
+  if (hc->speaker_encoder) {
+    out->has_speaker_encoder = 1;
+    out->speaker_embedding_dim = hc->speaker_encoder->embedding_dim();
+    out->device_bytes += (int64_t)hc->speaker_encoder->device_bytes();
   }
   if (hc->audio_encoder) {
     out->has_audio_encoder = 1;
@@ -793,6 +809,24 @@ q3tts_status q3tts_encode_reference_audio(q3tts_handle* h, const float* samples,
     if (quantizers_out) *quantizers_out = h->audio_encoder->quantizers_out();
     h->timing.h2d_bytes += n_samples * 4;
     h->timing.d2h_bytes += (int64_t)f * h->audio_encoder->quantizers_out() * 4;
+    tm.finish();
+  });
+}
+
+q3tts_status q3tts_extract_speaker_embedding(q3tts_handle* h, const float* samples, int64_t n_samples, float* embedding_out, int32_t capacity,
+                                             int32_t* dim_out, float* mels_out) {
+  return guarded(h, [&] {
+    Q3_CHECK(dim_out != nullptr, Q3TTS_ERR_INVALID_ARG, "NULL argument");
+    *dim_out = 0;
+    if (!h->speaker_encoder) return;  // extractSpeakerEmbedding returns nil without the weights (Qwen3TTSPipeline.swift:907-909)
+    Q3_CHECK(samples != nullptr && n_samples > 0 && embedding_out != nullptr, Q3TTS_ERR_INVALID_ARG, "bad arguments");
+    Q3_CHECK(capacity >= h->speaker_encoder->embedding_dim(), Q3TTS_ERR_CAPACITY, "embedding buffer holds %d floats, the speaker embedding has %d", capacity,
+             h->speaker_encoder->embedding_dim());
+    CallTimer tm(h);
+    h->speaker_encoder->extract(samples, n_samples, embedding_out, mels_out);
+    *dim_out = h->speaker_encoder->embedding_dim();
+    h->timing.h2d_bytes += n_samples * 4;
+    h->timing.d2h_bytes += (int64_t)*dim_out * 4;
     tm.finish();
   });
 }

@@ -12,7 +12,8 @@
 namespace q3 {
 
 class CodecDecoder;  // codec.h
-class AudioEncoder;  // audio_encoder.h
+class AudioEncoder;       // audio_encoder.h
+class SpeakerEncoderDev;  // speaker_encoder.h
 
 struct EngineOptions {
   int device = 0;
@@ -184,6 +185,7 @@ struct Handle {
   std::unique_ptr<TalkerEngine> talker;
   std::unique_ptr<CodecDecoder> codec;
   std::unique_ptr<AudioEncoder> audio_encoder;  // ICL reference-audio encoder, when the checkpoint carries one
+  std::unique_ptr<SpeakerEncoderDev> speaker_encoder;  // ECAPA-TDNN speaker encoder, when model.safetensors carries `speaker_encoder.*`
   q3tts_timing timing{};
   cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
   float* h_pcm = nullptr;  // pinned staging for PCM read-back

@@ -35,7 +35,8 @@ class Info(C.Structure):
                                    "cp_vocab_size", "num_code_groups", "quant_bits", "quant_group_size", "weight_dtype",
                                    "num_speakers", "has_codec", "codec_num_quantizers", "codec_total_upsample", "model_type",
                                    "codec_eos_id", "codec_pad_id", "max_batch", "kv_capacity", "max_frames")] + \
-               [("device_bytes", i64), ("has_audio_encoder", i32), ("audio_encoder_hidden", i32), ("reserved", i32 * 6)]
+               [("device_bytes", i64), ("has_audio_encoder", i32), ("audio_encoder_hidden", i32), ("has_speaker_encoder", i32), ("speaker_embedding_dim", i32),
+                ("reserved", i32 * 4)]
 
 
 class Request(C.Structure):
@@ -90,6 +91,7 @@ SYMBOLS = {
     "q3tts_sample_token": (i32, [C.c_void_p, p_f32, i32, f32, i32, f32, f32, p_i32, i32, u64, u64, p_i32]),
     "q3tts_rvq_embed": (i32, [C.c_void_p, p_i32, i32, i32, p_f32, p_f32, p_i32]),
     "q3tts_encode_reference_audio": (i32, [C.c_void_p, p_f32, i64, p_i32, i32, p_i32, p_i32, p_f32]),
+    "q3tts_extract_speaker_embedding": (i32, [C.c_void_p, p_f32, i64, p_f32, i32, p_i32, p_f32]),
     "q3tts_safetensors_check": (i32, [C.c_char_p, p_i32, C.POINTER(i64)]),
 }
 

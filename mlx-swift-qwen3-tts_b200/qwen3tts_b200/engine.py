@@ -272,6 +272,23 @@ class Engine:
         out = codes.reshape(-1)[: nq.value * n.value].reshape(nq.value, n.value).copy()
         return (out, lat[: n.value].copy()) if want_latent else out
 
+    # ---- ECAPA-TDNN speaker encoder
+    def extract_speaker_embedding(self, samples, want_mels: bool = False):
+        """24 kHz mono float32 samples -> speaker embedding float32 [speaker_embedding_dim] (the `speaker_embedding` request field), or
+        None without `speaker_encoder.*` weights (`Qwen3TTSPipeline.extractSpeakerEmbedding`).  want_mels: also return the log-mel
+        input [frames, 128]."""
+        if not self.info.has_speaker_encoder:
+            return (None, None) if want_mels else None
+        a = np.ascontiguousarray(np.asarray(samples, dtype=np.float32).reshape(-1))
+        dim = self.info.speaker_embedding_dim
+        emb = np.zeros(dim, dtype=np.float32)
+        mels = np.zeros((a.size // 256 + 1, 128), dtype=np.float32) if want_mels else None
+        n = A.i32(0)
+        A.check(A.lib().q3tts_extract_speaker_embedding(self._h, a.ctypes.data_as(A.p_f32), a.size, emb.ctypes.data_as(A.p_f32), dim, C.byref(n),
+                                                        mels.ctypes.data_as(A.p_f32) if want_mels else None), self._h)
+        emb = emb[: n.value].copy()
+        return (emb, mels) if want_mels else emb
+
     # ---- fused
     def generate_pcm(self, req: GenRequest, mode: int = A.DECODE_WHOLE):
         cap = max(req.max_tokens, 1) * self.info.codec_total_upsample

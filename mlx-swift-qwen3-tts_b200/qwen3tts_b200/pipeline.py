@@ -227,7 +227,7 @@ class Qwen3TTSPipeline:
 
     @property
     def supports_voice_cloning(self):
-        return False  # speaker encoder is a "next" row; embeddings are accepted as input
+        return bool(self.info.has_speaker_encoder)  # speakerEncoder?.isWeightsLoaded (Qwen3TTSPipeline.swift:82-84)
 
     @property
     def supports_icl(self):
@@ -373,10 +373,12 @@ class Qwen3TTSPipeline:
             on_progress(1.0)
         return np.concatenate(all_s) if all_s else np.zeros(0, np.float32)
 
-    # ---- voice cloning inputs (:906-945).  The ICL reference-audio encoder runs on the device when the checkpoint carries it; the
-    # ECAPA speaker encoder is not built: like the reference without `speaker_encoder.*` weights, the call returns nil
+    # ---- voice cloning inputs (:906-945).  Both encoders run on the device when the checkpoint carries their weights; without them the
+    # calls return nil like the reference
     def extract_speaker_embedding(self, audio_samples):
-        return None
+        """[Float] speaker embedding of reference audio, or None without a speaker encoder (Qwen3TTSPipeline.swift:906-919)."""
+        emb = self.engine.extract_speaker_embedding(audio_samples)
+        return None if emb is None or emb.size == 0 else emb
 
     def encode_reference_audio(self, audio_samples):
         """[[Int32]] [num_quantizers][time] of 24 kHz reference audio, or None without an encoder (Qwen3TTSPipeline.swift:924-945)."""

@@ -60,8 +60,8 @@ public final class Qwen3TTSPipeline: @unchecked Sendable {
     private var speakerIds: [String: Int32] = [:]
 
     public var availableSpeakers: [String] { speakerIds.keys.sorted() }
-    public var supportsVoiceCloning: Bool { false }   // speaker encoder: "next" row (SURVEY.md §8f); embeddings are accepted
-    public var supportsICL: Bool { false }            // reference-audio encoder: "next" row; pre-encoded codes are accepted
+    public var supportsVoiceCloning: Bool { info.has_speaker_encoder != 0 }   // speakerEncoder?.isWeightsLoaded (:82-84)
+    public var supportsICL: Bool { info.has_audio_encoder != 0 }              // audioEncoder != nil (:87-89)
     public var modelType: String? { info.model_type == 1 ? "voice_design" : (info.model_type == 2 ? "custom_voice" : nil) }
     public var supportsVoiceDesign: Bool { info.model_type == 1 }
     public var supportsCustomVoice: Bool { info.model_type == 2 }
@@ -264,7 +264,26 @@ public final class Qwen3TTSPipeline: @unchecked Sendable {
         return all
     }
 
-    public func extractSpeakerEmbedding(audioSamples: [Float]) -> [Float]? { nil }   // :906 — speaker encoder not in this engine yet
-    public func encodeReferenceAudio(audioSamples: [Float]) -> [[Int32]]? { nil }    // :924 — audio encoder not in this engine yet
+    /// :906 — ECAPA-TDNN on the device; nil without `speaker_encoder.*` weights
+    public func extractSpeakerEmbedding(audioSamples: [Float]) -> [Float]? {
+        guard let h = handle, info.has_speaker_encoder != 0, audioSamples.count >= 1024 else { return nil }
+        var emb = [Float](repeating: 0, count: Int(info.speaker_embedding_dim))
+        var dim: Int32 = 0
+        let st = q3tts_extract_speaker_embedding(h, audioSamples, Int64(audioSamples.count), &emb, Int32(emb.count), &dim, nil)
+        guard st == Q3TTS_OK, dim > 0 else { return nil }
+        return Array(emb.prefix(Int(dim)))
+    }
+
+    /// :924 — SEANet + transformer + split RVQ on the device; [num_quantizers][time], nil without `encoder.*` weights
+    public func encodeReferenceAudio(audioSamples: [Float]) -> [[Int32]]? {
+        guard let h = handle, info.has_audio_encoder != 0, !audioSamples.isEmpty else { return nil }
+        let cap = (audioSamples.count + 1919) / 1920 + 2
+        var codes = [Int32](repeating: 0, count: 64 * cap)
+        var frames: Int32 = 0, quantizers: Int32 = 0
+        let st = q3tts_encode_reference_audio(h, audioSamples, Int64(audioSamples.count), &codes, Int32(cap), &frames, &quantizers, nil)
+        guard st == Q3TTS_OK, frames > 0 else { return nil }
+        let T = Int(frames)
+        return (0..<Int(quantizers)).map { q in Array(codes[(q * T)..<((q + 1) * T)]) }
+    }
     public func clearCache() { if let h = handle { _ = q3tts_clear_cache(h) } }      // :951
 }

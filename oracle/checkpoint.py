@@ -415,14 +415,15 @@ def codec_config_json(c: CodecDims) -> dict:
 
 def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = "bf16", seed: int = 0,
                      codec_seed: int | None = None, visible: bool = True, with_codec: bool = True,
-                     normalize_codec: bool = True, init: str = "stress", quant_key: str = "quantization", encoder: str | None = None) -> str:
+                     normalize_codec: bool = True, init: str = "stress", quant_key: str = "quantization", encoder: str | None = None,
+                     speaker_encoder: str | None = None) -> str:
     """Write a complete synthetic model directory; returns `path`.  Idempotent via a stamp file.
 
     init: see `talker_tensors`.  quant_key = "quantization_config" writes the packed leaves WITHOUT a top-level
     `quantization` block, i.e. the checkpoint form `Qwen3Talker.load` dequantises offline to fp16 (Qwen3Talker.swift:139-175)."""
     t, c = preset(name)
     stamp = {"name": name, "bits": bits, "dtype": dtype, "seed": seed, "codec_seed": codec_seed, "visible": visible,
-             "with_codec": with_codec, "normalize_codec": normalize_codec, "init": init, "quant_key": quant_key, "encoder": encoder, "v": 5}
+             "with_codec": with_codec, "normalize_codec": normalize_codec, "init": init, "quant_key": quant_key, "encoder": encoder, "speaker_encoder": speaker_encoder, "v": 7}
     stamp_path = os.path.join(path, "synthetic_stamp.json")
     if os.path.exists(stamp_path):
         try:
@@ -435,7 +436,10 @@ def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = 
     if bits and quant_key != "quantization":
         cfg[quant_key] = cfg.pop("quantization")
     json.dump(cfg, open(os.path.join(path, "config.json"), "w"), indent=1)
-    save_file(talker_tensors(t, bits, dtype, seed, init=init), os.path.join(path, "model.safetensors"))
+    tt = talker_tensors(t, bits, dtype, seed, init=init)
+    if speaker_encoder:  # ECAPA-TDNN weights live in the talker file under `speaker_encoder.*` (SpeakerEncoder.swift:550-555)
+        tt.update(speaker_encoder_tensors(speaker_encoder, seed + 3000))
+    save_file(tt, os.path.join(path, "model.safetensors"))
     if with_codec:
         cj = codec_config_json(c)
         ct = codec_tensors(c, seed + 1000 if codec_seed is None else codec_seed, visible=visible)
@@ -451,6 +455,35 @@ def write_checkpoint(path: str, name: str = "tiny", bits: int = 8, dtype: str = 
         save_file({k: v.contiguous() for k, v in ct.items()}, os.path.join(path, "speech_tokenizer", "model.safetensors"))
     json.dump(stamp, open(stamp_path, "w"))
     return path
+
+
+def speaker_encoder_tensors(preset_name: str, seed: int) -> dict:
+    """Seeded ECAPA-TDNN weights under the `speaker_encoder.*` keys `SpeakerEncoder.load` reads (SpeakerEncoder.swift:550-603), PyTorch conv
+    layout [out, in, k], fp32.  "full" = the reference's only configuration (:399-418); "tiny" = the same graph at small widths."""
+    ch, se, att, enc, mel = {"full": (512, 128, 128, 1024, 128), "tiny": (64, 16, 16, 256, 128)}[preset_name]
+    mfa_ch = 3 * ch
+    r = _Rng(seed)
+    o: dict = {}
+
+    def conv(key, cout, cin, k, g=1.0):
+        o[f"speaker_encoder.{key}.weight"] = r.normal((cout, cin, k), g / np.sqrt(cin * k))
+        o[f"speaker_encoder.{key}.bias"] = r.normal((cout,), 0.05)
+
+    kernels = (5, 3, 3, 3, 1)
+    conv("blocks.0.conv", ch, mel, kernels[0], g=0.3)  # log-mel inputs are O(5): keep the first activations O(1)
+    for i in (1, 2, 3):
+        p = f"blocks.{i}"
+        conv(p + ".tdnn1.conv", ch, ch, 1, g=1.4)
+        for j in range(7):
+            conv(f"{p}.res2net_block.blocks.{j}.conv", ch // 8, ch // 8, kernels[i], g=1.4)
+        conv(p + ".tdnn2.conv", ch, ch, 1, g=1.4)
+        conv(p + ".se_block.conv1", se, ch, 1)
+        conv(p + ".se_block.conv2", ch, se, 1)
+    conv("mfa.conv", mfa_ch, mfa_ch, kernels[4], g=1.4)
+    conv("asp.tdnn.conv", att, 3 * mfa_ch, 1)
+    conv("asp.conv", mfa_ch, att, 1, g=2.0)
+    conv("fc", enc, 2 * mfa_ch, 1)
+    return o
 
 
 def _normalize_encoder_latent(e, et: dict, seconds: float = 1.0):

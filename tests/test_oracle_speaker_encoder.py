@@ -1,0 +1,105 @@
+"""CPU self-checks of the ECAPA-TDNN speaker-encoder restatement (oracle/speaker_encoder.py) against independent formulations:
+reflect padding vs torch's, the STFT front end vs torch.stft, the Slaney filterbank's published properties, attentive statistics
+pooling vs explicit loops, the Res2Net chunk recurrence, and the checkpoint keys `SpeakerEncoder.load` reads."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import ckpt
+from oracle import speaker_encoder as se
+
+
+@pytest.mark.parametrize("n,pad", [(10, 3), (600, 512), (5, 4), (7, 0), (1025, 512)])
+def test_reflect_indices_equal_torch_reflect_pad(n, pad):
+    """reflectPadSignal / reflectPad1d (SpeakerEncoder.swift:148-167, 213-232) are torch's `reflect` mode for pad < n."""
+    x = torch.arange(n, dtype=torch.float32)
+    want = F.pad(x[None, None], (pad, pad), mode="reflect")[0, 0] if pad else x
+    assert torch.equal(x[torch.from_numpy(se.reflect_indices(n, pad))], want)
+
+
+def test_mel_front_end_matches_torch_stft():
+    """speakerEncoderSTFT (:169-209) = centred, reflect-padded STFT with a symmetric (periodic=False) Hann window."""
+    a = (np.random.default_rng(0).standard_normal(24000 + 77) * 0.1).astype(np.float32)
+    got = se.mel_spectrogram(a)
+    assert got.shape == (a.size // 256 + 1, 128) and got.dtype == np.float32
+    spec = torch.stft(torch.from_numpy(a), 1024, 256, 1024, torch.hann_window(1024, periodic=False), center=True, pad_mode="reflect", return_complex=True)
+    want = torch.log(torch.clamp(spec.abs().T @ torch.from_numpy(se.mel_filterbank()), min=1e-5)).numpy()
+    assert np.abs(got - want).max() < 2e-4
+
+
+def test_slaney_filterbank_properties():
+    """createMelFilterbankImpl (:75-146): triangles on the Slaney scale (linear below 1 kHz, log above), area-normalised."""
+    fb = se.mel_filterbank()
+    assert fb.shape == (513, 128) and fb.dtype == np.float32 and (fb >= 0).all()
+    peaks = fb.argmax(0)
+    assert (np.diff(peaks) >= 0).all() and peaks[0] >= 1 and peaks[-1] <= 512
+    freqs = np.arange(513) * 12000.0 / 512
+    centre = freqs[peaks]
+    low = centre < 900
+    assert np.allclose(np.diff(centre[low]), np.diff(centre[low])[0], atol=24.0)   # linear spacing (one bin = 23.4 Hz)
+    hi = centre > 1500
+    ratio = centre[hi][1:] / centre[hi][:-1]
+    assert ratio.std() < 0.01                                                      # geometric spacing
+    # Slaney normalisation: every triangle integrates to ~1 over frequency
+    area = fb.sum(0) * (12000.0 / 512)
+    assert np.allclose(area[8:], 1.0, atol=0.12)
+    if True:  # librosa's published corner case: hz_to_mel(1000) = 15, the filterbank spans 0 .. fmax
+        assert fb[0].sum() == 0.0 and fb[-1].sum() == 0.0
+
+
+def test_forward_against_explicit_loops():
+    d = ckpt("tiny", 8, speaker_encoder="tiny")
+    orc = se.SpeakerEncoderOracle(d)
+    assert orc.present
+    a = (np.random.default_rng(1).standard_normal(24000) * 0.1).astype(np.float32)
+    rec = {}
+    emb = orc.extract_embedding(a, rec)
+    assert emb.shape == (256,) and np.isfinite(emb).all() and np.abs(emb).max() > 1e-3
+    # attentive statistics pooling (:366-396) by explicit loops over channels, in float64
+    h = torch.from_numpy(rec["mfa"]).double().T  # [C, T]
+    C, T = h.shape
+    w = {k: v.double() for k, v in orc.w.items()}
+    mean, std = h.mean(1), torch.sqrt(((h - h.mean(1, keepdim=True)) ** 2).mean(1) + 1e-12)
+    att_in = torch.cat([h, mean[:, None].expand(C, T), std[:, None].expand(C, T)], 0)
+    a1 = torch.tanh(torch.relu(w["asp.tdnn.conv.weight"][:, :, 0] @ att_in + w["asp.tdnn.conv.bias"][:, None]))
+    a2 = w["asp.conv.weight"][:, :, 0] @ a1 + w["asp.conv.bias"][:, None]
+    pooled = torch.zeros(2 * C, dtype=torch.float64)
+    for c in range(C):
+        p = torch.softmax(a2[c], 0)
+        m = (p * h[c]).sum()
+        pooled[c] = m
+        pooled[C + c] = torch.sqrt(torch.clamp((p * (h[c] - m) ** 2).sum(), min=1e-12))
+    want = (w["fc.weight"][:, :, 0] @ pooled + w["fc.bias"]).numpy()
+    assert np.abs(want - emb).max() < 1e-4
+
+
+def test_res2net_recurrence_and_tdnn_padding():
+    """TimeDelayNetBlock keeps the length for odd kernels at any dilation; chunk 0 of Res2Net passes through untouched."""
+    d = ckpt("tiny", 8, speaker_encoder="tiny")
+    orc = se.SpeakerEncoderOracle(d)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(64, 37, generator=g)
+    for i, (k, dil) in enumerate(zip(se.KERNELS[1:4], se.DILATIONS[1:4]), start=1):
+        y = orc._se_res2net(f"blocks.{i}", x, k, dil)
+        assert y.shape == x.shape
+    c = torch.randn(8, 37, generator=g)
+    y = orc._tdnn("blocks.1.res2net_block.blocks.0", c, 3, 2)
+    pad = F.pad(c[None], (2, 2), mode="reflect")
+    want = torch.relu(F.conv1d(pad, orc.w["blocks.1.res2net_block.blocks.0.conv.weight"], orc.w["blocks.1.res2net_block.blocks.0.conv.bias"], dilation=2))[0]
+    assert torch.allclose(y, want, atol=1e-6)
+
+
+def test_checkpoint_keys_are_the_ones_the_reference_loader_reads():
+    """SpeakerEncoder.load (:550-603) strips `speaker_encoder.` and applies `blocks.N.…`, `mfa.conv`, `asp.tdnn.conv`, `asp.conv`, `fc`."""
+    from oracle import checkpoint
+
+    t = checkpoint.speaker_encoder_tensors("full", 0)
+    keys = {k[len("speaker_encoder."):] for k in t}
+    need = {"blocks.0.conv.weight", "blocks.1.tdnn1.conv.weight", "blocks.3.res2net_block.blocks.6.conv.bias", "blocks.2.se_block.conv2.weight", "mfa.conv.weight",
+            "asp.tdnn.conv.weight", "asp.conv.bias", "fc.weight", "fc.bias"}
+    assert need <= keys
+    assert tuple(t["speaker_encoder.blocks.0.conv.weight"].shape) == (512, 128, 5)
+    assert tuple(t["speaker_encoder.mfa.conv.weight"].shape) == (1536, 1536, 1)
+    assert tuple(t["speaker_encoder.asp.tdnn.conv.weight"].shape) == (128, 4608, 1)
+    assert tuple(t["speaker_encoder.fc.weight"].shape) == (1024, 3072, 1)
