@@ -307,6 +307,12 @@ q3tts_status q3tts_conv_probe(int32_t device, const float* x, int32_t B, int32_t
 q3tts_status q3tts_profile_linear(q3tts_handle* h, int32_t which, int32_t m, int32_t iters, double* ms_out,
                                   int64_t* launches_out, int64_t* bytes_per_iter_out);
 
+/* test hook: launches a kernel that waits on an mbarrier nobody arrives at -- the failure mode of a broken TMA / tcgen05 protocol.  The
+ * bounded wait (csrc/tc_ptx.cuh mbar_wait) traps instead of hanging the GPU; the call returns Q3TTS_ERR_CUDA, the handle is POISONED (a
+ * kernel fault is sticky for the process's CUDA context): every later call on it returns Q3TTS_ERR_CUDA with the same q3tts_last_error
+ * text, q3tts_destroy still works.  No reference counterpart. */
+q3tts_status q3tts_debug_trap(q3tts_handle* h);
+
 /* measurement hook (scripts/skinny_trace.py): `iters` back-to-back launches (one CUDA graph, programmatic dependent launch,
  * a different weight matrix each) of the <= 128-row split-K cluster GEMM (csrc/gemm_skinny.cu) for an [M x K] . [N x K]^T
  * linear; returns the average time per launch and, for the LAST launch, 16 stamps per CTA: [0]/[9] %globaltimer at entry /

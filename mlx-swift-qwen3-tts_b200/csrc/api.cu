@@ -11,6 +11,7 @@
 #include "codec_kernels.h"
 #include "engine.h"
 #include "gemm_tc.h"
+#include "tc_ptx.cuh"
 
 using namespace q3;
 
@@ -41,12 +42,20 @@ template <typename F>
 q3tts_status guarded(q3tts_handle* h, F&& f) {
   if (!h) return Q3TTS_ERR_INVALID_ARG;
   std::lock_guard<std::mutex> lk(h->mu);
+  if (h->poisoned) return Q3TTS_ERR_CUDA;  // last_error keeps the fault that poisoned the handle
   try {
     Q3_CUDA(cudaSetDevice(h->opt.device));
     f();
     return Q3TTS_OK;
   } catch (const Error& e) {
     h->last_error = e.what();
+    cudaGetLastError();
+    // A fault inside a kernel (the bounded mbarrier wait of tc_ptx.cuh trapping, an illegal address) is STICKY: the context is gone for the
+    // whole process.  Say so once, deterministically, instead of letting every later call fail with whatever the runtime reports first.
+    if (e.status == Q3TTS_ERR_CUDA && cudaDeviceSynchronize() != cudaSuccess) {
+      h->poisoned = true;
+      h->last_error += " -- the CUDA context is unusable after this fault: the handle is poisoned, destroy it and restart the process";
+    }
     cudaGetLastError();
     return e.status;
   } catch (const std::exception& e) {
@@ -556,6 +565,27 @@ q3tts_status q3tts_clear_cache(q3tts_handle* h) {
   return guarded(h, [&] {
     Q3_CUDA(cudaStreamSynchronize(h->stream));
     if (h->talker) h->talker->drop_graphs();
+  });
+}
+
+namespace {
+// test hook: the failure mode of a broken TMA / mbarrier protocol -- a wait on a barrier nobody arrives at
+__global__ void debug_mbar_trap_kernel() {
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    q3::tcptx::mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) q3::tcptx::mbar_wait(&bar, 0);
+}
+}  // namespace
+
+q3tts_status q3tts_debug_trap(q3tts_handle* h) {
+  return guarded(h, [&] {
+    debug_mbar_trap_kernel<<<1, 32, 0, h->stream>>>();
+    Q3_CUDA(cudaGetLastError());
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
   });
 }
 

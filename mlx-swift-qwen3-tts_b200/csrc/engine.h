@@ -176,6 +176,7 @@ class TalkerEngine {
 struct Handle {
   std::mutex mu;
   std::string last_error;
+  bool poisoned = false;  // a kernel fault (trap, illegal address) left the CUDA context unusable: every later call fails the same way
   EngineOptions opt;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
