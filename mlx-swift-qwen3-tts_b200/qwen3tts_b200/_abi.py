@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqwen3tts_b200.so")
+LIB_PATH = os.environ.get("Q3TTS_LIB") or os.path.join(_HERE, "libqwen3tts_b200.so")  # Q3TTS_LIB: A/B measurements of two builds on one box
 
 OK = 0
 ERR_FILE_NOT_FOUND, ERR_DECODER_LOAD_FAILED, ERR_MODEL_NOT_LOADED, ERR_BAD_CONFIG, ERR_BAD_WEIGHTS = -1, -2, -3, -4, -5

@@ -348,12 +348,24 @@ class Qwen3TTSPipeline:
             return out
         cf = self.config.crossfade_samples
         all_s, tail = [], np.zeros(0, np.float32)
+        # chunks are independent generations (:813-864): a handle with several slots runs `max_batch` of them per batched call, the
+        # crossfade below consumes them in chunk order
+        group = max(1, int(self.info.max_batch))
+        done: dict = {}
         for i, tc in enumerate(chunks):
             if on_progress:
                 on_progress(i / len(chunks))
-            # generateBatch forwards the transcript but not the codes, so ICL stays off (:813-822)
-            req = self._request(tc, speaker=speaker, instruct=instruct, speaker_embedding=speaker_embedding, temperature=temperature, max_tokens=600)
-            ch, frames = self.engine.generate_pcm(req, A.DECODE_BATCHAPI)
+            if i not in done:
+                # generateBatch forwards the transcript but not the codes, so ICL stays off (:813-822)
+                reqs = [self._request(c, speaker=speaker, instruct=instruct, speaker_embedding=speaker_embedding, temperature=temperature, max_tokens=600)
+                        for c in chunks[i: i + group]]
+                if len(reqs) == 1:
+                    done[i] = self.engine.generate_pcm(reqs[0], A.DECODE_BATCHAPI)
+                else:
+                    pcms, fr = self.engine.generate_pcm_batch(reqs, A.DECODE_BATCHAPI)
+                    for j in range(len(reqs)):
+                        done[i + j] = (pcms[j], fr[j])
+            ch, frames = done.pop(i)
             if frames == 0 or ch.size == 0:
                 continue
             last = i == len(chunks) - 1

@@ -309,3 +309,23 @@ def test_generate_batch_crossfade_vs_oracle(tiny8, oracles):
         assert got.shape == ref.shape and snr_db(got, ref) >= SNR_DB
     finally:
         p.close()
+
+
+def test_generate_batch_chunk_parallel_equals_one_chunk_at_a_time(tiny8):
+    """generateBatch's chunks are independent generations (Qwen3TTSPipeline.swift:813-864): a handle with several slots runs them through one
+    batched call; the samples must be those of the same handle run chunk by chunk."""
+    import qwen3tts_b200 as q
+    from oracle import pipeline as opipe
+
+    steps = 24
+    p = q.Qwen3TTSPipeline(tiny8, q.Qwen3TTSPipelineConfiguration(max_batch=4))
+    try:
+        orig = p._request
+        p._request = lambda *a, **kw: orig(*a, **{**kw, "max_tokens": steps, "temperature": 0.0})
+        got = p.generate_batch(LONG_TEXT, speaker="aiden", temperature=0.0)
+        chunks = q.TextChunker.chunk(LONG_TEXT, q.TextChunker.default_max_words)
+        singles = [p.engine.generate_pcm(p._request(tc, speaker="aiden"), q.DECODE_BATCHAPI)[0] for tc in chunks]
+        ref = opipe.crossfade_concat([s for s in singles if s.size], p.config.crossfade_samples)
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+    finally:
+        p.close()

@@ -674,3 +674,36 @@ def test_trapped_kernel_surfaces_as_cuda_error_and_poisons_the_handle(tiny8):
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "TRAP-OK" in r.stdout, r.stdout + r.stderr
     print(r.stdout.strip())
+
+
+def test_two_handles_served_from_two_threads_equal_one_handle(tiny8):
+    """Throughput mode of bench config3 / INTEGRATION.md: two handles on one GPU, each fed by its own host thread (a batched frame step is a
+    latency-bound chain of launches, two chains overlap).  Handles share no mutable state: every request gets the bits it gets from one
+    handle run alone."""
+    import threading
+
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(5)
+    reqs = [q.GenRequest(text_ids=rng.integers(0, 600, size=int(rng.integers(12, 30))).tolist(), speaker_id=-1, temperature=0.7, seed=100 + i,
+                         max_tokens=20, keep_invalid_frames=True) for i in range(16)]
+    one = q.Engine(tiny8, max_batch=4, max_frames=64)
+    want = []
+    for b0 in range(0, 16, 4):
+        want += one.generate_codes_batch(reqs[b0:b0 + 4])
+    one.close()
+    engs = [q.Engine(tiny8, max_batch=4, max_frames=64) for _ in range(2)]
+    got = [None] * 16
+
+    def serve(h):
+        for b0 in range(4 * h, 16, 8):
+            for j, fr in enumerate(engs[h].generate_codes_batch(reqs[b0:b0 + 4])):
+                got[b0 + j] = fr
+
+    th = [threading.Thread(target=serve, args=(h,)) for h in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for e in engs:
+        e.close()
+    for i in range(16):
+        assert got[i] is not None and np.array_equal(got[i], want[i]), f"request {i} differs between one handle and two concurrent handles"
