@@ -409,7 +409,7 @@ def main():
     audio_s = samples_all / 24000.0
 
     hbm, tf, src = peaks()
-    roof = lat = cpu_base = None
+    roof = lat = cpu_base = inflight = None
     extras = not a.no_extras
     if rank == 0 and extras:
         # ---- roofline of the dominant kernel, live (algorithmic bytes = the weights as stored)
@@ -466,6 +466,38 @@ def main():
                "time_to_first_chunk_how": "measured wall clock, q3tts_stream_begin -> first q3tts_stream_next_audio (18-frame window), median of 3",
                "like_for_like_single_stream_rtfx": 80.0 / msf}
         e1.close()
+        # ---- the same step with several batches IN FLIGHT (not the headline: BASELINE.json configs[1] is one batch of 64): H handles on H host
+        # threads, each generating `steps` of the headline's batches through the same public call with its own host buffers
+        H = 4
+        more = [q.Engine(ckpt_dir, device=local_rank, max_batch=a.batch, max_frames=max(64, a.frames), kv_capacity=512, packed_gemm=a.packed_gemm) for _ in range(H - 1)]
+        handles = [eng] + more
+        bufs = [out_bufs] + [[np.zeros(a.frames * up, dtype=np.float32) for _ in range(a.batch)] for _ in more]
+        got = [0] * H
+
+        def serve(h, n_steps, seed0):
+            for i in range(n_steps):
+                pcm, _ = handles[h].generate_pcm_batch(make_requests(q, a.batch, a.frames, seed0 + 10 * h + i, rank), q.DECODE_STREAM, out_buffers=bufs[h])
+                got[h] += int(sum(p.size for p in pcm))
+
+        def run_all(n_steps, seed0):
+            th = [threading.Thread(target=serve, args=(h, n_steps, seed0)) for h in range(H)]
+            t0 = time.perf_counter()
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            return time.perf_counter() - t0
+
+        run_all(1, 2000)
+        got = [0] * H
+        torch.cuda.synchronize()
+        w_inflight = run_all(a.steps, 3000)
+        inflight = {"what": f"{H} handles on {H} host threads, {a.steps} batches of the headline workload each ({a.batch} utterances x {a.frames} frames, stream windows), "
+                            "q3tts_generate_pcm_batch with host buffers, wall clock; NOT the headline configuration (one batch of 64 at a time) -- it shows what the "
+                            "latency-bound launch chain leaves on the table when more than one batch is pending (DESIGN.md §7)",
+                    "handles": H, "e2e_value": sum(got) / 24000.0 / w_inflight, "unit": UNIT, "wall_s": w_inflight, "utterances_in_flight": H * a.batch}
+        for e in more:
+            e.close()
         if world == 1 and not a.no_cpu_baseline:
             v, sec = cpu_sample(ckpt_dir, a.frames, 2, 1)
             cpu_base = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
@@ -511,7 +543,7 @@ def main():
                 "talker": {"ms_per_frame_step_batch": talker_ms_frame, "prefill_ms_per_step": sum(r["prefill"] for r in res) / a.steps * 1e3,
                            "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev), "algorithmic_weight_bytes_per_frame_step": eng_bytes,
                            "frame_step_hbm_frac": (eng_bytes / max(1e-9, talker_ms_frame * 1e-3) / 1e9) / hbm},
-                "other_weight_operand_mode": ab, "config3": cfg3, "config4": cfg4,
+                "other_weight_operand_mode": ab, "batches_in_flight": inflight, "config3": cfg3, "config4": cfg4,
                 "wall_s_timed_region": total_max}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

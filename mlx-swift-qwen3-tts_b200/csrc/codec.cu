@@ -575,7 +575,12 @@ void CodecDecoder::decode_pass_tc(const int32_t* d_codes, int B, int T, float* d
       launch_tc_gemm(lc, g);
     }
   }
-  { TcGemm g = gemm(out_tc_, cur, B, Tc); g.pcm = d_pcm; launch_tc_gemm(lc, g); }
+  static const bool out_stream = !(getenv("Q3TTS_CODEC_OUT_STREAM") && atoi(getenv("Q3TTS_CODEC_OUT_STREAM")) == 0);
+  if (out_stream && out_conv_stream_supported(out_ch_)) {
+    launch_out_conv_stream_f16(lc, cur, out_w_, out_b_, out_ch_, B, Tc, d_pcm);  // HBM-bound: streamed once, fp32 weights in registers
+  } else {
+    TcGemm g = gemm(out_tc_, cur, B, Tc); g.pcm = d_pcm; launch_tc_gemm(lc, g);
+  }
 }
 
 void CodecDecoder::decode_pass_simt(const int32_t* d_codes, int B, int T, float* d_pcm) {

@@ -385,6 +385,77 @@ void launch_out_conv_f16(const LaunchCtx& c, const __half* x, const float* w, co
   c.tick();
 }
 
+// DecoderOutputConv as a STREAMING kernel (Vocoder/SpeechTokenizer.swift:823-840: causal 7-tap conv, C -> 1 channel, then the clip of
+// decodeImpl :927).  HBM-bound: every activation byte is needed once (B*T*C fp16 in, B*T fp32 out; 672 MACs per output are nothing).
+// A warp walks a strip of consecutive time steps; lane l holds the 7 x CPL weights of channels l, l + 32, ... in registers and a
+// sliding window of 7 partial sums: input row r adds x[r] . w[6 - j] to output r + j, so each row is read exactly once -- straight
+// from global memory, 64 contiguous bytes per load instruction, no shared memory -- and completes output r, which is reduced across
+// the lanes by shuffles and stored 32 outputs at a time.  Through the tensor-core GEMM (31 of 32 output columns zero padding) the
+// same conv ran at 17 % of the HBM roofline.
+template <int CPL>
+__global__ void __launch_bounds__(128) out_conv_stream_kernel(const __half* __restrict__ x, const float* __restrict__ w /*[7][C]*/,
+                                                              const float* __restrict__ bias, int T, int strip, int strips_per_b, int n_warps,
+                                                              float* __restrict__ y) {
+  constexpr int C = CPL * 32;
+  const int wid = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (wid >= n_warps) return;
+  const int b = wid / strips_per_b, t0 = (wid - b * strips_per_b) * strip;
+  const int t1 = t0 + strip < T ? t0 + strip : T;
+  const __half* xb = x + (size_t)b * T * C;
+  float wr[7][CPL];
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) wr[k][j] = w[k * C + j * 32 + lane];
+  const float b0 = bias[0];
+  float acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  float keep = 0.f;
+  const int r0 = t0 - 6 > 0 ? t0 - 6 : 0;  // rows before 0 are the causal zero padding
+#pragma unroll 7
+  for (int r = r0; r < t1; ++r) {
+    float xv[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) xv[j] = __half2float(xb[(size_t)r * C + j * 32 + lane]);
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) acc[j] = fmaf(xv[c], wr[6 - j][c], acc[j]);
+    float v = acc[0];  // output r is complete: rows r - 6 .. r have been added
+#pragma unroll
+    for (int j = 0; j < 6; ++j) acc[j] = acc[j + 1];
+    acc[6] = 0.f;
+    if (r >= t0) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      v += b0;
+      // clip(-1, 1); a NaN becomes 0 here so the host needs no scrub pass (Qwen3TTSPipeline.swift:565-570: NaN/Inf -> 0 after the clip)
+      v = (v != v) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v));
+      const int i = r - t0;
+      if ((i & 31) == lane) keep = v;
+      if ((i & 31) == 31 || r == t1 - 1) {
+        const int base = t0 + (i & ~31);
+        if (base + lane <= r) y[(size_t)b * T + base + lane] = keep;
+      }
+    }
+  }
+}
+bool out_conv_stream_supported(int C) { return C == 32 || C == 64 || C == 96 || C == 128; }
+void launch_out_conv_stream_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y) {
+  if (B <= 0 || T <= 0) return;
+  const int strip = 512;
+  const int strips = (T + strip - 1) / strip, n_warps = B * strips;
+  const unsigned blocks = (unsigned)((n_warps + 3) / 4);
+  switch (C / 32) {
+    case 1: out_conv_stream_kernel<1><<<blocks, 128, 0, c.stream>>>(x, w, bias, T, strip, strips, n_warps, y); break;
+    case 2: out_conv_stream_kernel<2><<<blocks, 128, 0, c.stream>>>(x, w, bias, T, strip, strips, n_warps, y); break;
+    case 3: out_conv_stream_kernel<3><<<blocks, 128, 0, c.stream>>>(x, w, bias, T, strip, strips, n_warps, y); break;
+    default: out_conv_stream_kernel<4><<<blocks, 128, 0, c.stream>>>(x, w, bias, T, strip, strips, n_warps, y); break;
+  }
+  c.tick();
+}
+
 void init_codec_kernels() {
   Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   Q3_CUDA(cudaFuncSetAttribute(out_conv_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));

@@ -27,6 +27,9 @@ void launch_rvq_embed(const LaunchCtx& c, const int* codes, const float* const* 
                       float* emb);
 void launch_out_conv(const LaunchCtx& c, const float* x, const float* w, const float* bias, int C, int B, int T, float* y);
 void launch_out_conv_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y);
+// streaming form (one pass over the activations, weights in registers); C in {32, 64, 96, 128}
+bool out_conv_stream_supported(int C);
+void launch_out_conv_stream_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y);
 // emb fp32 [M][2D] (bit-exact gather-sums) and/or its fp16 copy
 void launch_rvq_embed_f16(const LaunchCtx& c, const int* codes, const float* const* codebooks, int Q, int n_sem, int D, int size, int M,
                           __half* emb16);
