@@ -413,38 +413,60 @@ __global__ void __launch_bounds__(128) out_conv_stream_kernel(const __half* __re
   for (int j = 0; j < 7; ++j) acc[j] = 0.f;
   float keep = 0.f;
   const int r0 = t0 - 6 > 0 ? t0 - 6 : 0;  // rows before 0 are the causal zero padding
-#pragma unroll 7
-  for (int r = r0; r < t1; ++r) {
-    float xv[CPL];
+  // rows in chunks of 8, the next chunk's loads issued before the current chunk's arithmetic: 16 rows x 64 B per load in flight per warp
+  // (a row-at-a-time loop leaves one row in flight: the shuffles and the guarded store keep the compiler from hoisting the loads)
+  constexpr int R = 8;
+  __half cur[R][CPL], nxt[R][CPL];
+  auto fetch = [&](__half (&dst)[R][CPL], int r) {
 #pragma unroll
-    for (int j = 0; j < CPL; ++j) xv[j] = __half2float(xb[(size_t)r * C + j * 32 + lane]);
+    for (int i = 0; i < R; ++i) {
+      const int rr = r + i < T ? r + i : T - 1;  // clamped: rows past the strip only feed outputs that are never stored
 #pragma unroll
-    for (int j = 0; j < 7; ++j)
+      for (int j = 0; j < CPL; ++j) dst[i][j] = xb[(size_t)rr * C + j * 32 + lane];
+    }
+  };
+  fetch(cur, r0);
+  for (int r = r0; r < t1; r += R) {
+    if (r + R < t1) fetch(nxt, r + R);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) acc[j] = fmaf(xv[c], wr[6 - j][c], acc[j]);
-    float v = acc[0];  // output r is complete: rows r - 6 .. r have been added
+    for (int i = 0; i < R; ++i) {
+      float xv[CPL];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) acc[j] = acc[j + 1];
-    acc[6] = 0.f;
-    if (r >= t0) {
+      for (int c = 0; c < CPL; ++c) xv[c] = __half2float(cur[i][c]);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      v += b0;
-      // clip(-1, 1); a NaN becomes 0 here so the host needs no scrub pass (Qwen3TTSPipeline.swift:565-570: NaN/Inf -> 0 after the clip)
-      v = (v != v) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v));
-      const int i = r - t0;
-      if ((i & 31) == lane) keep = v;
-      if ((i & 31) == 31 || r == t1 - 1) {
-        const int base = t0 + (i & ~31);
-        if (base + lane <= r) y[(size_t)b * T + base + lane] = keep;
+      for (int j = 0; j < 7; ++j)
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) acc[j] = fmaf(xv[c], wr[6 - j][c], acc[j]);
+      float v = acc[0];  // output r + i is complete: rows r + i - 6 .. r + i have been added
+#pragma unroll
+      for (int j = 0; j < 6; ++j) acc[j] = acc[j + 1];
+      acc[6] = 0.f;
+      const int ro = r + i;
+      if (ro >= t0 && ro < t1) {  // warp-uniform
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        v += b0;
+        // clip(-1, 1); a NaN becomes 0 here so the host needs no scrub pass (Qwen3TTSPipeline.swift:565-570: NaN/Inf -> 0 after the clip)
+        v = (v != v) ? 0.0f : fminf(1.0f, fmaxf(-1.0f, v));
+        const int idx = ro - t0;
+        if ((idx & 31) == lane) keep = v;
+        if ((idx & 31) == 31 || ro == t1 - 1) {
+          const int base = t0 + (idx & ~31);
+          if (base + lane <= ro) y[(size_t)b * T + base + lane] = keep;
+        }
       }
     }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) cur[i][j] = nxt[i][j];
   }
 }
 bool out_conv_stream_supported(int C) { return C == 32 || C == 64 || C == 96 || C == 128; }
 void launch_out_conv_stream_f16(const LaunchCtx& c, const __half* x, const float* w, const float* bias, int C, int B, int T, float* y) {
   if (B <= 0 || T <= 0) return;
-  const int strip = 512;
+  static const int strip_env = getenv("Q3TTS_OUT_STRIP") ? atoi(getenv("Q3TTS_OUT_STRIP")) : 0;
+  const int strip = strip_env >= 32 ? (strip_env & ~31) : 256;  // multiple of 32 (outputs are stored 32 at a time); ~3 waves of warps at B x T = 64 x 49 920
   const int strips = (T + strip - 1) / strip, n_warps = B * strips;
   const unsigned blocks = (unsigned)((n_warps + 3) / 4);
   switch (C / 32) {
