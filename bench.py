@@ -20,7 +20,9 @@ prefill + 36 frame steps + windowed codec decode to PCM.
   config3  = BASELINE.json configs[2]: 1.7B bf16, 512 utterances x 125 frames sharded over the ranks, whole-sequence decode, with the
              NCCL gather of lengths + PCM to rank 0 AFTER the timed region (its time reported separately);
   config4  = BASELINE.json configs[3]: codec decode only, 128 clips x 750 frames sharded over the ranks, chunkedDecode(100, 10) and
-             whole-sequence T = 750.
+             whole-sequence T = 750;
+  config5  = BASELINE.json configs[4] (one GPU): 1.7B CustomVoice generateToFile of a long text (chunk-parallel) as CustomVoice and as an
+             ICL clone, with the reference-audio and speaker encoders timed on a 6 s clip.
 
 Multi-GPU: request-parallel replicas — one process per GPU (torchrun), each with its own shard of utterances (weak
 scaling on the headline line); NCCL carries only the barrier, the max-over-ranks time, the sums, and the result gather.
@@ -238,6 +240,57 @@ def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
                               "seconds": gather_s, "bytes_into_rank0": moved, "utterances_on_rank0": len(allpcm)}}
 
 
+def run_config5(q, checkpoint, a, local_rank):
+    """BASELINE.json configs[4]: 1.7B CustomVoice long-text generateToFile with chunking + ICL reference-audio encode / clone (rank 0,
+    one GPU).  Through the mirrored Swift API (qwen3tts_b200.Qwen3TTSPipeline): `encode_reference_audio` and `extract_speaker_embedding`
+    of a 6 s clip, then two files of the same 24-sentence text -- (a) CustomVoice: speaker + instruct, (b) clone: reference transcript +
+    the ICL codes -- with the reference's defaults (temperature 0.85, maxTokens 600 per text chunk, runtime 4/6-bit quantisation of the
+    bf16 checkpoint ON).  Random weights never emit EOS, so every text chunk runs its 600 frames (48 s of audio)."""
+    import tempfile
+
+    d = os.path.join(os.environ.get("Q3TTS_TEST_CKPT", "/tmp/q3tts_test_ckpt"), f"1.7b-cv_b0_bf16_s0_init{INIT}_enc")
+    checkpoint.write_checkpoint(d, "1.7b-cv", bits=0, dtype="bf16", seed=0, init=INIT, encoder="full", speaker_encoder="full")
+    t0 = time.perf_counter()
+    p = q.Qwen3TTSPipeline(d, q.Qwen3TTSPipelineConfiguration(device=local_rank, max_batch=32))
+    load_s = time.perf_counter() - t0
+    try:
+        assert p.supports_custom_voice and p.supports_icl and p.supports_voice_cloning
+        tt = np.arange(24000 * 6) / 24000.0
+        clip = (0.2 * np.sin(2 * np.pi * 220 * tt) * np.sin(2 * np.pi * 3 * tt) + 0.05 * np.random.default_rng(5).standard_normal(tt.size)).astype(np.float32)
+        p.encode_reference_audio(clip[:24000])  # warm-up (workspaces)
+        p.extract_speaker_embedding(clip[:24000])
+        t0 = time.perf_counter()
+        codes = p.encode_reference_audio(clip)
+        enc_ms = (time.perf_counter() - t0) * 1e3
+        enc_dev_ms = p.engine.timing().device_ms
+        t0 = time.perf_counter()
+        emb = p.extract_speaker_embedding(clip)
+        spk_ms = (time.perf_counter() - t0) * 1e3
+        spk_dev_ms = p.engine.timing().device_ms
+        sentence = "The quick brown fox jumps over the lazy dog near the quiet river bank while the evening light fades slowly. "
+        text = sentence * 24
+        chunks = q.TextChunker.chunk(text, q.TextChunker.default_max_words)
+        res = {}
+        with tempfile.TemporaryDirectory() as td:
+            for tag, kw in (("custom_voice", dict(speaker="aiden", instruct="Speak slowly, in a warm and calm voice.")),
+                            ("icl_clone", dict(reference_transcript="This is the reference recording.", reference_audio_codes=codes))):
+                path = os.path.join(td, tag + ".wav")
+                if tag == "custom_voice":
+                    p.generate_to_file(sentence * 2, path, **kw)  # warm-up: graphs, workspaces
+                t0 = time.perf_counter()
+                n = p.generate_to_file(text, path, **kw)
+                wall = time.perf_counter() - t0
+                res[tag] = {"samples": int(n), "audio_s": n / 24000.0, "wall_s": wall, "value": n / 24000.0 / wall, "unit": UNIT, "file_bytes": os.path.getsize(path)}
+        return {"workload": "BASELINE.json configs[4]: Qwen3-TTS-12Hz-1.7B CustomVoice (assumed dims, bf16 checkpoint, runtime 4/6-bit quantisation at load = the "
+                            f"reference's default), generateToFile of a {len(text.split())}-word text = {len(chunks)} text chunks x 600 frames run as ONE batch on a "
+                            "32-slot handle, 16+8 codec windows, 16-bit WAV on disk; wall clock through the mirrored Swift API incl. tokenisation, H2D / D2H and the file write",
+                "text_chunks": len(chunks), "load_s": load_s, **res,
+                "encode_reference_audio": {"clip_s": 6.0, "frames": int(codes.shape[1]), "quantizers": int(codes.shape[0]), "wall_ms": enc_ms, "device_ms": enc_dev_ms},
+                "extract_speaker_embedding": {"clip_s": 6.0, "dim": int(emb.size), "wall_ms": spk_ms, "device_ms": spk_dev_ms}}
+    finally:
+        p.close()
+
+
 def run_config4(q, ckpt_dir, dist, a, rank, local_rank, world, tf):
     """BASELINE.json configs[3]: codec decode only, codes int32 [128, 750, 16] uniform in [0, 2048), seed 3; batch axis split over ranks."""
     import torch
@@ -294,6 +347,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="headline line only (no latency / config3 / config4 blocks)")
     ap.add_argument("--config3", default="on", choices=["on", "off"])
     ap.add_argument("--config4", default="on", choices=["on", "off"])
+    ap.add_argument("--config5", default="on", choices=["on", "off"])
     ap.add_argument("--config3-utterances", type=int, default=512)
     ap.add_argument("--config3-handles", type=int, default=4, help="handles per GPU serving config3's batches concurrently (1 = one chain of launches)")
     ap.add_argument("--config4-clips", type=int, default=128)
@@ -518,11 +572,13 @@ def main():
               "ms_per_frame_step_batch": sum(r["talker"] - r["prefill"] for r in r2) / 2 / a.frames * 1e3}
         eng.close()
 
-    cfg3 = cfg4 = None
+    cfg3 = cfg4 = cfg5 = None
     if extras and a.config4 == "on":
         cfg4 = run_config4(q, ckpt_dir, dist, a, rank, local_rank, world, tf)
     if extras and a.config3 == "on":
         cfg3 = run_config3(q, checkpoint, dist, a, rank, local_rank, world)
+    if extras and a.config5 == "on" and world == 1:
+        cfg5 = run_config5(q, checkpoint, a, local_rank)
     clocks_all = sampler.snapshot()
     sampler.stop()
 
@@ -543,7 +599,7 @@ def main():
                 "talker": {"ms_per_frame_step_batch": talker_ms_frame, "prefill_ms_per_step": sum(r["prefill"] for r in res) / a.steps * 1e3,
                            "share_of_step": sum(r["talker"] for r in res) / max(1e-9, dev), "algorithmic_weight_bytes_per_frame_step": eng_bytes,
                            "frame_step_hbm_frac": (eng_bytes / max(1e-9, talker_ms_frame * 1e-3) / 1e9) / hbm},
-                "other_weight_operand_mode": ab, "batches_in_flight": inflight, "config3": cfg3, "config4": cfg4,
+                "other_weight_operand_mode": ab, "batches_in_flight": inflight, "config3": cfg3, "config4": cfg4, "config5": cfg5,
                 "wall_s_timed_region": total_max}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

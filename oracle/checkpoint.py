@@ -104,6 +104,8 @@ def preset(name: str) -> tuple[TalkerDims, CodecDims]:
         return TalkerDims(), CodecDims()
     if name == "1.7b":
         return TalkerDims(hidden_size=2048, intermediate_size=6144), CodecDims()
+    if name == "1.7b-cv":  # BASELINE.json configs[4]: the 1.7B CustomVoice variant (config.json `tts_model_type`, Qwen3Config.swift:230-233)
+        return TalkerDims(hidden_size=2048, intermediate_size=6144, tts_model_type="custom_voice"), CodecDims()
     if name == "tiny":
         t = TalkerDims(hidden_size=256, num_hidden_layers=2, text_vocab_size=640, text_hidden_size=128,
                        num_attention_heads=4, num_key_value_heads=2, head_dim=128, intermediate_size=512,

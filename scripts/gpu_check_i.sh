@@ -1,5 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for S in 128 256 512; do echo "strip=$S"; Q3TTS_OUT_STRIP=$S timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1; done
-echo "strip=256"; Q3TTS_OUT_STRIP=256 timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1
-echo "strip=128"; Q3TTS_OUT_STRIP=128 timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1
+timeout 1500 python bench.py --no-cpu-baseline --config3 off --config4 off > gpurun_out/r2b_bench_c5.json 2> gpurun_out/r2b_bench_c5.err; tail -5 gpurun_out/r2b_bench_c5.err
+python -c "
+import json
+j = json.loads(open('gpurun_out/r2b_bench_c5.json').read().strip().splitlines()[-1])
+print(json.dumps(j['config5'], indent=1))
+"
