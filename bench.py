@@ -179,7 +179,8 @@ def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
     # dependent launches that leaves the SMs > 85 % idle, so independent chains overlap (measured at 1.7B bf16, 512 utterances: 997 / 1408 / 1575 / 1712 audio-s/s
     # with 1 / 2 / 3 / 4 handles; one 128-row chain gains 1.24x over one 64-row chain).  Requests are independent: which handle serves one does not change its result.
     H = max(1, a.config3_handles)
-    engs = [q.Engine(d, device=local_rank, max_batch=B, max_frames=128, kv_capacity=512) for _ in range(H)]
+    engs = [q.Engine(d, device=local_rank, max_batch=B, max_frames=128, kv_capacity=512)]
+    engs += [engs[0].clone() for _ in range(H - 1)]  # q3tts_clone: one copy of the weights, H streams / KV rings / codec instances
     up = engs[0].info.codec_total_upsample
     allreq = make_requests(q, total, frames, 2, 0, lo=20, hi=61, temperature=0.85, stream=False)
     mine = [allreq[i] for i in idx]
@@ -523,7 +524,7 @@ def main():
         # ---- the same step with several batches IN FLIGHT (not the headline: BASELINE.json configs[1] is one batch of 64): H handles on H host
         # threads, each generating `steps` of the headline's batches through the same public call with its own host buffers
         H = 4
-        more = [q.Engine(ckpt_dir, device=local_rank, max_batch=a.batch, max_frames=max(64, a.frames), kv_capacity=512, packed_gemm=a.packed_gemm) for _ in range(H - 1)]
+        more = [eng.clone() for _ in range(H - 1)]  # q3tts_clone: shares eng's weights
         handles = [eng] + more
         bufs = [out_bufs] + [[np.zeros(a.frames * up, dtype=np.float32) for _ in range(a.batch)] for _ in more]
         got = [0] * H

@@ -159,6 +159,14 @@ int32_t q3tts_abi_version(void);
 void q3tts_default_options(q3tts_options* opts);
 void q3tts_default_request(q3tts_request* req);
 q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tts_handle** out);
+/* A second handle on the same device that SHARES the parent's talker weights (packed / dense tensors and their fp16 tensor-core copies;
+ * reference counted: parent and clones may be destroyed in any order) and owns everything mutable: stream, KV rings, slot state,
+ * activation buffers, CUDA graphs, codec instance.  Same options as the parent.  Purpose: a batched decode step is a latency-bound chain
+ * of ~570 dependent launches that leaves the SMs mostly idle; a host with more than max_batch pending requests serves them through 2-4
+ * handles from as many threads (1.7B bf16, 512 utterances: 997 / 1 408 / 1 575 / 1 712 audio-s/s with 1 / 2 / 3 / 4 handles) without
+ * paying for the weights again.  Results per request are bit-identical to the parent's.  The reference-audio and speaker encoders stay
+ * with the parent.  No reference counterpart (the reference serves one utterance at a time). */
+q3tts_status q3tts_clone(q3tts_handle* parent, q3tts_handle** out);
 void q3tts_destroy(q3tts_handle* h);
 /* error text of the last failing call on `h`; h == NULL: of the last failing q3tts_create on this thread */
 const char* q3tts_last_error(const q3tts_handle* h);

@@ -450,6 +450,7 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
     Q3_CUDA(cudaEventCreate(&h->ev_start));
     Q3_CUDA(cudaEventCreate(&h->ev_stop));
     const std::string dir(model_dir);
+    h->model_dir = dir;
     if (h->opt.load_talker) {
       // config.json, then model.safetensors (Qwen3TTSPipeline.swift:127-141)
       Json root = parse_json_file(dir + "/config.json");
@@ -480,6 +481,47 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
           cudaGetLastError();
         }
       }
+    }
+    Q3_CUDA(cudaStreamSynchronize(h->stream));
+    *out = h;
+    return Q3TTS_OK;
+  } catch (const Error& e) {
+    g_create_error = e.what();
+    cudaGetLastError();
+    delete h;
+    return e.status;
+  } catch (const std::exception& e) {
+    g_create_error = e.what();
+    delete h;
+    return Q3TTS_ERR_CUDA;
+  }
+}
+
+q3tts_status q3tts_clone(q3tts_handle* parent, q3tts_handle** out) {
+  if (!out) return Q3TTS_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!parent) return Q3TTS_ERR_INVALID_ARG;
+  q3tts_handle* h = nullptr;
+  try {
+    std::lock_guard<std::mutex> lk(parent->mu);
+    Q3_CHECK(!parent->poisoned, Q3TTS_ERR_CUDA, "the parent handle is poisoned");
+    Q3_CUDA(cudaSetDevice(parent->opt.device));
+    h = new q3tts_handle();
+    h->opt = parent->opt;
+    h->model_dir = parent->model_dir;
+    Q3_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));  // always its own stream: the point of a clone is a second chain
+    h->own_stream = true;
+    h->opt.stream = h->stream;
+    Q3_CUDA(cudaEventCreate(&h->ev_start));
+    Q3_CUDA(cudaEventCreate(&h->ev_stop));
+    if (parent->talker) {
+      h->cfg = parent->cfg;
+      h->talker.reset(new TalkerEngine(h->model_dir, h->cfg, h->opt, h->stream, &h->counter, parent->talker->shared()));
+      h->has_talker = true;
+    }
+    if (parent->codec) {  // codec weights are small (0.6 GB with their fp16 copies): loaded again, with their own workspace
+      h->codec.reset(new CodecDecoder(h->model_dir + "/speech_tokenizer", h->stream, &h->counter, h->opt.codec_max_frames));
+      h->codec->set_use_graph(h->opt.use_cuda_graph != 0);
     }
     Q3_CUDA(cudaStreamSynchronize(h->stream));
     *out = h;

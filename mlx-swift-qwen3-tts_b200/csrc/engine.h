@@ -31,10 +31,19 @@ struct Admission {
   int prefill_len = 0;
 };
 
+// Immutable after load: the checkpoint's tensors (packed / dense, runtime-quantised when asked) and the fp16 tensor-core copies.  Shared
+// by a handle and its clones (q3tts_clone): every handle owns its stream, KV rings, slot state and activation buffers, none owns the weights.
+struct TalkerShared {
+  DeviceArena arena;
+  TalkerWeights w;
+  int weight_dtype = Q3TTS_BF16, eff_bits = 0, eff_group = 64;
+  std::mutex mu;  // building the tensor-core copies (first handle of >= 3 slots)
+};
+
 class TalkerEngine {
  public:
   TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
-               LaunchCounter* counter);
+               LaunchCounter* counter, std::shared_ptr<TalkerShared> shared = nullptr);  // shared: a clone (weights are not loaded again)
   ~TalkerEngine();
 
   // Prompt assembly + prefill of `req` into `slot` (Model/Qwen3Talker.swift:344-462).
@@ -66,10 +75,11 @@ class TalkerEngine {
   int max_batch() const { return opt_.max_batch; }
   int kv_capacity() const { return opt_.kv_capacity; }
   int max_frames() const { return opt_.max_frames; }
-  int weight_dtype() const { return weight_dtype_; }
-  int quant_bits() const { return eff_bits_; }
-  int quant_group() const { return eff_group_; }
-  size_t device_bytes() const { return arena_.total(); }
+  int weight_dtype() const { return shared_->weight_dtype; }
+  int quant_bits() const { return shared_->eff_bits; }
+  int quant_group() const { return shared_->eff_group; }
+  size_t device_bytes() const { return arena_.total() + (owns_weights_ ? shared_->arena.total() : 0); }  // a clone reports its own state only
+  const std::shared_ptr<TalkerShared>& shared() const { return shared_; }
   size_t weight_bytes_per_frame() const { return w_.talker_step_bytes + 15 * w_.cp_pass_bytes; }
   int64_t graph_replays = 0, graph_nodes_replayed = 0, mega_launches = 0;
   bool megakernel_enabled() const { return mega_.ok; }
@@ -109,9 +119,10 @@ class TalkerEngine {
   EngineOptions opt_;
   cudaStream_t stream_;
   LaunchCounter* counter_;
-  DeviceArena arena_;
-  TalkerWeights w_;
-  int weight_dtype_ = Q3TTS_BF16, eff_bits_ = 0, eff_group_ = 64;
+  DeviceArena arena_;                     // this handle's state: KV rings, slots, activations, plans
+  std::shared_ptr<TalkerShared> shared_;  // the weights (declared before w_: w_ refers into it)
+  bool owns_weights_ = false;
+  TalkerWeights& w_;
 
   int max_rows_ = 0, max_tp_rows_ = 0, set_words_ = 0;
   // rows from which linears run on tensor cores (env Q3TTS_TC_MIN_ROWS sets both; 0 disables).  Decode steps switch at 3
@@ -175,6 +186,7 @@ class TalkerEngine {
 
 struct Handle {
   std::mutex mu;
+  std::string model_dir;
   std::string last_error;
   bool poisoned = false;  // a kernel fault (trap, illegal address) left the CUDA context unusable: every later call fails the same way
   EngineOptions opt;

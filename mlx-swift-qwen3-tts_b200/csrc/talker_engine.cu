@@ -14,10 +14,13 @@ void init_talker_kernels();  // talker_kernels.cu: opt-in shared-memory attribut
 int mega_max_blocks_per_sm(int fmt, int slots, size_t smem);  // frame_kernel.cu
 
 TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg, const EngineOptions& opt, cudaStream_t stream,
-                           LaunchCounter* counter)
-    : cfg_(cfg), opt_(opt), stream_(stream), counter_(counter) {
+                           LaunchCounter* counter, std::shared_ptr<TalkerShared> shared)
+    : cfg_(cfg), opt_(opt), stream_(stream), counter_(counter), shared_(shared ? shared : std::make_shared<TalkerShared>()),
+      owns_weights_(!shared), w_(shared_->w) {
   init_talker_kernels();
-  load_talker_weights(model_dir, cfg_, arena_, stream_, w_, weight_dtype_, eff_bits_, eff_group_, opt_.runtime_quantization != 0);
+  if (owns_weights_)
+    load_talker_weights(model_dir, cfg_, shared_->arena, stream_, w_, shared_->weight_dtype, shared_->eff_bits, shared_->eff_group,
+                        opt_.runtime_quantization != 0);
   const int B = opt_.max_batch, C = opt_.kv_capacity, F = opt_.max_frames;
   const int H = cfg_.hidden_size, Hcp = cfg_.cp.hidden_size;
   Q3_CHECK(B >= 1 && C >= 208 && F >= 1, Q3TTS_ERR_INVALID_ARG, "bad options: max_batch %d kv_capacity %d max_frames %d", B, C, F);
@@ -84,7 +87,10 @@ TalkerEngine::TalkerEngine(const std::string& model_dir, const TalkerConfig& cfg
   if (const char* e = getenv("Q3TTS_TC_MIN_ROWS")) tc_min_rows_ = tc_min_rows_step_ = atoi(e);
   if (tc_min_rows_step_ > 0 && B >= tc_min_rows_step_) {  // batched handle: fp16 copies for prefill, packed weights for decode steps
     init_tc_gemm();
-    build_tc_weights();
+    {
+      std::lock_guard<std::mutex> lk(shared_->mu);
+      if (!w_.has_tc) build_tc_weights();  // a clone finds them built
+    }
     d_h16_ = arena_.alloc((size_t)max_rows_ * std::max(wide_h, cfg_.text_hidden_size) * 2);
     d_attn16_ = arena_.alloc((size_t)max_rows_ * attn_w * 2);
     d_act16_ = arena_.alloc((size_t)max_rows_ * act_w * 2);
@@ -379,7 +385,7 @@ TcLinear TalkerEngine::make_tc(const Linear& L, bool interleave_halves, const fl
   TcLinear t;
   t.out = L.out; t.in = L.in; t.bias = L.bias;
   if (L.bits) { t.qw = L.qw; t.qscales = L.scales; t.qbiases = L.biases; t.qbits = L.bits; t.qgroup = L.group; t.qsdt = L.sdt; t.fold = fold; t.halves = interleave_halves; }
-  __half* dst = (__half*)arena_.alloc((size_t)L.out * L.in * 2);
+  __half* dst = (__half*)shared_->arena.alloc((size_t)L.out * L.in * 2);
   if (L.bits && fold) {
     float* tmp = nullptr;
     Q3_CUDA(cudaMalloc(&tmp, (size_t)L.out * L.in * 4));

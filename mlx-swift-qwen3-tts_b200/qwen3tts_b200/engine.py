@@ -149,6 +149,17 @@ class Engine:
         self.info = A.Info()
         A.check(L.q3tts_get_info(self._h, C.byref(self.info)), self._h)
 
+    def clone(self) -> "Engine":
+        """A second handle on the same device sharing this one's talker weights (q3tts_clone): own stream, KV rings, buffers and codec.
+        Serve more than `max_batch` pending requests through 2-4 handles from as many threads."""
+        h = C.c_void_p()
+        A.check(A.lib().q3tts_clone(self._h, C.byref(h)), None)
+        e = Engine.__new__(Engine)
+        e._h = h
+        e.info = A.Info()
+        A.check(A.lib().q3tts_get_info(e._h, C.byref(e.info)), e._h)
+        return e
+
     def close(self):
         if getattr(self, "_h", None):
             A.lib().q3tts_destroy(self._h)

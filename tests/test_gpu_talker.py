@@ -692,7 +692,9 @@ def test_two_handles_served_from_two_threads_equal_one_handle(tiny8):
     for b0 in range(0, 16, 4):
         want += one.generate_codes_batch(reqs[b0:b0 + 4])
     one.close()
-    engs = [q.Engine(tiny8, max_batch=4, max_frames=64) for _ in range(2)]
+    first = q.Engine(tiny8, max_batch=4, max_frames=64)
+    engs = [first, first.clone()]  # q3tts_clone: the second handle shares the first one's weights
+    assert engs[1].info.device_bytes < engs[0].info.device_bytes and engs[1].info.hidden_size == engs[0].info.hidden_size
     got = [None] * 16
 
     def serve(h):
@@ -703,7 +705,10 @@ def test_two_handles_served_from_two_threads_equal_one_handle(tiny8):
     th = [threading.Thread(target=serve, args=(h,)) for h in range(2)]
     [t.start() for t in th]
     [t.join() for t in th]
-    for e in engs:
-        e.close()
+    engs[0].close()  # the parent first: the clone keeps the shared weights alive
+    again = engs[1].generate_codes_batch(reqs[:4])
+    engs[1].close()
     for i in range(16):
         assert got[i] is not None and np.array_equal(got[i], want[i]), f"request {i} differs between one handle and two concurrent handles"
+    for i in range(4):
+        assert np.array_equal(again[i], want[i]), "a clone must outlive its parent"
