@@ -175,46 +175,30 @@ def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
         dist.barrier()
     total, frames, B = a.config3_utterances, 125, 64
     idx = parallel.shard_indices(total, rank, world)
-    # `--config3-handles` handles per GPU, each fed by its own host thread with batches of 64: a batched frame step is a chain of ~570
-    # dependent launches that leaves the SMs > 85 % idle, so independent chains overlap (measured at 1.7B bf16, 512 utterances: 997 / 1408 / 1575 / 1712 audio-s/s
-    # with 1 / 2 / 3 / 4 handles; one 128-row chain gains 1.24x over one 64-row chain).  Requests are independent: which handle serves one does not change its result.
+    # `--config3-handles` lanes per GPU: a batched frame step is a chain of ~570 dependent launches that leaves the SMs > 85 % idle, so
+    # independent chains overlap (measured at 1.7B bf16, 512 utterances: 997 / 1408 / 1575 / 1712 audio-s/s with 1 / 2 / 3 / 4 handles fed from
+    # host threads; one 128-row chain gains 1.24x over one 64-row chain).  Requests are independent: which lane serves one
+    # does not change its result.
     H = max(1, a.config3_handles)
-    engs = [q.Engine(d, device=local_rank, max_batch=B, max_frames=128, kv_capacity=512)]
-    engs += [engs[0].clone() for _ in range(H - 1)]  # q3tts_clone: one copy of the weights, H streams / KV rings / codec instances
-    up = engs[0].info.codec_total_upsample
+    eng = q.Engine(d, device=local_rank, max_batch=B, max_frames=128, kv_capacity=512, lanes=H)  # q3tts_options.lanes: H chains inside ONE call
+    up = eng.info.codec_total_upsample
     allreq = make_requests(q, total, frames, 2, 0, lo=20, hi=61, temperature=0.85, stream=False)
     mine = [allreq[i] for i in idx]
-    batches = [mine[b0:b0 + B] for b0 in range(0, len(mine), B)]  # calls of <= B keep host buffers bounded
-    for e in engs:
-        e.generate_pcm_batch(mine[:B], q.DECODE_WHOLE)  # warm-up: graphs, workspaces
+    eng.generate_pcm_batch(mine[:min(len(mine), B * H)], q.DECODE_WHOLE)  # warm-up: clones, graphs, workspaces
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    results = [None] * len(batches)
-    stats = [[0.0, 0] for _ in range(H)]
-
-    def serve(h):
-        for bi in range(h, len(batches), H):
-            outs, _ = engs[h].generate_pcm_batch(batches[bi], q.DECODE_WHOLE)
-            tm = engs[h].timing()
-            stats[h][0] += (tm.talker_ms + tm.decode_ms) * 1e-3
-            stats[h][1] += int(tm.kernel_launches)
-            results[bi] = list(outs)  # fresh host buffers per call
-
     t0 = time.perf_counter()
-    threads = [threading.Thread(target=serve, args=(h,)) for h in range(H)]
-    for t in threads:
-        t.start()
-    for t in threads:
-        t.join()
+    # one public call with the rank's whole share: the library splits it over its lanes (this handle + clones sharing its weights), every
+    # lane batches continuously over its 64 slots
+    pcm, _ = eng.generate_pcm_batch(mine, q.DECODE_WHOLE)
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
-    assert all(r is not None for r in results)
-    pcm = [p for r in results for p in r]
-    # device time of the region: every handle's calls are sequential on its own stream and the handles overlap, so the span is at least the
-    # busiest handle's sum of (talker + codec) event times -- for one handle exactly what it was before
-    dev_s = max(st[0] for st in stats)
-    launches = sum(st[1] for st in stats)
+    tm = eng.timing()
+    pcm = list(pcm)
+    # device time of the call: the lanes overlap; q3tts_timing.device_ms is the slowest lane's CUDA-event span (talker + codec of its share)
+    dev_s = (tm.device_ms if H > 1 else tm.talker_ms + tm.decode_ms) * 1e-3
+    launches = int(tm.kernel_launches)
     samples = sum(int(p.size) for p in pcm)
     dev = torch.device("cuda", local_rank)
     t_wall, sums = parallel.aggregate(dist if world > 1 else None, dev, wall, samples, (launches,))
@@ -227,14 +211,13 @@ def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
     allpcm, lengths, moved = parallel.gather_pcm(dist if world > 1 else None, dev, pcm, total, rank, world)
     torch.cuda.synchronize()
     gather_s = time.perf_counter() - g0
-    for e in engs:
-        e.close()
+    eng.close()
     if rank != 0:
         return None
     assert allpcm is not None and len(allpcm) == total and all(int(p.size) == l for p, l in zip(allpcm, lengths))
     return {"workload": f"BASELINE.json configs[2]: Qwen3-TTS-12Hz-1.7B (assumed dims H 2048 / MLP 6144, 2048->1024 code-predictor projection) bf16, "
-                        f"{total} utterances x 125 frames sharded over {world} GPU(s), batches of {B}, {H} handle(s) per GPU served concurrently, whole-sequence decode",
-            "handles_per_gpu": H,
+                        f"{total} utterances x 125 frames sharded over {world} GPU(s), batches of {B}, {H} lane(s) per GPU (q3tts_options.lanes: one q3tts_generate_pcm_batch call per rank), whole-sequence decode",
+            "lanes_per_gpu": H,
             "value": sums[0] / 24000.0 / t_dev, "e2e": sums[0] / 24000.0 / t_wall, "unit": UNIT, "n_gpus": world, "utterances": total,
             "device_s": t_dev, "wall_s": t_wall, "gpu_launches": int(sums[1]), "dtype": "bf16 weights -> f16 operands x f32 accumulate",
             "result_gather": {"collective": "all_reduce(lengths) + gather(PCM) to rank 0 over NCCL" if world > 1 else "single rank: no collective",
@@ -350,7 +333,7 @@ def main():
     ap.add_argument("--config4", default="on", choices=["on", "off"])
     ap.add_argument("--config5", default="on", choices=["on", "off"])
     ap.add_argument("--config3-utterances", type=int, default=512)
-    ap.add_argument("--config3-handles", type=int, default=4, help="handles per GPU serving config3's batches concurrently (1 = one chain of launches)")
+    ap.add_argument("--config3-handles", type=int, default=4, help="q3tts_options.lanes of config3's handle: launch chains served concurrently per GPU (1 = one chain)")
     ap.add_argument("--config4-clips", type=int, default=128)
     ap.add_argument("--packed-gemm", type=int, default=0, choices=[0, 1, 2],
                     help="q3tts_options.packed_gemm of the measured handle: 1 = packed weights dequantised inside the tcgen05 GEMM, 2 / 0 = fp16 operand copies")

@@ -72,7 +72,11 @@ typedef struct q3tts_options {
   int32_t runtime_quantization; /* Qwen3TTSPipelineConfiguration.applyRuntimeQuantization (Qwen3TTSPipeline.swift:25, 184, 961-980): a checkpoint
                                without a `quantization` block is MLX-quantised at load, group 64, 6 bits for embeddings / q,k,v projections /
                                heads, 4 bits for the rest (codes held in an 8-bit container).  0 = run the checkpoint as stored */
-  int32_t reserved[6];
+  int32_t lanes;            /* > 1: q3tts_generate_pcm_batch / q3tts_generate_codes_batch calls with more than max_batch requests are split over
+                               `lanes` handles (this one + lazily created q3tts_clone()s sharing its weights), each served by a worker thread
+                               of the call: several latency-bound launch chains overlap on the device (see q3tts_clone).  The threads live
+                               only inside the call and never call back into the host.  0 / 1 = one chain (continuous batching over max_batch slots) */
+  int32_t reserved[5];
 } q3tts_options;
 
 typedef struct q3tts_info {

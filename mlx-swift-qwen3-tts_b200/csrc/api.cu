@@ -4,6 +4,7 @@
 #include <deque>
 #include <chrono>
 #include <map>
+#include <thread>
 
 #include "audio_encoder.h"
 #include "speaker_encoder.h"
@@ -18,6 +19,11 @@ using namespace q3;
 namespace q3 {
 void init_talker_kernels();
 Handle::~Handle() {
+  for (Handle* l : lanes) {
+    cudaStreamSynchronize(l->stream);
+    delete l;
+  }
+  lanes.clear();
   talker.reset();
   codec.reset();
   audio_encoder.reset();
@@ -440,6 +446,7 @@ q3tts_status q3tts_create(const char* model_dir, const q3tts_options* opts, q3tt
     Q3_CHECK(o.packed_gemm >= 0 && o.packed_gemm <= 2, Q3TTS_ERR_INVALID_ARG, "options.packed_gemm must be 0, 1 or 2");
     h->opt.packed_gemm = o.packed_gemm;
     h->opt.runtime_quantization = o.runtime_quantization != 0;
+    h->opt.lanes = std::max(1, std::min(o.lanes, 8));
     if (o.cuda_stream) {
       h->stream = (cudaStream_t)o.cuda_stream;
     } else {
@@ -508,6 +515,7 @@ q3tts_status q3tts_clone(q3tts_handle* parent, q3tts_handle** out) {
     Q3_CUDA(cudaSetDevice(parent->opt.device));
     h = new q3tts_handle();
     h->opt = parent->opt;
+    h->opt.lanes = 1;  // a clone is one chain
     h->model_dir = parent->model_dir;
     Q3_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));  // always its own stream: the point of a clone is a second chain
     h->own_stream = true;
@@ -656,8 +664,71 @@ q3tts_status q3tts_generate_codes(q3tts_handle* h, const q3tts_request* req, int
   });
 }
 
-q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t* const* codes_out,
-                                        int32_t capacity_frames, int32_t* frames_out) {
+// ---- q3tts_options.lanes: one call, several launch chains ---------------------------------------------------------------
+// A call with more requests than one handle has slots is split into contiguous shares, one per lane (this handle + clones that share its
+// weights); every share runs the ordinary single-handle path -- continuous batching over the lane's slots -- on a worker thread that lives
+// only inside the call.  Requests are independent and a handle's numeric path is fixed at creation, so every request gets
+// the bits it gets from a single-lane call.  Requests that ask for logits dumps keep the call on one lane (one dump slot per handle).
+static bool use_lanes(q3tts_handle* h, const q3tts_request* reqs, int32_t n) {
+  if (!h || !reqs || h->opt.lanes <= 1 || n <= h->opt.max_batch || h->poisoned) return false;
+  for (int i = 0; i < n; ++i)
+    if (reqs[i].code0_logits_out || reqs[i].cp_logits_out) return false;
+  return true;
+}
+
+}  // extern "C"
+template <typename F>
+static q3tts_status over_lanes(q3tts_handle* h, int32_t n, F&& run) {
+  const int B = h->opt.max_batch;
+  const int blocks = (n + B - 1) / B;
+  const int L = std::min(h->opt.lanes, blocks);
+  {  // clones are created on the first call that needs them
+    std::lock_guard<std::mutex> lk(h->lanes_mu);
+    while ((int)h->lanes.size() < L - 1) {
+      q3tts_handle* c = nullptr;
+      const q3tts_status st = q3tts_clone(h, &c);
+      if (st != Q3TTS_OK) {
+        std::lock_guard<std::mutex> lk2(h->mu);
+        h->last_error = "lane handle not created: " + g_create_error;
+        return st;
+      }
+      h->lanes.push_back(c);
+    }
+  }
+  // contiguous shares in whole blocks of max_batch requests (the last lane takes the remainder)
+  std::vector<int> off(L + 1, 0);
+  for (int l = 0; l < L; ++l) off[l + 1] = std::min<int>(n, off[l] + (blocks / L + (l < blocks % L ? 1 : 0)) * B);
+  off[L] = n;
+  std::vector<q3tts_status> st(L, Q3TTS_OK);
+  std::vector<std::thread> workers;
+  for (int l = 1; l < L; ++l)
+    workers.emplace_back([&, l] { st[l] = run(static_cast<q3tts_handle*>(h->lanes[l - 1]), off[l], off[l + 1] - off[l]); });
+  st[0] = run(h, off[0], off[1] - off[0]);
+  for (auto& w : workers) w.join();
+  // the call's timing: the lanes ran side by side -- times are the slowest lane's, counters add up
+  std::lock_guard<std::mutex> lk(h->mu);
+  q3tts_status result = st[0];
+  for (int l = 1; l < L; ++l) {
+    q3::Handle* lane = h->lanes[l - 1];
+    std::lock_guard<std::mutex> lk2(lane->mu);
+    const q3tts_timing& t = lane->timing;
+    q3tts_timing& a = h->timing;
+    a.device_ms = std::max(a.device_ms, t.device_ms); a.prefill_ms = std::max(a.prefill_ms, t.prefill_ms);
+    a.decode_ms = std::max(a.decode_ms, t.decode_ms); a.talker_ms = std::max(a.talker_ms, t.talker_ms);
+    a.kernel_launches += t.kernel_launches; a.graph_replays += t.graph_replays; a.frames += t.frames;
+    a.h2d_bytes += t.h2d_bytes; a.d2h_bytes += t.d2h_bytes; a.codec_flops += t.codec_flops; a.persistent_launches += t.persistent_launches;
+    if (result == Q3TTS_OK && st[l] != Q3TTS_OK) {
+      result = st[l];
+      h->last_error = "lane " + std::to_string(l) + ": " + lane->last_error;
+      if (lane->poisoned) h->poisoned = true;  // one CUDA context: a kernel fault on any lane ends them all
+    }
+  }
+  return result;
+}
+extern "C" {
+
+static q3tts_status generate_codes_batch_one(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t* const* codes_out,
+                                             int32_t capacity_frames, int32_t* frames_out) {
   return guarded(h, [&] {
     Q3_CHECK(reqs && frames_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
@@ -672,6 +743,14 @@ q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* re
       h->timing.h2d_bytes += (int64_t)reqs[i].n_text_ids * 4;
     }
     tm.finish();
+  });
+}
+
+q3tts_status q3tts_generate_codes_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t* const* codes_out,
+                                        int32_t capacity_frames, int32_t* frames_out) {
+  if (!use_lanes(h, reqs, n) || !frames_out) return generate_codes_batch_one(h, reqs, n, codes_out, capacity_frames, frames_out);
+  return over_lanes(h, n, [&](q3tts_handle* lane, int off, int cnt) {
+    return generate_codes_batch_one(lane, reqs + off, cnt, codes_out ? codes_out + off : nullptr, capacity_frames, frames_out + off);
   });
 }
 
@@ -931,8 +1010,8 @@ q3tts_status q3tts_generate_pcm(q3tts_handle* h, const q3tts_request* req, int32
   });
 }
 
-q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t mode, float* const* pcm_out,
-                                      int64_t capacity_samples, int64_t* samples_out, int32_t* frames_out) {
+static q3tts_status generate_pcm_batch_one(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t mode, float* const* pcm_out,
+                                           int64_t capacity_samples, int64_t* samples_out, int32_t* frames_out) {
   return guarded(h, [&] {
     Q3_CHECK(reqs && pcm_out && samples_out && n >= 0, Q3TTS_ERR_INVALID_ARG, "NULL argument");
     Q3_CHECK(h->talker != nullptr, Q3TTS_ERR_MODEL_NOT_LOADED, "Model is not loaded");
@@ -967,6 +1046,14 @@ q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs
       fprintf(stderr, "[q3tts host] generate_pcm_batch n=%d: talker loop %.1f ms (device %.1f), plan %.1f ms, decode jobs %.1f ms (device %.1f)\n", n,
               ms(w0, w1), h->timing.talker_ms, ms(w1, w2), ms(w2, w3), h->timing.decode_ms);
     }
+  });
+}
+
+q3tts_status q3tts_generate_pcm_batch(q3tts_handle* h, const q3tts_request* reqs, int32_t n, int32_t mode, float* const* pcm_out,
+                                      int64_t capacity_samples, int64_t* samples_out, int32_t* frames_out) {
+  if (!use_lanes(h, reqs, n) || !pcm_out || !samples_out) return generate_pcm_batch_one(h, reqs, n, mode, pcm_out, capacity_samples, samples_out, frames_out);
+  return over_lanes(h, n, [&](q3tts_handle* lane, int off, int cnt) {
+    return generate_pcm_batch_one(lane, reqs + off, cnt, mode, pcm_out + off, capacity_samples, samples_out + off, frames_out ? frames_out + off : nullptr);
   });
 }
 

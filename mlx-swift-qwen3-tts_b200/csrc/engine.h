@@ -20,6 +20,7 @@ struct EngineOptions {
   cudaStream_t stream = nullptr;
   int max_batch = 1, kv_capacity = 512, max_frames = 2400, use_cuda_graph = 1;
   int load_codec = 1, load_talker = 1, codec_max_frames = 2400, codec_max_batch = 8;
+  int lanes = 1;  // q3tts_options.lanes
   int max_trailing = 1024;
   int packed_gemm = 0;  // q3tts_options::packed_gemm
   int runtime_quantization = 0;  // q3tts_options::runtime_quantization
@@ -212,6 +213,9 @@ struct Handle {
   // A stream owns talker slot 0 from q3tts_stream_begin to q3tts_stream_free: while it is open, every other talker call on
   // the handle (and a second stream) fails with Q3TTS_ERR_INVALID_ARG instead of silently re-admitting the slot.
   void* open_stream = nullptr;
+  // q3tts_options.lanes > 1: clones of this handle (created on the first call that needs them), destroyed with it
+  std::mutex lanes_mu;
+  std::vector<Handle*> lanes;
   ~Handle();
 };
 

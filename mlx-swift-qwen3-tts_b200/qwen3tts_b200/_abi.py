@@ -26,7 +26,7 @@ p_i32, p_f32 = C.POINTER(C.c_int32), C.POINTER(C.c_float)
 class Options(C.Structure):
     _fields_ = [("struct_size", i32), ("device", i32), ("cuda_stream", C.c_void_p), ("max_batch", i32), ("kv_capacity", i32),
                 ("max_frames", i32), ("use_cuda_graph", i32), ("load_codec", i32), ("load_talker", i32),
-                ("codec_max_frames", i32), ("codec_max_batch", i32), ("packed_gemm", i32), ("runtime_quantization", i32), ("reserved", i32 * 6)]
+                ("codec_max_frames", i32), ("codec_max_batch", i32), ("packed_gemm", i32), ("runtime_quantization", i32), ("lanes", i32), ("reserved", i32 * 5)]
 
 
 class Info(C.Structure):

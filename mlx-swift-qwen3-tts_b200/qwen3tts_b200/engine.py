@@ -131,7 +131,7 @@ class CodeStream:
 class Engine:
     def __init__(self, model_dir: str, device: int = 0, max_batch: int = 1, kv_capacity: int = 512, max_frames: int = 2400,
                  use_cuda_graph: bool = True, load_codec: bool = True, load_talker: bool = True, codec_max_frames: int = 2400,
-                 cuda_stream: int | None = None, packed_gemm: int = 0, runtime_quantization: bool = False):
+                 cuda_stream: int | None = None, packed_gemm: int = 0, runtime_quantization: bool = False, lanes: int = 1):
         L = A.lib()
         o = A.Options()
         L.q3tts_default_options(C.byref(o))
@@ -140,6 +140,7 @@ class Engine:
         o.load_codec, o.load_talker, o.codec_max_frames = int(load_codec), int(load_talker), codec_max_frames
         o.packed_gemm = int(packed_gemm)
         o.runtime_quantization = 1 if runtime_quantization else 0
+        o.lanes = int(lanes)
         if cuda_stream:
             o.cuda_stream = C.c_void_p(cuda_stream)
         h = C.c_void_p()

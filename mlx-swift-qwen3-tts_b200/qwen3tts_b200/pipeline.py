@@ -45,6 +45,7 @@ class Qwen3TTSPipelineConfiguration:  # Qwen3TTSPipeline.swift:22-54
     # engine-side options (no reference counterpart)
     device: int = 0
     max_batch: int = 1
+    lanes: int = 1  # q3tts_options.lanes: launch chains served side by side when a call carries more than max_batch requests
     kv_capacity: int = 512
     use_cuda_graph: bool = True
     seed: int = 0
@@ -209,7 +210,8 @@ class Qwen3TTSPipeline:
         try:
             self.engine = Engine(model_path, device=self.config.device, max_batch=self.config.max_batch,
                                  kv_capacity=self.config.kv_capacity, max_frames=max(self.config.default_max_tokens, 600),
-                                 use_cuda_graph=self.config.use_cuda_graph, runtime_quantization=self.config.apply_runtime_quantization)
+                                 use_cuda_graph=self.config.use_cuda_graph, runtime_quantization=self.config.apply_runtime_quantization,
+                                 lanes=self.config.lanes)
         except A.Q3Error as e:
             if e.status == A.ERR_FILE_NOT_FOUND:
                 raise FileNotFound(e.message.split(": ", 1)[-1]) from e
@@ -312,7 +314,7 @@ class Qwen3TTSPipeline:
         # Every text chunk is an independent generation with a fresh KV cache (Qwen3TTSPipeline.swift:668-691), so a handle with
         # several slots runs `max_batch` chunks at a time through the batched path; a handle's numeric path is fixed at creation,
         # so the samples of a chunk do not depend on how many chunks shared its steps.  The file is written in chunk order.
-        group = max(1, int(self.info.max_batch))
+        group = max(1, int(self.info.max_batch)) * max(1, int(self.config.lanes))
         for g0 in range(0, len(chunks), group):
             part = chunks[g0: g0 + group]
             if on_progress:
@@ -350,7 +352,7 @@ class Qwen3TTSPipeline:
         all_s, tail = [], np.zeros(0, np.float32)
         # chunks are independent generations (:813-864): a handle with several slots runs `max_batch` of them per batched call, the
         # crossfade below consumes them in chunk order
-        group = max(1, int(self.info.max_batch))
+        group = max(1, int(self.info.max_batch)) * max(1, int(self.config.lanes))
         done: dict = {}
         for i, tc in enumerate(chunks):
             if on_progress:

@@ -712,3 +712,31 @@ def test_two_handles_served_from_two_threads_equal_one_handle(tiny8):
         assert got[i] is not None and np.array_equal(got[i], want[i]), f"request {i} differs between one handle and two concurrent handles"
     for i in range(4):
         assert np.array_equal(again[i], want[i]), "a clone must outlive its parent"
+
+
+def test_lanes_option_one_call_equals_single_lane(tiny8):
+    """q3tts_options.lanes: a call with more requests than max_batch is split over clones of the handle served by worker threads inside
+    the call; every request gets the bits of a single-lane handle, whatever lane and whatever neighbours it had."""
+    import qwen3tts_b200 as q
+
+    rng = np.random.default_rng(9)
+    reqs = [q.GenRequest(text_ids=rng.integers(0, 600, size=int(rng.integers(12, 30))).tolist(), speaker_id=-1, temperature=0.7, seed=300 + i,
+                         max_tokens=int(rng.integers(6, 20)), keep_invalid_frames=True) for i in range(22)]
+    one = q.Engine(tiny8, max_batch=4, max_frames=64)
+    want = one.generate_codes_batch(reqs)  # continuous batching over 4 slots
+    want_pcm, want_frames = one.generate_pcm_batch(reqs[:10], q.DECODE_FILE)
+    one.close()
+    eng = q.Engine(tiny8, max_batch=4, max_frames=64, lanes=3)
+    got = eng.generate_codes_batch(reqs)
+    tm = eng.timing()
+    assert tm.frames == sum(len(f) for f in want)
+    for i in range(len(reqs)):
+        assert np.array_equal(got[i], want[i]), f"request {i} differs between 1 and 3 lanes"
+    pcm, frames = eng.generate_pcm_batch(reqs[:10], q.DECODE_FILE)
+    assert list(frames) == list(want_frames)
+    for a, b in zip(pcm, want_pcm):
+        assert np.array_equal(a, b)
+    small = eng.generate_codes_batch(reqs[:3])  # fits one lane: the ordinary path
+    for i in range(3):
+        assert np.array_equal(small[i], want[i])
+    eng.close()
