@@ -24,6 +24,8 @@ public struct Qwen3TTSPipelineConfiguration: Sendable {
     public var crossfadeSamples: Int
     public var device: Int32 = 0                // CUDA ordinal (replaces MLX_DEVICE / DeviceSelector)
     public var seed: UInt64 = 0
+    public var maxBatch: Int32 = 1              // q3tts_options.max_batch: utterance slots of the handle (text chunks of generateToFile run batched)
+    public var lanes: Int32 = 1                 // q3tts_options.lanes: launch chains served side by side for calls with more than maxBatch requests
     public init(applyRuntimeQuantization: Bool = true, defaultTemperature: Float = 0.85, defaultMaxTokens: Int = 2400,
                 defaultStreamingChunkSize: Int = 12, crossfadeSamples: Int = 480) {
         self.applyRuntimeQuantization = applyRuntimeQuantization
@@ -73,6 +75,8 @@ public final class Qwen3TTSPipeline: @unchecked Sendable {
         q3tts_default_options(&opts)
         opts.device = configuration.device
         opts.runtime_quantization = configuration.applyRuntimeQuantization ? 1 : 0
+        opts.max_batch = max(1, configuration.maxBatch)
+        opts.lanes = max(1, configuration.lanes)
         opts.max_frames = Int32(max(configuration.defaultMaxTokens, 600))
         var h: OpaquePointer?
         let st = q3tts_create(modelPath.path, &opts, &h)
