@@ -162,15 +162,25 @@ def cpu_sample_text(frames):
 
 
 # --------------------------------------------------------------------------------------------------- extra blocks (all ranks)
+def ckpt_17b_dir():
+    return os.path.join(os.environ.get("Q3TTS_TEST_CKPT", "/tmp/q3tts_test_ckpt"), f"1.7b-cv_b0_bf16_s0_init{INIT}_enc")
+
+
+def write_ckpt_17b(checkpoint):
+    """ONE synthetic 1.7B checkpoint for configs 3 and 5: bf16, BASELINE init, `tts_model_type` custom_voice, with the ICL reference-audio encoder
+    and the ECAPA speaker encoder (config 3 ignores the last three)."""
+    return checkpoint.write_checkpoint(ckpt_17b_dir(), "1.7b-cv", bits=0, dtype="bf16", seed=0, init=INIT, encoder="full", speaker_encoder="full")
+
+
 def run_config3(q, checkpoint, dist, a, rank, local_rank, world):
     """BASELINE.json configs[2]: 1.7B bf16, 512 synthetic utterances (ids 20-60 long, seed 2), 125 frames each, request-parallel."""
     import torch
 
     from qwen3tts_b200 import parallel
 
-    d = ckpt_path("1.7b", 0)
+    d = ckpt_17b_dir()
     if rank == 0:
-        checkpoint.write_checkpoint(d, "1.7b", bits=0, dtype="bf16", seed=0, init=INIT)
+        write_ckpt_17b(checkpoint)
     if world > 1:
         dist.barrier()
     total, frames, B = a.config3_utterances, 125, 64
@@ -232,8 +242,7 @@ def run_config5(q, checkpoint, a, local_rank):
     bf16 checkpoint ON).  Random weights never emit EOS, so every text chunk runs its 600 frames (48 s of audio)."""
     import tempfile
 
-    d = os.path.join(os.environ.get("Q3TTS_TEST_CKPT", "/tmp/q3tts_test_ckpt"), f"1.7b-cv_b0_bf16_s0_init{INIT}_enc")
-    checkpoint.write_checkpoint(d, "1.7b-cv", bits=0, dtype="bf16", seed=0, init=INIT, encoder="full", speaker_encoder="full")
+    d = write_ckpt_17b(checkpoint)
     t0 = time.perf_counter()
     p = q.Qwen3TTSPipeline(d, q.Qwen3TTSPipelineConfiguration(device=local_rank, max_batch=32))
     load_s = time.perf_counter() - t0
