@@ -16,12 +16,14 @@
 
 using namespace q3;
 
+struct q3tts_handle : q3::Handle {};
+
 namespace q3 {
 void init_talker_kernels();
 Handle::~Handle() {
-  for (Handle* l : lanes) {
+  for (Handle* l : lanes) {  // clones made for q3tts_options.lanes (allocated as q3tts_handle)
     cudaStreamSynchronize(l->stream);
-    delete l;
+    delete static_cast<q3tts_handle*>(l);
   }
   lanes.clear();
   talker.reset();
@@ -38,7 +40,6 @@ Handle::~Handle() {
 }
 }  // namespace q3
 
-struct q3tts_handle : q3::Handle {};
 
 namespace {
 
