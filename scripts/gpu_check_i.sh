@@ -1,17 +1,14 @@
 #!/bin/bash
-# full validation: every GPU test, smoke(), the default bench line (all extras), the reference arm
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2c_full_tests.log 2>&1; tail -3 gpurun_out/r2c_full_tests.log
-timeout 600 python __graft_entry__.py smoke > gpurun_out/r2c_smoke.log 2>&1; tail -1 gpurun_out/r2c_smoke.log
-timeout 1500 python bench.py > gpurun_out/r2c_bench_full.json 2> gpurun_out/r2c_bench_full.err; tail -2 gpurun_out/r2c_bench_full.err
-timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2c_bench_ref.json 2> gpurun_out/r2c_bench_ref.err
+for H in 4 8; do
+Q3TTS_PDL=0 timeout 1500 python bench.py --no-extras 2>/dev/null | python -c "
+import json,sys
+j = json.loads(sys.stdin.read().strip().splitlines()[-1]); print('PDL=0 headline', j['value'], j['e2e']['value'])
+" 
+Q3TTS_PDL=0 timeout 1500 python bench.py --no-cpu-baseline --config4 off --config5 off --config3-handles $H > gpurun_out/r2c_c3_nopdl_l$H.json 2> gpurun_out/r2c_c3_nopdl_l$H.err; tail -2 gpurun_out/r2c_c3_nopdl_l$H.err
 python -c "
 import json
-j = json.loads(open('gpurun_out/r2c_bench_full.json').read().strip().splitlines()[-1])
-print('value', j['value'], 'e2e', j['e2e']['value'], 'roof', j['roofline']['frac'], 'launches', j['gpu_launches'])
-print('inflight', j['batches_in_flight']['e2e_value']); print('c3', j['config3']['value'], j['config3']['e2e'])
-print('c4', j['config4']['chunked']['samples_per_s'], j['config4']['whole']['samples_per_s'])
-print('c5', j['config5']['custom_voice']['value'], j['config5']['icl_clone']['value'], j['config5']['encode_reference_audio'], j['config5']['extract_speaker_embedding'])
-print('cpu', j['cpu_baseline']['value'], j['cpu_baseline']['cores'])
-r = json.loads(open('gpurun_out/r2c_bench_ref.json').read().strip().splitlines()[-1]); print('ref', r['value'])
+j = json.loads(open('gpurun_out/r2c_c3_nopdl_l$H.json').read().strip().splitlines()[-1])
+c = j['config3']; print('PDL=0 lanes', c['lanes_per_gpu'], 'value', c['value'], 'e2e', c['e2e'], 'inflight', j['batches_in_flight']['e2e_value'])
 "
+done
