@@ -613,6 +613,10 @@ int32_t q3tts_speaker_id(const q3tts_handle* h, const char* name) {
 }
 
 q3tts_status q3tts_clear_cache(q3tts_handle* h) {
+  if (h) {  // the lanes of q3tts_options.lanes first (each under its own mutex)
+    std::lock_guard<std::mutex> lk(h->lanes_mu);
+    for (q3::Handle* l : h->lanes) q3tts_clear_cache(static_cast<q3tts_handle*>(l));
+  }
   return guarded(h, [&] {
     Q3_CUDA(cudaStreamSynchronize(h->stream));
     if (h->talker) h->talker->drop_graphs();
