@@ -31,6 +31,10 @@ constexpr int kMaxThreads = 448;   // ... up to three sets (persistent schedule)
 // Ring position as counters that wrap (stage, parity of the round) instead of `it % stages` / `(it / stages) & 1`: a runtime integer
 // division is ~35 dependent instructions, and one or two per k-block in the single MMA-issuing (or TMA-issuing) thread cost more than
 // the four MMAs of the k-block (measured in codec_unit.cu: the issuing thread, not memory or the tensor pipe, set the stage time).
+__device__ __forceinline__ int fast_div(int x, unsigned mul, unsigned shift) {
+  return (int)((__umulhi((unsigned)x, mul) + (unsigned)x) >> shift);
+}
+
 struct TcRing {
   int s = 0, n;
   uint32_t ph = 0;
@@ -61,6 +65,9 @@ struct TcParams {
   // per CTA (gridDim.x == tiles) is the classic launch; with fewer CTAs than tiles the kernel is PERSISTENT: the TMA ring runs on
   // across tile boundaries and two TMEM accumulators (n_acc = 2) let the epilogue of tile i overlap the MMAs of tile i + 1.
   int tiles_m, tiles_n, n_acc, acc_cols;
+  // division by tiles_n / tiles_per_batch without the ~35-instruction software divide (every epilogue thread decomposes its tile index
+  // once per tile: 5.8 % of a thin vocoder launch's instructions): q = (umulhi(x, mul) + x) >> shift, exact for x < 2^31
+  unsigned div_n_mul, div_n_shift, div_b_mul, div_b_shift;
   const __half* res16;
   __half* outr16;
   int epi_sets;  // sets of 4 epilogue warps; set e handles the 32-column chunks e, e + epi_sets, ... of every tile
@@ -110,10 +117,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // thread needs the same 32 values per chunk -- as global loads they were 24 of the 32 load instructions of a chunk.  One
   // column tile per kernel (tiles_n == 1: every thin vocoder layer) so the table is filled once; static parameters, no
   // dependency on the predecessor kernel.
-  __shared__ __align__(16) float s_bias[256], s_ea[256], s_ieb[256];
-  const bool tab = p.tiles_n == 1 && !p.swiglu;
+  // Round 2b: the table holds ALL N columns (index = absolute column) when N <= 768, so layers of several column tiles (the 1x1 and
+  // transposed convolutions at N = 288 / 384 / 768) use it too -- on the global-load path their epilogues stalled on the constants in
+  // front of every sine (ncu source view: 18 % of the stall samples on that line, another 10 % of the instructions in modulo / index code).
+  constexpr int kTabMax = 768;  // 9 KB static: two 100-KB-ring CTAs still share an SM
+  __shared__ __align__(16) float s_bias[kTabMax], s_ea[kTabMax], s_ieb[kTabMax];
+  const bool tab = p.tiles_n * p.bn <= kTabMax && !p.swiglu;
   if (tab) {
-    for (int cidx = threadIdx.x; cidx < p.bn; cidx += blockDim.x) {
+    for (int cidx = threadIdx.x; cidx < p.tiles_n * p.bn; cidx += blockDim.x) {
       const bool in = cidx < p.N;
       s_bias[cidx] = (p.bias && in) ? p.bias[cidx] : 0.f;
       if (p.snake_ea) {
@@ -155,8 +166,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         TcRing ra(a_st), rb(b_st);  // activation / weight rings
         bool waited = false;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-          const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
-          const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
+          const int m_tile = fast_div(tile, p.div_n_mul, p.div_n_shift), n_tile = tile - m_tile * p.tiles_n;
+          const int bidx = fast_div(m_tile, p.div_b_mul, p.div_b_shift), t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
           for (int kc = 0; kc < p.kb_per_tap; ++kc) {
             auto issue_b = [&](int tap) {
               if (rb.wrapped) mbar_wait(&b_empty[rb.s], rb.ph ^ 1u);
@@ -209,8 +220,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       };
       for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
-        const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
-        const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
+        const int m_tile = fast_div(tile, p.div_n_mul, p.div_n_shift), n_tile = tile - m_tile * p.tiles_n;
+        const int bidx = fast_div(m_tile, p.div_b_mul, p.div_b_shift), t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
         const int rot = p.k_rotate ? (int)(((unsigned)n_tile * 5u + (unsigned)m_tile * 3u) % (unsigned)num_kb) : 0;
         if (p.res_stages && ti > 0 && rt < (1 << 30)) {
           issue_residuals(ti, true);
@@ -312,8 +323,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t patch = smem_u32(patches + (size_t)(warp - 2) * epiio::kPatchBytes);
     pdl_wait();  // residual / bias-free inputs of the epilogue were written by earlier kernels
     for (int tile = blockIdx.x, ti = 0; tile < total_tiles; tile += gridDim.x, ++ti) {
-    const int m_tile = tile / p.tiles_n, n_tile = tile - m_tile * p.tiles_n;
-    const int bidx = m_tile / p.tiles_per_batch, t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
+    const int m_tile = fast_div(tile, p.div_n_mul, p.div_n_shift), n_tile = tile - m_tile * p.tiles_n;
+    const int bidx = fast_div(m_tile, p.div_b_mul, p.div_b_shift), t0 = (m_tile - bidx * p.tiles_per_batch) * kTileM, n0 = n_tile * p.bn;
     const int acc_i = p.n_acc == 2 ? (ti & 1) : 0, use = p.n_acc == 2 ? (ti >> 1) : ti;
     const uint32_t acc = tmem_base + (uint32_t)(acc_i * p.acc_cols);
     const int t = t0 + row;
@@ -377,7 +388,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (p.bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 b4 = tab ? *reinterpret_cast<const float4*>(s_bias + c + j) : *reinterpret_cast<const float4*>(p.bias + nb + j);
+          const float4 b4 = tab ? *reinterpret_cast<const float4*>(s_bias + nb + j) : *reinterpret_cast<const float4*>(p.bias + nb + j);
           v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
         }
       }
@@ -464,7 +475,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               int c = ch0 + j;
               while (!tab && c >= p.snake_ch) c -= p.snake_ch;
               float ea[4], ib[4];
-              if (tab) {  // column ob + j of the tile (n0 == 0): shared-memory table
+              if (tab) {  // absolute column ob + j: shared-memory table
                 const float4 a4 = *reinterpret_cast<const float4*>(s_ea + ob + j), b4 = *reinterpret_cast<const float4*>(s_ieb + ob + j);
                 ea[0] = a4.x; ea[1] = a4.y; ea[2] = a4.z; ea[3] = a4.w;
                 ib[0] = b4.x; ib[1] = b4.y; ib[2] = b4.z; ib[3] = b4.w;
@@ -583,7 +594,7 @@ bool tc_gemm_supported(const TcGemm& g) {
 
 void init_tc_gemm() {
   tc_resolve_encode();
-  Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+  Q3_CUDA(cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024));  // + 9 KB static (epilogue tables) + 1 KB reserved <= 227 KB
   init_tc_skinny();
 }
 
@@ -600,6 +611,14 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
   const int stage_bytes = kABytes + p.bn * kBlockK * 2;
   p.tiles_m = g.Bt * p.tiles_per_batch;
   p.tiles_n = (g.N + p.bn - 1) / p.bn;
+  auto magic = [](unsigned d, unsigned& mul, unsigned& shift) {  // d >= 1
+    unsigned l = 0;
+    while ((1ull << l) < d) ++l;
+    mul = (unsigned)(((1ull << 32) * ((1ull << l) - d)) / d + 1);
+    shift = l;
+  };
+  magic((unsigned)p.tiles_n, p.div_n_mul, p.div_n_shift);
+  magic((unsigned)p.tiles_per_batch, p.div_b_mul, p.div_b_shift);
   const long long tiles = (long long)p.tiles_m * p.tiles_n;
   int cols = 32;
   while (cols < p.bn) cols <<= 1;
@@ -681,7 +700,7 @@ void launch_tc_gemm(const LaunchCtx& c, const TcGemm& g) {
     Q3_CHECK(r == CUDA_SUCCESS, Q3TTS_ERR_CUDA, "cuTensorMapEncodeTiled (residual tiles) failed with CUresult %d", (int)r);
   }
   const size_t smem = (size_t)ring_bytes + (size_t)p.res_stages * p.res_bytes + 1024 + 64 * 8 + (size_t)tio_bytes;
-  Q3_CHECK(smem <= 220 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
+  Q3_CHECK(smem <= 212 * 1024, Q3TTS_ERR_CAPACITY, "tc_gemm: shared memory request %zu too large", smem);
   Q3_CHECK(2 * (p.halo ? p.a_stages + p.b_stages : p.stages) + 5 + 2 * p.res_stages <= 64, Q3TTS_ERR_CAPACITY, "tc_gemm: too many ring stages");
   dim3 grid((unsigned)(persistent ? std::min<long long>(tiles, resident) : tiles));
   launch_kernel_pdl(tc_gemm_kernel, grid, dim3(64 + 128 * p.epi_sets), smem, c.stream, pdl_enabled(), ma, mb, mr, p);

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/r2c_short_plain.json 2> gpurun_out/r2c_short_plain.err && \
-timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/r2c_launches_bench_short.csv python bench.py --steps 2 --warmup 1 --no-extras > gpurun_out/r2c_short_ncu.out 2>&1
-tail -1 gpurun_out/r2c_short_plain.json | cut -c1-200
-timeout 300 python scripts/codec_probe.py 64 26 1 > /dev/null 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2c_launches_codec.csv python scripts/codec_probe.py 64 26 1 > gpurun_out/r2c_codec_ncu.out 2>&1
-wc -l gpurun_out/r2c_launches_bench_short.csv gpurun_out/r2c_launches_codec.csv
+B=$PWD/mlx-swift-qwen3-tts_b200/qwen3tts_b200/libq3_base.so
+timeout 900 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_fullsize.py -x -q -m gpu -k "tc_ or snr" 2>&1 | tail -2
+for r in 1 2; do
+echo "base: $(Q3TTS_LIB=$B timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1 | cut -c1-120)"
+echo "new : $(timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1 | cut -c1-120)"
+done
