@@ -293,10 +293,142 @@ void launch_codec_attention_bidir(const LaunchCtx& c, const float* qkv, int ld, 
   codec_attention_kernel<float><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 0);
   c.tick();
 }
+// The same attention on tensor cores (mma.sync m16n8k16, fp16 operands, fp32 accumulate and softmax): the codec transformer's windows
+// are 18-750 frames of 16 heads x 64 dims -- a tile problem far too small for tcgen05 (a 128-row UMMA tile would be 80 % padding at
+// T = 26) but 3 000 shared-memory loads per CTA as a SIMT loop (52 us per layer at 64 x 26 frames, LDS-bound).  One warp owns 16 query
+// rows: Q fragments live in registers, K and V^T tiles of 64 keys are staged in shared memory as fp16 (row pitch 72 halves: the
+// fragment loads of the 8 x 4 lane grid hit 32 different banks), S = Q.K^T -> online softmax in registers -> the probabilities ARE the A
+// fragments of P.V (accumulator layout of one m16n8 tile = half an A fragment of the next MMA).  Operands are rounded to fp16 once
+// (q, k after RoPE, v, p): the same rounding every other contraction of this pipeline applies.
+__device__ __forceinline__ uint32_t att_pack(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void att_mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__global__ void __launch_bounds__(128) codec_attention_mma_kernel(const float* __restrict__ qkv, int ld, int T, int nh, int nkv, float scale,
+                                                                  __half* __restrict__ out, int ldo, int causal) {
+  constexpr int KT = 64, PITCH = 72;
+  __shared__ __align__(16) __half Ks[KT][PITCH];   // [key][dim]
+  __shared__ __align__(16) __half Vt[64][PITCH];   // [dim][key]
+  const int h = blockIdx.y, b = blockIdx.z, kvh = h / (nh / nkv);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int r0 = blockIdx.x * 64 + warp * 16;  // this warp's first query row
+  const float* base = qkv + (size_t)b * T * ld;
+  const int koff = nh * 64 + kvh * 64, voff = nh * 64 + nkv * 64 + kvh * 64;
+  // Q fragments: rows r0 + g and r0 + g + 8, 4 k-steps of 16 dims
+  uint32_t qa[4][4];
+  {
+    const int ra = r0 + g, rb = r0 + g + 8;
+    const float* qra = base + (size_t)(ra < T ? ra : 0) * ld + h * 64;
+    const float* qrb = base + (size_t)(rb < T ? rb : 0) * ld + h * 64;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float2 a_lo = *reinterpret_cast<const float2*>(qra + ks * 16 + 2 * t), a_hi = *reinterpret_cast<const float2*>(qra + ks * 16 + 8 + 2 * t);
+      const float2 b_lo = *reinterpret_cast<const float2*>(qrb + ks * 16 + 2 * t), b_hi = *reinterpret_cast<const float2*>(qrb + ks * 16 + 8 + 2 * t);
+      qa[ks][0] = att_pack(a_lo.x, a_lo.y); qa[ks][1] = att_pack(b_lo.x, b_lo.y);
+      qa[ks][2] = att_pack(a_hi.x, a_hi.y); qa[ks][3] = att_pack(b_hi.x, b_hi.y);
+    }
+  }
+  float o[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m_a = -INFINITY, m_b = -INFINITY, l_a = 0.f, l_b = 0.f;  // rows r0 + g / r0 + g + 8
+  const int cta_last = causal ? min(T, (int)blockIdx.x * 64 + 64) : T;   // keys any warp of this CTA needs
+  const int my_last = causal ? min(T, r0 + 16) : T;                      // keys THIS warp needs (uniform per warp)
+  for (int kt = 0; kt < cta_last; kt += KT) {
+    __syncthreads();
+    for (int i = tid; i < KT * 16; i += 128) {  // 64 keys x 16 float4 of K and of V
+      const int r = i >> 4, d = (i & 15) * 4;
+      float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+      if (kt + r < T) {
+        kv = *reinterpret_cast<const float4*>(base + (size_t)(kt + r) * ld + koff + d);
+        vv = *reinterpret_cast<const float4*>(base + (size_t)(kt + r) * ld + voff + d);
+      }
+      *reinterpret_cast<uint2*>(&Ks[r][d]) = make_uint2(att_pack(kv.x, kv.y), att_pack(kv.z, kv.w));
+      Vt[d][r] = __float2half_rn(vv.x); Vt[d + 1][r] = __float2half_rn(vv.y); Vt[d + 2][r] = __float2half_rn(vv.z); Vt[d + 3][r] = __float2half_rn(vv.w);
+    }
+    __syncthreads();
+    if (kt >= my_last || r0 >= T) continue;  // warp-uniform: nothing of this tile is visible to this warp's rows
+    // S = Q . K^T for 64 keys: 8 n-tiles of 8 keys
+    float sc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      sc[n][0] = sc[n][1] = sc[n][2] = sc[n][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Ks[n * 8 + g][ks * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Ks[n * 8 + g][ks * 16 + 8 + 2 * t]);
+        att_mma(sc[n], qa[ks][0], qa[ks][1], qa[ks][2], qa[ks][3], b0, b1);
+      }
+    }
+    // mask + scale; row maxima
+    const int ra = r0 + g, rb = r0 + g + 8;
+    float mx_a = -INFINITY, mx_b = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = kt + n * 8 + 2 * t + e;
+        const bool in = j < T;
+        sc[n][e] = (in && (!causal || j <= ra)) ? sc[n][e] * scale : -INFINITY;
+        sc[n][2 + e] = (in && (!causal || j <= rb)) ? sc[n][2 + e] * scale : -INFINITY;
+        mx_a = fmaxf(mx_a, sc[n][e]); mx_b = fmaxf(mx_b, sc[n][2 + e]);
+      }
+    }
+    mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 1)); mx_a = fmaxf(mx_a, __shfl_xor_sync(0xffffffffu, mx_a, 2));
+    mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 1)); mx_b = fmaxf(mx_b, __shfl_xor_sync(0xffffffffu, mx_b, 2));
+    const float mn_a = fmaxf(m_a, mx_a), mn_b = fmaxf(m_b, mx_b);
+    // a row with nothing visible yet keeps m = -inf: use 0 as the reference so exp(-inf - 0) = 0 (no NaN)
+    const float ref_a = mn_a == -INFINITY ? 0.f : mn_a, ref_b = mn_b == -INFINITY ? 0.f : mn_b;
+    const float corr_a = m_a == -INFINITY ? 0.f : __expf(m_a - ref_a), corr_b = m_b == -INFINITY ? 0.f : __expf(m_b - ref_b);
+    float sum_a = 0.f, sum_b = 0.f;
+    uint32_t pa[4][4];  // P as A fragments: k-step kk = keys 16 kk .. 16 kk + 15 = n-tiles 2 kk, 2 kk + 1
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const float p0 = __expf(sc[n][0] - ref_a), p1 = __expf(sc[n][1] - ref_a), p2 = __expf(sc[n][2] - ref_b), p3 = __expf(sc[n][3] - ref_b);
+      sum_a += p0 + p1; sum_b += p2 + p3;
+      pa[n >> 1][(n & 1) * 2] = att_pack(p0, p1);
+      pa[n >> 1][(n & 1) * 2 + 1] = att_pack(p2, p3);
+    }
+    sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 1); sum_a += __shfl_xor_sync(0xffffffffu, sum_a, 2);
+    sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 1); sum_b += __shfl_xor_sync(0xffffffffu, sum_b, 2);
+    l_a = l_a * corr_a + sum_a; l_b = l_b * corr_b + sum_b;
+    m_a = mn_a; m_b = mn_b;
+    // O = O * corr + P . V: 8 n-tiles of 8 dims, 4 k-steps of 16 keys
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      o[n][0] *= corr_a; o[n][1] *= corr_a; o[n][2] *= corr_b; o[n][3] *= corr_b;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[n * 8 + g][kk * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[n * 8 + g][kk * 16 + 8 + 2 * t]);
+        att_mma(o[n], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+      }
+    }
+  }
+  const int ra = r0 + g, rb = r0 + g + 8;
+  const float inv_a = l_a > 0.f ? 1.0f / l_a : 0.f, inv_b = l_b > 0.f ? 1.0f / l_b : 0.f;
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    if (ra < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + ra) * ldo + h * 64 + n * 8 + 2 * t) = att_pack(o[n][0] * inv_a, o[n][1] * inv_a);
+    if (rb < T) *reinterpret_cast<uint32_t*>(out + ((size_t)b * T + rb) * ldo + h * 64 + n * 8 + 2 * t) = att_pack(o[n][2] * inv_b, o[n][3] * inv_b);
+  }
+}
+
 void launch_codec_attention_f16(const LaunchCtx& c, const float* qkv, int ld, int B, int T, int nh, int nkv, __half* out, int ldo) {
   if (B <= 0 || T <= 0) return;
-  dim3 grid((T + 15) / 16, nh, B);
-  codec_attention_kernel<__half><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 1);
+  static const bool mma = !(getenv("Q3TTS_CODEC_ATT_MMA") && atoi(getenv("Q3TTS_CODEC_ATT_MMA")) == 0);
+  if (mma && ld % 4 == 0 && ldo % 2 == 0) {
+    dim3 grid((T + 63) / 64, nh, B);
+    codec_attention_mma_kernel<<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 1);
+  } else {
+    dim3 grid((T + 15) / 16, nh, B);
+    codec_attention_kernel<__half><<<grid, 128, 0, c.stream>>>(qkv, ld, T, nh, nkv, 1.0f / sqrtf(64.0f), out, ldo, 1);
+  }
   c.tick();
 }
 
