@@ -1,8 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-B=$PWD/mlx-swift-qwen3-tts_b200/qwen3tts_b200/libq3_base.so
-timeout 900 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_fullsize.py -x -q -m gpu -k "tc_ or snr" 2>&1 | tail -2
-for r in 1 2; do
-echo "base: $(Q3TTS_LIB=$B timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1 | cut -c1-120)"
-echo "new : $(timeout 300 python scripts/codec_probe.py 64 26 3 2>&1 | tail -1 | cut -c1-120)"
-done
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/r2e_bench_n2.json 2> gpurun_out/r2e_bench_n2.err; tail -2 gpurun_out/r2e_bench_n2.err
+python -c "
+import json
+j = json.loads(open('gpurun_out/r2e_bench_n2.json').read().strip().splitlines()[-1])
+print('N=2 value', j['value'], 'e2e', j['e2e']['value'], 'n_gpus', j['n_gpus'])
+print(json.dumps({k: v for k, v in j['config3'].items() if k != 'workload'}))
+print(json.dumps({k: v for k, v in j['config4'].items() if k != 'workload'}))
+print('c5', j['config5'])
+"
