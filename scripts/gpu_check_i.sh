@@ -1,10 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 4 > gpurun_out/r2e_bench_n4.json 2> gpurun_out/r2e_bench_n4.err; tail -2 gpurun_out/r2e_bench_n4.err
-python -c "
-import json
-j = json.loads(open('gpurun_out/r2e_bench_n4.json').read().strip().splitlines()[-1])
-print('N=4 value', j['value'], 'e2e', j['e2e']['value'], 'n_gpus', j['n_gpus'])
-print('c3', j['config3']['value'], j['config3']['e2e'], j['config3']['result_gather']['seconds'])
-print('c4', j['config4']['chunked']['samples_per_s'], j['config4']['whole']['samples_per_s'])
-"
+timeout 300 python scripts/codec_probe.py 64 26 1 > /dev/null 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"codec_attention_mma_kernel|out_conv_stream_kernel" --launch-skip 7 --launch-count 2 -o gpurun_out/r2e_codec_small -f python scripts/codec_probe.py 64 26 1 > gpurun_out/r2e_ncu_small.log 2>&1; tail -2 gpurun_out/r2e_ncu_small.log
+timeout 900 ncu --set full --clock-control none -k regex:"codec_attention_mma_kernel" --launch-skip 7 --launch-count 1 -o gpurun_out/r2e_codec_att750 -f python scripts/codec_probe.py 8 750 1 > gpurun_out/r2e_ncu_att750.log 2>&1; tail -1 gpurun_out/r2e_ncu_att750.log
