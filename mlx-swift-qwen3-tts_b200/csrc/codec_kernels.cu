@@ -545,9 +545,9 @@ __global__ void __launch_bounds__(128) out_conv_stream_kernel(const __half* __re
   for (int j = 0; j < 7; ++j) acc[j] = 0.f;
   float keep = 0.f;
   const int r0 = t0 - 6 > 0 ? t0 - 6 : 0;  // rows before 0 are the causal zero padding
-  // rows in chunks of 8, the next chunk's loads issued before the current chunk's arithmetic: 16 rows x 64 B per load in flight per warp
+  // rows in chunks of 7, the next chunk's loads issued before the current chunk's arithmetic: 14 rows x 64 B per load in flight per warp
   // (a row-at-a-time loop leaves one row in flight: the shuffles and the guarded store keep the compiler from hoisting the loads)
-  constexpr int R = 8;
+  constexpr int R = 7;  // = the window depth: after unrolling, the rotation of the 7 partial sums is a renaming, not 6 moves per row
   __half cur[R][CPL], nxt[R][CPL];
   auto fetch = [&](__half (&dst)[R][CPL], int r) {
 #pragma unroll
