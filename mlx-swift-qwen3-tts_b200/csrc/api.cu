@@ -687,6 +687,7 @@ static q3tts_status over_lanes(q3tts_handle* h, int32_t n, F&& run) {
   const int B = h->opt.max_batch;
   const int blocks = (n + B - 1) / B;
   const int L = std::min(h->opt.lanes, blocks);
+  std::vector<q3::Handle*> lanes;
   {  // clones are created on the first call that needs them
     std::lock_guard<std::mutex> lk(h->lanes_mu);
     while ((int)h->lanes.size() < L - 1) {
@@ -699,6 +700,7 @@ static q3tts_status over_lanes(q3tts_handle* h, int32_t n, F&& run) {
       }
       h->lanes.push_back(c);
     }
+    lanes.assign(h->lanes.begin(), h->lanes.begin() + (L - 1));  // a private copy: another call on this handle may grow the vector meanwhile
   }
   // contiguous shares in whole blocks of max_batch requests (the last lane takes the remainder)
   std::vector<int> off(L + 1, 0);
@@ -707,14 +709,14 @@ static q3tts_status over_lanes(q3tts_handle* h, int32_t n, F&& run) {
   std::vector<q3tts_status> st(L, Q3TTS_OK);
   std::vector<std::thread> workers;
   for (int l = 1; l < L; ++l)
-    workers.emplace_back([&, l] { st[l] = run(static_cast<q3tts_handle*>(h->lanes[l - 1]), off[l], off[l + 1] - off[l]); });
+    workers.emplace_back([&, l] { st[l] = run(static_cast<q3tts_handle*>(lanes[l - 1]), off[l], off[l + 1] - off[l]); });
   st[0] = run(h, off[0], off[1] - off[0]);
   for (auto& w : workers) w.join();
   // the call's timing: the lanes ran side by side -- times are the slowest lane's, counters add up
   std::lock_guard<std::mutex> lk(h->mu);
   q3tts_status result = st[0];
   for (int l = 1; l < L; ++l) {
-    q3::Handle* lane = h->lanes[l - 1];
+    q3::Handle* lane = lanes[l - 1];
     std::lock_guard<std::mutex> lk2(lane->mu);
     const q3tts_timing& t = lane->timing;
     q3tts_timing& a = h->timing;
