@@ -103,3 +103,35 @@ def test_checkpoint_keys_are_the_ones_the_reference_loader_reads():
     assert tuple(t["speaker_encoder.mfa.conv.weight"].shape) == (1536, 1536, 1)
     assert tuple(t["speaker_encoder.asp.tdnn.conv.weight"].shape) == (128, 4608, 1)
     assert tuple(t["speaker_encoder.fc.weight"].shape) == (1024, 3072, 1)
+
+
+def test_filterbank_against_an_independent_float64_slaney_construction():
+    """The published Slaney construction (librosa.filters.mel, htk=False, norm='slaney'), written independently in float64 with array
+    operations, against the oracle's scalar Float restatement of createMelFilterbankImpl (:75-146)."""
+    sr, n_fft, n_mels, fmin, fmax = 24000, 1024, 128, 0.0, 12000.0
+
+    def hz_to_mel(f):
+        f = np.asarray(f, dtype=np.float64)
+        f_sp = 200.0 / 3
+        mels = f / f_sp
+        min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+        min_log_mel = min_log_hz / f_sp
+        return np.where(f >= min_log_hz, min_log_mel + np.log(np.maximum(f, 1e-12) / min_log_hz) / logstep, mels)
+
+    def mel_to_hz(m):
+        m = np.asarray(m, dtype=np.float64)
+        f_sp = 200.0 / 3
+        min_log_hz, logstep = 1000.0, np.log(6.4) / 27.0
+        min_log_mel = min_log_hz / f_sp
+        return np.where(m >= min_log_mel, min_log_hz * np.exp(logstep * (m - min_log_mel)), f_sp * m)
+
+    fft_freqs = np.linspace(0, sr / 2, n_fft // 2 + 1)
+    mel_f = mel_to_hz(np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mels + 2))
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fft_freqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    weights = np.maximum(0, np.minimum(lower, upper)) * (2.0 / (mel_f[2:] - mel_f[:-2]))[:, None]  # [n_mels, n_freqs]
+    got = se.mel_filterbank()
+    assert got.shape == weights.T.shape
+    assert np.abs(got - weights.T).max() < 2e-6 * max(1.0, np.abs(weights).max())
