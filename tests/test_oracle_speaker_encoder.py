@@ -135,3 +135,58 @@ def test_filterbank_against_an_independent_float64_slaney_construction():
     got = se.mel_filterbank()
     assert got.shape == weights.T.shape
     assert np.abs(got - weights.T).max() < 2e-6 * max(1.0, np.abs(weights).max())
+
+
+def test_forward_against_torch_nn_modules_with_native_reflect_padding():
+    """The whole ECAPA-TDNN graph rebuilt from torch.nn layers (Conv1d with padding_mode='reflect' -- torch's own reflect padding and
+    dilation handling, nn.functional statistics) against the oracle's index-based restatement, float64."""
+    import torch.nn as nn
+
+    d = ckpt("tiny", 8, speaker_encoder="tiny")
+    orc = se.SpeakerEncoderOracle(d)
+    w = {k: v.double() for k, v in orc.w.items()}
+
+    def tdnn(prefix, k, dil):
+        wt = w[prefix + ".conv.weight"]
+        c = nn.Conv1d(wt.shape[1], wt.shape[0], k, dilation=dil, padding=(k - 1) * dil // 2, padding_mode="reflect" if k > 1 else "zeros").double()
+        with torch.no_grad():
+            c.weight.copy_(wt); c.bias.copy_(w[prefix + ".conv.bias"])
+        return nn.Sequential(c, nn.ReLU())
+
+    def conv1(prefix):
+        wt = w[prefix + ".weight"]
+        c = nn.Conv1d(wt.shape[1], wt.shape[0], 1).double()
+        with torch.no_grad():
+            c.weight.copy_(wt); c.bias.copy_(w[prefix + ".bias"])
+        return c
+
+    a = (np.random.default_rng(2).standard_normal(9000) * 0.1).astype(np.float32)
+    mels = se.mel_spectrogram(a)
+    x = torch.from_numpy(mels).double().T[None]  # [1, mel, T]
+    with torch.no_grad():
+        h = tdnn("blocks.0", se.KERNELS[0], se.DILATIONS[0])(x)
+        outs = []
+        for i in (1, 2, 3):
+            p = f"blocks.{i}"
+            r = h
+            y = tdnn(p + ".tdnn1", 1, 1)(h)
+            chunks = torch.chunk(y, se.SCALE, dim=1)
+            parts = [chunks[0]]
+            for j in range(1, se.SCALE):
+                inp = chunks[j] if j == 1 else chunks[j] + parts[-1]
+                parts.append(tdnn(f"{p}.res2net_block.blocks.{j - 1}", se.KERNELS[i], se.DILATIONS[i])(inp))
+            y = tdnn(p + ".tdnn2", 1, 1)(torch.cat(parts, 1))
+            s = torch.sigmoid(conv1(p + ".se_block.conv2")(torch.relu(conv1(p + ".se_block.conv1")(y.mean(2, keepdim=True)))))
+            h = y * s + r
+            outs.append(h)
+        m = tdnn("mfa", se.KERNELS[4], se.DILATIONS[4])(torch.cat(outs, 1))
+        T = m.shape[2]
+        mean = m.mean(2, keepdim=True)
+        std = torch.sqrt(m.var(2, keepdim=True, unbiased=False) + se.EPS)
+        att = torch.tanh(tdnn("asp.tdnn", 1, 1)(torch.cat([m, mean.expand(-1, -1, T), std.expand(-1, -1, T)], 1)))
+        att = torch.softmax(conv1("asp.conv")(att), dim=2)
+        wm = (att * m).sum(2, keepdim=True)
+        ws = torch.sqrt(torch.clamp((att * (m - wm) ** 2).sum(2, keepdim=True), min=se.EPS))
+        want = conv1("fc")(torch.cat([wm, ws], 1))[0, :, 0].numpy()
+    got = orc.forward(mels)
+    assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
