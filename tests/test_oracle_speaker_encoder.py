@@ -190,3 +190,32 @@ def test_forward_against_torch_nn_modules_with_native_reflect_padding():
         want = conv1("fc")(torch.cat([wm, ws], 1))[0, :, 0].numpy()
     got = orc.forward(mels)
     assert np.abs(got - want).max() < 1e-4 * max(1.0, np.abs(want).max())
+
+
+def test_forward_equals_hf_ecapa_time_delay_net():
+    """Third-party anchor: HuggingFace transformers ships the same ECAPA-TDNN (Qwen2.5-Omni's speaker encoder, `ECAPA_TimeDelayNet` with
+    TimeDelayNetBlock / Res2NetBlock / SqueezeExcitationRes2NetBlock / AttentiveStatisticsPooling -- the very class names the reference
+    restates in SpeakerEncoder/SpeakerEncoder.swift:234-524).  Same `speaker_encoder.*` weights in, same embedding out."""
+    pytest.importorskip("transformers")
+    hq = pytest.importorskip("transformers.models.qwen2_5_omni.modeling_qwen2_5_omni")
+    from transformers.models.qwen2_5_omni.configuration_qwen2_5_omni import Qwen2_5OmniDiTConfig
+
+    d = ckpt("tiny", 8, speaker_encoder="tiny")
+    orc = se.SpeakerEncoderOracle(d)
+    ch, mfa = orc.w["blocks.0.conv.weight"].shape[0], orc.w["mfa.conv.weight"].shape[0]
+    cfg = Qwen2_5OmniDiTConfig(mel_dim=128, enc_dim=orc.w["fc.weight"].shape[0], enc_channels=[ch, ch, ch, ch, mfa], enc_kernel_sizes=list(se.KERNELS),
+                               enc_dilations=list(se.DILATIONS), enc_res2net_scale=se.SCALE, enc_se_channels=orc.w["blocks.1.se_block.conv1.weight"].shape[0],
+                               enc_attention_channels=orc.w["asp.tdnn.conv.weight"].shape[0])
+    m = hq.ECAPA_TimeDelayNet(cfg).to(torch.float32).eval()
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k in sd:
+            assert k in orc.w, f"no oracle tensor for {k}"
+            sd[k].copy_(orc.w[k])
+    for L in (1024, 5000, 24000):
+        a = (np.random.default_rng(L).standard_normal(L) * 0.1).astype(np.float32)
+        mels = se.mel_spectrogram(a)
+        with torch.no_grad():
+            want = m(torch.from_numpy(mels)[None])[0].numpy()
+        got = orc.forward(mels)
+        assert np.abs(got - want).max() <= 1e-5 * max(1.0, np.abs(want).max()), L
