@@ -143,3 +143,40 @@ def test_codec_transformer_ignores_the_sliding_window_like_the_reference():
     assert torch.allclose(got, full, rtol=1e-5, atol=1e-5 * float(full.abs().max()))
     assert not torch.allclose(got[:, 80:], windowed[:, 80:], rtol=1e-3, atol=1e-3 * float(full.abs().max()))
     assert torch.allclose(got[:, :72], windowed[:, :72], rtol=1e-5, atol=1e-5 * float(full.abs().max()))  # the first 72 frames see no window
+
+
+def test_rvq_decode_equals_hf_mimi_split_quantizer():
+    """a16 / a17: codebook = embedding_sum / clip(cluster_usage, 1e-5) (AudioDecoder.swift:285-302) and SplitResidualVectorQuantizer.decode
+    (SpeechTokenizer.swift:492-692: gather-sum per chain in codebook order, 1x1 output projection without bias, first + rest) against HF Mimi's
+    split residual vector quantiser -- the gather-sums bit for bit, the projected sum to fp32 rounding."""
+    from transformers import MimiConfig
+    import transformers.models.mimi.modeling_mimi as hm
+
+    dec = oc.load_codec(ckpt("tiny", 8))
+    c = dec.c
+    D = dec.codebooks[0].shape[1]
+    out_dim = dec.w["decoder.quantizer.rvq_first.output_proj.weight"].shape[0]
+    n_sem = c.num_semantic_quantizers
+    cfg = MimiConfig(hidden_size=out_dim, codebook_size=c.codebook_size, codebook_dim=D, vector_quantization_hidden_dimension=D,
+                     num_quantizers=c.num_quantizers, num_semantic_quantizers=n_sem)
+    q = hm.MimiSplitResidualVectorQuantizer(cfg).eval()
+    with torch.no_grad():
+        for name, rvq, n in (("rvq_first", q.semantic_residual_vector_quantizer, n_sem), ("rvq_rest", q.acoustic_residual_vector_quantizer, c.num_quantizers - n_sem)):
+            for i in range(n):
+                p = f"decoder.quantizer.{name}.vq.layers.{i}._codebook"
+                cb = rvq.layers[i].codebook
+                cb.embed_sum.copy_(dec.w[p + ".embedding_sum"]); cb.cluster_usage.copy_(dec.w[p + ".cluster_usage"]); cb.initialized.fill_(1.0)
+                cb._embed = None
+            rvq.output_proj.weight.copy_(dec.w[f"decoder.quantizer.{name}.output_proj.weight"])
+        codes = torch.randint(0, c.codebook_size, (2, c.num_quantizers, 13), generator=torch.Generator().manual_seed(3))
+        # a dead codebook entry (usage 0 -> clipped to 1e-5) must behave the same on both sides
+        first, rest = dec.rvq_embed(codes)
+        hf_first = sum(q.semantic_residual_vector_quantizer.layers[i].codebook.decode(codes[:, i]) for i in range(n_sem))
+        hf_rest = torch.zeros_like(rest)
+        for i in range(c.num_quantizers - n_sem):
+            hf_rest = hf_rest + q.acoustic_residual_vector_quantizer.layers[i].codebook.decode(codes[:, n_sem + i])
+        assert torch.equal(first, hf_first + torch.zeros_like(first)) and torch.equal(rest, hf_rest)
+        want = q.decode(codes)
+        got = dec.quantizer_decode(codes)
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-6, atol=1e-6 * float(want.abs().max()))
