@@ -1,3 +1,4 @@
 #!/bin/bash
+# final state of the round: every GPU test
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_talker.py -x -q -m gpu -k "lanes or two_handles or trapped" 2>&1 | tail -2
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/r2f_full_tests.log 2>&1; tail -3 gpurun_out/r2f_full_tests.log
