@@ -23,7 +23,7 @@ and code-predictor stacks (max error 0.0, prefill and cached decode), Qwen3-Omni
 for SnakeBeta / causal convolutions / ConvNeXt / DecoderResidualUnit / the codec transformer, Mimi for
 the RVQ code-to-embedding path (bit for bit) and for the ICL encoder's SEANet CNN, downsampling conv and
 nearest-neighbour search (identical code ids), Qwen2.5-Omni's `ECAPA_TimeDelayNet` for the speaker
-encoder.  Where the REFERENCE deviates from those upstreams (transposed conv trims only its right side;
+encoder, and the Metal integration's `_affine_dequantize_tensor` for the MLX packed-weight layout.  Where the REFERENCE deviates from those upstreams (transposed conv trims only its right side;
 no sliding window in the codec transformer; zero-padded downsampling conv and bidirectional transformer
 in the ICL encoder) the oracle follows the reference and the tests state the deviation.  None of this is
 the reference itself: parity claims against the oracle stay "partial" by construction.

@@ -127,3 +127,32 @@ def test_runtime_bits_rule():
     four = ["layers.0.self_attn.o_proj", "layers.0.mlp.gate_proj", "layers.0.mlp.up_proj", "layers.0.mlp.down_proj", "text_projection.linear_fc1",
             "code_predictor.small_to_mtp_projection"]
     assert all(m.runtime_bits(p) == 6 for p in six) and all(m.runtime_bits(p) == 4 for p in four)
+
+
+@pytest.mark.parametrize("bits,group", [(4, 64), (8, 64), (4, 128), (8, 32)])
+def test_dequantize_layout_equals_hf_metal_affine(bits, group):
+    """Third-party statement of the MLX affine LAYOUT (Appendix C of SURVEY.md: uint32 words, element j of a word at bit offset j * bits, LSB
+    first; scales / biases per group along the input dimension; w = scale * q + bias): HuggingFace transformers' Metal integration dequantises
+    `quantization-mlx` checkpoints with `_affine_dequantize_tensor`.  Same packed words, scales and biases in -> same weights out, and its
+    packer produces the words `oracle.mlx_quant.pack` produces."""
+    import numpy as np
+    import torch
+
+    mq_hf = pytest.importorskip("transformers.integrations.metal_quantization")
+    from oracle import mlx_quant as mq
+
+    rng = np.random.default_rng(bits * 100 + group)
+    w = (rng.standard_normal((24, 256)) * 0.05).astype(np.float32)
+    packed, scales, biases = mq.quantize(w, group, bits, "f32")
+    mine = mq.dequantize(packed, scales, biases, group, bits, "f32")
+    s32 = torch.from_numpy(np.asarray(scales, dtype=np.float32)); b32 = torch.from_numpy(np.asarray(biases, dtype=np.float32))
+    theirs = mq_hf._affine_dequantize_tensor(torch.from_numpy(packed.view(np.int32)), s32, b32, group, bits).numpy()
+    assert np.array_equal(mine, theirs)
+    # the packer: HF quantises with a plain min/max rule (not MLX's edge-preserving one), so compare the PACKING of given codes
+    q = rng.integers(0, 1 << bits, size=(24, 256)).astype(np.uint32)
+    per = 32 // bits
+    hf_words = torch.zeros(24, 256 // per, dtype=torch.int32)
+    qi = torch.from_numpy(q.astype(np.int32))
+    for i in range(per):  # the loop of _affine_quantize_tensor
+        hf_words |= qi[:, i::per] << (bits * i)
+    assert np.array_equal(mq.pack(q, bits).view(np.int32), hf_words.numpy())
