@@ -123,6 +123,11 @@ def preset(name: str) -> tuple[TalkerDims, CodecDims]:
     if name == "codecfull":  # tiny talker + the full-size codec decoder (SpeechTokenizer.swift:42-74 defaults)
         t, _ = preset("tiny")
         return t, CodecDims()
+    if name == "tiny-cp":  # code predictor as wide as the talker (like the 0.6B model): no small_to_mtp_projection
+        t, c = preset("tiny")
+        t.code_predictor = CodePredictorDims(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, num_key_value_heads=1, head_dim=128,
+                                             intermediate_size=256)
+        return t, c
     if name == "tiny-mrope":
         t, c = preset("tiny")
         t.mrope_section = [24, 20, 20]

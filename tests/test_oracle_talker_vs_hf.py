@@ -81,3 +81,48 @@ def test_code_predictor_stack_equals_hf_qwen3():
             w1 = orc.linear(f"code_predictor.lm_head.{step}", o1.last_hidden_state[0])
             assert (l1 - w1).abs().max().item() <= 1e-5 * scale, f"pass {step}"
             past = o1.past_key_values
+
+
+def test_code_predictor_loop_equals_hf_qwen3_omni_code_predictor():
+    """The per-frame loop of the code predictor (Qwen3Talker.swift:501-523; Qwen3CodePredictor.swift:158-212): pass 0 = [talker hidden,
+    codec_embedding(code0)] -> lm_head[0]; pass g >= 1 = code_predictor.codec_embedding[g - 1](code_g) -> lm_head[g], KV cache growing by one.
+    HuggingFace's Qwen3-Omni talker code predictor implements the same multi-token-prediction loop with the SAME checkpoint key names
+    (`model.codec_embedding.{i}`, `lm_head.{i}`, `generation_steps`): drive both with the same greedy tokens, compare every pass's logits."""
+    hf = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    from transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe import Qwen3OmniMoeTalkerCodePredictorConfig
+
+    d = ckpt("tiny-cp", 0, "bf16")
+    orc = ot.TalkerOracle(d)
+    cp = orc.cfg.code_predictor
+    assert "code_predictor.small_to_mtp_projection.weight" not in orc.w and cp.hidden_size == orc.cfg.hidden_size
+    cfg = Qwen3OmniMoeTalkerCodePredictorConfig(vocab_size=cp.vocab_size, hidden_size=cp.hidden_size, intermediate_size=cp.intermediate_size,
+                                                num_hidden_layers=cp.num_hidden_layers, num_attention_heads=cp.num_attention_heads,
+                                                num_key_value_heads=cp.num_key_value_heads, head_dim=cp.head_dim, rms_norm_eps=cp.rms_norm_eps,
+                                                rope_theta=cp.rope_theta, num_code_groups=cp.num_code_groups, attn_implementation="eager")
+    m = hf.Qwen3OmniMoeTalkerCodePredictorModelForConditionalGeneration(cfg).to(torch.float32).eval()
+    sd = m.state_dict()
+    with torch.no_grad():
+        for k in sd:
+            src = "code_predictor." + (k[len("model."):] if k.startswith("model.") else k)
+            assert src in orc.w, f"no oracle tensor for {k}"
+            sd[k].copy_(orc.w[src])
+    g = torch.Generator().manual_seed(5)
+    hidden = torch.randn(1, orc.cfg.hidden_size, generator=g)  # the talker's last hidden state
+    code0 = 17
+    ce = orc.w["codec_embedding.weight"]
+    with torch.no_grad():
+        inp = torch.cat([hidden, ce[[code0]]], 0)
+        lg, cache = orc.cp_forward(inp, None, 0)
+        out = m(inputs_embeds=inp[None], use_cache=True)
+        scale = float(out.logits.abs().max())
+        assert (lg[-1] - out.logits[0, -1]).abs().max().item() <= 1e-5 * scale
+        tok = int(torch.argmax(lg[-1]))
+        past, steps = out.past_key_values, out.generation_steps
+        for gi in range(1, cp.num_code_groups - 1):
+            assert steps == gi
+            mine_in = orc.w[f"code_predictor.codec_embedding.{gi - 1}.weight"][[tok]]
+            lg, cache = orc.cp_forward(mine_in, cache, gi)
+            out = m(input_ids=torch.tensor([[tok]]), past_key_values=past, use_cache=True, generation_steps=steps)
+            assert (lg[-1] - out.logits[0, -1]).abs().max().item() <= 1e-5 * scale, f"pass {gi}"
+            tok = int(torch.argmax(lg[-1]))
+            past, steps = out.past_key_values, out.generation_steps
