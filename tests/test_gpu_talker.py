@@ -740,3 +740,17 @@ def test_lanes_option_one_call_equals_single_lane(tiny8):
     for i in range(3):
         assert np.array_equal(small[i], want[i])
     eng.close()
+
+
+@pytest.mark.parametrize("max_batch", [1, 4])
+def test_no_projection_code_predictor_at_tiny_size(max_batch, engines, oracles):
+    """The 0.6B layout at CPU-test size: the code predictor as wide as the talker, so there is no small_to_mtp_projection and the sampler's rows
+    enter the predictor's stack directly (Qwen3CodePredictor.swift:171-185) -- on both numeric paths (persistent frame kernel, tensor-core step)."""
+    import qwen3tts_b200 as q
+    from oracle import talker as otalker
+
+    d = ckpt("tiny-cp", 8)
+    rec = {}
+    want = oracles(d).generate_codes(_oreq(otalker, speaker_id=2861, temperature=0.0, max_tokens=16), record=rec, filter_invalid=False)
+    got = engines(d, max_batch=max_batch).generate_codes(q.GenRequest(text_ids=TEXT_IDS, speaker_id=2861, temperature=0.0, max_tokens=16, keep_invalid_frames=True))
+    _compare_greedy(got.tolist(), want, rec["margins"])
