@@ -126,3 +126,22 @@ def test_code_predictor_loop_equals_hf_qwen3_omni_code_predictor():
             assert (lg[-1] - out.logits[0, -1]).abs().max().item() <= 1e-5 * scale, f"pass {gi}"
             tok = int(torch.argmax(lg[-1]))
             past, steps = out.past_key_values, out.generation_steps
+
+
+def test_interleaved_mrope_with_identical_streams_is_plain_rope():
+    """Quirk a7: the reference routes positions through "interleaved MRoPE" (Qwen3Layers.swift:60-92, a port of upstream's
+    `apply_interleaved_mrope`) whenever `rope_scaling.mrope_section` is present, but always feeds three IDENTICAL position streams (:77-79) --
+    which makes it plain 1-D RoPE.  HF's interleaved-MRoPE rotary embedding (Qwen3-Omni talker) on identical streams against the oracle's
+    plain cos / sin tables."""
+    hf = pytest.importorskip("transformers.models.qwen3_omni_moe.modeling_qwen3_omni_moe")
+    import transformers.models.qwen3_omni_moe.configuration_qwen3_omni_moe as hc
+
+    cfg = hc.Qwen3OmniMoeTalkerTextConfig(hidden_size=256, num_attention_heads=2, num_key_value_heads=1, head_dim=128,
+                                          rope_parameters={"rope_type": "default", "rope_theta": 1000000.0, "mrope_section": [24, 20, 20]})
+    rot = hf.Qwen3OmniMoeTalkerRotaryEmbedding(cfg)
+    pos = torch.arange(3, 230)[None]
+    cos, sin = rot(torch.zeros(1, pos.shape[1], 256), pos)  # a 2-D position tensor is expanded to three identical streams
+    inv = ot.TalkerOracle._inv_freq(1000000.0, 128)
+    fr = pos[0].float()[:, None] * inv[None, :]
+    emb = torch.cat([fr, fr], -1)
+    assert torch.equal(cos[0], emb.cos()) and torch.equal(sin[0], emb.sin())
